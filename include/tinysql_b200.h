@@ -1,0 +1,285 @@
+/*
+ * tinysql_b200.h — C-ABI of the B200-native vectorized execution path for TinySQL.
+ *
+ * This is the drop-in boundary: exactly the calls a cgo shim inside TinySQL's
+ * `executor`, `expression` and `util/chunk` packages would bind (see INTEGRATION.md
+ * for the Go side).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point returns an int32 status (TQ_OK == 0).  On failure a
+ * thread-local message is available through tq_last_error().  The library is
+ * re-entrant across handles; one handle must be driven by one thread at a time
+ * (the reference calls Next from a single goroutine per operator instance,
+ * executor/executor.go:155-162).
+ *
+ * Reference citations are relative to /root/reference (pingcap-incubator/tinysql).
+ */
+#ifndef TINYSQL_B200_H
+#define TINYSQL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+enum {
+  TQ_OK = 0,
+  TQ_ERR_INVALID_ARG = 1,
+  TQ_ERR_UNSUPPORTED_TYPE = 2,      /* "unsupport column type for encode" util/codec/codec.go:235,335 */
+  TQ_ERR_OVERFLOW_BIGINT = 3,       /* types.ErrOverflow "BIGINT"           expression/builtin_arithmetic_vec.go:489 */
+  TQ_ERR_OVERFLOW_BIGINT_UNSIGNED = 4, /* types.ErrOverflow "BIGINT UNSIGNED" builtin_arithmetic_vec.go:441 */
+  TQ_ERR_OVERFLOW_DOUBLE = 5,       /* types.ErrOverflow "DOUBLE"           builtin_arithmetic_vec.go:52 */
+  TQ_ERR_DIVISION_BY_ZERO = 6,      /* handleDivisionByZeroError in strict mode, builtin_arithmetic_vec.go:369-375 */
+  TQ_ERR_CUDA = 7,                  /* device fault / launch failure (generic internal error) */
+  TQ_ERR_NO_DEVICE = 8,             /* no usable sm_100 device: there is NO CPU fallback */
+  TQ_ERR_OOM = 9,
+  TQ_ERR_STATE = 10                 /* call out of protocol order (e.g. probe before finalize_build) */
+};
+
+/* ------------------------------------------------------------------ types  */
+/* util/chunk/codec.go:171-181: every SQL integer / DOUBLE is an 8-byte slot;
+ * signedness comes from mysql.UnsignedFlag on the FieldType. */
+enum {
+  TQ_TYPE_INT64 = 1,   /* TINY..LONGLONG, YEAR (signed)            */
+  TQ_TYPE_UINT64 = 2,  /* same, with mysql.UnsignedFlag            */
+  TQ_TYPE_FLOAT64 = 3, /* DOUBLE                                   */
+  TQ_TYPE_FLOAT32 = 4, /* FLOAT (4-byte slot)      — not yet accepted by the operators */
+  TQ_TYPE_BYTES = 5    /* var-len (offsets + data) — not yet accepted by the operators */
+};
+
+/* Where the buffers of a tq_column live. */
+enum {
+  TQ_MEM_HOST = 0,   /* ordinary or pinned host memory (the cgo path)                 */
+  TQ_MEM_DEVICE = 1  /* device memory on the library's device (bench / multi-GPU path) */
+};
+
+/* One chunk.Column exactly as Go holds it (util/chunk/column.go:28-34):
+ *   data        = length * 8 bytes, little-endian values (NULL slots are don't-care)
+ *   null_bitmap = ceil(length/8) bytes; bit (i&7) of byte (i>>3); 1 = NOT NULL.
+ *                 May be NULL meaning "no NULLs". High bits of the last byte are ignored.
+ * For outputs the caller provides both buffers (capacity >= the rows it asks for). */
+typedef struct tq_column {
+  int64_t length;
+  uint8_t *null_bitmap;
+  int64_t *offsets; /* var-len only; must be NULL for fixed-width columns */
+  uint8_t *data;
+} tq_column;
+
+/* ------------------------------------------------------------------ library */
+/* Select the CUDA device for this process (one process per GPU).  Fails with
+ * TQ_ERR_NO_DEVICE when no sm_100 GPU is visible. */
+int32_t tq_init(int32_t device_ordinal);
+int32_t tq_shutdown(void);
+/* Copies the calling thread's last error text (NUL-terminated) into buf. */
+int32_t tq_last_error(char *buf, int32_t buf_len);
+const char *tq_version(void);
+
+/* util/chunk bridge: page-locked host memory so chunk.Column buffers are DMA-able
+ * (SURVEY §8b "Ownership" option ii). */
+int32_t tq_pinned_alloc(size_t bytes, void **out);
+int32_t tq_pinned_free(void *p);
+
+/* Device memory helpers used by the benchmark / multi-GPU drivers. */
+int32_t tq_device_alloc(size_t bytes, void **out);
+int32_t tq_device_free(void *p);
+int32_t tq_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int32_t tq_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+int32_t tq_memset_device(void *dst_dev, int32_t byte_value, size_t bytes);
+int32_t tq_device_synchronize(void);
+
+/* Device-side timing on the library's compute stream (the stream every kernel of
+ * this library is launched on).  tq_timer_stop returns elapsed milliseconds. */
+int32_t tq_timer_start(void);
+int32_t tq_timer_stop(float *elapsed_ms);
+/* Number of kernels this library has launched since process start. */
+int64_t tq_kernel_launch_count(void);
+/* Writes `bytes` of a scratch buffer to evict L2 between timed iterations. */
+int32_t tq_flush_l2(void);
+
+/* ------------------------------------------------------- vectorized builtins
+ * Replaces expression.vecEvalInt / vecEvalReal of the builtin signatures
+ * (expression/builtin.go:256-263).  `n` rows; a/b/out are columns of n rows in
+ * memory space `mem`; `out` buffers are caller-allocated (data n*8 bytes,
+ * null_bitmap ceil(n/8) bytes).  The callee fills data and null bitmap (all bits
+ * beyond n in the last byte are written as 0).  Error statuses follow the
+ * reference: any non-NULL row overflowing fails the whole call. */
+
+enum { TQ_CMP_LT = 0, TQ_CMP_LE = 1, TQ_CMP_GT = 2, TQ_CMP_GE = 3, TQ_CMP_EQ = 4, TQ_CMP_NE = 5 };
+/* builtin{LT,LE,GT,GE,EQ,NE}IntSig.vecEvalInt — expression/builtin_compare_vec.go:22-292,
+ * types.VecCompare{II,UU,IU,UI} types/compare.go:44-100.  Result int64 0/1. */
+int32_t tq_vec_compare_int(int32_t op, int64_t n, const tq_column *a, int32_t a_unsigned,
+                           const tq_column *b, int32_t b_unsigned, tq_column *out, int32_t mem);
+/* builtin{LT..NE}RealSig.vecEvalInt — expression/builtin_compare_vec_generated.go:23-473. */
+int32_t tq_vec_compare_real(int32_t op, int64_t n, const tq_column *a, const tq_column *b,
+                            tq_column *out, int32_t mem);
+
+enum { TQ_ARITH_PLUS = 0, TQ_ARITH_MINUS = 1, TQ_ARITH_MUL = 2, TQ_ARITH_DIV = 3 };
+/* builtinArithmetic{Plus,Minus,Multiply}IntSig / MultiplyIntUnsignedSig.vecEvalInt —
+ * expression/builtin_arithmetic_vec.go:88-340,389-532.  MUL with both unsigned flags set
+ * is MultiplyIntUnsigned, otherwise MultiplyInt (signed check), as the planner picks. */
+int32_t tq_vec_arith_int(int32_t op, int64_t n, const tq_column *a, int32_t a_unsigned,
+                         const tq_column *b, int32_t b_unsigned, tq_column *out, int32_t mem);
+/* builtinArithmetic{Plus,Minus,Multiply,Divide}RealSig.vecEvalReal —
+ * builtin_arithmetic_vec.go:25-86,282-387.  Division by zero yields NULL and bumps
+ * *div_by_zero_warnings (may be NULL) — the non-strict-mode behaviour of
+ * handleDivisionByZeroError; the Go shim turns the count into warnings/errors. */
+int32_t tq_vec_arith_real(int32_t op, int64_t n, const tq_column *a, const tq_column *b,
+                          tq_column *out, int64_t *div_by_zero_warnings, int32_t mem);
+
+enum { TQ_LOGIC_AND = 0, TQ_LOGIC_OR = 1 };
+/* builtinLogic{And,Or}Sig.vecEvalInt — expression/builtin_op_vec.go:29-68,173-215. */
+int32_t tq_vec_logic(int32_t op, int64_t n, const tq_column *a, const tq_column *b,
+                     tq_column *out, int32_t mem);
+
+enum {
+  TQ_UNARY_NOT_INT = 0,   /* builtinUnaryNotIntSig   builtin_op_vec.go:249-267 */
+  TQ_UNARY_NOT_REAL = 1,  /* builtinUnaryNotRealSig  builtin_op_vec.go:141-167 */
+  TQ_UNARY_MINUS_INT = 2, /* builtinUnaryMinusIntSig builtin_op_vec.go:221-243 */
+  TQ_UNARY_MINUS_REAL = 3,/* builtinUnaryMinusRealSig builtin_op_vec.go:74-86  */
+  TQ_UNARY_ISNULL = 4     /* builtin{Int,Real}IsNullSig builtin_op_vec.go:92-135 */
+};
+int32_t tq_vec_unary(int32_t op, int64_t n, const tq_column *a, int32_t a_unsigned,
+                     tq_column *out, int32_t mem);
+
+/* builtinIf{Int,Real}Sig — expression/builtin_control_vec_generated.go:117-207.
+ * cond is an int column; a/b/out share one 8-byte type (bits are moved verbatim). */
+int32_t tq_vec_if(int64_t n, const tq_column *cond, const tq_column *a, const tq_column *b,
+                  tq_column *out, int32_t mem);
+/* builtinIfNull{Int,Real}Sig — builtin_control_vec_generated.go:23-79. */
+int32_t tq_vec_ifnull(int64_t n, const tq_column *a, const tq_column *b, tq_column *out,
+                      int32_t mem);
+/* builtinInIntSig — expression/builtin_other_vec_generated.go:24-96.  list has n_list
+ * columns; list_unsigned[j] is the unsigned flag of list element j. */
+int32_t tq_vec_in_int(int64_t n, const tq_column *a, int32_t a_unsigned, int32_t n_list,
+                      const tq_column *list, const int32_t *list_unsigned, tq_column *out,
+                      int32_t mem);
+
+/* The BASELINE config-2 pair in one pass: lt_out = (a < b), plus_out = a + b, both
+ * signed BIGINT — one read of a and b instead of two (32 B/row instead of 48). */
+int32_t tq_vec_lt_plus_int(int64_t n, const tq_column *a, const tq_column *b,
+                           tq_column *lt_out, tq_column *plus_out, int32_t mem);
+
+/* expression.VectorizedFilter over an already-evaluated boolean-ish int column
+ * (expression/chunk_executor.go:196-245, toBool expression.go:281-326): selected[i] =
+ * (not NULL && value != 0).  selected is n bytes (Go []bool). */
+int32_t tq_vec_filter_int(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem);
+
+/* ------------------------------------------------------------------ hash join
+ * Replaces HashJoinExec (executor/join.go:31-146), hashRowContainer / rowHashMap
+ * (executor/hash_table.go), joiner (executor/joiner.go).  Protocol (= the reference's
+ * Open / fetchAndBuildHashTable / fetchAndProbeHashTable / Next / Close):
+ *
+ *   tq_join_create
+ *   tq_join_put_build   xN   one inner-side chunk each   (hashRowContainer.PutChunk)
+ *   tq_join_finalize_build
+ *   loop { tq_join_put_probe (one outer-side chunk)  |  tq_join_probe_eof }
+ *        interleaved with tq_join_next until it reports eof
+ *   tq_join_destroy                                  (Close; legal at any point)
+ *
+ * Output schema = left child columns ++ right child columns (executor/builder.go:443);
+ * with outer_is_right != 0 the build (inner) side is the left child. */
+enum { TQ_JOIN_INNER = 0, TQ_JOIN_LEFT_OUTER = 1, TQ_JOIN_RIGHT_OUTER = 2 }; /* planner/core/logical_plans.go:52-57 */
+
+typedef struct tq_join_desc {
+  int32_t join_type;          /* TQ_JOIN_*                                                    */
+  int32_t outer_is_right;     /* 1 iff InnerChildIdx == 0 (builder.go:451-477, joiner.go:93-95) */
+  int32_t n_build_cols;       /* inner-side schema                                            */
+  const int32_t *build_types; /* TQ_TYPE_* per inner column                                   */
+  int32_t n_probe_cols;       /* outer-side schema                                            */
+  const int32_t *probe_types;
+  int32_t n_keys;             /* len(innerKeys) == len(outerKeys)                             */
+  const int32_t *build_key_idx; /* innerKeys[i].Index                                         */
+  const int32_t *probe_key_idx; /* outerKeys[i].Index                                         */
+  int64_t probe_batch_rows;   /* device batch size the ≤1024-row chunks are accumulated into; 0 = default */
+} tq_join_desc;
+
+typedef struct tq_join tq_join;
+
+int32_t tq_join_create(const tq_join_desc *desc, tq_join **out);
+int32_t tq_join_put_build(tq_join *j, const tq_column *cols, int32_t mem);
+int32_t tq_join_finalize_build(tq_join *j);
+/* selected: outerSideFilter result (join.go:328), n bytes of 0/1 in HOST memory, or NULL = all selected. */
+int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *selected, int32_t mem);
+int32_t tq_join_probe_eof(tq_join *j);
+/* Fills at most max_rows joined rows into out_cols (n_build_cols + n_probe_cols caller-
+ * allocated columns, host memory).  *n_rows == 0 with *eof == 0 means "feed more probe
+ * chunks"; *n_rows == 0 with *eof != 0 is the reference's end of stream. */
+int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+int32_t tq_join_destroy(tq_join *j);
+
+/* Benchmark / multi-GPU variant of Next: pops the oldest finished device result batch and
+ * lends its device-resident columns (valid until the next call on this handle). */
+int32_t tq_join_next_device(tq_join *j, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+/* Statistics of the handle: [0] build rows inserted, [1] distinct build keys, [2] partitions,
+ * [3] probe rows consumed, [4] joined rows produced, [5] last probe kernel time in ns,
+ * [6] last build time in ns, [7] probe kernel launches.  */
+int32_t tq_join_stats(tq_join *j, int64_t *stats8);
+
+/* ------------------------------------------------------------------ hash agg
+ * Replaces HashAggExec + workers (executor/aggregate.go) and the aggfuncs it drives
+ * (executor/aggfuncs/ sources).  GROUP BY items and aggregate arguments are column
+ * references into the input chunk (the shim pre-projects expressions with tq_vec_*). */
+enum {
+  TQ_AGG_COUNT = 0,    /* aggfuncs/func_count.go      */
+  TQ_AGG_SUM = 1,      /* aggfuncs/func_sum.go        */
+  TQ_AGG_AVG = 2,      /* aggfuncs/func_avg.go        */
+  TQ_AGG_MAX = 3,      /* aggfuncs/func_max_min.go    */
+  TQ_AGG_MIN = 4,
+  TQ_AGG_FIRSTROW = 5  /* aggfuncs/func_first_row.go  */
+};
+
+typedef struct tq_agg_func {
+  int32_t func;    /* TQ_AGG_*                                                          */
+  int32_t arg_col; /* input column index; -1 = constant non-NULL argument (COUNT(*) == count(1)) */
+} tq_agg_func;
+
+typedef struct tq_agg_desc {
+  int32_t n_input_cols;
+  const int32_t *input_types;   /* TQ_TYPE_* per input column */
+  int32_t n_group_by;           /* 0 = scalar aggregate       */
+  const int32_t *group_by_cols; /* input column indices       */
+  int32_t n_funcs;
+  const tq_agg_func *funcs;     /* output column i = funcs[i] (builder.go:523-535) */
+  int64_t est_groups;           /* hint; 0 = unknown          */
+} tq_agg_desc;
+
+typedef struct tq_agg tq_agg;
+
+int32_t tq_agg_create(const tq_agg_desc *desc, tq_agg **out);
+/* Output type (TQ_TYPE_*) of aggregate i: COUNT → INT64; SUM/AVG keep the argument's eval
+ * type (AVG(int) is the truncating integer division of func_avg.go:53). */
+int32_t tq_agg_output_type(tq_agg *a, int32_t func_idx, int32_t *type_out);
+int32_t tq_agg_put(tq_agg *a, const tq_column *cols, int32_t mem);
+int32_t tq_agg_eof(tq_agg *a);
+int32_t tq_agg_next(tq_agg *a, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+int32_t tq_agg_next_device(tq_agg *a, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+int32_t tq_agg_destroy(tq_agg *a);
+/* [0] input rows, [1] groups, [2] last update-kernel time ns, [3] kernel launches */
+int32_t tq_agg_stats(tq_agg *a, int64_t *stats4);
+
+/* Partial → shuffle → final (aggregate.go:96-133,352-356,424-427), used across GPUs:
+ * tq_agg_export_partial lends device arrays holding one row per local group —
+ * n_group_by key columns followed by the partial-state columns (COUNT: count; SUM: sum
+ * [NULL = no value yet]; AVG: count then sum; MAX/MIN/FIRSTROW: value) — and
+ * tq_agg_merge_partial consumes rows of that layout with MergePartialResult semantics. */
+int32_t tq_agg_partial_width(tq_agg *a, int32_t *n_cols);
+int32_t tq_agg_export_partial(tq_agg *a, tq_column *out_cols, int64_t *n_rows);
+int32_t tq_agg_merge_partial(tq_agg *a, const tq_column *cols, int32_t mem);
+
+/* ------------------------------------------------------------- radix exchange
+ * The shard boundary of the multi-GPU path: splits rows into n_parts partitions by
+ * the key's hash (the moral equivalent of shuffleIntermData, aggregate.go:352-356).
+ * All buffers are device memory.  out_cols must hold `n` rows each; rows of partition p
+ * occupy [offsets[p], offsets[p+1]) of every output column, stable within a partition.
+ * part_offsets is a HOST array of n_parts+1 entries.  Rows whose key is NULL go to
+ * partition (row % n_parts): they never match but outer joins still emit them. */
+int32_t tq_partition_device(int32_t n_cols, const tq_column *cols, const int32_t *types,
+                            int32_t key_col, int64_t n, int32_t n_parts, tq_column *out_cols,
+                            int64_t *part_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYSQL_B200_H */

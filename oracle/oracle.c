@@ -1,0 +1,625 @@
+/*
+ * oracle.c — single-threaded CPU restatement of the TinySQL vectorized-execution hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  Written for obviousness, not speed.
+ * Compile with -fwrapv: Go integer arithmetic wraps, C's is undefined.
+ * Paths in comments are relative to /root/reference.
+ */
+#include "oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define DBL_MAX_ 1.7976931348623157e308 /* math.MaxFloat64 */
+
+/* ------------------------------------------------------------------ column helpers */
+/* util/chunk/column.go:89-92 IsNull: bit == 0 means NULL */
+static inline int col_is_null(const orc_column *c, int64_t i) {
+  if (!c->null_bitmap) return 0;
+  return !((c->null_bitmap[i >> 3] >> (i & 7)) & 1);
+}
+static inline void col_set_null(orc_column *c, int64_t i, int is_null) {
+  if (is_null) c->null_bitmap[i >> 3] &= (uint8_t)~(1u << (i & 7));
+  else c->null_bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
+}
+static inline int64_t col_i64(const orc_column *c, int64_t i) { return ((const int64_t *)c->data)[i]; }
+static inline uint64_t col_u64(const orc_column *c, int64_t i) { return ((const uint64_t *)c->data)[i]; }
+static inline double col_f64(const orc_column *c, int64_t i) { return ((const double *)c->data)[i]; }
+
+/* out column preparation == Column.ResizeInt64(n, false) (util/chunk/column.go:241-249,331):
+ * all rows start NOT NULL; we additionally keep the tail bits of the last byte 0. */
+static void out_init(orc_column *o, int64_t n) {
+  o->length = n;
+  int64_t nb = (n + 7) >> 3;
+  memset(o->null_bitmap, 0xFF, (size_t)nb);
+  if (n & 7) o->null_bitmap[nb - 1] = (uint8_t)((1u << (n & 7)) - 1);
+}
+/* Column.MergeNulls (util/chunk/column.go:559-574): result.null |= arg.null */
+static void merge_nulls(orc_column *o, const orc_column *a, int64_t n) {
+  for (int64_t i = 0; i < n; i++)
+    if (col_is_null(a, i)) col_set_null(o, i, 1);
+}
+
+/* ------------------------------------------------------------------ key encoding + FNV-1 */
+enum { NIL_FLAG = 0, FLOAT_FLAG = 5, VARINT_FLAG = 8, UVARINT_FLAG = 9 }; /* util/codec/codec.go:34-43 */
+
+/* encodeHashChunkRowIdx (util/codec/codec.go:212-240): (flag, raw 8 bytes) */
+static int encode_key(int type, const orc_column *c, int64_t row, uint8_t *flag, uint64_t *raw) {
+  if (col_is_null(c, row)) { *flag = NIL_FLAG; *raw = 0; return 1; }
+  *raw = col_u64(c, row);
+  switch (type) {
+    case ORC_TYPE_INT64: *flag = VARINT_FLAG; break;
+    case ORC_TYPE_UINT64: *flag = (col_i64(c, row) < 0) ? UVARINT_FLAG : VARINT_FLAG; break; /* :220-224 */
+    case ORC_TYPE_FLOAT64: *flag = FLOAT_FLAG; break;
+    default: *flag = 0xFF; break;
+  }
+  return 0;
+}
+
+/* Go hash/fnv New64(): FNV-1 (multiply then xor); restated in-repo at util/mvmap/fnv.go:16-29 */
+static inline uint64_t fnv1_byte(uint64_t h, uint8_t b) { return (h * 1099511628211ULL) ^ b; }
+
+uint64_t orc_hash_row(int n_keys, const int *types, const orc_column *cols, const int *key_idx, int64_t row,
+                      int *has_null) {
+  uint64_t h = 14695981039346656037ULL;
+  int hn = 0;
+  for (int k = 0; k < n_keys; k++) {
+    int ci = key_idx[k];
+    uint8_t flag; uint64_t raw;
+    int isnull = encode_key(types[ci], &cols[ci], row, &flag, &raw);
+    h = fnv1_byte(h, flag);                     /* h[i].Write(buf)  codec.go:273 */
+    if (isnull) { hn = 1; continue; }           /* b = nil; isNull[i] = true  codec.go:263-264 */
+    for (int b = 0; b < 8; b++) h = fnv1_byte(h, (uint8_t)(raw >> (8 * b))); /* h[i].Write(b) little-endian raw */
+  }
+  if (has_null) *has_null = hn;
+  return h;
+}
+
+int orc_equal_row(int n_keys, const int *types1, const orc_column *cols1, const int *idx1, int64_t row1,
+                  const int *types2, const orc_column *cols2, const int *idx2, int64_t row2) {
+  for (int k = 0; k < n_keys; k++) { /* util/codec/codec.go:367-380 */
+    uint8_t f1, f2; uint64_t r1, r2;
+    int n1 = encode_key(types1[idx1[k]], &cols1[idx1[k]], row1, &f1, &r1);
+    int n2 = encode_key(types2[idx2[k]], &cols2[idx2[k]], row2, &f2, &r2);
+    if (f1 != f2) return 0;
+    if (n1 != n2) return 0;
+    if (!n1 && r1 != r2) return 0;
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------ rowHashMap */
+/* executor/hash_table.go:181-272.  Go's map[uint64]entryAddr is an associative container;
+ * here an open-addressed table keyed by the 64-bit hash, value = head entry index.
+ * Entries form a chain through `next` (newest first); Get reverses to insertion order. */
+typedef struct { uint32_t chk, row; int64_t next; } rm_entry;
+struct orc_rowmap {
+  uint64_t *keys; int64_t *heads; uint8_t *used; int64_t cap, n_keys;
+  rm_entry *entries; int64_t n_entries, cap_entries;
+};
+orc_rowmap *orc_rowmap_new(void) {
+  orc_rowmap *m = (orc_rowmap *)calloc(1, sizeof(*m));
+  m->cap = 1024;
+  m->keys = (uint64_t *)calloc((size_t)m->cap, 8); m->heads = (int64_t *)calloc((size_t)m->cap, 8);
+  m->used = (uint8_t *)calloc((size_t)m->cap, 1);
+  m->cap_entries = 1024; m->entries = (rm_entry *)malloc(sizeof(rm_entry) * (size_t)m->cap_entries);
+  return m;
+}
+static int64_t rm_find(const orc_rowmap *m, uint64_t k) {
+  uint64_t x = k * 0x9E3779B97F4A7C15ULL;
+  int64_t i = (int64_t)(x >> 20) & (m->cap - 1);
+  while (m->used[i] && m->keys[i] != k) i = (i + 1) & (m->cap - 1);
+  return i;
+}
+static void rm_grow(orc_rowmap *m) {
+  int64_t oc = m->cap; uint64_t *ok = m->keys; int64_t *oh = m->heads; uint8_t *ou = m->used;
+  m->cap = oc * 2;
+  m->keys = (uint64_t *)calloc((size_t)m->cap, 8); m->heads = (int64_t *)calloc((size_t)m->cap, 8);
+  m->used = (uint8_t *)calloc((size_t)m->cap, 1);
+  for (int64_t i = 0; i < oc; i++) if (ou[i]) { int64_t s = rm_find(m, ok[i]); m->used[s] = 1; m->keys[s] = ok[i]; m->heads[s] = oh[i]; }
+  free(ok); free(oh); free(ou);
+}
+void orc_rowmap_put(orc_rowmap *m, uint64_t hash_key, uint32_t chk_idx, uint32_t row_idx) {
+  if ((m->n_keys + 1) * 2 > m->cap) rm_grow(m);
+  int64_t s = rm_find(m, hash_key);
+  int64_t old = -1;                               /* nullEntryAddr */
+  if (m->used[s]) old = m->heads[s]; else { m->used[s] = 1; m->keys[s] = hash_key; m->n_keys++; }
+  if (m->n_entries == m->cap_entries) { m->cap_entries *= 2; m->entries = (rm_entry *)realloc(m->entries, sizeof(rm_entry) * (size_t)m->cap_entries); }
+  rm_entry e = { chk_idx, row_idx, old };          /* e.next = oldEntryAddr  hash_table.go:249-252 */
+  m->entries[m->n_entries] = e;
+  m->heads[s] = m->n_entries++;                    /* m.hashTable[hashKey] = newEntryAddr */
+}
+int64_t orc_rowmap_get(orc_rowmap *m, uint64_t hash_key, uint32_t *pairs, int64_t cap) {
+  int64_t s = rm_find(m, hash_key);
+  if (!m->used[s]) return 0;
+  int64_t cnt = 0;
+  for (int64_t e = m->heads[s]; e != -1; e = m->entries[e].next) cnt++;
+  int64_t pos = cnt;                               /* "Keep the order of input" hash_table.go:266-270 */
+  for (int64_t e = m->heads[s]; e != -1; e = m->entries[e].next) {
+    pos--;
+    if (pos < cap) { pairs[2 * pos] = m->entries[e].chk; pairs[2 * pos + 1] = m->entries[e].row; }
+  }
+  return cnt;
+}
+int64_t orc_rowmap_len(orc_rowmap *m) { return m->n_entries; }
+void orc_rowmap_free(orc_rowmap *m) { if (!m) return; free(m->keys); free(m->heads); free(m->used); free(m->entries); free(m); }
+
+/* ------------------------------------------------------------------ growable output */
+typedef struct { uint64_t *data; uint8_t *nn; int64_t n, cap; } outbuf; /* nn: byte per row, 1 = not null */
+static void ob_push(outbuf *b, uint64_t v, int not_null) {
+  if (b->n == b->cap) {
+    b->cap = b->cap ? b->cap * 2 : 1024;
+    b->data = (uint64_t *)realloc(b->data, 8 * (size_t)b->cap);
+    b->nn = (uint8_t *)realloc(b->nn, (size_t)b->cap);
+  }
+  b->data[b->n] = v; b->nn[b->n] = (uint8_t)not_null; b->n++;
+}
+static void ob_finish(outbuf *b, orc_column *c) {
+  int64_t n = b->n;
+  c->length = n; c->offsets = NULL;
+  c->data = (uint8_t *)malloc(8 * (size_t)(n ? n : 1));
+  if (n) memcpy(c->data, b->data, 8 * (size_t)n);
+  int64_t nb = (n + 7) >> 3;
+  c->null_bitmap = (uint8_t *)calloc((size_t)(nb ? nb : 1), 1);
+  for (int64_t i = 0; i < n; i++) if (b->nn[i]) c->null_bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
+  free(b->data); free(b->nn);
+}
+void orc_free_columns(int n, orc_column *cols) {
+  for (int i = 0; i < n; i++) { free(cols[i].data); free(cols[i].null_bitmap); cols[i].data = NULL; cols[i].null_bitmap = NULL; }
+}
+
+/* ------------------------------------------------------------------ hash join */
+static void append_row(outbuf *obs, int base, int ncols, const orc_column *cols, int64_t row) {
+  for (int c = 0; c < ncols; c++) {
+    if (row < 0) ob_push(&obs[base + c], 0, 0);            /* defaultInner: all NULL (builder.go:463-465) */
+    else ob_push(&obs[base + c], col_u64(&cols[c], row), !col_is_null(&cols[c], row));
+  }
+}
+
+int orc_hash_join(int join_type, int outer_is_right,
+                  int n_build_cols, const int *build_types, const orc_column *build_cols,
+                  int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
+                  int n_keys, const int *build_key_idx, const int *probe_key_idx,
+                  const uint8_t *selected, orc_column *out_cols, int64_t *n_out) {
+  if (join_type < 0 || join_type > 2 || n_keys < 1) return ORC_ERR_INVALID;
+  for (int c = 0; c < n_build_cols; c++) if (build_types[c] < 1 || build_types[c] > 3) return ORC_ERR_UNSUPPORTED;
+  for (int c = 0; c < n_probe_cols; c++) if (probe_types[c] < 1 || probe_types[c] > 3) return ORC_ERR_UNSUPPORTED;
+  int64_t nb = n_build_cols ? build_cols[0].length : 0, np = n_probe_cols ? probe_cols[0].length : 0;
+
+  /* fetchAndBuildHashTable [stub join.go:148] + hashRowContainer.PutChunk (hash_table.go:146-169) */
+  orc_rowmap *m = orc_rowmap_new();
+  for (int64_t i = 0; i < nb; i++) {
+    int has_null;
+    uint64_t h = orc_hash_row(n_keys, build_types, build_cols, build_key_idx, i, &has_null);
+    if (has_null) continue;                                    /* hash_table.go:161-163 */
+    orc_rowmap_put(m, h, (uint32_t)(i >> 32), (uint32_t)i);    /* RowPtr; we pack the global row index */
+  }
+
+  int ncols = n_build_cols + n_probe_cols;
+  outbuf *obs = (outbuf *)calloc((size_t)ncols, sizeof(outbuf));
+  /* output = lhs cols ++ rhs cols (joiner.go:145-150, 361-366); outer_is_right => build side is lhs */
+  int build_base = outer_is_right ? 0 : n_probe_cols;
+  int probe_base = outer_is_right ? n_build_cols : 0;
+  int is_outer = (join_type != 0);
+
+  uint32_t *pairs = NULL; int64_t pairs_cap = 0;
+  /* runJoinWorker [stub join.go:243] -> join2Chunk (join.go:325-362) */
+  for (int64_t i = 0; i < np; i++) {
+    int has_null = 0; uint64_t h = 0;
+    int sel = selected ? selected[i] != 0 : 1;
+    if (sel) h = orc_hash_row(n_keys, probe_types, probe_cols, probe_key_idx, i, &has_null); /* HashChunkSelected */
+    int64_t n_matched = 0;
+    if (sel && !has_null) {
+      /* GetMatchedRows (hash_table.go:110-134): candidates by hash in insertion order, verified by EqualChunkRow */
+      int64_t cnt = orc_rowmap_get(m, h, pairs, pairs_cap);
+      if (cnt > pairs_cap) { pairs_cap = cnt * 2; pairs = (uint32_t *)realloc(pairs, 8 * (size_t)pairs_cap); cnt = orc_rowmap_get(m, h, pairs, pairs_cap); }
+      for (int64_t c = 0; c < cnt; c++) {
+        int64_t brow = ((int64_t)pairs[2 * c] << 32) | pairs[2 * c + 1];
+        if (!orc_equal_row(n_keys, build_types, build_cols, build_key_idx, brow, probe_types, probe_cols, probe_key_idx, i)) continue;
+        /* tryToMatchInners with no OtherConditions: makeJoinRowToChunk per inner (joiner.go:225-248,288-311,351-378) */
+        append_row(obs, build_base, n_build_cols, build_cols, brow);
+        append_row(obs, probe_base, n_probe_cols, probe_cols, i);
+        n_matched++;
+      }
+    }
+    if (n_matched == 0 && is_outer) {                           /* onMissMatch joiner.go:274-277,337-340; inner: :405 */
+      append_row(obs, build_base, n_build_cols, build_cols, -1);
+      append_row(obs, probe_base, n_probe_cols, probe_cols, i);
+    }
+  }
+  free(pairs);
+  orc_rowmap_free(m);
+  *n_out = ncols ? obs[0].n : 0;
+  for (int c = 0; c < ncols; c++) ob_finish(&obs[c], &out_cols[c]);
+  free(obs);
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ hash aggregation */
+enum { AGG_COUNT = 0, AGG_SUM = 1, AGG_AVG = 2, AGG_MAX = 3, AGG_MIN = 4, AGG_FIRSTROW = 5 };
+
+/* one PartialResult (aggfuncs/ sources partialResult4*): a tagged union of the states */
+typedef struct {
+  int64_t i;      /* count (COUNT, AVG) */
+  int64_t si;     /* int sum / int value */
+  double sf;      /* float sum / float value */
+  uint8_t is_null;   /* SUM/MAX/MIN: no value yet (func_sum.go:40-44) */
+  uint8_t got_first; /* FIRSTROW (func_first_row.go:22-28) */
+} agg_state;
+
+static void state_alloc(int func, agg_state *s) { /* AllocPartialResult */
+  memset(s, 0, sizeof(*s));
+  if (func == AGG_SUM || func == AGG_MAX || func == AGG_MIN) s->is_null = 1;
+}
+
+/* types.AddInt64 (types/overflow.go:33-40) */
+static int add_int64(int64_t a, int64_t b, int64_t *r) {
+  if ((a > 0 && b > 0 && INT64_MAX - a < b) || (a < 0 && b < 0 && INT64_MIN - a > b)) return ORC_ERR_OVERFLOW_BIGINT;
+  *r = a + b; return ORC_OK;
+}
+
+/* UpdatePartialResult for one input row */
+static int state_update(int func, int type, const orc_column *arg, int64_t row, agg_state *s) {
+  int isnull = arg ? col_is_null(arg, row) : 0;    /* arg == NULL: constant 1 (COUNT(*) == count(1), parser.y:3258-3262) */
+  switch (func) {
+    case AGG_COUNT: if (!isnull) s->i++; return ORC_OK;                    /* func_count.go:33-49 */
+    case AGG_SUM:
+      if (isnull) return ORC_OK;
+      if (type == ORC_TYPE_FLOAT64) {                                      /* func_sum.go:62-82 */
+        double v = arg ? col_f64(arg, row) : 1.0;
+        if (s->is_null) { s->sf = v; s->is_null = 0; } else s->sf += v;
+      } else {                                                              /* func_sum.go:115-140 */
+        int64_t v = arg ? col_i64(arg, row) : 1;
+        if (s->is_null) { s->si = v; s->is_null = 0; return ORC_OK; }
+        return add_int64(s->si, v, &s->si);
+      }
+      return ORC_OK;
+    case AGG_AVG:
+      if (isnull) return ORC_OK;
+      if (type == ORC_TYPE_FLOAT64) { s->sf += arg ? col_f64(arg, row) : 1.0; s->i++; return ORC_OK; } /* func_avg.go:172-190 */
+      { int rc = add_int64(s->si, arg ? col_i64(arg, row) : 1, &s->si); if (rc) return rc; s->i++; return ORC_OK; } /* :63-83 */
+    case AGG_MAX: case AGG_MIN: {
+      if (isnull) return ORC_OK;
+      int is_max = (func == AGG_MAX);
+      if (type == ORC_TYPE_FLOAT64) {                                      /* func_max_min.go:275-295 */
+        double v = col_f64(arg, row);
+        if (s->is_null) { s->sf = v; s->is_null = 0; }
+        else if ((is_max && v > s->sf) || (!is_max && v < s->sf)) s->sf = v;
+      } else if (type == ORC_TYPE_UINT64) {                                /* :146-167 */
+        uint64_t v = col_u64(arg, row), cur = (uint64_t)s->si;
+        if (s->is_null) { s->si = (int64_t)v; s->is_null = 0; }
+        else if ((is_max && v > cur) || (!is_max && v < cur)) s->si = (int64_t)v;
+      } else {                                                              /* :83-103 */
+        int64_t v = col_i64(arg, row);
+        if (s->is_null) { s->si = v; s->is_null = 0; }
+        else if ((is_max && v > s->si) || (!is_max && v < s->si)) s->si = v;
+      }
+      return ORC_OK;
+    }
+    case AGG_FIRSTROW:                                                      /* func_first_row.go:67-81 */
+      if (s->got_first) return ORC_OK;
+      s->got_first = 1; s->is_null = (uint8_t)isnull;
+      if (arg) { s->si = col_i64(arg, row); memcpy(&s->sf, &s->si, 8); } else { s->si = 1; }
+      return ORC_OK;
+  }
+  return ORC_ERR_INVALID;
+}
+
+/* MergePartialResult(src, dst) */
+static int state_merge(int func, int type, const agg_state *src, agg_state *dst) {
+  switch (func) {
+    case AGG_COUNT: dst->i += src->i; return ORC_OK;                       /* func_count.go:115-119 */
+    case AGG_SUM:
+      if (src->is_null) return ORC_OK;
+      if (type == ORC_TYPE_FLOAT64) { dst->sf += src->sf; dst->is_null = 0; return ORC_OK; } /* func_sum.go:84-92 */
+      { int rc = add_int64(src->si, dst->si, &dst->si); if (rc) return rc; dst->is_null = 0; return ORC_OK; } /* :142-154 */
+    case AGG_AVG:
+      if (src->i == 0) return ORC_OK;                                       /* func_avg.go:120-131, 230-238 */
+      if (type == ORC_TYPE_FLOAT64) { dst->sf += src->sf; dst->i += src->i; return ORC_OK; }
+      { int rc = add_int64(src->si, dst->si, &dst->si); if (rc) return rc; dst->i += src->i; return ORC_OK; }
+    case AGG_MAX: case AGG_MIN: {
+      if (src->is_null) return ORC_OK;                                      /* func_max_min.go:105-118 */
+      if (dst->is_null) { *dst = *src; return ORC_OK; }
+      int is_max = (func == AGG_MAX);
+      if (type == ORC_TYPE_FLOAT64) { if ((is_max && src->sf > dst->sf) || (!is_max && src->sf < dst->sf)) dst->sf = src->sf; }
+      else if (type == ORC_TYPE_UINT64) { uint64_t a = (uint64_t)src->si, b = (uint64_t)dst->si; if ((is_max && a > b) || (!is_max && a < b)) dst->si = src->si; }
+      else { if ((is_max && src->si > dst->si) || (!is_max && src->si < dst->si)) dst->si = src->si; }
+      return ORC_OK;
+    }
+    case AGG_FIRSTROW: if (!dst->got_first) *dst = *src; return ORC_OK;     /* func_first_row.go:83-89 */
+  }
+  return ORC_ERR_INVALID;
+}
+
+/* AppendFinalResult2Chunk */
+static void state_final(int func, int type, const agg_state *s, outbuf *ob) {
+  uint64_t bits;
+  switch (func) {
+    case AGG_COUNT: ob_push(ob, (uint64_t)s->i, 1); return;                /* func_count.go:23-27 */
+    case AGG_SUM: case AGG_MAX: case AGG_MIN:
+      if (s->is_null) { ob_push(ob, 0, 0); return; }                        /* func_sum.go:53-60 */
+      if (type == ORC_TYPE_FLOAT64) { memcpy(&bits, &s->sf, 8); ob_push(ob, bits, 1); } else ob_push(ob, (uint64_t)s->si, 1);
+      return;
+    case AGG_AVG:
+      if (s->i == 0) { ob_push(ob, 0, 0); return; }                         /* func_avg.go:47-55,159-167 */
+      if (type == ORC_TYPE_FLOAT64) { double r = s->sf / (double)s->i; memcpy(&bits, &r, 8); ob_push(ob, bits, 1); }
+      else ob_push(ob, (uint64_t)(s->si / s->i), 1);                        /* Go truncating int division */
+      return;
+    case AGG_FIRSTROW:
+      if (s->is_null || !s->got_first) { ob_push(ob, 0, 0); return; }       /* func_first_row.go:91-99 */
+      ob_push(ob, (uint64_t)s->si, 1); return;
+  }
+}
+
+/* Group key = HashGroupKey bytes (util/codec/codec.go:713-746).  The varint / cmp-float encodings
+ * are injective on (is_null, 8 raw bytes), so the oracle keys on exactly that pair per GROUP BY item. */
+typedef struct { uint64_t *keys; /* n_gb*2 words per group: isnull, bits */ agg_state *states; int64_t n, cap;
+                 int64_t *slots; int64_t n_slots; int n_gb, n_funcs; } agg_map;
+
+static void amap_init(agg_map *m, int n_gb, int n_funcs) {
+  memset(m, 0, sizeof(*m)); m->n_gb = n_gb; m->n_funcs = n_funcs; m->n_slots = 1024;
+  m->slots = (int64_t *)malloc(8 * (size_t)m->n_slots); for (int64_t i = 0; i < m->n_slots; i++) m->slots[i] = -1;
+}
+static uint64_t akey_hash(const uint64_t *k, int nw) { uint64_t h = 1469598103934665603ULL; for (int i = 0; i < nw; i++) { h ^= k[i]; h *= 0x100000001B3ULL; h ^= h >> 29; } return h; }
+static int64_t amap_get(agg_map *m, const uint64_t *key, const int *funcs) { /* getPartialResult aggregate.go:396-410 */
+  int nw = m->n_gb * 2;
+  if ((m->n + 1) * 2 > m->n_slots) {
+    m->n_slots *= 2; m->slots = (int64_t *)realloc(m->slots, 8 * (size_t)m->n_slots);
+    for (int64_t i = 0; i < m->n_slots; i++) m->slots[i] = -1;
+    for (int64_t g = 0; g < m->n; g++) { int64_t s = (int64_t)(akey_hash(m->keys + g * nw, nw) & (uint64_t)(m->n_slots - 1)); while (m->slots[s] >= 0) s = (s + 1) & (m->n_slots - 1); m->slots[s] = g; }
+  }
+  int64_t s = (int64_t)(akey_hash(key, nw) & (uint64_t)(m->n_slots - 1));
+  while (m->slots[s] >= 0) { if (nw == 0 || !memcmp(m->keys + m->slots[s] * nw, key, 8 * (size_t)nw)) return m->slots[s]; s = (s + 1) & (m->n_slots - 1); }
+  if (m->n == m->cap) { m->cap = m->cap ? m->cap * 2 : 1024; m->keys = (uint64_t *)realloc(m->keys, 8 * (size_t)(nw ? nw : 1) * (size_t)m->cap); m->states = (agg_state *)realloc(m->states, sizeof(agg_state) * (size_t)(m->n_funcs ? m->n_funcs : 1) * (size_t)m->cap); }
+  if (nw) memcpy(m->keys + m->n * nw, key, 8 * (size_t)nw);
+  for (int f = 0; f < m->n_funcs; f++) state_alloc(funcs[f], &m->states[m->n * m->n_funcs + f]);
+  m->slots[s] = m->n;
+  return m->n++;
+}
+static void amap_free(agg_map *m) { free(m->keys); free(m->states); free(m->slots); }
+
+int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int64_t n_rows,
+                 int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_func *funcs,
+                 int n_partial_workers, orc_column *out_cols, int64_t *n_out) {
+  if (n_partial_workers < 1) n_partial_workers = 1;
+  for (int c = 0; c < n_input_cols; c++) if (types[c] < 1 || types[c] > 3) return ORC_ERR_UNSUPPORTED;
+  int *fn = (int *)malloc(sizeof(int) * (size_t)(n_funcs ? n_funcs : 1));
+  int *ft = (int *)malloc(sizeof(int) * (size_t)(n_funcs ? n_funcs : 1));
+  for (int f = 0; f < n_funcs; f++) { fn[f] = funcs[f].func; ft[f] = funcs[f].arg_col >= 0 ? types[funcs[f].arg_col] : ORC_TYPE_INT64; }
+  agg_map *partial = (agg_map *)malloc(sizeof(agg_map) * (size_t)n_partial_workers);
+  for (int w = 0; w < n_partial_workers; w++) amap_init(&partial[w], n_group_by, n_funcs);
+  uint64_t key[64];
+  int rc = ORC_OK;
+  /* fetchChildData deals chunks to partial workers (aggregate.go:487-522); updatePartialResult (:332-350) */
+  for (int64_t i = 0; i < n_rows && rc == ORC_OK; i++) {
+    int w = (int)((i / 1024) % n_partial_workers);
+    for (int g = 0; g < n_group_by; g++) {
+      const orc_column *c = &cols[group_by_cols[g]];
+      int isnull = col_is_null(c, i);
+      key[2 * g] = (uint64_t)isnull; key[2 * g + 1] = isnull ? 0 : col_u64(c, i);   /* NilFlag: NULL is its own group */
+    }
+    int64_t gi = amap_get(&partial[w], key, fn);
+    for (int f = 0; f < n_funcs && rc == ORC_OK; f++)
+      rc = state_update(fn[f], ft[f], funcs[f].arg_col >= 0 ? &cols[funcs[f].arg_col] : NULL, i, &partial[w].states[gi * n_funcs + f]);
+  }
+  /* shuffleIntermData [stub :354] + consumeIntermData [stub :424]: every group reaches exactly one
+   * final worker and is merged there with MergePartialResult; one final map is result-equivalent. */
+  agg_map fin; amap_init(&fin, n_group_by, n_funcs);
+  for (int w = 0; w < n_partial_workers && rc == ORC_OK; w++)
+    for (int64_t g = 0; g < partial[w].n && rc == ORC_OK; g++) {
+      int64_t gi = amap_get(&fin, partial[w].keys + g * n_group_by * 2, fn);
+      for (int f = 0; f < n_funcs && rc == ORC_OK; f++)
+        rc = state_merge(fn[f], ft[f], &partial[w].states[g * n_funcs + f], &fin.states[gi * n_funcs + f]);
+    }
+  outbuf *obs = (outbuf *)calloc((size_t)(n_funcs ? n_funcs : 1), sizeof(outbuf));
+  if (rc == ORC_OK) {
+    if (fin.n == 0 && n_group_by == 0) {
+      /* empty input, no GROUP BY: defaultVal row (aggregate.go:572-574, builder.go:517-540):
+       * COUNT -> 0, everything else NULL.  (all-FIRSTROW aggregates produce no row.) */
+      int all_first = 1; for (int f = 0; f < n_funcs; f++) if (fn[f] != AGG_FIRSTROW) all_first = 0;
+      if (!all_first) for (int f = 0; f < n_funcs; f++) { if (fn[f] == AGG_COUNT) ob_push(&obs[f], 0, 1); else ob_push(&obs[f], 0, 0); }
+    } else {
+      for (int64_t g = 0; g < fin.n; g++)              /* getFinalResult aggregate.go:429-457 */
+        for (int f = 0; f < n_funcs; f++) state_final(fn[f], ft[f], &fin.states[g * n_funcs + f], &obs[f]);
+    }
+  }
+  *n_out = n_funcs ? obs[0].n : 0;
+  for (int f = 0; f < n_funcs; f++) ob_finish(&obs[f], &out_cols[f]);
+  free(obs);
+  for (int w = 0; w < n_partial_workers; w++) amap_free(&partial[w]);
+  amap_free(&fin); free(partial); free(fn); free(ft);
+  return rc;
+}
+
+/* ------------------------------------------------------------------ vectorized builtins */
+/* types/compare.go:44-100 VecCompare{UU,II,UI,IU} -> -1/0/1 */
+static int cmp_int(int ua, int ub, int64_t x, int64_t y) {
+  if (ua && ub) { uint64_t a = (uint64_t)x, b = (uint64_t)y; return a < b ? -1 : (a == b ? 0 : 1); }
+  if (!ua && !ub) return x < y ? -1 : (x == y ? 0 : 1);
+  if (ua && !ub) { /* VecCompareUI :72-85 */
+    if (y < 0 || (uint64_t)x > (uint64_t)INT64_MAX) return 1;
+    return x < y ? -1 : (x == y ? 0 : 1);
+  }
+  /* VecCompareIU :88-100 */
+  if (x < 0 || (uint64_t)y > (uint64_t)INT64_MAX) return -1;
+  return x < y ? -1 : (x == y ? 0 : 1);
+}
+static int64_t cmp_result(int op, int c) { /* vecResOf{LT,LE,GT,GE,EQ,NE} builtin_compare_vec.go:214-279 */
+  switch (op) { case 0: return c < 0; case 1: return c <= 0; case 2: return c > 0; case 3: return c >= 0; case 4: return c == 0; default: return c != 0; }
+}
+
+int orc_vec_compare_int(int op, int64_t n, const orc_column *a, int ua, const orc_column *b, int ub, orc_column *out) {
+  if (op < 0 || op > 5) return ORC_ERR_INVALID;
+  out_init(out, n);                                   /* result.ResizeInt64(n, false)  builtin_compare_vec.go:207 */
+  int64_t *r = (int64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) r[i] = cmp_result(op, cmp_int(ua, ub, col_i64(a, i), col_i64(b, i))); /* all rows, NULL or not */
+  merge_nulls(out, a, n); merge_nulls(out, b, n);     /* result.MergeNulls(buf0, buf1) :209 */
+  return ORC_OK;
+}
+
+/* types.CompareFloat64 (types/compare.go): x<y -> -1; x==y -> 0; else 1 (NaN compares as 1) */
+static int cmp_f64(double x, double y) { return x < y ? -1 : (x == y ? 0 : 1); }
+int orc_vec_compare_real(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out) {
+  if (op < 0 || op > 5) return ORC_ERR_INVALID;
+  out_init(out, n); merge_nulls(out, a, n); merge_nulls(out, b, n);   /* builtin_compare_vec_generated.go:44-45 */
+  int64_t *r = (int64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) {
+    if (col_is_null(out, i)) { r[i] = 0; continue; }               /* `continue`: slot is don't-care; we pin it to 0 */
+    r[i] = cmp_result(op, cmp_f64(col_f64(a, i), col_f64(b, i)));
+  }
+  return ORC_OK;
+}
+
+int orc_vec_arith_int(int op, int64_t n, const orc_column *a, int ua, const orc_column *b, int ub, orc_column *out) {
+  if (op < 0 || op > 2) return ORC_ERR_INVALID;
+  out_init(out, n); merge_nulls(out, a, n); merge_nulls(out, b, n);
+  int64_t *r = (int64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) {
+    if (col_is_null(out, i)) { r[i] = 0; continue; }                /* `if result.IsNull(i) continue` — slot don't-care, pinned 0 */
+    int64_t lh = col_i64(a, i), rh = col_i64(b, i);
+    if (op == 0) {                                                   /* builtin_arithmetic_vec.go:431-495 */
+      if (ua && ub) { if ((uint64_t)lh > UINT64_MAX - (uint64_t)rh) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED; }        /* plusUU :437 */
+      else if (ua && !ub) {                                          /* plusUS :448-459 (second test restated verbatim: lh twice) */
+        if (rh < 0 && (uint64_t)(-rh) > (uint64_t)lh) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
+        if (rh > 0 && (uint64_t)lh > UINT64_MAX - (uint64_t)lh) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
+      } else if (!ua && ub) {                                        /* plusSU :464-476 */
+        if (lh < 0 && (uint64_t)(-lh) > (uint64_t)rh) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
+        if (lh > 0 && (uint64_t)rh > UINT64_MAX - (uint64_t)lh) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
+      } else {                                                       /* plusSS :481-495 */
+        if ((lh > 0 && rh > INT64_MAX - lh) || (lh < 0 && rh < INT64_MIN - lh)) return ORC_ERR_OVERFLOW_BIGINT;
+      }
+      r[i] = lh + rh;
+    } else if (op == 1) {                                            /* Minus, forceToSigned == false (default SQL mode) :130-139 */
+      if (ua && ub) { if ((uint64_t)lh < (uint64_t)rh) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED; }                      /* minusUU :208 */
+      else if (ua && !ub) {                                          /* minusUS :224-229 */
+        if (rh >= 0 && (uint64_t)lh < (uint64_t)rh) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
+        if (rh < 0 && (uint64_t)lh > UINT64_MAX - (uint64_t)(-rh)) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
+      } else if (!ua && ub) {                                        /* minusSU :245 */
+        if ((uint64_t)(lh - INT64_MIN) < (uint64_t)rh) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
+      } else {                                                       /* minusSS :260 */
+        if ((lh > 0 && -rh > INT64_MAX - lh) || (lh < 0 && -rh < INT64_MIN - lh)) return ORC_ERR_OVERFLOW_BIGINT;
+      }
+      r[i] = lh - rh;
+    } else {
+      if (ua && ub) {                                                /* MultiplyIntUnsigned :521-529 */
+        uint64_t x = (uint64_t)lh, y = (uint64_t)rh, res = x * y;
+        if (x != 0 && res / x != y) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
+        r[i] = (int64_t)res;
+      } else {                                                       /* MultiplyInt :332-338 */
+        int64_t tmp = lh * rh;
+        /* Go's wrapping quotient: MinInt64 / -1 == MinInt64 (no trap) */
+        int64_t q = (lh == -1 && tmp == INT64_MIN) ? INT64_MIN : (lh != 0 ? tmp / lh : 0);
+        if (lh != 0 && q != rh) return ORC_ERR_OVERFLOW_BIGINT;
+        r[i] = tmp;
+      }
+    }
+  }
+  return ORC_OK;
+}
+
+int orc_vec_arith_real(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out, int64_t *div_by_zero) {
+  if (op < 0 || op > 3) return ORC_ERR_INVALID;
+  out_init(out, n); merge_nulls(out, a, n); merge_nulls(out, b, n);
+  double *r = (double *)out->data;
+  int64_t dz = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (col_is_null(out, i)) { r[i] = 0; continue; }
+    double x = col_f64(a, i), y = col_f64(b, i);
+    switch (op) {
+      case 0: if ((x > 0 && y > DBL_MAX_ - x) || (x < 0 && y < -DBL_MAX_ - x)) return ORC_ERR_OVERFLOW_DOUBLE; r[i] = x + y; break;   /* :302-305 */
+      case 1: if ((x > 0 && -y > DBL_MAX_ - x) || (x < 0 && -y < -DBL_MAX_ - x)) return ORC_ERR_OVERFLOW_DOUBLE; r[i] = x - y; break; /* :80-83 */
+      case 2: r[i] = x * y; if (isinf(r[i])) return ORC_ERR_OVERFLOW_DOUBLE; break;                                                  /* :49-52 */
+      case 3:                                                                                                                        /* :368-381 */
+        if (y == 0) { dz++; col_set_null(out, i, 1); r[i] = 0; break; }
+        r[i] = x / y; if (isinf(r[i])) return ORC_ERR_OVERFLOW_DOUBLE; break;
+    }
+  }
+  if (div_by_zero) *div_by_zero = dz;
+  return ORC_OK;
+}
+
+int orc_vec_logic(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out) {
+  out_init(out, n);
+  int64_t *r = (int64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) {
+    int n0 = col_is_null(a, i), n1 = col_is_null(b, i);
+    int64_t v0 = col_i64(a, i), v1 = col_i64(b, i);
+    if (op == 0) {                                                   /* LogicAnd builtin_op_vec.go:192-211 */
+      if (!n0 && v0 == 0) { r[i] = 0; }
+      else if (!n1 && v1 == 0) { r[i] = 0; }
+      else if (n0 || n1) { r[i] = 0; col_set_null(out, i, 1); }
+      else r[i] = 1;
+    } else if (op == 1) {                                            /* LogicOr :46-66 */
+      if ((!n0 && v0 != 0) || (!n1 && v1 != 0)) r[i] = 1;
+      else if (n0 || n1) { r[i] = 0; col_set_null(out, i, 1); }
+      else r[i] = 0;
+    } else return ORC_ERR_INVALID;
+  }
+  return ORC_OK;
+}
+
+int orc_vec_unary(int op, int64_t n, const orc_column *a, int ua, orc_column *out) {
+  out_init(out, n);
+  int64_t *r = (int64_t *)out->data; double *rf = (double *)out->data;
+  for (int64_t i = 0; i < n; i++) {
+    int isn = col_is_null(a, i);
+    switch (op) {
+      case 0: if (isn) { col_set_null(out, i, 1); r[i] = 0; } else r[i] = (col_i64(a, i) == 0); break;        /* UnaryNotInt :255-265 */
+      case 1: if (isn) { col_set_null(out, i, 1); r[i] = 0; } else r[i] = (col_f64(a, i) == 0); break;        /* UnaryNotReal :152-165 */
+      case 2: {                                                                                              /* UnaryMinusInt :221-243 — no NULL test in the loops; NULL slots are don't-care in the column contract, so the oracle skips them */
+        if (isn) { col_set_null(out, i, 1); r[i] = 0; break; }
+        int64_t v = col_i64(a, i);
+        if (ua) { if ((uint64_t)v > (uint64_t)INT64_MAX + 1ULL) return ORC_ERR_OVERFLOW_BIGINT; }
+        else if (v == INT64_MIN) return ORC_ERR_OVERFLOW_BIGINT;
+        r[i] = -v; break;
+      }
+      case 3: if (isn) { col_set_null(out, i, 1); rf[i] = 0; } else rf[i] = -col_f64(a, i); break;           /* UnaryMinusReal :74-86 */
+      case 4: r[i] = isn ? 1 : 0; break;                                                                     /* IsNull :98-106: never NULL */
+      default: return ORC_ERR_INVALID;
+    }
+  }
+  return ORC_OK;
+}
+
+int orc_vec_if(int64_t n, const orc_column *c, const orc_column *a, const orc_column *b, orc_column *out) {
+  out_init(out, n);
+  uint64_t *r = (uint64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) {                    /* builtin_control_vec_generated.go:141-156 */
+    const orc_column *src = (col_is_null(c, i) || col_i64(c, i) == 0) ? b : a;
+    if (col_is_null(src, i)) { col_set_null(out, i, 1); r[i] = 0; } else r[i] = col_u64(src, i);
+  }
+  return ORC_OK;
+}
+int orc_vec_ifnull(int64_t n, const orc_column *a, const orc_column *b, orc_column *out) {
+  out_init(out, n);
+  uint64_t *r = (uint64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) {                    /* builtin_control_vec_generated.go:38-45 */
+    const orc_column *src = col_is_null(a, i) ? b : a;
+    if (col_is_null(src, i)) { col_set_null(out, i, 1); r[i] = 0; } else r[i] = col_u64(src, i);
+  }
+  return ORC_OK;
+}
+int orc_vec_in_int(int64_t n, const orc_column *a, int ua, int n_list, const orc_column *list, const int *lu, orc_column *out) {
+  out_init(out, n);
+  int64_t *r = (int64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) {                    /* builtin_other_vec_generated.go:42-94 */
+    int has_null = 0, found = 0;
+    for (int j = 0; j < n_list; j++) {
+      if (col_is_null(&list[j], i) || col_is_null(a, i)) { has_null = 1; continue; }  /* buf1.MergeNulls(buf0) */
+      int64_t x = col_i64(a, i), y = col_i64(&list[j], i);
+      int eq;
+      if ((ua && lu[j]) || (!ua && !lu[j])) eq = (x == y);
+      else if (!ua && lu[j]) eq = (x >= 0 && y == x);
+      else eq = (y >= 0 && y == x);
+      if (eq) found = 1;
+    }
+    if (found) r[i] = 1; else { r[i] = 0; if (has_null) col_set_null(out, i, 1); }
+  }
+  return ORC_OK;
+}
+int orc_vec_filter_int(int64_t n, const orc_column *a, uint8_t *selected) {
+  /* VectorizedFilter over one int column: VecEvalBool + toBool (expression/expression.go:205-326):
+   * selected = !isNull && value != 0 */
+  for (int64_t i = 0; i < n; i++) selected[i] = (uint8_t)(!col_is_null(a, i) && col_i64(a, i) != 0);
+  return ORC_OK;
+}

@@ -1,0 +1,102 @@
+/*
+ * oracle.h — CPU restatement of the TinySQL hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product (libtinysql_b200.so) never links or calls it.
+ * Each function cites the reference file:line it restates (paths relative to
+ * /root/reference).  Parity status: pinned against the reference's own known-answer
+ * tests re-expressed in tests/test_oracle_golden.py (the Go reference cannot be built
+ * here: no Go toolchain, and the join/agg hot functions are course stubs).
+ */
+#ifndef TQ_ORACLE_H
+#define TQ_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* identical layout to tq_column (include/tinysql_b200.h) */
+typedef struct orc_column {
+  int64_t length;
+  uint8_t *null_bitmap;
+  int64_t *offsets;
+  uint8_t *data;
+} orc_column;
+
+enum { ORC_OK = 0, ORC_ERR_INVALID = 1, ORC_ERR_UNSUPPORTED = 2, ORC_ERR_OVERFLOW_BIGINT = 3,
+       ORC_ERR_OVERFLOW_BIGINT_UNSIGNED = 4, ORC_ERR_OVERFLOW_DOUBLE = 5, ORC_ERR_DIV_ZERO = 6 };
+enum { ORC_TYPE_INT64 = 1, ORC_TYPE_UINT64 = 2, ORC_TYPE_FLOAT64 = 3 };
+
+/* FNV-1 64 over flag||raw8 per key column — executor/hash_table.go:55-72 (fnv.New64),
+ * util/codec/codec.go:249-276.  Exposed for the codec known-answer tests. */
+uint64_t orc_hash_row(int n_keys, const int *types, const orc_column *cols, const int *key_idx,
+                      int64_t row, int *has_null);
+/* util/codec/codec.go:363-382 EqualChunkRow */
+int orc_equal_row(int n_keys, const int *types1, const orc_column *cols1, const int *idx1, int64_t row1,
+                  const int *types2, const orc_column *cols2, const int *idx2, int64_t row2);
+
+/* rowHashMap Put/Get — executor/hash_table.go:221-272; for the TestRowHashMap golden. */
+typedef struct orc_rowmap orc_rowmap;
+orc_rowmap *orc_rowmap_new(void);
+void orc_rowmap_put(orc_rowmap *m, uint64_t hash_key, uint32_t chk_idx, uint32_t row_idx);
+/* returns count; fills up to cap (chk_idx,row_idx) pairs in INSERTION order */
+int64_t orc_rowmap_get(orc_rowmap *m, uint64_t hash_key, uint32_t *pairs, int64_t cap);
+int64_t orc_rowmap_len(orc_rowmap *m);
+void orc_rowmap_free(orc_rowmap *m);
+
+/* HashJoinExec — executor/join.go:125-362 + Appendix B of SURVEY.md for the stubs.
+ * The inner side is given as one concatenated column set (chunking does not affect
+ * results: RowPtr order == row order).  Output columns are malloc'ed by the oracle in
+ * (probe row asc, build insertion asc) order; free with orc_free_columns. */
+int orc_hash_join(int join_type, int outer_is_right,
+                  int n_build_cols, const int *build_types, const orc_column *build_cols,
+                  int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
+                  int n_keys, const int *build_key_idx, const int *probe_key_idx,
+                  const uint8_t *selected, orc_column *out_cols, int64_t *n_out);
+void orc_free_columns(int n, orc_column *cols);
+
+/* HashAggExec — executor/aggregate.go:332-457,559-588; aggfuncs/ sources.  n_partial_workers
+ * >= 1 reproduces the partial -> shuffle -> final split: input is dealt in 1024-row chunks
+ * round-robin to the partial workers, partials are merged in worker order with
+ * MergePartialResult.  Output rows are in first-seen group order of the merge. */
+typedef struct orc_agg_func { int32_t func; int32_t arg_col; } orc_agg_func;
+int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int64_t n_rows,
+                 int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_func *funcs,
+                 int n_partial_workers, orc_column *out_cols, int64_t *n_out);
+
+/* vectorized builtins — restated statement by statement from expression/builtin_*_vec*.go */
+int orc_vec_compare_int(int op, int64_t n, const orc_column *a, int a_unsigned, const orc_column *b,
+                        int b_unsigned, orc_column *out);
+int orc_vec_compare_real(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out);
+int orc_vec_arith_int(int op, int64_t n, const orc_column *a, int a_unsigned, const orc_column *b,
+                      int b_unsigned, orc_column *out);
+int orc_vec_arith_real(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out,
+                       int64_t *div_by_zero);
+int orc_vec_logic(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out);
+int orc_vec_unary(int op, int64_t n, const orc_column *a, int a_unsigned, orc_column *out);
+int orc_vec_if(int64_t n, const orc_column *c, const orc_column *a, const orc_column *b, orc_column *out);
+int orc_vec_ifnull(int64_t n, const orc_column *a, const orc_column *b, orc_column *out);
+int orc_vec_in_int(int64_t n, const orc_column *a, int a_unsigned, int n_list, const orc_column *list,
+                   const int *list_unsigned, orc_column *out);
+int orc_vec_filter_int(int64_t n, const orc_column *a, uint8_t *selected);
+
+/* ---- multi-threaded CPU restatement of the reference *design* (cpu_ref.c): the baseline
+ * timed beside the GPU path.  Serial build + `workers` probe goroutine-equivalents over
+ * 1024-row chunks with private result chunks (join.go:194-362); returns joined rows and
+ * writes elapsed seconds (build+probe) — results are checksummed, not returned. */
+int64_t orc_mt_join_bench(int64_t n_build, const int64_t *bk, const int64_t *bv,
+                          int64_t n_probe, const int64_t *pk, const int64_t *pv,
+                          int workers, double *build_seconds, double *probe_seconds,
+                          uint64_t *checksum);
+/* P partial workers + F final workers, SUM(f64)+COUNT(*) GROUP BY int64 (aggregate.go:96-133) */
+int64_t orc_mt_agg_bench(int64_t n, const int64_t *k, const double *x, int partial_workers,
+                         int final_workers, double *seconds, double *sum_of_sums, int64_t *sum_of_counts);
+/* 1024-row-chunk LT + Plus loops (builtin_compare_vec.go:186-223, builtin_arithmetic_vec.go:389-495) */
+int64_t orc_mt_lt_plus_bench(int64_t n, const int64_t *a, const int64_t *b, int64_t *lt_out,
+                             int64_t *plus_out, int workers, double *seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,154 @@
+"""ctypes binding of oracle/liboracle.so (the CPU restatement; TEST INFRASTRUCTURE)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from tinysql_b200._lib import TQAggFunc, TQColumn
+from tinysql_b200.chunk import Chunk, Column, tq_array, unpack_not_null, _NP
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        _lib = C.CDLL(ORACLE_SO)
+        _lib.orc_hash_row.restype = C.c_uint64
+        _lib.orc_rowmap_new.restype = C.c_void_p
+        _lib.orc_rowmap_get.restype = C.c_int64
+        _lib.orc_rowmap_len.restype = C.c_int64
+        _lib.orc_mt_join_bench.restype = C.c_int64
+        _lib.orc_mt_agg_bench.restype = C.c_int64
+        _lib.orc_mt_lt_plus_bench.restype = C.c_int64
+    return _lib
+
+
+def _i32(vals):
+    return (C.c_int32 * max(len(vals), 1))(*vals)
+
+
+def _take(tq_cols, types, n):
+    """Copy oracle-malloc'ed columns into numpy-backed Columns."""
+    cols = []
+    for t, tp in zip(tq_cols, types):
+        if n:
+            vals = np.ctypeslib.as_array(C.cast(t.data, C.POINTER(C.c_uint64)), shape=(n,)).copy().view(_NP[tp])
+            bm = np.ctypeslib.as_array(C.cast(t.null_bitmap, C.POINTER(C.c_uint8)), shape=((n + 7) >> 3,)).copy()
+            cols.append(Column(tp, vals, unpack_not_null(bm, n)))
+        else:
+            cols.append(Column(tp, np.zeros(0, dtype=_NP[tp]), np.zeros(0, dtype=bool)))
+    return cols
+
+
+def hash_join(join_type, outer_is_right, build_types, build_cols, probe_types, probe_cols, build_keys, probe_keys, selected=None):
+    lib = load()
+    ncols = len(build_cols) + len(probe_cols)
+    out = (TQColumn * ncols)()
+    n = C.c_int64(0)
+    sel = None
+    if selected is not None:
+        sel = np.ascontiguousarray(selected, dtype=np.uint8)
+    rc = lib.orc_hash_join(C.c_int(join_type), C.c_int(1 if outer_is_right else 0), C.c_int(len(build_cols)), _i32(build_types),
+                           tq_array(build_cols), C.c_int(len(probe_cols)), _i32(probe_types), tq_array(probe_cols), C.c_int(len(build_keys)),
+                           _i32(build_keys), _i32(probe_keys), C.c_void_p(sel.ctypes.data) if sel is not None else None, out, C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"oracle join failed: {rc}")
+    types = (list(build_types) + list(probe_types)) if outer_is_right else (list(probe_types) + list(build_types))
+    cols = _take(out, types, n.value)
+    lib.orc_free_columns(C.c_int(ncols), out)
+    return Chunk(cols)
+
+
+def agg_out_type(func, arg_tp):
+    if func == 0:
+        return 1
+    if func in (1, 2) and arg_tp == 2:
+        return 1
+    return arg_tp
+
+
+def hash_agg(types, cols, group_by, funcs, n_partial_workers=1):
+    """returns (status, Chunk)"""
+    lib = load()
+    n_rows = cols[0].length if cols else 0
+    fa = (TQAggFunc * max(len(funcs), 1))(*[TQAggFunc(f, a) for f, a in funcs])
+    out = (TQColumn * max(len(funcs), 1))()
+    n = C.c_int64(0)
+    rc = lib.orc_hash_agg(C.c_int(len(cols)), _i32(types), tq_array(cols), C.c_int64(n_rows), C.c_int(len(group_by)), _i32(group_by),
+                          C.c_int(len(funcs)), fa, C.c_int(n_partial_workers), out, C.byref(n))
+    out_types = [agg_out_type(f, types[a] if a >= 0 else 1) for f, a in funcs]
+    res = Chunk(_take(out, out_types, n.value if rc == 0 else 0))
+    lib.orc_free_columns(C.c_int(len(funcs)), out)
+    return rc, res
+
+
+def _vec(fn, out_tp, n, *args):
+    out = Column.empty(out_tp, n)
+    to = out.tq()
+    rc = fn(*args, C.byref(to))
+    return rc, out
+
+
+def vec_compare_int(op, a, b):
+    ta, tb = a.tq(), b.tq()
+    return _vec(load().orc_vec_compare_int, 1, a.length, C.c_int(op), C.c_int64(a.length), C.byref(ta), C.c_int(a.tp == 2), C.byref(tb), C.c_int(b.tp == 2))
+
+
+def vec_compare_real(op, a, b):
+    ta, tb = a.tq(), b.tq()
+    return _vec(load().orc_vec_compare_real, 1, a.length, C.c_int(op), C.c_int64(a.length), C.byref(ta), C.byref(tb))
+
+
+def vec_arith_int(op, a, b):
+    ta, tb = a.tq(), b.tq()
+    out_tp = 2 if (a.tp == 2 or b.tp == 2) else 1
+    return _vec(load().orc_vec_arith_int, out_tp, a.length, C.c_int(op), C.c_int64(a.length), C.byref(ta), C.c_int(a.tp == 2), C.byref(tb), C.c_int(b.tp == 2))
+
+
+def vec_arith_real(op, a, b):
+    ta, tb = a.tq(), b.tq()
+    out = Column.empty(3, a.length)
+    to = out.tq()
+    dz = C.c_int64(0)
+    rc = load().orc_vec_arith_real(C.c_int(op), C.c_int64(a.length), C.byref(ta), C.byref(tb), C.byref(to), C.byref(dz))
+    return rc, out, dz.value
+
+
+def vec_logic(op, a, b):
+    ta, tb = a.tq(), b.tq()
+    return _vec(load().orc_vec_logic, 1, a.length, C.c_int(op), C.c_int64(a.length), C.byref(ta), C.byref(tb))
+
+
+def vec_unary(op, a):
+    ta = a.tq()
+    return _vec(load().orc_vec_unary, 3 if op == 3 else 1, a.length, C.c_int(op), C.c_int64(a.length), C.byref(ta), C.c_int(a.tp == 2))
+
+
+def vec_if(c, a, b):
+    tc, ta, tb = c.tq(), a.tq(), b.tq()
+    return _vec(load().orc_vec_if, a.tp, a.length, C.c_int64(a.length), C.byref(tc), C.byref(ta), C.byref(tb))
+
+
+def vec_ifnull(a, b):
+    ta, tb = a.tq(), b.tq()
+    return _vec(load().orc_vec_ifnull, a.tp, a.length, C.c_int64(a.length), C.byref(ta), C.byref(tb))
+
+
+def vec_in_int(a, lst):
+    ta = a.tq()
+    arr = tq_array(lst)
+    return _vec(load().orc_vec_in_int, 1, a.length, C.c_int64(a.length), C.byref(ta), C.c_int(a.tp == 2), C.c_int(len(lst)), arr,
+                _i32([1 if c.tp == 2 else 0 for c in lst]))
+
+
+def vec_filter_int(a):
+    ta = a.tq()
+    sel = np.zeros(max(a.length, 1), dtype=np.uint8)
+    load().orc_vec_filter_int(C.c_int64(a.length), C.byref(ta), C.c_void_p(sel.ctypes.data))
+    return sel[: a.length]

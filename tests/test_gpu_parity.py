@@ -1,0 +1,353 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for integer / key / COUNT work; SUM/AVG(float64) within 1e-9 relative (north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from tinysql_b200 import _lib as L
+from tinysql_b200 import expression as E
+from tinysql_b200.chunk import FLOAT64, INT64, UINT64, Chunk, Column
+from tinysql_b200.executor import (AGG_AVG, AGG_COUNT, AGG_FIRSTROW, AGG_MAX, AGG_MIN, AGG_SUM, INNER_JOIN, LEFT_OUTER_JOIN,
+                                   RIGHT_OUTER_JOIN, HashAggExec, HashJoinExec, MockDataSource)
+from util import assert_col_equal, assert_same_multiset, assert_same_ordered, gen_col
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 63, 64, 65, 1024, 4097, 100003]
+
+
+# ------------------------------------------------------------------ vectorized builtins
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("ta,tb", [(INT64, INT64), (UINT64, UINT64), (UINT64, INT64), (INT64, UINT64)])
+def test_compare_int(lib, n, ta, tb):
+    rng = np.random.default_rng(n * 7 + ta * 3 + tb)
+    a, b = gen_col(rng, ta, n), gen_col(rng, tb, n)
+    if n > 10:  # force ties
+        b.values[: n // 4] = a.values[: n // 4].astype(b.values.dtype)
+    for op in range(6):
+        rc, want = O.vec_compare_int(op, a, b)
+        assert rc == 0
+        assert_col_equal(E.vec_compare_int(op, a, b), want)
+
+
+@pytest.mark.parametrize("n", [0, 65, 4097])
+def test_compare_real(lib, n):
+    rng = np.random.default_rng(n)
+    a, b = gen_col(rng, FLOAT64, n), gen_col(rng, FLOAT64, n)
+    if n > 10:
+        b.values[:10] = a.values[:10]
+        a.values[10] = np.nan
+    for op in range(6):
+        rc, want = O.vec_compare_real(op, a, b)
+        assert_col_equal(E.vec_compare_real(op, a, b), want)
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("op", [E.PLUS, E.MINUS, E.MUL])
+@pytest.mark.parametrize("ta,tb", [(INT64, INT64), (UINT64, UINT64), (UINT64, INT64), (INT64, UINT64)])
+def test_arith_int_no_overflow(lib, n, op, ta, tb):
+    rng = np.random.default_rng(n + op * 11 + ta + 5 * tb)
+    lim = (1 << 30) if op == E.MUL else (1 << 61)
+    a = gen_col(rng, ta, n, lo=(0 if ta == UINT64 else -lim), hi=lim)
+    b = gen_col(rng, tb, n, lo=(0 if tb == UINT64 else -lim), hi=lim)
+    rc, want = O.vec_arith_int(op, a, b)
+    if rc == 0:
+        assert_col_equal(E.vec_arith_int(op, a, b), want)
+    else:  # e.g. unsigned minus going negative: same error kind
+        with pytest.raises(L.TQError) as ei:
+            E.vec_arith_int(op, a, b)
+        assert ei.value.status == rc
+
+
+def test_arith_int_overflow_errors(lib):
+    big = (1 << 63) - 1
+    cases = [
+        (E.PLUS, INT64, INT64, [1, big], [1, 1]),
+        (E.PLUS, INT64, INT64, [-2, -big - 1], [1, -1]),
+        (E.MINUS, INT64, INT64, [0, -big - 1], [0, 1]),
+        (E.MUL, INT64, INT64, [3, big], [3, 2]),
+        (E.MUL, INT64, INT64, [-1], [-big - 1]),  # Go's wrapping quotient hides this one: NO error in the reference
+        (E.MUL, INT64, INT64, [-big - 1], [-1]),
+        (E.PLUS, UINT64, UINT64, [np.uint64(1 << 63)], [np.uint64(1 << 63)]),
+        (E.MINUS, UINT64, UINT64, [1], [2]),
+        (E.MUL, UINT64, UINT64, [np.uint64(1 << 33)], [np.uint64(1 << 33)]),
+        (E.MINUS, UINT64, INT64, [1], [2]),
+        (E.MINUS, INT64, UINT64, [-1], [np.uint64(1 << 63)]),
+        (E.PLUS, INT64, UINT64, [-5], [3]),
+        (E.PLUS, UINT64, INT64, [3], [-5]),
+    ]
+    for op, ta, tb, av, bv in cases:
+        a, b = Column(ta, av), Column(tb, bv)
+        rc, want = O.vec_arith_int(op, a, b)
+        if rc == 0:
+            assert_col_equal(E.vec_arith_int(op, a, b), want)
+        else:
+            with pytest.raises(L.TQError) as ei:
+                E.vec_arith_int(op, a, b)
+            assert ei.value.status == rc, (op, ta, tb, av, bv)
+    # overflow on a NULL row is ignored (`if result.IsNull(i) continue`)
+    a = Column(INT64, [big, 5], [False, True])
+    b = Column(INT64, [big, 6], [True, True])
+    out = E.vec_arith_int(E.PLUS, a, b)
+    assert out.tolist() == [None, 11]
+
+
+@pytest.mark.parametrize("n", [0, 65, 4097, 100003])
+@pytest.mark.parametrize("op", [E.PLUS, E.MINUS, E.MUL, E.DIV])
+def test_arith_real(lib, n, op):
+    rng = np.random.default_rng(n + op)
+    a, b = gen_col(rng, FLOAT64, n), gen_col(rng, FLOAT64, n)
+    if n > 10:
+        b.values[3] = 0.0
+        b.values[5] = -0.0
+    rc, want, dz = O.vec_arith_real(op, a, b)
+    got, gdz = E.vec_arith_real(op, a, b)
+    assert rc == 0 and gdz == dz
+    assert_col_equal(got, want)
+
+
+def test_arith_real_overflow(lib):
+    a, b = Column(FLOAT64, [1e308]), Column(FLOAT64, [1e308])
+    for op in (E.PLUS, E.MUL):
+        with pytest.raises(L.TQError) as ei:
+            E.vec_arith_real(op, a, b)
+        assert ei.value.status == L.TQ_ERR_OVERFLOW_DOUBLE
+    with pytest.raises(L.TQError):
+        E.vec_arith_real(E.DIV, a, Column(FLOAT64, [1e-300]))
+
+
+@pytest.mark.parametrize("n", [0, 63, 4097])
+def test_logic_unary_control(lib, n):
+    rng = np.random.default_rng(n + 99)
+    a = gen_col(rng, INT64, n, lo=-1, hi=2)
+    b = gen_col(rng, INT64, n, lo=-1, hi=2)
+    c = gen_col(rng, INT64, n, lo=-5, hi=5)
+    f = gen_col(rng, FLOAT64, n)
+    if n > 4:
+        f.values[2] = 0.0
+    for op in (E.AND, E.OR):
+        assert_col_equal(E.vec_logic(op, a, b), O.vec_logic(op, a, b)[1])
+    for op, arg in ((E.NOT_INT, a), (E.NOT_REAL, f), (E.MINUS_INT, c), (E.MINUS_REAL, f), (E.ISNULL, a)):
+        rc, want = O.vec_unary(op, arg)
+        assert rc == 0
+        assert_col_equal(E.vec_unary(op, arg), want)
+    assert_col_equal(E.vec_if(a, b, c), O.vec_if(a, b, c)[1])
+    assert_col_equal(E.vec_ifnull(a, c), O.vec_ifnull(a, c)[1])
+    assert_col_equal(E.vec_if(a, f, f), O.vec_if(a, f, f)[1])
+    lst = [gen_col(rng, INT64, n, lo=-5, hi=5), gen_col(rng, UINT64, n, lo=0, hi=5), gen_col(rng, INT64, n, lo=-5, hi=5, null_frac=0)]
+    assert_col_equal(E.vec_in_int(c, lst), O.vec_in_int(c, lst)[1])
+    assert np.array_equal(E.vectorized_filter(a), O.vec_filter_int(a))
+
+
+def test_unary_minus_overflow(lib):
+    with pytest.raises(L.TQError) as ei:
+        E.vec_unary(E.MINUS_INT, Column(INT64, [1, -(1 << 63)]))
+    assert ei.value.status == L.TQ_ERR_OVERFLOW_BIGINT
+    with pytest.raises(L.TQError):
+        E.vec_unary(E.MINUS_INT, Column(UINT64, [np.uint64((1 << 63) + 1)]))
+    assert E.vec_unary(E.MINUS_INT, Column(UINT64, [np.uint64(1 << 63)])).raw()[0] == np.uint64(1 << 63)
+
+
+@pytest.mark.parametrize("n", [65, 100003, (1 << 22) + 77])
+def test_lt_plus_fused(lib, n):
+    rng = np.random.default_rng(n)
+    a, b = gen_col(rng, INT64, n), gen_col(rng, INT64, n)  # [-2^62, 2^62): builtin_arithmetic_vec_test.go:47-52
+    lt, plus = E.vec_lt_plus_int(a, b)
+    assert_col_equal(lt, O.vec_compare_int(E.LT, a, b)[1])
+    assert_col_equal(plus, O.vec_arith_int(E.PLUS, a, b)[1])
+
+
+# ------------------------------------------------------------------ hash join
+def _run_join(btypes, bcols, ptypes, pcols, jt=INNER_JOIN, outer_is_right=False, selected=None, chunk=1024, batch=0, bkey=0, pkey=0):
+    inner = MockDataSource(btypes, bcols, chunk)
+    outer = MockDataSource(ptypes, pcols, chunk)
+    filt = None
+    if selected is not None:
+        state = {"pos": 0}
+
+        def filt(chk):
+            lo = state["pos"]
+            state["pos"] += chk.num_rows()
+            return selected[lo:state["pos"]]
+    e = HashJoinExec(outer, inner, [pkey], [bkey], jt, outer_is_right, filt, batch)
+    e.Open()
+    got = e.drain()
+    e.Close()
+    want = O.hash_join(jt, outer_is_right, btypes, bcols, ptypes, pcols, [bkey], [pkey], selected)
+    return got, want
+
+
+@pytest.mark.parametrize("nb,npr", [(0, 0), (0, 100), (100, 0), (1, 1), (1000, 5000), (5000, 100000)])
+@pytest.mark.parametrize("jt,oir", [(INNER_JOIN, False), (INNER_JOIN, True), (LEFT_OUTER_JOIN, False), (RIGHT_OUTER_JOIN, True)])
+def test_join_random(lib, nb, npr, jt, oir):
+    rng = np.random.default_rng(nb * 31 + npr + jt)
+    ndv = max(nb // 3, 1)
+    bcols = [gen_col(rng, INT64, nb, 0.05, 0, ndv * 2), gen_col(rng, INT64, nb, 0.1), gen_col(rng, FLOAT64, nb, 0.1)]
+    pcols = [gen_col(rng, FLOAT64, npr, 0.1), gen_col(rng, INT64, npr, 0.05, 0, ndv * 2)]
+    got, want = _run_join([INT64, INT64, FLOAT64], bcols, [FLOAT64, INT64], pcols, jt, oir, pkey=1)
+    assert_same_multiset(got, want)
+    assert_same_ordered(got, want)  # single probe batch: (probe row asc, build insertion asc) order is kept
+
+
+def test_join_selected_and_batches(lib):
+    rng = np.random.default_rng(5)
+    nb, npr = 3000, 40000
+    bcols = [gen_col(rng, INT64, nb, 0.05, 0, 1000), gen_col(rng, INT64, nb, 0)]
+    pcols = [gen_col(rng, INT64, npr, 0.05, 0, 1500), gen_col(rng, INT64, npr, 0.3)]
+    sel = (rng.random(npr) < 0.7).astype(np.uint8)
+    for jt, oir in ((INNER_JOIN, True), (LEFT_OUTER_JOIN, False)):
+        # small device batches (4096 rows) and ragged chunk sizes exercise the accumulate / re-slice path
+        got, want = _run_join([INT64, INT64], bcols, [INT64, INT64], pcols, jt, oir, selected=sel, chunk=1000, batch=4096)
+        assert_same_multiset(got, want)
+
+
+def test_join_duplicates_large_segments(lib):
+    # 100 x 100 duplicate join (join_test.go:175-182) and a >32-row duplicate segment (bitonic path)
+    b = [Column(INT64, [7] * 100 + [8] * 3), Column(INT64, list(range(103)))]
+    p = [Column(INT64, [7] * 100 + [9]), Column(INT64, list(range(101)))]
+    got, want = _run_join([INT64, INT64], b, [INT64, INT64], p)
+    assert got.num_rows() == 10000
+    assert_same_ordered(got, want)
+    rng = np.random.default_rng(1)
+    nb = 20000
+    b = [Column(INT64, rng.integers(0, 7, nb)), Column(INT64, np.arange(nb))]
+    p = [Column(INT64, np.arange(10)), Column(INT64, np.arange(10))]
+    got, want = _run_join([INT64, INT64], b, [INT64, INT64], p)
+    assert_same_ordered(got, want)
+
+
+def test_join_signed_unsigned_keys(lib):
+    # util/codec/codec_test.go:735-769: uint64(1) == int64(1); uint64(2^64-1) != int64(-1)
+    b = [Column(UINT64, np.array([1, (1 << 64) - 1, 5], dtype=np.uint64))]
+    p = [Column(INT64, [1, -1, 5, 7])]
+    got, want = _run_join([UINT64], b, [INT64], p)
+    assert_same_ordered(got, want)
+    assert got.num_rows() == 2
+    # both unsigned: the big value matches itself
+    p2 = [Column(UINT64, np.array([(1 << 64) - 1], dtype=np.uint64))]
+    got, want = _run_join([UINT64], b, [UINT64], p2)
+    assert got.num_rows() == 1
+    # float keys: bit equality (+0.0 != -0.0; NaN == same NaN)
+    bf = [Column(FLOAT64, [0.0, np.nan, 1.5])]
+    pf = [Column(FLOAT64, [-0.0, np.nan, 1.5, 0.0])]
+    got, want = _run_join([FLOAT64], bf, [FLOAT64], pf)
+    assert_same_ordered(got, want)
+    assert got.num_rows() == 3
+    # int vs double keys never match (flags differ)
+    got, want = _run_join([FLOAT64], bf, [INT64], [Column(INT64, [0, 1])], LEFT_OUTER_JOIN)
+    assert_same_ordered(got, want)
+
+
+def test_join_sentinel_key(lib):
+    s = np.int64(np.uint64(0xA5C3F00DDEADBEEF).astype(np.int64))
+    b = [Column(INT64, [s, 1, s]), Column(INT64, [10, 11, 12])]
+    p = [Column(INT64, [s, 2, 1])]
+    got, want = _run_join([INT64, INT64], b, [INT64], p)
+    assert_same_ordered(got, want)
+    assert got.num_rows() == 3
+
+
+def test_join_early_close(lib):
+    inner = MockDataSource([INT64], [Column(INT64, np.arange(5000))])
+    outer = MockDataSource([INT64], [Column(INT64, np.arange(5000))])
+    e = HashJoinExec(outer, inner, [0], [0])
+    e.Open()
+    c = e.Next(1)  # `limit 1` then Close (join_test.go:175-182)
+    assert c.num_rows() == 1
+    e.Close()
+    e2 = HashJoinExec(outer, inner, [0], [0])
+    e2.Open()
+    e2.Close()  # Close straight after Open
+
+
+# ------------------------------------------------------------------ hash aggregation
+def _run_agg(types, cols, group_by, funcs, chunk=1024, est=0):
+    src = MockDataSource(types, cols, chunk)
+    e = HashAggExec(src, group_by, funcs, est)
+    e.Open()
+    got = e.drain()
+    e.Close()
+    return got
+
+
+def _sorted_by_key(chunk, key_idx):
+    n = chunk.num_rows()
+    nn = chunk.cols[key_idx].not_null()
+    raw = chunk.cols[key_idx].raw().copy()
+    raw[~nn] = 0
+    order = np.lexsort((raw, nn))
+    return [Column(c.tp, c.values[order], c.not_null()[order]) for c in chunk.cols]
+
+
+@pytest.mark.parametrize("n,ndv", [(0, 1), (1, 1), (5000, 10), (200000, 5000), (300000, 250000)])
+def test_agg_group_by(lib, n, ndv):
+    rng = np.random.default_rng(n + ndv)
+    k = gen_col(rng, INT64, n, 0.05, 0, ndv)
+    x = gen_col(rng, FLOAT64, n, 0.1)
+    x.values[:] = np.abs(x.values)  # no cancellation: tolerance 1e-9 relative is on SUM of same-signed terms
+    v = gen_col(rng, INT64, n, 0.1, -1000, 1000)
+    u = gen_col(rng, UINT64, n, 0.1, 0, 1 << 40)
+    types, cols = [INT64, FLOAT64, INT64, UINT64], [k, x, v, u]
+    funcs = [(AGG_SUM, 1), (AGG_COUNT, -1), (AGG_FIRSTROW, 0), (AGG_COUNT, 1), (AGG_AVG, 1), (AGG_SUM, 2), (AGG_AVG, 2), (AGG_MAX, 2),
+             (AGG_MIN, 2), (AGG_MAX, 1), (AGG_MIN, 1), (AGG_MAX, 3), (AGG_MIN, 3)]
+    got = _run_agg(types, cols, [0], funcs, est=ndv)
+    rc, want = O.hash_agg(types, cols, [0], funcs, 4)
+    assert rc == 0
+    assert got.num_rows() == want.num_rows()
+    g, w = _sorted_by_key(got, 2), _sorted_by_key(want, 2)
+    for i, (f, a) in enumerate(funcs):
+        if types[a if a >= 0 else 0] == FLOAT64 and f in (AGG_SUM, AGG_AVG):
+            assert np.array_equal(g[i].not_null(), w[i].not_null())
+            m = g[i].not_null()
+            assert np.allclose(g[i].values[m], w[i].values[m], rtol=1e-9, atol=0)
+        else:
+            assert_col_equal(g[i], w[i])
+
+
+def test_agg_scalar_and_empty(lib):
+    # aggregate_test.go:51-69: count on an empty table => 0 / sum => NULL; with GROUP BY => no rows
+    e = Column(INT64, [])
+    got = _run_agg([INT64], [e], [], [(AGG_COUNT, 0), (AGG_SUM, 0), (AGG_MAX, 0)])
+    assert got.rows() == [(0, None, None)]
+    got = _run_agg([INT64], [e], [0], [(AGG_COUNT, 0)])
+    assert got.num_rows() == 0
+    rng = np.random.default_rng(3)
+    v = gen_col(rng, INT64, 70001, 0.2, -50, 50)
+    f = Column(FLOAT64, np.abs(rng.normal(size=70001)), rng.random(70001) > 0.2)
+    funcs = [(AGG_COUNT, -1), (AGG_COUNT, 0), (AGG_SUM, 0), (AGG_AVG, 0), (AGG_MAX, 0), (AGG_MIN, 0), (AGG_SUM, 1), (AGG_AVG, 1)]
+    got = _run_agg([INT64, FLOAT64], [v, f], [], funcs)
+    rc, want = O.hash_agg([INT64, FLOAT64], [v, f], [], funcs, 3)
+    assert rc == 0 and got.num_rows() == 1
+    for i in range(6):
+        assert_col_equal(got.cols[i], want.cols[i])
+    for i in (6, 7):
+        assert np.allclose(got.cols[i].values, want.cols[i].values, rtol=1e-9)
+
+
+def test_agg_int_sum_overflow(lib):
+    big = (1 << 62)
+    v = Column(INT64, [big, big, big])
+    with pytest.raises(L.TQError) as ei:
+        _run_agg([INT64], [v], [], [(AGG_SUM, 0)])
+    assert ei.value.status == L.TQ_ERR_OVERFLOW_BIGINT
+    assert O.hash_agg([INT64], [v], [], [(AGG_SUM, 0)])[0] == 3
+    # in range once the negatives arrive: both agree when every prefix is in range
+    v2 = Column(INT64, [big, -big, big, -big, 5])
+    got = _run_agg([INT64], [v2], [], [(AGG_SUM, 0)])
+    assert got.rows() == [(5,)]
+
+
+def test_agg_table_growth(lib):
+    # est_groups far too small: the table grows several times and deferred rows are replayed
+    rng = np.random.default_rng(9)
+    n = 400000
+    k = Column(INT64, rng.integers(0, 300000, n))
+    x = Column(INT64, rng.integers(-100, 100, n))
+    funcs = [(AGG_FIRSTROW, 0), (AGG_SUM, 1), (AGG_COUNT, -1)]
+    got = _run_agg([INT64, INT64], [k, x], [0], funcs, est=1)
+    rc, want = O.hash_agg([INT64, INT64], [k, x], [0], funcs)
+    g, w = _sorted_by_key(got, 0), _sorted_by_key(want, 0)
+    for a, b in zip(g, w):
+        assert_col_equal(a, b)

@@ -1,0 +1,880 @@
+// agg.cu — HashAggExec on the device (replaces executor/aggregate.go and executor/aggfuncs).
+//
+// One open-addressed table of group keys lives in HBM/L2 (8-byte key per slot, lock-free insertion by
+// atomicCAS); aggregate states are struct-of-arrays indexed by the SLOT, so an input row costs one key
+// probe plus one L2 atomic per state word (RED.ADD.F64 / ATOM.ADD.U64 / ATOM.MAX.U64).  Rows whose
+// whole warp lands in one slot (scalar aggregates, heavy skew) are combined with warp shuffles first.
+// Partial -> final (aggregate.go:96-133) is the same kernel in "merge" mode: COUNT adds partial counts,
+// AVG adds (count, sum) pairs — the semantics of MergePartialResult.
+#include <deque>
+#include <memory>
+#include <new>
+
+#include "common.cuh"
+
+namespace tq {
+
+static constexpr int AGG_MAXC = 16;
+static constexpr int AGG_MAXF = 16;
+static constexpr uint64_t AGG_EMPTY = 0xA5C3F00DDEADBEEFull;
+static constexpr uint32_t SLOT_NONE = 0xFFFFFFFFu;
+
+enum : unsigned { AERR_BIGINT = 1u };
+
+// state words per function (all 8 bytes, zero-initialised):
+//   COUNT      w0 = count
+//   SUM  f64   w0 = sum (double bits)          w1 = non-NULL inputs seen
+//   SUM  int   w0 = sum low 64   w2 = sum high 64 (128-bit exact)   w1 = non-NULL inputs seen
+//   AVG        like SUM; w1 is the count
+//   MAX / MIN  w0 = order-mapped value (atomicMax), w1 = non-NULL inputs seen
+//   FIRSTROW   w0 = value, w1 = 1 claimed | 2 value-is-NULL (claim by atomicCAS), w2 = 1 when w0 is published
+struct AggFuncDev {
+  int func;
+  int arg_col;     // -1: constant non-NULL 1
+  int arg_col2;    // merge mode AVG: the partial-sum column (arg_col is the partial count)
+  int arg_type;    // TQ_TYPE_* of the value being aggregated
+  int key_passthrough;  // FIRSTROW over the GROUP BY column: answered from the slot key, no state
+  uint64_t *w0, *w1, *w2;
+};
+
+struct AggParams {
+  int n_cols;
+  DCol cols[AGG_MAXC];
+  int key_col;  // -1: no GROUP BY (one group)
+  int merge;    // 0: Partial1/Complete (raw rows)  1: Final (partial rows)
+  int n_funcs;
+  AggFuncDev f[AGG_MAXF];
+  uint64_t *slot_keys;
+  uint64_t mask, n_slots;     // side slots: n_slots = NULL group, n_slots+1 = the AGG_EMPTY key
+  uint32_t *side_used;        // [0] NULL group seen, [1] sentinel-key group seen
+  unsigned long long *n_used; // occupied regular slots
+  uint64_t limit;             // insertion of NEW keys stops here; such rows are deferred
+  uint32_t *deferred;
+  unsigned *n_deferred;
+  const uint32_t *row_list;   // when set: process rows row_list[0..n)
+  int64_t n;
+};
+
+__device__ __forceinline__ uint64_t order_map(uint64_t bits, int type) {
+  // monotone map into unsigned order: signed -> flip sign bit; double -> IEEE total-order trick
+  if (type == TQ_TYPE_UINT64) return bits;
+  if (type == TQ_TYPE_INT64) return bits ^ 0x8000000000000000ull;
+  return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ uint64_t order_unmap(uint64_t m, int type) {
+  if (type == TQ_TYPE_UINT64) return m;
+  if (type == TQ_TYPE_INT64) return m ^ 0x8000000000000000ull;
+  return (m >> 63) ? (m & 0x7fffffffffffffffull) : ~m;
+}
+
+__device__ __forceinline__ void add128(uint64_t *lo, uint64_t *hi, int64_t v) {
+  const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(lo), (unsigned long long)v);
+  const unsigned long long carry = (old + (unsigned long long)v) < old ? 1ull : 0ull;
+  const unsigned long long hi_add = (unsigned long long)(v >> 63) + carry;  // sign extension + carry
+  if (hi_add) atomicAdd(reinterpret_cast<unsigned long long *>(hi), hi_add);
+}
+
+__global__ void __launch_bounds__(256) k_agg_update(const AggParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_round = (p.n + 31) & ~31ll;
+  int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; it < n_round; it += stride) {  // whole warps iterate together (n_round is a multiple of 32)
+    const bool active = it < p.n;
+    int64_t r = 0;
+    uint32_t slot = SLOT_NONE;
+    if (active) {
+      r = p.row_list ? (int64_t)p.row_list[it] : it;
+      // ---- find or insert the group (getGroupKey + getPartialResult, aggregate.go:359-410)
+      if (p.key_col < 0) {
+        slot = (uint32_t)p.n_slots;
+        if (p.side_used[0] == 0) p.side_used[0] = 1;
+      } else if (!tqd::bm_not_null(p.cols[p.key_col].bm, r)) {
+        slot = (uint32_t)p.n_slots;  // NilFlag: NULL is its own group (codec.go:718-720)
+        if (p.side_used[0] == 0) p.side_used[0] = 1;
+      } else {
+        const uint64_t key = p.cols[p.key_col].data[r];
+        if (key == AGG_EMPTY) {
+          slot = (uint32_t)p.n_slots + 1;
+          if (p.side_used[1] == 0) p.side_used[1] = 1;
+        } else {
+          uint64_t idx = tqd::mix64(key) & p.mask;
+          bool defer = false;
+          for (uint64_t probes = 0;; probes++) {
+            if (probes > p.mask) { defer = true; break; }  // table full (cannot happen below `limit`)
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&p.slot_keys[idx]);
+            if (cur == key) break;
+            if (cur == AGG_EMPTY) {
+              if (*reinterpret_cast<volatile unsigned long long *>(p.n_used) >= p.limit) { defer = true; break; }
+              cur = atomicCAS(reinterpret_cast<unsigned long long *>(&p.slot_keys[idx]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
+              if (cur == AGG_EMPTY) { atomicAdd(p.n_used, 1ull); break; }
+              if (cur == key) break;
+            }
+            idx = (idx + 1) & p.mask;
+          }
+          if (defer) {
+            const unsigned pos = atomicAdd(p.n_deferred, 1u);
+            p.deferred[pos] = (uint32_t)r;
+          } else {
+            slot = (uint32_t)idx;
+          }
+        }
+      }
+    }
+    const bool live = slot != SLOT_NONE;
+    // warp-uniform group? then reduce with shuffles and let lane `leader` do the atomics
+    const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+    if (live_mask == 0) continue;
+    const int leader = __ffs(live_mask) - 1;
+    const uint32_t lead_slot = __shfl_sync(0xffffffffu, slot, leader);
+    const bool uniform = __all_sync(0xffffffffu, !live || slot == lead_slot);
+
+    for (int fi = 0; fi < p.n_funcs; fi++) {
+      const AggFuncDev &f = p.f[fi];
+      if (f.key_passthrough) continue;
+      bool nn = false;
+      uint64_t v = 1;
+      if (live) {
+        if (f.arg_col < 0) nn = true;
+        else { nn = tqd::bm_not_null(p.cols[f.arg_col].bm, r); v = p.cols[f.arg_col].data[r]; }
+      }
+      switch (f.func) {
+        case TQ_AGG_COUNT: {  // func_count.go:33-49 (raw: count non-NULL) / :99-113 (merge: add partial counts)
+          const long long add = nn ? (p.merge ? (long long)v : 1ll) : 0ll;
+          // 64-bit warp sum (counts in merge mode can exceed 32 bits)
+          if (uniform) {
+            long long s = add;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (lane == leader && s) atomicAdd(reinterpret_cast<unsigned long long *>(&f.w0[lead_slot]), (unsigned long long)s);
+          } else if (live && add) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(&f.w0[slot]), (unsigned long long)add);
+          }
+          break;
+        }
+        case TQ_AGG_SUM:
+        case TQ_AGG_AVG: {
+          // raw: func_sum.go:62-82,115-140; func_avg.go:63-83,172-190.   merge: func_sum.go:84-92,142-154; func_avg.go:93-131,200-238
+          long long cnt_add = nn ? 1ll : 0ll;
+          uint64_t val = v;
+          bool val_nn = nn;
+          if (p.merge && f.func == TQ_AGG_AVG) {
+            // partial row = (count, sum): skipped if either is NULL (func_avg.go:96-110)
+            bool nn2 = false; uint64_t v2 = 0;
+            if (live) { nn2 = tqd::bm_not_null(p.cols[f.arg_col2].bm, r); v2 = p.cols[f.arg_col2].data[r]; }
+            val_nn = nn && nn2;
+            cnt_add = val_nn ? (long long)v : 0ll;
+            val = v2;
+          }
+          if (f.arg_type == TQ_TYPE_FLOAT64) {
+            double x = val_nn ? __longlong_as_double((long long)val) : 0.0;
+            if (uniform) {
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, d); cnt_add += __shfl_xor_sync(0xffffffffu, cnt_add, d); }
+              if (lane == leader && cnt_add) {
+                atomicAdd(reinterpret_cast<double *>(&f.w0[lead_slot]), x);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&f.w1[lead_slot]), (unsigned long long)cnt_add);
+              }
+            } else if (live && val_nn) {
+              atomicAdd(reinterpret_cast<double *>(&f.w0[slot]), x);
+              atomicAdd(reinterpret_cast<unsigned long long *>(&f.w1[slot]), (unsigned long long)cnt_add);
+            }
+          } else {
+            if (live && val_nn) {  // exact 128-bit accumulation; range is checked when the group is finalised
+              add128(&f.w0[slot], &f.w2[slot], (int64_t)val);
+              atomicAdd(reinterpret_cast<unsigned long long *>(&f.w1[slot]), (unsigned long long)cnt_add);
+            }
+          }
+          break;
+        }
+        case TQ_AGG_MAX:
+        case TQ_AGG_MIN: {  // func_max_min.go:83-118 (+ Uint / Float64 twins); merge is the same comparison
+          if (live && nn) {
+            uint64_t m = order_map(v, f.arg_type);
+            if (f.func == TQ_AGG_MIN) m = ~m;
+            atomicMax(reinterpret_cast<unsigned long long *>(&f.w0[slot]), (unsigned long long)m);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&f.w1[slot]), 1ull);
+          }
+          break;
+        }
+        default: {  // FIRSTROW func_first_row.go:67-89: the first row to claim the group wins
+          if (live) {
+            const unsigned long long want = nn ? 1ull : 3ull;
+            const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&f.w1[slot]), 0ull, want);
+            if (prev == 0ull) f.w0[slot] = v;
+          }
+          break;
+        }
+      }
+    }
+  }
+}
+
+struct CollectParams {
+  int n_funcs;
+  AggFuncDev f[AGG_MAXF];
+  DColMut out[AGG_MAXF];
+  const uint64_t *slot_keys;
+  uint64_t n_slots;
+  const uint32_t *side_used;
+  unsigned long long *out_n;
+  unsigned *err;
+  int has_group_by;
+  // partial export (tq_agg_export_partial): key column + raw states instead of final values
+  int export_partial;
+  DColMut out_key;
+  DColMut out_state[2 * AGG_MAXF];
+};
+
+__device__ __forceinline__ void put_out(const DColMut &o, unsigned long long pos, uint64_t v, bool nn) {
+  o.data[pos] = v;
+  if (nn) atomicOr(&o.bm[pos >> 5], 1u << (pos & 31));
+}
+
+// getFinalResult (aggregate.go:429-457): one output row per occupied slot, AppendFinalResult2Chunk per function.
+__global__ void __launch_bounds__(256) k_agg_collect(const CollectParams p) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t total = p.n_slots + 2;
+  for (; i < total; i += stride) {
+    bool used;
+    uint64_t key = 0;
+    bool key_nn = true;
+    if (i < p.n_slots) { key = p.slot_keys[i]; used = key != AGG_EMPTY; }
+    else if (i == p.n_slots) { used = p.side_used[0] != 0; key_nn = false; }
+    else { used = p.side_used[1] != 0; key = AGG_EMPTY; }
+    if (!used) continue;
+    const unsigned long long pos = atomicAdd(p.out_n, 1ull);
+    if (p.export_partial) {
+      if (p.has_group_by) put_out(p.out_key, pos, key_nn ? key : 0, key_nn);
+      int w = 0;
+      for (int fi = 0; fi < p.n_funcs; fi++) {
+        const AggFuncDev &f = p.f[fi];
+        if (f.key_passthrough) { put_out(p.out_state[w++], pos, key_nn ? key : 0, key_nn); continue; }
+        switch (f.func) {
+          case TQ_AGG_COUNT: put_out(p.out_state[w++], pos, f.w0[i], true); break;
+          case TQ_AGG_SUM:
+          case TQ_AGG_AVG: {
+            const uint64_t cnt = f.w1[i];
+            uint64_t sum = f.w0[i];
+            if (f.arg_type != TQ_TYPE_FLOAT64) {
+              const int64_t hi = (int64_t)f.w2[i];
+              if (cnt && hi != ((int64_t)sum >> 63)) atomicOr(p.err, AERR_BIGINT);
+            }
+            if (f.func == TQ_AGG_AVG) put_out(p.out_state[w++], pos, cnt, true);   // AVG partial = (count, sum) descriptor.go:57-92
+            put_out(p.out_state[w++], pos, cnt ? sum : 0, cnt != 0);
+            break;
+          }
+          case TQ_AGG_MAX:
+          case TQ_AGG_MIN: {
+            const uint64_t cnt = f.w1[i];
+            uint64_t m = f.w0[i];
+            if (f.func == TQ_AGG_MIN) m = ~m;
+            put_out(p.out_state[w++], pos, cnt ? order_unmap(m, f.arg_type) : 0, cnt != 0);
+            break;
+          }
+          default: {
+            const uint64_t st = f.w1[i];
+            put_out(p.out_state[w++], pos, (st == 1) ? f.w0[i] : 0, st == 1);
+            break;
+          }
+        }
+      }
+      continue;
+    }
+    for (int fi = 0; fi < p.n_funcs; fi++) {
+      const AggFuncDev &f = p.f[fi];
+      if (f.key_passthrough) { put_out(p.out[fi], pos, key_nn ? key : 0, key_nn); continue; }
+      switch (f.func) {
+        case TQ_AGG_COUNT: put_out(p.out[fi], pos, f.w0[i], true); break;            // func_count.go:23-27
+        case TQ_AGG_SUM: {                                                          // func_sum.go:53-60,104-113
+          const uint64_t cnt = f.w1[i];
+          if (cnt == 0) { put_out(p.out[fi], pos, 0, false); break; }
+          if (f.arg_type != TQ_TYPE_FLOAT64) {
+            const int64_t hi = (int64_t)f.w2[i];
+            if (hi != ((int64_t)f.w0[i] >> 63)) atomicOr(p.err, AERR_BIGINT);    // types.AddInt64 overflow (types/overflow.go:33-40)
+          }
+          put_out(p.out[fi], pos, f.w0[i], true);
+          break;
+        }
+        case TQ_AGG_AVG: {                                                          // func_avg.go:47-55,159-167
+          const int64_t cnt = (int64_t)f.w1[i];
+          if (cnt == 0) { put_out(p.out[fi], pos, 0, false); break; }
+          if (f.arg_type == TQ_TYPE_FLOAT64) {
+            const double r = __longlong_as_double((long long)f.w0[i]) / (double)cnt;
+            put_out(p.out[fi], pos, (uint64_t)__double_as_longlong(r), true);
+          } else {
+            const int64_t hi = (int64_t)f.w2[i];
+            const int64_t sum = (int64_t)f.w0[i];
+            if (hi != (sum >> 63)) atomicOr(p.err, AERR_BIGINT);
+            put_out(p.out[fi], pos, (uint64_t)(sum / cnt), true);                   // Go truncating division
+          }
+          break;
+        }
+        case TQ_AGG_MAX:
+        case TQ_AGG_MIN: {                                                          // func_max_min.go:73-81
+          const uint64_t cnt = f.w1[i];
+          uint64_t m = f.w0[i];
+          if (f.func == TQ_AGG_MIN) m = ~m;
+          put_out(p.out[fi], pos, cnt ? order_unmap(m, f.arg_type) : 0, cnt != 0);
+          break;
+        }
+        default: {                                                                  // func_first_row.go:91-99
+          const uint64_t st = f.w1[i];
+          put_out(p.out[fi], pos, (st == 1) ? f.w0[i] : 0, st == 1);
+          break;
+        }
+      }
+    }
+  }
+}
+
+__global__ void k_fill_u64(uint64_t *p, uint64_t n, uint64_t v) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// Move every occupied slot (key + all state words) of the old table into the new, larger one.
+__global__ void __launch_bounds__(256) k_agg_rehash(const uint64_t *old_keys, uint64_t old_slots, const uint64_t *old_state, uint64_t *new_keys,
+                                                     uint64_t new_mask, uint64_t *new_state, int n_words) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t old_total = old_slots + 2, new_total = new_mask + 1 + 2;
+  for (; i < old_total; i += stride) {
+    uint64_t dst;
+    if (i >= old_slots) dst = (new_mask + 1) + (i - old_slots);  // side slots keep their role
+    else {
+      const uint64_t key = old_keys[i];
+      if (key == AGG_EMPTY) continue;
+      uint64_t idx = tqd::mix64(key) & new_mask;
+      for (;;) {
+        const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&new_keys[idx]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
+        if (prev == AGG_EMPTY) break;
+        idx = (idx + 1) & new_mask;
+      }
+      dst = idx;
+    }
+    for (int w = 0; w < n_words; w++) new_state[(uint64_t)w * new_total + dst] = old_state[(uint64_t)w * old_total + i];
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct AggHostAccum {
+  PinBuf data, bm;
+  int64_t n = 0, cap = 0;
+  bool has_bm = false;
+};
+
+}  // namespace tq
+
+using namespace tq;
+
+struct AggResult {
+  std::vector<DevBuf> data, bm;
+  std::vector<PinBuf> h_data, h_bm;
+  int64_t n = 0;
+  bool on_host = false;
+};
+
+struct tq_agg {
+  int n_cols = 0, n_group_by = 0, n_funcs = 0;
+  int types[AGG_MAXC];
+  int key_col = -1;
+  tq_agg_func funcs[AGG_MAXF];
+  int arg_type[AGG_MAXF];
+  int out_type[AGG_MAXF];
+  int key_passthrough[AGG_MAXF];
+  int word_base[AGG_MAXF];  // first state word of function i
+  int n_words = 0;
+  int64_t est_groups = 0;
+  int64_t batch_rows = 1 << 22;
+
+  // table
+  DevBuf keys, state, meta;   // meta: [0..1] side_used u32, [2] n_deferred u32, [3] err u32, u64@16 n_used, u64@24 out_n
+  uint64_t n_slots = 0;
+  DevBuf deferred;
+  PinBuf meta_host;
+  // host staging (double-buffered)
+  struct Stage { std::vector<PinBuf> data, bm; std::vector<bool> has_bm; int64_t n = 0; std::vector<DevBuf> d_data, d_bm; cudaEvent_t ev_done = nullptr; bool in_flight = false; } stage[2];
+  int cur_stage = 0;
+  int64_t rows_total = 0, launches = 0, last_update_ns = 0;
+  bool eof = false, finalized = false, closed = false;
+  bool merge_mode_seen = false, raw_mode_seen = false;
+  AggResult result;
+  int64_t result_pos = 0;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  ~tq_agg() {
+    for (auto &s : stage) if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
+  }
+};
+
+namespace tq {
+
+static int agg_grid(int64_t n) {
+  const int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)rt().sm_count * 8;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+static int words_of(int func, int arg_type) {
+  switch (func) {
+    case TQ_AGG_COUNT: return 1;
+    case TQ_AGG_SUM: case TQ_AGG_AVG: return arg_type == TQ_TYPE_FLOAT64 ? 2 : 3;
+    case TQ_AGG_MAX: case TQ_AGG_MIN: return 2;
+    default: return 2;
+  }
+}
+
+static int32_t agg_alloc_table(tq_agg *a, uint64_t n_slots) {
+  cudaStream_t s = rt().compute;
+  a->n_slots = n_slots;
+  const uint64_t total = n_slots + 2;
+  TQ_TRY(a->keys.reserve(total * 8));
+  TQ_TRY(a->state.reserve((size_t)(a->n_words ? a->n_words : 1) * total * 8));
+  k_fill_u64<<<agg_grid((int64_t)n_slots), 256, 0, s>>>(a->keys.as<uint64_t>(), n_slots, AGG_EMPTY);
+  count_launch();
+  TQ_CUDA(cudaMemsetAsync(a->state.p, 0, (size_t)(a->n_words ? a->n_words : 1) * total * 8, s));
+  return check_launch("k_fill_u64");
+}
+
+static void fill_funcs(tq_agg *a, AggFuncDev *f, uint64_t *state_base, uint64_t total, bool merge) {
+  int pcol = a->n_group_by;  // merge-mode input layout: key cols, then partial-state columns in function order
+  for (int i = 0; i < a->n_funcs; i++) {
+    AggFuncDev &d = f[i];
+    d.func = a->funcs[i].func;
+    d.arg_type = a->arg_type[i];
+    d.key_passthrough = a->key_passthrough[i];
+    d.arg_col = a->funcs[i].arg_col;
+    d.arg_col2 = -1;
+    if (merge) {
+      d.arg_col = pcol++;
+      if (d.func == TQ_AGG_AVG && !d.key_passthrough) d.arg_col2 = pcol++;
+    }
+    const int wb = a->word_base[i];
+    d.w0 = state_base + (uint64_t)wb * total;
+    d.w1 = state_base + (uint64_t)(wb + 1) * total;
+    d.w2 = state_base + (uint64_t)(wb + 2) * total;
+  }
+}
+
+static int32_t agg_grow(tq_agg *a, uint64_t new_slots) {
+  cudaStream_t s = rt().compute;
+  DevBuf old_keys = std::move(a->keys), old_state = std::move(a->state);
+  const uint64_t old_slots = a->n_slots;
+  TQ_TRY(agg_alloc_table(a, new_slots));
+  k_agg_rehash<<<agg_grid((int64_t)old_slots + 2), 256, 0, s>>>(old_keys.as<uint64_t>(), old_slots, old_state.as<uint64_t>(), a->keys.as<uint64_t>(),
+                                                                new_slots - 1, a->state.as<uint64_t>(), a->n_words);
+  count_launch();
+  TQ_TRY(check_launch("k_agg_rehash"));
+  TQ_CUDA(cudaStreamSynchronize(s));  // old buffers are freed when this scope ends
+  return TQ_OK;
+}
+
+// Run the update kernel over device columns; handles deferred rows by growing the table.
+static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int64_t n, bool merge) {
+  if (n == 0) return TQ_OK;
+  Runtime &r = rt();
+  cudaStream_t s = r.compute;
+  if (a->n_slots == 0) {
+    uint64_t want = 1 << 16;
+    const uint64_t hint = a->est_groups > 0 ? (uint64_t)a->est_groups : 0;
+    while (want < hint * 4) want <<= 1;
+    TQ_TRY(agg_alloc_table(a, want));
+    TQ_CUDA(cudaMemsetAsync(a->meta.p, 0, 64, s));
+  }
+  if (n > 0xFFFFFFF0ll) { set_error("aggregate batch too large"); return TQ_ERR_INVALID_ARG; }
+  TQ_TRY(a->deferred.reserve((size_t)n * 4));
+  uint32_t *meta32 = a->meta.as<uint32_t>();
+  unsigned long long *meta64 = reinterpret_cast<unsigned long long *>(a->meta.as<uint8_t>() + 16);
+  const uint32_t *row_list = nullptr;
+  DevBuf row_list_buf;
+  int64_t todo = n;
+  TQ_CUDA(cudaEventRecord(a->ev_a, s));
+  for (int round = 0; round < 64; round++) {
+    AggParams p{};
+    p.n_cols = n_in_cols;
+    for (int c = 0; c < n_in_cols; c++) p.cols[c] = cols[c];
+    p.key_col = a->n_group_by ? (merge ? 0 : a->key_col) : -1;
+    p.merge = merge ? 1 : 0;
+    p.n_funcs = a->n_funcs;
+    const uint64_t total = a->n_slots + 2;
+    fill_funcs(a, p.f, a->state.as<uint64_t>(), total, merge);
+    p.slot_keys = a->keys.as<uint64_t>();
+    p.mask = a->n_slots - 1;
+    p.n_slots = a->n_slots;
+    p.side_used = meta32;
+    p.n_used = meta64;
+    p.limit = a->n_slots / 2;
+    p.deferred = a->deferred.as<uint32_t>();
+    p.n_deferred = meta32 + 2;
+    p.row_list = row_list;
+    p.n = todo;
+    TQ_CUDA(cudaMemsetAsync(meta32 + 2, 0, 4, s));
+    k_agg_update<<<agg_grid(todo), 256, 0, s>>>(p);
+    count_launch();
+    a->launches++;
+    TQ_TRY(check_launch("k_agg_update"));
+    if (round == 0) TQ_CUDA(cudaEventRecord(a->ev_b, s));
+    TQ_CUDA(cudaMemcpyAsync(a->meta_host.p, a->meta.p, 64, cudaMemcpyDeviceToHost, s));
+    TQ_CUDA(cudaStreamSynchronize(s));
+    const uint32_t n_def = a->meta_host.as<uint32_t>()[2];
+    if (round == 0) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, a->ev_a, a->ev_b) == cudaSuccess) a->last_update_ns = (int64_t)(ms * 1e6);
+    }
+    if (n_def == 0) return TQ_OK;
+    // the table reached its load limit: grow 4x (at least enough for every deferred row) and redo only those rows
+    const uint64_t used = *reinterpret_cast<unsigned long long *>(a->meta_host.as<uint8_t>() + 16);
+    uint64_t want = a->n_slots * 4;
+    while (want / 2 < used + n_def) want <<= 1;
+    TQ_TRY(agg_grow(a, want));
+    TQ_TRY(row_list_buf.reserve((size_t)n_def * 4));
+    TQ_CUDA(cudaMemcpyAsync(row_list_buf.p, a->deferred.p, (size_t)n_def * 4, cudaMemcpyDeviceToDevice, s));
+    row_list = row_list_buf.as<uint32_t>();
+    todo = n_def;
+  }
+  set_error("aggregate table failed to converge");
+  return TQ_ERR_CUDA;
+}
+
+static int32_t agg_flush_stage(tq_agg *a, bool merge, int n_in_cols) {
+  tq_agg::Stage &st = a->stage[a->cur_stage];
+  if (st.n == 0) return TQ_OK;
+  Runtime &r = rt();
+  st.d_data.resize(n_in_cols);
+  st.d_bm.resize(n_in_cols);
+  std::vector<DCol> view(n_in_cols);
+  for (int c = 0; c < n_in_cols; c++) {
+    TQ_TRY(st.d_data[c].reserve((size_t)st.n * 8));
+    TQ_CUDA(cudaMemcpyAsync(st.d_data[c].p, st.data[c].p, (size_t)st.n * 8, cudaMemcpyHostToDevice, r.compute));
+    view[c].data = st.d_data[c].as<uint64_t>();
+    view[c].bm = nullptr;
+    if (st.has_bm[c]) {
+      TQ_TRY(st.d_bm[c].reserve(bitmap_alloc_bytes(st.n)));
+      TQ_CUDA(cudaMemcpyAsync(st.d_bm[c].p, st.bm[c].p, bitmap_bytes(st.n), cudaMemcpyHostToDevice, r.compute));
+      view[c].bm = st.d_bm[c].as<uint32_t>();
+    }
+  }
+  const int64_t n = st.n;
+  st.n = 0;
+  for (int c = 0; c < n_in_cols; c++) st.has_bm[c] = false;
+  a->cur_stage ^= 1;  // (agg_update_device synchronises; the flip keeps the door open for async overlap)
+  return agg_update_device(a, view.data(), n_in_cols, n, merge);
+}
+
+static int32_t agg_put_common(tq_agg *a, const tq_column *cols, int32_t mem, bool merge, int n_in_cols) {
+  if (!a || !cols) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(ensure_init());
+  if (a->eof) { set_error("put after eof"); return TQ_ERR_STATE; }
+  if ((merge && a->raw_mode_seen) || (!merge && a->merge_mode_seen)) { set_error("one handle cannot mix raw rows and partial rows"); return TQ_ERR_STATE; }
+  (merge ? a->merge_mode_seen : a->raw_mode_seen) = true;
+  const int64_t rows = cols[0].length;
+  if (rows < 0) return TQ_ERR_INVALID_ARG;
+  for (int c = 0; c < n_in_cols; c++) {
+    if (cols[c].length != rows) { set_error("ragged aggregate input chunk"); return TQ_ERR_INVALID_ARG; }
+    if (cols[c].offsets) { set_error("unsupport column type for encode (var-len column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
+    if (rows && !cols[c].data) return TQ_ERR_INVALID_ARG;
+  }
+  if (rows == 0) return TQ_OK;
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  a->rows_total += rows;
+  if (mem == TQ_MEM_DEVICE) {
+    TQ_TRY(agg_flush_stage(a, merge, n_in_cols));
+    std::vector<DCol> view(n_in_cols);
+    for (int c = 0; c < n_in_cols; c++) { view[c].data = (const uint64_t *)cols[c].data; view[c].bm = (const uint32_t *)cols[c].null_bitmap; }
+    return agg_update_device(a, view.data(), n_in_cols, rows, merge);
+  }
+  // host chunks accumulate in pinned staging until a device batch is full
+  int64_t done = 0;
+  while (done < rows) {
+    tq_agg::Stage &st = a->stage[a->cur_stage];
+    if ((int)st.data.size() != n_in_cols) { st.data.resize(n_in_cols); st.bm.resize(n_in_cols); st.has_bm.assign(n_in_cols, false); }
+    int64_t room = a->batch_rows - st.n;
+    if (room <= 0) { TQ_TRY(agg_flush_stage(a, merge, n_in_cols)); continue; }
+    int64_t take = rows - done < room ? rows - done : room;
+    if (take < rows - done) take &= ~7ll;  // keep source bitmap offsets byte aligned when a chunk is split
+    if (take == 0) { TQ_TRY(agg_flush_stage(a, merge, n_in_cols)); continue; }
+    for (int c = 0; c < n_in_cols; c++) {
+      if (st.data[c].cap < (size_t)a->batch_rows * 8) TQ_TRY(st.data[c].reserve((size_t)a->batch_rows * 8));
+      if (st.bm[c].cap < bitmap_alloc_bytes(a->batch_rows)) { TQ_TRY(st.bm[c].reserve(bitmap_alloc_bytes(a->batch_rows))); }
+      memcpy(st.data[c].as<uint8_t>() + st.n * 8, cols[c].data + done * 8, (size_t)take * 8);
+      if (cols[c].null_bitmap && !st.has_bm[c]) { host_bitmap_append(st.bm[c].as<uint8_t>(), 0, nullptr, st.n); st.has_bm[c] = true; }
+      if (st.has_bm[c]) {
+        if (cols[c].null_bitmap) {
+          // source offset `done` is a multiple of 8 by construction
+          host_bitmap_append(st.bm[c].as<uint8_t>(), st.n, cols[c].null_bitmap + (done >> 3), take);
+        } else host_bitmap_append(st.bm[c].as<uint8_t>(), st.n, nullptr, take);
+      }
+    }
+    st.n += take;
+    done += take;
+  }
+  return TQ_OK;
+}
+
+static int32_t agg_finalize(tq_agg *a, bool export_partial, AggResult &res, int n_out_cols) {
+  Runtime &r = rt();
+  cudaStream_t s = r.compute;
+  res.data.resize(n_out_cols);
+  res.bm.resize(n_out_cols);
+  res.n = 0;
+  res.on_host = false;
+  if (a->n_slots == 0) return TQ_OK;  // no input at all
+  TQ_CUDA(cudaMemcpyAsync(a->meta_host.p, a->meta.p, 64, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaStreamSynchronize(s));
+  const uint32_t *m32 = a->meta_host.as<uint32_t>();
+  const uint64_t used = *reinterpret_cast<unsigned long long *>(a->meta_host.as<uint8_t>() + 16);
+  const int64_t groups = (int64_t)used + (m32[0] ? 1 : 0) + (m32[1] ? 1 : 0);
+  CollectParams p{};
+  p.n_funcs = a->n_funcs;
+  fill_funcs(a, p.f, a->state.as<uint64_t>(), a->n_slots + 2, false);
+  for (int c = 0; c < n_out_cols; c++) {
+    TQ_TRY(res.data[c].reserve((size_t)(groups ? groups : 1) * 8));
+    TQ_TRY(res.bm[c].reserve(bitmap_alloc_bytes(groups)));
+    TQ_CUDA(cudaMemsetAsync(res.bm[c].p, 0, bitmap_alloc_bytes(groups), s));
+  }
+  if (export_partial) {
+    p.export_partial = 1;
+    int c = 0;
+    if (a->n_group_by) { p.out_key.data = res.data[c].as<uint64_t>(); p.out_key.bm = res.bm[c].as<uint32_t>(); c++; }
+    for (int w = 0; c < n_out_cols; c++, w++) { p.out_state[w].data = res.data[c].as<uint64_t>(); p.out_state[w].bm = res.bm[c].as<uint32_t>(); }
+  } else {
+    for (int c = 0; c < n_out_cols; c++) { p.out[c].data = res.data[c].as<uint64_t>(); p.out[c].bm = res.bm[c].as<uint32_t>(); }
+  }
+  p.slot_keys = a->keys.as<uint64_t>();
+  p.n_slots = a->n_slots;
+  p.side_used = a->meta.as<uint32_t>();
+  p.out_n = reinterpret_cast<unsigned long long *>(a->meta.as<uint8_t>() + 24);
+  p.err = a->meta.as<uint32_t>() + 3;
+  p.has_group_by = a->n_group_by ? 1 : 0;
+  TQ_CUDA(cudaMemsetAsync(a->meta.as<uint8_t>() + 24, 0, 8, s));
+  TQ_CUDA(cudaMemsetAsync(a->meta.as<uint32_t>() + 3, 0, 4, s));
+  k_agg_collect<<<agg_grid((int64_t)a->n_slots + 2), 256, 0, s>>>(p);
+  count_launch();
+  a->launches++;
+  TQ_TRY(check_launch("k_agg_collect"));
+  TQ_CUDA(cudaMemcpyAsync(a->meta_host.p, a->meta.p, 64, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaStreamSynchronize(s));
+  const uint64_t out_n = *reinterpret_cast<unsigned long long *>(a->meta_host.as<uint8_t>() + 24);
+  if ((int64_t)out_n != groups) { set_error("internal: collected %llu groups, expected %lld", (unsigned long long)out_n, (long long)groups); return TQ_ERR_CUDA; }
+  if (a->meta_host.as<uint32_t>()[3] & AERR_BIGINT) { set_error("BIGINT value is out of range in 'sum'"); return TQ_ERR_OVERFLOW_BIGINT; }
+  res.n = groups;
+  return TQ_OK;
+}
+
+static int partial_width(const tq_agg *a) {
+  int w = a->n_group_by;
+  for (int i = 0; i < a->n_funcs; i++) w += (a->funcs[i].func == TQ_AGG_AVG && !a->key_passthrough[i]) ? 2 : 1;
+  return w;
+}
+
+}  // namespace tq
+
+extern "C" {
+
+int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
+  if (!d || !out) return TQ_ERR_INVALID_ARG;
+  *out = nullptr;
+  TQ_TRY(ensure_init());
+  if (d->n_input_cols < 0 || d->n_input_cols > AGG_MAXC || d->n_funcs < 0 || d->n_funcs > AGG_MAXF) { set_error("too many columns / functions"); return TQ_ERR_INVALID_ARG; }
+  if (d->n_group_by < 0) return TQ_ERR_INVALID_ARG;
+  if (d->n_group_by > 1) { set_error("GROUP BY over %d items: only zero or one GROUP BY column is implemented", d->n_group_by); return TQ_ERR_UNSUPPORTED_TYPE; }
+  for (int c = 0; c < d->n_input_cols; c++) {
+    const int t = d->input_types[c];
+    if (t != TQ_TYPE_INT64 && t != TQ_TYPE_UINT64 && t != TQ_TYPE_FLOAT64) { set_error("unsupport column type for encode %d", t); return TQ_ERR_UNSUPPORTED_TYPE; }
+  }
+  tq_agg *a = new (std::nothrow) tq_agg();
+  if (!a) return TQ_ERR_OOM;
+  a->n_cols = d->n_input_cols;
+  a->n_group_by = d->n_group_by;
+  a->n_funcs = d->n_funcs;
+  a->est_groups = d->est_groups;
+  for (int c = 0; c < a->n_cols; c++) a->types[c] = d->input_types[c];
+  if (a->n_group_by) {
+    a->key_col = d->group_by_cols[0];
+    if (a->key_col < 0 || a->key_col >= a->n_cols) { delete a; return TQ_ERR_INVALID_ARG; }
+  }
+  int words = 0;
+  for (int i = 0; i < a->n_funcs; i++) {
+    a->funcs[i] = d->funcs[i];
+    const int fn = a->funcs[i].func, ac = a->funcs[i].arg_col;
+    if (fn < TQ_AGG_COUNT || fn > TQ_AGG_FIRSTROW || ac >= a->n_cols || ((fn == TQ_AGG_MAX || fn == TQ_AGG_MIN) && ac < 0)) {
+      set_error("bad aggregate descriptor %d", i);
+      delete a;
+      return TQ_ERR_INVALID_ARG;
+    }
+    a->arg_type[i] = ac >= 0 ? a->types[ac] : TQ_TYPE_INT64;
+    if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->arg_type[i] == TQ_TYPE_UINT64) a->arg_type[i] = TQ_TYPE_INT64;  // sum4Int64 reads EvalInt (func_sum.go:118)
+    a->out_type[i] = fn == TQ_AGG_COUNT ? TQ_TYPE_INT64 : (ac >= 0 ? a->types[ac] : TQ_TYPE_INT64);
+    if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->out_type[i] == TQ_TYPE_UINT64) a->out_type[i] = TQ_TYPE_INT64;
+    a->key_passthrough[i] = (fn == TQ_AGG_FIRSTROW && a->n_group_by && ac == a->key_col) ? 1 : 0;
+    a->word_base[i] = words;
+    words += a->key_passthrough[i] ? 0 : 3;  // three words reserved per function keeps w0/w1/w2 addressing uniform
+  }
+  a->n_words = words;
+  int32_t st = a->meta.reserve(64);
+  if (st == TQ_OK) st = a->meta_host.reserve(64);
+  cudaError_t e = cudaEventCreate(&a->ev_a);
+  if (e == cudaSuccess) e = cudaEventCreate(&a->ev_b);
+  if (st == TQ_OK && e != cudaSuccess) st = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
+  if (st != TQ_OK) { delete a; return st; }
+  *out = a;
+  return TQ_OK;
+}
+
+int32_t tq_agg_output_type(tq_agg *a, int32_t i, int32_t *t) {
+  if (!a || !t || i < 0 || i >= a->n_funcs) return TQ_ERR_INVALID_ARG;
+  *t = a->out_type[i];
+  return TQ_OK;
+}
+
+int32_t tq_agg_put(tq_agg *a, const tq_column *cols, int32_t mem) {
+  if (!a) return TQ_ERR_INVALID_ARG;
+  return agg_put_common(a, cols, mem, false, a->n_cols);
+}
+
+int32_t tq_agg_merge_partial(tq_agg *a, const tq_column *cols, int32_t mem) {
+  if (!a) return TQ_ERR_INVALID_ARG;
+  return agg_put_common(a, cols, mem, true, partial_width(a));
+}
+
+int32_t tq_agg_partial_width(tq_agg *a, int32_t *n) {
+  if (!a || !n) return TQ_ERR_INVALID_ARG;
+  *n = partial_width(a);
+  return TQ_OK;
+}
+
+int32_t tq_agg_eof(tq_agg *a) {
+  if (!a) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(ensure_init());
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  if (a->eof) return TQ_OK;
+  const bool merge = a->merge_mode_seen;
+  TQ_TRY(agg_flush_stage(a, merge, merge ? partial_width(a) : a->n_cols));
+  a->eof = true;
+  return TQ_OK;
+}
+
+static int32_t agg_ensure_final(tq_agg *a) {
+  if (a->finalized) return TQ_OK;
+  if (!a->eof) { set_error("next before eof: HashAgg is a pipeline breaker"); return TQ_ERR_STATE; }
+  TQ_TRY(agg_finalize(a, false, a->result, a->n_funcs));
+  a->finalized = true;
+  a->result_pos = 0;
+  return TQ_OK;
+}
+
+int32_t tq_agg_next(tq_agg *a, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof) {
+  if (!a || !n_rows || !eof || max_rows <= 0 || (a->n_funcs && !out_cols)) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(ensure_init());
+  *n_rows = 0;
+  *eof = 0;
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  TQ_TRY(agg_ensure_final(a));
+  AggResult &res = a->result;
+  // empty input without GROUP BY: one default row — COUNT 0, everything else NULL (aggregate.go:572-574,
+  // builder.go:517-540); all-FIRSTROW aggregates produce no row
+  if (a->rows_total == 0 && a->n_group_by == 0 && a->result_pos == 0) {
+    bool all_first = true;
+    for (int i = 0; i < a->n_funcs; i++) if (a->funcs[i].func != TQ_AGG_FIRSTROW) all_first = false;
+    a->result_pos = 1;
+    if (!all_first && a->n_funcs) {
+      for (int i = 0; i < a->n_funcs; i++) {
+        if (!out_cols[i].data || !out_cols[i].null_bitmap) return TQ_ERR_INVALID_ARG;
+        memset(out_cols[i].data, 0, 8);
+        out_cols[i].null_bitmap[0] = (a->funcs[i].func == TQ_AGG_COUNT) ? 1 : 0;
+        out_cols[i].length = 1;
+      }
+      *n_rows = 1;
+      return TQ_OK;
+    }
+  }
+  if (a->rows_total == 0 || a->result_pos >= res.n) { *eof = 1; for (int i = 0; i < a->n_funcs; i++) out_cols[i].length = 0; return TQ_OK; }
+  if (!res.on_host) {
+    res.h_data.resize(a->n_funcs);
+    res.h_bm.resize(a->n_funcs);
+    for (int c = 0; c < a->n_funcs; c++) {
+      TQ_TRY(res.h_data[c].reserve((size_t)res.n * 8));
+      TQ_TRY(res.h_bm[c].reserve(bitmap_alloc_bytes(res.n)));
+      TQ_CUDA(cudaMemcpyAsync(res.h_data[c].p, res.data[c].p, (size_t)res.n * 8, cudaMemcpyDeviceToHost, r.compute));
+      TQ_CUDA(cudaMemcpyAsync(res.h_bm[c].p, res.bm[c].p, bitmap_bytes(res.n), cudaMemcpyDeviceToHost, r.compute));
+    }
+    TQ_CUDA(cudaStreamSynchronize(r.compute));
+    res.on_host = true;
+  }
+  const int64_t take = res.n - a->result_pos < max_rows ? res.n - a->result_pos : max_rows;
+  for (int c = 0; c < a->n_funcs; c++) {
+    if (!out_cols[c].data || !out_cols[c].null_bitmap) { set_error("output column %d needs data and null_bitmap buffers", c); return TQ_ERR_INVALID_ARG; }
+    memcpy(out_cols[c].data, res.h_data[c].as<uint8_t>() + a->result_pos * 8, (size_t)take * 8);
+    host_bitmap_extract(out_cols[c].null_bitmap, res.h_bm[c].as<uint8_t>(), a->result_pos, take);
+    out_cols[c].length = take;
+  }
+  a->result_pos += take;
+  *n_rows = take;
+  return TQ_OK;
+}
+
+int32_t tq_agg_next_device(tq_agg *a, tq_column *out_cols, int64_t *n_rows, int32_t *eof) {
+  if (!a || !out_cols || !n_rows || !eof) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(ensure_init());
+  *n_rows = 0;
+  *eof = 0;
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  TQ_TRY(agg_ensure_final(a));
+  if (a->result_pos > 0 || a->result.n == 0) { *eof = 1; return TQ_OK; }
+  for (int c = 0; c < a->n_funcs; c++) {
+    out_cols[c].length = a->result.n;
+    out_cols[c].data = a->result.data[c].as<uint8_t>();
+    out_cols[c].null_bitmap = a->result.bm[c].as<uint8_t>();
+    out_cols[c].offsets = nullptr;
+  }
+  *n_rows = a->result.n;
+  a->result_pos = a->result.n;
+  return TQ_OK;
+}
+
+int32_t tq_agg_export_partial(tq_agg *a, tq_column *out_cols, int64_t *n_rows) {
+  if (!a || !out_cols || !n_rows) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(ensure_init());
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  if (!a->eof) TQ_TRY(tq_agg_eof(a));
+  const int w = partial_width(a);
+  TQ_TRY(agg_finalize(a, true, a->result, w));
+  for (int c = 0; c < w; c++) {
+    out_cols[c].length = a->result.n;
+    out_cols[c].data = a->result.data[c].as<uint8_t>();
+    out_cols[c].null_bitmap = a->result.bm[c].as<uint8_t>();
+    out_cols[c].offsets = nullptr;
+  }
+  *n_rows = a->result.n;
+  return TQ_OK;
+}
+
+int32_t tq_agg_stats(tq_agg *a, int64_t *s) {
+  if (!a || !s) return TQ_ERR_INVALID_ARG;
+  s[0] = a->rows_total;
+  s[1] = a->result.n;
+  s[2] = a->last_update_ns;
+  s[3] = a->launches;
+  return TQ_OK;
+}
+
+int32_t tq_agg_destroy(tq_agg *a) {
+  if (!a) return TQ_OK;
+  if (rt().inited) {
+    cudaSetDevice(rt().device);
+    cudaDeviceSynchronize();  // Close may run after Open without Next (aggregate.go:187-197)
+  }
+  delete a;
+  return TQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's operator interface for the hot path:
+executor.Executor{Open, Next, Close} (executor/executor.go:146-162) for HashJoinExec
+(executor/join.go) and HashAggExec (executor/aggregate.go), driving the C-ABI exactly the way the
+Go shim in INTEGRATION.md does: children hand up <=1024-row chunks, Next fills <=requiredRows rows,
+0 rows == end of stream.  All operator logic (batching, hashing, matching, aggregation, re-slicing)
+is inside libtinysql_b200.so; nothing here computes results.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .chunk import (FLOAT64, INT64, MAX_CHUNK_SIZE, UINT64, Chunk, Column, DeviceColumn, device_to_host, tq_array)
+
+INNER_JOIN, LEFT_OUTER_JOIN, RIGHT_OUTER_JOIN = 0, 1, 2  # planner/core/logical_plans.go:52-57
+AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MAX, AGG_MIN, AGG_FIRSTROW = range(6)
+
+
+class MockDataSource:
+    """executor/benchmark_test.go:50-177 mockDataSource: replays prepared chunks of <= maxChunkSize rows."""
+
+    def __init__(self, types, columns, chunk_size=MAX_CHUNK_SIZE):
+        self.types = list(types)
+        n = columns[0].length if columns else 0
+        self.chunks = [Chunk([c.slice(lo, min(lo + chunk_size, n)) for c in columns]) for lo in range(0, n, chunk_size)]
+        self.pos = 0
+
+    def Open(self):
+        self.pos = 0
+
+    def Next(self):
+        if self.pos >= len(self.chunks):
+            return Chunk([Column(t, np.zeros(0)) for t in self.types])
+        self.pos += 1
+        return self.chunks[self.pos - 1]
+
+    def Close(self):
+        pass
+
+
+def _i32arr(vals):
+    return (C.c_int32 * max(len(vals), 1))(*vals)
+
+
+class HashJoinExec:
+    """executor/join.go:31-146.  inner = build side, outer = probe side; output = left ++ right."""
+
+    def __init__(self, outer_exec, inner_exec, outer_keys, inner_keys, join_type=INNER_JOIN, outer_is_right=False,
+                 outer_filter=None, probe_batch_rows=0, max_chunk_size=MAX_CHUNK_SIZE):
+        self.outer, self.inner = outer_exec, inner_exec
+        self.outer_keys, self.inner_keys = list(outer_keys), list(inner_keys)
+        self.join_type, self.outer_is_right = join_type, outer_is_right
+        self.outer_filter = outer_filter  # callable(chunk) -> selected bytes (expression.VectorizedFilter result)
+        self.probe_batch_rows = probe_batch_rows
+        self.max_chunk_size = max_chunk_size
+        self.handle = None
+        self.prepared = False
+        self.outer_done = False
+        lhs, rhs = (inner_exec.types, outer_exec.types) if outer_is_right else (outer_exec.types, inner_exec.types)
+        self.types = list(lhs) + list(rhs)
+
+    def Open(self):
+        self.outer.Open()
+        self.inner.Open()
+        lib = L.load()
+        bt, pt = _i32arr(self.inner.types), _i32arr(self.outer.types)
+        bk, pk = _i32arr(self.inner_keys), _i32arr(self.outer_keys)
+        d = L.TQJoinDesc(self.join_type, 1 if self.outer_is_right else 0, len(self.inner.types), bt, len(self.outer.types), pt,
+                         len(self.inner_keys), bk, pk, self.probe_batch_rows)
+        h = C.c_void_p()
+        L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
+        self.handle = h
+        self.prepared = False
+        self.outer_done = False
+
+    def _build(self):
+        """fetchAndBuildHashTable (join.go:148-158): drain the inner child into the row container."""
+        lib = L.load()
+        while True:
+            chk = self.inner.Next()
+            if chk.num_rows() == 0:
+                break
+            L.check(lib.tq_join_put_build(self.handle, tq_array(chk.cols), L.TQ_MEM_HOST))
+        L.check(lib.tq_join_finalize_build(self.handle))
+
+    def Next(self, required_rows=None):
+        """Returns a Chunk with <= required_rows rows; 0 rows == EOF (join.go:125-146)."""
+        lib = L.load()
+        req = required_rows or self.max_chunk_size
+        if not self.prepared:
+            self._build()
+            self.prepared = True
+        out = [Column.empty(t, req) for t in self.types]
+        arr = tq_array(out, req)
+        n, eof = C.c_int64(0), C.c_int32(0)
+        while True:
+            L.check(lib.tq_join_next(self.handle, req, arr, C.byref(n), C.byref(eof)))
+            if n.value > 0 or eof.value:
+                break
+            # fetchOuterSideChunks (join.go:194-221): feed one more outer chunk
+            chk = self.outer.Next()
+            if chk.num_rows() == 0:
+                L.check(lib.tq_join_probe_eof(self.handle))
+                continue
+            sel = None
+            if self.outer_filter is not None:
+                sel = np.ascontiguousarray(self.outer_filter(chk), dtype=np.uint8)
+            L.check(lib.tq_join_put_probe(self.handle, tq_array(chk.cols), sel.ctypes.data if sel is not None else None, L.TQ_MEM_HOST))
+        k = n.value
+        return Chunk([Column(t, c.values[:k], c.not_null()[:k]) for t, c in zip(self.types, out)])
+
+    def Close(self):
+        if self.handle is not None:
+            L.load().tq_join_destroy(self.handle)
+            self.handle = None
+        self.outer.Close()
+        self.inner.Close()
+
+    def drain(self):
+        chunks = []
+        while True:
+            c = self.Next()
+            if c.num_rows() == 0:
+                break
+            chunks.append(c)
+        return Chunk.concat(chunks, self.types)
+
+
+class HashAggExec:
+    """executor/aggregate.go:54-155.  funcs: list of (AGG_*, arg_col or -1); one GROUP BY column or none."""
+
+    def __init__(self, child, group_by, funcs, est_groups=0, max_chunk_size=MAX_CHUNK_SIZE):
+        self.child, self.group_by, self.funcs = child, list(group_by), list(funcs)
+        self.est_groups, self.max_chunk_size = est_groups, max_chunk_size
+        self.handle = None
+        self.prepared = False
+        self.types = []
+
+    def Open(self):
+        self.child.Open()
+        lib = L.load()
+        it, gb = _i32arr(self.child.types), _i32arr(self.group_by)
+        fa = (L.TQAggFunc * max(len(self.funcs), 1))(*[L.TQAggFunc(f, a) for f, a in self.funcs])
+        d = L.TQAggDesc(len(self.child.types), it, len(self.group_by), gb, len(self.funcs), fa, self.est_groups)
+        h = C.c_void_p()
+        L.check(lib.tq_agg_create(C.byref(d), C.byref(h)))
+        self.handle = h
+        self.types = []
+        for i in range(len(self.funcs)):
+            t = C.c_int32(0)
+            L.check(lib.tq_agg_output_type(h, i, C.byref(t)))
+            self.types.append(t.value)
+        self.prepared = False
+
+    def Next(self, required_rows=None):
+        lib = L.load()
+        req = required_rows or self.max_chunk_size
+        if not self.prepared:  # fetchChildData + partial workers (aggregate.go:487-522,307-350)
+            while True:
+                chk = self.child.Next()
+                if chk.num_rows() == 0:
+                    break
+                L.check(lib.tq_agg_put(self.handle, tq_array(chk.cols), L.TQ_MEM_HOST))
+            L.check(lib.tq_agg_eof(self.handle))
+            self.prepared = True
+        out = [Column.empty(t, req) for t in self.types]
+        arr = tq_array(out, req)
+        n, eof = C.c_int64(0), C.c_int32(0)
+        L.check(lib.tq_agg_next(self.handle, req, arr, C.byref(n), C.byref(eof)))
+        k = n.value
+        return Chunk([Column(t, c.values[:k], c.not_null()[:k]) for t, c in zip(self.types, out)])
+
+    def Close(self):
+        if self.handle is not None:
+            L.load().tq_agg_destroy(self.handle)
+            self.handle = None
+        self.child.Close()
+
+    def drain(self):
+        chunks = []
+        while True:
+            c = self.Next()
+            if c.num_rows() == 0:
+                break
+            chunks.append(c)
+        return Chunk.concat(chunks, self.types)

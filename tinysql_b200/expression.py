@@ -1,0 +1,112 @@
+"""expression.vecEval* surface (expression/builtin.go:256-263) bound to the CUDA kernels.
+
+Each function mirrors one vectorized builtin signature: it takes evaluated argument columns and
+returns the result column, raising TQError with the reference's error kinds (types.ErrOverflow…).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .chunk import Column, FLOAT64, INT64, UINT64, tq_array
+
+LT, LE, GT, GE, EQ, NE = range(6)
+PLUS, MINUS, MUL, DIV = range(4)
+AND, OR = 0, 1
+NOT_INT, NOT_REAL, MINUS_INT, MINUS_REAL, ISNULL = range(5)
+
+
+def _u(col):
+    return 1 if col.tp == UINT64 else 0
+
+
+def vec_compare_int(op, a, b):
+    """builtin{LT,LE,GT,GE,EQ,NE}IntSig.vecEvalInt — expression/builtin_compare_vec.go:22-292"""
+    out = Column.empty(INT64, a.length)
+    ta, tb, to = a.tq(), b.tq(), out.tq()
+    L.check(L.load().tq_vec_compare_int(op, a.length, C.byref(ta), _u(a), C.byref(tb), _u(b), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_compare_real(op, a, b):
+    """builtin{LT..NE}RealSig.vecEvalInt — expression/builtin_compare_vec_generated.go"""
+    out = Column.empty(INT64, a.length)
+    ta, tb, to = a.tq(), b.tq(), out.tq()
+    L.check(L.load().tq_vec_compare_real(op, a.length, C.byref(ta), C.byref(tb), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_arith_int(op, a, b):
+    """builtinArithmetic{Plus,Minus,Multiply}IntSig.vecEvalInt — expression/builtin_arithmetic_vec.go"""
+    out = Column.empty(UINT64 if (_u(a) or _u(b)) else INT64, a.length)
+    ta, tb, to = a.tq(), b.tq(), out.tq()
+    L.check(L.load().tq_vec_arith_int(op, a.length, C.byref(ta), _u(a), C.byref(tb), _u(b), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_arith_real(op, a, b):
+    """builtinArithmetic{Plus,Minus,Multiply,Divide}RealSig.vecEvalReal; returns (column, div-by-zero warnings)"""
+    out = Column.empty(FLOAT64, a.length)
+    ta, tb, to = a.tq(), b.tq(), out.tq()
+    dz = C.c_int64(0)
+    L.check(L.load().tq_vec_arith_real(op, a.length, C.byref(ta), C.byref(tb), C.byref(to), C.byref(dz), L.TQ_MEM_HOST))
+    return out, dz.value
+
+
+def vec_logic(op, a, b):
+    """builtinLogic{And,Or}Sig.vecEvalInt — expression/builtin_op_vec.go:29-68,173-215"""
+    out = Column.empty(INT64, a.length)
+    ta, tb, to = a.tq(), b.tq(), out.tq()
+    L.check(L.load().tq_vec_logic(op, a.length, C.byref(ta), C.byref(tb), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_unary(op, a):
+    """UnaryNot / UnaryMinus / IsNull — expression/builtin_op_vec.go"""
+    out_tp = FLOAT64 if op == MINUS_REAL else INT64
+    out = Column.empty(out_tp, a.length)
+    ta, to = a.tq(), out.tq()
+    L.check(L.load().tq_vec_unary(op, a.length, C.byref(ta), _u(a), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_if(cond, a, b):
+    """builtinIf{Int,Real}Sig — expression/builtin_control_vec_generated.go:117-207"""
+    out = Column.empty(a.tp, a.length)
+    tc, ta, tb, to = cond.tq(), a.tq(), b.tq(), out.tq()
+    L.check(L.load().tq_vec_if(a.length, C.byref(tc), C.byref(ta), C.byref(tb), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_ifnull(a, b):
+    """builtinIfNull{Int,Real}Sig — expression/builtin_control_vec_generated.go:23-79"""
+    out = Column.empty(a.tp, a.length)
+    ta, tb, to = a.tq(), b.tq(), out.tq()
+    L.check(L.load().tq_vec_ifnull(a.length, C.byref(ta), C.byref(tb), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_in_int(a, lst):
+    """builtinInIntSig — expression/builtin_other_vec_generated.go:24-96"""
+    out = Column.empty(INT64, a.length)
+    ta, to = a.tq(), out.tq()
+    arr = tq_array(lst)
+    flags = (C.c_int32 * max(len(lst), 1))(*[_u(c) for c in lst])
+    L.check(L.load().tq_vec_in_int(a.length, C.byref(ta), _u(a), len(lst), arr, flags, C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_lt_plus_int(a, b):
+    """BASELINE config 2 in one pass: (a < b, a + b) over signed BIGINT columns."""
+    lt, plus = Column.empty(INT64, a.length), Column.empty(INT64, a.length)
+    ta, tb, t1, t2 = a.tq(), b.tq(), lt.tq(), plus.tq()
+    L.check(L.load().tq_vec_lt_plus_int(a.length, C.byref(ta), C.byref(tb), C.byref(t1), C.byref(t2), L.TQ_MEM_HOST))
+    return lt, plus
+
+
+def vectorized_filter(a):
+    """expression.VectorizedFilter over one evaluated int column (expression/chunk_executor.go:196-245)."""
+    sel = np.zeros(max(a.length, 1), dtype=np.uint8)
+    ta = a.tq()
+    L.check(L.load().tq_vec_filter_int(a.length, C.byref(ta), sel.ctypes.data, L.TQ_MEM_HOST))
+    return sel[: a.length]
