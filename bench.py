@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — joined rows/sec of the B200 hash join on BASELINE.json's headline config.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                   (the CPU restatement of the reference design)
+  python bench.py --workload {join,agg,expr}             (secondary configs C4 / C2; default join = C3)
+
+A "step" = one full pass of the hot path over the synthetic tables of the workload (for the join:
+build 1e7 rows + probe 1e8 rows -> 1e8 joined rows materialised in HBM), inputs resident in HBM.
+`e2e` = the same job through the C-ABI with pinned HOST buffers, PCIe copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ synthetic tables
+def gen_join_tables(n_build, n_probe, key_range, seed_b=3, seed_p=4, rank=0):
+    """C3: B.k = permutation of [0, n_build) (seed 3), B.v = 7k+1; P.k uniform [0, key_range) (seed 4), P.v = row id."""
+    rb = np.random.default_rng(seed_b + 1000 * rank)
+    rp = np.random.default_rng(seed_p + 1000 * rank)
+    if key_range == n_build:
+        bk = rb.permutation(n_build).astype(np.int64)
+    else:  # a shard of a bigger table: distinct keys of this rank's residue class
+        bk = rb.permutation(n_build).astype(np.int64)
+    bv = bk * 7 + 1
+    pk = rp.integers(0, key_range, n_probe, dtype=np.int64)
+    pv = np.arange(n_probe, dtype=np.int64)
+    return bk, bv, pk, pv
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm (oracle/cpu_ref.c)
+def cpu_join_sample(n_build, n_probe_full, sample_probe, workers, seed_rank=0):
+    import oracle_py as O
+    lib = O.load()
+    bk, bv, pk, pv = gen_join_tables(n_build, sample_probe, n_build, rank=seed_rank)
+    bs, ps, ck = C.c_double(0), C.c_double(0), C.c_uint64(0)
+    rows = lib.orc_mt_join_bench(C.c_int64(n_build), C.c_void_p(bk.ctypes.data), C.c_void_p(bv.ctypes.data), C.c_int64(sample_probe),
+                                 C.c_void_p(pk.ctypes.data), C.c_void_p(pv.ctypes.data), C.c_int(workers), C.byref(bs), C.byref(ps), C.byref(ck))
+    assert rows == sample_probe, (rows, sample_probe)
+    # whole-job estimate: the build is paid once, the probe scales with the probe rows
+    est_total_s = bs.value + ps.value * (n_probe_full / sample_probe)
+    return {"value": n_probe_full / est_total_s, "unit": "joined rows/s", "cores": workers, "kind": "port",
+            "sample": f"full serial build of {n_build} rows ({bs.value:.2f} s) + probe of the first {sample_probe} of {n_probe_full} probe rows "
+                      f"({ps.value:.2f} s, {workers} worker threads), extrapolated to the whole probe side; "
+                      "oracle/cpu_ref.c = C restatement of the reference's goroutine design (no Go toolchain in this image)",
+            "build_s": bs.value, "probe_s": ps.value}
+
+
+# ------------------------------------------------------------------ GPU arm
+class JoinBench:
+    def __init__(self, lib, L, n_build, n_probe, rank=0, world=1):
+        from tinysql_b200.chunk import INT64, Column, DeviceColumn
+        self.lib, self.L = lib, L
+        self.n_build, self.n_probe = n_build, n_probe
+        self.bk, self.bv, self.pk, self.pv = gen_join_tables(n_build, n_probe, n_build, rank=rank)
+        self.d_b = [DeviceColumn.from_host(Column(INT64, self.bk)), DeviceColumn.from_host(Column(INT64, self.bv))]
+        self.d_p = [DeviceColumn.from_host(Column(INT64, self.pk)), DeviceColumn.from_host(Column(INT64, self.pv))]
+        self.INT64 = INT64
+
+    def desc(self, batch=0):
+        L = self.L
+        t = (C.c_int32 * 2)(1, 1)
+        k = (C.c_int32 * 1)(0)
+        self._keep = (t, k)
+        return L.TQJoinDesc(0, 1, 2, t, 2, t, 1, k, k, batch)
+
+    def step_device(self):
+        """build + probe with inputs resident in HBM; returns (joined rows, probe kernel ns, build ns)."""
+        L, lib = self.L, self.lib
+        h = C.c_void_p()
+        d = self.desc()
+        L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
+        barr = (L.TQColumn * 2)(self.d_b[0].tq(), self.d_b[1].tq())
+        for i in range(2):
+            barr[i].null_bitmap = None
+        parr = (L.TQColumn * 2)(self.d_p[0].tq(), self.d_p[1].tq())
+        for i in range(2):
+            parr[i].null_bitmap = None
+        L.check(lib.tq_join_put_build(h, barr, L.TQ_MEM_DEVICE))
+        L.check(lib.tq_join_finalize_build(h))
+        L.check(lib.tq_join_put_probe(h, parr, None, L.TQ_MEM_DEVICE))
+        L.check(lib.tq_join_probe_eof(h))
+        out = (L.TQColumn * 4)()
+        n, eof = C.c_int64(0), C.c_int32(0)
+        L.check(lib.tq_join_next_device(h, out, C.byref(n), C.byref(eof)))
+        st = (C.c_int64 * 8)()
+        lib.tq_join_stats(h, st)
+        rows = n.value
+        self.last_out = None
+        L.check(lib.tq_join_destroy(h))
+        return rows, st[5], st[6]
+
+    def setup_e2e(self):
+        """pinned host inputs / outputs for the C-ABI host path"""
+        lib, L = self.lib, self.L
+
+        def pinned(n_items, src=None):
+            p = C.c_void_p()
+            L.check(lib.tq_pinned_alloc(n_items * 8, C.byref(p)))
+            arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(n_items,))
+            if src is not None:
+                arr[:] = src
+            return p, arr
+
+        self.h_b = [pinned(self.n_build, self.bk), pinned(self.n_build, self.bv)]
+        self.h_p = [pinned(self.n_probe, self.pk), pinned(self.n_probe, self.pv)]
+        self.out_rows = 1 << 22
+        self.h_out = [pinned(self.out_rows) for _ in range(4)]
+        self.h_out_bm = [np.zeros((self.out_rows + 7) // 8 + 8, dtype=np.uint8) for _ in range(4)]
+
+    def step_e2e(self):
+        """Open/build/probe/Next-until-EOF/Close through the C-ABI with HOST buffers."""
+        L, lib = self.L, self.lib
+        h = C.c_void_p()
+        d = self.desc(batch=1 << 23)
+        L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
+
+        def cols(bufs, n):
+            a = (L.TQColumn * len(bufs))()
+            for i, (p, _) in enumerate(bufs):
+                a[i].length, a[i].data, a[i].null_bitmap, a[i].offsets = n, p.value, None, None
+            return a
+        L.check(lib.tq_join_put_build(h, cols(self.h_b, self.n_build), L.TQ_MEM_HOST))
+        L.check(lib.tq_join_finalize_build(h))
+        out = (L.TQColumn * 4)()
+        for i in range(4):
+            out[i].data = self.h_out[i][0].value
+            out[i].null_bitmap = self.h_out_bm[i].ctypes.data
+        n, eof = C.c_int64(0), C.c_int32(0)
+        total = 0
+        checksum = 0
+        # feed the probe side in 8M-row host pieces, draining results as they complete (Next contract)
+        piece = 1 << 23
+        for lo in range(0, self.n_probe, piece):
+            rows = min(piece, self.n_probe - lo)
+            a = (L.TQColumn * 2)()
+            for i, (p, _) in enumerate(self.h_p):
+                a[i].length, a[i].data, a[i].null_bitmap, a[i].offsets = rows, p.value + lo * 8, None, None
+            L.check(lib.tq_join_put_probe(h, a, None, L.TQ_MEM_HOST))
+        L.check(lib.tq_join_probe_eof(h))
+        while True:
+            L.check(lib.tq_join_next(h, self.out_rows, out, C.byref(n), C.byref(eof)))
+            if n.value == 0 and eof.value:
+                break
+            total += n.value
+            checksum += int(self.h_out[1][1][0])  # touch the result on the host
+        L.check(lib.tq_join_destroy(h))
+        return total
+
+
+def run_join_bench(args, rank, world, local_rank, dist):
+    from tinysql_b200 import _lib as L
+    lib = L.load()
+    L.check(lib.tq_init(local_rank))
+    n_build, n_probe = args.build_rows, args.probe_rows
+    peak, peak_src = measured_peak()
+    if world > 1:
+        from tinysql_b200 import dist as D
+        return D.bench_distributed_join(args, rank, world, local_rank, dist, peak, peak_src)
+    jb = JoinBench(lib, L, n_build, n_probe, rank, world)
+    launches0 = lib.tq_kernel_launch_count()
+    for _ in range(args.warmup):
+        rows, _, _ = jb.step_device()
+        assert rows == n_probe, rows
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.tq_device_synchronize()
+    launches1 = lib.tq_kernel_launch_count()
+    probe_ns, build_ns = [], []
+    ms = C.c_float(0)
+    L.check(lib.tq_timer_start())
+    for _ in range(args.steps):
+        rows, pns, bns = jb.step_device()
+        probe_ns.append(pns)
+        build_ns.append(bns)
+    L.check(lib.tq_timer_stop(C.byref(ms)))
+    lib.tq_device_synchronize()
+    clocks = sampler.stop()
+    launches2 = lib.tq_kernel_launch_count()
+    ms_per_step = ms.value / args.steps
+    value = n_probe / (ms_per_step * 1e-3)
+    # roofline of the dominant kernel (k_probe): 64 algorithmic bytes per probe row (SURVEY §8d / DESIGN.md)
+    probe_s = statistics.mean(probe_ns) * 1e-9
+    achieved = 64.0 * n_probe / probe_s / 1e9
+    if args.kernel_only:
+        return {"value": value, "ms_per_step": ms_per_step, "kernel_ms": probe_s * 1e3, "build_ms": statistics.mean(build_ns) * 1e-6,
+                "frac": achieved / peak, "gpu_launches": int(launches2 - launches1)}
+    # end to end through the C-ABI with pinned host buffers
+    jb.setup_e2e()
+    e2e_steps = max(1, min(args.steps, 3))
+    jb.step_e2e()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        total = jb.step_e2e()
+        assert total == n_probe
+    lib.tq_device_synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    workers = os.cpu_count() or 1
+    cpu = cpu_join_sample(n_build, n_probe, min(n_probe, args.cpu_sample_rows), workers)
+    out = {
+        "metric": "joined rows/sec on 1e8-row int64 equi-join", "value": value, "unit": "joined rows/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic",
+        "config": {"workload": f"C3: int64 equi-join, uniform keys, build={n_build} probe={n_probe}, 100% match, output (B.k,B.v,P.k,P.v) materialised",
+                   "build_rows": n_build, "probe_rows": n_probe, "l2": "inputs (1.76 GB) and output (3.2 GB) exceed the 126 MB L2; no flush needed",
+                   "step": "tq_join create + build + probe + result, inputs resident in HBM"},
+        "roofline": {"bound": "hbm", "kernel": "k_probe", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_row": 64, "kernel_ms": probe_s * 1e3,
+                     "build_ms": statistics.mean(build_ns) * 1e-6},
+        "e2e": {"value": n_probe / e2e_s, "unit": "joined rows/s", "h2d_bytes_per_step": 16 * (n_build + n_probe), "d2h_bytes_per_step": 32 * n_probe,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches2 - launches1), "clocks": clocks, "cpu_baseline": cpu,
+    }
+    return out
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU restatement of the reference's goroutine design on the host cores."""
+    if rank != 0:
+        return None
+    n_build, n_probe = args.build_rows, args.probe_rows
+    workers = os.cpu_count() or 1
+    sample = min(n_probe, args.cpu_sample_rows)
+    res = None
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_join_sample(n_build, n_probe, sample, workers)
+        if i >= args.warmup:
+            times.append(r)
+        res = r
+    v = statistics.mean([r["value"] for r in times]) if times else res["value"]
+    res = dict(res)
+    res["value"] = v
+    return {"impl": "reference", "metric": "joined rows/sec on 1e8-row int64 equi-join", "value": v, "unit": "joined rows/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_probe / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"C3: int64 equi-join, uniform keys, build={n_build} probe={n_probe}", "build_rows": n_build, "probe_rows": n_probe},
+            "cpu_baseline": res, "e2e": {"value": v, "unit": "joined rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="join", choices=["join", "agg", "expr"])
+    ap.add_argument("--build-rows", type=int, default=10_000_000)
+    ap.add_argument("--probe-rows", type=int, default=100_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=20_000_000)
+    ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and CPU legs (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        out = run_reference(args, rank)
+        if out is not None:
+            print(json.dumps(out))
+        return
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl")
+        dist = dist_mod
+    if args.workload == "join":
+        out = run_join_bench(args, rank, world, local_rank, dist)
+    else:
+        from tinysql_b200 import bench_extra
+        out = bench_extra.run(args, rank, world, local_rank)
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

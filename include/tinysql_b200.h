@@ -117,8 +117,9 @@ int32_t tq_vec_compare_real(int32_t op, int64_t n, const tq_column *a, const tq_
 
 enum { TQ_ARITH_PLUS = 0, TQ_ARITH_MINUS = 1, TQ_ARITH_MUL = 2, TQ_ARITH_DIV = 3 };
 /* builtinArithmetic{Plus,Minus,Multiply}IntSig / MultiplyIntUnsignedSig.vecEvalInt —
- * expression/builtin_arithmetic_vec.go:88-340,389-532.  MUL with both unsigned flags set
- * is MultiplyIntUnsigned, otherwise MultiplyInt (signed check), as the planner picks. */
+ * expression/builtin_arithmetic_vec.go:88-340,389-532.  MUL with EITHER unsigned flag set
+ * is MultiplyIntUnsigned (both operands read as uint64), otherwise MultiplyInt — the choice
+ * multiplyFunctionClass.getFunction makes (expression/builtin_arithmetic.go:344-352). */
 int32_t tq_vec_arith_int(int32_t op, int64_t n, const tq_column *a, int32_t a_unsigned,
                          const tq_column *b, int32_t b_unsigned, tq_column *out, int32_t mem);
 /* builtinArithmetic{Plus,Minus,Multiply,Divide}RealSig.vecEvalReal —

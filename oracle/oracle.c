@@ -501,7 +501,7 @@ int orc_vec_arith_int(int op, int64_t n, const orc_column *a, int ua, const orc_
       }
       r[i] = lh - rh;
     } else {
-      if (ua && ub) {                                                /* MultiplyIntUnsigned :521-529 */
+      if (ua || ub) {                                                /* MultiplyIntUnsigned :521-529 — chosen when EITHER side is unsigned (builtin_arithmetic.go:344-348) */
         uint64_t x = (uint64_t)lh, y = (uint64_t)rh, res = x * y;
         if (x != 0 && res / x != y) return ORC_ERR_OVERFLOW_BIGINT_UNSIGNED;
         r[i] = (int64_t)res;

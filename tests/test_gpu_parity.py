@@ -203,6 +203,52 @@ def test_join_selected_and_batches(lib):
         assert_same_multiset(got, want)
 
 
+@pytest.mark.parametrize("jt,oir", [(INNER_JOIN, True), (LEFT_OUTER_JOIN, False), (RIGHT_OUTER_JOIN, True)])
+def test_join_partitioned_path(lib, jt, oir):
+    """build side >= 65536 rows: partition tables in shared memory (TMA bulk loads), radix-scattered probe side."""
+    rng = np.random.default_rng(77 + jt)
+    nb, npr = 300000, 1200000
+    bcols = [gen_col(rng, INT64, nb, 0.02, 0, 250000), gen_col(rng, INT64, nb, 0.1), gen_col(rng, FLOAT64, nb, 0.1)]
+    pcols = [gen_col(rng, INT64, npr, 0.1), gen_col(rng, INT64, npr, 0.03, 0, 400000)]
+    sel = (rng.random(npr) < 0.8).astype(np.uint8)
+    got, want = _run_join([INT64, INT64, FLOAT64], bcols, [INT64, INT64], pcols, jt, oir, selected=sel, pkey=1, batch=1 << 19)
+    assert_same_multiset(got, want)
+
+
+def test_join_partitioned_smem_tables(lib, monkeypatch):
+    """~2400 build rows per partition: every partition table is TMA-bulk-loaded into shared memory"""
+    monkeypatch.setenv("TQ_JOIN_PART_ROWS", "2400")
+    rng = np.random.default_rng(123)
+    nb, npr = 300000, 900000
+    bcols = [gen_col(rng, INT64, nb, 0.02, 0, 200000), gen_col(rng, INT64, nb, 0.1)]
+    pcols = [gen_col(rng, INT64, npr, 0.05, 0, 260000), gen_col(rng, FLOAT64, npr, 0.1)]
+    for jt, oir in ((INNER_JOIN, False), (LEFT_OUTER_JOIN, False)):
+        got, want = _run_join([INT64, INT64], bcols, [INT64, FLOAT64], pcols, jt, oir, batch=1 << 19)
+        assert_same_multiset(got, want)
+
+
+def test_join_partitioned_unique_pk_fk(lib):
+    """the C3 shape at 1/20 scale: unique build keys, every probe row matches exactly once"""
+    rng = np.random.default_rng(3)
+    nb, npr = 500000, 5000000
+    bk = rng.permutation(nb).astype(np.int64)
+    b = [Column(INT64, bk), Column(INT64, bk * 7 + 1)]
+    pk = rng.integers(0, nb, npr)
+    p = [Column(INT64, pk), Column(INT64, np.arange(npr))]
+    inner, outer = MockDataSource([INT64, INT64], b, 1 << 20), MockDataSource([INT64, INT64], p, 1 << 20)
+    e = HashJoinExec(outer, inner, [0], [0], INNER_JOIN, True)
+    e.Open()
+    got = e.drain()
+    e.Close()
+    assert got.num_rows() == npr
+    # size-independent properties: B.k == P.k, B.v == 7k+1, every probe row id appears exactly once
+    assert np.array_equal(got.cols[0].values, got.cols[2].values)
+    assert np.array_equal(got.cols[1].values, got.cols[0].values * 7 + 1)
+    ids = np.sort(got.cols[3].values)
+    assert np.array_equal(ids, np.arange(npr))
+    assert np.array_equal(got.cols[2].values, pk[got.cols[3].values])
+
+
 def test_join_duplicates_large_segments(lib):
     # 100 x 100 duplicate join (join_test.go:175-182) and a >32-row duplicate segment (bitonic path)
     b = [Column(INT64, [7] * 100 + [8] * 3), Column(INT64, list(range(103)))]

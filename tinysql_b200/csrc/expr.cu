@@ -180,7 +180,7 @@ struct FArithInt {
       o[0] = ul - ur;
     } else {
       const uint64_t lo = ul * ur;
-      if (ua && ub) {                                                                                    // MultiplyIntUnsigned :521-529
+      if (ua || ub) {                                                                                    // MultiplyIntUnsigned :521-529 (either side unsigned: builtin_arithmetic.go:344-348)
         if (__umul64hi(ul, ur) != 0) err |= ERR_UBIGINT;
       } else {                                                                                           // MultiplyInt :332-338
         // `x != 0 && tmp/x != y` with Go's wrapping quotient: a true overflow is missed exactly when

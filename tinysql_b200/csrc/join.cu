@@ -1,18 +1,19 @@
 // join.cu — HashJoinExec on the device (replaces executor/join.go, hash_table.go, joiner.go).
 //
-// Build (tq_join_finalize_build): the inner side is materialised in HBM, then
-//   k_build_insert   every non-NULL-key row finds/claims the slot of its key in an open-addressed
-//                    table of DISTINCT keys (atomicCAS) and bumps the slot's count
-//   exclusive scan   slot counts -> CSR offsets
-//   k_build_fill     row ids are scattered into their key's CSR segment
-//   k_build_fixsort  offsets restored, segments of duplicate keys sorted ascending (= the reference's
-//                    insertion order, rowHashMap.Get hash_table.go:259-272)
-//   k_gather_col     build columns are permuted into CSR order, so a probe hit (off, cnt) addresses
-//                    cnt CONTIGUOUS build rows — no row-pointer chasing on the probe side
-// Probe (one launch per device batch): k_probe — each CTA takes 1024-row tiles: 128-bit slot loads,
-//   per-row match counts, block scan, one atomicAdd for the tile's output range, then an
-//   output-centric expansion (thread per OUTPUT row, binary search in the tile's prefix array) with
-//   coalesced 8-byte column stores and ballot-assembled null-bitmap words.
+// Table.  Open-addressed entries of 2 or 4 eight-byte words, word 0 = the join key.  Large build sides
+// are split by the TOP bits of the key hash into 2^pbits partition tables stored back to back (linear
+// probing wraps inside a partition), so the probe side can be radix-scattered the same way and only a
+// few partition tables are live — in L2, or in shared memory when a partition image is <= 128 KB.
+//   ROW mode (unique build keys, <= 4 words per row — the PK-FK join): the entry IS the build row:
+//       word0 = key, then the other build columns, then an optional NOT-NULL mask word.
+//       One 16/32-byte sector per probe; the build is: init, insert (atomicCAS), write rows.
+//   CSR mode (duplicate keys or wide rows): word1 = (offset | count << 32) into build rows packed
+//       row-major in key order; duplicates keep build insertion order (rowHashMap.Get, hash_table.go:259-272).
+//       Build: insert+count, exclusive scan, fill, sort duplicate segments, gather rows.
+// Probe.  Small build (one table): k_probe, ordered output (probe row asc, build insertion asc) via
+//   ticketed tiles + decoupled look-back.  Large build: k_probe_part_hist -> scan -> k_probe_scatter
+//   (shared-memory counting sort of 8192-row tiles, coalesced full-sector stores) -> k_probe_part(_uniq).
+#include <cstdlib>
 #include <deque>
 #include <memory>
 #include <new>
@@ -22,15 +23,15 @@
 namespace tq {
 
 static constexpr int MAXC = 16;  // columns per join side
-static constexpr uint64_t EMPTY_KEY = 0xA5C3F00DDEADBEEFull;  // slot sentinel; a real key with this value lives in a side segment
+static constexpr uint64_t EMPTY_KEY = 0xA5C3F00DDEADBEEFull;  // empty-entry marker; a real key with this value lives in a side entry/segment
 static constexpr uint32_t ROW_INVALID = 0xFFFFFFFFu, ROW_SENTINEL = 0xFFFFFFFEu;
 static constexpr uint32_t OFF_MISS = 0xFFFFFFFFu;
-
-struct __align__(16) Slot {
-  uint64_t key;
-  uint32_t off;
-  uint32_t cnt;
-};
+static constexpr int64_t PART_MIN_BUILD_ROWS = 1 << 18;  // below this the whole table (<= 8 MB) is L2-resident anyway
+static constexpr int PART_MAX_BITS = 12;
+static constexpr uint64_t PART_MAX_SMEM_BYTES = 128 << 10;  // a partition table image that still fits in shared memory
+static int64_t g_tiles_per_cta = 8;
+static int64_t g_part_target_rows = 150000;              // build rows per partition: a partition table ~ 4-8 MB, a few live ones fit in L2
+static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
 
 // key_mode: how (flag, raw bytes) equality (util/codec/codec.go:212-240,363-382) maps onto raw 8-byte equality
 //   0: flags always agree (both signed, both unsigned, or both DOUBLE)  -> raw equality
@@ -40,10 +41,14 @@ struct __align__(16) Slot {
 enum { KEYMODE_RAW = 0, KEYMODE_NO_SIGNBIT = 1, KEYMODE_NEVER = 2 };
 
 struct JoinTable {
-  Slot *slots;
-  uint64_t mask;
-  uint32_t sent_off, sent_cnt;
+  uint64_t *words;  // entry e = words[e << shift ...]
+  uint64_t mask;    // entries per partition table - 1
+  int pbits;        // log2(#partition tables); 0 = one table
+  int shift;        // log2(words per entry): 1 or 2
+  int row_mode;
+  uint32_t sent_off, sent_cnt;  // CSR: CSR segment of the EMPTY_KEY-valued key.  ROW: sent_off = entry index of that row, sent_cnt = 0/1
 };
+__device__ __forceinline__ uint64_t part_of_hash(uint64_t h, int pbits) { return pbits ? (h >> (64 - pbits)) : 0; }
 
 __device__ __forceinline__ bool key_valid(uint64_t key, bool not_null, int key_mode) {
   if (!not_null) return false;
@@ -52,41 +57,105 @@ __device__ __forceinline__ bool key_valid(uint64_t key, bool not_null, int key_m
   return false;
 }
 
-__global__ void k_init_slots(Slot *slots, uint64_t n) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    Slot s;
-    s.key = EMPTY_KEY; s.off = 0; s.cnt = 0;
-    slots[i] = s;
-  }
+// (word0, word1) of an entry with one 128-bit load
+__device__ __forceinline__ ulonglong2 ld_entry(const uint64_t *words, uint64_t e, int shift) {
+  return *reinterpret_cast<const ulonglong2 *>(words + (e << shift));
 }
 
-// counters[0] = sentinel-key row count, [1] = sentinel fill cursor, [2] = distinct keys, [3] = large-segment worklist length
-__global__ void __launch_bounds__(256) k_build_insert(const uint64_t *keys, const uint32_t *bm, int64_t n, int key_mode, Slot *slots,
-                                                       uint64_t mask, uint32_t *row_slot, uint32_t *counters) {
+__global__ void k_init_table(uint64_t *words, uint64_t n_entries, int shift) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t n_words = n_entries << shift, wmask = (1ull << shift) - 1;
+  for (; i < n_words; i += stride) words[i] = (i & wmask) ? 0ull : EMPTY_KEY;
+}
+
+// counters: [0] EMPTY_KEY-valued rows, [1] their fill cursor, [2] distinct regular keys, [3] large-segment worklist length,
+//           [4] max rows of a build partition, [5] valid regular rows, u64 @ [8] scan total
+__global__ void __launch_bounds__(256) k_build_insert(const uint64_t *keys, const uint32_t *bm, int64_t n, int key_mode, uint64_t *words,
+                                                       uint64_t mask, int pbits, int shift, uint32_t *row_slot, uint32_t *counters) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned my_valid = 0, my_new = 0;
   for (; i < n; i += stride) {
     const uint64_t key = keys[i];
     if (!key_valid(key, tqd::bm_not_null(bm, i), key_mode)) { row_slot[i] = ROW_INVALID; continue; }  // hash_table.go:161-163
     if (key == EMPTY_KEY) { atomicAdd(&counters[0], 1u); row_slot[i] = ROW_SENTINEL; continue; }
-    uint64_t idx = tqd::mix64(key) & mask;
+    const uint64_t h = tqd::mix64(key);
+    const uint64_t base = part_of_hash(h, pbits) * (mask + 1);
+    uint64_t loc = h & mask;
+    my_valid++;
     for (;;) {
-      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&slots[idx].key), (unsigned long long)EMPTY_KEY,
+      const uint64_t e = base + loc;
+      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&words[e << shift]), (unsigned long long)EMPTY_KEY,
                                                 (unsigned long long)key);
       if (prev == EMPTY_KEY || prev == key) {
-        atomicAdd(&slots[idx].cnt, 1u);
-        row_slot[i] = (uint32_t)idx;
+        my_new += (prev == EMPTY_KEY);
+        atomicAdd(reinterpret_cast<uint32_t *>(&words[(e << shift) + 1]) + 1, 1u);  // count lives in the high half of word 1
+        row_slot[i] = (uint32_t)e;
         break;
       }
-      idx = (idx + 1) & mask;
+      loc = (loc + 1) & mask;
     }
+  }
+  my_valid = __reduce_add_sync(0xffffffffu, my_valid);
+  my_new = __reduce_add_sync(0xffffffffu, my_new);
+  if ((threadIdx.x & 31) == 0) {
+    if (my_valid) atomicAdd(&counters[5], my_valid);
+    if (my_new) atomicAdd(&counters[2], my_new);
   }
 }
 
-__global__ void __launch_bounds__(256) k_build_fill(const uint32_t *row_slot, int64_t n, Slot *slots, uint32_t sent_off, uint32_t *counters,
-                                                     uint32_t *row_ids) {
+// rows per build partition (valid keys only) — decides the partition table capacity
+__global__ void __launch_bounds__(256) k_build_part_hist(const uint64_t *keys, const uint32_t *bm, int64_t n, int key_mode, int pbits,
+                                                          uint32_t *part_cnt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint64_t key = keys[i];
+    if (!key_valid(key, tqd::bm_not_null(bm, i), key_mode) || key == EMPTY_KEY) continue;
+    atomicAdd(&part_cnt[part_of_hash(tqd::mix64(key), pbits)], 1u);
+  }
+}
+
+__global__ void k_max_u32(const uint32_t *v, int n, uint32_t *out) {
+  uint32_t m = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = max(m, v[i]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ROW mode: the row that claimed an entry writes its other columns (and NOT-NULL mask) into it.
+struct BuildRowParams {
+  int n_cols, key_col;
+  DCol cols[MAXC];
+  int word_of_col[MAXC];  // word index inside the entry (key column -> 0)
+  int mask_word;          // -1: no build column holds NULLs
+  const uint32_t *row_slot;
+  int64_t n;
+  uint64_t *words;
+  int shift;
+  uint32_t sent_entry;
+};
+__global__ void __launch_bounds__(256) k_build_rows(const BuildRowParams b) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < b.n; i += stride) {
+    uint32_t e = b.row_slot[i];
+    if (e == ROW_INVALID) continue;
+    if (e == ROW_SENTINEL) e = b.sent_entry;
+    uint64_t *ent = b.words + ((uint64_t)e << b.shift);
+    uint64_t m = 0;
+    for (int c = 0; c < b.n_cols; c++) {
+      if (c != b.key_col || e == b.sent_entry) ent[b.word_of_col[c]] = b.cols[c].data[i];
+      m |= (uint64_t)tqd::bm_not_null(b.cols[c].bm, i) << c;
+    }
+    if (b.mask_word >= 0) ent[b.mask_word] = m;
+  }
+}
+
+// ---- CSR mode build kernels
+__global__ void __launch_bounds__(256) k_build_fill(const uint32_t *row_slot, int64_t n, uint64_t *words, int shift, uint32_t sent_off,
+                                                     uint32_t *counters, uint32_t *row_ids) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -94,23 +163,22 @@ __global__ void __launch_bounds__(256) k_build_fill(const uint32_t *row_slot, in
     if (s == ROW_INVALID) continue;
     uint32_t pos;
     if (s == ROW_SENTINEL) pos = sent_off + atomicAdd(&counters[1], 1u);
-    else pos = atomicAdd(&slots[s].off, 1u);
+    else pos = atomicAdd(reinterpret_cast<uint32_t *>(&words[((uint64_t)s << shift) + 1]), 1u);  // offset = low half of word 1
     row_ids[pos] = (uint32_t)i;
   }
 }
 
-// Restores off (k_build_fill advanced it by cnt) and sorts duplicate-key segments ascending by row id.
-__global__ void __launch_bounds__(256) k_build_fixsort(Slot *slots, uint64_t n_slots, uint32_t *row_ids, uint32_t *counters,
+// Restores the offsets (k_build_fill advanced them by count) and sorts duplicate-key segments ascending by row id.
+__global__ void __launch_bounds__(256) k_build_fixsort(uint64_t *words, uint64_t n_entries, int shift, uint32_t *row_ids, uint32_t *counters,
                                                         uint2 *worklist, uint32_t worklist_cap) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  unsigned distinct = 0;
-  for (; i < n_slots; i += stride) {
-    const uint32_t cnt = slots[i].cnt;
+  for (; i < n_entries; i += stride) {
+    uint32_t *w1 = reinterpret_cast<uint32_t *>(&words[(i << shift) + 1]);
+    const uint32_t cnt = w1[1];
     if (cnt == 0) continue;
-    distinct++;
-    const uint32_t off = slots[i].off - cnt;
-    slots[i].off = off;
+    const uint32_t off = w1[0] - cnt;
+    w1[0] = off;
     if (cnt == 1) continue;
     if (cnt <= 32) {
       uint32_t *seg = row_ids + off;  // insertion sort: segments are tiny
@@ -125,8 +193,6 @@ __global__ void __launch_bounds__(256) k_build_fixsort(Slot *slots, uint64_t n_s
       if (w < worklist_cap) worklist[w] = make_uint2(off, cnt);
     }
   }
-  distinct = __reduce_add_sync(0xffffffffu, distinct);
-  if ((threadIdx.x & 31) == 0 && distinct) atomicAdd(&counters[2], distinct);
 }
 
 // One CTA per large duplicate segment: bitonic sort in global memory (indices >= cnt act as +inf).
@@ -160,23 +226,26 @@ __global__ void __launch_bounds__(256) k_sort_large(const uint2 *worklist, uint3
   }
 }
 
-// B'[pos] = B[row_ids[pos]] (data + null bit): build columns in CSR order.
-__global__ void __launch_bounds__(256) k_gather_col(const uint64_t *src, const uint32_t *src_bm, const uint32_t *row_ids, int64_t n,
-                                                     uint64_t *dst, uint32_t *dst_bm) {
-  const int lane = threadIdx.x & 31;
-  const int64_t n_words = (n + 31) >> 5;
-  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (; w < n_words; w += stride) {
-    const int64_t pos = w * 32 + lane;
-    bool nn = false;
-    if (pos < n) {
-      const uint32_t r = row_ids[pos];
-      dst[pos] = src[r];
-      nn = tqd::bm_not_null(src_bm, r);
+// B'[pos] = B[row_ids[pos]] packed row-major (+ NOT-NULL mask per row): build rows in CSR order.
+struct GatherParams {
+  int n_cols;
+  DCol cols[MAXC];
+  const uint32_t *row_ids;
+  int64_t n;
+  uint64_t *out_rows;
+  uint32_t *out_mask;  // nullptr: no build column holds NULLs
+};
+__global__ void __launch_bounds__(256) k_gather_rows(const GatherParams g) {
+  int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; pos < g.n; pos += stride) {
+    const uint32_t r = g.row_ids[pos];
+    uint32_t mask = 0;
+    for (int c = 0; c < g.n_cols; c++) {
+      g.out_rows[pos * g.n_cols + c] = g.cols[c].data[r];
+      mask |= (uint32_t)tqd::bm_not_null(g.cols[c].bm, r) << c;
     }
-    const unsigned word = __ballot_sync(0xffffffffu, nn);
-    if (dst_bm && lane == 0) dst_bm[w] = word;
+    if (g.out_mask) g.out_mask[pos] = mask;
   }
 }
 
@@ -187,46 +256,252 @@ static constexpr int PROBE_TILE = PROBE_THREADS * PROBE_ROWS_PER_THREAD;
 
 struct ProbeParams {
   int n_probe_cols, n_build_cols;
-  DCol probe[MAXC];
-  DCol build[MAXC];           // CSR-ordered build columns
+  DCol probe[MAXC];           // probe columns (the partitioned copies on the partitioned path)
   DColMut out_probe[MAXC];    // destination of probe column c (bm == nullptr: column cannot hold NULLs, bitmap pre-filled)
   DColMut out_build[MAXC];
-  const uint8_t *selected;    // outerSideFilter result or nullptr
+  // build rows: CSR mode = rows packed row-major in key order; ROW mode = the table entries themselves
+  const uint64_t *build_rows;
+  int build_stride;           // words between consecutive build rows
+  int build_word[MAXC];       // word of build column c inside a row
+  const uint32_t *build_mask; // CSR mode: NOT-NULL mask per row (nullptr: no NULLs)
+  int build_mask_word;        // ROW mode: word holding the NOT-NULL mask (-1: none)
+  const uint8_t *selected;    // outerSideFilter result or nullptr (one-table path only; the scatter applies it on the partitioned path)
   int key_col;
   int key_mode;
   int is_outer;               // LeftOuter / RightOuter: misses emit probe row ++ NULLs (joiner.go:274-277,337-340)
   int64_t n;
   uint64_t capacity;          // rows the output columns can hold
   unsigned long long *cursor; // [0] rows produced (may exceed capacity: then the batch is re-run), [1] matched probe rows
+  // ordered output (one-table path): tiles are handed out by ticket and each tile learns the output offset of all
+  // earlier tiles by decoupled look-back over tile_state (bits 63..62: 1 = tile total, 2 = inclusive prefix)
+  unsigned long long *tile_state;
+  unsigned *ticket;
+  // partitioned path: rows of partition q are [part_off[q], part_off[q+1]) of the probe columns; partition
+  // 2^pbits holds the rows that cannot match (NULL / filtered keys) and exists only for outer joins
+  const uint32_t *part_off;
+  int split;                  // CTAs per partition
+  int table_in_smem;          // partition table images fit in shared memory (TMA bulk-loaded)
 };
 
-__device__ __forceinline__ Slot ld_slot(const Slot *p) {
-  const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);  // one 128-bit load: key | off,cnt
-  Slot s;
-  s.key = v.x;
-  s.off = (uint32_t)v.y;
-  s.cnt = (uint32_t)(v.y >> 32);
-  return s;
+struct TileSmem {
+  unsigned long long prefix[PROBE_TILE + 1];
+  uint32_t off[PROBE_TILE];
+  unsigned long long warp_sums[PROBE_THREADS / 32 + 1];
+  unsigned long long base;
+  long long tile;
+};
+
+// build-side values of one match.  `off` = build row index (CSR position or entry index), OFF_MISS = pad with NULLs.
+struct BuildRow {
+  const uint64_t *row;
+  uint32_t mask;
+  uint64_t w0, w1;  // words 0 and 1 of the row when the caller already holds them in registers (ROW mode)
+  bool have01;
+  __device__ __forceinline__ uint64_t word(int w) const { return (have01 && w < 2) ? (w ? w1 : w0) : row[w]; }
+};
+__device__ __forceinline__ BuildRow build_row_of(const ProbeParams &p, bool want, uint32_t off, bool have01 = false, uint64_t w0 = 0, uint64_t w1 = 0) {
+  BuildRow b;
+  b.row = nullptr;
+  b.mask = 0;
+  b.have01 = have01;
+  b.w0 = w0;
+  b.w1 = w1;
+  if (want && off != OFF_MISS) {
+    b.row = p.build_rows + (uint64_t)off * (uint64_t)p.build_stride;
+    if (p.build_mask) b.mask = p.build_mask[off];
+    else if (p.build_mask_word >= 0) b.mask = (uint32_t)b.word(p.build_mask_word);
+    else b.mask = 0xFFFFFFFFu;
+  }
+  return b;
 }
 
-__global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeParams p, const JoinTable t) {
-  __shared__ unsigned long long s_prefix[PROBE_TILE + 1];
-  __shared__ uint32_t s_off[PROBE_TILE];
-  __shared__ unsigned long long s_warp_sums[PROBE_THREADS / 32 + 1];
-  __shared__ unsigned long long s_base;
+// Look one key up.  Returns (off, cnt): CSR mode = CSR segment; ROW mode = (entry index, 1).  cnt == 0: miss.
+// `first` is the already-loaded (word0, word1) of the home entry at partition-local index loc.
+template <bool SMEM>
+__device__ __forceinline__ uint2 resolve(const JoinTable &t, const uint64_t *tbl /*partition base (global or smem)*/, uint64_t ebase, uint64_t key,
+                                         uint32_t loc, ulonglong2 &cur /* in: home entry; out: matched entry (word0, word1) */) {
+  while (cur.x != key && cur.x != EMPTY_KEY) {  // linear probing; short at load factor <= 0.5
+    loc = (loc + 1) & (uint32_t)t.mask;
+    cur = ld_entry(tbl, loc, t.shift);
+  }
+  if (cur.x != key) return make_uint2(OFF_MISS, 0);
+  if (t.row_mode) return make_uint2((uint32_t)(ebase + loc), 1u);
+  return make_uint2((uint32_t)cur.y, (uint32_t)(cur.y >> 32));
+}
 
+// Phase B: exclusive scan of the tile's PROBE_TILE match counts (held in sm.prefix as counts on entry).
+// Returns the tile total M; sm.prefix[0..TILE] holds the exclusive prefix afterwards.
+__device__ __forceinline__ unsigned long long tile_scan(TileSmem &sm, unsigned &matched_acc, bool &any_multi) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long c4[PROBE_ROWS_PER_THREAD], tsum = 0;
+  unsigned matched = 0;
+#pragma unroll
+  for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
+    c4[k] = sm.prefix[tid * PROBE_ROWS_PER_THREAD + k];
+    tsum += c4[k];
+    matched += (sm.off[tid * PROBE_ROWS_PER_THREAD + k] != OFF_MISS);
+  }
+  const bool my_multi = (c4[0] > 1) | (c4[1] > 1) | (c4[2] > 1) | (c4[3] > 1);
+  unsigned long long inc = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += v;
+  }
+  matched = __reduce_add_sync(0xffffffffu, matched);
+  if (lane == 31) sm.warp_sums[warp] = inc;
+  any_multi = __syncthreads_or(my_multi) != 0;  // (barrier) also orders the c4 reads before the prefix writes below
+  if (warp == 0) {
+    unsigned long long w = (lane < PROBE_THREADS / 32) ? sm.warp_sums[lane] : 0;
+    unsigned long long winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += v;
+    }
+    if (lane < PROBE_THREADS / 32) sm.warp_sums[lane] = winc - w;
+    if (lane == PROBE_THREADS / 32 - 1) sm.warp_sums[PROBE_THREADS / 32] = winc;
+  }
+  if (lane == 0) matched_acc += matched;  // per-warp running total; flushed once per CTA (one same-address atomic, not one per tile)
+  __syncthreads();
+  unsigned long long run = inc - tsum + sm.warp_sums[warp];
+#pragma unroll
+  for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
+    sm.prefix[tid * PROBE_ROWS_PER_THREAD + k] = run;
+    run += c4[k];
+  }
+  const unsigned long long M = sm.warp_sums[PROBE_THREADS / 32];
+  if (tid == 0) sm.prefix[PROBE_TILE] = M;
+  return M;
+}
+
+// Phase D, general: output-centric expansion.  Thread per OUTPUT row q in [base, base+M): binary search of the
+// tile prefix gives the probe row r and the index j of the match inside the key's CSR segment; column stores are
+// coalesced along q and the null-bitmap words are assembled with ballots (warp iterations are aligned to
+// 32-row bitmap words; the partial first/last words of the tile are merged with atomicOr).
+__device__ __forceinline__ void tile_expand(const ProbeParams &p, const TileSmem &sm, int64_t tile_base, unsigned long long base,
+                                            unsigned long long M) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long base_al = base & ~31ull;
+  const unsigned long long end = base + M;
+  for (unsigned long long q0 = base_al + (unsigned long long)warp * 32; q0 < end; q0 += PROBE_THREADS) {
+    const unsigned long long q = q0 + lane;
+    const bool active = q >= base && q < end;
+    const bool full_word = q0 >= base && q0 + 32 <= end;
+    int r = 0;
+    unsigned long long j = 0;
+    uint32_t off = OFF_MISS;
+    if (active) {
+      const unsigned long long o = q - base;
+      int lo = 0, hi = PROBE_TILE;  // find r: prefix[r] <= o < prefix[r+1]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sm.prefix[mid] <= o) lo = mid; else hi = mid;
+      }
+      r = lo;
+      j = o - sm.prefix[r];
+      off = sm.off[r];
+    }
+    const int64_t row = tile_base + r;
+    for (int c = 0; c < p.n_probe_cols; c++) {
+      bool nn = false;
+      if (active) {
+        tqd::st_stream_u64(p.out_probe[c].data + q, p.probe[c].data[row]);
+        nn = tqd::bm_not_null(p.probe[c].bm, row);
+      }
+      if (p.out_probe[c].bm) {
+        const unsigned word = __ballot_sync(0xffffffffu, nn);
+        if (lane == 0 && word) {
+          if (full_word) p.out_probe[c].bm[q0 >> 5] = word;
+          else atomicOr(&p.out_probe[c].bm[q0 >> 5], word);
+        }
+      }
+    }
+    const BuildRow b = build_row_of(p, active, off == OFF_MISS ? OFF_MISS : (uint32_t)(off + j));
+    for (int c = 0; c < p.n_build_cols; c++) {
+      if (active) tqd::st_stream_u64(p.out_build[c].data + q, b.row ? b.word(p.build_word[c]) : 0ull);  // miss: defaultInner = NULL (builder.go:463-465)
+      if (p.out_build[c].bm) {
+        const unsigned word = __ballot_sync(0xffffffffu, (b.mask >> c) & 1u);
+        if (lane == 0 && word) {
+          if (full_word) p.out_build[c].bm[q0 >> 5] = word;
+          else atomicOr(&p.out_build[c].bm[q0 >> 5], word);
+        }
+      }
+    }
+  }
+}
+
+// OR `bit` into bm[q >> 5] for every active lane, one atomic per distinct word in the warp (q is monotone in the
+// lane index, so there are 1-2 distinct words).  All 32 lanes must call.
+__device__ __forceinline__ void warp_set_bits(uint32_t *bm, bool active, unsigned long long q, bool nn) {
+  const int lane = threadIdx.x & 31;
+  unsigned pending = __ballot_sync(0xffffffffu, active);
+  const unsigned long long widx = q >> 5;
+  const unsigned bit = (active && nn) ? (1u << (q & 31)) : 0u;
+  while (pending) {
+    const int leader = __ffs(pending) - 1;
+    const unsigned long long w = __shfl_sync(0xffffffffu, widx, leader);
+    const bool in_group = active && widx == w;
+    const unsigned word = __reduce_or_sync(0xffffffffu, in_group ? bit : 0u);
+    if (lane == leader && word) atomicOr(&bm[w], word);
+    pending &= ~__ballot_sync(0xffffffffu, in_group);
+  }
+}
+
+// Emit one output row (row-centric paths): probe columns of `row` + build row `off` at output position q.
+// All 32 lanes of the warp must call (the bitmap helper is warp-collective).
+__device__ __forceinline__ void emit_row(const ProbeParams &p, bool emit, int64_t row, uint64_t key, uint32_t off, unsigned long long q,
+                                         bool have01 = false, uint64_t w0 = 0, uint64_t w1 = 0) {
+  for (int c = 0; c < p.n_probe_cols; c++) {
+    bool nn = false;
+    if (emit) {
+      const uint64_t v = (c == p.key_col) ? key : tqd::ld_stream_u64(p.probe[c].data + row);
+      tqd::st_stream_u64(p.out_probe[c].data + q, v);
+      nn = tqd::bm_not_null(p.probe[c].bm, row);
+    }
+    if (p.out_probe[c].bm) warp_set_bits(p.out_probe[c].bm, emit, q, nn);
+  }
+  const BuildRow b = build_row_of(p, emit, off, have01, w0, w1);
+  for (int c = 0; c < p.n_build_cols; c++) {
+    if (emit) tqd::st_stream_u64(p.out_build[c].data + q, b.row ? b.word(p.build_word[c]) : 0ull);
+    if (p.out_build[c].bm) warp_set_bits(p.out_build[c].bm, emit, q, (b.mask >> c) & 1u);
+  }
+}
+
+// Phase D for tiles in which every probe row has at most one output (unique build keys / misses): row-centric.
+__device__ __forceinline__ void tile_emit_rowwise(const ProbeParams &p, const TileSmem &sm, int64_t tile_base, unsigned long long base,
+                                                  const uint64_t (&key)[PROBE_ROWS_PER_THREAD]) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
+    const int rl = k * PROBE_THREADS + tid;
+    const unsigned long long pre = sm.prefix[rl];
+    const bool emit = sm.prefix[rl + 1] != pre;
+    emit_row(p, emit, tile_base + rl, key[k], sm.off[rl], base + pre);
+  }
+}
+
+// ---- one-table probe (small build sides): ordered output
+__global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeParams p, const JoinTable t) {
+  __shared__ TileSmem sm;
+  const int tid = threadIdx.x;
   const int64_t n_tiles = (p.n + PROBE_TILE - 1) / PROBE_TILE;
   const uint64_t *keys = p.probe[p.key_col].data;
   const uint32_t *kbm = p.probe[p.key_col].bm;
+  unsigned matched_acc = 0;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (;;) {
+    if (tid == 0) sm.tile = (long long)atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const int64_t tile = sm.tile;
+    if (tile >= n_tiles) break;
     const int64_t tile_base = tile * PROBE_TILE;
     // ---- phase A: look up PROBE_ROWS_PER_THREAD keys per thread (coalesced: row = base + k*256 + tid)
     uint64_t key[PROBE_ROWS_PER_THREAD];
     bool valid[PROBE_ROWS_PER_THREAD];
-    Slot s[PROBE_ROWS_PER_THREAD];
-    uint64_t idx[PROBE_ROWS_PER_THREAD];
+    ulonglong2 first[PROBE_ROWS_PER_THREAD];
+    uint64_t ebase[PROBE_ROWS_PER_THREAD];
+    uint32_t loc[PROBE_ROWS_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
       const int64_t r = tile_base + k * PROBE_THREADS + tid;
@@ -237,140 +512,388 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeParams p, co
         const bool sel = p.selected ? (p.selected[r] != 0) : true;          // join.go:344 `!selected[i] || hasNull[i]` -> miss
         valid[k] = sel && key_valid(key[k], tqd::bm_not_null(kbm, r), p.key_mode);
       }
-      idx[k] = tqd::mix64(key[k]) & t.mask;
+      const uint64_t h = tqd::mix64(key[k]);
+      ebase[k] = part_of_hash(h, t.pbits) * (t.mask + 1);
+      loc[k] = (uint32_t)(h & t.mask);
     }
 #pragma unroll
-    for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {  // the 4 random 16-byte loads are issued back to back
-      if (valid[k] && key[k] != EMPTY_KEY) s[k] = ld_slot(t.slots + idx[k]);
-      else { s[k].key = EMPTY_KEY; s[k].off = 0; s[k].cnt = 0; }
+    for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {  // the 4 random entry loads are issued back to back
+      first[k] = make_ulonglong2(EMPTY_KEY, 0);
+      if (valid[k] && key[k] != EMPTY_KEY) first[k] = ld_entry(t.words, ebase[k] + loc[k], t.shift);
     }
 #pragma unroll
     for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
-      uint32_t off = OFF_MISS, cnt = 0;
+      uint2 m = make_uint2(OFF_MISS, 0);
       if (valid[k]) {
-        if (key[k] == EMPTY_KEY) {
-          if (t.sent_cnt) { off = t.sent_off; cnt = t.sent_cnt; }
-        } else {
-          Slot cur = s[k];
-          uint64_t i = idx[k];
-          while (cur.key != key[k] && cur.key != EMPTY_KEY) {  // linear probing; rare at load factor <= 0.5
-            i = (i + 1) & t.mask;
-            cur = ld_slot(t.slots + i);
-          }
-          if (cur.key == key[k]) { off = cur.off; cnt = cur.cnt; }
-        }
+        if (key[k] == EMPTY_KEY) { if (t.sent_cnt) m = make_uint2(t.sent_off, t.sent_cnt); }
+        else m = resolve<false>(t, t.words + (ebase[k] << t.shift), ebase[k], key[k], loc[k], first[k]);
       }
       const int64_t r = tile_base + k * PROBE_THREADS + tid;
-      const uint32_t c = cnt ? cnt : ((p.is_outer && r < p.n) ? 1u : 0u);  // onMissMatch
-      s_off[k * PROBE_THREADS + tid] = cnt ? off : OFF_MISS;
-      s_prefix[k * PROBE_THREADS + tid] = c;
+      const uint32_t c = m.y ? m.y : ((p.is_outer && r < p.n) ? 1u : 0u);  // onMissMatch
+      sm.off[k * PROBE_THREADS + tid] = m.y ? m.x : OFF_MISS;
+      sm.prefix[k * PROBE_THREADS + tid] = c;
     }
     __syncthreads();
-    // ---- phase B: exclusive scan of the tile's 1024 counts (thread owns 4 consecutive entries)
-    unsigned long long c4[PROBE_ROWS_PER_THREAD], tsum = 0;
-    unsigned matched = 0;
-#pragma unroll
-    for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
-      c4[k] = s_prefix[tid * PROBE_ROWS_PER_THREAD + k];
-      tsum += c4[k];
-      matched += (s_off[tid * PROBE_ROWS_PER_THREAD + k] != OFF_MISS);
-    }
-    unsigned long long inc = tsum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += v;
-    }
-    matched = __reduce_add_sync(0xffffffffu, matched);
-    if (lane == 31) s_warp_sums[warp] = inc;
-    __syncthreads();  // also orders the c4 reads before the prefix writes below
-    if (warp == 0) {
-      unsigned long long w = (lane < PROBE_THREADS / 32) ? s_warp_sums[lane] : 0;
-      unsigned long long winc = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long v = __shfl_up_sync(0xffffffffu, winc, d);
-        if (lane >= d) winc += v;
-      }
-      if (lane < PROBE_THREADS / 32) s_warp_sums[lane] = winc - w;
-      if (lane == PROBE_THREADS / 32 - 1) s_warp_sums[PROBE_THREADS / 32] = winc;
-    }
-    if (lane == 0 && matched) atomicAdd(p.cursor + 1, (unsigned long long)matched);
-    __syncthreads();
-    unsigned long long run = inc - tsum + s_warp_sums[warp];
-#pragma unroll
-    for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
-      s_prefix[tid * PROBE_ROWS_PER_THREAD + k] = run;
-      run += c4[k];
-    }
-    const unsigned long long M = s_warp_sums[PROBE_THREADS / 32];
+    bool any_multi;
+    const unsigned long long M = tile_scan(sm, matched_acc, any_multi);
     if (tid == 0) {
-      s_prefix[PROBE_TILE] = M;
-      s_base = M ? atomicAdd(p.cursor, M) : 0ull;  // ---- phase C: claim [base, base+M) of the output
-    }
-    __syncthreads();
-    const unsigned long long base = s_base;
-    // ---- phase D: output-centric expansion (skipped if this tile does not fit: the host re-runs the batch)
-    if (M && base + M <= p.capacity) {
-      const unsigned long long base_al = base & ~31ull;
-      const unsigned long long end = base + M;
-      for (unsigned long long q0 = base_al + (unsigned long long)warp * 32; q0 < end; q0 += PROBE_THREADS) {
-        const unsigned long long q = q0 + lane;
-        const bool active = q >= base && q < end;
-        const bool full_word = q0 >= base && q0 + 32 <= end;
-        int r = 0;
-        unsigned long long j = 0;
-        uint32_t off = OFF_MISS;
-        if (active) {
-          const unsigned long long o = q - base;
-          int lo = 0, hi = PROBE_TILE;  // find r: prefix[r] <= o < prefix[r+1]
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_prefix[mid] <= o) lo = mid; else hi = mid;
-          }
-          r = lo;
-          j = o - s_prefix[r];
-          off = s_off[r];
-        }
-        // physical row of entry r: entries are stored [k*256 + tid]
-        const int64_t row = tile_base + r;
-        for (int c = 0; c < p.n_probe_cols; c++) {
-          bool nn = false;
-          if (active) {
-            p.out_probe[c].data[q] = p.probe[c].data[row];
-            nn = tqd::bm_not_null(p.probe[c].bm, row);
-          }
-          if (p.out_probe[c].bm) {
-            const unsigned word = __ballot_sync(0xffffffffu, nn);
-            if (lane == 0 && word) {
-              if (full_word) p.out_probe[c].bm[q0 >> 5] = word;
-              else atomicOr(&p.out_probe[c].bm[q0 >> 5], word);
-            }
-          }
-        }
-        for (int c = 0; c < p.n_build_cols; c++) {
-          bool nn = false;
-          if (active) {
-            uint64_t v = 0;
-            if (off != OFF_MISS) {
-              const uint64_t bpos = (uint64_t)off + j;
-              v = p.build[c].data[bpos];
-              nn = tqd::bm_not_null(p.build[c].bm, (int64_t)bpos);
-            }
-            p.out_build[c].data[q] = v;  // defaultInner: NULL (builder.go:463-465)
-          }
-          if (p.out_build[c].bm) {
-            const unsigned word = __ballot_sync(0xffffffffu, nn);
-            if (lane == 0 && word) {
-              if (full_word) p.out_build[c].bm[q0 >> 5] = word;
-              else atomicOr(&p.out_build[c].bm[q0 >> 5], word);
-            }
-          }
+      // ---- phase C: output offset = sum of the totals of all earlier tiles (decoupled look-back), which
+      // makes the result order (probe row asc, build insertion asc) — the reference's order inside a chunk
+      constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL = (1ull << 62) - 1;
+      volatile unsigned long long *st = p.tile_state;
+      unsigned long long excl = 0;
+      if (tile > 0) {
+        st[tile] = FLAG_AGG | M;
+        for (int64_t prev = tile - 1;; prev--) {
+          unsigned long long v;
+          do { v = st[prev]; } while ((v >> 62) == 0);
+          excl += v & VAL;
+          if ((v >> 62) == 2) break;
         }
       }
+      st[tile] = FLAG_INC | (excl + M);
+      if (M) atomicAdd(p.cursor, M);
+      sm.base = excl;
+    }
+    __syncthreads();
+    const unsigned long long base = sm.base;
+    if (M && base + M <= p.capacity) {  // else: the host re-runs the batch with the exact size
+      if (any_multi) tile_expand(p, sm, tile_base, base, M);
+      else tile_emit_rowwise(p, sm, tile_base, base, key);
     }
     __syncthreads();  // smem is reused by the next tile
   }
+  if ((tid & 31) == 0 && matched_acc) atomicAdd(p.cursor + 1, (unsigned long long)matched_acc);
+}
+
+// ---- probe-side radix scatter -------------------------------------------------------------------------
+static constexpr int SCAT_THREADS = 256;
+static constexpr int SCAT_ROWS_PER_THREAD = 16;
+static constexpr int SCAT_TILE = SCAT_THREADS * SCAT_ROWS_PER_THREAD;
+static constexpr uint32_t PID_DROP = 0xFFFFFFFFu;
+
+struct ScatterParams {
+  int n_cols;
+  DCol in[MAXC];
+  DColMut out[MAXC];
+  const uint8_t *selected;
+  int key_col, key_mode, is_outer, pbits;
+  int64_t n;
+  uint32_t *part_cnt;     // histogram (2^pbits + 1 bins; the last bin = rows that cannot match)
+  uint32_t *part_cursor;  // scatter cursors, initialised to the exclusive scan of part_cnt
+};
+
+__device__ __forceinline__ uint32_t probe_pid(const ScatterParams &p, int64_t r, uint64_t key) {
+  const bool sel = p.selected ? (p.selected[r] != 0) : true;
+  if (sel && key_valid(key, tqd::bm_not_null(p.in[p.key_col].bm, r), p.key_mode)) return (uint32_t)part_of_hash(tqd::mix64(key), p.pbits);
+  return p.is_outer ? (1u << p.pbits) : PID_DROP;  // inner join: a row that cannot match produces nothing (joiner.go:405)
+}
+
+__global__ void __launch_bounds__(SCAT_THREADS) k_probe_part_hist(const ScatterParams p) {
+  extern __shared__ uint32_t s_hist[];
+  const int n_bins = (1 << p.pbits) + 1;
+  for (int i = threadIdx.x; i < n_bins; i += SCAT_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  const uint64_t *keys = p.in[p.key_col].data;
+  int64_t i = (int64_t)blockIdx.x * SCAT_THREADS + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * SCAT_THREADS;
+  for (; i < p.n; i += stride) {
+    const uint32_t pid = probe_pid(p, i, tqd::ld_stream_u64(keys + i));
+    if (pid != PID_DROP) atomicAdd(&s_hist[pid], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < n_bins; b += SCAT_THREADS)
+    if (s_hist[b]) atomicAdd(&p.part_cnt[b], s_hist[b]);
+}
+
+// One tile = SCAT_TILE (4096) rows.  The tile is counting-sorted by partition in shared memory (histogram -> local
+// exclusive scan -> sorted position per row), each non-empty partition claims its run with ONE global
+// atomicAdd, and every column then goes global -> shared (coalesced, at the row's sorted position) ->
+// global (coalesced, consecutive lanes store consecutive destinations: whole 32-byte sectors).
+__global__ void __launch_bounds__(SCAT_THREADS, 4) k_probe_scatter(const ScatterParams p) {
+  extern __shared__ __align__(16) unsigned char s_scat[];
+  const int n_bins = (1 << p.pbits) + 1;
+  uint64_t *s_stage = reinterpret_cast<uint64_t *>(s_scat);                       // [SCAT_TILE] one column of the tile, sorted
+  uint32_t *s_bins = reinterpret_cast<uint32_t *>(s_scat + SCAT_TILE * 8);        // [n_bins] tile counts, then local exclusive offsets
+  uint32_t *s_gdelta = s_bins + n_bins;                                           // [n_bins] (claimed global run start) - (local offset)
+  uint16_t *s_spid = reinterpret_cast<uint16_t *>(s_gdelta + n_bins);             // [SCAT_TILE] sorted position -> partition
+  uint8_t *s_nn = reinterpret_cast<uint8_t *>(s_spid + SCAT_TILE);                // [SCAT_TILE] sorted position -> NOT NULL flag
+  __shared__ uint32_t s_warp[SCAT_THREADS / 32 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bpt = (n_bins + SCAT_THREADS - 1) / SCAT_THREADS;  // bins per thread in the scan
+  const uint64_t *keys = p.in[p.key_col].data;
+  const int64_t n_tiles = (p.n + SCAT_TILE - 1) / SCAT_TILE;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t tile_base = tile * SCAT_TILE;
+    for (int b = tid; b < n_bins; b += SCAT_THREADS) s_bins[b] = 0;
+    __syncthreads();
+    uint32_t pid[SCAT_ROWS_PER_THREAD], spos[SCAT_ROWS_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < SCAT_ROWS_PER_THREAD; k++) {
+      const int64_t r = tile_base + k * SCAT_THREADS + tid;
+      pid[k] = PID_DROP;
+      if (r < p.n) pid[k] = probe_pid(p, r, keys[r]);
+      spos[k] = (pid[k] != PID_DROP) ? atomicAdd(&s_bins[pid[k]], 1u) : 0u;  // rank inside the partition
+    }
+    __syncthreads();
+    // exclusive scan over the bins (thread t owns bins [t*bpt, (t+1)*bpt))
+    uint32_t tsum = 0;
+    for (int q = 0; q < bpt; q++) { const int b = tid * bpt + q; if (b < n_bins) tsum += s_bins[b]; }
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = (lane < SCAT_THREADS / 32) ? s_warp[lane] : 0, winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += v; }
+      if (lane < SCAT_THREADS / 32) s_warp[lane] = winc - w;
+      if (lane == SCAT_THREADS / 32 - 1) s_warp[SCAT_THREADS / 32] = winc;
+    }
+    __syncthreads();
+    uint32_t run = inc - tsum + s_warp[warp];
+    for (int q = 0; q < bpt; q++) {
+      const int b = tid * bpt + q;
+      if (b < n_bins) {
+        const uint32_t c = s_bins[b];
+        s_bins[b] = run;
+        if (c) s_gdelta[b] = atomicAdd(&p.part_cursor[b], c) - run;
+        run += c;
+      }
+    }
+    const uint32_t total = s_warp[SCAT_THREADS / 32];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SCAT_ROWS_PER_THREAD; k++) {
+      if (pid[k] == PID_DROP) continue;
+      spos[k] += s_bins[pid[k]];
+      s_spid[spos[k]] = (uint16_t)pid[k];
+    }
+    for (int c = 0; c < p.n_cols; c++) {
+      const bool has_bm = p.out[c].bm != nullptr;
+#pragma unroll
+      for (int k = 0; k < SCAT_ROWS_PER_THREAD; k++) {
+        if (pid[k] == PID_DROP) continue;
+        const int64_t r = tile_base + k * SCAT_THREADS + tid;
+        s_stage[spos[k]] = p.in[c].data[r];
+        if (has_bm) s_nn[spos[k]] = (uint8_t)tqd::bm_not_null(p.in[c].bm, r);
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < total; i += SCAT_THREADS) {
+        const uint32_t dst = s_gdelta[s_spid[i]] + i;
+        tqd::st_stream_u64(p.out[c].data + dst, s_stage[i]);
+        if (has_bm && s_nn[i]) atomicOr(&p.out[c].bm[dst >> 5], 1u << (dst & 31));
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- partitioned probe: the partition's table image lives in shared memory ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+               "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(mbar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Common prologue of the partitioned probe kernels: which rows does this CTA own, where is its table.
+struct PartCtx {
+  uint32_t part;
+  int64_t p_lo, p_hi, t_lo, t_hi;
+  bool has_table, use_smem;
+  const uint64_t *tbl;  // partition table (global memory, or the shared-memory image once loaded)
+  uint64_t ebase;       // first entry index of the partition
+};
+__device__ __forceinline__ bool part_prologue(const ProbeParams &p, const JoinTable &t, unsigned char *s_dyn, uint64_t *s_mbar, PartCtx &c) {
+  const uint32_t n_parts = 1u << t.pbits;
+  c.part = blockIdx.x / p.split;
+  const uint32_t sub = blockIdx.x % p.split;
+  c.p_lo = p.part_off[c.part];
+  c.p_hi = p.part_off[c.part + 1];
+  const int64_t p_tiles = (c.p_hi - c.p_lo + PROBE_TILE - 1) / PROBE_TILE;
+  c.t_lo = p_tiles * sub / p.split;
+  c.t_hi = p_tiles * (sub + 1) / p.split;
+  if (c.t_lo >= c.t_hi) return false;
+  c.has_table = c.part < n_parts;  // partition n_parts: rows that cannot match (outer joins only)
+  const uint64_t cap = t.mask + 1;
+  c.ebase = (uint64_t)(c.has_table ? c.part : 0) * cap;
+  c.tbl = t.words + (c.ebase << t.shift);
+  // Small partition tables are copied into shared memory by TMA; larger ones are probed in place — consecutive
+  // CTAs work on the same partition, so only a few partition tables are live at a time and they stay in L2.
+  c.use_smem = c.has_table && p.table_in_smem;
+  if (c.use_smem) {
+    if (threadIdx.x == 0) {
+      mbar_init(s_mbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)((cap << t.shift) * 8);
+      mbar_expect_tx(s_mbar, bytes);
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(c.tbl);
+      for (uint32_t o = 0; o < bytes; o += 16384) tma_load_1d(s_dyn + o, src + o, min(16384u, bytes - o), s_mbar);
+    }
+    c.tbl = reinterpret_cast<const uint64_t *>(s_dyn);
+  }
+  return true;
+}
+
+// ---- partitioned probe, UNIQUE build keys (PK-FK joins): every probe row yields 0 or 1 rows ---------------
+// Lean variant: warp w of the CTA owns rows [w*128, w*128+128) of the tile; matches are compacted with
+// ballots, a shared-memory atomic orders the 8 warps inside the tile and one global atomic claims the tile's
+// output range — two barriers per tile, no prefix arrays, no search.
+__global__ void __launch_bounds__(PROBE_THREADS) k_probe_part_uniq(const ProbeParams p, const JoinTable t) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ unsigned s_total[2];
+  __shared__ unsigned long long s_base[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PartCtx cx;
+  if (!part_prologue(p, t, s_dyn, &s_mbar, cx)) return;
+  if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
+  __syncthreads();
+  const uint64_t *keys = p.probe[p.key_col].data;
+  const unsigned lt_mask = (1u << lane) - 1;
+  unsigned matched_acc = 0;
+  bool table_ready = !cx.use_smem;
+  constexpr int R = PROBE_ROWS_PER_THREAD;
+  for (int64_t tile = cx.t_lo; tile < cx.t_hi; tile++) {
+    const int par = (int)(tile & 1);
+    const int64_t wbase = cx.p_lo + tile * PROBE_TILE + warp * (32 * R);  // this warp's 128 rows
+    uint64_t key[R];
+    bool inb[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const int64_t r = wbase + k * 32 + lane;
+      inb[k] = r < cx.p_hi;
+      key[k] = inb[k] ? tqd::ld_stream_u64(keys + r) : 0;
+    }
+    if (!table_ready) { mbar_wait(&s_mbar, 0); table_ready = true; }  // the key loads above overlap the table copy
+    uint32_t loc[R];
+    ulonglong2 first[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {  // independent entry loads issued back to back
+      loc[k] = (uint32_t)(tqd::mix64(key[k]) & t.mask);
+      first[k] = make_ulonglong2(EMPTY_KEY, 0);
+      if (inb[k] && cx.has_table && key[k] != EMPTY_KEY) first[k] = ld_entry(cx.tbl, loc[k], t.shift);
+    }
+    uint32_t off[R];
+    unsigned bal[R];
+    unsigned wcnt = 0;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      off[k] = OFF_MISS;
+      if (inb[k] && cx.has_table) {  // every row of a regular partition has a valid key (the scatter filtered the rest)
+        if (key[k] == EMPTY_KEY) { if (t.sent_cnt) off[k] = t.sent_off; }
+        else off[k] = resolve<true>(t, cx.tbl, cx.ebase, key[k], loc[k], first[k]).x;  // first[k] now holds the matched entry
+      }
+      const bool emit = inb[k] && (off[k] != OFF_MISS || p.is_outer);
+      bal[k] = __ballot_sync(0xffffffffu, emit);
+      wcnt += __popc(bal[k]);
+      const unsigned mb = __ballot_sync(0xffffffffu, off[k] != OFF_MISS);
+      if (lane == 0) matched_acc += __popc(mb);
+    }
+    unsigned woff = 0;
+    if (lane == 0 && wcnt) woff = atomicAdd(&s_total[par], wcnt);
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned tot = s_total[par];
+      s_base[par] = tot ? atomicAdd(p.cursor, (unsigned long long)tot) : 0ull;
+      s_total[par] = 0;  // next use of this parity is two tiles away, behind two more barriers
+    }
+    __syncthreads();
+    unsigned long long q0 = s_base[par] + __shfl_sync(0xffffffffu, woff, 0);
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const unsigned long long q = q0 + __popc(bal[k] & lt_mask);
+      q0 += __popc(bal[k]);
+      const bool emit = ((bal[k] >> lane) & 1u) && q < p.capacity;  // capacity == probe rows: always fits for unique keys
+      // ROW mode: words 0/1 of the build row are already in registers (the matched entry)
+      emit_row(p, emit, wbase + k * 32 + lane, key[k], off[k], q, t.row_mode && key[k] != EMPTY_KEY, first[k].x, first[k].y);
+    }
+  }
+  if (lane == 0 && matched_acc) atomicAdd(p.cursor + 1, (unsigned long long)matched_acc);
+}
+
+// ---- partitioned probe, general (duplicate build keys): block scan + output-centric expansion ------------
+__global__ void __launch_bounds__(PROBE_THREADS) k_probe_part(const ProbeParams p, const JoinTable t) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ TileSmem sm;
+  __shared__ __align__(8) uint64_t s_mbar;
+
+  const int tid = threadIdx.x;
+  PartCtx cx;
+  if (!part_prologue(p, t, s_dyn, &s_mbar, cx)) return;
+  const uint64_t *keys = p.probe[p.key_col].data;
+  unsigned matched_acc = 0;
+  bool table_ready = !cx.use_smem;
+  for (int64_t tile = cx.t_lo; tile < cx.t_hi; tile++) {
+    const int64_t tile_base = cx.p_lo + tile * PROBE_TILE;
+    uint64_t key[PROBE_ROWS_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
+      const int64_t r = tile_base + k * PROBE_THREADS + tid;
+      key[k] = (r < cx.p_hi) ? tqd::ld_stream_u64(keys + r) : 0;
+    }
+    if (!table_ready) { mbar_wait(&s_mbar, 0); table_ready = true; }
+    uint32_t loc[PROBE_ROWS_PER_THREAD];
+    ulonglong2 first[PROBE_ROWS_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
+      const int64_t r = tile_base + k * PROBE_THREADS + tid;
+      loc[k] = (uint32_t)(tqd::mix64(key[k]) & t.mask);
+      first[k] = make_ulonglong2(EMPTY_KEY, 0);
+      if (r < cx.p_hi && cx.has_table && key[k] != EMPTY_KEY) first[k] = ld_entry(cx.tbl, loc[k], t.shift);
+    }
+#pragma unroll
+    for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
+      const int64_t r = tile_base + k * PROBE_THREADS + tid;
+      uint2 m = make_uint2(OFF_MISS, 0);
+      if (r < cx.p_hi && cx.has_table) {
+        if (key[k] == EMPTY_KEY) { if (t.sent_cnt) m = make_uint2(t.sent_off, t.sent_cnt); }
+        else m = resolve<true>(t, cx.tbl, cx.ebase, key[k], loc[k], first[k]);
+      }
+      const uint32_t c = m.y ? m.y : ((p.is_outer && r < cx.p_hi) ? 1u : 0u);
+      sm.off[k * PROBE_THREADS + tid] = m.y ? m.x : OFF_MISS;
+      sm.prefix[k * PROBE_THREADS + tid] = c;
+    }
+    __syncthreads();
+    bool any_multi;
+    const unsigned long long M = tile_scan(sm, matched_acc, any_multi);
+    if (tid == 0) sm.base = M ? atomicAdd(p.cursor, M) : 0ull;  // partition-major output: order across tiles is free
+    __syncthreads();
+    const unsigned long long base = sm.base;
+    if (M && base + M <= p.capacity) {
+      if (any_multi) tile_expand(p, sm, tile_base, base, M);
+      else tile_emit_rowwise(p, sm, tile_base, base, key);
+    }
+    __syncthreads();
+  }
+  if ((tid & 31) == 0 && matched_acc) atomicAdd(p.cursor + 1, (unsigned long long)matched_acc);
 }
 
 // ------------------------------------------------------------------ host side
@@ -462,10 +985,17 @@ struct tq_join {
   int64_t n_build = 0;
   std::vector<DevColBuf> b_cols;          // materialised inner side (owned) ...
   std::vector<DCol> b_view;               // ... or borrowed view
-  std::vector<DevColBuf> csr_cols;        // build columns in CSR order
+  DevBuf csr_rows, csr_mask;              // build rows in CSR order, row-major (+ per-row NOT-NULL mask)
+  bool build_has_nulls = false;
   DevBuf slots, row_slot, row_ids, counters, worklist, scan_scratch;
+  int shift = 1;                          // log2(words per table entry)
+  bool row_mode = false;                  // unique build keys: the entries hold the build rows
+  int row_word[MAXC];                     // ROW mode: word of build column c inside the entry
+  int row_mask_word = -1;
   JoinTable table{};
   uint64_t n_slots = 0;
+  int pbits = 0;                          // log2(#partition tables); 0 = one global table
+  DevBuf b_part_cnt;
   int64_t n_valid = 0, n_distinct = 0;
   bool build_unique = true;
   int64_t build_ns = 0;
@@ -478,6 +1008,10 @@ struct tq_join {
   int in_flip = 0;
   PinBuf p_sel_pin[2];
   DevBuf cursors;                         // 2 x {rows, matched} device counters
+  DevBuf tile_state[2];                   // per cursor slot: look-back words + ticket
+  std::vector<DevColBuf> part_cols[2];    // per cursor slot: probe columns in partition order
+  DevBuf part_cnt[2], part_off[2], part_cursor[2];
+  DevBuf scan_scratch2;
   PinBuf cursors_host;
   PendingBatch pending;
   std::deque<std::unique_ptr<ResultBatch>> results;
@@ -528,76 +1062,145 @@ static int32_t join_build(tq_join *j) {
   cudaStream_t s = r.compute;
   const int64_t n = j->n_build;
   TQ_CUDA(cudaEventRecord(j->ev_a[0], s));
-  // table of distinct keys at load factor <= 0.5
-  uint64_t n_slots = 64;
-  while (n_slots < (uint64_t)n * 2) n_slots <<= 1;
-  if (n_slots > 0xFFFFFFF0ull) { set_error("build side too large: %lld rows", (long long)n); return TQ_ERR_INVALID_ARG; }
-  j->n_slots = n_slots;
-  TQ_TRY(j->slots.reserve(n_slots * sizeof(Slot)));
-  TQ_TRY(j->row_slot.reserve((size_t)(n ? n : 1) * 4));
-  TQ_TRY(j->row_ids.reserve((size_t)(n ? n : 1) * 4));
+  const DCol key = j->b_view[j->build_key];
   TQ_TRY(j->counters.reserve(64));
-  const uint32_t worklist_cap = (uint32_t)((n / 33) + 2);
-  TQ_TRY(j->worklist.reserve((size_t)worklist_cap * 8));
-  Slot *slots = j->slots.as<Slot>();
   uint32_t *counters = j->counters.as<uint32_t>();
   TQ_CUDA(cudaMemsetAsync(counters, 0, 64, s));
-  k_init_slots<<<stream_grid((int64_t)n_slots), 256, 0, s>>>(slots, n_slots);
+  j->build_has_nulls = false;
+  for (int c = 0; c < j->n_build_cols; c++) j->build_has_nulls |= (j->b_view[c].bm != nullptr);
+  // entry layout: ROW mode needs key + other columns (+ mask word) to fit 2 or 4 words
+  const int row_words = j->n_build_cols + (j->build_has_nulls ? 1 : 0);
+  const bool row_candidate = row_words <= 4;
+  const int shift = (row_candidate && row_words > 2) ? 2 : 1;
+  j->shift = shift;
+  // Partitioning: ~g_part_target_rows build rows per partition table; small build sides keep ONE table.
+  uint64_t n_slots = 64, cap = 0;
+  int pbits = 0;
+  if (n >= PART_MIN_BUILD_ROWS && !g_force_global_table) {
+    uint64_t P = 1;
+    while (P * (uint64_t)g_part_target_rows < (uint64_t)n) P <<= 1;
+    while ((1ull << pbits) < P) pbits++;
+    if (pbits > PART_MAX_BITS) pbits = PART_MAX_BITS;
+    P = 1ull << pbits;
+    TQ_TRY(j->b_part_cnt.reserve(P * 4));
+    TQ_CUDA(cudaMemsetAsync(j->b_part_cnt.p, 0, P * 4, s));
+    k_build_part_hist<<<stream_grid(n), 256, 0, s>>>(key.data, key.bm, n, j->key_mode, pbits, j->b_part_cnt.as<uint32_t>());
+    k_max_u32<<<1, 1024, 0, s>>>(j->b_part_cnt.as<uint32_t>(), (int)P, counters + 4);
+    count_launch(2);
+    TQ_TRY(check_launch("k_build_part_hist"));
+    uint32_t max_cnt = 0;
+    TQ_CUDA(cudaMemcpyAsync(&max_cnt, counters + 4, 4, cudaMemcpyDeviceToHost, s));
+    TQ_CUDA(cudaStreamSynchronize(s));
+    cap = 64;
+    while (cap < (uint64_t)max_cnt * 2) cap <<= 1;        // load factor <= 0.5 in the fullest partition (short probe sequences)
+    if (cap * P > (uint64_t)n * 12 + 4096) { pbits = 0; cap = 0; }  // heavily skewed hash partitions: one table instead
+    else n_slots = P * cap;
+  }
+  if (pbits == 0) {
+    while (n_slots < (uint64_t)n * 2) n_slots <<= 1;       // one table at load factor <= 0.5
+    cap = n_slots;
+  }
+  j->pbits = pbits;
+  if (n_slots > 0xFFFFFFF0ull) { set_error("build side too large: %lld rows", (long long)n); return TQ_ERR_INVALID_ARG; }
+  j->n_slots = n_slots;
+  const uint64_t n_entries = n_slots + 1;  // +1: side entry for the EMPTY_KEY-valued key in ROW mode
+  TQ_TRY(j->slots.reserve((n_entries << shift) * 8));
+  TQ_TRY(j->row_slot.reserve((size_t)(n ? n : 1) * 4));
+  uint64_t *words = j->slots.as<uint64_t>();
+  k_init_table<<<stream_grid((int64_t)(n_entries << shift)), 256, 0, s>>>(words, n_entries, shift);
   count_launch();
-  const DCol key = j->b_view[j->build_key];
   if (n > 0) {
-    k_build_insert<<<stream_grid(n), 256, 0, s>>>(key.data, key.bm, n, j->key_mode, slots, n_slots - 1, j->row_slot.as<uint32_t>(), counters);
+    k_build_insert<<<stream_grid(n), 256, 0, s>>>(key.data, key.bm, n, j->key_mode, words, cap - 1, pbits, shift, j->row_slot.as<uint32_t>(), counters);
     count_launch();
   }
   TQ_TRY(check_launch("k_build_insert"));
-  // CSR offsets: exclusive scan of slot counts, written into slot.off (AoS stride: 4 words)
-  uint64_t *d_total = reinterpret_cast<uint64_t *>(counters + 8);
-  TQ_TRY(exclusive_scan_u32(&slots[0].cnt, 4, &slots[0].off, 4, (int64_t)n_slots, d_total, j->scan_scratch, s));
   uint32_t h_counters[16];
   TQ_CUDA(cudaMemcpyAsync(h_counters, counters, 64, cudaMemcpyDeviceToHost, s));
   TQ_CUDA(cudaStreamSynchronize(s));
-  const uint64_t total_regular = *reinterpret_cast<uint64_t *>(h_counters + 8);
   const uint32_t sent_cnt = h_counters[0];
-  j->n_valid = (int64_t)(total_regular + sent_cnt);
-  j->table.slots = slots;
-  j->table.mask = n_slots - 1;
-  j->table.sent_off = (uint32_t)total_regular;
-  j->table.sent_cnt = sent_cnt;
-  if (n > 0) {
-    k_build_fill<<<stream_grid(n), 256, 0, s>>>(j->row_slot.as<uint32_t>(), n, slots, j->table.sent_off, counters, j->row_ids.as<uint32_t>());
-    count_launch();
-  }
-  k_build_fixsort<<<stream_grid((int64_t)n_slots), 256, 0, s>>>(slots, n_slots, j->row_ids.as<uint32_t>(), counters, j->worklist.as<uint2>(), worklist_cap);
-  count_launch();
-  TQ_TRY(check_launch("k_build_fixsort"));
-  TQ_CUDA(cudaMemcpyAsync(h_counters, counters, 64, cudaMemcpyDeviceToHost, s));
-  TQ_CUDA(cudaStreamSynchronize(s));
-  uint32_t n_large = h_counters[3];
-  j->n_distinct = (int64_t)h_counters[2] + (sent_cnt ? 1 : 0);
+  const int64_t valid_regular = h_counters[5], distinct_regular = h_counters[2];
+  j->n_valid = valid_regular + sent_cnt;
+  j->n_distinct = distinct_regular + (sent_cnt ? 1 : 0);
   j->build_unique = (j->n_distinct == j->n_valid);
-  if (sent_cnt > 1) {  // the sentinel-key segment is sorted like any other large segment
-    uint2 w = make_uint2(j->table.sent_off, sent_cnt);
-    TQ_CUDA(cudaMemcpyAsync(j->worklist.as<uint2>() + n_large, &w, sizeof(w), cudaMemcpyHostToDevice, s));
-    n_large++;
-  }
-  if (n_large) {
-    k_sort_large<<<n_large, 256, 0, s>>>(j->worklist.as<uint2>(), j->row_ids.as<uint32_t>());
-    count_launch();
-    TQ_TRY(check_launch("k_sort_large"));
-  }
-  // build columns into CSR order
-  j->csr_cols.resize(j->n_build_cols);
-  const int64_t nv = j->n_valid;
-  for (int c = 0; c < j->n_build_cols; c++) {
-    TQ_TRY(j->csr_cols[c].data.reserve((size_t)(nv ? nv : 1) * 8));
-    TQ_TRY(j->csr_cols[c].bm.reserve(bitmap_alloc_bytes(nv)));
-    if (nv) {
-      k_gather_col<<<stream_grid(nv), 256, 0, s>>>(j->b_view[c].data, j->b_view[c].bm, j->row_ids.as<uint32_t>(), nv,
-                                                    j->csr_cols[c].data.as<uint64_t>(), j->csr_cols[c].bm.as<uint32_t>());
+  j->table.words = words;
+  j->table.mask = cap - 1;
+  j->table.pbits = pbits;
+  j->table.shift = shift;
+  j->row_mode = j->build_unique && row_candidate;
+  j->table.row_mode = j->row_mode ? 1 : 0;
+  if (j->row_mode) {
+    // ---- ROW mode: the claiming row writes its columns into the entry; nothing else to do
+    BuildRowParams b{};
+    b.n_cols = j->n_build_cols;
+    b.key_col = j->build_key;
+    int w = 1;
+    for (int c = 0; c < j->n_build_cols; c++) {
+      b.cols[c] = j->b_view[c];
+      j->row_word[c] = (c == j->build_key) ? 0 : w++;
+      b.word_of_col[c] = j->row_word[c];
+    }
+    j->row_mask_word = j->build_has_nulls ? w : -1;
+    b.mask_word = j->row_mask_word;
+    b.row_slot = j->row_slot.as<uint32_t>();
+    b.n = n;
+    b.words = words;
+    b.shift = shift;
+    b.sent_entry = (uint32_t)n_slots;
+    j->table.sent_off = (uint32_t)n_slots;
+    j->table.sent_cnt = sent_cnt;
+    if (n > 0) {
+      k_build_rows<<<stream_grid(n), 256, 0, s>>>(b);
+      count_launch();
+      TQ_TRY(check_launch("k_build_rows"));
+    }
+  } else {
+    // ---- CSR mode: exclusive scan of the entry counts (high half of word 1) into the offsets (low half)
+    TQ_TRY(j->row_ids.reserve((size_t)(n ? n : 1) * 4));
+    const uint32_t worklist_cap = (uint32_t)((n / 33) + 2);
+    TQ_TRY(j->worklist.reserve((size_t)worklist_cap * 8));
+    uint32_t *w32 = reinterpret_cast<uint32_t *>(words);
+    const int stride32 = 2 << shift;
+    uint64_t *d_total = reinterpret_cast<uint64_t *>(counters + 8);
+    TQ_TRY(exclusive_scan_u32(w32 + 3, stride32, w32 + 2, stride32, (int64_t)n_slots, d_total, j->scan_scratch, s));
+    j->table.sent_off = (uint32_t)valid_regular;  // the EMPTY_KEY-valued key's segment follows all regular segments
+    j->table.sent_cnt = sent_cnt;
+    if (n > 0) {
+      k_build_fill<<<stream_grid(n), 256, 0, s>>>(j->row_slot.as<uint32_t>(), n, words, shift, j->table.sent_off, counters, j->row_ids.as<uint32_t>());
       count_launch();
     }
+    k_build_fixsort<<<stream_grid((int64_t)n_slots), 256, 0, s>>>(words, n_slots, shift, j->row_ids.as<uint32_t>(), counters, j->worklist.as<uint2>(), worklist_cap);
+    count_launch();
+    TQ_TRY(check_launch("k_build_fixsort"));
+    TQ_CUDA(cudaMemcpyAsync(h_counters, counters, 64, cudaMemcpyDeviceToHost, s));
+    TQ_CUDA(cudaStreamSynchronize(s));
+    uint32_t n_large = h_counters[3];
+    if (sent_cnt > 1) {  // the sentinel-key segment is sorted like any other large segment
+      uint2 w = make_uint2(j->table.sent_off, sent_cnt);
+      TQ_CUDA(cudaMemcpyAsync(j->worklist.as<uint2>() + n_large, &w, sizeof(w), cudaMemcpyHostToDevice, s));
+      n_large++;
+    }
+    if (n_large) {
+      k_sort_large<<<n_large, 256, 0, s>>>(j->worklist.as<uint2>(), j->row_ids.as<uint32_t>());
+      count_launch();
+      TQ_TRY(check_launch("k_sort_large"));
+    }
+    // build rows into CSR order, packed row-major
+    const int64_t nv = j->n_valid;
+    TQ_TRY(j->csr_rows.reserve((size_t)(nv ? nv : 1) * 8 * j->n_build_cols));
+    if (j->build_has_nulls) TQ_TRY(j->csr_mask.reserve((size_t)(nv ? nv : 1) * 4));
+    if (nv) {
+      GatherParams g{};
+      g.n_cols = j->n_build_cols;
+      for (int c = 0; c < j->n_build_cols; c++) g.cols[c] = j->b_view[c];
+      g.row_ids = j->row_ids.as<uint32_t>();
+      g.n = nv;
+      g.out_rows = j->csr_rows.as<uint64_t>();
+      g.out_mask = j->build_has_nulls ? j->csr_mask.as<uint32_t>() : nullptr;
+      k_gather_rows<<<stream_grid(nv), 256, 0, s>>>(g);
+      count_launch();
+    }
+    TQ_TRY(check_launch("k_gather_rows"));
   }
-  TQ_TRY(check_launch("k_gather_col"));
   TQ_CUDA(cudaEventRecord(j->ev_b[0], s));
   TQ_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
@@ -623,6 +1226,7 @@ static std::unique_ptr<ResultBatch> get_result_batch(tq_join *j) {
 // Enqueue one probe launch for `n` rows of device columns `probe` into rb (capacity rows).
 static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const uint8_t *d_selected, int64_t n, ResultBatch *rb, uint64_t capacity,
                             int cursor_slot) {
+  if (n > 0xFFFFFFF0ll) { set_error("probe batch of %lld rows exceeds the 32-bit partition offsets; feed smaller batches", (long long)n); return TQ_ERR_INVALID_ARG; }
   Runtime &r = rt();
   cudaStream_t s = r.compute;
   const int ncols = j->n_build_cols + j->n_probe_cols;
@@ -642,6 +1246,14 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
   unsigned long long *cur = j->cursors.as<unsigned long long>() + 2 * cursor_slot;
   p.cursor = cur;
   TQ_CUDA(cudaMemsetAsync(cur, 0, 16, s));
+  {
+    const int64_t n_tiles = (n + PROBE_TILE - 1) / PROBE_TILE;
+    DevBuf &ts = j->tile_state[cursor_slot];
+    TQ_TRY(ts.reserve((size_t)(n_tiles + 1) * 8));
+    TQ_CUDA(cudaMemsetAsync(ts.p, 0, (size_t)(n_tiles + 1) * 8, s));
+    p.tile_state = ts.as<unsigned long long>();
+    p.ticket = reinterpret_cast<unsigned *>(ts.as<unsigned long long>() + n_tiles);
+  }
   for (int c = 0; c < ncols; c++) {
     TQ_TRY(rb->cols[c].data.reserve((size_t)(capacity ? capacity : 1) * 8));
     TQ_TRY(rb->cols[c].bm.reserve(bitmap_alloc_bytes((int64_t)capacity)));
@@ -654,19 +1266,108 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     TQ_CUDA(cudaMemsetAsync(o.bm.p, may_null ? 0x00 : 0xFF, bitmap_alloc_bytes((int64_t)capacity), s));
     p.out_probe[c].bm = may_null ? o.bm.as<uint32_t>() : nullptr;
   }
+  if (j->row_mode) {
+    p.build_rows = j->slots.as<uint64_t>();
+    p.build_stride = 1 << j->shift;
+    for (int c = 0; c < j->n_build_cols; c++) p.build_word[c] = j->row_word[c];
+    p.build_mask = nullptr;
+    p.build_mask_word = j->row_mask_word;
+  } else {
+    p.build_rows = j->csr_rows.as<uint64_t>();
+    p.build_stride = j->n_build_cols;
+    for (int c = 0; c < j->n_build_cols; c++) p.build_word[c] = c;
+    p.build_mask = j->build_has_nulls ? j->csr_mask.as<uint32_t>() : nullptr;
+    p.build_mask_word = -1;
+  }
   for (int c = 0; c < j->n_build_cols; c++) {
-    p.build[c].data = j->csr_cols[c].data.as<uint64_t>();
-    p.build[c].bm = j->csr_cols[c].bm.as<uint32_t>();
     DevColBuf &o = rb->cols[build_base + c];
     p.out_build[c].data = o.data.as<uint64_t>();
-    TQ_CUDA(cudaMemsetAsync(o.bm.p, 0x00, bitmap_alloc_bytes((int64_t)capacity), s));
-    p.out_build[c].bm = o.bm.as<uint32_t>();
+    const bool may_null = p.is_outer || j->build_has_nulls;  // outer-join misses pad the inner side with NULLs
+    TQ_CUDA(cudaMemsetAsync(o.bm.p, may_null ? 0x00 : 0xFF, bitmap_alloc_bytes((int64_t)capacity), s));
+    p.out_build[c].bm = may_null ? o.bm.as<uint32_t>() : nullptr;
   }
   TQ_CUDA(cudaEventRecord(j->ev_a[cursor_slot], s));
-  k_probe<<<probe_grid(n), PROBE_THREADS, 0, s>>>(p, j->table);
-  count_launch();
-  j->probe_launches++;
-  TQ_TRY(check_launch("k_probe"));
+  if (j->pbits == 0) {
+    k_probe<<<probe_grid(n), PROBE_THREADS, 0, s>>>(p, j->table);
+    count_launch();
+    j->probe_launches++;
+    TQ_TRY(check_launch("k_probe"));
+  } else {
+    // ---- partitioned pipeline: histogram -> scan -> scatter -> per-partition probe with the table in smem
+    const int P = 1 << j->pbits;
+    const int n_bins = P + 1;
+    static bool attr_done = false;
+    if (!attr_done) {
+      TQ_CUDA(cudaFuncSetAttribute(k_probe_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_MAX_SMEM_BYTES));
+      TQ_CUDA(cudaFuncSetAttribute(k_probe_part_uniq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_MAX_SMEM_BYTES));
+      TQ_CUDA(cudaFuncSetAttribute(k_probe_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 8)));
+      TQ_CUDA(cudaFuncSetAttribute(k_probe_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((1 << PART_MAX_BITS) + 1) * 4)));
+      attr_done = true;
+    }
+    DevBuf &cnt = j->part_cnt[cursor_slot], &off = j->part_off[cursor_slot], &cur_b = j->part_cursor[cursor_slot];
+    TQ_TRY(cnt.reserve((size_t)(n_bins + 1) * 4));
+    TQ_TRY(off.reserve((size_t)(n_bins + 1) * 4));
+    TQ_TRY(cur_b.reserve((size_t)(n_bins + 1) * 4));
+    TQ_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)(n_bins + 1) * 4, s));
+    std::vector<DevColBuf> &pc = j->part_cols[cursor_slot];
+    pc.resize(j->n_probe_cols);
+    ScatterParams sp{};
+    sp.n_cols = j->n_probe_cols;
+    sp.selected = d_selected;
+    sp.key_col = j->probe_key;
+    sp.key_mode = j->key_mode;
+    sp.is_outer = p.is_outer;
+    sp.pbits = j->pbits;
+    sp.n = n;
+    sp.part_cnt = cnt.as<uint32_t>();
+    sp.part_cursor = cur_b.as<uint32_t>();
+    for (int c = 0; c < j->n_probe_cols; c++) {
+      TQ_TRY(pc[c].data.reserve((size_t)n * 8));
+      sp.in[c] = probe[c];
+      sp.out[c].data = pc[c].data.as<uint64_t>();
+      sp.out[c].bm = nullptr;
+      if (probe[c].bm) {
+        TQ_TRY(pc[c].bm.reserve(bitmap_alloc_bytes(n)));
+        TQ_CUDA(cudaMemsetAsync(pc[c].bm.p, 0, bitmap_alloc_bytes(n), s));
+        sp.out[c].bm = pc[c].bm.as<uint32_t>();
+      }
+      p.probe[c].data = pc[c].data.as<uint64_t>();
+      p.probe[c].bm = sp.out[c].bm;
+    }
+    const int smem_bins = n_bins * 4;
+    const int smem_scat = SCAT_TILE * 8 + n_bins * 8 + SCAT_TILE * 2 + SCAT_TILE;
+    const int hist_grid = rt().sm_count * 4;
+    k_probe_part_hist<<<hist_grid, SCAT_THREADS, smem_bins, s>>>(sp);
+    count_launch();
+    TQ_TRY(check_launch("k_probe_part_hist"));
+    // part_off[q] = first row of partition q; the extra zero bin makes part_off[n_bins] the total
+    TQ_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), 1, off.as<uint32_t>(), 1, n_bins + 1, nullptr, j->scan_scratch2, s));
+    TQ_CUDA(cudaMemcpyAsync(cur_b.p, off.p, (size_t)(n_bins + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    const int64_t scat_tiles = (n + SCAT_TILE - 1) / SCAT_TILE;
+    const int64_t scat_cap = (int64_t)rt().sm_count * 4;
+    k_probe_scatter<<<(int)(scat_tiles < scat_cap ? scat_tiles : scat_cap), SCAT_THREADS, smem_scat, s>>>(sp);
+    count_launch();
+    TQ_TRY(check_launch("k_probe_scatter"));
+    p.selected = nullptr;
+    p.part_off = off.as<uint32_t>();
+    const int work_parts = p.is_outer ? n_bins : P;
+    // ~g_tiles_per_cta tiles per CTA: enough CTAs per partition that only a handful of partitions are live at once
+    const int64_t tiles_per_part = (n / work_parts + PROBE_TILE - 1) / PROBE_TILE;
+    int64_t split64 = tiles_per_part / g_tiles_per_cta;
+    if (split64 < 1) split64 = 1;
+    if (split64 * work_parts > (1ll << 30)) split64 = (1ll << 30) / work_parts;
+    int split = (int)split64;
+    p.split = split;
+    const size_t image_bytes = (size_t)((j->table.mask + 1) << j->shift) * 8;
+    const bool in_smem = image_bytes <= PART_MAX_SMEM_BYTES;
+    p.table_in_smem = in_smem ? 1 : 0;
+    const size_t table_bytes = in_smem ? image_bytes : 0;
+    if (j->build_unique) k_probe_part_uniq<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
+    else k_probe_part<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
+    count_launch();
+    j->probe_launches += 3;
+    TQ_TRY(check_launch("k_probe_part"));
+  }
   TQ_CUDA(cudaEventRecord(j->ev_b[cursor_slot], s));
   TQ_CUDA(cudaMemcpyAsync(j->cursors_host.as<unsigned long long>() + 2 * cursor_slot, cur, 16, cudaMemcpyDeviceToHost, s));
   return TQ_OK;
@@ -839,6 +1540,9 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   // LeftOuter keeps the left child as the outer side, RightOuter the right child (builder.go:451-477)
   if (d->join_type == TQ_JOIN_LEFT_OUTER && d->outer_is_right) { set_error("left outer join needs outer_is_right == 0"); return TQ_ERR_INVALID_ARG; }
   if (d->join_type == TQ_JOIN_RIGHT_OUTER && !d->outer_is_right) { set_error("right outer join needs outer_is_right == 1"); return TQ_ERR_INVALID_ARG; }
+  { const char *e = getenv("TQ_JOIN_FORCE_GLOBAL"); g_force_global_table = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_TILES_PER_CTA"); if (e && atoll(e) > 0) g_tiles_per_cta = atoll(e); }
+  { const char *e = getenv("TQ_JOIN_PART_ROWS"); if (e && atoll(e) > 0) g_part_target_rows = atoll(e); }
   tq_join *j = new (std::nothrow) tq_join();
   if (!j) return TQ_ERR_OOM;
   j->join_type = d->join_type;
@@ -1080,7 +1784,7 @@ int32_t tq_join_stats(tq_join *j, int64_t *s) {
   if (!j || !s) return TQ_ERR_INVALID_ARG;
   s[0] = j->n_valid;
   s[1] = j->n_distinct;
-  s[2] = 1;
+  s[2] = 1ll << j->pbits;
   s[3] = j->probe_rows_total;
   s[4] = j->joined_rows_total;
   s[5] = j->last_probe_ns;

@@ -1,5 +1,7 @@
 // runtime.cu — process-wide runtime of libtinysql_b200.so: device selection, streams, error text,
 // pinned/device memory helpers, device timers, exclusive scan primitive.
+#include <map>
+
 #include "common.cuh"
 
 namespace tq {
@@ -22,8 +24,8 @@ int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 Runtime &rt() {
-  static Runtime r;
-  return r;
+  static Runtime *r = new Runtime();  // leaked: must outlive every static DevBuf
+  return *r;
 }
 
 static int32_t init_device(int ordinal) {
@@ -82,11 +84,56 @@ int32_t check_launch(const char *kernel) {
   return TQ_OK;
 }
 
+// ---------------------------------------------------------------- caching allocators
+// cudaMalloc / cudaHostAlloc of GB-sized buffers cost milliseconds; operators are created per query, so
+// released blocks are kept and handed back to the next request of a similar size (best fit within 2x).
+struct BlockCache {
+  std::mutex mu;
+  std::multimap<size_t, void *> free_blocks;
+  size_t cached_bytes = 0;
+  size_t max_cached;
+  explicit BlockCache(size_t cap) : max_cached(cap) {}
+  void *take(size_t bytes, size_t *got) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = free_blocks.lower_bound(bytes);
+    if (it == free_blocks.end() || it->first > bytes * 2 + (1u << 20)) return nullptr;
+    void *p = it->second;
+    *got = it->first;
+    cached_bytes -= it->first;
+    free_blocks.erase(it);
+    return p;
+  }
+  bool give(void *p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cached_bytes + bytes > max_cached) return false;
+    free_blocks.emplace(bytes, p);
+    cached_bytes += bytes;
+    return true;
+  }
+  template <typename FreeFn> void drain(FreeFn f) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &kv : free_blocks) f(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+// leaked on purpose: DevBuf/PinBuf objects with static storage release into these during exit
+static BlockCache &dev_cache() { static BlockCache *c = new BlockCache((size_t)96 << 30); return *c; }
+static BlockCache &pin_cache() { static BlockCache *c = new BlockCache((size_t)24 << 30); return *c; }
+
 int32_t DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return TQ_OK;
   release();
   size_t want = bytes + (bytes >> 4) + 256;  // a little headroom so slowly growing batches do not realloc
+  want = (want + 511) & ~(size_t)511;
+  size_t got = 0;
+  if (void *q = dev_cache().take(want, &got)) { p = q; cap = got; return TQ_OK; }
   cudaError_t e = cudaMalloc(&p, want);
+  if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once
+    cudaGetLastError();
+    dev_cache().drain([](void *q) { cudaFree(q); });
+    e = cudaMalloc(&p, want);
+  }
   if (e != cudaSuccess) {
     p = nullptr;
     cap = 0;
@@ -96,7 +143,7 @@ int32_t DevBuf::reserve(size_t bytes) {
   return TQ_OK;
 }
 void DevBuf::release() {
-  if (p) cudaFree(p);
+  if (p && !dev_cache().give(p, cap)) cudaFree(p);
   p = nullptr;
   cap = 0;
 }
@@ -104,7 +151,15 @@ int32_t PinBuf::reserve(size_t bytes) {
   if (bytes <= cap) return TQ_OK;
   release();
   size_t want = bytes + (bytes >> 4) + 256;
+  want = (want + 4095) & ~(size_t)4095;
+  size_t got = 0;
+  if (void *q = pin_cache().take(want, &got)) { p = q; cap = got; return TQ_OK; }
   cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    pin_cache().drain([](void *q) { cudaFreeHost(q); });
+    e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+  }
   if (e != cudaSuccess) {
     p = nullptr;
     cap = 0;
@@ -114,7 +169,7 @@ int32_t PinBuf::reserve(size_t bytes) {
   return TQ_OK;
 }
 void PinBuf::release() {
-  if (p) cudaFreeHost(p);
+  if (p && !pin_cache().give(p, cap)) cudaFreeHost(p);
   p = nullptr;
   cap = 0;
 }
@@ -296,6 +351,8 @@ int32_t tq_shutdown(void) {
   if (!r.inited) return TQ_OK;
   cudaSetDevice(r.device);
   cudaDeviceSynchronize();
+  dev_cache().drain([](void *q) { cudaFree(q); });
+  pin_cache().drain([](void *q) { cudaFreeHost(q); });
   if (r.l2_scratch) cudaFree(r.l2_scratch);
   r.l2_scratch = nullptr;
   cudaEventDestroy(r.t0);
