@@ -215,6 +215,23 @@ def test_join_partitioned_path(lib, jt, oir):
     assert_same_multiset(got, want)
 
 
+def test_join_partitioned_skewed_probe_overflows_slab(lib):
+    """a hot probe key sends most rows to ONE partition: the optimistic (histogram-free) scatter overflows its slab,
+    flags it, and the batch is re-run on the exact histogram path — same answer"""
+    rng = np.random.default_rng(8)
+    nb, npr = 300000, 1000000
+    bk = rng.permutation(nb).astype(np.int64)
+    b = [Column(INT64, bk), Column(INT64, bk + 5)]
+    pk = rng.integers(0, nb, npr).astype(np.int64)
+    pk[rng.random(npr) < 0.8] = 4242
+    p = [Column(INT64, pk), Column(INT64, np.arange(npr))]
+    got, want = _run_join([INT64, INT64], b, [INT64, INT64], p, INNER_JOIN, True, chunk=1 << 20)
+    assert_same_multiset(got, want)
+    # second batch on the same handle takes the exact path from the start
+    got, want = _run_join([INT64, INT64], b, [INT64, INT64], p, LEFT_OUTER_JOIN, False, chunk=1 << 18, batch=1 << 19)
+    assert_same_multiset(got, want)
+
+
 def test_join_partitioned_smem_tables(lib, monkeypatch):
     """~2400 build rows per partition: every partition table is TMA-bulk-loaded into shared memory"""
     monkeypatch.setenv("TQ_JOIN_PART_ROWS", "2400")
@@ -227,8 +244,11 @@ def test_join_partitioned_smem_tables(lib, monkeypatch):
         assert_same_multiset(got, want)
 
 
-def test_join_partitioned_unique_pk_fk(lib):
-    """the C3 shape at 1/20 scale: unique build keys, every probe row matches exactly once"""
+@pytest.mark.parametrize("no_fast", ["0", "1"])
+def test_join_partitioned_unique_pk_fk(lib, monkeypatch, no_fast):
+    """the C3 shape at 1/20 scale: unique build keys, every probe row matches exactly once
+    (no_fast=0: the template-specialised PK-FK kernel; 1: the generic unique-key kernel)"""
+    monkeypatch.setenv("TQ_JOIN_NO_FAST", no_fast)
     rng = np.random.default_rng(3)
     nb, npr = 500000, 5000000
     bk = rng.permutation(nb).astype(np.int64)
@@ -247,6 +267,22 @@ def test_join_partitioned_unique_pk_fk(lib):
     ids = np.sort(got.cols[3].values)
     assert np.array_equal(ids, np.arange(npr))
     assert np.array_equal(got.cols[2].values, pk[got.cols[3].values])
+
+
+@pytest.mark.parametrize("nbc,npc", [(1, 1), (3, 2), (4, 4), (2, 3)])
+def test_join_fast_kernel_shapes(lib, nbc, npc):
+    """row-table fast path across column counts (16- and 32-byte entries), incl. misses and the empty-marker key"""
+    rng = np.random.default_rng(nbc * 10 + npc)
+    nb, npr = 400000, 1500000
+    s = np.int64(np.uint64(0xA5C3F00DDEADBEEF).astype(np.int64))
+    bk = rng.permutation(nb * 2)[:nb].astype(np.int64)
+    bk[7] = s
+    bcols = [Column(INT64, bk)] + [Column(INT64, bk * (c + 3) + c) for c in range(1, nbc)]
+    pk = rng.integers(0, nb * 2, npr).astype(np.int64)
+    pk[11] = s
+    pcols = [Column(FLOAT64, rng.random(npr)) for _ in range(npc - 1)] + [Column(INT64, pk)]
+    got, want = _run_join([INT64] * nbc, bcols, [FLOAT64] * (npc - 1) + [INT64], pcols, INNER_JOIN, True, pkey=npc - 1, chunk=1 << 20)
+    assert_same_multiset(got, want)
 
 
 def test_join_duplicates_large_segments(lib):

@@ -31,6 +31,8 @@ static constexpr int PART_MAX_BITS = 12;
 static constexpr uint64_t PART_MAX_SMEM_BYTES = 128 << 10;  // a partition table image that still fits in shared memory
 static int64_t g_tiles_per_cta = 8;
 static int64_t g_part_target_rows = 150000;              // build rows per partition: a partition table ~ 4-8 MB, a few live ones fit in L2
+static bool g_exact_scatter = false;                     // TQ_JOIN_EXACT_SCATTER=1: always run the probe-side histogram pass
+static bool g_no_fast_kernel = false;                    // TQ_JOIN_NO_FAST=1: use the generic kernels (tests)
 static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
 
 // key_mode: how (flag, raw bytes) equality (util/codec/codec.go:212-240,363-382) maps onto raw 8-byte equality
@@ -57,6 +59,8 @@ __device__ __forceinline__ bool key_valid(uint64_t key, bool not_null, int key_m
   return false;
 }
 
+__device__ __forceinline__ uint32_t home_loc(uint64_t h, uint64_t mask, int shift) { return (uint32_t)((shift == 1) ? ((h & mask) & ~1ull) : (h & mask)); }
+
 // (word0, word1) of an entry with one 128-bit load
 __device__ __forceinline__ ulonglong2 ld_entry(const uint64_t *words, uint64_t e, int shift) {
   return *reinterpret_cast<const ulonglong2 *>(words + (e << shift));
@@ -71,50 +75,103 @@ __global__ void k_init_table(uint64_t *words, uint64_t n_entries, int shift) {
 
 // counters: [0] EMPTY_KEY-valued rows, [1] their fill cursor, [2] distinct regular keys, [3] large-segment worklist length,
 //           [4] max rows of a build partition, [5] valid regular rows, u64 @ [8] scan total
-__global__ void __launch_bounds__(256) k_build_insert(const uint64_t *keys, const uint32_t *bm, int64_t n, int key_mode, uint64_t *words,
-                                                       uint64_t mask, int pbits, int shift, uint32_t *row_slot, uint32_t *counters) {
+// The thread whose atomicCAS claims an entry also writes its row into it when the row fits the entry (ROW-mode
+// candidate): if the keys then turn out to be unique the table is complete after this one kernel.
+struct InsertParams {
+  int n_cols, key_col, key_mode;
+  DCol cols[MAXC];
+  int word_of_col[MAXC];  // word inside the entry (key column -> 0); only used when write_rows
+  int mask_word;          // -1: no NOT-NULL mask word
+  int write_rows;
+  int64_t n;
+  uint64_t *words;
+  uint64_t mask;
+  int pbits, shift;
+  uint32_t sent_entry;
+  uint32_t *row_slot;
+  uint32_t *counters;
+};
+__device__ __forceinline__ void write_row_words(const InsertParams &b, uint64_t *ent, int64_t i, bool with_key) {
+  uint64_t m = 0;
+  for (int c = 0; c < b.n_cols; c++) {
+    if (c != b.key_col || with_key) ent[b.word_of_col[c]] = b.cols[c].data[i];
+    m |= (uint64_t)tqd::bm_not_null(b.cols[c].bm, i) << c;
+  }
+  if (b.mask_word >= 0) ent[b.mask_word] = m;
+}
+__global__ void __launch_bounds__(256) k_build_insert(const InsertParams b) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint64_t *keys = b.cols[b.key_col].data;
+  const uint32_t *bm = b.cols[b.key_col].bm;
   unsigned my_valid = 0, my_new = 0;
-  for (; i < n; i += stride) {
+  for (; i < b.n; i += stride) {
     const uint64_t key = keys[i];
-    if (!key_valid(key, tqd::bm_not_null(bm, i), key_mode)) { row_slot[i] = ROW_INVALID; continue; }  // hash_table.go:161-163
-    if (key == EMPTY_KEY) { atomicAdd(&counters[0], 1u); row_slot[i] = ROW_SENTINEL; continue; }
+    if (!key_valid(key, tqd::bm_not_null(bm, i), b.key_mode)) { b.row_slot[i] = ROW_INVALID; continue; }  // hash_table.go:161-163
+    if (key == EMPTY_KEY) {
+      const uint32_t prior = atomicAdd(&b.counters[0], 1u);
+      b.row_slot[i] = ROW_SENTINEL;
+      if (b.write_rows && prior == 0) write_row_words(b, b.words + ((uint64_t)b.sent_entry << b.shift), i, true);
+      continue;
+    }
     const uint64_t h = tqd::mix64(key);
-    const uint64_t base = part_of_hash(h, pbits) * (mask + 1);
-    uint64_t loc = h & mask;
+    const uint64_t base = part_of_hash(h, b.pbits) * (b.mask + 1);
+    uint64_t loc = (b.shift == 1) ? ((h & b.mask) & ~1ull) : (h & b.mask);  // 16-byte entries: start on a 32-byte sector boundary (probes read entry PAIRS)
     my_valid++;
     for (;;) {
       const uint64_t e = base + loc;
-      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&words[e << shift]), (unsigned long long)EMPTY_KEY,
+      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&b.words[e << b.shift]), (unsigned long long)EMPTY_KEY,
                                                 (unsigned long long)key);
-      if (prev == EMPTY_KEY || prev == key) {
-        my_new += (prev == EMPTY_KEY);
-        atomicAdd(reinterpret_cast<uint32_t *>(&words[(e << shift) + 1]) + 1, 1u);  // count lives in the high half of word 1
-        row_slot[i] = (uint32_t)e;
-        break;
+      if (prev == EMPTY_KEY) {
+        my_new++;
+        if (b.write_rows) write_row_words(b, b.words + (e << b.shift), i, false);
       }
-      loc = (loc + 1) & mask;
+      if (prev == EMPTY_KEY || prev == key) { b.row_slot[i] = (uint32_t)e; break; }
+      loc = (loc + 1) & b.mask;
     }
   }
   my_valid = __reduce_add_sync(0xffffffffu, my_valid);
   my_new = __reduce_add_sync(0xffffffffu, my_new);
   if ((threadIdx.x & 31) == 0) {
-    if (my_valid) atomicAdd(&counters[5], my_valid);
-    if (my_new) atomicAdd(&counters[2], my_new);
+    if (my_valid) atomicAdd(&b.counters[5], my_valid);
+    if (my_new) atomicAdd(&b.counters[2], my_new);
   }
 }
 
-// rows per build partition (valid keys only) — decides the partition table capacity
+// CSR mode only (duplicate keys): clear word 1 of every entry (it may hold an inlined column), then count rows per key.
+__global__ void k_clear_word1(uint64_t *words, uint64_t n_entries, int shift) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n_entries; i += stride) words[(i << shift) + 1] = 0;
+}
+__global__ void __launch_bounds__(256) k_build_count(const uint32_t *row_slot, int64_t n, uint64_t *words, int shift) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint32_t e = row_slot[i];
+    if (e == ROW_INVALID || e == ROW_SENTINEL) continue;
+    atomicAdd(reinterpret_cast<uint32_t *>(&words[((uint64_t)e << shift) + 1]) + 1, 1u);  // count = high half of word 1
+  }
+}
+
+// rows per build partition (valid keys only) — decides the partition table capacity.  Per-CTA shared-memory
+// histogram, then one global atomic per non-empty bin per CTA.
 __global__ void __launch_bounds__(256) k_build_part_hist(const uint64_t *keys, const uint32_t *bm, int64_t n, int key_mode, int pbits,
                                                           uint32_t *part_cnt) {
+  __shared__ uint32_t s_hist[1 << PART_MAX_BITS];
+  const int n_bins = 1 << pbits;
+  for (int b = threadIdx.x; b < n_bins; b += blockDim.x) s_hist[b] = 0;
+  __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     const uint64_t key = keys[i];
     if (!key_valid(key, tqd::bm_not_null(bm, i), key_mode) || key == EMPTY_KEY) continue;
-    atomicAdd(&part_cnt[part_of_hash(tqd::mix64(key), pbits)], 1u);
+    atomicAdd(&s_hist[part_of_hash(tqd::mix64(key), pbits)], 1u);
   }
+  __syncthreads();
+  for (int b = threadIdx.x; b < n_bins; b += blockDim.x)
+    if (s_hist[b]) atomicAdd(&part_cnt[b], s_hist[b]);
 }
 
 __global__ void k_max_u32(const uint32_t *v, int n, uint32_t *out) {
@@ -122,35 +179,6 @@ __global__ void k_max_u32(const uint32_t *v, int n, uint32_t *out) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) m = max(m, v[i]);
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
-}
-
-// ROW mode: the row that claimed an entry writes its other columns (and NOT-NULL mask) into it.
-struct BuildRowParams {
-  int n_cols, key_col;
-  DCol cols[MAXC];
-  int word_of_col[MAXC];  // word index inside the entry (key column -> 0)
-  int mask_word;          // -1: no build column holds NULLs
-  const uint32_t *row_slot;
-  int64_t n;
-  uint64_t *words;
-  int shift;
-  uint32_t sent_entry;
-};
-__global__ void __launch_bounds__(256) k_build_rows(const BuildRowParams b) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < b.n; i += stride) {
-    uint32_t e = b.row_slot[i];
-    if (e == ROW_INVALID) continue;
-    if (e == ROW_SENTINEL) e = b.sent_entry;
-    uint64_t *ent = b.words + ((uint64_t)e << b.shift);
-    uint64_t m = 0;
-    for (int c = 0; c < b.n_cols; c++) {
-      if (c != b.key_col || e == b.sent_entry) ent[b.word_of_col[c]] = b.cols[c].data[i];
-      m |= (uint64_t)tqd::bm_not_null(b.cols[c].bm, i) << c;
-    }
-    if (b.mask_word >= 0) ent[b.mask_word] = m;
-  }
 }
 
 // ---- CSR mode build kernels
@@ -278,7 +306,8 @@ struct ProbeParams {
   unsigned *ticket;
   // partitioned path: rows of partition q are [part_off[q], part_off[q+1]) of the probe columns; partition
   // 2^pbits holds the rows that cannot match (NULL / filtered keys) and exists only for outer joins
-  const uint32_t *part_off;
+  const uint32_t *part_lo, *part_hi;  // exact path: hi == lo + 1 (one offsets array); optimistic slabs: hi = scatter cursors
+  const uint32_t *part_lim;           // optimistic slabs: end of each partition's slab (nullptr on the exact path)
   int split;                  // CTAs per partition
   int table_in_smem;          // partition table images fit in shared memory (TMA bulk-loaded)
 };
@@ -514,7 +543,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeParams p, co
       }
       const uint64_t h = tqd::mix64(key[k]);
       ebase[k] = part_of_hash(h, t.pbits) * (t.mask + 1);
-      loc[k] = (uint32_t)(h & t.mask);
+      loc[k] = home_loc(h, t.mask, t.shift);
     }
 #pragma unroll
     for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {  // the 4 random entry loads are issued back to back
@@ -566,6 +595,15 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeParams p, co
   if ((tid & 31) == 0 && matched_acc) atomicAdd(p.cursor + 1, (unsigned long long)matched_acc);
 }
 
+__global__ void k_init_slabs(uint32_t *lo, uint32_t *cursor, uint32_t *lim, int n_parts, uint32_t slab, uint32_t tail_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_parts) return;
+  const uint32_t start = (uint32_t)i * slab;  // bin n_parts (rows that cannot match, outer joins) takes the tail
+  lo[i] = start;
+  cursor[i] = start;
+  lim[i] = (i < n_parts) ? start + slab : start + tail_rows;
+}
+
 // ---- probe-side radix scatter -------------------------------------------------------------------------
 static constexpr int SCAT_THREADS = 256;
 static constexpr int SCAT_ROWS_PER_THREAD = 16;
@@ -580,7 +618,9 @@ struct ScatterParams {
   int key_col, key_mode, is_outer, pbits;
   int64_t n;
   uint32_t *part_cnt;     // histogram (2^pbits + 1 bins; the last bin = rows that cannot match)
-  uint32_t *part_cursor;  // scatter cursors, initialised to the exclusive scan of part_cnt
+  uint32_t *part_cursor;  // scatter cursors, initialised to the first row of each partition
+  const uint32_t *part_lim;  // optimistic slabs: one past the last row a partition may hold (nullptr: exact offsets, cannot overflow)
+  unsigned long long *overflow;  // set when a slab was too small
 };
 
 __device__ __forceinline__ uint32_t probe_pid(const ScatterParams &p, int64_t r, uint64_t key) {
@@ -616,7 +656,8 @@ __global__ void __launch_bounds__(SCAT_THREADS, 4) k_probe_scatter(const Scatter
   uint64_t *s_stage = reinterpret_cast<uint64_t *>(s_scat);                       // [SCAT_TILE] one column of the tile, sorted
   uint32_t *s_bins = reinterpret_cast<uint32_t *>(s_scat + SCAT_TILE * 8);        // [n_bins] tile counts, then local exclusive offsets
   uint32_t *s_gdelta = s_bins + n_bins;                                           // [n_bins] (claimed global run start) - (local offset)
-  uint16_t *s_spid = reinterpret_cast<uint16_t *>(s_gdelta + n_bins);             // [SCAT_TILE] sorted position -> partition
+  uint32_t *s_imax = s_gdelta + n_bins;                                           // [n_bins] first sorted position of the tile that no longer fits the slab
+  uint16_t *s_spid = reinterpret_cast<uint16_t *>(s_imax + n_bins);               // [SCAT_TILE] sorted position -> partition
   uint8_t *s_nn = reinterpret_cast<uint8_t *>(s_spid + SCAT_TILE);                // [SCAT_TILE] sorted position -> NOT NULL flag
   __shared__ uint32_t s_warp[SCAT_THREADS / 32 + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -658,7 +699,16 @@ __global__ void __launch_bounds__(SCAT_THREADS, 4) k_probe_scatter(const Scatter
       if (b < n_bins) {
         const uint32_t c = s_bins[b];
         s_bins[b] = run;
-        if (c) s_gdelta[b] = atomicAdd(&p.part_cursor[b], c) - run;
+        if (c) {
+          const uint32_t g = atomicAdd(&p.part_cursor[b], c);
+          s_gdelta[b] = g - run;
+          uint32_t imax = 0xFFFFFFFFu;
+          if (p.part_lim) {
+            const uint32_t lim = p.part_lim[b];
+            if (g + c > lim) { imax = (g < lim) ? run + (lim - g) : run; atomicOr(p.overflow, 1ull); }
+          }
+          s_imax[b] = imax;
+        }
         run += c;
       }
     }
@@ -681,13 +731,133 @@ __global__ void __launch_bounds__(SCAT_THREADS, 4) k_probe_scatter(const Scatter
       }
       __syncthreads();
       for (uint32_t i = tid; i < total; i += SCAT_THREADS) {
-        const uint32_t dst = s_gdelta[s_spid[i]] + i;
+        const uint32_t bin = s_spid[i];
+        if (i >= s_imax[bin]) continue;  // slab full (optimistic path only)
+        const uint32_t dst = s_gdelta[bin] + i;
         tqd::st_stream_u64(p.out[c].data + dst, s_stage[i]);
         if (has_bm && s_nn[i]) atomicOr(&p.out[c].bm[dst >> 5], 1u << (dst & 31));
       }
       __syncthreads();
     }
   }
+}
+
+// Scatter fast path: no input column carries a NULL bitmap and the column count is a template parameter.  All
+// columns of the tile are requested up front (8 rows x NP columns in flight per thread), then each column goes
+// registers -> shared (sorted position) -> global (coalesced).  512 threads x 8 rows = the same 4096-row tile.
+static constexpr int SCATF_THREADS = 512;
+static constexpr int SCATF_ROWS = SCAT_TILE / SCATF_THREADS;
+template <int NP>
+__global__ void __launch_bounds__(SCATF_THREADS, (NP <= 2 ? 2 : 1)) k_probe_scatter_fast(const ScatterParams p) {
+  extern __shared__ __align__(16) unsigned char s_scat[];
+  const int n_bins = (1 << p.pbits) + 1;
+  uint64_t *s_stage = reinterpret_cast<uint64_t *>(s_scat);
+  uint32_t *s_bins = reinterpret_cast<uint32_t *>(s_scat + SCAT_TILE * 8);
+  uint32_t *s_gdelta = s_bins + n_bins;
+  uint32_t *s_imax = s_gdelta + n_bins;
+  uint16_t *s_spid = reinterpret_cast<uint16_t *>(s_imax + n_bins);
+  __shared__ uint32_t s_warp[SCATF_THREADS / 32 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bpt = (n_bins + SCATF_THREADS - 1) / SCATF_THREADS;
+  const uint64_t *in[NP];
+  uint64_t *out[NP];
+#pragma unroll
+  for (int c = 0; c < NP; c++) { in[c] = p.in[c].data; out[c] = p.out[c].data; }
+  const int kc = p.key_col;
+  const int64_t n_tiles = (p.n + SCAT_TILE - 1) / SCAT_TILE;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t tile_base = tile * SCAT_TILE;
+    for (int b = tid; b < n_bins; b += SCATF_THREADS) s_bins[b] = 0;
+    uint64_t v[NP][SCATF_ROWS];
+#pragma unroll
+    for (int k = 0; k < SCATF_ROWS; k++) {
+      const int64_t r = tile_base + k * SCATF_THREADS + tid;
+#pragma unroll
+      for (int c = 0; c < NP; c++) v[c][k] = (r < p.n) ? tqd::ld_stream_u64(in[c] + r) : 0;
+    }
+    __syncthreads();
+    uint32_t pid[SCATF_ROWS], spos[SCATF_ROWS];
+#pragma unroll
+    for (int k = 0; k < SCATF_ROWS; k++) {
+      const int64_t r = tile_base + k * SCATF_THREADS + tid;
+      uint64_t key = v[0][k];
+#pragma unroll
+      for (int c = 1; c < NP; c++) if (c == kc) key = v[c][k];
+      pid[k] = PID_DROP;
+      if (r < p.n) {
+        const bool sel = p.selected ? (p.selected[r] != 0) : true;
+        if (sel && key_valid(key, true, p.key_mode)) pid[k] = (uint32_t)part_of_hash(tqd::mix64(key), p.pbits);
+        else if (p.is_outer) pid[k] = 1u << p.pbits;
+      }
+      spos[k] = (pid[k] != PID_DROP) ? atomicAdd(&s_bins[pid[k]], 1u) : 0u;
+    }
+    __syncthreads();
+    uint32_t tsum = 0;
+    for (int q = 0; q < bpt; q++) { const int b = tid * bpt + q; if (b < n_bins) tsum += s_bins[b]; }
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = (lane < SCATF_THREADS / 32) ? s_warp[lane] : 0, winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += x; }
+      if (lane < SCATF_THREADS / 32) s_warp[lane] = winc - w;
+      if (lane == SCATF_THREADS / 32 - 1) s_warp[SCATF_THREADS / 32] = winc;
+    }
+    __syncthreads();
+    uint32_t run = inc - tsum + s_warp[warp];
+    for (int q = 0; q < bpt; q++) {
+      const int b = tid * bpt + q;
+      if (b < n_bins) {
+        const uint32_t c = s_bins[b];
+        s_bins[b] = run;
+        if (c) {
+          const uint32_t g = atomicAdd(&p.part_cursor[b], c);
+          s_gdelta[b] = g - run;
+          uint32_t imax = 0xFFFFFFFFu;
+          if (p.part_lim) {
+            const uint32_t lim = p.part_lim[b];
+            if (g + c > lim) { imax = (g < lim) ? run + (lim - g) : run; atomicOr(p.overflow, 1ull); }
+          }
+          s_imax[b] = imax;
+        }
+        run += c;
+      }
+    }
+    const uint32_t total = s_warp[SCATF_THREADS / 32];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SCATF_ROWS; k++) {
+      if (pid[k] == PID_DROP) continue;
+      spos[k] += s_bins[pid[k]];
+      s_spid[spos[k]] = (uint16_t)pid[k];
+    }
+#pragma unroll
+    for (int c = 0; c < NP; c++) {
+#pragma unroll
+      for (int k = 0; k < SCATF_ROWS; k++)
+        if (pid[k] != PID_DROP) s_stage[spos[k]] = v[c][k];
+      __syncthreads();
+      for (uint32_t i = tid; i < total; i += SCATF_THREADS) {
+        const uint32_t bin = s_spid[i];
+        if (i >= s_imax[bin]) continue;
+        tqd::st_stream_u64(out[c] + s_gdelta[bin] + i, s_stage[i]);
+      }
+      __syncthreads();
+    }
+  }
+}
+typedef void (*ScatterKernel)(const ScatterParams);
+static ScatterKernel scatter_fast_kernel(int np) {
+  switch (np) {
+    case 1: return k_probe_scatter_fast<1>;
+    case 2: return k_probe_scatter_fast<2>;
+    case 3: return k_probe_scatter_fast<3>;
+    case 4: return k_probe_scatter_fast<4>;
+  }
+  return nullptr;
 }
 
 // ---- partitioned probe: the partition's table image lives in shared memory ------------------------------
@@ -731,8 +901,9 @@ __device__ __forceinline__ bool part_prologue(const ProbeParams &p, const JoinTa
   const uint32_t n_parts = 1u << t.pbits;
   c.part = blockIdx.x / p.split;
   const uint32_t sub = blockIdx.x % p.split;
-  c.p_lo = p.part_off[c.part];
-  c.p_hi = p.part_off[c.part + 1];
+  c.p_lo = p.part_lo[c.part];
+  c.p_hi = p.part_hi[c.part];
+  if (p.part_lim && c.p_hi > (int64_t)p.part_lim[c.part]) c.p_hi = p.part_lim[c.part];  // overflowed slab: the batch is re-run anyway
   const int64_t p_tiles = (c.p_hi - c.p_lo + PROBE_TILE - 1) / PROBE_TILE;
   c.t_lo = p_tiles * sub / p.split;
   c.t_hi = p_tiles * (sub + 1) / p.split;
@@ -797,7 +968,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part_uniq(const ProbePa
     ulonglong2 first[R];
 #pragma unroll
     for (int k = 0; k < R; k++) {  // independent entry loads issued back to back
-      loc[k] = (uint32_t)(tqd::mix64(key[k]) & t.mask);
+      loc[k] = home_loc(tqd::mix64(key[k]), t.mask, t.shift);
       first[k] = make_ulonglong2(EMPTY_KEY, 0);
       if (inb[k] && cx.has_table && key[k] != EMPTY_KEY) first[k] = ld_entry(cx.tbl, loc[k], t.shift);
     }
@@ -839,6 +1010,196 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part_uniq(const ProbePa
   if (lane == 0 && matched_acc) atomicAdd(p.cursor + 1, (unsigned long long)matched_acc);
 }
 
+// ---- the PK-FK fast path: inner join, ROW-mode table, no output column can hold NULLs ------------------------
+// Same structure as k_probe_part_uniq with the column counts as template parameters: column pointers live in
+// registers, the loops unroll, words 0/1 of the build row come straight from the matched entry.  16-byte
+// entries are fetched as 32-byte aligned PAIRS (the insert starts probing on an even entry), so one sector
+// read checks two candidate slots and dependent collision round-trips are rare.
+struct EntryPair {
+  ulonglong2 a, b;
+};
+__device__ __forceinline__ EntryPair ld_pair(const uint64_t *tbl, uint32_t loc_even, bool smem) {
+  EntryPair e;
+  const uint64_t *p = tbl + ((uint64_t)loc_even << 1);
+  if (smem) {
+    e.a = *reinterpret_cast<const ulonglong2 *>(p);
+    e.b = *reinterpret_cast<const ulonglong2 *>(p + 2);
+  } else {  // one 256-bit load = one sector
+    asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(e.a.x), "=l"(e.a.y), "=l"(e.b.x), "=l"(e.b.y) : "l"(p));
+  }
+  return e;
+}
+
+template <int NP, int NB>
+__global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const ProbeParams p, const JoinTable t) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ unsigned s_total[2];
+  __shared__ unsigned long long s_base[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PartCtx cx;
+  if (!part_prologue(p, t, s_dyn, &s_mbar, cx)) return;
+  if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
+  __syncthreads();
+  const uint64_t *pin[NP];
+  uint64_t *pout[NP];
+  uint64_t *bout[NB];
+  int bw[NB];
+#pragma unroll
+  for (int c = 0; c < NP; c++) { pin[c] = p.probe[c].data; pout[c] = p.out_probe[c].data; }
+#pragma unroll
+  for (int c = 0; c < NB; c++) { bout[c] = p.out_build[c].data; bw[c] = p.build_word[c]; }
+  const int kc = p.key_col;
+  const uint64_t *keys = pin[0];
+#pragma unroll
+  for (int c = 1; c < NP; c++) if (c == kc) keys = pin[c];
+  const unsigned lt_mask = (1u << lane) - 1;
+  const uint32_t mask = (uint32_t)t.mask;
+  const int shift = t.shift;
+  const bool smem = cx.use_smem;
+  unsigned matched_acc = 0;
+  bool table_ready = !cx.use_smem;
+  constexpr int R = PROBE_ROWS_PER_THREAD;
+  // software pipeline: the keys of tile i+1 are requested before the barriers / atomics of tile i
+  uint64_t nkey[R];
+  {
+    const int64_t wb = cx.p_lo + cx.t_lo * PROBE_TILE + warp * (32 * R) + lane;
+#pragma unroll
+    for (int k = 0; k < R; k++) nkey[k] = (wb + k * 32 < cx.p_hi) ? tqd::ld_stream_u64(keys + wb + k * 32) : EMPTY_KEY;
+  }
+  for (int64_t tile = cx.t_lo; tile < cx.t_hi; tile++) {
+    const int par = (int)(tile & 1);
+    const int64_t wbase = cx.p_lo + tile * PROBE_TILE + warp * (32 * R) + lane;  // this lane's first row
+    uint64_t key[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) key[k] = nkey[k];
+    if (!table_ready) { mbar_wait(&s_mbar, 0); table_ready = true; }
+    uint32_t loc[R];
+    ulonglong2 ent[R];
+    unsigned bal[R];
+    unsigned wcnt = 0;
+    if (shift == 1) {
+      EntryPair pr[R];
+#pragma unroll
+      for (int k = 0; k < R; k++) {  // R independent sector loads in flight
+        loc[k] = home_loc(tqd::mix64(key[k]), mask, 1);
+        pr[k].a = make_ulonglong2(EMPTY_KEY, 0);
+        pr[k].b = pr[k].a;
+        if (key[k] != EMPTY_KEY) pr[k] = ld_pair(cx.tbl, loc[k], smem);
+      }
+      if (tile + 1 < cx.t_hi) {
+        const int64_t wb = wbase + PROBE_TILE;
+#pragma unroll
+        for (int k = 0; k < R; k++) nkey[k] = (wb + k * 32 < cx.p_hi) ? tqd::ld_stream_u64(keys + wb + k * 32) : EMPTY_KEY;
+      }
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        bool hit = false;
+        ent[k] = pr[k].a;
+        if (key[k] != EMPTY_KEY) {
+          for (;;) {
+            if (pr[k].a.x == key[k]) { ent[k] = pr[k].a; hit = true; break; }
+            if (pr[k].a.x == EMPTY_KEY) break;
+            if (pr[k].b.x == key[k]) { ent[k] = pr[k].b; loc[k] += 1; hit = true; break; }
+            if (pr[k].b.x == EMPTY_KEY) break;
+            loc[k] = (loc[k] + 2) & mask;
+            pr[k] = ld_pair(cx.tbl, loc[k], smem);
+          }
+        } else if ((wbase + k * 32) < cx.p_hi && t.sent_cnt) {  // a probe key equal to the empty marker: its row is the side entry
+          loc[k] = (uint32_t)(t.sent_off - cx.ebase);
+          ent[k] = ld_entry(t.words, t.sent_off, 1);
+          hit = true;
+        }
+        bal[k] = __ballot_sync(0xffffffffu, hit);
+        wcnt += __popc(bal[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        loc[k] = home_loc(tqd::mix64(key[k]), mask, shift);
+        ent[k] = make_ulonglong2(EMPTY_KEY, 0);
+        if (key[k] != EMPTY_KEY) ent[k] = ld_entry(cx.tbl, loc[k], shift);
+      }
+      if (tile + 1 < cx.t_hi) {
+        const int64_t wb = wbase + PROBE_TILE;
+#pragma unroll
+        for (int k = 0; k < R; k++) nkey[k] = (wb + k * 32 < cx.p_hi) ? tqd::ld_stream_u64(keys + wb + k * 32) : EMPTY_KEY;
+      }
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        bool hit = false;
+        if (key[k] != EMPTY_KEY) {
+          while (ent[k].x != key[k] && ent[k].x != EMPTY_KEY) {
+            loc[k] = (loc[k] + 1) & mask;
+            ent[k] = ld_entry(cx.tbl, loc[k], shift);
+          }
+          hit = ent[k].x == key[k];
+        } else if ((wbase + k * 32) < cx.p_hi && t.sent_cnt) {
+          loc[k] = (uint32_t)(t.sent_off - cx.ebase);
+          ent[k] = ld_entry(t.words, t.sent_off, shift);
+          hit = true;
+        }
+        bal[k] = __ballot_sync(0xffffffffu, hit);
+        wcnt += __popc(bal[k]);
+      }
+    }
+    unsigned woff = 0;
+    if (lane == 0) {
+      matched_acc += wcnt;
+      if (wcnt) woff = atomicAdd(&s_total[par], wcnt);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned tot = s_total[par];
+      s_base[par] = tot ? atomicAdd(p.cursor, (unsigned long long)tot) : 0ull;
+      s_total[par] = 0;
+    }
+    __syncthreads();
+    unsigned long long q0 = s_base[par] + __shfl_sync(0xffffffffu, woff, 0);
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const unsigned long long q = q0 + __popc(bal[k] & lt_mask);
+      q0 += __popc(bal[k]);
+      if (((bal[k] >> lane) & 1u) && q < p.capacity) {
+        const int64_t row = wbase + k * 32;
+#pragma unroll
+        for (int c = 0; c < NP; c++) tqd::st_stream_u64(pout[c] + q, (c == kc) ? key[k] : tqd::ld_stream_u64(pin[c] + row));
+#pragma unroll
+        for (int c = 0; c < NB; c++) {
+          uint64_t v;
+          if (bw[c] == 0) v = ent[k].x;
+          else if (bw[c] == 1) v = ent[k].y;
+          else v = t.words[((cx.ebase + loc[k]) << shift) + bw[c]];  // words 2..3 of a 32-byte entry: same sector, L1/L2 hit
+          tqd::st_stream_u64(bout[c] + q, v);
+        }
+      }
+    }
+  }
+  if (lane == 0 && matched_acc) atomicAdd(p.cursor + 1, (unsigned long long)matched_acc);
+}
+
+typedef void (*ProbeKernel)(const ProbeParams, const JoinTable);
+template <int NP>
+static ProbeKernel fast_kernel_nb(int nb) {
+  switch (nb) {
+    case 1: return k_probe_part_fast<NP, 1>;
+    case 2: return k_probe_part_fast<NP, 2>;
+    case 3: return k_probe_part_fast<NP, 3>;
+    case 4: return k_probe_part_fast<NP, 4>;
+  }
+  return nullptr;
+}
+static ProbeKernel fast_kernel(int np, int nb) {
+  switch (np) {
+    case 1: return fast_kernel_nb<1>(nb);
+    case 2: return fast_kernel_nb<2>(nb);
+    case 3: return fast_kernel_nb<3>(nb);
+    case 4: return fast_kernel_nb<4>(nb);
+  }
+  return nullptr;
+}
+
 // ---- partitioned probe, general (duplicate build keys): block scan + output-centric expansion ------------
 __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part(const ProbeParams p, const JoinTable t) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -865,7 +1226,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part(const ProbeParams 
 #pragma unroll
     for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
       const int64_t r = tile_base + k * PROBE_THREADS + tid;
-      loc[k] = (uint32_t)(tqd::mix64(key[k]) & t.mask);
+      loc[k] = home_loc(tqd::mix64(key[k]), t.mask, t.shift);
       first[k] = make_ulonglong2(EMPTY_KEY, 0);
       if (r < cx.p_hi && cx.has_table && key[k] != EMPTY_KEY) first[k] = ld_entry(cx.tbl, loc[k], t.shift);
     }
@@ -1010,7 +1371,8 @@ struct tq_join {
   DevBuf cursors;                         // 2 x {rows, matched} device counters
   DevBuf tile_state[2];                   // per cursor slot: look-back words + ticket
   std::vector<DevColBuf> part_cols[2];    // per cursor slot: probe columns in partition order
-  DevBuf part_cnt[2], part_off[2], part_cursor[2];
+  DevBuf part_cnt[2], part_off[2], part_cursor[2], part_lim[2];
+  bool optimistic_scatter = true;         // skip the probe-side histogram pass: fixed slabs with 25% slack (falls back on overflow)
   DevBuf scan_scratch2;
   PinBuf cursors_host;
   PendingBatch pending;
@@ -1109,8 +1471,31 @@ static int32_t join_build(tq_join *j) {
   uint64_t *words = j->slots.as<uint64_t>();
   k_init_table<<<stream_grid((int64_t)(n_entries << shift)), 256, 0, s>>>(words, n_entries, shift);
   count_launch();
+  InsertParams ip{};
+  ip.n_cols = j->n_build_cols;
+  ip.key_col = j->build_key;
+  ip.key_mode = j->key_mode;
+  {
+    int w = 1;
+    for (int c = 0; c < j->n_build_cols; c++) {
+      ip.cols[c] = j->b_view[c];
+      j->row_word[c] = (c == j->build_key) ? 0 : w++;
+      ip.word_of_col[c] = j->row_word[c];
+    }
+    j->row_mask_word = j->build_has_nulls ? w : -1;
+  }
+  ip.mask_word = j->row_mask_word;
+  ip.write_rows = row_candidate ? 1 : 0;
+  ip.n = n;
+  ip.words = words;
+  ip.mask = cap - 1;
+  ip.pbits = pbits;
+  ip.shift = shift;
+  ip.sent_entry = (uint32_t)n_slots;
+  ip.row_slot = j->row_slot.as<uint32_t>();
+  ip.counters = counters;
   if (n > 0) {
-    k_build_insert<<<stream_grid(n), 256, 0, s>>>(key.data, key.bm, n, j->key_mode, words, cap - 1, pbits, shift, j->row_slot.as<uint32_t>(), counters);
+    k_build_insert<<<stream_grid(n), 256, 0, s>>>(ip);
     count_launch();
   }
   TQ_TRY(check_launch("k_build_insert"));
@@ -1129,32 +1514,15 @@ static int32_t join_build(tq_join *j) {
   j->row_mode = j->build_unique && row_candidate;
   j->table.row_mode = j->row_mode ? 1 : 0;
   if (j->row_mode) {
-    // ---- ROW mode: the claiming row writes its columns into the entry; nothing else to do
-    BuildRowParams b{};
-    b.n_cols = j->n_build_cols;
-    b.key_col = j->build_key;
-    int w = 1;
-    for (int c = 0; c < j->n_build_cols; c++) {
-      b.cols[c] = j->b_view[c];
-      j->row_word[c] = (c == j->build_key) ? 0 : w++;
-      b.word_of_col[c] = j->row_word[c];
-    }
-    j->row_mask_word = j->build_has_nulls ? w : -1;
-    b.mask_word = j->row_mask_word;
-    b.row_slot = j->row_slot.as<uint32_t>();
-    b.n = n;
-    b.words = words;
-    b.shift = shift;
-    b.sent_entry = (uint32_t)n_slots;
+    // ---- ROW mode: every key is unique, so the claiming rows have already written the whole table
     j->table.sent_off = (uint32_t)n_slots;
     j->table.sent_cnt = sent_cnt;
-    if (n > 0) {
-      k_build_rows<<<stream_grid(n), 256, 0, s>>>(b);
-      count_launch();
-      TQ_TRY(check_launch("k_build_rows"));
-    }
   } else {
-    // ---- CSR mode: exclusive scan of the entry counts (high half of word 1) into the offsets (low half)
+    // ---- CSR mode: count rows per key, then exclusive scan of the counts (high half of word 1) into the offsets (low half)
+    k_clear_word1<<<stream_grid((int64_t)n_entries), 256, 0, s>>>(words, n_entries, shift);
+    if (n > 0) k_build_count<<<stream_grid(n), 256, 0, s>>>(j->row_slot.as<uint32_t>(), n, words, shift);
+    count_launch(2);
+    TQ_TRY(check_launch("k_build_count"));
     TQ_TRY(j->row_ids.reserve((size_t)(n ? n : 1) * 4));
     const uint32_t worklist_cap = (uint32_t)((n / 33) + 2);
     TQ_TRY(j->worklist.reserve((size_t)worklist_cap * 8));
@@ -1243,9 +1611,9 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
   p.is_outer = (j->join_type != TQ_JOIN_INNER);
   p.n = n;
   p.capacity = capacity;
-  unsigned long long *cur = j->cursors.as<unsigned long long>() + 2 * cursor_slot;
+  unsigned long long *cur = j->cursors.as<unsigned long long>() + 4 * cursor_slot;  // [0] rows, [1] matched probe rows, [2] slab overflow
   p.cursor = cur;
-  TQ_CUDA(cudaMemsetAsync(cur, 0, 16, s));
+  TQ_CUDA(cudaMemsetAsync(cur, 0, 32, s));
   {
     const int64_t n_tiles = (n + PROBE_TILE - 1) / PROBE_TILE;
     DevBuf &ts = j->tile_state[cursor_slot];
@@ -1300,7 +1668,7 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     if (!attr_done) {
       TQ_CUDA(cudaFuncSetAttribute(k_probe_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_MAX_SMEM_BYTES));
       TQ_CUDA(cudaFuncSetAttribute(k_probe_part_uniq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_MAX_SMEM_BYTES));
-      TQ_CUDA(cudaFuncSetAttribute(k_probe_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 8)));
+      TQ_CUDA(cudaFuncSetAttribute(k_probe_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 12)));
       TQ_CUDA(cudaFuncSetAttribute(k_probe_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((1 << PART_MAX_BITS) + 1) * 4)));
       attr_done = true;
     }
@@ -1321,35 +1689,71 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     sp.n = n;
     sp.part_cnt = cnt.as<uint32_t>();
     sp.part_cursor = cur_b.as<uint32_t>();
+    // Optimistic slabs: hash partitions of a probe batch are near-uniform, so every partition gets a fixed slab of
+    // n/P * 1.25 + 4096 rows and the histogram pass (a full extra read of the key column) is skipped; the scatter
+    // flags a slab that would overflow and finalize_pending re-runs the batch on the exact path.
+    const bool optimistic = j->optimistic_scatter && !g_exact_scatter;
+    const uint64_t slab = (uint64_t)n / P + (uint64_t)n / P / 4 + 4096;
+    const uint64_t part_rows = optimistic ? slab * P + (p.is_outer ? (uint64_t)n : 0) : (uint64_t)n;
+    if (part_rows > 0xFFFFFFF0ull) { set_error("probe batch too large for 32-bit partition offsets"); return TQ_ERR_INVALID_ARG; }
     for (int c = 0; c < j->n_probe_cols; c++) {
-      TQ_TRY(pc[c].data.reserve((size_t)n * 8));
+      TQ_TRY(pc[c].data.reserve((size_t)part_rows * 8));
       sp.in[c] = probe[c];
       sp.out[c].data = pc[c].data.as<uint64_t>();
       sp.out[c].bm = nullptr;
       if (probe[c].bm) {
-        TQ_TRY(pc[c].bm.reserve(bitmap_alloc_bytes(n)));
-        TQ_CUDA(cudaMemsetAsync(pc[c].bm.p, 0, bitmap_alloc_bytes(n), s));
+        TQ_TRY(pc[c].bm.reserve(bitmap_alloc_bytes((int64_t)part_rows)));
+        TQ_CUDA(cudaMemsetAsync(pc[c].bm.p, 0, bitmap_alloc_bytes((int64_t)part_rows), s));
         sp.out[c].bm = pc[c].bm.as<uint32_t>();
       }
       p.probe[c].data = pc[c].data.as<uint64_t>();
       p.probe[c].bm = sp.out[c].bm;
     }
     const int smem_bins = n_bins * 4;
-    const int smem_scat = SCAT_TILE * 8 + n_bins * 8 + SCAT_TILE * 2 + SCAT_TILE;
-    const int hist_grid = rt().sm_count * 4;
-    k_probe_part_hist<<<hist_grid, SCAT_THREADS, smem_bins, s>>>(sp);
-    count_launch();
-    TQ_TRY(check_launch("k_probe_part_hist"));
-    // part_off[q] = first row of partition q; the extra zero bin makes part_off[n_bins] the total
-    TQ_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), 1, off.as<uint32_t>(), 1, n_bins + 1, nullptr, j->scan_scratch2, s));
-    TQ_CUDA(cudaMemcpyAsync(cur_b.p, off.p, (size_t)(n_bins + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    const int smem_scat = SCAT_TILE * 8 + n_bins * 12 + SCAT_TILE * 2 + SCAT_TILE;
+    if (optimistic) {
+      DevBuf &lim = j->part_lim[cursor_slot];
+      TQ_TRY(lim.reserve((size_t)(n_bins + 1) * 4));
+      k_init_slabs<<<(n_bins + 255) / 256, 256, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), P, (uint32_t)slab, (uint32_t)n);
+      count_launch();
+      sp.part_lim = lim.as<uint32_t>();
+      sp.overflow = cur + 2;
+      p.part_lo = off.as<uint32_t>();
+      p.part_hi = cur_b.as<uint32_t>();   // after the scatter: one past the last row written into each slab
+      p.part_lim = lim.as<uint32_t>();
+    } else {
+      const int hist_grid = rt().sm_count * 4;
+      k_probe_part_hist<<<hist_grid, SCAT_THREADS, smem_bins, s>>>(sp);
+      count_launch();
+      TQ_TRY(check_launch("k_probe_part_hist"));
+      // off[q] = first row of partition q; the extra zero bin makes off[n_bins] the total
+      TQ_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), 1, off.as<uint32_t>(), 1, n_bins + 1, nullptr, j->scan_scratch2, s));
+      TQ_CUDA(cudaMemcpyAsync(cur_b.p, off.p, (size_t)(n_bins + 1) * 4, cudaMemcpyDeviceToDevice, s));
+      sp.part_lim = nullptr;
+      sp.overflow = cur + 2;
+      p.part_lo = off.as<uint32_t>();
+      p.part_hi = off.as<uint32_t>() + 1;
+      p.part_lim = nullptr;
+    }
     const int64_t scat_tiles = (n + SCAT_TILE - 1) / SCAT_TILE;
     const int64_t scat_cap = (int64_t)rt().sm_count * 4;
-    k_probe_scatter<<<(int)(scat_tiles < scat_cap ? scat_tiles : scat_cap), SCAT_THREADS, smem_scat, s>>>(sp);
+    bool any_in_bm = false;
+    for (int c = 0; c < j->n_probe_cols; c++) any_in_bm |= (probe[c].bm != nullptr);
+    ScatterKernel sfast = (!any_in_bm && !g_no_fast_kernel) ? scatter_fast_kernel(j->n_probe_cols) : nullptr;
+    if (sfast) {
+      static bool sattr[5] = {};
+      if (!sattr[j->n_probe_cols]) {
+        TQ_CUDA(cudaFuncSetAttribute(sfast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 12)));
+        sattr[j->n_probe_cols] = true;
+      }
+      const int64_t fcap = (int64_t)rt().sm_count * (j->n_probe_cols <= 2 ? 2 : 1);
+      sfast<<<(int)(scat_tiles < fcap ? scat_tiles : fcap), SCATF_THREADS, smem_scat, s>>>(sp);
+    } else {
+      k_probe_scatter<<<(int)(scat_tiles < scat_cap ? scat_tiles : scat_cap), SCAT_THREADS, smem_scat, s>>>(sp);
+    }
     count_launch();
     TQ_TRY(check_launch("k_probe_scatter"));
     p.selected = nullptr;
-    p.part_off = off.as<uint32_t>();
     const int work_parts = p.is_outer ? n_bins : P;
     // ~g_tiles_per_cta tiles per CTA: enough CTAs per partition that only a handful of partitions are live at once
     const int64_t tiles_per_part = (n / work_parts + PROBE_TILE - 1) / PROBE_TILE;
@@ -1362,14 +1766,25 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     const bool in_smem = image_bytes <= PART_MAX_SMEM_BYTES;
     p.table_in_smem = in_smem ? 1 : 0;
     const size_t table_bytes = in_smem ? image_bytes : 0;
-    if (j->build_unique) k_probe_part_uniq<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
+    bool any_out_bm = false;
+    for (int c = 0; c < j->n_probe_cols; c++) any_out_bm |= (p.out_probe[c].bm != nullptr);
+    for (int c = 0; c < j->n_build_cols; c++) any_out_bm |= (p.out_build[c].bm != nullptr);
+    ProbeKernel fast = (j->row_mode && !p.is_outer && !any_out_bm && !g_no_fast_kernel) ? fast_kernel(j->n_probe_cols, j->n_build_cols) : nullptr;
+    if (fast) {
+      static bool fast_attr[5][5] = {};
+      if (!fast_attr[j->n_probe_cols][j->n_build_cols]) {
+        TQ_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_MAX_SMEM_BYTES));
+        fast_attr[j->n_probe_cols][j->n_build_cols] = true;
+      }
+      fast<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
+    } else if (j->build_unique) k_probe_part_uniq<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
     else k_probe_part<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
     count_launch();
     j->probe_launches += 3;
     TQ_TRY(check_launch("k_probe_part"));
   }
   TQ_CUDA(cudaEventRecord(j->ev_b[cursor_slot], s));
-  TQ_CUDA(cudaMemcpyAsync(j->cursors_host.as<unsigned long long>() + 2 * cursor_slot, cur, 16, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaMemcpyAsync(j->cursors_host.as<unsigned long long>() + 4 * cursor_slot, cur, 32, cudaMemcpyDeviceToHost, s));
   return TQ_OK;
 }
 
@@ -1398,11 +1813,18 @@ static int32_t finalize_pending(tq_join *j) {
   if (!pb.active) return TQ_OK;
   Runtime &r = rt();
   TQ_CUDA(cudaEventSynchronize(pb.ev_k));
-  unsigned long long *hc = j->cursors_host.as<unsigned long long>() + 2 * pb.cursor_slot;
+  unsigned long long *hc = j->cursors_host.as<unsigned long long>() + 4 * pb.cursor_slot;
   uint64_t produced = hc[0];
   float ms = 0;
   if (cudaEventElapsedTime(&ms, j->ev_a[pb.cursor_slot], j->ev_b[pb.cursor_slot]) == cudaSuccess) j->last_probe_ns = (int64_t)(ms * 1e6);
   else cudaGetLastError();
+  if (hc[2]) {
+    // a partition slab of the optimistic (histogram-free) scatter was too small — skewed keys: exact offsets from now on
+    j->optimistic_scatter = false;
+    TQ_TRY(launch_probe(j, pb.probe, pb.d_selected, pb.n, pb.rb.get(), pb.rb->capacity, pb.cursor_slot));
+    TQ_CUDA(cudaStreamSynchronize(r.compute));
+    produced = hc[0];
+  }
   if (produced > pb.rb->capacity) {
     // duplicate build keys: the first launch served as the count pass; run again with the exact size
     TQ_TRY(launch_probe(j, pb.probe, pb.d_selected, pb.n, pb.rb.get(), produced, pb.cursor_slot));
@@ -1541,6 +1963,8 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   if (d->join_type == TQ_JOIN_LEFT_OUTER && d->outer_is_right) { set_error("left outer join needs outer_is_right == 0"); return TQ_ERR_INVALID_ARG; }
   if (d->join_type == TQ_JOIN_RIGHT_OUTER && !d->outer_is_right) { set_error("right outer join needs outer_is_right == 1"); return TQ_ERR_INVALID_ARG; }
   { const char *e = getenv("TQ_JOIN_FORCE_GLOBAL"); g_force_global_table = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_NO_FAST"); g_no_fast_kernel = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_EXACT_SCATTER"); g_exact_scatter = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_TILES_PER_CTA"); if (e && atoll(e) > 0) g_tiles_per_cta = atoll(e); }
   { const char *e = getenv("TQ_JOIN_PART_ROWS"); if (e && atoll(e) > 0) g_part_target_rows = atoll(e); }
   tq_join *j = new (std::nothrow) tq_join();
