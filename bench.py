@@ -177,7 +177,7 @@ class JoinBench:
 
         self.h_b = [pinned(self.n_build, self.bk), pinned(self.n_build, self.bv)]
         self.h_p = [pinned(self.n_probe, self.pk), pinned(self.n_probe, self.pv)]
-        self.out_rows = 1 << 22
+        self.out_rows = 1 << 23
         self.h_out = [pinned(self.out_rows) for _ in range(4)]
         self.h_out_bm = [np.zeros((self.out_rows + 7) // 8 + 8, dtype=np.uint8) for _ in range(4)]
 
@@ -202,21 +202,28 @@ class JoinBench:
         n, eof = C.c_int64(0), C.c_int32(0)
         total = 0
         checksum = 0
-        # feed the probe side in 8M-row host pieces, draining results as they complete (Next contract)
+        # feed the probe side in 8M-row host pieces and drain whatever is ready after each one (the Next contract:
+        # 0 rows with eof == 0 means "feed more"); result copies of piece i overlap the upload + kernels of piece i+1
         piece = 1 << 23
+
+        def drain():
+            nonlocal total, checksum
+            while True:
+                L.check(lib.tq_join_next(h, self.out_rows, out, C.byref(n), C.byref(eof)))
+                if n.value == 0:
+                    return bool(eof.value)
+                total += n.value
+                checksum += int(self.h_out[1][1][0])  # touch the result on the host
         for lo in range(0, self.n_probe, piece):
             rows = min(piece, self.n_probe - lo)
             a = (L.TQColumn * 2)()
             for i, (p, _) in enumerate(self.h_p):
                 a[i].length, a[i].data, a[i].null_bitmap, a[i].offsets = rows, p.value + lo * 8, None, None
             L.check(lib.tq_join_put_probe(h, a, None, L.TQ_MEM_HOST))
+            drain()
         L.check(lib.tq_join_probe_eof(h))
-        while True:
-            L.check(lib.tq_join_next(h, self.out_rows, out, C.byref(n), C.byref(eof)))
-            if n.value == 0 and eof.value:
-                break
-            total += n.value
-            checksum += int(self.h_out[1][1][0])  # touch the result on the host
+        while not drain():
+            pass
         L.check(lib.tq_join_destroy(h))
         return total
 

@@ -1874,7 +1874,7 @@ static int32_t start_batch(tq_join *j, const std::vector<DCol> &probe, const uin
 }
 
 // Ship one piece of host rows to the device (double-buffered input sets) and start its probe.
-static int32_t process_host_piece(tq_join *j, const tq_column *cols, int64_t row0, int64_t rows, const uint8_t *selected) {
+static int32_t process_host_piece(tq_join *j, const tq_column *cols, int64_t row0, int64_t rows, const uint8_t *selected, bool eager_d2h = true) {
   Runtime &r = rt();
   const int slot = j->in_flip;
   j->in_flip ^= 1;
@@ -1906,7 +1906,7 @@ static int32_t process_host_piece(tq_join *j, const tq_column *cols, int64_t row
   }
   TQ_CUDA(cudaEventRecord(in.ev_h2d, r.h2d));
   TQ_CUDA(cudaStreamWaitEvent(r.compute, in.ev_h2d, 0));
-  return start_batch(j, view, d_sel, rows, /*want_host=*/true, slot);
+  return start_batch(j, view, d_sel, rows, /*want_host=*/eager_d2h, slot);
 }
 
 static int32_t flush_probe_staging(tq_join *j) {
@@ -2109,7 +2109,7 @@ int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *sele
     TQ_TRY(flush_probe_staging(j));
     for (int64_t row0 = 0; row0 < rows; row0 += j->batch_rows) {
       const int64_t piece = rows - row0 < j->batch_rows ? rows - row0 : j->batch_rows;
-      TQ_TRY(process_host_piece(j, cols, row0, piece, selected));
+      TQ_TRY(process_host_piece(j, cols, row0, piece, selected, /*eager_d2h=*/false));
     }
     TQ_CUDA(cudaStreamSynchronize(r.h2d));  // caller may reuse its buffers on return
     return TQ_OK;
@@ -2149,7 +2149,9 @@ int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t 
   for (;;) {
     if (j->host_cur && j->host_cur_pos < j->host_cur->n) break;
     if (j->host_cur) { recycle(j, std::move(j->host_cur)); j->host_cur_pos = 0; }
-    if (j->results.empty()) TQ_TRY(finalize_pending(j));
+    // The batch in flight is only waited for at end of input: until then "no rows yet" means "feed more", so the
+    // D2H of batch i overlaps the H2D + kernels of batch i+1.
+    if (j->results.empty() && j->probe_eof) TQ_TRY(finalize_pending(j));
     if (j->results.empty()) {
       *eof = j->probe_eof ? 1 : 0;
       for (int c = 0; c < ncols; c++) out_cols[c].length = 0;
@@ -2159,6 +2161,9 @@ int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t 
     j->results.pop_front();
     j->host_cur_pos = 0;
     if (!j->host_cur->on_host) {
+      // Large consumer buffers: copy straight from HBM into the caller's columns (no staging, no CPU memcpy).
+      const bool direct = max_rows >= (1 << 18) && (max_rows & 7) == 0;
+      if (direct) { TQ_CUDA(cudaStreamSynchronize(r.compute)); break; }
       TQ_CUDA(cudaStreamSynchronize(r.compute));
       TQ_TRY(enqueue_d2h(j, j->host_cur.get()));
     }
@@ -2166,8 +2171,24 @@ int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t 
   }
   ResultBatch *rb = j->host_cur.get();
   const int64_t take = (rb->n - j->host_cur_pos) < max_rows ? (rb->n - j->host_cur_pos) : max_rows;
-  for (int c = 0; c < ncols; c++) {
+  for (int c = 0; c < ncols; c++)
     if (!out_cols[c].data || !out_cols[c].null_bitmap) { set_error("output column %d needs data and null_bitmap buffers", c); return TQ_ERR_INVALID_ARG; }
+  if (!rb->on_host) {
+    if ((j->host_cur_pos & 7) != 0) { set_error("internal: unaligned direct result copy"); return TQ_ERR_STATE; }
+    for (int c = 0; c < ncols; c++) {
+      TQ_CUDA(cudaMemcpyAsync(out_cols[c].data, rb->cols[c].data.as<uint8_t>() + j->host_cur_pos * 8, (size_t)take * 8, cudaMemcpyDeviceToHost, r.d2h));
+      TQ_CUDA(cudaMemcpyAsync(out_cols[c].null_bitmap, rb->cols[c].bm.as<uint8_t>() + (j->host_cur_pos >> 3), bitmap_bytes(take), cudaMemcpyDeviceToHost, r.d2h));
+      out_cols[c].length = take;
+    }
+    TQ_CUDA(cudaStreamSynchronize(r.d2h));
+    if (take & 7) for (int c = 0; c < ncols; c++) out_cols[c].null_bitmap[bitmap_bytes(take) - 1] &= (uint8_t)((1u << (take & 7)) - 1);
+    j->host_cur_pos += take;
+    // a partially consumed batch continues on the staged path if the next call asks for a small / unaligned slice
+    if (j->host_cur_pos < rb->n && (j->host_cur_pos & 7) != 0) { TQ_TRY(enqueue_d2h(j, rb)); TQ_CUDA(cudaEventSynchronize(rb->ev_ready)); }
+    *n_rows = take;
+    return TQ_OK;
+  }
+  for (int c = 0; c < ncols; c++) {
     memcpy(out_cols[c].data, rb->h_data[c].as<uint8_t>() + j->host_cur_pos * 8, (size_t)take * 8);
     host_bitmap_extract(out_cols[c].null_bitmap, rb->h_bm[c].as<uint8_t>(), j->host_cur_pos, take);
     out_cols[c].length = take;
