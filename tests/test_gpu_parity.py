@@ -421,6 +421,25 @@ def test_agg_int_sum_overflow(lib):
     assert got.rows() == [(5,)]
 
 
+def test_agg_not_null_columns_compact_state(lib):
+    """TQ_TYPE_NOT_NULL on the argument columns drops the SUM/MAX/MIN 'seen' word (16-byte group records)"""
+    rng = np.random.default_rng(21)
+    n = 250000
+    k = Column(INT64, rng.integers(0, 40000, n))
+    x = Column(FLOAT64, np.floor(rng.random(n) * 4096) / 16)  # dyadic values: float sums exact in any order
+    v = Column(INT64, rng.integers(-1000, 1000, n))
+    funcs = [(AGG_SUM, 1), (AGG_COUNT, -1), (AGG_FIRSTROW, 0), (AGG_MAX, 2), (AGG_MIN, 1), (AGG_AVG, 2)]
+    src = MockDataSource([INT64, FLOAT64, INT64], [k, x, v], 1 << 16)
+    e = HashAggExec(src, [0], funcs, 40000, not_null_cols=(0, 1, 2))
+    e.Open()
+    got = e.drain()
+    e.Close()
+    rc, want = O.hash_agg([INT64, FLOAT64, INT64], [k, x, v], [0], funcs, 2)
+    g, w = _sorted_by_key(got, 2), _sorted_by_key(want, 2)
+    for a, b in zip(g, w):
+        assert_col_equal(a, b)
+
+
 def test_agg_table_growth(lib):
     # est_groups far too small: the table grows several times and deferred rows are replayed
     rng = np.random.default_rng(9)

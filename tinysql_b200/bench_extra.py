@@ -108,7 +108,7 @@ def run_agg(args, lib, peak, peak_src, sampler_cls):
     k = np.random.default_rng(5).integers(0, groups, n, dtype=np.int64)
     x = np.random.default_rng(6).random(n)                      # randDatum, executor/benchmark_test.go:118-119
     dk, dx = DeviceColumn.from_host(Column(INT64, k)), DeviceColumn.from_host(Column(FLOAT64, x))
-    types = (C.c_int32 * 2)(INT64, FLOAT64)
+    types = (C.c_int32 * 2)(INT64 | 0x100, FLOAT64 | 0x100)  # both columns NOT NULL (TQ_TYPE_NOT_NULL)
     gb = (C.c_int32 * 1)(0)
     funcs = (L.TQAggFunc * 3)(L.TQAggFunc(1, 1), L.TQAggFunc(0, -1), L.TQAggFunc(5, 0))  # SUM(x), COUNT(*), firstrow(k)
     desc = L.TQAggDesc(2, types, 1, gb, 3, funcs, groups)

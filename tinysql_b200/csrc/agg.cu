@@ -1,9 +1,11 @@
 // agg.cu — HashAggExec on the device (replaces executor/aggregate.go and executor/aggfuncs).
 //
-// One open-addressed table of group keys lives in HBM/L2 (8-byte key per slot, lock-free insertion by
-// atomicCAS); aggregate states are struct-of-arrays indexed by the SLOT, so an input row costs one key
-// probe plus one L2 atomic per state word (RED.ADD.F64 / ATOM.ADD.U64 / ATOM.MAX.U64).  Rows whose
-// whole warp lands in one slot (scalar aggregates, heavy skew) are combined with warp shuffles first.
+// One open-addressed table lives in L2: a dense KEY array probed in 4-key buckets (one 32-byte sector holds four
+// candidate slots, so a lookup is ~one L2 round trip even at load factor 0.5; slots are claimed lock-free with
+// atomicCAS) and an array-of-structs STATE array (the words of one group are contiguous: 16 bytes for SUM(f64) +
+// COUNT, i.e. two groups per sector).  An input row costs the key bucket load plus one L2 reduction per updated
+// state word (RED.ADD.F64 / RED.ADD.U64 / ATOM.MAX.U64).  Rows whose whole warp lands in one slot
+// (scalar aggregates, heavy skew) are combined with warp shuffles first.
 // Partial -> final (aggregate.go:96-133) is the same kernel in "merge" mode: COUNT adds partial counts,
 // AVG adds (count, sum) pairs — the semantics of MergePartialResult.
 #include <deque>
@@ -21,20 +23,22 @@ static constexpr uint32_t SLOT_NONE = 0xFFFFFFFFu;
 
 enum : unsigned { AERR_BIGINT = 1u };
 
-// state words per function (all 8 bytes, zero-initialised):
+// state words per function (8 bytes each, zero-initialised; w* are word offsets inside the slot, -1 = absent):
 //   COUNT      w0 = count
-//   SUM  f64   w0 = sum (double bits)          w1 = non-NULL inputs seen
-//   SUM  int   w0 = sum low 64   w2 = sum high 64 (128-bit exact)   w1 = non-NULL inputs seen
-//   AVG        like SUM; w1 is the count
-//   MAX / MIN  w0 = order-mapped value (atomicMax), w1 = non-NULL inputs seen
-//   FIRSTROW   w0 = value, w1 = 1 claimed | 2 value-is-NULL (claim by atomicCAS), w2 = 1 when w0 is published
+//   SUM  f64   w0 = sum (double bits)                                 w1 = "a non-NULL input was seen" flag
+//   SUM  int   w0 = sum low 64, w2 = sum high 64 (128-bit exact)      w1 = flag
+//   AVG        like SUM, but w1 is the COUNT of non-NULL inputs (atomic)
+//   MAX / MIN  w0 = order-mapped value (atomicMax)                    w1 = flag
+//   FIRSTROW   w0 = value, w1 = 1 claimed | 3 claimed-and-NULL (claim by atomicCAS)
 struct AggFuncDev {
   int func;
   int arg_col;     // -1: constant non-NULL 1
   int arg_col2;    // merge mode AVG: the partial-sum column (arg_col is the partial count)
   int arg_type;    // TQ_TYPE_* of the value being aggregated
   int key_passthrough;  // FIRSTROW over the GROUP BY column: answered from the slot key, no state
-  uint64_t *w0, *w1, *w2;
+  int w0, w1, w2;       // word offsets of the state inside the slot
+  int use_flag;         // SUM/MAX/MIN: maintain the "seen a non-NULL input" flag in w1
+  int arg_not_null;     // the argument column is declared NOT NULL (mysql.NotNullFlag): no flag word, bitmaps ignored
 };
 
 struct AggParams {
@@ -44,7 +48,9 @@ struct AggParams {
   int merge;    // 0: Partial1/Complete (raw rows)  1: Final (partial rows)
   int n_funcs;
   AggFuncDev f[AGG_MAXF];
-  uint64_t *slot_keys;
+  uint64_t *keys;             // keys[i] of slot i (AGG_EMPTY = free); probed as aligned buckets of 4
+  uint64_t *tbl;              // state record of slot i = tbl[i * stride ...]
+  int stride;                 // words per state record (power of two)
   uint64_t mask, n_slots;     // side slots: n_slots = NULL group, n_slots+1 = the AGG_EMPTY key
   uint32_t *side_used;        // [0] NULL group seen, [1] sentinel-key group seen
   unsigned long long *n_used; // occupied regular slots
@@ -74,147 +80,183 @@ __device__ __forceinline__ void add128(uint64_t *lo, uint64_t *hi, int64_t v) {
   if (hi_add) atomicAdd(reinterpret_cast<unsigned long long *>(hi), hi_add);
 }
 
-__global__ void __launch_bounds__(256) k_agg_update(const AggParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t n_round = (p.n + 31) & ~31ll;
-  int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; it < n_round; it += stride) {  // whole warps iterate together (n_round is a multiple of 32)
-    const bool active = it < p.n;
-    int64_t r = 0;
-    uint32_t slot = SLOT_NONE;
-    if (active) {
-      r = p.row_list ? (int64_t)p.row_list[it] : it;
-      // ---- find or insert the group (getGroupKey + getPartialResult, aggregate.go:359-410)
-      if (p.key_col < 0) {
-        slot = (uint32_t)p.n_slots;
-        if (p.side_used[0] == 0) p.side_used[0] = 1;
-      } else if (!tqd::bm_not_null(p.cols[p.key_col].bm, r)) {
-        slot = (uint32_t)p.n_slots;  // NilFlag: NULL is its own group (codec.go:718-720)
-        if (p.side_used[0] == 0) p.side_used[0] = 1;
-      } else {
-        const uint64_t key = p.cols[p.key_col].data[r];
-        if (key == AGG_EMPTY) {
-          slot = (uint32_t)p.n_slots + 1;
-          if (p.side_used[1] == 0) p.side_used[1] = 1;
-        } else {
-          uint64_t idx = tqd::mix64(key) & p.mask;
-          bool defer = false;
-          for (uint64_t probes = 0;; probes++) {
-            if (probes > p.mask) { defer = true; break; }  // table full (cannot happen below `limit`)
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&p.slot_keys[idx]);
-            if (cur == key) break;
-            if (cur == AGG_EMPTY) {
-              if (*reinterpret_cast<volatile unsigned long long *>(p.n_used) >= p.limit) { defer = true; break; }
-              cur = atomicCAS(reinterpret_cast<unsigned long long *>(&p.slot_keys[idx]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
-              if (cur == AGG_EMPTY) { atomicAdd(p.n_used, 1ull); break; }
-              if (cur == key) break;
-            }
-            idx = (idx + 1) & p.mask;
-          }
-          if (defer) {
-            const unsigned pos = atomicAdd(p.n_deferred, 1u);
-            p.deferred[pos] = (uint32_t)r;
-          } else {
-            slot = (uint32_t)idx;
-          }
-        }
-      }
-    }
-    const bool live = slot != SLOT_NONE;
-    // warp-uniform group? then reduce with shuffles and let lane `leader` do the atomics
-    const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-    if (live_mask == 0) continue;
-    const int leader = __ffs(live_mask) - 1;
-    const uint32_t lead_slot = __shfl_sync(0xffffffffu, slot, leader);
-    const bool uniform = __all_sync(0xffffffffu, !live || slot == lead_slot);
+// w1 bookkeeping: AVG needs the exact count of non-NULL inputs (atomic); SUM / MAX / MIN only need to know that one
+// was seen — a flag that is read (same sector as the state just updated) and stored once, instead of an atomic per row.
+// While no batch has carried a NULL bitmap for the argument the flag is not maintained at all (use_flag == 0): a group
+// that exists then has a value by construction; the first nullable batch back-fills the flags (k_agg_set_flags).
+__device__ __forceinline__ void note_seen(uint64_t *w1, bool exact_count, bool use_flag, long long cnt) {
+  if (exact_count) atomicAdd(reinterpret_cast<unsigned long long *>(w1), (unsigned long long)cnt);
+  else if (use_flag && *reinterpret_cast<volatile unsigned long long *>(w1) == 0ull) *reinterpret_cast<volatile unsigned long long *>(w1) = 1ull;  // use_flag is 0 when there is no flag word
+}
 
-    for (int fi = 0; fi < p.n_funcs; fi++) {
-      const AggFuncDev &f = p.f[fi];
-      if (f.key_passthrough) continue;
-      bool nn = false;
-      uint64_t v = 1;
-      if (live) {
-        if (f.arg_col < 0) nn = true;
-        else { nn = tqd::bm_not_null(p.cols[f.arg_col].bm, r); v = p.cols[f.arg_col].data[r]; }
+// Apply one input row to its group's state (UpdatePartialResult / MergePartialResult).  Warp-collective: all 32 lanes call.
+__device__ __forceinline__ void agg_apply(const AggParams &p, uint32_t slot, int64_t r) {
+  const int lane = threadIdx.x & 31;
+  const bool live = slot != SLOT_NONE;
+  // warp-uniform group? then reduce with shuffles and let lane `leader` do the atomics
+  const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+  if (live_mask == 0) return;
+  const int leader = __ffs(live_mask) - 1;
+  const uint32_t lead_slot = __shfl_sync(0xffffffffu, slot, leader);
+  const bool uniform = __all_sync(0xffffffffu, !live || slot == lead_slot);
+  uint64_t *const sl = p.tbl + (uint64_t)(live ? slot : 0) * p.stride;       // this row's slot record
+  uint64_t *const lsl = p.tbl + (uint64_t)lead_slot * p.stride;              // the warp leader's
+  for (int fi = 0; fi < p.n_funcs; fi++) {
+    const AggFuncDev &f = p.f[fi];
+    if (f.key_passthrough) continue;
+    bool nn = false;
+    uint64_t v = 1;
+    if (live) {
+      if (f.arg_col < 0) nn = true;
+      else { nn = f.arg_not_null ? true : tqd::bm_not_null(p.cols[f.arg_col].bm, r); v = p.cols[f.arg_col].data[r]; }
+    }
+    switch (f.func) {
+      case TQ_AGG_COUNT: {  // func_count.go:33-49 (raw: count non-NULL) / :99-113 (merge: add partial counts)
+        const long long add = nn ? (p.merge ? (long long)v : 1ll) : 0ll;
+        if (uniform) {  // 64-bit warp sum (counts in merge mode can exceed 32 bits)
+          long long s = add;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+          if (lane == leader && s) atomicAdd(reinterpret_cast<unsigned long long *>(lsl + f.w0), (unsigned long long)s);
+        } else if (live && add) {
+          atomicAdd(reinterpret_cast<unsigned long long *>(sl + f.w0), (unsigned long long)add);
+        }
+        break;
       }
-      switch (f.func) {
-        case TQ_AGG_COUNT: {  // func_count.go:33-49 (raw: count non-NULL) / :99-113 (merge: add partial counts)
-          const long long add = nn ? (p.merge ? (long long)v : 1ll) : 0ll;
-          // 64-bit warp sum (counts in merge mode can exceed 32 bits)
+      case TQ_AGG_SUM:
+      case TQ_AGG_AVG: {
+        // raw: func_sum.go:62-82,115-140; func_avg.go:63-83,172-190.   merge: func_sum.go:84-92,142-154; func_avg.go:93-131,200-238
+        long long cnt_add = nn ? 1ll : 0ll;
+        uint64_t val = v;
+        bool val_nn = nn;
+        if (p.merge && f.func == TQ_AGG_AVG) {
+          // partial row = (count, sum): skipped if either is NULL (func_avg.go:96-110)
+          bool nn2 = false; uint64_t v2 = 0;
+          if (live) { nn2 = tqd::bm_not_null(p.cols[f.arg_col2].bm, r); v2 = p.cols[f.arg_col2].data[r]; }
+          val_nn = nn && nn2;
+          cnt_add = val_nn ? (long long)v : 0ll;
+          val = v2;
+        }
+        const bool exact = f.func == TQ_AGG_AVG;
+        if (f.arg_type == TQ_TYPE_FLOAT64) {
+          double x = val_nn ? __longlong_as_double((long long)val) : 0.0;
           if (uniform) {
-            long long s = add;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if (lane == leader && s) atomicAdd(reinterpret_cast<unsigned long long *>(&f.w0[lead_slot]), (unsigned long long)s);
-          } else if (live && add) {
-            atomicAdd(reinterpret_cast<unsigned long long *>(&f.w0[slot]), (unsigned long long)add);
-          }
-          break;
-        }
-        case TQ_AGG_SUM:
-        case TQ_AGG_AVG: {
-          // raw: func_sum.go:62-82,115-140; func_avg.go:63-83,172-190.   merge: func_sum.go:84-92,142-154; func_avg.go:93-131,200-238
-          long long cnt_add = nn ? 1ll : 0ll;
-          uint64_t val = v;
-          bool val_nn = nn;
-          if (p.merge && f.func == TQ_AGG_AVG) {
-            // partial row = (count, sum): skipped if either is NULL (func_avg.go:96-110)
-            bool nn2 = false; uint64_t v2 = 0;
-            if (live) { nn2 = tqd::bm_not_null(p.cols[f.arg_col2].bm, r); v2 = p.cols[f.arg_col2].data[r]; }
-            val_nn = nn && nn2;
-            cnt_add = val_nn ? (long long)v : 0ll;
-            val = v2;
-          }
-          if (f.arg_type == TQ_TYPE_FLOAT64) {
-            double x = val_nn ? __longlong_as_double((long long)val) : 0.0;
-            if (uniform) {
-#pragma unroll
-              for (int d = 16; d > 0; d >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, d); cnt_add += __shfl_xor_sync(0xffffffffu, cnt_add, d); }
-              if (lane == leader && cnt_add) {
-                atomicAdd(reinterpret_cast<double *>(&f.w0[lead_slot]), x);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&f.w1[lead_slot]), (unsigned long long)cnt_add);
-              }
-            } else if (live && val_nn) {
-              atomicAdd(reinterpret_cast<double *>(&f.w0[slot]), x);
-              atomicAdd(reinterpret_cast<unsigned long long *>(&f.w1[slot]), (unsigned long long)cnt_add);
+            for (int d = 16; d > 0; d >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, d); cnt_add += __shfl_xor_sync(0xffffffffu, cnt_add, d); }
+            if (lane == leader && cnt_add) {
+              atomicAdd(reinterpret_cast<double *>(lsl + f.w0), x);
+              note_seen(lsl + f.w1, exact, f.use_flag, cnt_add);
             }
-          } else {
-            if (live && val_nn) {  // exact 128-bit accumulation; range is checked when the group is finalised
-              add128(&f.w0[slot], &f.w2[slot], (int64_t)val);
-              atomicAdd(reinterpret_cast<unsigned long long *>(&f.w1[slot]), (unsigned long long)cnt_add);
-            }
+          } else if (live && val_nn) {
+            atomicAdd(reinterpret_cast<double *>(sl + f.w0), x);
+            note_seen(sl + f.w1, exact, f.use_flag, cnt_add);
           }
-          break;
-        }
-        case TQ_AGG_MAX:
-        case TQ_AGG_MIN: {  // func_max_min.go:83-118 (+ Uint / Float64 twins); merge is the same comparison
-          if (live && nn) {
-            uint64_t m = order_map(v, f.arg_type);
-            if (f.func == TQ_AGG_MIN) m = ~m;
-            atomicMax(reinterpret_cast<unsigned long long *>(&f.w0[slot]), (unsigned long long)m);
-            atomicAdd(reinterpret_cast<unsigned long long *>(&f.w1[slot]), 1ull);
+        } else {
+          if (live && val_nn) {  // exact 128-bit accumulation; range is checked when the group is finalised
+            add128(sl + f.w0, sl + f.w2, (int64_t)val);
+            note_seen(sl + f.w1, exact, f.use_flag, cnt_add);
           }
-          break;
         }
-        default: {  // FIRSTROW func_first_row.go:67-89: the first row to claim the group wins
-          if (live) {
-            const unsigned long long want = nn ? 1ull : 3ull;
-            const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&f.w1[slot]), 0ull, want);
-            if (prev == 0ull) f.w0[slot] = v;
+        break;
+      }
+      case TQ_AGG_MAX:
+      case TQ_AGG_MIN: {  // func_max_min.go:83-118 (+ Uint / Float64 twins); merge is the same comparison
+        if (live && nn) {
+          uint64_t m = order_map(v, f.arg_type);
+          if (f.func == TQ_AGG_MIN) m = ~m;
+          atomicMax(reinterpret_cast<unsigned long long *>(sl + f.w0), (unsigned long long)m);
+          note_seen(sl + f.w1, false, f.use_flag, 1);
+        }
+        break;
+      }
+      default: {  // FIRSTROW func_first_row.go:67-89: the first row to claim the group wins
+        if (live) {
+          const unsigned long long want = nn ? 1ull : 3ull;
+          if (*reinterpret_cast<volatile unsigned long long *>(sl + f.w1) == 0ull) {
+            const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(sl + f.w1), 0ull, want);
+            if (prev == 0ull) sl[f.w0] = v;
           }
-          break;
         }
+        break;
       }
     }
   }
 }
 
+// four adjacent keys = one sector; volatile so concurrent inserts are observed (L1 is bypassed)
+__device__ __forceinline__ void ld_bucket(const uint64_t *keys, uint64_t b, unsigned long long (&k)[4]) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(k[0]), "=l"(k[1]) : "l"(keys + b));
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(k[2]), "=l"(k[3]) : "l"(keys + b + 2));
+}
+
+__global__ void __launch_bounds__(256) k_agg_update(const AggParams p) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = (p.n + 31) & ~31ll;  // whole warps iterate together
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_round; it += stride) {
+    uint32_t slot = SLOT_NONE;
+    int64_t r = 0;
+    if (it < p.n) {
+      r = p.row_list ? (int64_t)p.row_list[it] : it;
+      // ---- getGroupKey (aggregate.go:359-394): NULL is its own group (NilFlag, codec.go:718-720)
+      if (p.key_col < 0 || !tqd::bm_not_null(p.cols[p.key_col].bm, r)) {
+        slot = (uint32_t)p.n_slots;
+        if (p.side_used[0] == 0) p.side_used[0] = 1;
+      } else {
+        const uint64_t key = tqd::ld_stream_u64(p.cols[p.key_col].data + r);
+        if (key == AGG_EMPTY) {
+          slot = (uint32_t)p.n_slots + 1;
+          if (p.side_used[1] == 0) p.side_used[1] = 1;
+        } else {
+          // ---- getPartialResult (aggregate.go:396-410): find or claim the group's slot, bucket by bucket
+          uint64_t b = (tqd::mix64(key) & p.mask) & ~3ull;
+          bool defer = false, found = false;
+          for (uint64_t buckets = 0; !found && !defer; buckets++) {
+            if (buckets * 4 > p.mask) { defer = true; break; }  // table full (cannot happen below `limit`)
+            unsigned long long k[4];
+            ld_bucket(p.keys, b, k);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              if (found || defer) break;
+              if (k[j] == key) { slot = (uint32_t)(b + j); found = true; break; }
+              if (k[j] == AGG_EMPTY) {
+                if (*reinterpret_cast<volatile unsigned long long *>(p.n_used) >= p.limit) { defer = true; break; }
+                const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&p.keys[b + j]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
+                if (prev == AGG_EMPTY) { atomicAdd(p.n_used, 1ull); slot = (uint32_t)(b + j); found = true; break; }
+                if (prev == key) { slot = (uint32_t)(b + j); found = true; break; }
+                // another key won this slot: keep scanning
+              }
+            }
+            b = (b + 4) & p.mask;
+          }
+          if (defer) { slot = SLOT_NONE; p.deferred[atomicAdd(p.n_deferred, 1u)] = (uint32_t)r; }
+        }
+      }
+    }
+    agg_apply(p, slot, r);
+  }
+}
+
+// One-time back-fill when the first batch with a NULL bitmap for a SUM/MAX/MIN argument arrives: every group that
+// exists so far was fed only non-NULL values, so its "seen" flag becomes 1.
+__global__ void k_agg_set_flags(const uint64_t *keys, uint64_t *tbl, int stride, uint64_t n_slots, const uint32_t *side_used, int w1) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n_slots + 2; i += gstride) {
+    const bool used = i < n_slots ? keys[i] != AGG_EMPTY : side_used[i - n_slots] != 0;
+    if (used) tbl[i * stride + w1] = 1;
+  }
+}
+
+// value of the SUM/MAX/MIN "seen" word when the flag is not maintained: the group exists, so it has a value
+__device__ __forceinline__ uint64_t seen_of(const AggFuncDev &f, const uint64_t *sl) { return (f.func == TQ_AGG_AVG || (f.use_flag && f.w1 >= 0)) ? sl[f.w1] : 1ull; }
+
 struct CollectParams {
   int n_funcs;
   AggFuncDev f[AGG_MAXF];
   DColMut out[AGG_MAXF];
-  const uint64_t *slot_keys;
+  const uint64_t *keys;
+  const uint64_t *tbl;
+  int stride;
   uint64_t n_slots;
   const uint32_t *side_used;
   unsigned long long *out_n;
@@ -240,7 +282,8 @@ __global__ void __launch_bounds__(256) k_agg_collect(const CollectParams p) {
     bool used;
     uint64_t key = 0;
     bool key_nn = true;
-    if (i < p.n_slots) { key = p.slot_keys[i]; used = key != AGG_EMPTY; }
+    const uint64_t *sl = p.tbl + i * p.stride;
+    if (i < p.n_slots) { key = p.keys[i]; used = key != AGG_EMPTY; }
     else if (i == p.n_slots) { used = p.side_used[0] != 0; key_nn = false; }
     else { used = p.side_used[1] != 0; key = AGG_EMPTY; }
     if (!used) continue;
@@ -252,13 +295,13 @@ __global__ void __launch_bounds__(256) k_agg_collect(const CollectParams p) {
         const AggFuncDev &f = p.f[fi];
         if (f.key_passthrough) { put_out(p.out_state[w++], pos, key_nn ? key : 0, key_nn); continue; }
         switch (f.func) {
-          case TQ_AGG_COUNT: put_out(p.out_state[w++], pos, f.w0[i], true); break;
+          case TQ_AGG_COUNT: put_out(p.out_state[w++], pos, sl[f.w0], true); break;
           case TQ_AGG_SUM:
           case TQ_AGG_AVG: {
-            const uint64_t cnt = f.w1[i];
-            uint64_t sum = f.w0[i];
+            const uint64_t cnt = seen_of(f, sl);
+            uint64_t sum = sl[f.w0];
             if (f.arg_type != TQ_TYPE_FLOAT64) {
-              const int64_t hi = (int64_t)f.w2[i];
+              const int64_t hi = (int64_t)sl[f.w2];
               if (cnt && hi != ((int64_t)sum >> 63)) atomicOr(p.err, AERR_BIGINT);
             }
             if (f.func == TQ_AGG_AVG) put_out(p.out_state[w++], pos, cnt, true);   // AVG partial = (count, sum) descriptor.go:57-92
@@ -267,15 +310,15 @@ __global__ void __launch_bounds__(256) k_agg_collect(const CollectParams p) {
           }
           case TQ_AGG_MAX:
           case TQ_AGG_MIN: {
-            const uint64_t cnt = f.w1[i];
-            uint64_t m = f.w0[i];
+            const uint64_t cnt = seen_of(f, sl);
+            uint64_t m = sl[f.w0];
             if (f.func == TQ_AGG_MIN) m = ~m;
             put_out(p.out_state[w++], pos, cnt ? order_unmap(m, f.arg_type) : 0, cnt != 0);
             break;
           }
           default: {
-            const uint64_t st = f.w1[i];
-            put_out(p.out_state[w++], pos, (st == 1) ? f.w0[i] : 0, st == 1);
+            const uint64_t st = sl[f.w1];
+            put_out(p.out_state[w++], pos, (st == 1) ? sl[f.w0] : 0, st == 1);
             break;
           }
         }
@@ -286,26 +329,26 @@ __global__ void __launch_bounds__(256) k_agg_collect(const CollectParams p) {
       const AggFuncDev &f = p.f[fi];
       if (f.key_passthrough) { put_out(p.out[fi], pos, key_nn ? key : 0, key_nn); continue; }
       switch (f.func) {
-        case TQ_AGG_COUNT: put_out(p.out[fi], pos, f.w0[i], true); break;            // func_count.go:23-27
+        case TQ_AGG_COUNT: put_out(p.out[fi], pos, sl[f.w0], true); break;            // func_count.go:23-27
         case TQ_AGG_SUM: {                                                          // func_sum.go:53-60,104-113
-          const uint64_t cnt = f.w1[i];
+          const uint64_t cnt = seen_of(f, sl);
           if (cnt == 0) { put_out(p.out[fi], pos, 0, false); break; }
           if (f.arg_type != TQ_TYPE_FLOAT64) {
-            const int64_t hi = (int64_t)f.w2[i];
-            if (hi != ((int64_t)f.w0[i] >> 63)) atomicOr(p.err, AERR_BIGINT);    // types.AddInt64 overflow (types/overflow.go:33-40)
+            const int64_t hi = (int64_t)sl[f.w2];
+            if (hi != ((int64_t)sl[f.w0] >> 63)) atomicOr(p.err, AERR_BIGINT);    // types.AddInt64 overflow (types/overflow.go:33-40)
           }
-          put_out(p.out[fi], pos, f.w0[i], true);
+          put_out(p.out[fi], pos, sl[f.w0], true);
           break;
         }
         case TQ_AGG_AVG: {                                                          // func_avg.go:47-55,159-167
-          const int64_t cnt = (int64_t)f.w1[i];
+          const int64_t cnt = (int64_t)sl[f.w1];
           if (cnt == 0) { put_out(p.out[fi], pos, 0, false); break; }
           if (f.arg_type == TQ_TYPE_FLOAT64) {
-            const double r = __longlong_as_double((long long)f.w0[i]) / (double)cnt;
+            const double r = __longlong_as_double((long long)sl[f.w0]) / (double)cnt;
             put_out(p.out[fi], pos, (uint64_t)__double_as_longlong(r), true);
           } else {
-            const int64_t hi = (int64_t)f.w2[i];
-            const int64_t sum = (int64_t)f.w0[i];
+            const int64_t hi = (int64_t)sl[f.w2];
+            const int64_t sum = (int64_t)sl[f.w0];
             if (hi != (sum >> 63)) atomicOr(p.err, AERR_BIGINT);
             put_out(p.out[fi], pos, (uint64_t)(sum / cnt), true);                   // Go truncating division
           }
@@ -313,15 +356,15 @@ __global__ void __launch_bounds__(256) k_agg_collect(const CollectParams p) {
         }
         case TQ_AGG_MAX:
         case TQ_AGG_MIN: {                                                          // func_max_min.go:73-81
-          const uint64_t cnt = f.w1[i];
-          uint64_t m = f.w0[i];
+          const uint64_t cnt = seen_of(f, sl);
+          uint64_t m = sl[f.w0];
           if (f.func == TQ_AGG_MIN) m = ~m;
           put_out(p.out[fi], pos, cnt ? order_unmap(m, f.arg_type) : 0, cnt != 0);
           break;
         }
         default: {                                                                  // func_first_row.go:91-99
-          const uint64_t st = f.w1[i];
-          put_out(p.out[fi], pos, (st == 1) ? f.w0[i] : 0, st == 1);
+          const uint64_t st = sl[f.w1];
+          put_out(p.out[fi], pos, (st == 1) ? sl[f.w0] : 0, st == 1);
           break;
         }
       }
@@ -335,19 +378,19 @@ __global__ void k_fill_u64(uint64_t *p, uint64_t n, uint64_t v) {
   for (; i < n; i += stride) p[i] = v;
 }
 
-// Move every occupied slot (key + all state words) of the old table into the new, larger one.
-__global__ void __launch_bounds__(256) k_agg_rehash(const uint64_t *old_keys, uint64_t old_slots, const uint64_t *old_state, uint64_t *new_keys,
-                                                     uint64_t new_mask, uint64_t *new_state, int n_words) {
+// Move every occupied slot (key + state record) of the old table into the new, larger one.
+__global__ void __launch_bounds__(256) k_agg_rehash(const uint64_t *old_keys, const uint64_t *old_tbl, uint64_t old_slots, uint64_t *new_keys,
+                                                     uint64_t *new_tbl, uint64_t new_mask, int stride) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t old_total = old_slots + 2, new_total = new_mask + 1 + 2;
-  for (; i < old_total; i += stride) {
+  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t old_total = old_slots + 2;
+  for (; i < old_total; i += gstride) {
     uint64_t dst;
     if (i >= old_slots) dst = (new_mask + 1) + (i - old_slots);  // side slots keep their role
     else {
       const uint64_t key = old_keys[i];
       if (key == AGG_EMPTY) continue;
-      uint64_t idx = tqd::mix64(key) & new_mask;
+      uint64_t idx = (tqd::mix64(key) & new_mask) & ~3ull;  // same bucket-aligned probe order as the update kernel
       for (;;) {
         const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&new_keys[idx]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
         if (prev == AGG_EMPTY) break;
@@ -355,7 +398,7 @@ __global__ void __launch_bounds__(256) k_agg_rehash(const uint64_t *old_keys, ui
       }
       dst = idx;
     }
-    for (int w = 0; w < n_words; w++) new_state[(uint64_t)w * new_total + dst] = old_state[(uint64_t)w * old_total + i];
+    for (int w = 0; w < stride; w++) new_tbl[dst * stride + w] = old_tbl[i * stride + w];
   }
 }
 
@@ -385,13 +428,15 @@ struct tq_agg {
   int arg_type[AGG_MAXF];
   int out_type[AGG_MAXF];
   int key_passthrough[AGG_MAXF];
-  int word_base[AGG_MAXF];  // first state word of function i
-  int n_words = 0;
+  int w0[AGG_MAXF], w1[AGG_MAXF], w2[AGG_MAXF];  // state word offsets inside the slot record
+  int stride = 1;           // words per slot (power of two)
+  bool not_null[AGG_MAXC] = {};    // input column declared NOT NULL (TQ_TYPE_NOT_NULL)
+  bool flag_on[AGG_MAXF] = {};  // SUM/MAX/MIN: a batch with a NULL bitmap (or partial rows) has been seen for this argument
   int64_t est_groups = 0;
   int64_t batch_rows = 1 << 22;
 
   // table
-  DevBuf keys, state, meta;   // meta: [0..1] side_used u32, [2] n_deferred u32, [3] err u32, u64@16 n_used, u64@24 out_n
+  DevBuf keys, table, meta;   // meta: [0..1] side_used u32, [2] n_deferred u32, [3] err u32, u64@16 n_used, u64@24 out_n
   uint64_t n_slots = 0;
   DevBuf deferred;
   PinBuf meta_host;
@@ -432,15 +477,15 @@ static int32_t agg_alloc_table(tq_agg *a, uint64_t n_slots) {
   cudaStream_t s = rt().compute;
   a->n_slots = n_slots;
   const uint64_t total = n_slots + 2;
-  TQ_TRY(a->keys.reserve(total * 8));
-  TQ_TRY(a->state.reserve((size_t)(a->n_words ? a->n_words : 1) * total * 8));
+  TQ_TRY(a->keys.reserve((n_slots + 4) * 8));
+  TQ_TRY(a->table.reserve(total * a->stride * 8));
   k_fill_u64<<<agg_grid((int64_t)n_slots), 256, 0, s>>>(a->keys.as<uint64_t>(), n_slots, AGG_EMPTY);
   count_launch();
-  TQ_CUDA(cudaMemsetAsync(a->state.p, 0, (size_t)(a->n_words ? a->n_words : 1) * total * 8, s));
+  TQ_CUDA(cudaMemsetAsync(a->table.p, 0, total * a->stride * 8, s));
   return check_launch("k_fill_u64");
 }
 
-static void fill_funcs(tq_agg *a, AggFuncDev *f, uint64_t *state_base, uint64_t total, bool merge) {
+static void fill_funcs(tq_agg *a, AggFuncDev *f, bool merge) {
   int pcol = a->n_group_by;  // merge-mode input layout: key cols, then partial-state columns in function order
   for (int i = 0; i < a->n_funcs; i++) {
     AggFuncDev &d = f[i];
@@ -453,23 +498,24 @@ static void fill_funcs(tq_agg *a, AggFuncDev *f, uint64_t *state_base, uint64_t 
       d.arg_col = pcol++;
       if (d.func == TQ_AGG_AVG && !d.key_passthrough) d.arg_col2 = pcol++;
     }
-    const int wb = a->word_base[i];
-    d.w0 = state_base + (uint64_t)wb * total;
-    d.w1 = state_base + (uint64_t)(wb + 1) * total;
-    d.w2 = state_base + (uint64_t)(wb + 2) * total;
+    d.w0 = a->w0[i];
+    d.w1 = a->w1[i];
+    d.w2 = a->w2[i];
+    d.use_flag = (a->flag_on[i] && a->w1[i] >= 0) ? 1 : 0;
+    d.arg_not_null = (!merge && a->funcs[i].arg_col >= 0 && a->not_null[a->funcs[i].arg_col]) ? 1 : 0;
   }
 }
 
 static int32_t agg_grow(tq_agg *a, uint64_t new_slots) {
   cudaStream_t s = rt().compute;
-  DevBuf old_keys = std::move(a->keys), old_state = std::move(a->state);
+  DevBuf old_keys = std::move(a->keys), old_tbl = std::move(a->table);
   const uint64_t old_slots = a->n_slots;
   TQ_TRY(agg_alloc_table(a, new_slots));
-  k_agg_rehash<<<agg_grid((int64_t)old_slots + 2), 256, 0, s>>>(old_keys.as<uint64_t>(), old_slots, old_state.as<uint64_t>(), a->keys.as<uint64_t>(),
-                                                                new_slots - 1, a->state.as<uint64_t>(), a->n_words);
+  k_agg_rehash<<<agg_grid((int64_t)old_slots + 2), 256, 0, s>>>(old_keys.as<uint64_t>(), old_tbl.as<uint64_t>(), old_slots, a->keys.as<uint64_t>(),
+                                                                a->table.as<uint64_t>(), new_slots - 1, a->stride);
   count_launch();
   TQ_TRY(check_launch("k_agg_rehash"));
-  TQ_CUDA(cudaStreamSynchronize(s));  // old buffers are freed when this scope ends
+  TQ_CUDA(cudaStreamSynchronize(s));  // the old buffers are released when this scope ends
   return TQ_OK;
 }
 
@@ -481,11 +527,22 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
   if (a->n_slots == 0) {
     uint64_t want = 1 << 16;
     const uint64_t hint = a->est_groups > 0 ? (uint64_t)a->est_groups : 0;
-    while (want < hint * 4) want <<= 1;
+    while (want < hint * 2) want <<= 1;  // load factor <= 0.5 at the planner's NDV estimate
     TQ_TRY(agg_alloc_table(a, want));
     TQ_CUDA(cudaMemsetAsync(a->meta.p, 0, 64, s));
   }
   if (n > 0xFFFFFFF0ll) { set_error("aggregate batch too large"); return TQ_ERR_INVALID_ARG; }
+  for (int i = 0; i < a->n_funcs; i++) {
+    const int fn = a->funcs[i].func;
+    if (a->flag_on[i] || a->w1[i] < 0 || a->key_passthrough[i] || !(fn == TQ_AGG_SUM || fn == TQ_AGG_MAX || fn == TQ_AGG_MIN)) continue;
+    const int ac = a->funcs[i].arg_col;
+    const bool nullable_now = merge || (ac >= 0 && cols[ac].bm != nullptr);
+    if (!nullable_now) continue;
+    k_agg_set_flags<<<agg_grid((int64_t)a->n_slots + 2), 256, 0, s>>>(a->keys.as<uint64_t>(), a->table.as<uint64_t>(), a->stride, a->n_slots, a->meta.as<uint32_t>(), a->w1[i]);
+    count_launch();
+    TQ_TRY(check_launch("k_agg_set_flags"));
+    a->flag_on[i] = true;
+  }
   TQ_TRY(a->deferred.reserve((size_t)n * 4));
   uint32_t *meta32 = a->meta.as<uint32_t>();
   unsigned long long *meta64 = reinterpret_cast<unsigned long long *>(a->meta.as<uint8_t>() + 16);
@@ -500,9 +557,10 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
     p.key_col = a->n_group_by ? (merge ? 0 : a->key_col) : -1;
     p.merge = merge ? 1 : 0;
     p.n_funcs = a->n_funcs;
-    const uint64_t total = a->n_slots + 2;
-    fill_funcs(a, p.f, a->state.as<uint64_t>(), total, merge);
-    p.slot_keys = a->keys.as<uint64_t>();
+    fill_funcs(a, p.f, merge);
+    p.keys = a->keys.as<uint64_t>();
+    p.tbl = a->table.as<uint64_t>();
+    p.stride = a->stride;
     p.mask = a->n_slots - 1;
     p.n_slots = a->n_slots;
     p.side_used = meta32;
@@ -631,7 +689,7 @@ static int32_t agg_finalize(tq_agg *a, bool export_partial, AggResult &res, int 
   const int64_t groups = (int64_t)used + (m32[0] ? 1 : 0) + (m32[1] ? 1 : 0);
   CollectParams p{};
   p.n_funcs = a->n_funcs;
-  fill_funcs(a, p.f, a->state.as<uint64_t>(), a->n_slots + 2, false);
+  fill_funcs(a, p.f, false);
   for (int c = 0; c < n_out_cols; c++) {
     TQ_TRY(res.data[c].reserve((size_t)(groups ? groups : 1) * 8));
     TQ_TRY(res.bm[c].reserve(bitmap_alloc_bytes(groups)));
@@ -645,7 +703,9 @@ static int32_t agg_finalize(tq_agg *a, bool export_partial, AggResult &res, int 
   } else {
     for (int c = 0; c < n_out_cols; c++) { p.out[c].data = res.data[c].as<uint64_t>(); p.out[c].bm = res.bm[c].as<uint32_t>(); }
   }
-  p.slot_keys = a->keys.as<uint64_t>();
+  p.keys = a->keys.as<uint64_t>();
+  p.tbl = a->table.as<uint64_t>();
+  p.stride = a->stride;
   p.n_slots = a->n_slots;
   p.side_used = a->meta.as<uint32_t>();
   p.out_n = reinterpret_cast<unsigned long long *>(a->meta.as<uint8_t>() + 24);
@@ -684,7 +744,7 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
   if (d->n_group_by < 0) return TQ_ERR_INVALID_ARG;
   if (d->n_group_by > 1) { set_error("GROUP BY over %d items: only zero or one GROUP BY column is implemented", d->n_group_by); return TQ_ERR_UNSUPPORTED_TYPE; }
   for (int c = 0; c < d->n_input_cols; c++) {
-    const int t = d->input_types[c];
+    const int t = d->input_types[c] & 0xFF;
     if (t != TQ_TYPE_INT64 && t != TQ_TYPE_UINT64 && t != TQ_TYPE_FLOAT64) { set_error("unsupport column type for encode %d", t); return TQ_ERR_UNSUPPORTED_TYPE; }
   }
   tq_agg *a = new (std::nothrow) tq_agg();
@@ -693,7 +753,7 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
   a->n_group_by = d->n_group_by;
   a->n_funcs = d->n_funcs;
   a->est_groups = d->est_groups;
-  for (int c = 0; c < a->n_cols; c++) a->types[c] = d->input_types[c];
+  for (int c = 0; c < a->n_cols; c++) { a->types[c] = d->input_types[c] & 0xFF; a->not_null[c] = (d->input_types[c] & TQ_TYPE_NOT_NULL) != 0; }
   if (a->n_group_by) {
     a->key_col = d->group_by_cols[0];
     if (a->key_col < 0 || a->key_col >= a->n_cols) { delete a; return TQ_ERR_INVALID_ARG; }
@@ -712,10 +772,19 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
     a->out_type[i] = fn == TQ_AGG_COUNT ? TQ_TYPE_INT64 : (ac >= 0 ? a->types[ac] : TQ_TYPE_INT64);
     if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->out_type[i] == TQ_TYPE_UINT64) a->out_type[i] = TQ_TYPE_INT64;
     a->key_passthrough[i] = (fn == TQ_AGG_FIRSTROW && a->n_group_by && ac == a->key_col) ? 1 : 0;
-    a->word_base[i] = words;
-    words += a->key_passthrough[i] ? 0 : 3;  // three words reserved per function keeps w0/w1/w2 addressing uniform
+    a->w0[i] = a->w1[i] = a->w2[i] = 0;
+    if (!a->key_passthrough[i]) {
+      const bool int_sum = (fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->arg_type[i] != TQ_TYPE_FLOAT64;
+      const bool arg_nn = ac >= 0 && a->not_null[ac];
+      const bool flag_only = (fn == TQ_AGG_SUM || fn == TQ_AGG_MAX || fn == TQ_AGG_MIN);
+      a->w0[i] = words++;
+      a->w1[i] = -1;
+      if (fn != TQ_AGG_COUNT && !(flag_only && arg_nn)) a->w1[i] = words++;
+      if (int_sum) a->w2[i] = words++;
+    }
   }
-  a->n_words = words;
+  a->stride = 1;
+  while (a->stride < words) a->stride <<= 1;
   int32_t st = a->meta.reserve(64);
   if (st == TQ_OK) st = a->meta_host.reserve(64);
   cudaError_t e = cudaEventCreate(&a->ev_a);

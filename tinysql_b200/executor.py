@@ -129,8 +129,9 @@ class HashJoinExec:
 class HashAggExec:
     """executor/aggregate.go:54-155.  funcs: list of (AGG_*, arg_col or -1); one GROUP BY column or none."""
 
-    def __init__(self, child, group_by, funcs, est_groups=0, max_chunk_size=MAX_CHUNK_SIZE):
+    def __init__(self, child, group_by, funcs, est_groups=0, max_chunk_size=MAX_CHUNK_SIZE, not_null_cols=()):
         self.child, self.group_by, self.funcs = child, list(group_by), list(funcs)
+        self.not_null_cols = set(not_null_cols)  # input columns whose FieldType carries mysql.NotNullFlag
         self.est_groups, self.max_chunk_size = est_groups, max_chunk_size
         self.handle = None
         self.prepared = False
@@ -139,7 +140,8 @@ class HashAggExec:
     def Open(self):
         self.child.Open()
         lib = L.load()
-        it, gb = _i32arr(self.child.types), _i32arr(self.group_by)
+        it = _i32arr([t | (0x100 if i in self.not_null_cols else 0) for i, t in enumerate(self.child.types)])  # TQ_TYPE_NOT_NULL
+        gb = _i32arr(self.group_by)
         fa = (L.TQAggFunc * max(len(self.funcs), 1))(*[L.TQAggFunc(f, a) for f, a in self.funcs])
         d = L.TQAggDesc(len(self.child.types), it, len(self.group_by), gb, len(self.funcs), fa, self.est_groups)
         h = C.c_void_p()
