@@ -348,7 +348,7 @@ def main():
     if args.workload == "join":
         out = run_join_bench(args, rank, world, local_rank, dist)
     else:
-        from tinysql_b200 import bench_extra
+        import bench_extra
         out = bench_extra.run(args, rank, world, local_rank)
     if rank == 0 and out is not None:
         print(json.dumps(out))

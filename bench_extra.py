@@ -1,4 +1,5 @@
-"""bench.py --workload {expr,agg}: the secondary BASELINE configs on one B200.
+"""bench.py --workload {expr,agg}: the secondary BASELINE configs on one B200 (benchmark infrastructure, like bench.py:
+the cpu_baseline legs load the oracle; the product package tinysql_b200/ never does).
   expr = C2: vectorized LT + Plus (builtin_compare_vec / builtin_arithmetic_vec) over 1e8 int64 rows
   agg  = C4: 1e8-row GROUP BY int64 key with SUM(float64), COUNT(*), 1e6 groups
 Same JSON contract as the join line (value = device-resident, e2e = pinned host buffers through the C-ABI)."""
@@ -9,8 +10,8 @@ import time
 
 import numpy as np
 
-from . import _lib as L
-from .chunk import FLOAT64, INT64, Column, DeviceColumn
+from tinysql_b200 import _lib as L
+from tinysql_b200.chunk import FLOAT64, INT64, Column, DeviceColumn
 
 
 def _pinned(lib, n_items, dtype, src=None):
@@ -187,7 +188,7 @@ def run(args, rank, world, local_rank):
     if rank != 0:
         return None
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
     from bench import ClockSampler, measured_peak
     lib = L.load()
     L.check(lib.tq_init(local_rank))

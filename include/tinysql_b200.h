@@ -284,6 +284,17 @@ int32_t tq_partition_device(int32_t n_cols, const tq_column *cols, const int32_t
                             int32_t key_col, int64_t n, int32_t n_parts, tq_column *out_cols,
                             int64_t *part_offsets);
 
+/* Fused scatter + exchange over NVLink peer memory (one process per GPU, buffers shared through CUDA IPC):
+ *   tq_partition_count_device  rows of `key` per destination partition (hash >> 40) % n_parts, n_parts <= 8; rows whose
+ *                              key is NULL are not counted / exchanged (they cannot match in an inner join);
+ *   tq_partition_push_device   scatters every row straight into partition q's destination columns
+ *                              dest_data[q * n_cols + c] (device pointers, local or PEER-mapped) starting at row
+ *                              dest_row_offsets[q]; the offsets come from an all-gather of the counts.
+ * Columns must be NOT NULL (no bitmaps), n_cols <= 4. */
+int32_t tq_partition_count_device(const tq_column *key, int64_t n, int32_t n_parts, int64_t *counts);
+int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts,
+                                 void *const *dest_data, const int64_t *dest_row_offsets);
+
 #ifdef __cplusplus
 }
 #endif

@@ -621,17 +621,26 @@ struct ScatterParams {
   uint32_t *part_cursor;  // scatter cursors, initialised to the first row of each partition
   const uint32_t *part_lim;  // optimistic slabs: one past the last row a partition may hold (nullptr: exact offsets, cannot overflow)
   unsigned long long *overflow;  // set when a slab was too small
+  // multi-GPU push scatter: partition = (hash >> 40) % n_parts_mod and partition q's rows go to out_bin[q][c] — the
+  // receive buffer of rank q, a PEER pointer mapped through CUDA IPC: the stores travel over NVLink
+  int n_parts_mod;
+  uint64_t *out_bin[8][4];
 };
+__device__ __forceinline__ int scatter_bins(const ScatterParams &p) { return (p.n_parts_mod ? p.n_parts_mod : (1 << p.pbits)) + 1; }
+__device__ __forceinline__ uint32_t scatter_pid(const ScatterParams &p, uint64_t key) {
+  const uint64_t h = tqd::mix64(key);
+  return p.n_parts_mod ? (uint32_t)((h >> 40) % (uint64_t)p.n_parts_mod) : (uint32_t)part_of_hash(h, p.pbits);
+}
 
 __device__ __forceinline__ uint32_t probe_pid(const ScatterParams &p, int64_t r, uint64_t key) {
   const bool sel = p.selected ? (p.selected[r] != 0) : true;
-  if (sel && key_valid(key, tqd::bm_not_null(p.in[p.key_col].bm, r), p.key_mode)) return (uint32_t)part_of_hash(tqd::mix64(key), p.pbits);
-  return p.is_outer ? (1u << p.pbits) : PID_DROP;  // inner join: a row that cannot match produces nothing (joiner.go:405)
+  if (sel && key_valid(key, tqd::bm_not_null(p.in[p.key_col].bm, r), p.key_mode)) return scatter_pid(p, key);
+  return p.is_outer ? (uint32_t)(scatter_bins(p) - 1) : PID_DROP;  // inner join: a row that cannot match produces nothing (joiner.go:405)
 }
 
 __global__ void __launch_bounds__(SCAT_THREADS) k_probe_part_hist(const ScatterParams p) {
   extern __shared__ uint32_t s_hist[];
-  const int n_bins = (1 << p.pbits) + 1;
+  const int n_bins = scatter_bins(p);
   for (int i = threadIdx.x; i < n_bins; i += SCAT_THREADS) s_hist[i] = 0;
   __syncthreads();
   const uint64_t *keys = p.in[p.key_col].data;
@@ -652,7 +661,7 @@ __global__ void __launch_bounds__(SCAT_THREADS) k_probe_part_hist(const ScatterP
 // global (coalesced, consecutive lanes store consecutive destinations: whole 32-byte sectors).
 __global__ void __launch_bounds__(SCAT_THREADS, 4) k_probe_scatter(const ScatterParams p) {
   extern __shared__ __align__(16) unsigned char s_scat[];
-  const int n_bins = (1 << p.pbits) + 1;
+  const int n_bins = scatter_bins(p);
   uint64_t *s_stage = reinterpret_cast<uint64_t *>(s_scat);                       // [SCAT_TILE] one column of the tile, sorted
   uint32_t *s_bins = reinterpret_cast<uint32_t *>(s_scat + SCAT_TILE * 8);        // [n_bins] tile counts, then local exclusive offsets
   uint32_t *s_gdelta = s_bins + n_bins;                                           // [n_bins] (claimed global run start) - (local offset)
@@ -750,7 +759,7 @@ static constexpr int SCATF_ROWS = SCAT_TILE / SCATF_THREADS;
 template <int NP>
 __global__ void __launch_bounds__(SCATF_THREADS, (NP <= 2 ? 2 : 1)) k_probe_scatter_fast(const ScatterParams p) {
   extern __shared__ __align__(16) unsigned char s_scat[];
-  const int n_bins = (1 << p.pbits) + 1;
+  const int n_bins = scatter_bins(p);
   uint64_t *s_stage = reinterpret_cast<uint64_t *>(s_scat);
   uint32_t *s_bins = reinterpret_cast<uint32_t *>(s_scat + SCAT_TILE * 8);
   uint32_t *s_gdelta = s_bins + n_bins;
@@ -786,8 +795,8 @@ __global__ void __launch_bounds__(SCATF_THREADS, (NP <= 2 ? 2 : 1)) k_probe_scat
       pid[k] = PID_DROP;
       if (r < p.n) {
         const bool sel = p.selected ? (p.selected[r] != 0) : true;
-        if (sel && key_valid(key, true, p.key_mode)) pid[k] = (uint32_t)part_of_hash(tqd::mix64(key), p.pbits);
-        else if (p.is_outer) pid[k] = 1u << p.pbits;
+        if (sel && key_valid(key, true, p.key_mode)) pid[k] = scatter_pid(p, key);
+        else if (p.is_outer) pid[k] = (uint32_t)(n_bins - 1);
       }
       spos[k] = (pid[k] != PID_DROP) ? atomicAdd(&s_bins[pid[k]], 1u) : 0u;
     }
@@ -843,7 +852,9 @@ __global__ void __launch_bounds__(SCATF_THREADS, (NP <= 2 ? 2 : 1)) k_probe_scat
       for (uint32_t i = tid; i < total; i += SCATF_THREADS) {
         const uint32_t bin = s_spid[i];
         if (i >= s_imax[bin]) continue;
-        tqd::st_stream_u64(out[c] + s_gdelta[bin] + i, s_stage[i]);
+        uint64_t *dst = p.n_parts_mod ? p.out_bin[bin & 7][c] : out[c];
+        const uint32_t d32 = s_gdelta[bin] + i;  // 32-bit wrap-around arithmetic: (run start - local offset) + sorted position
+        tqd::st_stream_u64(dst + d32, s_stage[i]);
       }
       __syncthreads();
     }
@@ -2235,6 +2246,98 @@ int32_t tq_join_stats(tq_join *j, int64_t *s) {
   s[5] = j->last_probe_ns;
   s[6] = j->build_ns;
   s[7] = j->probe_launches;
+  return TQ_OK;
+}
+
+// ---- multi-GPU shard boundary: count, then push-scatter straight into the peers' receive buffers ---------------
+static int32_t part_common_check(int32_t n_parts, int64_t n) {
+  if (n_parts < 1 || n_parts > 8 || n < 0 || n > 0xFFFFFFF0ll) { set_error("push partitioning supports 1..8 partitions and < 2^32 rows"); return TQ_ERR_INVALID_ARG; }
+  return TQ_OK;
+}
+
+int32_t tq_partition_count_device(const tq_column *key, int64_t n, int32_t n_parts, int64_t *counts) {
+  TQ_TRY(ensure_init());
+  if (!key || !counts) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(part_common_check(n_parts, n));
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  cudaStream_t s = r.compute;
+  static DevBuf cnt;
+  static PinBuf h_cnt;
+  TQ_TRY(cnt.reserve(64));
+  TQ_TRY(h_cnt.reserve(64));
+  TQ_CUDA(cudaMemsetAsync(cnt.p, 0, 64, s));
+  if (n > 0) {
+    ScatterParams sp{};
+    sp.n_cols = 1;
+    sp.in[0].data = (const uint64_t *)key->data;
+    sp.in[0].bm = (const uint32_t *)key->null_bitmap;
+    sp.key_col = 0;
+    sp.key_mode = KEYMODE_RAW;
+    sp.is_outer = 0;  // rows with a NULL key cannot match in an inner join: they are not exchanged
+    sp.n = n;
+    sp.part_cnt = cnt.as<uint32_t>();
+    sp.n_parts_mod = n_parts;
+    k_probe_part_hist<<<r.sm_count * 4, SCAT_THREADS, (n_parts + 1) * 4, s>>>(sp);
+    count_launch();
+    TQ_TRY(check_launch("k_probe_part_hist"));
+  }
+  TQ_CUDA(cudaMemcpyAsync(h_cnt.p, cnt.p, 64, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < n_parts; i++) counts[i] = h_cnt.as<uint32_t>()[i];
+  return TQ_OK;
+}
+
+int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts, void *const *dest_data,
+                                 const int64_t *dest_row_offsets) {
+  TQ_TRY(ensure_init());
+  if (!cols || !dest_data || !dest_row_offsets || n_cols < 1 || n_cols > 4 || key_col < 0 || key_col >= n_cols) {
+    set_error("tq_partition_push_device: 1..4 columns");
+    return TQ_ERR_INVALID_ARG;
+  }
+  TQ_TRY(part_common_check(n_parts, n));
+  for (int c = 0; c < n_cols; c++)
+    if (cols[c].null_bitmap) { set_error("tq_partition_push_device: columns with NULL bitmaps are not supported (use tq_partition_device)"); return TQ_ERR_UNSUPPORTED_TYPE; }
+  if (n == 0) return TQ_OK;
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  cudaStream_t s = r.compute;
+  static DevBuf cursor;
+  TQ_TRY(cursor.reserve(64));
+  uint32_t h_cur[16] = {0};
+  ScatterParams sp{};
+  sp.n_cols = n_cols;
+  sp.key_col = key_col;
+  sp.key_mode = KEYMODE_RAW;
+  sp.is_outer = 0;
+  sp.n = n;
+  sp.n_parts_mod = n_parts;
+  for (int c = 0; c < n_cols; c++) { sp.in[c].data = (const uint64_t *)cols[c].data; sp.in[c].bm = nullptr; sp.out[c].data = nullptr; sp.out[c].bm = nullptr; }
+  for (int q = 0; q < n_parts; q++) {
+    if (dest_row_offsets[q] < 0 || dest_row_offsets[q] > 0xFFFFFFF0ll) { set_error("destination offset out of range"); return TQ_ERR_INVALID_ARG; }
+    h_cur[q] = (uint32_t)dest_row_offsets[q];
+    for (int c = 0; c < n_cols; c++) sp.out_bin[q][c] = (uint64_t *)dest_data[q * n_cols + c];
+  }
+  TQ_CUDA(cudaMemcpyAsync(cursor.p, h_cur, 64, cudaMemcpyHostToDevice, s));
+  sp.part_cursor = cursor.as<uint32_t>();
+  sp.part_lim = nullptr;
+  static DevBuf ovf;
+  TQ_TRY(ovf.reserve(8));
+  sp.overflow = ovf.as<unsigned long long>();
+  ScatterKernel k = scatter_fast_kernel(n_cols);
+  static bool attr[5] = {};
+  if (!attr[n_cols]) {
+    TQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 12)));
+    attr[n_cols] = true;
+  }
+  const int n_bins = n_parts + 1;
+  const int smem = SCAT_TILE * 8 + n_bins * 12 + SCAT_TILE * 2 + SCAT_TILE;
+  const int64_t tiles = (n + SCAT_TILE - 1) / SCAT_TILE;
+  const int64_t cap = (int64_t)r.sm_count * (n_cols <= 2 ? 2 : 1);
+  k<<<(int)(tiles < cap ? tiles : cap), SCATF_THREADS, smem, s>>>(sp);
+  count_launch();
+  TQ_TRY(check_launch("k_probe_scatter_fast(push)"));
+  TQ_CUDA(cudaStreamSynchronize(s));
   return TQ_OK;
 }
 

@@ -9,6 +9,7 @@ rank  (mix64(key) >> 40) % world  — a pure function of its key, so equal keys 
 The exchange logic is backend-agnostic (gloo on CPU in tests/test_dist_gloo.py with injected partition / join functions).
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -31,33 +32,159 @@ def dest_rank_np(keys, world):
     return ((mix64_np(keys) >> np.uint64(40)) % np.uint64(world)).astype(np.int64)
 
 
-def exchange(cols, send_offsets, world, rank, group=None):
+def exchange_counts(send_offsets_list, world, rank, device, group=None):
+    """One all-gather for any number of partitioned tables: returns, per table, the rows every source rank sends HERE."""
+    mine = torch.tensor([[offs[p + 1] - offs[p] for p in range(world)] for offs in send_offsets_list], dtype=torch.int64, device=device)
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine, group=group)            # world x tables x world counts (tiny)
+    m = torch.stack(allc).cpu().numpy()                 # ONE device->host sync
+    return [[int(m[src, t, rank]) for src in range(world)] for t in range(len(send_offsets_list))]
+
+
+def exchange(cols, send_offsets, world, rank, group=None, recv_counts=None, async_op=False):
     """cols: list of 1-D tensors, all partitioned the same way: rows [send_offsets[p], send_offsets[p+1]) go to rank p.
-    Returns (list of received columns, recv_counts).  One count all-gather + one grouped send/recv for all columns."""
+    Returns (list of received columns, recv_counts[, work handles]).  NCCL: one all_to_all_single per column (NCCL
+    send/recv groups inside); other backends (gloo has no all-to-all): one grouped batch of isend/irecv."""
     dev = cols[0].device
-    send_counts = torch.tensor([send_offsets[p + 1] - send_offsets[p] for p in range(world)], dtype=torch.int64, device=dev)
-    all_counts = [torch.empty(world, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(all_counts, send_counts, group=group)  # G x G count matrix (tiny)
-    recv_counts = [int(all_counts[src][rank]) for src in range(world)]
-    recv_off = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
-    total = int(recv_off[-1])
+    if recv_counts is None:
+        recv_counts = exchange_counts([send_offsets], world, rank, dev, group)[0]
+    send_counts = [int(send_offsets[p + 1] - send_offsets[p]) for p in range(world)]
+    total = int(sum(recv_counts))
     out = [torch.empty(total, dtype=c.dtype, device=dev) for c in cols]
-    ops = []
-    for ci, c in enumerate(cols):
-        for peer in range(world):
-            s_lo, s_hi = int(send_offsets[peer]), int(send_offsets[peer + 1])
-            r_lo, r_hi = int(recv_off[peer]), int(recv_off[peer + 1])
-            if peer == rank:
-                out[ci][r_lo:r_hi].copy_(c[s_lo:s_hi])
-                continue
-            if s_hi > s_lo:
-                ops.append(dist.P2POp(dist.isend, c[s_lo:s_hi], peer, group=group))
-            if r_hi > r_lo:
-                ops.append(dist.P2POp(dist.irecv, out[ci][r_lo:r_hi], peer, group=group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):  # one ncclGroupStart/End around every send and recv
-            req.wait()
+    works = []
+    if dist.get_backend(group) == "nccl":
+        for ci, c in enumerate(cols):
+            src = c[int(send_offsets[0]): int(send_offsets[world])]
+            w = dist.all_to_all_single(out[ci], src, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group, async_op=async_op)
+            if async_op:
+                works.append(w)
+    else:
+        recv_off = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
+        ops = []
+        for ci, c in enumerate(cols):
+            for peer in range(world):
+                s_lo, s_hi = int(send_offsets[peer]), int(send_offsets[peer + 1])
+                r_lo, r_hi = int(recv_off[peer]), int(recv_off[peer + 1])
+                if peer == rank:
+                    out[ci][r_lo:r_hi].copy_(c[s_lo:s_hi])
+                    continue
+                if s_hi > s_lo:
+                    ops.append(dist.P2POp(dist.isend, c[s_lo:s_hi], peer, group=group))
+                if r_hi > r_lo:
+                    ops.append(dist.P2POp(dist.irecv, out[ci][r_lo:r_hi], peer, group=group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):  # one group around every send and recv
+                req.wait()
+    if async_op:
+        return out, recv_counts, works
     return out, recv_counts
+
+
+class PeerExchange:
+    """All-to-all over NVSwitch PEER MEMORY instead of NCCL send/recv: every rank keeps its partitioned columns in
+    persistent "send" buffers whose CUDA IPC handles are shared once; an exchange is then one tiny offsets all-gather
+    plus, per source rank, a peer-to-peer copy (copy engines over NVLink) that PULLS the slice addressed to this rank.
+    Two barriers per exchange order the producers' scatter kernels against the consumers' pulls."""
+
+    def __init__(self, world, rank, device, n_tables_cols, capacity_rows, dtype=torch.int64):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.world, self.rank, self.dev = world, rank, device
+        # send[t][c]: partition output of table t, column c (written by tq_partition_device)
+        self.send = [[torch.empty(cap, dtype=dtype, device=device) for _ in range(nc)] for nc, cap in zip(n_tables_cols, capacity_rows)]
+        handles = [[reduce_tensor(x) for x in cols] for cols in self.send]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles)
+        self.peer = []
+        for src in range(world):
+            if src == rank:
+                self.peer.append(self.send)
+            else:
+                self.peer.append([[fn(*args) for fn, args in cols] for cols in gathered[src]])
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(max(1, min(world - 1, 4)))]
+
+    def offsets_matrix(self, offsets_list):
+        """all ranks' partition offsets for every table: [src][table][world+1] (one all-gather, one D2H sync)"""
+        mine = torch.tensor(offsets_list, dtype=torch.int64, device=self.dev)
+        allo = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allo, mine)
+        return torch.stack(allo).cpu().numpy()
+
+    def pull(self, table, offs, out=None):
+        """copy, from every source rank, the rows it partitioned for THIS rank.  offs = offsets_matrix(...)[:, table, :]"""
+        world, rank = self.world, self.rank
+        counts = [int(offs[src, rank + 1] - offs[src, rank]) for src in range(world)]
+        total = sum(counts)
+        ncols = len(self.send[table])
+        if out is None:
+            out = [torch.empty(total, dtype=self.send[table][c].dtype, device=self.dev) for c in range(ncols)]
+        cur = torch.cuda.current_stream()
+        pos = 0
+        events = []
+        for i, src in enumerate([(rank + d) % world for d in range(world)]):  # start with the local slice, then ring order
+            lo, hi = int(offs[src, rank]), int(offs[src, rank + 1])
+            dst_lo = sum(counts[:src])
+            st = self.streams[i % len(self.streams)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for c in range(ncols):
+                    out[c][dst_lo:dst_lo + (hi - lo)].copy_(self.peer[src][table][c][lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            events.append(ev)
+        return out, counts, events
+
+
+class PushExchange:
+    """The fused scatter + exchange: every rank owns persistent RECEIVE buffers (CUDA IPC handles shared once); per step
+    each rank counts its rows per destination (tq_partition_count_device), one tiny all-gather turns the counts into
+    write offsets, and tq_partition_push_device scatters every row straight into the destination rank's receive buffer —
+    stores over NVLink peer memory, no separate exchange pass.  Two barriers per step order pushes against consumers."""
+
+    def __init__(self, lib, L, world, rank, device, n_tables_cols, capacity_rows, dtype=torch.int64):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.lib, self.L, self.world, self.rank, self.dev = lib, L, world, rank, device
+        self.cap = list(capacity_rows)
+        self.recv = [[torch.empty(cap, dtype=dtype, device=device) for _ in range(nc)] for nc, cap in zip(n_tables_cols, capacity_rows)]
+        handles = [[reduce_tensor(x) for x in cols] for cols in self.recv]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles)
+        self.peer = []
+        for dst in range(world):
+            self.peer.append(self.recv if dst == rank else [[fn(*args) for fn, args in cols] for cols in gathered[dst]])
+
+    def counts(self, key_cols):
+        """local rows per destination for each table: tq_partition_count_device"""
+        out = []
+        for k in key_cols:
+            n = int(k.numel())
+            c = (C.c_int64 * self.world)()
+            col = _tq_cols(self.L, [k], n)
+            self.L.check(self.lib.tq_partition_count_device(col, n, self.world, c))
+            out.append(list(c))
+        return out
+
+    def plan(self, local_counts):
+        """all-gather the count matrices; returns (write offsets [table][dst], rows arriving here [table])"""
+        mine = torch.tensor(local_counts, dtype=torch.int64, device=self.dev)      # [tables][world]
+        allc = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allc, mine)
+        m = torch.stack(allc).cpu().numpy()                                      # [src][table][dst]
+        offs = [[int(m[: self.rank, t, d].sum()) for d in range(self.world)] for t in range(m.shape[1])]
+        arriving = [int(m[:, t, self.rank].sum()) for t in range(m.shape[1])]
+        for t, a in enumerate(arriving):
+            if a > self.cap[t]:
+                raise RuntimeError(f"receive buffer of table {t} too small: {a} rows arriving, capacity {self.cap[t]} (skewed keys)")
+        return offs, arriving
+
+    def push(self, table, cols, offs):
+        n = int(cols[0].numel())
+        ncols = len(cols)
+        dest = (C.c_void_p * (self.world * ncols))()
+        for d in range(self.world):
+            for c in range(ncols):
+                dest[d * ncols + c] = self.peer[d][table][c].data_ptr()
+        o = (C.c_int64 * self.world)(*offs)
+        self.L.check(self.lib.tq_partition_push_device(ncols, _tq_cols(self.L, cols, n), 0, n, self.world, dest, o))
 
 
 def distributed_join(build_cols, probe_cols, world, rank, partition_fn, local_join_fn, group=None):
@@ -90,25 +217,36 @@ def gpu_partition_fn(lib, L):
     return fn
 
 
-def gpu_local_join(lib, L, build, probe, keep_result=False):
-    """inner join, key = column 0 of both sides, int64 columns, inputs resident in HBM.  Returns (rows, stats[, columns])."""
-    nb, npr = int(build[0].numel()), int(probe[0].numel())
+def join_begin(lib, L, build, n_probe_cols=2):
+    """create the join and build its table from device-resident build columns (key = column 0)"""
+    nb = int(build[0].numel())
     t_b = (C.c_int32 * len(build))(*([1] * len(build)))
-    t_p = (C.c_int32 * len(probe))(*([1] * len(probe)))
+    t_p = (C.c_int32 * n_probe_cols)(*([1] * n_probe_cols))
     k = (C.c_int32 * 1)(0)
-    d = L.TQJoinDesc(0, 1, len(build), t_b, len(probe), t_p, 1, k, k, 0)
+    d = L.TQJoinDesc(0, 1, len(build), t_b, n_probe_cols, t_p, 1, k, k, 0)
     h = C.c_void_p()
     L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
-    total = 0
-    result = None
     try:
         if nb:
             L.check(lib.tq_join_put_build(h, _tq_cols(L, build, nb), L.TQ_MEM_DEVICE))
         L.check(lib.tq_join_finalize_build(h))
+    except Exception:
+        lib.tq_join_destroy(h)
+        raise
+    return (h, len(build))
+
+
+def join_finish(lib, L, handle, probe, keep_result=False):
+    """probe with device-resident columns, drain, destroy.  Returns (rows, stats[, columns])."""
+    h, n_build_cols = handle
+    npr = int(probe[0].numel())
+    total = 0
+    result = None
+    try:
         if npr:
             L.check(lib.tq_join_put_probe(h, _tq_cols(L, probe, npr), None, L.TQ_MEM_DEVICE))
         L.check(lib.tq_join_probe_eof(h))
-        out = (L.TQColumn * (len(build) + len(probe)))()
+        out = (L.TQColumn * (n_build_cols + len(probe)))()
         n, eof = C.c_int64(0), C.c_int32(0)
         while True:
             L.check(lib.tq_join_next_device(h, out, C.byref(n), C.byref(eof)))
@@ -117,12 +255,17 @@ def gpu_local_join(lib, L, build, probe, keep_result=False):
             total += n.value
             if keep_result and n.value:
                 from .chunk import device_to_host
-                result = [device_to_host(1, out[c].data, None, n.value) for c in range(len(build) + len(probe))]
+                result = [device_to_host(1, out[c].data, None, n.value) for c in range(n_build_cols + len(probe))]
         st = (C.c_int64 * 8)()
         lib.tq_join_stats(h, st)
     finally:
         lib.tq_join_destroy(h)
     return (total, list(st), result) if keep_result else (total, list(st))
+
+
+def gpu_local_join(lib, L, build, probe, keep_result=False):
+    """inner join, key = column 0 of both sides, int64 columns, inputs resident in HBM."""
+    return join_finish(lib, L, join_begin(lib, L, build, len(probe)), probe, keep_result)
 
 
 def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_src):
@@ -143,20 +286,123 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
     pk = torch.from_numpy(pk_h).to(dev)
     pv = torch.arange(n_p, dtype=torch.int64, device=dev) + rank * n_p
     part = gpu_partition_fn(lib, L)
+    mode = os.environ.get("TQ_DIST_EXCHANGE", "push")
+    use_peer = mode == "peer"
+    px = None
+    pushx = None
+    if mode == "push":
+        try:
+            slack = lambda n: int(n * 1.25) + (1 << 16)   # keys are hash-spread: +25 % covers the imbalance
+            pushx = PushExchange(lib, L, world, rank, dev, [2, 2], [slack(n_b), slack(n_p)])
+        except Exception as e:
+            if rank == 0:
+                print(f"[dist] push exchange unavailable ({e}); falling back", flush=True)
+            pushx = None
+        okp = torch.tensor([1 if pushx is not None else 0], device=dev)
+        dist_mod.all_reduce(okp, op=dist_mod.ReduceOp.MIN)
+        if int(okp) == 0:
+            pushx, use_peer = None, True
+    if use_peer:
+        try:
+            px = PeerExchange(world, rank, dev, [2, 2], [n_b, n_p])
+        except Exception as e:  # no CUDA IPC in this container: NCCL all_to_all instead
+            if rank == 0:
+                print(f"[dist] peer-memory exchange unavailable ({e}); using NCCL all_to_all", flush=True)
+            px = None
+    ok = torch.tensor([1 if px is not None else 0], device=dev)
+    dist_mod.all_reduce(ok, op=dist_mod.ReduceOp.MIN)
+    if int(ok) == 0:
+        px = None
 
-    def step():
-        b_part, b_off = part([bk, bv], world)
+    phase_ms = {}
+
+    def tick(name, t0):
         torch.cuda.synchronize()
-        b_recv, _ = exchange(b_part, b_off, world, rank)
-        p_part, p_off = part([pk, pv], world)
-        torch.cuda.synchronize()
-        p_recv, _ = exchange(p_part, p_off, world, rank)
-        torch.cuda.synchronize()
-        rows, st = gpu_local_join(lib, L, b_recv, p_recv)
+        lib.tq_device_synchronize()
+        phase_ms[name] = phase_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
+    profile_phases = os.environ.get("TQ_DIST_PHASES") == "1"  # extra syncs per phase (diagnostics only; slows the step)
+
+    def part_into(cols, outs):
+        n = int(cols[0].numel())
+        offs = (C.c_int64 * (world + 1))()
+        types = (C.c_int32 * len(cols))(*([1] * len(cols)))
+        L.check(lib.tq_partition_device(len(cols), _tq_cols(L, cols, n), types, 0, n, world, _tq_cols(L, outs, n), offs))
+        return list(offs)
+
+    def step_peer():
+        t = time.perf_counter()
+        b_off = part_into([bk, bv], px.send[0])   # tq_partition_device synchronises its stream before returning
+        p_off = part_into([pk, pv], px.send[1])
+        if profile_phases:
+            t = tick("partition", t)
+        offs = px.offsets_matrix([b_off, p_off])  # also orders every rank's scatter before anyone pulls
+        b_recv, _, ev_b = px.pull(0, offs[:, 0, :])
+        p_recv, _, ev_p = px.pull(1, offs[:, 1, :])
+        for ev in ev_b:
+            ev.synchronize()
+        if profile_phases:
+            t = tick("pull_build(+probe in flight)", t)
+        h = join_begin(lib, L, b_recv)            # the probe rows are still arriving while the table is built
+        for ev in ev_p:
+            ev.synchronize()
+        if profile_phases:
+            t = tick("build+pull_probe", t)
+        rows, st = join_finish(lib, L, h, p_recv)
+        if profile_phases:
+            t = tick("local_probe", t)
+        dist_mod.barrier()                        # nobody overwrites its send buffers until every peer has pulled
         return rows, st, int(p_recv[0].numel())
+
+    def step_nccl():
+        t = time.perf_counter()
+        b_part, b_off = part([bk, bv], world)
+        p_part, p_off = part([pk, pv], world)
+        if profile_phases:
+            t = tick("partition", t)
+        torch.cuda.synchronize()
+        b_cnt, p_cnt = exchange_counts([b_off, p_off], world, rank, dev)
+        b_recv, _ = exchange(b_part, b_off, world, rank, recv_counts=b_cnt)
+        # the probe rows travel while the hash table is built from the build rows that already arrived
+        p_recv, _, works = exchange(p_part, p_off, world, rank, recv_counts=p_cnt, async_op=True)
+        torch.cuda.current_stream().synchronize()
+        if profile_phases:
+            t = tick("exchange_build", t)
+        h = join_begin(lib, L, b_recv)
+        for w in works:
+            w.wait()
+        torch.cuda.synchronize()
+        if profile_phases:
+            t = tick("build+exchange_probe", t)
+        rows, st = join_finish(lib, L, h, p_recv)
+        if profile_phases:
+            t = tick("local_probe", t)
+        return rows, st, int(p_recv[0].numel())
+
+    def step_push():
+        t = time.perf_counter()
+        cnt = pushx.counts([bk, pk])
+        offs, arriving = pushx.plan(cnt)            # all-gather: also means every rank finished consuming the last step
+        if profile_phases:
+            t = tick("count+plan", t)
+        pushx.push(0, [bk, bv], offs[0])
+        pushx.push(1, [pk, pv], offs[1])            # rows cross NVLink as the scatter kernel stores them
+        dist_mod.barrier()                          # every rank's pushes have landed
+        if profile_phases:
+            t = tick("push_scatter", t)
+        b_recv = [x[: arriving[0]] for x in pushx.recv[0]]
+        p_recv = [x[: arriving[1]] for x in pushx.recv[1]]
+        rows, st = gpu_local_join(lib, L, b_recv, p_recv)
+        if profile_phases:
+            t = tick("local_join", t)
+        return rows, st, arriving[1]
+
+    step = step_push if pushx is not None else (step_peer if px is not None else step_nccl)
 
     for _ in range(args.warmup):
         step()
+    phase_ms.clear()
     from bench import ClockSampler
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -195,11 +441,13 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
         "data": "synthetic",
         "config": {"workload": f"C5-style: int64 equi-join radix-partitioned over {world} GPUs; per GPU build={n_b} probe={n_p} (global {N_b} x {n_p * world}), "
                                "uniform keys, 100% match; partition -> grouped NCCL send/recv -> local join",
-                   "build_rows_per_gpu": n_b, "probe_rows_per_gpu": n_p, "parallelism": f"key-hash partitions over {world} ranks",
+                   "build_rows_per_gpu": n_b, "probe_rows_per_gpu": n_p, "parallelism": f"key-hash partitions over {world} ranks", "exchange": ("push scatter into peer receive buffers (CUDA IPC, stores over NVLink)" if pushx is not None else
+                                "peer-memory pull (CUDA IPC + NVLink copies)" if px is not None else "NCCL all_to_all_single"),
                    "l2": "inputs and outputs exceed the 126 MB L2; no flush needed"},
         "roofline": {"bound": "hbm", "kernel": "local probe pipeline (rank 0)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_row": 64, "kernel_ms": probe_s * 1e3},
         "e2e": {"value": value, "unit": "joined rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "multi-GPU line: shards are generated in HBM; the host-buffer e2e figure is reported on the 1-GPU line"},
         "gpu_launches": int(launches2 - launches1), "clocks": clocks, "wall_ms_per_step_max": float(tmax[2]) / args.steps,
+        "phase_ms_rank0": {k: v / args.steps for k, v in phase_ms.items()},
     }
