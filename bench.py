@@ -29,6 +29,21 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def measured_traffic():
+    """dram__bytes_read + dram__bytes_write of the probe-pipeline kernels, from the committed ncu --set full capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_join_probe_traffic.json")) as f:
+            return float(json.load(f)["probe_pipeline_total"])
+    except Exception:
+        return None
+
+
+def join_config(n_build, n_probe):
+    return {"workload": f"C3: int64 equi-join, uniform keys, build={n_build} probe={n_probe}, 100% match, output (B.k,B.v,P.k,P.v) materialised",
+            "build_rows": n_build, "probe_rows": n_probe, "l2": "inputs (1.76 GB) and output (3.2 GB) exceed the 126 MB L2; no flush needed",
+            "step": "tq_join create + build + probe + result, inputs resident in HBM"}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -281,11 +296,11 @@ def run_join_bench(args, rank, world, local_rank, dist):
         "metric": "joined rows/sec on 1e8-row int64 equi-join", "value": value, "unit": "joined rows/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
-        "config": {"workload": f"C3: int64 equi-join, uniform keys, build={n_build} probe={n_probe}, 100% match, output (B.k,B.v,P.k,P.v) materialised",
-                   "build_rows": n_build, "probe_rows": n_probe, "l2": "inputs (1.76 GB) and output (3.2 GB) exceed the 126 MB L2; no flush needed",
-                   "step": "tq_join create + build + probe + result, inputs resident in HBM"},
-        "roofline": {"bound": "hbm", "kernel": "k_probe", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_row": 64, "kernel_ms": probe_s * 1e3,
+        "config": join_config(n_build, n_probe),
+        "roofline": {"bound": "hbm", "kernel": "probe pipeline = k_probe_scatter_fast<2> + k_probe_part_fast<2,2> (timed together with CUDA events on the library stream)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": measured_traffic() if (n_build, n_probe) == (10_000_000, 100_000_000) else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_row": 64, "algorithmic_bytes": 64 * n_probe, "kernel_ms": probe_s * 1e3,
                      "build_ms": statistics.mean(build_ns) * 1e-6},
         "e2e": {"value": n_probe / e2e_s, "unit": "joined rows/s", "h2d_bytes_per_step": 16 * (n_build + n_probe), "d2h_bytes_per_step": 32 * n_probe,
                 "ms_per_step": e2e_s * 1e3},
@@ -314,7 +329,7 @@ def run_reference(args, rank):
     return {"impl": "reference", "metric": "joined rows/sec on 1e8-row int64 equi-join", "value": v, "unit": "joined rows/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_probe / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": {"workload": f"C3: int64 equi-join, uniform keys, build={n_build} probe={n_probe}", "build_rows": n_build, "probe_rows": n_probe},
+            "config": join_config(n_build, n_probe),
             "cpu_baseline": res, "e2e": {"value": v, "unit": "joined rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 

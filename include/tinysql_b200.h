@@ -291,6 +291,9 @@ int32_t tq_partition_device(int32_t n_cols, const tq_column *cols, const int32_t
  *                              dest_data[q * n_cols + c] (device pointers, local or PEER-mapped) starting at row
  *                              dest_row_offsets[q]; the offsets come from an all-gather of the counts.
  * Columns must be NOT NULL (no bitmaps), n_cols <= 4. */
+/* Kernel-level load/store access from this process's device to `peer_device` (cudaDeviceEnablePeerAccess): required
+ * before tq_partition_push_device is handed PEER pointers. */
+int32_t tq_enable_peer_access(int32_t peer_device);
 int32_t tq_partition_count_device(const tq_column *key, int64_t n, int32_t n_parts, int64_t *counts);
 int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts,
                                  void *const *dest_data, const int64_t *dest_row_offsets);

@@ -1160,6 +1160,18 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const Prob
       matched_acc += wcnt;
       if (wcnt) woff = atomicAdd(&s_total[par], wcnt);
     }
+    // the other probe columns of the matched rows are requested NOW: their latency hides behind the two barriers and
+    // the global atomic below (only word 1 of the matched entry stays live: word 0 is the key itself)
+    uint64_t pay[NP][R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const bool hit = (bal[k] >> lane) & 1u;
+#pragma unroll
+      for (int c = 0; c < NP; c++) {
+        pay[c][k] = 0;
+        if (c != kc && hit) pay[c][k] = tqd::ld_stream_u64(pin[c] + wbase + k * 32);
+      }
+    }
     __syncthreads();
     if (tid == 0) {
       const unsigned tot = s_total[par];
@@ -1173,9 +1185,8 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const Prob
       const unsigned long long q = q0 + __popc(bal[k] & lt_mask);
       q0 += __popc(bal[k]);
       if (((bal[k] >> lane) & 1u) && q < p.capacity) {
-        const int64_t row = wbase + k * 32;
 #pragma unroll
-        for (int c = 0; c < NP; c++) tqd::st_stream_u64(pout[c] + q, (c == kc) ? key[k] : tqd::ld_stream_u64(pin[c] + row));
+        for (int c = 0; c < NP; c++) tqd::st_stream_u64(pout[c] + q, (c == kc) ? key[k] : pay[c][k]);
 #pragma unroll
         for (int c = 0; c < NB; c++) {
           uint64_t v;

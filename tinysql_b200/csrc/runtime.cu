@@ -434,6 +434,19 @@ int32_t tq_timer_stop(float *elapsed_ms) {
 }
 int64_t tq_kernel_launch_count(void) { return rt().launches.load(); }
 
+int32_t tq_enable_peer_access(int32_t peer_device) {
+  TQ_TRY(ensure_init());
+  Runtime &r = rt();
+  if (peer_device == r.device) return TQ_OK;
+  int can = 0;
+  TQ_CUDA(cudaDeviceCanAccessPeer(&can, r.device, peer_device));
+  if (!can) { set_error("device %d cannot access device %d as a peer", r.device, peer_device); return TQ_ERR_NO_DEVICE; }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return TQ_OK; }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+  return TQ_OK;
+}
+
 int32_t tq_flush_l2(void) {
   TQ_TRY(ensure_init());
   Runtime &r = rt();

@@ -151,6 +151,10 @@ class PushExchange:
         self.peer = []
         for dst in range(world):
             self.peer.append(self.recv if dst == rank else [[fn(*args) for fn, args in cols] for cols in gathered[dst]])
+        # the scatter kernel STORES into the peers' buffers: kernel-level peer access must be on (IPC mapping alone only serves copies)
+        for dst in range(world):
+            if dst != rank:
+                L.check(lib.tq_enable_peer_access(self.peer[dst][0][0].device.index))
 
     def counts(self, key_cols):
         """local rows per destination for each table: tq_partition_count_device"""
