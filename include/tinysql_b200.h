@@ -294,9 +294,19 @@ int32_t tq_partition_device(int32_t n_cols, const tq_column *cols, const int32_t
 /* Kernel-level load/store access from this process's device to `peer_device` (cudaDeviceEnablePeerAccess): required
  * before tq_partition_push_device is handed PEER pointers. */
 int32_t tq_enable_peer_access(int32_t peer_device);
+/* CUDA IPC (cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle) for buffers from tq_device_alloc: a rank exports its
+ * receive buffer as a 64-byte handle; peers open it under THEIR device and push rows into it over NVLink. */
+int32_t tq_ipc_get_handle(void *dev_ptr, void *handle64);
+int32_t tq_ipc_open_handle(const void *handle64, void **dev_ptr);
+int32_t tq_ipc_close_handle(void *dev_ptr);
 int32_t tq_partition_count_device(const tq_column *key, int64_t n, int32_t n_parts, int64_t *counts);
 int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts,
                                  void *const *dest_data, const int64_t *dest_row_offsets);
+/* Same, enqueued on the library's second stream and not waited for: lets the probe rows cross NVLink while the hash
+ * table is being built on the compute stream; tq_partition_push_wait blocks until the push has completed. */
+int32_t tq_partition_push_device_async(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts,
+                                       void *const *dest_data, const int64_t *dest_row_offsets);
+int32_t tq_partition_push_wait(void);
 
 #ifdef __cplusplus
 }

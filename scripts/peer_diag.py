@@ -7,16 +7,17 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl")
 from tinysql_b200 import _lib as L
 lib = L.load(); L.check(lib.tq_init(local))
-from torch.multiprocessing.reductions import reduce_tensor
 dev = torch.device("cuda", local)
-buf = torch.zeros(1 << 20, dtype=torch.int64, device=dev)
+own = C.c_void_p(); L.check(lib.tq_device_alloc(8 << 20, C.byref(own))); L.check(lib.tq_memset_device(own, 0, 8 << 20))
+hb = (C.c_ubyte * 64)(); L.check(lib.tq_ipc_get_handle(own, hb))
 g = [None] * world
-dist.all_gather_object(g, reduce_tensor(buf))
+dist.all_gather_object(g, bytes(hb))
 peer = (rank + 1) % world
-fn, args = g[peer]
-pt = fn(*args)
-print(rank, "peer tensor device", pt.device, "ptr", hex(pt.data_ptr()), "can_access", torch.cuda.can_device_access_peer(local, pt.device.index), flush=True)
-print(rank, "enable_peer ->", lib.tq_enable_peer_access(pt.device.index), L.last_error(), flush=True)
+pp = C.c_void_p(); L.check(lib.tq_ipc_open_handle((C.c_ubyte * 64).from_buffer_copy(g[peer]), C.byref(pp)))
+class PT:
+    def data_ptr(self): return pp.value
+pt = PT()
+print(rank, "peer ptr", hex(pp.value), flush=True)
 def step(name, f):
     try:
         f(); lib.tq_device_synchronize(); torch.cuda.synchronize()
@@ -25,7 +26,6 @@ def step(name, f):
         print(rank, name, "FAILED", str(e)[:200], flush=True); raise
 step("memset peer via lib", lambda: L.check(lib.tq_memset_device(C.c_void_p(pt.data_ptr()), 1, 64)))
 loc = torch.arange(4096, dtype=torch.int64, device=dev)
-step("torch copy local->peer", lambda: pt[:4096].copy_(loc))
 # push with everything local first, then with the peer as partition 1
 k = torch.arange(10000, dtype=torch.int64, device=dev); v = k * 2
 def push(dst_ptrs):
@@ -40,5 +40,5 @@ step("push all-local", lambda: push([l0.data_ptr(), l1.data_ptr(), l2.data_ptr()
 dist.barrier()
 step("push part1->peer", lambda: push([l0.data_ptr(), l1.data_ptr(), pt.data_ptr(), pt.data_ptr() + 8 * 20000]))
 dist.barrier()
-print(rank, "received sum", int(buf[:40000].sum()), flush=True)
+hostbuf = np.zeros(40000, np.int64); L.check(lib.tq_memcpy_d2h(hostbuf.ctypes.data, own, 320000)); print(rank, "received sum", int(hostbuf.sum()), flush=True)
 dist.destroy_process_group()

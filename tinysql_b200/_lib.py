@@ -73,8 +73,11 @@ SYMBOLS = {
     "tq_agg_merge_partial": (_I32, [_P, _COL, _I32]),
     "tq_partition_device": (_I32, [_I32, _COL, C.POINTER(_I32), _I32, _I64, _I32, _COL, C.POINTER(_I64)]),
     "tq_enable_peer_access": (_I32, [_I32]),
+    "tq_ipc_get_handle": (_I32, [_P, _P]), "tq_ipc_open_handle": (_I32, [_P, C.POINTER(_P)]), "tq_ipc_close_handle": (_I32, [_P]),
     "tq_partition_count_device": (_I32, [_COL, _I64, _I32, C.POINTER(_I64)]),
     "tq_partition_push_device": (_I32, [_I32, _COL, _I32, _I64, _I32, C.POINTER(_P), C.POINTER(_I64)]),
+    "tq_partition_push_device_async": (_I32, [_I32, _COL, _I32, _I64, _I32, C.POINTER(_P), C.POINTER(_I64)]),
+    "tq_partition_push_wait": (_I32, []),
 }
 
 # status codes (include/tinysql_b200.h)

@@ -31,6 +31,7 @@ static constexpr int PART_MAX_BITS = 12;
 static constexpr uint64_t PART_MAX_SMEM_BYTES = 128 << 10;  // a partition table image that still fits in shared memory
 static int64_t g_tiles_per_cta = 8;
 static int64_t g_part_target_rows = 150000;              // build rows per partition: a partition table ~ 4-8 MB, a few live ones fit in L2
+static int64_t g_max_load_pct = 50;                      // TQ_JOIN_MAX_LOAD_PCT: partition-table load-factor bound (pair probing keeps chains short)
 static bool g_exact_scatter = false;                     // TQ_JOIN_EXACT_SCATTER=1: always run the probe-side histogram pass
 static bool g_no_fast_kernel = false;                    // TQ_JOIN_NO_FAST=1: use the generic kernels (tests)
 static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
@@ -1476,7 +1477,7 @@ static int32_t join_build(tq_join *j) {
     TQ_CUDA(cudaMemcpyAsync(&max_cnt, counters + 4, 4, cudaMemcpyDeviceToHost, s));
     TQ_CUDA(cudaStreamSynchronize(s));
     cap = 64;
-    while (cap < (uint64_t)max_cnt * 2) cap <<= 1;        // load factor <= 0.5 in the fullest partition (short probe sequences)
+    while (cap * (uint64_t)g_max_load_pct < (uint64_t)max_cnt * 100) cap <<= 1;  // load factor <= g_max_load_pct % in the fullest partition
     if (cap * P > (uint64_t)n * 12 + 4096) { pbits = 0; cap = 0; }  // heavily skewed hash partitions: one table instead
     else n_slots = P * cap;
   }
@@ -1987,6 +1988,7 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   { const char *e = getenv("TQ_JOIN_FORCE_GLOBAL"); g_force_global_table = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_NO_FAST"); g_no_fast_kernel = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_EXACT_SCATTER"); g_exact_scatter = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_MAX_LOAD_PCT"); if (e && atoll(e) >= 10 && atoll(e) <= 90) g_max_load_pct = atoll(e); }
   { const char *e = getenv("TQ_JOIN_TILES_PER_CTA"); if (e && atoll(e) > 0) g_tiles_per_cta = atoll(e); }
   { const char *e = getenv("TQ_JOIN_PART_ROWS"); if (e && atoll(e) > 0) g_part_target_rows = atoll(e); }
   tq_join *j = new (std::nothrow) tq_join();
@@ -2299,8 +2301,8 @@ int32_t tq_partition_count_device(const tq_column *key, int64_t n, int32_t n_par
   return TQ_OK;
 }
 
-int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts, void *const *dest_data,
-                                 const int64_t *dest_row_offsets) {
+static int32_t partition_push(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts, void *const *dest_data,
+                              const int64_t *dest_row_offsets, bool async) {
   TQ_TRY(ensure_init());
   if (!cols || !dest_data || !dest_row_offsets || n_cols < 1 || n_cols > 4 || key_col < 0 || key_col >= n_cols) {
     set_error("tq_partition_push_device: 1..4 columns");
@@ -2312,10 +2314,15 @@ int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t 
   if (n == 0) return TQ_OK;
   Runtime &r = rt();
   std::lock_guard<std::recursive_mutex> lk(r.mu);
-  cudaStream_t s = r.compute;
-  static DevBuf cursor;
+  // async pushes run on the library's second stream so the probe rows can cross NVLink while the hash table is built
+  cudaStream_t s = async ? r.h2d : r.compute;
+  static DevBuf cursors[2];
+  DevBuf &cursor = cursors[async ? 1 : 0];
   TQ_TRY(cursor.reserve(64));
-  uint32_t h_cur[16] = {0};
+  static PinBuf h_cur_pin[2];
+  TQ_TRY(h_cur_pin[async ? 1 : 0].reserve(64));
+  uint32_t *h_cur = h_cur_pin[async ? 1 : 0].as<uint32_t>();
+  memset(h_cur, 0, 64);
   ScatterParams sp{};
   sp.n_cols = n_cols;
   sp.key_col = key_col;
@@ -2344,11 +2351,30 @@ int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t 
   const int n_bins = n_parts + 1;
   const int smem = SCAT_TILE * 8 + n_bins * 12 + SCAT_TILE * 2 + SCAT_TILE;
   const int64_t tiles = (n + SCAT_TILE - 1) / SCAT_TILE;
-  const int64_t cap = (int64_t)r.sm_count * (n_cols <= 2 ? 2 : 1);
+  int64_t cap = (int64_t)r.sm_count * (n_cols <= 2 ? 2 : 1);
+  if (async) {  // an overlapped push is NVLink-bound: a few dozen CTAs saturate the links and leave the SMs to the local probe
+    static int64_t push_ctas = -1;
+    if (push_ctas < 0) { const char *e = getenv("TQ_PUSH_CTAS"); push_ctas = (e && atoll(e) > 0) ? atoll(e) : 0; }
+    if (push_ctas > 0 && push_ctas < cap) cap = push_ctas;
+  }
   k<<<(int)(tiles < cap ? tiles : cap), SCATF_THREADS, smem, s>>>(sp);
   count_launch();
   TQ_TRY(check_launch("k_probe_scatter_fast(push)"));
-  TQ_CUDA(cudaStreamSynchronize(s));
+  if (!async) TQ_CUDA(cudaStreamSynchronize(s));
+  return TQ_OK;
+}
+
+int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts, void *const *dest_data,
+                                 const int64_t *dest_row_offsets) {
+  return partition_push(n_cols, cols, key_col, n, n_parts, dest_data, dest_row_offsets, false);
+}
+int32_t tq_partition_push_device_async(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts, void *const *dest_data,
+                                       const int64_t *dest_row_offsets) {
+  return partition_push(n_cols, cols, key_col, n, n_parts, dest_data, dest_row_offsets, true);
+}
+int32_t tq_partition_push_wait(void) {
+  TQ_TRY(ensure_init());
+  TQ_CUDA(cudaStreamSynchronize(rt().h2d));
   return TQ_OK;
 }
 

@@ -447,6 +447,33 @@ int32_t tq_enable_peer_access(int32_t peer_device) {
   return TQ_OK;
 }
 
+// CUDA IPC for the peer-memory exchange: buffers allocated by tq_device_alloc are exported as 64-byte handles and
+// opened by the other ranks' processes while THEIR device is current (lazy peer access), so their kernels can store
+// into this buffer over NVLink.
+int32_t tq_ipc_get_handle(void *dev_ptr, void *handle64) {
+  TQ_TRY(ensure_init());
+  if (!dev_ptr || !handle64) return TQ_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  TQ_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle64, &h, 64);
+  return TQ_OK;
+}
+int32_t tq_ipc_open_handle(const void *handle64, void **dev_ptr) {
+  TQ_TRY(ensure_init());
+  if (!handle64 || !dev_ptr) return TQ_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  TQ_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return TQ_OK;
+}
+int32_t tq_ipc_close_handle(void *dev_ptr) {
+  TQ_TRY(ensure_init());
+  if (!dev_ptr) return TQ_OK;
+  TQ_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return TQ_OK;
+}
+
 int32_t tq_flush_l2(void) {
   TQ_TRY(ensure_init());
   Runtime &r = rt();

@@ -134,27 +134,75 @@ class PeerExchange:
         return out, counts, events
 
 
-class PushExchange:
-    """The fused scatter + exchange: every rank owns persistent RECEIVE buffers (CUDA IPC handles shared once); per step
-    each rank counts its rows per destination (tq_partition_count_device), one tiny all-gather turns the counts into
-    write offsets, and tq_partition_push_device scatters every row straight into the destination rank's receive buffer —
-    stores over NVLink peer memory, no separate exchange pass.  Two barriers per step order pushes against consumers."""
+class RawCol:
+    """a device column that is just (pointer, rows): quacks like the torch tensors the helpers below take"""
 
-    def __init__(self, lib, L, world, rank, device, n_tables_cols, capacity_rows, dtype=torch.int64):
-        from torch.multiprocessing.reductions import reduce_tensor
+    def __init__(self, ptr, n):
+        self.ptr, self.n = ptr, n
+
+    def data_ptr(self):
+        return self.ptr
+
+    def numel(self):
+        return self.n
+
+    def __getitem__(self, sl):
+        assert sl.start in (None, 0) and sl.step in (None, 1)
+        return RawCol(self.ptr, min(self.n, sl.stop))
+
+
+class PushExchange:
+    """The fused scatter + exchange: every rank owns persistent RECEIVE buffers (tq_device_alloc) exported once as CUDA IPC
+    handles; every peer opens them under its own device (lazy peer access, like NCCL's P2P transport).  Per step each
+    rank counts its rows per destination (tq_partition_count_device), one tiny all-gather turns the counts into write
+    offsets, and tq_partition_push_device scatters every row straight into the destination rank's receive buffer —
+    stores over NVLink peer memory, no separate exchange pass.  Barriers order pushes against consumers."""
+
+    def __init__(self, lib, L, world, rank, device, n_tables_cols, capacity_rows):
         self.lib, self.L, self.world, self.rank, self.dev = lib, L, world, rank, device
         self.cap = list(capacity_rows)
-        self.recv = [[torch.empty(cap, dtype=dtype, device=device) for _ in range(nc)] for nc, cap in zip(n_tables_cols, capacity_rows)]
-        handles = [[reduce_tensor(x) for x in cols] for cols in self.recv]
+        self.own, handles = [], []
+        for nc, cap in zip(n_tables_cols, capacity_rows):
+            ptrs, hs = [], []
+            for _ in range(nc):
+                p = C.c_void_p()
+                L.check(lib.tq_device_alloc(cap * 8, C.byref(p)))
+                h = (C.c_ubyte * 64)()
+                L.check(lib.tq_ipc_get_handle(p, h))
+                ptrs.append(p.value)
+                hs.append(bytes(h))
+            self.own.append(ptrs)
+            handles.append(hs)
         gathered = [None] * world
         dist.all_gather_object(gathered, handles)
-        self.peer = []
+        self.peer_ptr = []   # [dst][table][col] -> address valid in THIS process
+        self._opened = []
         for dst in range(world):
-            self.peer.append(self.recv if dst == rank else [[fn(*args) for fn, args in cols] for cols in gathered[dst]])
-        # the scatter kernel STORES into the peers' buffers: kernel-level peer access must be on (IPC mapping alone only serves copies)
-        for dst in range(world):
-            if dst != rank:
-                L.check(lib.tq_enable_peer_access(self.peer[dst][0][0].device.index))
+            if dst == rank:
+                self.peer_ptr.append(self.own)
+                continue
+            tabs = []
+            for hs in gathered[dst]:
+                cols = []
+                for hb in hs:
+                    p = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(hb)
+                    L.check(lib.tq_ipc_open_handle(buf, C.byref(p)))
+                    cols.append(p.value)
+                    self._opened.append(p.value)
+                tabs.append(cols)
+            self.peer_ptr.append(tabs)
+        self.recv = [[RawCol(p, cap) for p in ptrs] for ptrs, cap in zip(self.own, self.cap)]
+
+    def close(self):
+        for p in self._opened:
+            self.lib.tq_ipc_close_handle(C.c_void_p(p))
+        self._opened = []
+        dist.barrier()  # nobody frees a buffer a peer still has mapped
+        for ptrs in self.own:
+            for p in ptrs:
+                self.lib.tq_device_free(C.c_void_p(p))
+        self.own = []
 
     def counts(self, key_cols):
         """local rows per destination for each table: tq_partition_count_device"""
@@ -180,15 +228,19 @@ class PushExchange:
                 raise RuntimeError(f"receive buffer of table {t} too small: {a} rows arriving, capacity {self.cap[t]} (skewed keys)")
         return offs, arriving
 
-    def push(self, table, cols, offs):
+    def push(self, table, cols, offs, async_op=False):
         n = int(cols[0].numel())
         ncols = len(cols)
         dest = (C.c_void_p * (self.world * ncols))()
         for d in range(self.world):
             for c in range(ncols):
-                dest[d * ncols + c] = self.peer[d][table][c].data_ptr()
+                dest[d * ncols + c] = self.peer_ptr[d][table][c]
         o = (C.c_int64 * self.world)(*offs)
-        self.L.check(self.lib.tq_partition_push_device(ncols, _tq_cols(self.L, cols, n), 0, n, self.world, dest, o))
+        fn = self.lib.tq_partition_push_device_async if async_op else self.lib.tq_partition_push_device
+        self.L.check(fn(ncols, _tq_cols(self.L, cols, n), 0, n, self.world, dest, o))
+
+    def wait(self):
+        self.L.check(self.lib.tq_partition_push_wait())
 
 
 def distributed_join(build_cols, probe_cols, world, rank, partition_fn, local_join_fn, group=None):
@@ -384,23 +436,52 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
             t = tick("local_probe", t)
         return rows, st, int(p_recv[0].numel())
 
+    n_chunks = max(1, int(os.environ.get("TQ_DIST_CHUNKS", "1")))
+    bounds = [n_p * i // n_chunks for i in range(n_chunks + 1)]
+    pk_c = [pk[bounds[i]:bounds[i + 1]] for i in range(n_chunks)]
+    pv_c = [pv[bounds[i]:bounds[i + 1]] for i in range(n_chunks)]
+
     def step_push():
+        """count -> one all-gather -> push build -> [push probe chunk i+1 over NVLink || probe chunk i locally]"""
         t = time.perf_counter()
-        cnt = pushx.counts([bk, pk])
-        offs, arriving = pushx.plan(cnt)            # all-gather: also means every rank finished consuming the last step
+        cnt = pushx.counts([bk] + pk_c)                      # rows per destination: build, then every probe chunk
+        mine = torch.tensor(cnt, dtype=torch.int64, device=dev)
+        allc = [torch.empty_like(mine) for _ in range(world)]
+        dist_mod.all_gather(allc, mine)                      # also: every rank has finished consuming the previous step
+        m = torch.stack(allc).cpu().numpy()                  # [src][table][dst]; table 0 = build, 1.. = probe chunks
+        arr_b = int(m[:, 0, rank].sum())
+        arr_c = [int(m[:, 1 + i, rank].sum()) for i in range(n_chunks)]
+        if arr_b > pushx.cap[0] or sum(arr_c) > pushx.cap[1]:
+            raise RuntimeError("receive buffer too small (skewed keys)")
+        # write offsets: chunk i of the probe side lands behind chunks < i in the destination's receive buffer
+        off_b = [int(m[:rank, 0, d].sum()) for d in range(world)]
+        base = [[int(m[:, 1:1 + i, d].sum()) for d in range(world)] for i in range(n_chunks)]
+        off_c = [[base[i][d] + int(m[:rank, 1 + i, d].sum()) for d in range(world)] for i in range(n_chunks)]
         if profile_phases:
             t = tick("count+plan", t)
-        pushx.push(0, [bk, bv], offs[0])
-        pushx.push(1, [pk, pv], offs[1])            # rows cross NVLink as the scatter kernel stores them
-        dist_mod.barrier()                          # every rank's pushes have landed
+        pushx.push(0, [bk, bv], off_b)                       # rows cross NVLink as the scatter kernel stores them
+        dist_mod.barrier()                                   # every rank's build rows have landed
+        pushx.push(1, [pk_c[0], pv_c[0]], off_c[0], async_op=True)   # first probe chunk travels while the table is built
+        h = join_begin(lib, L, [x[:arr_b] for x in pushx.recv[0]])
         if profile_phases:
-            t = tick("push_scatter", t)
-        b_recv = [x[: arriving[0]] for x in pushx.recv[0]]
-        p_recv = [x[: arriving[1]] for x in pushx.recv[1]]
-        rows, st = gpu_local_join(lib, L, b_recv, p_recv)
+            t = tick("push_build+build", t)
+        hh, nbc = h
+        my_base = 0
+        for i in range(n_chunks):
+            pushx.wait()
+            dist_mod.barrier()                               # chunk i has landed everywhere
+            if i + 1 < n_chunks:
+                pushx.push(1, [pk_c[i + 1], pv_c[i + 1]], off_c[i + 1], async_op=True)
+            if arr_c[i]:
+                cols = [RawCol(x.ptr + my_base * 8, arr_c[i]) for x in pushx.recv[1]]
+                L.check(lib.tq_join_put_probe(hh, _tq_cols(L, cols, arr_c[i]), None, L.TQ_MEM_DEVICE))   # asynchronous: kernels queued
+            my_base += arr_c[i]
         if profile_phases:
-            t = tick("local_join", t)
-        return rows, st, arriving[1]
+            t = tick("push_probe||local_probe", t)
+        rows, st = join_finish(lib, L, h, [RawCol(0, 0), RawCol(0, 0)])
+        if profile_phases:
+            t = tick("drain", t)
+        return rows, st, sum(arr_c)
 
     step = step_push if pushx is not None else (step_peer if px is not None else step_nccl)
 
