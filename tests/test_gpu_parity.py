@@ -493,3 +493,91 @@ def test_partition_count_and_push_local(lib):
         allv = np.sort(np.concatenate(seen)) if seen else np.zeros(0, np.int64)
         assert np.array_equal(allv, np.arange(n))
         dk.free(); dv.free()
+
+
+# ------------------------------------------------------------------ partial -> final aggregation (the multi-GPU agg shape)
+def test_agg_partial_export_and_final_merge(lib):
+    """two Partial1 handles over disjoint halves -> tq_agg_export_partial -> one Final handle via tq_agg_merge_partial
+    == the oracle over all rows (AggFuncDesc.Split, descriptor.go:57-92; MergePartialResult semantics)"""
+    from tinysql_b200.chunk import DeviceColumn, device_to_host, tq_array
+    rng = np.random.default_rng(44)
+    n = 120000
+    k = gen_col(rng, INT64, n, 0.03, 0, 3000)
+    x = gen_col(rng, FLOAT64, n, 0.1)
+    x.values[:] = np.floor(np.abs(x.values)) / 4          # dyadic: float sums exact in any order
+    v = gen_col(rng, INT64, n, 0.1, -500, 500)
+    types = [INT64, FLOAT64, INT64]
+    funcs = [(AGG_FIRSTROW, 0), (AGG_COUNT, -1), (AGG_COUNT, 2), (AGG_SUM, 1), (AGG_AVG, 1), (AGG_SUM, 2), (AGG_AVG, 2), (AGG_MAX, 2), (AGG_MIN, 1)]
+
+    def make():
+        it, gb = (C.c_int32 * 3)(*types), (C.c_int32 * 1)(0)
+        fa = (L.TQAggFunc * len(funcs))(*[L.TQAggFunc(f, a) for f, a in funcs])
+        d = L.TQAggDesc(3, it, 1, gb, len(funcs), fa, 3000)
+        h = C.c_void_p()
+        L.check(lib.tq_agg_create(C.byref(d), C.byref(h)))
+        return h, (it, gb, fa)
+    final, keep_f = make()
+    width = C.c_int32(0)
+    L.check(lib.tq_agg_partial_width(final, C.byref(width)))
+    assert width.value == 1 + len(funcs) + 2               # key + one column per function, AVG twice (count, sum)
+    for lo, hi in ((0, n // 2), (n // 2, n)):
+        part, keep_p = make()
+        cols = [c.slice(lo, hi) for c in (k, x, v)]
+        L.check(lib.tq_agg_put(part, tq_array(cols), L.TQ_MEM_HOST))
+        L.check(lib.tq_agg_eof(part))
+        out = (L.TQColumn * width.value)()
+        rows = C.c_int64(0)
+        L.check(lib.tq_agg_export_partial(part, out, C.byref(rows)))   # device-resident partial rows
+        assert rows.value > 0
+        L.check(lib.tq_agg_merge_partial(final, out, L.TQ_MEM_DEVICE))
+        L.check(lib.tq_agg_destroy(part))
+    L.check(lib.tq_agg_eof(final))
+    out_types = []
+    for i in range(len(funcs)):
+        t = C.c_int32(0)
+        L.check(lib.tq_agg_output_type(final, i, C.byref(t)))
+        out_types.append(t.value)
+    res = [Column.empty(t, 4096) for t in out_types]
+    got_cols = [[] for _ in funcs]
+    got_nn = [[] for _ in funcs]
+    while True:
+        arr = tq_array(res, 4096)
+        nr, eof = C.c_int64(0), C.c_int32(0)
+        L.check(lib.tq_agg_next(final, 4096, arr, C.byref(nr), C.byref(eof)))
+        if nr.value == 0:
+            break
+        for i, c in enumerate(res):
+            got_cols[i].append(c.values[: nr.value].copy())
+            got_nn[i].append(c.not_null()[: nr.value].copy())
+    L.check(lib.tq_agg_destroy(final))
+    got = Chunk([Column(t, np.concatenate(a), np.concatenate(b)) for t, a, b in zip(out_types, got_cols, got_nn)])
+    rc, want = O.hash_agg(types, [k, x, v], [0], funcs, 2)
+    assert rc == 0 and got.num_rows() == want.num_rows()
+    g, w = _sorted_by_key(got, 0), _sorted_by_key(want, 0)
+    for a, b in zip(g, w):
+        assert_col_equal(a, b)
+
+
+def test_vec_builtins_device_memory_mode(lib):
+    """TQ_MEM_DEVICE: operands and results stay in HBM (the path a fused Selection/Projection feeding the operators takes)"""
+    from tinysql_b200.chunk import DeviceColumn
+    rng = np.random.default_rng(2)
+    for n in (1, 64, 100003):
+        a, b = gen_col(rng, INT64, n, 0.2), gen_col(rng, INT64, n, 0.2)
+        da, db = DeviceColumn.from_host(a), DeviceColumn.from_host(b)
+        out1, out2 = DeviceColumn(INT64, n), DeviceColumn(INT64, n)
+        ta, tb, t1, t2 = da.tq(), db.tq(), out1.tq(), out2.tq()
+        L.check(lib.tq_vec_compare_int(E.GE, n, C.byref(ta), 0, C.byref(tb), 0, C.byref(t1), L.TQ_MEM_DEVICE))
+        assert_col_equal(out1.to_host(), O.vec_compare_int(E.GE, a, b)[1])
+        L.check(lib.tq_vec_lt_plus_int(n, C.byref(ta), C.byref(tb), C.byref(t1), C.byref(t2), L.TQ_MEM_DEVICE))
+        assert_col_equal(out1.to_host(), O.vec_compare_int(E.LT, a, b)[1])
+        assert_col_equal(out2.to_host(), O.vec_arith_int(E.PLUS, a, b)[1])
+        sel = np.zeros(n, dtype=np.uint8)
+        dsel = C.c_void_p()
+        L.check(lib.tq_device_alloc(n, C.byref(dsel)))
+        L.check(lib.tq_vec_filter_int(n, C.byref(ta), dsel, L.TQ_MEM_DEVICE))
+        L.check(lib.tq_memcpy_d2h(sel.ctypes.data, dsel, n))
+        assert np.array_equal(sel, O.vec_filter_int(a))
+        lib.tq_device_free(dsel)
+        for d in (da, db, out1, out2):
+            d.free()
