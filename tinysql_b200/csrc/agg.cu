@@ -13,6 +13,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "dict.cuh"
 
 namespace tq {
 
@@ -422,8 +423,12 @@ struct AggResult {
 
 struct tq_agg {
   int n_cols = 0, n_group_by = 0, n_funcs = 0;
+  int n_funcs_all = 0;      // n_funcs + one hidden FIRSTROW per GROUP BY column when there are several (their values leave with export_partial)
   int types[AGG_MAXC];
-  int key_col = -1;
+  int key_col = -1;         // the key column of the update kernel: the GROUP BY column, or the hidden encoded column (index n_cols)
+  int gb_cols[MK_MAX_KEYS];
+  MultiKeyEncoder mk;       // several GROUP BY columns: exact fold of the key tuple into one 64-bit word (dict.cuh)
+  DevBuf mk_comb;
   tq_agg_func funcs[AGG_MAXF];
   int arg_type[AGG_MAXF];
   int out_type[AGG_MAXF];
@@ -464,15 +469,6 @@ static int agg_grid(int64_t n) {
   return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
-static int words_of(int func, int arg_type) {
-  switch (func) {
-    case TQ_AGG_COUNT: return 1;
-    case TQ_AGG_SUM: case TQ_AGG_AVG: return arg_type == TQ_TYPE_FLOAT64 ? 2 : 3;
-    case TQ_AGG_MAX: case TQ_AGG_MIN: return 2;
-    default: return 2;
-  }
-}
-
 static int32_t agg_alloc_table(tq_agg *a, uint64_t n_slots) {
   cudaStream_t s = rt().compute;
   a->n_slots = n_slots;
@@ -487,14 +483,15 @@ static int32_t agg_alloc_table(tq_agg *a, uint64_t n_slots) {
 
 static void fill_funcs(tq_agg *a, AggFuncDev *f, bool merge) {
   int pcol = a->n_group_by;  // merge-mode input layout: key cols, then partial-state columns in function order
-  for (int i = 0; i < a->n_funcs; i++) {
+  for (int i = 0; i < a->n_funcs_all; i++) {
     AggFuncDev &d = f[i];
     d.func = a->funcs[i].func;
     d.arg_type = a->arg_type[i];
     d.key_passthrough = a->key_passthrough[i];
     d.arg_col = a->funcs[i].arg_col;
     d.arg_col2 = -1;
-    if (merge) {
+    if (merge && i >= a->n_funcs) d.arg_col = i - a->n_funcs;  // hidden FIRSTROW of GROUP BY column j reads key column j of the partial rows
+    else if (merge) {
       d.arg_col = pcol++;
       if (d.func == TQ_AGG_AVG && !d.key_passthrough) d.arg_col2 = pcol++;
     }
@@ -532,6 +529,22 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
     TQ_CUDA(cudaMemsetAsync(a->meta.p, 0, 64, s));
   }
   if (n > 0xFFFFFFF0ll) { set_error("aggregate batch too large"); return TQ_ERR_INVALID_ARG; }
+  std::vector<DCol> wide;
+  if (a->n_group_by > 1) {
+    // getGroupKey (aggregate.go:359-394) over several GROUP BY items: the key tuple is folded, exactly, into one word
+    DCol kc[MK_MAX_KEYS];
+    for (int g = 0; g < a->n_group_by; g++) kc[g] = cols[merge ? g : a->gb_cols[g]];
+    TQ_TRY(a->mk_comb.reserve((size_t)n * 8));
+    TQ_TRY(a->mk.encode(kc, nullptr, n, /*insert=*/true, /*null_is_value=*/true, a->mk_comb.as<uint64_t>(), nullptr, s));
+    wide.assign(cols, cols + n_in_cols);
+    DCol hidden;
+    hidden.data = a->mk_comb.as<uint64_t>();
+    hidden.bm = nullptr;
+    wide.push_back(hidden);
+    cols = wide.data();
+    n_in_cols++;
+  }
+  if (n_in_cols > AGG_MAXC) { set_error("aggregate input of %d columns exceeds the limit of %d", n_in_cols, AGG_MAXC); return TQ_ERR_INVALID_ARG; }
   for (int i = 0; i < a->n_funcs; i++) {
     const int fn = a->funcs[i].func;
     if (a->flag_on[i] || a->w1[i] < 0 || a->key_passthrough[i] || !(fn == TQ_AGG_SUM || fn == TQ_AGG_MAX || fn == TQ_AGG_MIN)) continue;
@@ -554,9 +567,9 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
     AggParams p{};
     p.n_cols = n_in_cols;
     for (int c = 0; c < n_in_cols; c++) p.cols[c] = cols[c];
-    p.key_col = a->n_group_by ? (merge ? 0 : a->key_col) : -1;
+    p.key_col = a->n_group_by ? (a->n_group_by > 1 ? n_in_cols - 1 : (merge ? 0 : a->key_col)) : -1;
     p.merge = merge ? 1 : 0;
-    p.n_funcs = a->n_funcs;
+    p.n_funcs = a->n_funcs_all;
     fill_funcs(a, p.f, merge);
     p.keys = a->keys.as<uint64_t>();
     p.tbl = a->table.as<uint64_t>();
@@ -695,7 +708,14 @@ static int32_t agg_finalize(tq_agg *a, bool export_partial, AggResult &res, int 
     TQ_TRY(res.bm[c].reserve(bitmap_alloc_bytes(groups)));
     TQ_CUDA(cudaMemsetAsync(res.bm[c].p, 0, bitmap_alloc_bytes(groups), s));
   }
-  if (export_partial) {
+  if (export_partial && a->n_group_by > 1) {
+    // key columns come from the hidden FIRSTROW states (last in function order), partial states follow them in the row
+    p.export_partial = 1;
+    p.n_funcs = a->n_funcs_all;
+    const int k = a->n_group_by, w_user = n_out_cols - k;
+    for (int w = 0; w < w_user; w++) { p.out_state[w].data = res.data[k + w].as<uint64_t>(); p.out_state[w].bm = res.bm[k + w].as<uint32_t>(); }
+    for (int g = 0; g < k; g++) { p.out_state[w_user + g].data = res.data[g].as<uint64_t>(); p.out_state[w_user + g].bm = res.bm[g].as<uint32_t>(); }
+  } else if (export_partial) {
     p.export_partial = 1;
     int c = 0;
     if (a->n_group_by) { p.out_key.data = res.data[c].as<uint64_t>(); p.out_key.bm = res.bm[c].as<uint32_t>(); c++; }
@@ -710,7 +730,7 @@ static int32_t agg_finalize(tq_agg *a, bool export_partial, AggResult &res, int 
   p.side_used = a->meta.as<uint32_t>();
   p.out_n = reinterpret_cast<unsigned long long *>(a->meta.as<uint8_t>() + 24);
   p.err = a->meta.as<uint32_t>() + 3;
-  p.has_group_by = a->n_group_by ? 1 : 0;
+  p.has_group_by = a->n_group_by == 1 ? 1 : 0;
   TQ_CUDA(cudaMemsetAsync(a->meta.as<uint8_t>() + 24, 0, 8, s));
   TQ_CUDA(cudaMemsetAsync(a->meta.as<uint32_t>() + 3, 0, 4, s));
   k_agg_collect<<<agg_grid((int64_t)a->n_slots + 2), 256, 0, s>>>(p);
@@ -742,7 +762,11 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
   TQ_TRY(ensure_init());
   if (d->n_input_cols < 0 || d->n_input_cols > AGG_MAXC || d->n_funcs < 0 || d->n_funcs > AGG_MAXF) { set_error("too many columns / functions"); return TQ_ERR_INVALID_ARG; }
   if (d->n_group_by < 0) return TQ_ERR_INVALID_ARG;
-  if (d->n_group_by > 1) { set_error("GROUP BY over %d items: only zero or one GROUP BY column is implemented", d->n_group_by); return TQ_ERR_UNSUPPORTED_TYPE; }
+  if (d->n_group_by > MK_MAX_KEYS) { set_error("GROUP BY over %d items: at most %d are supported", d->n_group_by, MK_MAX_KEYS); return TQ_ERR_INVALID_ARG; }
+  if (d->n_group_by > 1 && (d->n_input_cols + 1 > AGG_MAXC || d->n_funcs + d->n_group_by > AGG_MAXF)) {
+    set_error("multi-column GROUP BY needs one spare input column and %d spare function slots", d->n_group_by);
+    return TQ_ERR_INVALID_ARG;
+  }
   for (int c = 0; c < d->n_input_cols; c++) {
     const int t = d->input_types[c] & 0xFF;
     if (t != TQ_TYPE_INT64 && t != TQ_TYPE_UINT64 && t != TQ_TYPE_FLOAT64) { set_error("unsupport column type for encode %d", t); return TQ_ERR_UNSUPPORTED_TYPE; }
@@ -754,13 +778,17 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
   a->n_funcs = d->n_funcs;
   a->est_groups = d->est_groups;
   for (int c = 0; c < a->n_cols; c++) { a->types[c] = d->input_types[c] & 0xFF; a->not_null[c] = (d->input_types[c] & TQ_TYPE_NOT_NULL) != 0; }
-  if (a->n_group_by) {
-    a->key_col = d->group_by_cols[0];
-    if (a->key_col < 0 || a->key_col >= a->n_cols) { delete a; return TQ_ERR_INVALID_ARG; }
+  for (int g = 0; g < a->n_group_by; g++) {
+    a->gb_cols[g] = d->group_by_cols[g];
+    if (a->gb_cols[g] < 0 || a->gb_cols[g] >= a->n_cols) { delete a; return TQ_ERR_INVALID_ARG; }
   }
+  if (a->n_group_by == 1) a->key_col = a->gb_cols[0];
+  else if (a->n_group_by > 1) { a->key_col = a->n_cols; a->mk.k = a->n_group_by; }
+  a->n_funcs_all = a->n_funcs + (a->n_group_by > 1 ? a->n_group_by : 0);
   int words = 0;
-  for (int i = 0; i < a->n_funcs; i++) {
-    a->funcs[i] = d->funcs[i];
+  for (int i = 0; i < a->n_funcs_all; i++) {
+    if (i < a->n_funcs) a->funcs[i] = d->funcs[i];
+    else { a->funcs[i].func = TQ_AGG_FIRSTROW; a->funcs[i].arg_col = a->gb_cols[i - a->n_funcs]; }
     const int fn = a->funcs[i].func, ac = a->funcs[i].arg_col;
     if (fn < TQ_AGG_COUNT || fn > TQ_AGG_FIRSTROW || ac >= a->n_cols || ((fn == TQ_AGG_MAX || fn == TQ_AGG_MIN) && ac < 0)) {
       set_error("bad aggregate descriptor %d", i);
@@ -771,7 +799,7 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
     if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->arg_type[i] == TQ_TYPE_UINT64) a->arg_type[i] = TQ_TYPE_INT64;  // sum4Int64 reads EvalInt (func_sum.go:118)
     a->out_type[i] = fn == TQ_AGG_COUNT ? TQ_TYPE_INT64 : (ac >= 0 ? a->types[ac] : TQ_TYPE_INT64);
     if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->out_type[i] == TQ_TYPE_UINT64) a->out_type[i] = TQ_TYPE_INT64;
-    a->key_passthrough[i] = (fn == TQ_AGG_FIRSTROW && a->n_group_by && ac == a->key_col) ? 1 : 0;
+    a->key_passthrough[i] = (fn == TQ_AGG_FIRSTROW && a->n_group_by == 1 && ac == a->key_col) ? 1 : 0;
     a->w0[i] = a->w1[i] = a->w2[i] = 0;
     if (!a->key_passthrough[i]) {
       const bool int_sum = (fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->arg_type[i] != TQ_TYPE_FLOAT64;

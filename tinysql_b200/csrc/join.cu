@@ -19,6 +19,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "dict.cuh"
 
 namespace tq {
 
@@ -1358,6 +1359,15 @@ struct tq_join {
   int build_types[MAXC], probe_types[MAXC];
   int build_key = 0, probe_key = 0;
   int key_mode = KEYMODE_RAW;
+  // Several key columns (n_keys > 1): each side carries one hidden column — the key tuple folded exactly into one
+  // 64-bit word (dict.cuh) — which is the key of the single-key kernels.  n_build_cols / n_probe_cols count it;
+  // nb_user / np_user are what the caller passes and receives.
+  int nb_user = 0, np_user = 0;
+  int bkeys[MK_MAX_KEYS], pkeys[MK_MAX_KEYS];
+  bool mk_no_signbit[MK_MAX_KEYS] = {};
+  MultiKeyEncoder mk;
+  DevBuf mk_build_key, mk_build_bm, mk_probe_key[2], mk_probe_bm[2];
+  std::vector<int> out_map;               // caller's output column -> column of the result batch
   int64_t batch_rows = 1 << 22;
 
   enum State { BUILDING, PROBING, CLOSED } state = BUILDING;
@@ -1873,11 +1883,26 @@ static int32_t start_batch(tq_join *j, const std::vector<DCol> &probe, const uin
   if (n == 0) return TQ_OK;
   Runtime &r = rt();
   if (j->pending.active && j->pending.cursor_slot == slot) TQ_TRY(finalize_pending(j));
+  std::vector<DCol> encoded;
+  const std::vector<DCol> *pin = &probe;
+  if (j->n_keys > 1) {
+    // probe-side key tuples -> the hidden key column (lookup only: a value the build side never had is a miss)
+    DCol kc[MK_MAX_KEYS];
+    for (int i = 0; i < j->n_keys; i++) kc[i] = probe[j->pkeys[i]];
+    TQ_TRY(j->mk_probe_key[slot].reserve((size_t)n * 8));
+    TQ_TRY(j->mk_probe_bm[slot].reserve(bitmap_alloc_bytes(n)));
+    TQ_TRY(j->mk.encode(kc, j->mk_no_signbit, n, /*insert=*/false, /*null_is_value=*/false, j->mk_probe_key[slot].as<uint64_t>(),
+                        j->mk_probe_bm[slot].as<uint32_t>(), r.compute));
+    encoded = probe;
+    encoded[j->np_user].data = j->mk_probe_key[slot].as<uint64_t>();
+    encoded[j->np_user].bm = j->mk_probe_bm[slot].as<uint32_t>();
+    pin = &encoded;
+  }
   // a join on unique build keys produces at most one row per probe row; with duplicate keys the
   // first launch doubles as the count pass (finalize_pending re-runs with the exact size)
   const uint64_t capacity = (uint64_t)n;
   std::unique_ptr<ResultBatch> rb = get_result_batch(j);
-  TQ_TRY(launch_probe(j, probe, d_selected, n, rb.get(), capacity, slot));
+  TQ_TRY(launch_probe(j, *pin, d_selected, n, rb.get(), capacity, slot));
   cudaEvent_t ev = nullptr;
   TQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   TQ_CUDA(cudaEventRecord(ev, r.compute));
@@ -1887,7 +1912,7 @@ static int32_t start_batch(tq_join *j, const std::vector<DCol> &probe, const uin
   pb.ev_k = ev;
   pb.active = true;
   pb.rb = std::move(rb);
-  pb.probe = probe;
+  pb.probe = *pin;
   pb.d_selected = d_selected;
   pb.n = n;
   pb.want_host = want_host;
@@ -1908,7 +1933,7 @@ static int32_t process_host_piece(tq_join *j, const tq_column *cols, int64_t row
   in.cols.resize(j->n_probe_cols);
   std::vector<DCol> view(j->n_probe_cols);
   if ((row0 & 7) != 0) { set_error("internal: unaligned host piece"); return TQ_ERR_INVALID_ARG; }
-  for (int c = 0; c < j->n_probe_cols; c++) {
+  for (int c = 0; c < j->np_user; c++) {
     TQ_TRY(in.cols[c].data.reserve((size_t)rows * 8));
     TQ_CUDA(cudaMemcpyAsync(in.cols[c].data.p, cols[c].data + row0 * 8, (size_t)rows * 8, cudaMemcpyHostToDevice, r.h2d));
     view[c].data = in.cols[c].data.as<uint64_t>();
@@ -1935,8 +1960,8 @@ static int32_t process_host_piece(tq_join *j, const tq_column *cols, int64_t row
 static int32_t flush_probe_staging(tq_join *j) {
   if (j->p_host.empty() || j->p_host[0].n == 0) return TQ_OK;
   const int64_t rows = j->p_host[0].n;
-  std::vector<tq_column> cols(j->n_probe_cols);
-  for (int c = 0; c < j->n_probe_cols; c++) {
+  std::vector<tq_column> cols(j->np_user);
+  for (int c = 0; c < j->np_user; c++) {
     cols[c].length = rows;
     cols[c].data = j->p_host[c].data.as<uint8_t>();
     cols[c].null_bitmap = j->p_host[c].has_bm ? j->p_host[c].bm.as<uint8_t>() : nullptr;
@@ -1972,16 +1997,16 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
     set_error("join sides must have 1..%d columns", MAXC);
     return TQ_ERR_INVALID_ARG;
   }
-  if (d->n_keys != 1) {
-    set_error("hash join on %d key columns: only single-column keys are implemented", d->n_keys);
-    return TQ_ERR_UNSUPPORTED_TYPE;
-  }
+  if (d->n_keys < 1 || d->n_keys > MK_MAX_KEYS) { set_error("hash join on %d key columns: 1..%d are supported", d->n_keys, MK_MAX_KEYS); return TQ_ERR_INVALID_ARG; }
+  const int hidden = d->n_keys > 1 ? 1 : 0;
+  if (d->n_build_cols + hidden > MAXC || d->n_probe_cols + hidden > MAXC) { set_error("multi-column join keys need one spare column per side"); return TQ_ERR_INVALID_ARG; }
   for (int c = 0; c < d->n_build_cols; c++)
     if (!type_ok(d->build_types[c])) { set_error("unsupport column type for encode %d", d->build_types[c]); return TQ_ERR_UNSUPPORTED_TYPE; }
   for (int c = 0; c < d->n_probe_cols; c++)
     if (!type_ok(d->probe_types[c])) { set_error("unsupport column type for encode %d", d->probe_types[c]); return TQ_ERR_UNSUPPORTED_TYPE; }
-  if (d->build_key_idx[0] < 0 || d->build_key_idx[0] >= d->n_build_cols || d->probe_key_idx[0] < 0 || d->probe_key_idx[0] >= d->n_probe_cols)
-    return TQ_ERR_INVALID_ARG;
+  for (int i = 0; i < d->n_keys; i++)
+    if (d->build_key_idx[i] < 0 || d->build_key_idx[i] >= d->n_build_cols || d->probe_key_idx[i] < 0 || d->probe_key_idx[i] >= d->n_probe_cols)
+      return TQ_ERR_INVALID_ARG;
   // LeftOuter keeps the left child as the outer side, RightOuter the right child (builder.go:451-477)
   if (d->join_type == TQ_JOIN_LEFT_OUTER && d->outer_is_right) { set_error("left outer join needs outer_is_right == 0"); return TQ_ERR_INVALID_ARG; }
   if (d->join_type == TQ_JOIN_RIGHT_OUTER && !d->outer_is_right) { set_error("right outer join needs outer_is_right == 1"); return TQ_ERR_INVALID_ARG; }
@@ -1995,21 +2020,47 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   if (!j) return TQ_ERR_OOM;
   j->join_type = d->join_type;
   j->outer_is_right = d->outer_is_right ? 1 : 0;
-  j->n_build_cols = d->n_build_cols;
-  j->n_probe_cols = d->n_probe_cols;
-  j->n_keys = 1;
+  j->nb_user = d->n_build_cols;
+  j->np_user = d->n_probe_cols;
+  j->n_build_cols = d->n_build_cols + hidden;
+  j->n_probe_cols = d->n_probe_cols + hidden;
+  j->n_keys = d->n_keys;
   for (int c = 0; c < d->n_build_cols; c++) j->build_types[c] = d->build_types[c];
   for (int c = 0; c < d->n_probe_cols; c++) j->probe_types[c] = d->probe_types[c];
-  j->build_key = d->build_key_idx[0];
-  j->probe_key = d->probe_key_idx[0];
-  const int bt = j->build_types[j->build_key], pt = j->probe_types[j->probe_key];
-  const bool bf = bt == TQ_TYPE_FLOAT64, pf = pt == TQ_TYPE_FLOAT64;
-  if (bf != pf) j->key_mode = KEYMODE_NEVER;
-  else if (!bf && bt != pt) j->key_mode = KEYMODE_NO_SIGNBIT;
-  else j->key_mode = KEYMODE_RAW;
+  // key comparison across types (codec.go:219-231,363-382): a DOUBLE never equals an integer key; signed vs unsigned
+  // integers are equal only when both are below 2^63
+  auto mode_of = [](int bt, int pt) {
+    const bool bf = bt == TQ_TYPE_FLOAT64, pf = pt == TQ_TYPE_FLOAT64;
+    if (bf != pf) return (int)KEYMODE_NEVER;
+    if (!bf && bt != pt) return (int)KEYMODE_NO_SIGNBIT;
+    return (int)KEYMODE_RAW;
+  };
+  if (!hidden) {
+    j->build_key = d->build_key_idx[0];
+    j->probe_key = d->probe_key_idx[0];
+    j->key_mode = mode_of(j->build_types[j->build_key], j->probe_types[j->probe_key]);
+  } else {
+    j->build_key = j->nb_user;
+    j->probe_key = j->np_user;
+    j->build_types[j->nb_user] = TQ_TYPE_UINT64;
+    j->probe_types[j->np_user] = TQ_TYPE_UINT64;
+    j->key_mode = KEYMODE_RAW;
+    j->mk.k = d->n_keys;
+    for (int i = 0; i < d->n_keys; i++) {
+      j->bkeys[i] = d->build_key_idx[i];
+      j->pkeys[i] = d->probe_key_idx[i];
+      const int m = mode_of(j->build_types[j->bkeys[i]], j->probe_types[j->pkeys[i]]);
+      if (m == KEYMODE_NEVER) j->key_mode = KEYMODE_NEVER;
+      j->mk_no_signbit[i] = (m == KEYMODE_NO_SIGNBIT);
+    }
+  }
+  {
+    const int first_user = j->outer_is_right ? j->nb_user : j->np_user, first_int = j->outer_is_right ? j->n_build_cols : j->n_probe_cols;
+    for (int u = 0; u < j->nb_user + j->np_user; u++) j->out_map.push_back(u < first_user ? u : u - first_user + first_int);
+  }
   if (d->probe_batch_rows > 0) j->batch_rows = (d->probe_batch_rows + 63) & ~63ll;
-  j->b_host.resize(j->n_build_cols);
-  j->p_host.resize(j->n_probe_cols);
+  j->b_host.resize(j->nb_user);
+  j->p_host.resize(j->np_user);
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < 2 && e == cudaSuccess; i++) {
     e = cudaEventCreate(&j->ev_a[i]);
@@ -2031,16 +2082,16 @@ int32_t tq_join_put_build(tq_join *j, const tq_column *cols, int32_t mem) {
   j->build_mem = mem;
   const int64_t rows = cols[0].length;
   if (rows < 0) return TQ_ERR_INVALID_ARG;
-  for (int c = 0; c < j->n_build_cols; c++) {
+  for (int c = 0; c < j->nb_user; c++) {
     if (cols[c].length != rows) { set_error("ragged build chunk"); return TQ_ERR_INVALID_ARG; }
     if (cols[c].offsets) { set_error("unsupport column type for encode (var-len column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
     if (rows && !cols[c].data) return TQ_ERR_INVALID_ARG;
   }
   if (rows == 0) return TQ_OK;
   if (mem == TQ_MEM_HOST) {
-    for (int c = 0; c < j->n_build_cols; c++) TQ_TRY(j->b_host[c].append(cols[c], rows));
+    for (int c = 0; c < j->nb_user; c++) TQ_TRY(j->b_host[c].append(cols[c], rows));
   } else {
-    j->b_dev_chunks.emplace_back(cols, cols + j->n_build_cols);
+    j->b_dev_chunks.emplace_back(cols, cols + j->nb_user);
   }
   j->n_build += rows;
   return TQ_OK;
@@ -2054,14 +2105,14 @@ int32_t tq_join_finalize_build(tq_join *j) {
   std::lock_guard<std::recursive_mutex> lk(r.mu);
   j->b_view.assign(j->n_build_cols, DCol());
   if (j->build_mem == TQ_MEM_DEVICE && j->b_dev_chunks.size() == 1) {
-    for (int c = 0; c < j->n_build_cols; c++) {
+    for (int c = 0; c < j->nb_user; c++) {
       j->b_view[c].data = (const uint64_t *)j->b_dev_chunks[0][c].data;
       j->b_view[c].bm = (const uint32_t *)j->b_dev_chunks[0][c].null_bitmap;
     }
   } else if (j->build_mem == TQ_MEM_DEVICE) {
     // several device chunks: concatenate (data D2D; bitmaps need 8-row alignment at chunk boundaries)
-    j->b_cols.resize(j->n_build_cols);
-    for (int c = 0; c < j->n_build_cols; c++) {
+    j->b_cols.resize(j->nb_user);
+    for (int c = 0; c < j->nb_user; c++) {
       TQ_TRY(j->b_cols[c].data.reserve((size_t)j->n_build * 8));
       TQ_TRY(j->b_cols[c].bm.reserve(bitmap_alloc_bytes(j->n_build)));
       int64_t off = 0;
@@ -2081,14 +2132,28 @@ int32_t tq_join_finalize_build(tq_join *j) {
       j->b_view[c].bm = any_bm ? j->b_cols[c].bm.as<uint32_t>() : nullptr;
     }
   } else {
-    j->b_cols.resize(j->n_build_cols);
-    for (int c = 0; c < j->n_build_cols; c++) {
+    j->b_cols.resize(j->nb_user);
+    for (int c = 0; c < j->nb_user; c++) {
       TQ_TRY(upload_col(j->b_host[c], j->b_cols[c], r.compute));
       j->b_view[c].data = j->b_cols[c].data.as<uint64_t>();
       j->b_view[c].bm = j->b_host[c].has_bm ? j->b_cols[c].bm.as<uint32_t>() : nullptr;
     }
   }
+  if (j->n_keys > 1) {
+    // build-side key tuples -> the hidden key column; a NULL in any key column leaves the row out of the table (hash_table.go:161-163)
+    DCol kc[MK_MAX_KEYS];
+    bool any_bm = false;
+    for (int i = 0; i < j->n_keys; i++) { kc[i] = j->b_view[j->bkeys[i]]; any_bm |= (kc[i].bm != nullptr); }
+    TQ_TRY(j->mk_build_key.reserve((size_t)(j->n_build ? j->n_build : 1) * 8));
+    if (any_bm) TQ_TRY(j->mk_build_bm.reserve(bitmap_alloc_bytes(j->n_build)));
+    TQ_TRY(j->mk.encode(kc, nullptr, j->n_build, /*insert=*/true, /*null_is_value=*/false, j->mk_build_key.as<uint64_t>(),
+                        any_bm ? j->mk_build_bm.as<uint32_t>() : nullptr, r.compute));
+    j->b_view[j->nb_user].data = j->mk_build_key.as<uint64_t>();
+    j->b_view[j->nb_user].bm = any_bm ? j->mk_build_bm.as<uint32_t>() : nullptr;
+  }
   TQ_TRY(join_build(j));
+  j->mk_build_key.release();
+  j->mk_build_bm.release();
   for (auto &h : j->b_host) { h.data.release(); h.bm.release(); }
   j->b_dev_chunks.clear();
   j->state = tq_join::PROBING;
@@ -2102,7 +2167,7 @@ int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *sele
   if (j->probe_eof) { set_error("put_probe after probe_eof"); return TQ_ERR_STATE; }
   const int64_t rows = cols[0].length;
   if (rows < 0) return TQ_ERR_INVALID_ARG;
-  for (int c = 0; c < j->n_probe_cols; c++) {
+  for (int c = 0; c < j->np_user; c++) {
     if (cols[c].length != rows) { set_error("ragged probe chunk"); return TQ_ERR_INVALID_ARG; }
     if (cols[c].offsets) { set_error("unsupport column type for encode (var-len column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
     if (rows && !cols[c].data) return TQ_ERR_INVALID_ARG;
@@ -2113,7 +2178,7 @@ int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *sele
   if (mem == TQ_MEM_DEVICE) {
     TQ_TRY(flush_probe_staging(j));
     std::vector<DCol> view(j->n_probe_cols);
-    for (int c = 0; c < j->n_probe_cols; c++) {
+    for (int c = 0; c < j->np_user; c++) {
       view[c].data = (const uint64_t *)cols[c].data;
       view[c].bm = (const uint32_t *)cols[c].null_bitmap;
     }
@@ -2140,7 +2205,7 @@ int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *sele
   }
   if (j->p_host[0].n + rows > j->batch_rows) TQ_TRY(flush_probe_staging(j));
   const int64_t before = j->p_host[0].n;
-  for (int c = 0; c < j->n_probe_cols; c++) TQ_TRY(j->p_host[c].append(cols[c], rows));
+  for (int c = 0; c < j->np_user; c++) TQ_TRY(j->p_host[c].append(cols[c], rows));
   if (selected && !j->p_sel_any) { j->p_sel_host.assign((size_t)before, 1); j->p_sel_any = true; }
   if (j->p_sel_any) {
     if (selected) j->p_sel_host.insert(j->p_sel_host.end(), selected, selected + rows);
@@ -2169,7 +2234,7 @@ int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t 
   if (j->state == tq_join::BUILDING) { set_error("next before finalize_build"); return TQ_ERR_STATE; }
   Runtime &r = rt();
   std::lock_guard<std::recursive_mutex> lk(r.mu);
-  const int ncols = j->n_build_cols + j->n_probe_cols;
+  const int ncols = j->nb_user + j->np_user;  // hidden key columns stay behind (out_map)
   for (;;) {
     if (j->host_cur && j->host_cur_pos < j->host_cur->n) break;
     if (j->host_cur) { recycle(j, std::move(j->host_cur)); j->host_cur_pos = 0; }
@@ -2200,8 +2265,9 @@ int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t 
   if (!rb->on_host) {
     if ((j->host_cur_pos & 7) != 0) { set_error("internal: unaligned direct result copy"); return TQ_ERR_STATE; }
     for (int c = 0; c < ncols; c++) {
-      TQ_CUDA(cudaMemcpyAsync(out_cols[c].data, rb->cols[c].data.as<uint8_t>() + j->host_cur_pos * 8, (size_t)take * 8, cudaMemcpyDeviceToHost, r.d2h));
-      TQ_CUDA(cudaMemcpyAsync(out_cols[c].null_bitmap, rb->cols[c].bm.as<uint8_t>() + (j->host_cur_pos >> 3), bitmap_bytes(take), cudaMemcpyDeviceToHost, r.d2h));
+      const int ic = j->out_map[c];
+      TQ_CUDA(cudaMemcpyAsync(out_cols[c].data, rb->cols[ic].data.as<uint8_t>() + j->host_cur_pos * 8, (size_t)take * 8, cudaMemcpyDeviceToHost, r.d2h));
+      TQ_CUDA(cudaMemcpyAsync(out_cols[c].null_bitmap, rb->cols[ic].bm.as<uint8_t>() + (j->host_cur_pos >> 3), bitmap_bytes(take), cudaMemcpyDeviceToHost, r.d2h));
       out_cols[c].length = take;
     }
     TQ_CUDA(cudaStreamSynchronize(r.d2h));
@@ -2213,8 +2279,9 @@ int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t 
     return TQ_OK;
   }
   for (int c = 0; c < ncols; c++) {
-    memcpy(out_cols[c].data, rb->h_data[c].as<uint8_t>() + j->host_cur_pos * 8, (size_t)take * 8);
-    host_bitmap_extract(out_cols[c].null_bitmap, rb->h_bm[c].as<uint8_t>(), j->host_cur_pos, take);
+    const int ic = j->out_map[c];
+    memcpy(out_cols[c].data, rb->h_data[ic].as<uint8_t>() + j->host_cur_pos * 8, (size_t)take * 8);
+    host_bitmap_extract(out_cols[c].null_bitmap, rb->h_bm[ic].as<uint8_t>(), j->host_cur_pos, take);
     out_cols[c].length = take;
   }
   j->host_cur_pos += take;
@@ -2238,11 +2305,11 @@ int32_t tq_join_next_device(tq_join *j, tq_column *out_cols, int64_t *n_rows, in
   }
   j->lent = std::move(j->results.front());
   j->results.pop_front();
-  const int ncols = j->n_build_cols + j->n_probe_cols;
+  const int ncols = j->nb_user + j->np_user;
   for (int c = 0; c < ncols; c++) {
     out_cols[c].length = j->lent->n;
-    out_cols[c].data = j->lent->cols[c].data.as<uint8_t>();
-    out_cols[c].null_bitmap = j->lent->cols[c].bm.as<uint8_t>();
+    out_cols[c].data = j->lent->cols[j->out_map[c]].data.as<uint8_t>();
+    out_cols[c].null_bitmap = j->lent->cols[j->out_map[c]].bm.as<uint8_t>();
     out_cols[c].offsets = nullptr;
   }
   *n_rows = j->lent->n;
