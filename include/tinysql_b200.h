@@ -45,8 +45,9 @@ enum {
   TQ_TYPE_INT64 = 1,   /* TINY..LONGLONG, YEAR (signed)            */
   TQ_TYPE_UINT64 = 2,  /* same, with mysql.UnsignedFlag            */
   TQ_TYPE_FLOAT64 = 3, /* DOUBLE                                   */
-  TQ_TYPE_FLOAT32 = 4, /* FLOAT (4-byte slot)      — not yet accepted by the operators */
-  TQ_TYPE_BYTES = 5,   /* var-len (offsets + data) — not yet accepted by the operators */
+  TQ_TYPE_FLOAT32 = 4, /* FLOAT (4-byte slots)     — HashJoin payload (non-key) columns, host memory      */
+  TQ_TYPE_BYTES = 5,   /* var-len (offsets + data) — HashJoin payload (non-key) columns, host memory:
+                        *   offsets = length+1 int64 (Go's Column.offsets), data = the cells' bytes            */
   /* OR-ed into a tq_agg_desc.input_types entry: the column's FieldType carries mysql.NotNullFlag.  Lets HashAgg
    * drop the per-group "saw a non-NULL input" word of SUM / MAX / MIN (16-byte instead of 32-byte group records
    * for SUM + COUNT); any null bitmap passed for such a column is ignored. */
@@ -90,6 +91,7 @@ int32_t tq_device_alloc(size_t bytes, void **out);
 int32_t tq_device_free(void *p);
 int32_t tq_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int32_t tq_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+int32_t tq_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes); /* e.g. keep rows lent by *_next_device / export_partial */
 int32_t tq_memset_device(void *dst_dev, int32_t byte_value, size_t bytes);
 int32_t tq_device_synchronize(void);
 
@@ -194,7 +196,7 @@ typedef struct tq_join_desc {
   const int32_t *build_types; /* TQ_TYPE_* per inner column                                   */
   int32_t n_probe_cols;       /* outer-side schema                                            */
   const int32_t *probe_types;
-  int32_t n_keys;             /* len(innerKeys) == len(outerKeys)                             */
+  int32_t n_keys;             /* len(innerKeys) == len(outerKeys), 1..8; key columns are 8-byte types */
   const int32_t *build_key_idx; /* innerKeys[i].Index                                         */
   const int32_t *probe_key_idx; /* outerKeys[i].Index                                         */
   int64_t probe_batch_rows;   /* device batch size the ≤1024-row chunks are accumulated into; 0 = default */
@@ -212,6 +214,10 @@ int32_t tq_join_probe_eof(tq_join *j);
  * allocated columns, host memory).  *n_rows == 0 with *eof == 0 means "feed more probe
  * chunks"; *n_rows == 0 with *eof != 0 is the reference's end of stream. */
 int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+/* Data bytes each output column of the NEXT tq_join_next(j, max_rows, ...) call will carry (8 * rows for the 8-byte
+ * types, 4 * rows for FLOAT, the cells' total length for var-len columns), so the caller can size out_cols[c].data —
+ * the "*_next_size query" of the ownership contract.  All zero when that call would return no rows. */
+int32_t tq_join_next_bytes(tq_join *j, int64_t max_rows, int64_t *bytes_per_col);
 int32_t tq_join_destroy(tq_join *j);
 
 /* Benchmark / multi-GPU variant of Next: pops the oldest finished device result batch and

@@ -145,7 +145,14 @@ int64_t orc_rowmap_len(orc_rowmap *m) { return m->n_entries; }
 void orc_rowmap_free(orc_rowmap *m) { if (!m) return; free(m->keys); free(m->heads); free(m->used); free(m->entries); free(m); }
 
 /* ------------------------------------------------------------------ growable output */
-typedef struct { uint64_t *data; uint8_t *nn; int64_t n, cap; } outbuf; /* nn: byte per row, 1 = not null */
+/* One output column under construction.  elem = 8 (every integer type, DOUBLE), 4 (FLOAT) or 0 (var-len: bytes +
+ * offsets) — util/chunk/codec.go:171-181 getFixedLen. */
+typedef struct {
+  uint64_t *data; uint8_t *nn; int64_t n, cap; /* nn: byte per row, 1 = not null */
+  int elem;
+  uint8_t *bytes; int64_t nbytes, bcap; int64_t *offs; int64_t ocap;
+} outbuf;
+static int elem_of_type(int t) { return t == ORC_TYPE_FLOAT32 ? 4 : (t == ORC_TYPE_BYTES ? 0 : 8); }
 static void ob_push(outbuf *b, uint64_t v, int not_null) {
   if (b->n == b->cap) {
     b->cap = b->cap ? b->cap * 2 : 1024;
@@ -154,26 +161,63 @@ static void ob_push(outbuf *b, uint64_t v, int not_null) {
   }
   b->data[b->n] = v; b->nn[b->n] = (uint8_t)not_null; b->n++;
 }
+/* Append cell `row` of src (row < 0: a NULL cell).  Restates the per-column copy of chunk.CopySelectedJoinRows
+ * (util/chunk/chunk_util.go:38-66,84-110): fixed-width cells copy elemLen bytes, var-len cells copy
+ * data[offsets[i]:offsets[i+1]] and push the new end offset; the NULL bit travels separately. */
+static void ob_push_cell(outbuf *b, const orc_column *src, int64_t row) {
+  int not_null = row >= 0 && !col_is_null(src, row);
+  if (b->elem == 8) { ob_push(b, row >= 0 ? col_u64(src, row) : 0, not_null); return; }
+  if (b->elem == 4) {
+    uint32_t v = 0;
+    if (row >= 0) memcpy(&v, src->data + 4 * row, 4);
+    ob_push(b, v, not_null);
+    return;
+  }
+  int64_t start = 0, end = 0;
+  if (row >= 0) { start = src->offsets[row]; end = src->offsets[row + 1]; }
+  if (b->nbytes + (end - start) > b->bcap) {
+    b->bcap = b->bcap ? b->bcap * 2 : 4096;
+    while (b->bcap < b->nbytes + (end - start)) b->bcap *= 2;
+    b->bytes = (uint8_t *)realloc(b->bytes, (size_t)b->bcap);
+  }
+  if (end > start) memcpy(b->bytes + b->nbytes, src->data + start, (size_t)(end - start));
+  b->nbytes += end - start;
+  if (b->n + 2 > b->ocap) { b->ocap = b->ocap ? b->ocap * 2 : 1024; b->offs = (int64_t *)realloc(b->offs, 8 * (size_t)b->ocap); }
+  if (b->n == 0) b->offs[0] = 0;
+  b->offs[b->n + 1] = b->nbytes;
+  ob_push(b, 0, not_null);
+}
 static void ob_finish(outbuf *b, orc_column *c) {
   int64_t n = b->n;
   c->length = n; c->offsets = NULL;
-  c->data = (uint8_t *)malloc(8 * (size_t)(n ? n : 1));
-  if (n) memcpy(c->data, b->data, 8 * (size_t)n);
+  if (b->elem == 8) {
+    c->data = (uint8_t *)malloc(8 * (size_t)(n ? n : 1));
+    if (n) memcpy(c->data, b->data, 8 * (size_t)n);
+  } else if (b->elem == 4) {
+    c->data = (uint8_t *)malloc(4 * (size_t)(n ? n : 1));
+    for (int64_t i = 0; i < n; i++) { uint32_t v = (uint32_t)b->data[i]; memcpy(c->data + 4 * i, &v, 4); }
+  } else {
+    c->data = (uint8_t *)malloc((size_t)(b->nbytes ? b->nbytes : 1));
+    if (b->nbytes) memcpy(c->data, b->bytes, (size_t)b->nbytes);
+    c->offsets = (int64_t *)malloc(8 * (size_t)(n + 1));
+    c->offsets[0] = 0;
+    if (n) memcpy(c->offsets, b->offs, 8 * (size_t)(n + 1));
+  }
   int64_t nb = (n + 7) >> 3;
   c->null_bitmap = (uint8_t *)calloc((size_t)(nb ? nb : 1), 1);
   for (int64_t i = 0; i < n; i++) if (b->nn[i]) c->null_bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
-  free(b->data); free(b->nn);
+  free(b->data); free(b->nn); free(b->bytes); free(b->offs);
 }
 void orc_free_columns(int n, orc_column *cols) {
-  for (int i = 0; i < n; i++) { free(cols[i].data); free(cols[i].null_bitmap); cols[i].data = NULL; cols[i].null_bitmap = NULL; }
+  for (int i = 0; i < n; i++) {
+    free(cols[i].data); free(cols[i].null_bitmap); free(cols[i].offsets);
+    cols[i].data = NULL; cols[i].null_bitmap = NULL; cols[i].offsets = NULL;
+  }
 }
 
 /* ------------------------------------------------------------------ hash join */
 static void append_row(outbuf *obs, int base, int ncols, const orc_column *cols, int64_t row) {
-  for (int c = 0; c < ncols; c++) {
-    if (row < 0) ob_push(&obs[base + c], 0, 0);            /* defaultInner: all NULL (builder.go:463-465) */
-    else ob_push(&obs[base + c], col_u64(&cols[c], row), !col_is_null(&cols[c], row));
-  }
+  for (int c = 0; c < ncols; c++) ob_push_cell(&obs[base + c], &cols[c], row); /* row < 0: defaultInner, all NULL (builder.go:463-465) */
 }
 
 int orc_hash_join(int join_type, int outer_is_right,
@@ -182,8 +226,10 @@ int orc_hash_join(int join_type, int outer_is_right,
                   int n_keys, const int *build_key_idx, const int *probe_key_idx,
                   const uint8_t *selected, orc_column *out_cols, int64_t *n_out) {
   if (join_type < 0 || join_type > 2 || n_keys < 1) return ORC_ERR_INVALID;
-  for (int c = 0; c < n_build_cols; c++) if (build_types[c] < 1 || build_types[c] > 3) return ORC_ERR_UNSUPPORTED;
-  for (int c = 0; c < n_probe_cols; c++) if (probe_types[c] < 1 || probe_types[c] > 3) return ORC_ERR_UNSUPPORTED;
+  for (int c = 0; c < n_build_cols; c++) if (build_types[c] < 1 || build_types[c] > 5) return ORC_ERR_UNSUPPORTED;
+  for (int c = 0; c < n_probe_cols; c++) if (probe_types[c] < 1 || probe_types[c] > 5) return ORC_ERR_UNSUPPORTED;
+  /* key columns: the 8-byte types only (FLOAT / var-len keys are not restated — "unsupport column type", codec.go:235) */
+  for (int k = 0; k < n_keys; k++) if (build_types[build_key_idx[k]] > 3 || probe_types[probe_key_idx[k]] > 3) return ORC_ERR_UNSUPPORTED;
   int64_t nb = n_build_cols ? build_cols[0].length : 0, np = n_probe_cols ? probe_cols[0].length : 0;
 
   /* fetchAndBuildHashTable [stub join.go:148] + hashRowContainer.PutChunk (hash_table.go:146-169) */
@@ -201,6 +247,8 @@ int orc_hash_join(int join_type, int outer_is_right,
   int build_base = outer_is_right ? 0 : n_probe_cols;
   int probe_base = outer_is_right ? n_build_cols : 0;
   int is_outer = (join_type != 0);
+  for (int c = 0; c < n_build_cols; c++) obs[build_base + c].elem = elem_of_type(build_types[c]);
+  for (int c = 0; c < n_probe_cols; c++) obs[probe_base + c].elem = elem_of_type(probe_types[c]);
 
   uint32_t *pairs = NULL; int64_t pairs_cap = 0;
   /* runJoinWorker [stub join.go:243] -> join2Chunk (join.go:325-362) */
@@ -412,6 +460,7 @@ int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int
         rc = state_merge(fn[f], ft[f], &partial[w].states[g * n_funcs + f], &fin.states[gi * n_funcs + f]);
     }
   outbuf *obs = (outbuf *)calloc((size_t)(n_funcs ? n_funcs : 1), sizeof(outbuf));
+  for (int f = 0; f < n_funcs; f++) obs[f].elem = 8;
   if (rc == ORC_OK) {
     if (fin.n == 0 && n_group_by == 0) {
       /* empty input, no GROUP BY: defaultVal row (aggregate.go:572-574, builder.go:517-540):

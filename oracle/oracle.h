@@ -26,7 +26,8 @@ typedef struct orc_column {
 
 enum { ORC_OK = 0, ORC_ERR_INVALID = 1, ORC_ERR_UNSUPPORTED = 2, ORC_ERR_OVERFLOW_BIGINT = 3,
        ORC_ERR_OVERFLOW_BIGINT_UNSIGNED = 4, ORC_ERR_OVERFLOW_DOUBLE = 5, ORC_ERR_DIV_ZERO = 6 };
-enum { ORC_TYPE_INT64 = 1, ORC_TYPE_UINT64 = 2, ORC_TYPE_FLOAT64 = 3 };
+enum { ORC_TYPE_INT64 = 1, ORC_TYPE_UINT64 = 2, ORC_TYPE_FLOAT64 = 3,
+       ORC_TYPE_FLOAT32 = 4 /* 4-byte slots */, ORC_TYPE_BYTES = 5 /* offsets + data; join payload columns only */ };
 
 /* FNV-1 64 over flag||raw8 per key column — executor/hash_table.go:55-72 (fnv.New64),
  * util/codec/codec.go:249-276.  Exposed for the codec known-answer tests. */

@@ -38,11 +38,20 @@ def _take(tq_cols, types, n):
     cols = []
     for t, tp in zip(tq_cols, types):
         if n:
-            vals = np.ctypeslib.as_array(C.cast(t.data, C.POINTER(C.c_uint64)), shape=(n,)).copy().view(_NP[tp])
             bm = np.ctypeslib.as_array(C.cast(t.null_bitmap, C.POINTER(C.c_uint8)), shape=((n + 7) >> 3,)).copy()
-            cols.append(Column(tp, vals, unpack_not_null(bm, n)))
+            nn = unpack_not_null(bm, n)
+            if tp == 5:  # var-len: offsets + bytes
+                off = np.ctypeslib.as_array(C.cast(t.offsets, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+                data = np.ctypeslib.as_array(C.cast(t.data, C.POINTER(C.c_uint8)), shape=(max(int(off[n]), 1),)).copy()
+                cols.append(Column(tp, [data[off[i]:off[i + 1]].tobytes() if nn[i] else None for i in range(n)], nn))
+            elif tp == 4:  # FLOAT: 4-byte slots
+                vals = np.ctypeslib.as_array(C.cast(t.data, C.POINTER(C.c_uint32)), shape=(n,)).copy().view(np.float32)
+                cols.append(Column(tp, vals, nn))
+            else:
+                vals = np.ctypeslib.as_array(C.cast(t.data, C.POINTER(C.c_uint64)), shape=(n,)).copy().view(_NP[tp])
+                cols.append(Column(tp, vals, nn))
         else:
-            cols.append(Column(tp, np.zeros(0, dtype=_NP[tp]), np.zeros(0, dtype=bool)))
+            cols.append(Column(tp, [] if tp == 5 else np.zeros(0, dtype=_NP[tp]), np.zeros(0, dtype=bool)))
     return cols
 
 

@@ -78,6 +78,57 @@ def test_distributed_join_matches_single_process_oracle(tmp_path, world):
     assert np.array_equal(key(got), key(want))
 
 
+def _agg_worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tinysql_b200 import dist as D
+    rng = np.random.default_rng(200 + rank)
+    n = 30000 + 13 * rank
+    k = rng.integers(0, 700, n)
+    v = rng.integers(-50, 50, n)
+
+    def partial_fn(cols):  # CPU stand-in for Partial1 + tq_agg_export_partial: rows (key, count, sum)
+        kk, vv = cols[0].numpy(), cols[1].numpy()
+        keys, inv = np.unique(kk, return_inverse=True)
+        cnt = np.bincount(inv, minlength=len(keys)).astype(np.int64)
+        sm = np.bincount(inv, weights=vv, minlength=len(keys)).astype(np.int64)
+        return [torch.from_numpy(keys.astype(np.int64)), torch.from_numpy(cnt), torch.from_numpy(sm)]
+
+    def partition_fn(cols, world):
+        d = D.dest_rank_np(cols[0].numpy(), world)
+        order = np.argsort(d, kind="stable")
+        counts = np.bincount(d, minlength=world)
+        return [c[torch.from_numpy(order)] for c in cols], [0] + list(np.cumsum(counts))
+
+    def final_fn(recv):    # MergePartialResult: counts add, sums add
+        kk, cc, ss = (t.numpy() for t in recv)
+        keys, inv = np.unique(kk, return_inverse=True)
+        return keys, np.bincount(inv, weights=cc, minlength=len(keys)).astype(np.int64), np.bincount(inv, weights=ss, minlength=len(keys)).astype(np.int64)
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64))
+    keys, cnt, sm = D.distributed_agg([t(k), t(v)], world, rank, partial_fn, partition_fn, final_fn)
+    assert np.all(D.dest_rank_np(keys, world) == rank)   # every group is finalised on exactly one rank
+    np.savez(os.path.join(outdir, f"a{rank}.npz"), keys=keys, cnt=cnt, sm=sm, k=k, v=v)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_agg_partial_shuffle_final(tmp_path, world):
+    """partial -> shuffle -> final across ranks == the oracle's HashAgg over all rows (aggregate.go:96-133,352-356)"""
+    import oracle_py as O
+    from tinysql_b200.chunk import INT64, Column
+    port = _free_port()
+    mp.spawn(_agg_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(tmp_path, f"a{r}.npz")) for r in range(world)]
+    got = sorted(zip(np.concatenate([p["keys"] for p in parts]).tolist(), np.concatenate([p["cnt"] for p in parts]).tolist(),
+                     np.concatenate([p["sm"] for p in parts]).tolist()))
+    k, v = np.concatenate([p["k"] for p in parts]), np.concatenate([p["v"] for p in parts])
+    rc, want = O.hash_agg([INT64, INT64], [Column(INT64, k), Column(INT64, v)], [0], [(5, 0), (0, -1), (1, 1)], 2)
+    assert rc == 0 and got == sorted(want.rows())
+
+
 def test_dest_rank_matches_device_rule():
     """the numpy stand-in uses the same key -> rank rule as partition.cu (mix64(key) >> 40) % n_parts"""
     from tinysql_b200 import dist as D

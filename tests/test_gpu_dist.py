@@ -24,3 +24,4 @@ def test_two_gpu_join_matches_oracle():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "DIST_CHECK_OK world=2" in out.stdout
+    assert "DIST_AGG_OK world=2" in out.stdout

@@ -42,6 +42,7 @@ SYMBOLS = {
     "tq_pinned_alloc": (_I32, [C.c_size_t, C.POINTER(_P)]), "tq_pinned_free": (_I32, [_P]),
     "tq_device_alloc": (_I32, [C.c_size_t, C.POINTER(_P)]), "tq_device_free": (_I32, [_P]),
     "tq_memcpy_h2d": (_I32, [_P, _P, C.c_size_t]), "tq_memcpy_d2h": (_I32, [_P, _P, C.c_size_t]),
+    "tq_memcpy_d2d": (_I32, [_P, _P, C.c_size_t]),
     "tq_memset_device": (_I32, [_P, _I32, C.c_size_t]), "tq_device_synchronize": (_I32, []),
     "tq_timer_start": (_I32, []), "tq_timer_stop": (_I32, [C.POINTER(C.c_float)]),
     "tq_kernel_launch_count": (_I64, []), "tq_flush_l2": (_I32, []),
@@ -61,6 +62,7 @@ SYMBOLS = {
     "tq_join_put_probe": (_I32, [_P, _COL, _P, _I32]), "tq_join_probe_eof": (_I32, [_P]),
     "tq_join_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
     "tq_join_next_device": (_I32, [_P, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
+    "tq_join_next_bytes": (_I32, [_P, _I64, C.POINTER(_I64)]),
     "tq_join_stats": (_I32, [_P, C.POINTER(_I64)]), "tq_join_destroy": (_I32, [_P]),
     "tq_agg_create": (_I32, [C.POINTER(TQAggDesc), C.POINTER(_P)]),
     "tq_agg_output_type": (_I32, [_P, _I32, C.POINTER(_I32)]),
@@ -83,7 +85,8 @@ SYMBOLS = {
 # status codes (include/tinysql_b200.h)
 TQ_OK, TQ_ERR_INVALID_ARG, TQ_ERR_UNSUPPORTED_TYPE, TQ_ERR_OVERFLOW_BIGINT, TQ_ERR_OVERFLOW_BIGINT_UNSIGNED = 0, 1, 2, 3, 4
 TQ_ERR_OVERFLOW_DOUBLE, TQ_ERR_DIVISION_BY_ZERO, TQ_ERR_CUDA, TQ_ERR_NO_DEVICE, TQ_ERR_OOM, TQ_ERR_STATE = 5, 6, 7, 8, 9, 10
-TQ_TYPE_INT64, TQ_TYPE_UINT64, TQ_TYPE_FLOAT64 = 1, 2, 3
+TQ_TYPE_INT64, TQ_TYPE_UINT64, TQ_TYPE_FLOAT64, TQ_TYPE_FLOAT32, TQ_TYPE_BYTES = 1, 2, 3, 4, 5
+TQ_TYPE_NOT_NULL = 0x100
 TQ_MEM_HOST, TQ_MEM_DEVICE = 0, 1
 
 _lib = None

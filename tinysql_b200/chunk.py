@@ -12,7 +12,8 @@ from . import _lib as L
 MAX_CHUNK_SIZE = 1024  # DefMaxChunkSize sessionctx/variable/tidb_vars.go:241
 
 INT64, UINT64, FLOAT64 = L.TQ_TYPE_INT64, L.TQ_TYPE_UINT64, L.TQ_TYPE_FLOAT64
-_NP = {INT64: np.int64, UINT64: np.uint64, FLOAT64: np.float64}
+FLOAT32, BYTES = L.TQ_TYPE_FLOAT32, L.TQ_TYPE_BYTES  # FLOAT (4-byte slots) / var-len (offsets + data): join payload columns
+_NP = {INT64: np.int64, UINT64: np.uint64, FLOAT64: np.float64, FLOAT32: np.float32}
 
 
 def bitmap_bytes(n):
@@ -31,7 +32,13 @@ def unpack_not_null(bitmap, n):
 
 
 class Column:
-    """One fixed-width 8-byte chunk.Column in host memory."""
+    """One fixed-width chunk.Column in host memory (8-byte slots; 4-byte for FLOAT).  Column(BYTES, [...]) and
+    Column.empty(BYTES, ...) build the var-len flavour (VarColumn)."""
+
+    def __new__(cls, tp=None, *args, **kw):
+        if tp == L.TQ_TYPE_BYTES and cls is Column:
+            return object.__new__(VarColumn)
+        return object.__new__(cls)
 
     def __init__(self, tp, values, not_null=None):
         self.tp = tp
@@ -53,6 +60,8 @@ class Column:
         return unpack_not_null(self.bitmap, self.length)
 
     def raw(self):
+        if self.values.dtype.itemsize == 4:
+            return self.values.view(np.uint32).astype(np.uint64)
         return self.values.view(np.uint64)
 
     def slice(self, lo, hi):
@@ -70,6 +79,65 @@ class Column:
     def tolist(self):
         nn = self.not_null()
         return [self.values[i].item() if nn[i] else None for i in range(self.length)]
+
+
+class VarColumn(Column):
+    """A var-len chunk.Column (util/chunk/column.go:28-34): int64 offsets[length+1] + the cells' bytes."""
+
+    def __init__(self, tp, values, not_null=None):
+        assert tp == BYTES
+        self.tp = BYTES
+        vals = [b"" if v is None else bytes(v) for v in values]
+        if not_null is None and any(v is None for v in values):
+            not_null = [v is not None for v in values]
+        self.length = len(vals)
+        self.offsets = np.zeros(self.length + 1, dtype=np.int64)
+        if self.length:
+            np.cumsum([len(v) for v in vals], out=self.offsets[1:])
+        self.data = np.frombuffer(b"".join(vals), dtype=np.uint8).copy() if self.length else np.zeros(0, dtype=np.uint8)
+        self.bitmap = None if not_null is None else pack_not_null(not_null)
+
+    @classmethod
+    def empty(cls, tp, n, nbytes=0):
+        """Caller-allocated result column: offsets for n rows, `nbytes` of cell data, bitmap."""
+        c = object.__new__(cls)
+        c.tp, c.length = BYTES, n
+        c.offsets = np.zeros(n + 1, dtype=np.int64)
+        c.data = np.zeros(max(nbytes, 1), dtype=np.uint8)
+        c.bitmap = np.zeros(bitmap_bytes(max(n, 1)), dtype=np.uint8)
+        return c
+
+    @property
+    def values(self):
+        """object array of the cells (bytes); NULL cells are b''"""
+        return np.array([self.data[self.offsets[i]:self.offsets[i + 1]].tobytes() for i in range(self.length)], dtype=object)
+
+    def raw(self):
+        import hashlib
+        return np.array([int.from_bytes(hashlib.blake2b(v, digest_size=8).digest(), "little") for v in self.values], dtype=np.uint64)
+
+    def slice(self, lo, hi):
+        nn = self.not_null()[lo:hi]
+        return VarColumn(BYTES, [v if ok else None for v, ok in zip(self.values[lo:hi], nn)], None if self.bitmap is None else nn)
+
+    def head(self, k):
+        """first k rows of a filled result column"""
+        nn = self.not_null()[:k]
+        cells = [self.data[self.offsets[i]:self.offsets[i + 1]].tobytes() for i in range(k)]
+        return VarColumn(BYTES, cells, nn)
+
+    def tq(self, length=None):
+        t = L.TQColumn()
+        t.length = self.length if length is None else length
+        t.data = self.data.ctypes.data if self.data.size else None
+        t.null_bitmap = self.bitmap.ctypes.data if self.bitmap is not None else None
+        t.offsets = self.offsets.ctypes.data
+        return t
+
+    def tolist(self):
+        nn = self.not_null()
+        v = self.values
+        return [v[i] if nn[i] else None for i in range(self.length)]
 
 
 def tq_array(cols, length=None):
@@ -94,7 +162,10 @@ class Chunk:
         for ci, tp in enumerate(types):
             vals = [c.cols[ci].values for c in chunks if c.num_rows()]
             nns = [c.cols[ci].not_null() for c in chunks if c.num_rows()]
-            if vals:
+            if tp == BYTES:
+                cells = [v if ok else None for va, na in zip(vals, nns) for v, ok in zip(va, na)]
+                cols.append(VarColumn(BYTES, cells, np.concatenate(nns) if nns else None))
+            elif vals:
                 cols.append(Column(tp, np.concatenate(vals), np.concatenate(nns)))
             else:
                 cols.append(Column(tp, np.zeros(0, dtype=_NP[tp]), np.zeros(0, dtype=bool)))

@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "dict.cuh"
+#include "varlen.cuh"
 
 namespace tq {
 
@@ -1311,7 +1312,33 @@ struct HostAccum {
     n += rows;
     return TQ_OK;
   }
+  // indirect (FLOAT / var-len) columns: only the NULL bitmap is staged here, the cells go to a HostVarAccum
+  int32_t append_nulls(const tq_column &c, int64_t rows) {
+    TQ_TRY(ensure(n + rows));
+    host_bitmap_append(bm.as<uint8_t>(), n, c.null_bitmap, rows);
+    if (c.null_bitmap) has_bm = true;
+    n += rows;
+    return TQ_OK;
+  }
   void reset() { n = 0; has_bm = false; }
+};
+
+// host staging of the cells of one FLOAT (elem 4) or var-len (elem 0) column
+struct HostVarAccum {
+  std::vector<int64_t> off{0};
+  std::vector<uint8_t> bytes;
+  int elem = 0;
+  int64_t n = 0;
+  void append(const tq_column &c, int64_t rows) {
+    if (elem == 4) bytes.insert(bytes.end(), c.data, c.data + rows * 4);
+    else {
+      const int64_t base = c.offsets[0];
+      for (int64_t i = 0; i < rows; i++) off.push_back(off.back() + (c.offsets[i + 1] - c.offsets[i]));
+      bytes.insert(bytes.end(), c.data + base, c.data + c.offsets[rows]);
+    }
+    n += rows;
+  }
+  void reset() { off.assign(1, 0); bytes.clear(); n = 0; }
 };
 
 struct DevColBuf {
@@ -1324,6 +1351,7 @@ struct ResultBatch {
   uint64_t capacity = 0;
   // host copies (host-consumer path)
   std::vector<PinBuf> h_data, h_bm;
+  std::vector<VarOut> var;   // gathered FLOAT / var-len output columns (indexed like cols)
   bool on_host = false;
   cudaEvent_t ev_ready = nullptr;
   ~ResultBatch() { if (ev_ready) cudaEventDestroy(ev_ready); }
@@ -1331,6 +1359,7 @@ struct ResultBatch {
 
 struct ProbeInputSet {  // device copy of one host probe batch
   std::vector<DevColBuf> cols;
+  std::vector<SideStore> store;  // cells of the indirect probe columns of this batch
   DevBuf selected;
   cudaEvent_t ev_h2d = nullptr;
   ~ProbeInputSet() { if (ev_h2d) cudaEventDestroy(ev_h2d); }
@@ -1368,6 +1397,14 @@ struct tq_join {
   MultiKeyEncoder mk;
   DevBuf mk_build_key, mk_build_bm, mk_probe_key[2], mk_probe_bm[2];
   std::vector<int> out_map;               // caller's output column -> column of the result batch
+  // FLOAT / var-len payload columns travel through the kernels as row ids into a side store (varlen.cuh)
+  bool b_ind[MAXC] = {}, p_ind[MAXC] = {}, any_ind = false;
+  int b_elem[MAXC] = {}, p_elem[MAXC] = {};
+  SideStore b_store[MAXC];
+  HostVarAccum b_var[MAXC], p_var[MAXC];
+  int out_side[2 * MAXC] = {};            // per result-batch column: 0 = plain, 1 = build-side store, 2 = probe-side store
+  int out_col[2 * MAXC] = {};
+  DevBuf lens_scratch, scan_scratch3;
   int64_t batch_rows = 1 << 22;
 
   enum State { BUILDING, PROBING, CLOSED } state = BUILDING;
@@ -1441,6 +1478,35 @@ static int stream_grid(int64_t n) {
 }
 
 static bool type_ok(int t) { return t == TQ_TYPE_INT64 || t == TQ_TYPE_UINT64 || t == TQ_TYPE_FLOAT64; }
+static bool type_indirect(int t) { return t == TQ_TYPE_FLOAT32 || t == TQ_TYPE_BYTES; }
+
+// Upload the staged cells of an indirect column into its device store.
+static int32_t upload_store(const HostVarAccum &h, SideStore &st, cudaStream_t s) {
+  st.elem = h.elem;
+  st.n = h.n;
+  st.base = 0;
+  TQ_TRY(st.bytes.reserve(h.bytes.size() + 16));
+  if (!h.bytes.empty()) TQ_CUDA(cudaMemcpyAsync(st.bytes.p, h.bytes.data(), h.bytes.size(), cudaMemcpyHostToDevice, s));
+  if (h.elem == 0) {
+    TQ_TRY(st.offsets.reserve(h.off.size() * 8));
+    TQ_CUDA(cudaMemcpyAsync(st.offsets.p, h.off.data(), h.off.size() * 8, cudaMemcpyHostToDevice, s));
+  }
+  TQ_CUDA(cudaStreamSynchronize(s));  // pageable source
+  return TQ_OK;
+}
+
+// Result row ids -> cells, for every indirect column of a finished result batch.
+static int32_t materialize_indirect(tq_join *j, ResultBatch *rb, int slot) {
+  const int ncols = j->n_build_cols + j->n_probe_cols;
+  rb->var.resize(ncols);
+  for (int ic = 0; ic < ncols; ic++) {
+    if (!j->out_side[ic]) continue;
+    const SideStore &st = j->out_side[ic] == 1 ? j->b_store[j->out_col[ic]] : j->in_set[slot].store[j->out_col[ic]];
+    TQ_TRY(gather_cells(st, rb->cols[ic].data.as<uint64_t>(), rb->cols[ic].bm.as<uint32_t>(), rb->n, rb->var[ic], j->lens_scratch, j->scan_scratch3,
+                        rt().compute));
+  }
+  return TQ_OK;
+}
 
 static int32_t upload_col(const HostAccum &h, DevColBuf &d, cudaStream_t s) {
   TQ_TRY(d.data.reserve((size_t)(h.n ? h.n : 1) * 8));
@@ -1621,6 +1687,7 @@ static std::unique_ptr<ResultBatch> get_result_batch(tq_join *j) {
   else rb.reset(new ResultBatch());
   rb->n = 0;
   rb->on_host = false;
+  for (auto &v : rb->var) v.used = false;
   return rb;
 }
 
@@ -1830,9 +1897,20 @@ static int32_t enqueue_d2h(tq_join *j, ResultBatch *rb) {
   for (int c = 0; c < ncols; c++) {
     TQ_TRY(rb->h_data[c].reserve((size_t)(rb->n ? rb->n : 1) * 8));
     TQ_TRY(rb->h_bm[c].reserve(bitmap_alloc_bytes(rb->n)));
+    const bool ind = c < (int)rb->var.size() && rb->var[c].used;
     if (rb->n) {
-      TQ_CUDA(cudaMemcpyAsync(rb->h_data[c].p, rb->cols[c].data.p, (size_t)rb->n * 8, cudaMemcpyDeviceToHost, r.d2h));
+      if (!ind) TQ_CUDA(cudaMemcpyAsync(rb->h_data[c].p, rb->cols[c].data.p, (size_t)rb->n * 8, cudaMemcpyDeviceToHost, r.d2h));
       TQ_CUDA(cudaMemcpyAsync(rb->h_bm[c].p, rb->cols[c].bm.p, bitmap_bytes(rb->n), cudaMemcpyDeviceToHost, r.d2h));
+    }
+    if (ind) {
+      VarOut &v = rb->var[c];
+      TQ_TRY(v.h_bytes.reserve((size_t)v.total + 16));
+      if (v.total) TQ_CUDA(cudaMemcpyAsync(v.h_bytes.p, v.bytes.p, (size_t)v.total, cudaMemcpyDeviceToHost, r.d2h));
+      if (v.elem == 0) {
+        TQ_TRY(v.h_off.reserve((size_t)(rb->n + 1) * 8));
+        TQ_CUDA(cudaMemcpyAsync(v.h_off.p, v.off.p, (size_t)(rb->n + 1) * 8, cudaMemcpyDeviceToHost, r.d2h));
+      }
+      v.on_host = true;
     }
   }
   TQ_CUDA(cudaEventRecord(rb->ev_ready, r.d2h));
@@ -1868,6 +1946,7 @@ static int32_t finalize_pending(tq_join *j) {
   }
   pb.rb->n = (int64_t)produced;
   j->joined_rows_total += (int64_t)produced;
+  if (j->any_ind) TQ_TRY(materialize_indirect(j, pb.rb.get(), pb.cursor_slot));  // synchronises the compute stream
   if (pb.want_host) {
     TQ_CUDA(cudaStreamWaitEvent(r.d2h, pb.ev_k, 0));
     TQ_TRY(enqueue_d2h(j, pb.rb.get()));
@@ -1933,9 +2012,30 @@ static int32_t process_host_piece(tq_join *j, const tq_column *cols, int64_t row
   in.cols.resize(j->n_probe_cols);
   std::vector<DCol> view(j->n_probe_cols);
   if ((row0 & 7) != 0) { set_error("internal: unaligned host piece"); return TQ_ERR_INVALID_ARG; }
+  if (j->any_ind) in.store.resize(j->np_user);
   for (int c = 0; c < j->np_user; c++) {
     TQ_TRY(in.cols[c].data.reserve((size_t)rows * 8));
-    TQ_CUDA(cudaMemcpyAsync(in.cols[c].data.p, cols[c].data + row0 * 8, (size_t)rows * 8, cudaMemcpyHostToDevice, r.h2d));
+    if (j->p_ind[c]) {
+      // the cells go to this batch's side store; the join sees row ids 0..rows-1 (+ the column's NULL bitmap)
+      SideStore &st = in.store[c];
+      st.elem = j->p_elem[c];
+      st.n = rows;
+      if (st.elem == 4) {
+        st.base = 0;
+        TQ_TRY(st.bytes.reserve((size_t)rows * 4 + 16));
+        TQ_CUDA(cudaMemcpyAsync(st.bytes.p, cols[c].data + row0 * 4, (size_t)rows * 4, cudaMemcpyHostToDevice, r.h2d));
+      } else {
+        const int64_t b0 = cols[c].offsets[row0], b1 = cols[c].offsets[row0 + rows];
+        st.base = b0;
+        TQ_TRY(st.offsets.reserve((size_t)(rows + 1) * 8));
+        TQ_TRY(st.bytes.reserve((size_t)(b1 - b0) + 16));
+        TQ_CUDA(cudaMemcpyAsync(st.offsets.p, cols[c].offsets + row0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, r.h2d));
+        if (b1 > b0) TQ_CUDA(cudaMemcpyAsync(st.bytes.p, cols[c].data + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, r.h2d));
+      }
+      TQ_TRY(iota_u64(in.cols[c].data.as<uint64_t>(), rows, r.compute));
+    } else {
+      TQ_CUDA(cudaMemcpyAsync(in.cols[c].data.p, cols[c].data + row0 * 8, (size_t)rows * 8, cudaMemcpyHostToDevice, r.h2d));
+    }
     view[c].data = in.cols[c].data.as<uint64_t>();
     view[c].bm = nullptr;
     if (cols[c].null_bitmap) {
@@ -1966,6 +2066,10 @@ static int32_t flush_probe_staging(tq_join *j) {
     cols[c].data = j->p_host[c].data.as<uint8_t>();
     cols[c].null_bitmap = j->p_host[c].has_bm ? j->p_host[c].bm.as<uint8_t>() : nullptr;
     cols[c].offsets = nullptr;
+    if (j->p_ind[c]) {
+      cols[c].data = j->p_var[c].bytes.data();
+      cols[c].offsets = j->p_elem[c] == 0 ? j->p_var[c].off.data() : nullptr;
+    }
   }
   const uint8_t *sel = j->p_sel_any ? j->p_sel_host.data() : nullptr;
   // The staging buffers are reused right after this call, so the H2D copies must have completed.
@@ -1975,6 +2079,7 @@ static int32_t flush_probe_staging(tq_join *j) {
     if (e != cudaSuccess) st = cuda_fail(e, "sync h2d", __FILE__, __LINE__);
   }
   for (auto &h : j->p_host) h.reset();
+  for (int c = 0; c < j->np_user; c++) j->p_var[c].reset();
   j->p_sel_host.clear();
   j->p_sel_any = false;
   return st;
@@ -2001,12 +2106,18 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   const int hidden = d->n_keys > 1 ? 1 : 0;
   if (d->n_build_cols + hidden > MAXC || d->n_probe_cols + hidden > MAXC) { set_error("multi-column join keys need one spare column per side"); return TQ_ERR_INVALID_ARG; }
   for (int c = 0; c < d->n_build_cols; c++)
-    if (!type_ok(d->build_types[c])) { set_error("unsupport column type for encode %d", d->build_types[c]); return TQ_ERR_UNSUPPORTED_TYPE; }
+    if (!type_ok(d->build_types[c]) && !type_indirect(d->build_types[c])) { set_error("unsupport column type for encode %d", d->build_types[c]); return TQ_ERR_UNSUPPORTED_TYPE; }
   for (int c = 0; c < d->n_probe_cols; c++)
-    if (!type_ok(d->probe_types[c])) { set_error("unsupport column type for encode %d", d->probe_types[c]); return TQ_ERR_UNSUPPORTED_TYPE; }
-  for (int i = 0; i < d->n_keys; i++)
+    if (!type_ok(d->probe_types[c]) && !type_indirect(d->probe_types[c])) { set_error("unsupport column type for encode %d", d->probe_types[c]); return TQ_ERR_UNSUPPORTED_TYPE; }
+  for (int i = 0; i < d->n_keys; i++) {
     if (d->build_key_idx[i] < 0 || d->build_key_idx[i] >= d->n_build_cols || d->probe_key_idx[i] < 0 || d->probe_key_idx[i] >= d->n_probe_cols)
       return TQ_ERR_INVALID_ARG;
+    // join keys: the 8-byte types (FLOAT / var-len keys hit the reference's "unsupport column type" too, codec.go:235)
+    if (!type_ok(d->build_types[d->build_key_idx[i]]) || !type_ok(d->probe_types[d->probe_key_idx[i]])) {
+      set_error("unsupport column type for encode (join key column of type %d / %d)", d->build_types[d->build_key_idx[i]], d->probe_types[d->probe_key_idx[i]]);
+      return TQ_ERR_UNSUPPORTED_TYPE;
+    }
+  }
   // LeftOuter keeps the left child as the outer side, RightOuter the right child (builder.go:451-477)
   if (d->join_type == TQ_JOIN_LEFT_OUTER && d->outer_is_right) { set_error("left outer join needs outer_is_right == 0"); return TQ_ERR_INVALID_ARG; }
   if (d->join_type == TQ_JOIN_RIGHT_OUTER && !d->outer_is_right) { set_error("right outer join needs outer_is_right == 1"); return TQ_ERR_INVALID_ARG; }
@@ -2055,6 +2166,23 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
     }
   }
   {
+    const int bbase = j->outer_is_right ? 0 : j->n_probe_cols, pbase = j->outer_is_right ? j->n_build_cols : 0;
+    for (int c = 0; c < j->nb_user; c++)
+      if (type_indirect(j->build_types[c])) {
+        j->b_ind[c] = j->any_ind = true;
+        j->b_elem[c] = j->b_var[c].elem = (j->build_types[c] == TQ_TYPE_FLOAT32) ? 4 : 0;
+        j->out_side[bbase + c] = 1;
+        j->out_col[bbase + c] = c;
+      }
+    for (int c = 0; c < j->np_user; c++)
+      if (type_indirect(j->probe_types[c])) {
+        j->p_ind[c] = j->any_ind = true;
+        j->p_elem[c] = j->p_var[c].elem = (j->probe_types[c] == TQ_TYPE_FLOAT32) ? 4 : 0;
+        j->out_side[pbase + c] = 2;
+        j->out_col[pbase + c] = c;
+      }
+  }
+  {
     const int first_user = j->outer_is_right ? j->nb_user : j->np_user, first_int = j->outer_is_right ? j->n_build_cols : j->n_probe_cols;
     for (int u = 0; u < j->nb_user + j->np_user; u++) j->out_map.push_back(u < first_user ? u : u - first_user + first_int);
   }
@@ -2083,13 +2211,19 @@ int32_t tq_join_put_build(tq_join *j, const tq_column *cols, int32_t mem) {
   const int64_t rows = cols[0].length;
   if (rows < 0) return TQ_ERR_INVALID_ARG;
   for (int c = 0; c < j->nb_user; c++) {
+    const bool var = j->b_ind[c] && j->b_elem[c] == 0;
     if (cols[c].length != rows) { set_error("ragged build chunk"); return TQ_ERR_INVALID_ARG; }
-    if (cols[c].offsets) { set_error("unsupport column type for encode (var-len column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
-    if (rows && !cols[c].data) return TQ_ERR_INVALID_ARG;
+    if (!var && cols[c].offsets) { set_error("unsupport column type for encode (var-len data in fixed-width column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
+    if (var && !cols[c].offsets) { set_error("var-len column %d needs offsets", c); return TQ_ERR_INVALID_ARG; }
+    if (rows && !cols[c].data && !(var && cols[c].offsets[rows] == cols[c].offsets[0])) return TQ_ERR_INVALID_ARG;
+    if (j->b_ind[c] && mem != TQ_MEM_HOST) { set_error("FLOAT / var-len columns are accepted from host memory only"); return TQ_ERR_UNSUPPORTED_TYPE; }
   }
   if (rows == 0) return TQ_OK;
   if (mem == TQ_MEM_HOST) {
-    for (int c = 0; c < j->nb_user; c++) TQ_TRY(j->b_host[c].append(cols[c], rows));
+    for (int c = 0; c < j->nb_user; c++) {
+      if (j->b_ind[c]) { j->b_var[c].append(cols[c], rows); TQ_TRY(j->b_host[c].append_nulls(cols[c], rows)); }
+      else TQ_TRY(j->b_host[c].append(cols[c], rows));
+    }
   } else {
     j->b_dev_chunks.emplace_back(cols, cols + j->nb_user);
   }
@@ -2135,6 +2269,11 @@ int32_t tq_join_finalize_build(tq_join *j) {
     j->b_cols.resize(j->nb_user);
     for (int c = 0; c < j->nb_user; c++) {
       TQ_TRY(upload_col(j->b_host[c], j->b_cols[c], r.compute));
+      if (j->b_ind[c]) {  // the column the kernels see: row ids into the side store
+        TQ_TRY(iota_u64(j->b_cols[c].data.as<uint64_t>(), j->n_build, r.compute));
+        TQ_TRY(upload_store(j->b_var[c], j->b_store[c], r.compute));
+        j->b_var[c].reset();
+      }
       j->b_view[c].data = j->b_cols[c].data.as<uint64_t>();
       j->b_view[c].bm = j->b_host[c].has_bm ? j->b_cols[c].bm.as<uint32_t>() : nullptr;
     }
@@ -2168,9 +2307,12 @@ int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *sele
   const int64_t rows = cols[0].length;
   if (rows < 0) return TQ_ERR_INVALID_ARG;
   for (int c = 0; c < j->np_user; c++) {
+    const bool var = j->p_ind[c] && j->p_elem[c] == 0;
     if (cols[c].length != rows) { set_error("ragged probe chunk"); return TQ_ERR_INVALID_ARG; }
-    if (cols[c].offsets) { set_error("unsupport column type for encode (var-len column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
-    if (rows && !cols[c].data) return TQ_ERR_INVALID_ARG;
+    if (!var && cols[c].offsets) { set_error("unsupport column type for encode (var-len data in fixed-width column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
+    if (var && !cols[c].offsets) { set_error("var-len column %d needs offsets", c); return TQ_ERR_INVALID_ARG; }
+    if (rows && !cols[c].data && !(var && cols[c].offsets[rows] == cols[c].offsets[0])) return TQ_ERR_INVALID_ARG;
+    if (j->p_ind[c] && mem != TQ_MEM_HOST) { set_error("FLOAT / var-len columns are accepted from host memory only"); return TQ_ERR_UNSUPPORTED_TYPE; }
   }
   if (rows == 0) return TQ_OK;
   Runtime &r = rt();
@@ -2205,7 +2347,10 @@ int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *sele
   }
   if (j->p_host[0].n + rows > j->batch_rows) TQ_TRY(flush_probe_staging(j));
   const int64_t before = j->p_host[0].n;
-  for (int c = 0; c < j->np_user; c++) TQ_TRY(j->p_host[c].append(cols[c], rows));
+  for (int c = 0; c < j->np_user; c++) {
+    if (j->p_ind[c]) { j->p_var[c].append(cols[c], rows); TQ_TRY(j->p_host[c].append_nulls(cols[c], rows)); }
+    else TQ_TRY(j->p_host[c].append(cols[c], rows));
+  }
   if (selected && !j->p_sel_any) { j->p_sel_host.assign((size_t)before, 1); j->p_sel_any = true; }
   if (j->p_sel_any) {
     if (selected) j->p_sel_host.insert(j->p_sel_host.end(), selected, selected + rows);
@@ -2226,6 +2371,63 @@ int32_t tq_join_probe_eof(tq_join *j) {
   return TQ_OK;
 }
 
+// Make j->host_cur the result batch the next rows come from (waiting / copying as needed).  *have == 0: no rows now
+// (*eof tells whether the stream has ended).
+static int32_t join_current_batch(tq_join *j, int64_t max_rows, int *have, int32_t *eof) {
+  Runtime &r = rt();
+  *have = 0;
+  for (;;) {
+    if (j->host_cur && j->host_cur_pos < j->host_cur->n) break;
+    if (j->host_cur) { recycle(j, std::move(j->host_cur)); j->host_cur_pos = 0; }
+    // The batch in flight is only waited for at end of input: until then "no rows yet" means "feed more", so the
+    // D2H of batch i overlaps the H2D + kernels of batch i+1.
+    if (j->results.empty() && j->probe_eof) TQ_TRY(finalize_pending(j));
+    if (j->results.empty()) {
+      *eof = j->probe_eof ? 1 : 0;
+      return TQ_OK;
+    }
+    j->host_cur = std::move(j->results.front());
+    j->results.pop_front();
+    j->host_cur_pos = 0;
+    if (!j->host_cur->on_host) {
+      // Large consumer buffers: copy straight from HBM into the caller's columns (no staging, no CPU memcpy).
+      const bool direct = !j->any_ind && max_rows >= (1 << 18) && (max_rows & 7) == 0;
+      if (direct) { TQ_CUDA(cudaStreamSynchronize(r.compute)); break; }
+      TQ_CUDA(cudaStreamSynchronize(r.compute));
+      TQ_TRY(enqueue_d2h(j, j->host_cur.get()));
+    }
+    TQ_CUDA(cudaEventSynchronize(j->host_cur->ev_ready));
+  }
+  *have = 1;
+  return TQ_OK;
+}
+
+int32_t tq_join_next_bytes(tq_join *j, int64_t max_rows, int64_t *bytes_per_col) {
+  if (!j || !bytes_per_col || max_rows <= 0) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(ensure_init());
+  if (j->state == tq_join::BUILDING) { set_error("next before finalize_build"); return TQ_ERR_STATE; }
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  const int ncols = j->nb_user + j->np_user;
+  for (int c = 0; c < ncols; c++) bytes_per_col[c] = 0;
+  int have = 0;
+  int32_t eof = 0;
+  TQ_TRY(join_current_batch(j, max_rows, &have, &eof));
+  if (!have) return TQ_OK;
+  ResultBatch *rb = j->host_cur.get();
+  const int64_t take = (rb->n - j->host_cur_pos) < max_rows ? (rb->n - j->host_cur_pos) : max_rows;
+  for (int c = 0; c < ncols; c++) {
+    const int ic = j->out_map[c];
+    if (!j->out_side[ic]) bytes_per_col[c] = take * 8;
+    else if (rb->var[ic].elem == 4) bytes_per_col[c] = take * 4;
+    else {
+      const int64_t *off = rb->var[ic].h_off.as<int64_t>() + j->host_cur_pos;
+      bytes_per_col[c] = off[take] - off[0];
+    }
+  }
+  return TQ_OK;
+}
+
 int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof) {
   if (!j || !out_cols || !n_rows || !eof || max_rows <= 0) return TQ_ERR_INVALID_ARG;
   TQ_TRY(ensure_init());
@@ -2235,33 +2437,21 @@ int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t 
   Runtime &r = rt();
   std::lock_guard<std::recursive_mutex> lk(r.mu);
   const int ncols = j->nb_user + j->np_user;  // hidden key columns stay behind (out_map)
-  for (;;) {
-    if (j->host_cur && j->host_cur_pos < j->host_cur->n) break;
-    if (j->host_cur) { recycle(j, std::move(j->host_cur)); j->host_cur_pos = 0; }
-    // The batch in flight is only waited for at end of input: until then "no rows yet" means "feed more", so the
-    // D2H of batch i overlaps the H2D + kernels of batch i+1.
-    if (j->results.empty() && j->probe_eof) TQ_TRY(finalize_pending(j));
-    if (j->results.empty()) {
-      *eof = j->probe_eof ? 1 : 0;
-      for (int c = 0; c < ncols; c++) out_cols[c].length = 0;
-      return TQ_OK;
-    }
-    j->host_cur = std::move(j->results.front());
-    j->results.pop_front();
-    j->host_cur_pos = 0;
-    if (!j->host_cur->on_host) {
-      // Large consumer buffers: copy straight from HBM into the caller's columns (no staging, no CPU memcpy).
-      const bool direct = max_rows >= (1 << 18) && (max_rows & 7) == 0;
-      if (direct) { TQ_CUDA(cudaStreamSynchronize(r.compute)); break; }
-      TQ_CUDA(cudaStreamSynchronize(r.compute));
-      TQ_TRY(enqueue_d2h(j, j->host_cur.get()));
-    }
-    TQ_CUDA(cudaEventSynchronize(j->host_cur->ev_ready));
+  int have = 0;
+  TQ_TRY(join_current_batch(j, max_rows, &have, eof));
+  if (!have) {
+    for (int c = 0; c < ncols; c++) out_cols[c].length = 0;
+    return TQ_OK;
   }
   ResultBatch *rb = j->host_cur.get();
   const int64_t take = (rb->n - j->host_cur_pos) < max_rows ? (rb->n - j->host_cur_pos) : max_rows;
-  for (int c = 0; c < ncols; c++)
-    if (!out_cols[c].data || !out_cols[c].null_bitmap) { set_error("output column %d needs data and null_bitmap buffers", c); return TQ_ERR_INVALID_ARG; }
+  for (int c = 0; c < ncols; c++) {
+    const bool var = j->out_side[j->out_map[c]] && rb->var[j->out_map[c]].elem == 0;
+    if (!out_cols[c].null_bitmap || (!out_cols[c].data && !var) || (var && !out_cols[c].offsets)) {
+      set_error("output column %d needs data and null_bitmap buffers (and offsets for a var-len column)", c);
+      return TQ_ERR_INVALID_ARG;
+    }
+  }
   if (!rb->on_host) {
     if ((j->host_cur_pos & 7) != 0) { set_error("internal: unaligned direct result copy"); return TQ_ERR_STATE; }
     for (int c = 0; c < ncols; c++) {
@@ -2280,7 +2470,19 @@ int32_t tq_join_next(tq_join *j, int64_t max_rows, tq_column *out_cols, int64_t 
   }
   for (int c = 0; c < ncols; c++) {
     const int ic = j->out_map[c];
-    memcpy(out_cols[c].data, rb->h_data[ic].as<uint8_t>() + j->host_cur_pos * 8, (size_t)take * 8);
+    if (j->out_side[ic]) {
+      // FLOAT: 4-byte slots; var-len: offsets rebased to 0 + the cells' bytes (chunk.Column layout, column.go:28-34)
+      const VarOut &v = rb->var[ic];
+      if (v.elem == 4) memcpy(out_cols[c].data, v.h_bytes.as<uint8_t>() + j->host_cur_pos * 4, (size_t)take * 4);
+      else {
+        const int64_t *off = v.h_off.as<int64_t>() + j->host_cur_pos;
+        const int64_t b0 = off[0];
+        for (int64_t i = 0; i <= take; i++) out_cols[c].offsets[i] = off[i] - b0;
+        if (off[take] > b0) memcpy(out_cols[c].data, v.h_bytes.as<uint8_t>() + b0, (size_t)(off[take] - b0));
+      }
+    } else {
+      memcpy(out_cols[c].data, rb->h_data[ic].as<uint8_t>() + j->host_cur_pos * 8, (size_t)take * 8);
+    }
     host_bitmap_extract(out_cols[c].null_bitmap, rb->h_bm[ic].as<uint8_t>(), j->host_cur_pos, take);
     out_cols[c].length = take;
   }
@@ -2308,9 +2510,14 @@ int32_t tq_join_next_device(tq_join *j, tq_column *out_cols, int64_t *n_rows, in
   const int ncols = j->nb_user + j->np_user;
   for (int c = 0; c < ncols; c++) {
     out_cols[c].length = j->lent->n;
-    out_cols[c].data = j->lent->cols[j->out_map[c]].data.as<uint8_t>();
-    out_cols[c].null_bitmap = j->lent->cols[j->out_map[c]].bm.as<uint8_t>();
+    const int ic = j->out_map[c];
+    out_cols[c].data = j->lent->cols[ic].data.as<uint8_t>();
+    out_cols[c].null_bitmap = j->lent->cols[ic].bm.as<uint8_t>();
     out_cols[c].offsets = nullptr;
+    if (j->out_side[ic]) {  // gathered FLOAT / var-len column, device resident
+      out_cols[c].data = j->lent->var[ic].bytes.as<uint8_t>();
+      if (j->lent->var[ic].elem == 0) out_cols[c].offsets = j->lent->var[ic].off.as<int64_t>();
+    }
   }
   *n_rows = j->lent->n;
   return TQ_OK;

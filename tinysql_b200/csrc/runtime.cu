@@ -408,6 +408,12 @@ int32_t tq_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes) {
   TQ_CUDA(cudaStreamSynchronize(rt().compute));
   return TQ_OK;
 }
+int32_t tq_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes) {
+  TQ_TRY(ensure_init());
+  TQ_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, rt().compute));
+  TQ_CUDA(cudaStreamSynchronize(rt().compute));
+  return TQ_OK;
+}
 int32_t tq_memset_device(void *dst_dev, int32_t byte_value, size_t bytes) {
   TQ_TRY(ensure_init());
   TQ_CUDA(cudaMemsetAsync(dst_dev, byte_value, bytes, rt().compute));

@@ -253,7 +253,78 @@ def distributed_join(build_cols, probe_cols, world, rank, partition_fn, local_jo
     return local_join_fn(b_recv, p_recv)
 
 
+def distributed_agg(cols, world, rank, partial_fn, partition_fn, final_fn, group=None):
+    """The reference's partial -> shuffle -> final HashAgg (executor/aggregate.go:96-133,352-356,424-457) across ranks:
+    partial_fn(cols) -> partial rows as a list of int64 tensors, GROUP BY key first (one row per LOCAL group:
+    rows/world -> <= NDV rows, so the exchange moves groups, not input rows); partition_fn as in distributed_join
+    (same key -> rank rule); final_fn(received partial rows) -> this rank's final groups (MergePartialResult)."""
+    partials = partial_fn(cols)
+    part, off = partition_fn(partials, world)
+    recv, _ = exchange(part, off, world, rank, group)
+    return final_fn(recv)
+
+
 # ---------------------------------------------------------------------------------------------- GPU plumbing
+def gpu_agg_fns(lib, L, types, group_col, funcs, est_groups=0):
+    """(partial_fn, final_fn) for distributed_agg on device-resident NOT NULL int64/float64 columns: Partial1 handle ->
+    tq_agg_export_partial; Final handle <- tq_agg_merge_partial.  Columns are declared TQ_TYPE_NOT_NULL: the partial
+    states then carry no NULLs, so the exchange moves plain 8-byte columns (nullable inputs: merge locally instead)."""
+    def make():
+        it = (C.c_int32 * len(types))(*[t | L.TQ_TYPE_NOT_NULL for t in types])
+        gb = (C.c_int32 * 1)(group_col)
+        fa = (L.TQAggFunc * len(funcs))(*[L.TQAggFunc(f, a) for f, a in funcs])
+        d = L.TQAggDesc(len(types), it, 1, gb, len(funcs), fa, est_groups)
+        h = C.c_void_p()
+        L.check(lib.tq_agg_create(C.byref(d), C.byref(h)))
+        return h, (it, gb, fa)
+
+    def partial_fn(cols):
+        torch.cuda.synchronize()   # the library works on its own stream
+        h, keep = make()
+        try:
+            n = int(cols[0].numel())
+            if n:
+                L.check(lib.tq_agg_put(h, _tq_cols(L, cols, n), L.TQ_MEM_DEVICE))
+            width = C.c_int32(0)
+            L.check(lib.tq_agg_partial_width(h, C.byref(width)))
+            out = (L.TQColumn * width.value)()
+            rows = C.c_int64(0)
+            L.check(lib.tq_agg_export_partial(h, out, C.byref(rows)))
+            # the lent arrays die with the handle: copy them into tensors the exchange can own
+            res = []
+            for c in range(width.value):
+                t = torch.empty(rows.value, dtype=torch.int64, device=cols[0].device)
+                if rows.value:
+                    torch.cuda.current_stream().synchronize()
+                    L.check(lib.tq_memcpy_d2d(t.data_ptr(), out[c].data, rows.value * 8))
+                res.append(t)
+        finally:
+            lib.tq_agg_destroy(h)
+        return res
+
+    def final_fn(recv):
+        torch.cuda.synchronize()
+        h, keep = make()
+        try:
+            n = int(recv[0].numel())
+            if n:
+                L.check(lib.tq_agg_merge_partial(h, _tq_cols(L, recv, n), L.TQ_MEM_DEVICE))
+            L.check(lib.tq_agg_eof(h))
+            out = (L.TQColumn * len(funcs))()
+            rows, eof = C.c_int64(0), C.c_int32(0)
+            L.check(lib.tq_agg_next_device(h, out, C.byref(rows), C.byref(eof)))
+            from .chunk import device_to_host
+            res = []
+            for i in range(len(funcs)):
+                t = C.c_int32(0)
+                L.check(lib.tq_agg_output_type(h, i, C.byref(t)))
+                res.append(device_to_host(t.value, out[i].data, out[i].null_bitmap, rows.value))
+        finally:
+            lib.tq_agg_destroy(h)
+        return res
+    return partial_fn, final_fn
+
+
 def _tq_cols(L, tensors, n):
     arr = (L.TQColumn * len(tensors))()
     for i, t in enumerate(tensors):

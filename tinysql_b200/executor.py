@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .chunk import (FLOAT64, INT64, MAX_CHUNK_SIZE, UINT64, Chunk, Column, DeviceColumn, device_to_host, tq_array)
+from .chunk import (BYTES, FLOAT64, INT64, MAX_CHUNK_SIZE, UINT64, Chunk, Column, DeviceColumn, VarColumn, device_to_host, tq_array)
 
 INNER_JOIN, LEFT_OUTER_JOIN, RIGHT_OUTER_JOIN = 0, 1, 2  # planner/core/logical_plans.go:52-57
 AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MAX, AGG_MIN, AGG_FIRSTROW = range(6)
@@ -30,7 +30,7 @@ class MockDataSource:
 
     def Next(self):
         if self.pos >= len(self.chunks):
-            return Chunk([Column(t, np.zeros(0)) for t in self.types])
+            return Chunk([Column(t, [] if t == BYTES else np.zeros(0)) for t in self.types])
         self.pos += 1
         return self.chunks[self.pos - 1]
 
@@ -90,10 +90,19 @@ class HashJoinExec:
         if not self.prepared:
             self._build()
             self.prepared = True
-        out = [Column.empty(t, req) for t in self.types]
+        has_var = BYTES in self.types
+        out = [VarColumn.empty(BYTES, req) if t == BYTES else Column.empty(t, req) for t in self.types]
         arr = tq_array(out, req)
         n, eof = C.c_int64(0), C.c_int32(0)
         while True:
+            if has_var:
+                # size the var-len result buffers for this call (the *_next_size query of the ownership contract)
+                need = (C.c_int64 * len(self.types))()
+                L.check(lib.tq_join_next_bytes(self.handle, req, need))
+                for i, t in enumerate(self.types):
+                    if t == BYTES:
+                        out[i] = VarColumn.empty(BYTES, req, int(need[i]))
+                arr = tq_array(out, req)
             L.check(lib.tq_join_next(self.handle, req, arr, C.byref(n), C.byref(eof)))
             if n.value > 0 or eof.value:
                 break
@@ -107,7 +116,7 @@ class HashJoinExec:
                 sel = np.ascontiguousarray(self.outer_filter(chk), dtype=np.uint8)
             L.check(lib.tq_join_put_probe(self.handle, tq_array(chk.cols), sel.ctypes.data if sel is not None else None, L.TQ_MEM_HOST))
         k = n.value
-        return Chunk([Column(t, c.values[:k], c.not_null()[:k]) for t, c in zip(self.types, out)])
+        return Chunk([c.head(k) if t == BYTES else Column(t, c.values[:k], c.not_null()[:k]) for t, c in zip(self.types, out)])
 
     def Close(self):
         if self.handle is not None:
