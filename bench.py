@@ -145,12 +145,12 @@ class JoinBench:
         self.d_p = [DeviceColumn.from_host(Column(INT64, self.pk)), DeviceColumn.from_host(Column(INT64, self.pv))]
         self.INT64 = INT64
 
-    def desc(self, batch=0):
+    def desc(self, batch=0, flags=0):
         L = self.L
         t = (C.c_int32 * 2)(1, 1)
         k = (C.c_int32 * 1)(0)
         self._keep = (t, k)
-        return L.TQJoinDesc(0, 1, 2, t, 2, t, 1, k, k, batch)
+        return L.TQJoinDesc(0, 1, 2, t, 2, t, 1, k, k, batch, flags)
 
     def step_device(self):
         """build + probe with inputs resident in HBM; returns (joined rows, probe kernel ns, build ns)."""
@@ -200,7 +200,9 @@ class JoinBench:
         """Open/build/probe/Next-until-EOF/Close through the C-ABI with HOST buffers."""
         L, lib = self.L, self.lib
         h = C.c_void_p()
-        d = self.desc(batch=1 << 23)
+        # the host buffers are C-owned pinned memory (tq_pinned_alloc) that nobody rewrites during the step: declare them
+        # stable so the upload of piece i+1 overlaps the download of result i (both still inside the timed region)
+        d = self.desc(batch=1 << 23, flags=L.TQ_JOIN_STABLE_INPUT)
         L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
 
         def cols(bufs, n):

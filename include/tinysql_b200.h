@@ -200,7 +200,15 @@ typedef struct tq_join_desc {
   const int32_t *build_key_idx; /* innerKeys[i].Index                                         */
   const int32_t *probe_key_idx; /* outerKeys[i].Index                                         */
   int64_t probe_batch_rows;   /* device batch size the ≤1024-row chunks are accumulated into; 0 = default */
+  int32_t flags;              /* TQ_JOIN_STABLE_INPUT or 0                                    */
 } tq_join_desc;
+
+/* tq_join_desc.flags.  STABLE_INPUT: every host buffer passed to tq_join_put_build / tq_join_put_probe stays valid and
+ * unmodified until the handle is destroyed (the util/chunk bridge hands out C-owned pinned columns and does not recycle
+ * them while the join runs).  Large host columns are then uploaded asynchronously: the call returns while the DMA is in
+ * flight, so the upload of batch i+1 overlaps the result download of batch i.  Without the flag every call finishes
+ * reading its arguments before it returns (the cgo pointer rule). */
+enum { TQ_JOIN_STABLE_INPUT = 1 };
 
 typedef struct tq_join tq_join;
 

@@ -285,6 +285,24 @@ def test_join_fast_kernel_shapes(lib, nbc, npc):
     assert_same_multiset(got, want)
 
 
+@pytest.mark.parametrize("stable", [False, True])
+def test_join_large_host_chunks_direct_upload(lib, stable):
+    """build and probe sides arriving as LARGE host columns (>= 2^18 rows per chunk): the build data goes straight to HBM
+    (no pinned staging copy; the device columns grow twice here), probe pieces stream from the caller's buffers; with
+    TQ_JOIN_STABLE_INPUT the uploads are not awaited before the call returns"""
+    rng = np.random.default_rng(19)
+    nb, npr = 700000, 2000000
+    bcols = [gen_col(rng, INT64, nb, 0.02, 0, 600000), gen_col(rng, INT64, nb, 0.1), gen_col(rng, FLOAT64, nb, 0.1)]
+    pcols = [gen_col(rng, INT64, npr, 0.1), gen_col(rng, INT64, npr, 0.03, 0, 800000)]
+    inner, outer = MockDataSource([INT64, INT64, FLOAT64], bcols, 1 << 18), MockDataSource([INT64, INT64], pcols, 1 << 19)
+    e = HashJoinExec(outer, inner, [1], [0], LEFT_OUTER_JOIN, False, None, 1 << 19, max_chunk_size=1 << 18, stable_input=stable)
+    e.Open()
+    got = e.drain()
+    e.Close()
+    want = O.hash_join(LEFT_OUTER_JOIN, False, [INT64, INT64, FLOAT64], bcols, [INT64, INT64], pcols, [0], [1])
+    assert_same_multiset(got, want)
+
+
 def test_join_duplicates_large_segments(lib):
     # 100 x 100 duplicate join (join_test.go:175-182) and a >32-row duplicate segment (bitonic path)
     b = [Column(INT64, [7] * 100 + [8] * 3), Column(INT64, list(range(103)))]

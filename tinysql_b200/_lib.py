@@ -19,7 +19,7 @@ class TQJoinDesc(C.Structure):
     _fields_ = [("join_type", C.c_int32), ("outer_is_right", C.c_int32), ("n_build_cols", C.c_int32),
                 ("build_types", C.POINTER(C.c_int32)), ("n_probe_cols", C.c_int32), ("probe_types", C.POINTER(C.c_int32)),
                 ("n_keys", C.c_int32), ("build_key_idx", C.POINTER(C.c_int32)), ("probe_key_idx", C.POINTER(C.c_int32)),
-                ("probe_batch_rows", C.c_int64)]
+                ("probe_batch_rows", C.c_int64), ("flags", C.c_int32)]
 
 
 class TQAggFunc(C.Structure):
@@ -88,6 +88,7 @@ TQ_ERR_OVERFLOW_DOUBLE, TQ_ERR_DIVISION_BY_ZERO, TQ_ERR_CUDA, TQ_ERR_NO_DEVICE, 
 TQ_TYPE_INT64, TQ_TYPE_UINT64, TQ_TYPE_FLOAT64, TQ_TYPE_FLOAT32, TQ_TYPE_BYTES = 1, 2, 3, 4, 5
 TQ_TYPE_NOT_NULL = 0x100
 TQ_MEM_HOST, TQ_MEM_DEVICE = 0, 1
+TQ_JOIN_STABLE_INPUT = 1
 
 _lib = None
 

@@ -1286,7 +1286,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part(const ProbeParams 
 // Pinned accumulation of ≤1024-row host chunks into one column.
 struct HostAccum {
   PinBuf data, bm;
-  int64_t n = 0, cap = 0;
+  int64_t n = 0, cap = 0, bm_cap = 0;
   bool has_bm = false;
   int32_t ensure(int64_t rows) {
     if (rows <= cap) return TQ_OK;
@@ -1302,6 +1302,7 @@ struct HostAccum {
     std::swap(data.p, nd.p); std::swap(data.cap, nd.cap);
     std::swap(bm.p, nb.p); std::swap(bm.cap, nb.cap);
     cap = ncap;
+    bm_cap = ncap;
     return TQ_OK;
   }
   int32_t append(const tq_column &c, int64_t rows) {
@@ -1314,7 +1315,15 @@ struct HostAccum {
   }
   // indirect (FLOAT / var-len) columns: only the NULL bitmap is staged here, the cells go to a HostVarAccum
   int32_t append_nulls(const tq_column &c, int64_t rows) {
-    TQ_TRY(ensure(n + rows));
+    if (n + rows > bm_cap) {  // bitmap-only growth (no 8-byte slots behind it)
+      int64_t ncap = bm_cap ? bm_cap : 4096;
+      while (ncap < n + rows) ncap *= 2;
+      PinBuf nb;
+      TQ_TRY(nb.reserve(bitmap_alloc_bytes(ncap)));
+      if (n) memcpy(nb.p, bm.p, bitmap_bytes(n));
+      std::swap(bm.p, nb.p); std::swap(bm.cap, nb.cap);
+      bm_cap = ncap;
+    }
     host_bitmap_append(bm.as<uint8_t>(), n, c.null_bitmap, rows);
     if (c.null_bitmap) has_bm = true;
     n += rows;
@@ -1414,6 +1423,12 @@ struct tq_join {
   std::vector<std::vector<tq_column>> b_dev_chunks;  // borrowed device chunks
   int build_mem = -1;
   int64_t n_build = 0;
+  int flags = 0;                          // TQ_JOIN_* flags of the descriptor
+  // large host build chunks skip the pinned staging copy: data goes straight to these device columns (H2D from the
+  // caller's buffer inside the call), only the NULL bitmaps are staged on the host
+  bool b_direct = false;
+  std::vector<DevBuf> b_ddata;
+  int64_t b_dcap = 0;
   std::vector<DevColBuf> b_cols;          // materialised inner side (owned) ...
   std::vector<DCol> b_view;               // ... or borrowed view
   DevBuf csr_rows, csr_mask;              // build rows in CSR order, row-major (+ per-row NOT-NULL mask)
@@ -1512,7 +1527,8 @@ static int32_t upload_col(const HostAccum &h, DevColBuf &d, cudaStream_t s) {
   TQ_TRY(d.data.reserve((size_t)(h.n ? h.n : 1) * 8));
   TQ_TRY(d.bm.reserve(bitmap_alloc_bytes(h.n)));
   if (h.n) {
-    TQ_CUDA(cudaMemcpyAsync(d.data.p, h.data.p, (size_t)h.n * 8, cudaMemcpyHostToDevice, s));
+    // (bitmap-only accumulators — row-id columns — have no staged data: the caller fills d.data itself)
+    if (h.data.p) TQ_CUDA(cudaMemcpyAsync(d.data.p, h.data.p, (size_t)h.n * 8, cudaMemcpyHostToDevice, s));
     TQ_CUDA(cudaMemcpyAsync(d.bm.p, h.bm.p, bitmap_bytes(h.n), cudaMemcpyHostToDevice, s));
   }
   return TQ_OK;
@@ -2136,6 +2152,7 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   j->n_build_cols = d->n_build_cols + hidden;
   j->n_probe_cols = d->n_probe_cols + hidden;
   j->n_keys = d->n_keys;
+  j->flags = d->flags;
   for (int c = 0; c < d->n_build_cols; c++) j->build_types[c] = d->build_types[c];
   for (int c = 0; c < d->n_probe_cols; c++) j->probe_types[c] = d->probe_types[c];
   // key comparison across types (codec.go:219-231,363-382): a DOUBLE never equals an integer key; signed vs unsigned
@@ -2220,9 +2237,37 @@ int32_t tq_join_put_build(tq_join *j, const tq_column *cols, int32_t mem) {
   }
   if (rows == 0) return TQ_OK;
   if (mem == TQ_MEM_HOST) {
-    for (int c = 0; c < j->nb_user; c++) {
-      if (j->b_ind[c]) { j->b_var[c].append(cols[c], rows); TQ_TRY(j->b_host[c].append_nulls(cols[c], rows)); }
-      else TQ_TRY(j->b_host[c].append(cols[c], rows));
+    if (j->n_build == 0) {
+      j->b_direct = rows >= (1 << 18);
+      for (int c = 0; c < j->nb_user; c++) if (j->b_ind[c]) j->b_direct = false;
+    }
+    if (j->b_direct) {
+      Runtime &r = rt();
+      std::lock_guard<std::recursive_mutex> lk(r.mu);
+      const int64_t need = j->n_build + rows;
+      if (need > j->b_dcap) {
+        const int64_t ncap = need > j->b_dcap * 2 ? need : j->b_dcap * 2;
+        j->b_ddata.resize(j->nb_user);
+        for (int c = 0; c < j->nb_user; c++) {
+          DevBuf nb;
+          TQ_TRY(nb.reserve((size_t)ncap * 8));
+          if (j->n_build) TQ_CUDA(cudaMemcpyAsync(nb.p, j->b_ddata[c].p, (size_t)j->n_build * 8, cudaMemcpyDeviceToDevice, r.compute));
+          TQ_CUDA(cudaStreamSynchronize(r.compute));  // the old block goes back to the allocator below
+          j->b_ddata[c] = std::move(nb);
+        }
+        j->b_dcap = ncap;
+      }
+      for (int c = 0; c < j->nb_user; c++) {
+        TQ_CUDA(cudaMemcpyAsync(j->b_ddata[c].as<uint8_t>() + j->n_build * 8, cols[c].data, (size_t)rows * 8, cudaMemcpyHostToDevice, r.h2d));
+        TQ_TRY(j->b_host[c].append_nulls(cols[c], rows));
+      }
+      // cgo pointers are only valid during the call — unless the caller declared its input buffers stable
+      if (!(j->flags & TQ_JOIN_STABLE_INPUT)) TQ_CUDA(cudaStreamSynchronize(r.h2d));
+    } else {
+      for (int c = 0; c < j->nb_user; c++) {
+        if (j->b_ind[c]) { j->b_var[c].append(cols[c], rows); TQ_TRY(j->b_host[c].append_nulls(cols[c], rows)); }
+        else TQ_TRY(j->b_host[c].append(cols[c], rows));
+      }
     }
   } else {
     j->b_dev_chunks.emplace_back(cols, cols + j->nb_user);
@@ -2268,7 +2313,15 @@ int32_t tq_join_finalize_build(tq_join *j) {
   } else {
     j->b_cols.resize(j->nb_user);
     for (int c = 0; c < j->nb_user; c++) {
-      TQ_TRY(upload_col(j->b_host[c], j->b_cols[c], r.compute));
+      if (j->b_direct) {
+        // data is already in HBM (put_build); only the staged NULL bitmap is uploaded
+        TQ_CUDA(cudaStreamSynchronize(r.h2d));
+        j->b_cols[c].data = std::move(j->b_ddata[c]);
+        TQ_TRY(j->b_cols[c].bm.reserve(bitmap_alloc_bytes(j->n_build)));
+        TQ_CUDA(cudaMemcpyAsync(j->b_cols[c].bm.p, j->b_host[c].bm.p, bitmap_bytes(j->n_build), cudaMemcpyHostToDevice, r.compute));
+      } else {
+        TQ_TRY(upload_col(j->b_host[c], j->b_cols[c], r.compute));
+      }
       if (j->b_ind[c]) {  // the column the kernels see: row ids into the side store
         TQ_TRY(iota_u64(j->b_cols[c].data.as<uint64_t>(), j->n_build, r.compute));
         TQ_TRY(upload_store(j->b_var[c], j->b_store[c], r.compute));
@@ -2342,7 +2395,9 @@ int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *sele
       const int64_t piece = rows - row0 < j->batch_rows ? rows - row0 : j->batch_rows;
       TQ_TRY(process_host_piece(j, cols, row0, piece, selected, /*eager_d2h=*/false));
     }
-    TQ_CUDA(cudaStreamSynchronize(r.h2d));  // caller may reuse its buffers on return
+    // the caller may reuse its buffers on return — unless it declared them stable (TQ_JOIN_STABLE_INPUT): then the
+    // upload keeps running while the caller drains the previous batch (H2D and D2H overlap on the full-duplex link)
+    if (!(j->flags & TQ_JOIN_STABLE_INPUT)) TQ_CUDA(cudaStreamSynchronize(r.h2d));
     return TQ_OK;
   }
   if (j->p_host[0].n + rows > j->batch_rows) TQ_TRY(flush_probe_staging(j));
@@ -2391,9 +2446,10 @@ static int32_t join_current_batch(tq_join *j, int64_t max_rows, int *have, int32
     j->host_cur_pos = 0;
     if (!j->host_cur->on_host) {
       // Large consumer buffers: copy straight from HBM into the caller's columns (no staging, no CPU memcpy).
+      // (a queued batch is complete: finalize_pending waited for its kernels — no stream-wide sync here, so the copy
+      // below runs while the NEXT batch is still uploading / probing)
       const bool direct = !j->any_ind && max_rows >= (1 << 18) && (max_rows & 7) == 0;
-      if (direct) { TQ_CUDA(cudaStreamSynchronize(r.compute)); break; }
-      TQ_CUDA(cudaStreamSynchronize(r.compute));
+      if (direct) break;
       TQ_TRY(enqueue_d2h(j, j->host_cur.get()));
     }
     TQ_CUDA(cudaEventSynchronize(j->host_cur->ev_ready));

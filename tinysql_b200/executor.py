@@ -46,12 +46,13 @@ class HashJoinExec:
     """executor/join.go:31-146.  inner = build side, outer = probe side; output = left ++ right."""
 
     def __init__(self, outer_exec, inner_exec, outer_keys, inner_keys, join_type=INNER_JOIN, outer_is_right=False,
-                 outer_filter=None, probe_batch_rows=0, max_chunk_size=MAX_CHUNK_SIZE):
+                 outer_filter=None, probe_batch_rows=0, max_chunk_size=MAX_CHUNK_SIZE, stable_input=False):
         self.outer, self.inner = outer_exec, inner_exec
         self.outer_keys, self.inner_keys = list(outer_keys), list(inner_keys)
         self.join_type, self.outer_is_right = join_type, outer_is_right
         self.outer_filter = outer_filter  # callable(chunk) -> selected bytes (expression.VectorizedFilter result)
         self.probe_batch_rows = probe_batch_rows
+        self.stable_input = stable_input  # TQ_JOIN_STABLE_INPUT: the children keep every chunk alive and unmodified until Close
         self.max_chunk_size = max_chunk_size
         self.handle = None
         self.prepared = False
@@ -66,7 +67,7 @@ class HashJoinExec:
         bt, pt = _i32arr(self.inner.types), _i32arr(self.outer.types)
         bk, pk = _i32arr(self.inner_keys), _i32arr(self.outer_keys)
         d = L.TQJoinDesc(self.join_type, 1 if self.outer_is_right else 0, len(self.inner.types), bt, len(self.outer.types), pt,
-                         len(self.inner_keys), bk, pk, self.probe_batch_rows)
+                         len(self.inner_keys), bk, pk, self.probe_batch_rows, L.TQ_JOIN_STABLE_INPUT if self.stable_input else 0)
         h = C.c_void_p()
         L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
         self.handle = h
