@@ -120,6 +120,16 @@ int32_t tq_vec_compare_int(int32_t op, int64_t n, const tq_column *a, int32_t a_
 /* builtin{LT..NE}RealSig.vecEvalInt — expression/builtin_compare_vec_generated.go:23-473. */
 int32_t tq_vec_compare_real(int32_t op, int64_t n, const tq_column *a, const tq_column *b,
                             tq_column *out, int32_t mem);
+/* String (var-len column) builtins.  a / b: offsets + data (+ bitmap); out: int64 column.
+ *   op TQ_CMP_LT..TQ_CMP_NE  builtin{LT..NE}StringSig.vecEvalInt — expression/builtin_compare_vec_generated.go:65-555
+ *   op TQ_STR_STRCMP         builtinStrcmpSig.vecEvalInt (-1 / 0 / 1) — expression/builtin_string_vec.go:52-83
+ * Order is types.CompareString (types/compare.go:115-123): byte-wise.  NULL iff either argument is NULL. */
+enum { TQ_STR_STRCMP = 6 };
+int32_t tq_vec_compare_string(int32_t op, int64_t n, const tq_column *a, const tq_column *b, tq_column *out, int32_t mem);
+/*   TQ_STR_LENGTH  builtinLengthSig: byte length (expression/builtin_string.go:75-81; the vectorized body is a course stub)
+ *   TQ_STR_ISNULL  builtinStringIsNullSig.vecEvalInt — expression/builtin_string_vec.go:21-42 (never NULL) */
+enum { TQ_STR_LENGTH = 0, TQ_STR_ISNULL = 1 };
+int32_t tq_vec_string_unary(int32_t op, int64_t n, const tq_column *a, tq_column *out, int32_t mem);
 
 enum { TQ_ARITH_PLUS = 0, TQ_ARITH_MINUS = 1, TQ_ARITH_MUL = 2, TQ_ARITH_DIV = 3 };
 /* builtinArithmetic{Plus,Minus,Multiply}IntSig / MultiplyIntUnsignedSig.vecEvalInt —

@@ -672,3 +672,55 @@ int orc_vec_filter_int(int64_t n, const orc_column *a, uint8_t *selected) {
   for (int64_t i = 0; i < n; i++) selected[i] = (uint8_t)(!col_is_null(a, i) && col_i64(a, i) != 0);
   return ORC_OK;
 }
+
+/* ------------------------------------------------------------------ string builtins */
+/* types.CompareString (types/compare.go:115-123): Go string order = unsigned byte order, shorter first on a tie */
+static int compare_string(const uint8_t *x, int64_t lx, const uint8_t *y, int64_t ly) {
+  int64_t m = lx < ly ? lx : ly;
+  int c = m ? memcmp(x, y, (size_t)m) : 0;
+  if (c) return c < 0 ? -1 : 1;
+  return lx < ly ? -1 : (lx > ly ? 1 : 0);
+}
+/* builtin{LT..NE}StringSig.vecEvalInt (builtin_compare_vec_generated.go:65-555): MergeNulls, then per non-NULL row
+ * val = CompareString(a, b) mapped through the operator; op 6 = builtinStrcmpSig (builtin_string_vec.go:52-83). */
+int orc_vec_compare_string(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out) {
+  if (op < 0 || op > 6) return ORC_ERR_INVALID;
+  int64_t *o = (int64_t *)out->data;
+  out->length = n;
+  memset(out->null_bitmap, 0, (size_t)((n + 7) >> 3));
+  for (int64_t i = 0; i < n; i++) {
+    o[i] = 0;
+    if (col_is_null(a, i) || col_is_null(b, i)) continue;
+    out->null_bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
+    int c = compare_string(a->data + a->offsets[i], a->offsets[i + 1] - a->offsets[i], b->data + b->offsets[i], b->offsets[i + 1] - b->offsets[i]);
+    switch (op) {
+      case 0: o[i] = c < 0; break;
+      case 1: o[i] = c <= 0; break;
+      case 2: o[i] = c > 0; break;
+      case 3: o[i] = c >= 0; break;
+      case 4: o[i] = c == 0; break;
+      case 5: o[i] = c != 0; break;
+      default: o[i] = c; break;
+    }
+  }
+  return ORC_OK;
+}
+/* op 0: builtinLengthSig.evalInt per row — int64(len([]byte(val))), NULL in, NULL out (builtin_string.go:75-81);
+ * op 1: builtinStringIsNullSig.vecEvalInt (builtin_string_vec.go:21-42) */
+int orc_vec_string_unary(int op, int64_t n, const orc_column *a, orc_column *out) {
+  if (op < 0 || op > 1) return ORC_ERR_INVALID;
+  int64_t *o = (int64_t *)out->data;
+  out->length = n;
+  memset(out->null_bitmap, 0, (size_t)((n + 7) >> 3));
+  for (int64_t i = 0; i < n; i++) {
+    int isnull = col_is_null(a, i);
+    if (op == 0) {
+      o[i] = isnull ? 0 : a->offsets[i + 1] - a->offsets[i];
+      if (!isnull) out->null_bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
+    } else {
+      o[i] = isnull ? 1 : 0;
+      out->null_bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
+    }
+  }
+  return ORC_OK;
+}

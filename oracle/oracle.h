@@ -97,6 +97,10 @@ int64_t orc_mt_agg_bench(int64_t n, const int64_t *k, const double *x, int parti
 int64_t orc_mt_lt_plus_bench(int64_t n, const int64_t *a, const int64_t *b, int64_t *lt_out,
                              int64_t *plus_out, int workers, double *seconds);
 
+/* string builtins over var-len columns (offsets + data) */
+int orc_vec_compare_string(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out);
+int orc_vec_string_unary(int op, int64_t n, const orc_column *a, orc_column *out);
+
 #ifdef __cplusplus
 }
 #endif

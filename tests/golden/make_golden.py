@@ -10,7 +10,7 @@ Run:  python tests/golden/make_golden.py      (rewrites reference_cases.json det
 import json
 import os
 
-I, U, F = "int64", "uint64", "float64"
+I, U, F, B = "int64", "uint64", "float64", "bytes"
 N = None
 MAXU = (1 << 64) - 1
 
@@ -107,6 +107,26 @@ EXPR = [
     dict(op="in", cite="expression/builtin_other_test.go:37", args=[[U, MAXU], [U, MAXU], [I, 2], [I, 3]], expect=[I, 1]),
     dict(op="in", cite="expression/builtin_other_test.go:38", args=[[I, -1], [U, MAXU], [I, 2], [I, 3]], expect=[I, 0]),
     dict(op="in", cite="expression/builtin_other_test.go:39", args=[[U, MAXU], [I, -1], [I, 2], [I, 3]], expect=[I, 0]),
+]
+
+# ---- expression/builtin_string_test.go (string-typed argument cases; the int / float argument cases go through a CAST
+# that is planner work, not part of the vectorized signature)
+EXPR += [
+    dict(op="length", cite="expression/builtin_string_test.go:31", args=[[B, "abc"]], expect=[I, 3]),
+    dict(op="length", cite="expression/builtin_string_test.go:32", args=[[B, "\u4f60\u597d"]], expect=[I, 6]),
+    dict(op="length", cite="expression/builtin_string_test.go:35", args=[[B, N]], expect=[I, N]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:69", args=[[B, "123"], [B, "123"]], expect=[I, 0]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:70", args=[[B, "123"], [B, "1"]], expect=[I, 1]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:71", args=[[B, "1"], [B, "123"]], expect=[I, -1]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:72", args=[[B, "123"], [B, "45"]], expect=[I, -1]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:75", args=[[B, N], [B, "123"]], expect=[I, N]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:76", args=[[B, "123"], [B, N]], expect=[I, N]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:77", args=[[B, ""], [B, "123"]], expect=[I, -1]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:78", args=[[B, "123"], [B, ""]], expect=[I, 1]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:79", args=[[B, ""], [B, ""]], expect=[I, 0]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:80", args=[[B, ""], [B, N]], expect=[I, N]),
+    dict(op="strcmp", cite="expression/builtin_string_test.go:82", args=[[B, N], [B, N]], expect=[I, N]),
+    dict(op="lt", cite="expression/builtin_compare_test.go:35", args=[[B, "123"], [B, "123"]], expect=[I, 0]),
 ]
 
 # ---- util/codec/codec_test.go TestHashChunkRow (:735-769) as join-key equalities

@@ -156,6 +156,16 @@ def vec_in_int(a, lst):
                 _i32([1 if c.tp == 2 else 0 for c in lst]))
 
 
+def vec_compare_string(op, a, b):
+    ta, tb = a.tq(), b.tq()
+    return _vec(load().orc_vec_compare_string, 1, a.length, C.c_int(op), C.c_int64(a.length), C.byref(ta), C.byref(tb))
+
+
+def vec_string_unary(op, a):
+    ta = a.tq()
+    return _vec(load().orc_vec_string_unary, 1, a.length, C.c_int(op), C.c_int64(a.length), C.byref(ta))
+
+
 def vec_filter_int(a):
     ta = a.tq()
     sel = np.zeros(max(a.length, 1), dtype=np.uint8)

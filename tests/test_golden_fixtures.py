@@ -9,16 +9,18 @@ import numpy as np
 import pytest
 
 import oracle_py as O
-from tinysql_b200.chunk import FLOAT64, INT64, UINT64, Chunk, Column
+from tinysql_b200.chunk import BYTES, FLOAT64, INT64, UINT64, Chunk, Column
 
 CASES = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cases.json")))
-TP = {"int64": INT64, "uint64": UINT64, "float64": FLOAT64}
+TP = {"int64": INT64, "uint64": UINT64, "float64": FLOAT64, "bytes": BYTES}
 NP = {INT64: np.int64, UINT64: np.uint64, FLOAT64: np.float64}
 JT = {"inner": 0, "left": 1, "right": 2}
 FN = {"count": 0, "sum": 1, "avg": 2, "max": 3, "min": 4, "firstrow": 5}
 
 
 def col(tp, vals):
+    if tp == BYTES:
+        return Column(BYTES, [None if v is None else v.encode("utf-8") for v in vals])
     return Column(tp, np.array([0 if v is None else v for v in vals], dtype=NP[tp]), [v is not None for v in vals])
 
 
@@ -48,7 +50,15 @@ class OracleEngine:
         return out
 
     def compare(self, op, a, b):
-        rc, out = O.vec_compare_real(op, a, b) if a.tp == FLOAT64 else O.vec_compare_int(op, a, b)
+        if a.tp == BYTES:
+            rc, out = O.vec_compare_string(op, a, b)
+        else:
+            rc, out = O.vec_compare_real(op, a, b) if a.tp == FLOAT64 else O.vec_compare_int(op, a, b)
+        assert rc == 0
+        return out
+
+    def length(self, a):
+        rc, out = O.vec_string_unary(0, a)
         assert rc == 0
         return out
 
@@ -88,7 +98,13 @@ class GpuEngine:
 
     def compare(self, op, a, b):
         from tinysql_b200 import expression as E
+        if a.tp == BYTES:
+            return E.vec_compare_string(op, a, b)
         return E.vec_compare_real(op, a, b) if a.tp == FLOAT64 else E.vec_compare_int(op, a, b)
+
+    def length(self, a):
+        from tinysql_b200 import expression as E
+        return E.vec_string_unary(E.STR_LENGTH, a)
 
     def in_int(self, a, lst):
         from tinysql_b200 import expression as E
@@ -159,7 +175,7 @@ def test_reference_agg_goldens(engine, case):
 
 # ------------------------------------------------------------------ vectorized builtins
 ARITH = {"plus": 0, "minus": 1, "mul": 2}
-CMP = {"lt": 0, "le": 1, "gt": 2, "ge": 3, "eq": 4, "ne": 5}
+CMP = {"lt": 0, "le": 1, "gt": 2, "ge": 3, "eq": 4, "ne": 5, "strcmp": 6}
 
 
 @pytest.mark.parametrize("engine", ENGINES, indirect=True)
@@ -172,6 +188,8 @@ def test_reference_builtin_goldens(engine, case):
         out = engine.arith(ARITH[case["op"]], args[0], args[1])
     elif case["op"] in CMP:
         out = engine.compare(CMP[case["op"]], args[0], args[1])
+    elif case["op"] == "length":
+        out = engine.length(args[0])
     else:
         out = engine.in_int(args[0], args[1:])
     tp, want = TP[case["expect"][0]], case["expect"][1]

@@ -54,6 +54,8 @@ SYMBOLS = {
     "tq_vec_unary": (_I32, [_I32, _I64, _COL, _I32, _COL, _I32]),
     "tq_vec_if": (_I32, [_I64, _COL, _COL, _COL, _COL, _I32]),
     "tq_vec_ifnull": (_I32, [_I64, _COL, _COL, _COL, _I32]),
+    "tq_vec_compare_string": (_I32, [_I32, _I64, _COL, _COL, _COL, _I32]),
+    "tq_vec_string_unary": (_I32, [_I32, _I64, _COL, _COL, _I32]),
     "tq_vec_in_int": (_I32, [_I64, _COL, _I32, _I32, _COL, C.POINTER(_I32), _COL, _I32]),
     "tq_vec_lt_plus_int": (_I32, [_I64, _COL, _COL, _COL, _COL, _I32]),
     "tq_vec_filter_int": (_I32, [_I64, _COL, _P, _I32]),

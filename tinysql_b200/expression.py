@@ -14,6 +14,8 @@ LT, LE, GT, GE, EQ, NE = range(6)
 PLUS, MINUS, MUL, DIV = range(4)
 AND, OR = 0, 1
 NOT_INT, NOT_REAL, MINUS_INT, MINUS_REAL, ISNULL = range(5)
+STRCMP = 6                     # tq_vec_compare_string op beyond LT..NE
+STR_LENGTH, STR_ISNULL = 0, 1  # tq_vec_string_unary ops
 
 
 def _u(col):
@@ -33,6 +35,23 @@ def vec_compare_real(op, a, b):
     out = Column.empty(INT64, a.length)
     ta, tb, to = a.tq(), b.tq(), out.tq()
     L.check(L.load().tq_vec_compare_real(op, a.length, C.byref(ta), C.byref(tb), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_compare_string(op, a, b):
+    """builtin{LT..NE}StringSig.vecEvalInt (builtin_compare_vec_generated.go:65-555); op STRCMP: builtinStrcmpSig
+    (builtin_string_vec.go:52-83).  a, b: var-len columns."""
+    out = Column.empty(INT64, a.length)
+    ta, tb, to = a.tq(), b.tq(), out.tq()
+    L.check(L.load().tq_vec_compare_string(op, a.length, C.byref(ta), C.byref(tb), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_string_unary(op, a):
+    """STR_LENGTH: builtinLengthSig (builtin_string.go:75-81); STR_ISNULL: builtinStringIsNullSig (builtin_string_vec.go:21-42)"""
+    out = Column.empty(INT64, a.length)
+    ta, to = a.tq(), out.tq()
+    L.check(L.load().tq_vec_string_unary(op, a.length, C.byref(ta), C.byref(to), L.TQ_MEM_HOST))
     return out
 
 
