@@ -458,6 +458,72 @@ def test_agg_not_null_columns_compact_state(lib):
         assert_col_equal(a, b)
 
 
+@pytest.mark.parametrize("n,ndv,est,hot", [(1300000, 900, 900, 0), (1500000, 60000, 60000, 0), (1200000, 250000, 100, 0),
+                                           (1400000, 40000, 40000, 0.7), (6000000, 5000, 0, 0)])
+def test_agg_shared_memory_preaggregation(lib, monkeypatch, n, ndv, est, hot):
+    """large NOT NULL batches take the scatter -> shared-memory pre-aggregation -> merge path (k_agg_preagg): one table per
+    CTA (ndv 900), partitioned (ndv 60000), an estimate far too small (tables fill up -> general path), a hot key that
+    overflows its slab (-> general path), and no estimate at all (first batch general, the next ones pre-aggregated)"""
+    monkeypatch.setenv("TQ_AGG_PREAGG_PART", "1")  # the radix-partitioned variant is opt-in (slower than the general path today)
+    rng = np.random.default_rng(n % 1000 + ndv)
+    kv = rng.integers(0, ndv, n)
+    if hot:
+        kv[rng.random(n) < hot] = 7
+    k = Column(INT64, kv)
+    x = Column(FLOAT64, np.floor(rng.random(n) * 4096) / 16)   # dyadic: float sums exact in any order
+    y = Column(FLOAT64, np.floor(rng.random(n) * 1024) / 4)
+    types, cols = [INT64, FLOAT64, FLOAT64], [k, x, y]
+    funcs = [(AGG_SUM, 1), (AGG_COUNT, -1), (AGG_FIRSTROW, 0), (AGG_AVG, 2), (AGG_COUNT, 1)]
+    src = MockDataSource(types, cols, 1 << 19)
+    e = HashAggExec(src, [0], funcs, est, not_null_cols=(0, 1, 2))
+    e.Open()
+    got = e.drain()
+    e.Close()
+    rc, want = O.hash_agg(types, cols, [0], funcs, 2)
+    assert rc == 0
+    g, w = _sorted_by_key(got, 2), _sorted_by_key(want, 2)
+    for a, b in zip(g, w):
+        assert_col_equal(a, b)
+
+
+def test_agg_preaggregation_marker_key_and_device_batch(lib):
+    """one device-resident batch (the bench shape) holding the table's empty-marker value as a key: the pre-aggregation
+    gives up and the general path answers"""
+    from tinysql_b200.chunk import DeviceColumn
+    rng = np.random.default_rng(77)
+    n = 1 << 21
+    kv = rng.integers(0, 3000, n)
+    kv[5] = np.int64(np.uint64(0xA5C3F00DDEADBEEF).astype(np.int64))
+    xv = np.floor(rng.random(n) * 256) / 2
+    for with_marker in (True, False):
+        kk = kv.copy()
+        if not with_marker:
+            kk[5] = 1
+        dk, dx = DeviceColumn.from_host(Column(INT64, kk)), DeviceColumn.from_host(Column(FLOAT64, xv))
+        it, gb = (C.c_int32 * 2)(INT64 | 0x100, FLOAT64 | 0x100), (C.c_int32 * 1)(0)
+        fl = [(AGG_SUM, 1), (AGG_COUNT, -1), (AGG_FIRSTROW, 0)]
+        fa = (L.TQAggFunc * 3)(*[L.TQAggFunc(f, a) for f, a in fl])
+        d = L.TQAggDesc(2, it, 1, gb, 3, fa, 3000)
+        h = C.c_void_p()
+        L.check(lib.tq_agg_create(C.byref(d), C.byref(h)))
+        cols = (L.TQColumn * 2)(dk.tq(), dx.tq())
+        cols[0].null_bitmap = None
+        cols[1].null_bitmap = None
+        L.check(lib.tq_agg_put(h, cols, L.TQ_MEM_DEVICE))
+        L.check(lib.tq_agg_eof(h))
+        res = [Column.empty(t, 4096) for t in (FLOAT64, INT64, INT64)]
+        from tinysql_b200.chunk import tq_array
+        nr, eof = C.c_int64(0), C.c_int32(0)
+        L.check(lib.tq_agg_next(h, 4096, tq_array(res, 4096), C.byref(nr), C.byref(eof)))
+        L.check(lib.tq_agg_destroy(h))
+        got = Chunk([Column(c.tp, c.values[: nr.value], c.not_null()[: nr.value]) for c in res])
+        rc, want = O.hash_agg([INT64, FLOAT64], [Column(INT64, kk), Column(FLOAT64, xv)], [0], fl, 1)
+        gs, ws = _sorted_by_key(got, 2), _sorted_by_key(want, 2)
+        for a, b in zip(gs, ws):
+            assert_col_equal(a, b)
+        dk.free(); dx.free()
+
+
 def test_agg_table_growth(lib):
     # est_groups far too small: the table grows several times and deferred rows are replayed
     rng = np.random.default_rng(9)

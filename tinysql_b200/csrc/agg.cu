@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "dict.cuh"
+#include "scatter.cuh"
 
 namespace tq {
 
@@ -403,6 +404,92 @@ __global__ void __launch_bounds__(256) k_agg_rehash(const uint64_t *old_keys, co
   }
 }
 
+// ------------------------------------------------------------------ shared-memory pre-aggregation
+// Large batches over a moderate number of groups do not have to pay one L2 atomic per row and state word.  The batch is
+// radix-scattered by the top hash bits of the key (scatter.cuh) so that one partition's groups fit a shared-memory hash
+// table; each CTA aggregates its slice of a partition with shared-memory atomics and emits ONE partial row per group
+// it saw — (key, COUNT | SUM | (COUNT, SUM) ...), the layout of tq_agg_export_partial — and the partial rows (~groups,
+// not ~rows) then go through the ordinary merge path (MergePartialResult semantics, aggregate.go:424-457).  This is the
+// reference's own partial -> final split (aggregate.go:96-133) with the partial workers living in shared memory.
+enum { PRE_COUNT = 0, PRE_SUM_F64 = 1, PRE_AVG_F64 = 2, PRE_KEY = 3 };
+struct PreFunc { int kind, col, w; };
+static constexpr uint32_t PRE_SLOTS = 4096;      // shared-memory table entries per CTA
+static constexpr int PRE_THREADS = 512;
+static constexpr int PRE_MAX_GROUPS_PER_PART = 2400;
+static constexpr int PRE_MAX_OUT_COLS = 1 + 2 * AGG_MAXF;
+struct PreParams {
+  const uint64_t *col[4];        // col[0] = key, then the distinct argument columns (slabs, or the batch itself when pbits == 0)
+  const uint32_t *lo, *hi, *lim; // partition bounds inside the slabs (pbits > 0)
+  int64_t n;
+  int pbits, split;
+  int n_funcs, W;                // W = state words per group
+  PreFunc f[AGG_MAXF];
+  uint64_t *out[PRE_MAX_OUT_COLS];  // partial-row columns: key, then per function its partial state column(s)
+  unsigned long long *out_n;
+  unsigned long long out_cap;
+  unsigned *fallback;            // non-zero: a table filled up / the marker key appeared / output full -> redo on the general path
+};
+
+__global__ void __launch_bounds__(PRE_THREADS) k_agg_preagg(const PreParams p) {
+  extern __shared__ __align__(16) uint64_t s_pre[];
+  uint64_t *s_keys = s_pre;
+  uint64_t *s_st = s_pre + PRE_SLOTS;
+  for (uint32_t i = threadIdx.x; i < PRE_SLOTS; i += PRE_THREADS) s_keys[i] = AGG_EMPTY;
+  for (uint32_t i = threadIdx.x; i < PRE_SLOTS * (uint32_t)p.W; i += PRE_THREADS) s_st[i] = 0;
+  __syncthreads();
+  const uint32_t part = blockIdx.x / p.split, sub = blockIdx.x % p.split;
+  int64_t lo = 0, hi = p.n;
+  if (p.pbits) {
+    lo = p.lo[part];
+    hi = p.hi[part];
+    if (hi > (int64_t)p.lim[part]) hi = p.lim[part];  // overflowed slab: the batch is redone anyway
+  }
+  const int64_t len = hi - lo;
+  const int64_t r_lo = lo + len * sub / p.split, r_hi = lo + len * (sub + 1) / p.split;
+  for (int64_t r = r_lo + threadIdx.x; r < r_hi; r += PRE_THREADS) {
+    const uint64_t key = tqd::ld_stream_u64(p.col[0] + r);
+    if (key == AGG_EMPTY) { atomicOr(p.fallback, 1u); continue; }
+    uint32_t idx = (uint32_t)(tqd::mix64(key) >> 20) & (PRE_SLOTS - 1);  // bits disjoint from the partition bits and the global table's
+    bool ok = false;
+    for (uint32_t probes = 0; probes < PRE_SLOTS; probes++) {
+      const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&s_keys[idx]);
+      if (cur == key) { ok = true; break; }
+      if (cur == AGG_EMPTY) {
+        const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&s_keys[idx]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
+        if (prev == AGG_EMPTY || prev == key) { ok = true; break; }
+      }
+      idx = (idx + 1) & (PRE_SLOTS - 1);
+    }
+    if (!ok) { atomicOr(p.fallback, 2u); continue; }
+    uint64_t *st = s_st + (size_t)idx * p.W;
+    for (int fi = 0; fi < p.n_funcs; fi++) {
+      const PreFunc &f = p.f[fi];
+      if (f.kind == PRE_COUNT) atomicAdd(reinterpret_cast<unsigned long long *>(st + f.w), 1ull);
+      else if (f.kind == PRE_SUM_F64) atomicAdd(reinterpret_cast<double *>(st + f.w), __longlong_as_double((long long)tqd::ld_stream_u64(p.col[f.col] + r)));
+      else if (f.kind == PRE_AVG_F64) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(st + f.w), 1ull);
+        atomicAdd(reinterpret_cast<double *>(st + f.w + 1), __longlong_as_double((long long)tqd::ld_stream_u64(p.col[f.col] + r)));
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < PRE_SLOTS; i += PRE_THREADS) {
+    const uint64_t key = s_keys[i];
+    if (key == AGG_EMPTY) continue;
+    const unsigned long long pos = atomicAdd(p.out_n, 1ull);
+    if (pos >= p.out_cap) { atomicOr(p.fallback, 4u); continue; }
+    const uint64_t *st = s_st + (size_t)i * p.W;
+    p.out[0][pos] = key;
+    int oc = 1;
+    for (int fi = 0; fi < p.n_funcs; fi++) {
+      const PreFunc &f = p.f[fi];
+      if (f.kind == PRE_KEY) p.out[oc++][pos] = key;
+      else if (f.kind == PRE_AVG_F64) { p.out[oc++][pos] = st[f.w]; p.out[oc++][pos] = st[f.w + 1]; }
+      else p.out[oc++][pos] = st[f.w];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host side
 struct AggHostAccum {
   PinBuf data, bm;
@@ -429,6 +516,13 @@ struct tq_agg {
   int gb_cols[MK_MAX_KEYS];
   MultiKeyEncoder mk;       // several GROUP BY columns: exact fold of the key tuple into one 64-bit word (dict.cuh)
   DevBuf mk_comb;
+  // shared-memory pre-aggregation of large batches (k_agg_preagg)
+  bool pre_disabled = false;
+  bool pre_partitioned = false;  // TQ_AGG_PREAGG_PART=1: also pre-aggregate when the groups need radix partitioning (measured slower)
+  int64_t known_groups = 0;  // groups in the table after the last batch
+  std::vector<DevBuf> pre_slabs, pre_out;
+  DevBuf pre_lo, pre_hi, pre_lim, pre_meta;
+  cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;
   tq_agg_func funcs[AGG_MAXF];
   int arg_type[AGG_MAXF];
   int out_type[AGG_MAXF];
@@ -458,6 +552,8 @@ struct tq_agg {
     for (auto &s : stage) if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_b) cudaEventDestroy(ev_b);
+    if (ev_pa) cudaEventDestroy(ev_pa);
+    if (ev_pb) cudaEventDestroy(ev_pb);
   }
 };
 
@@ -516,11 +612,127 @@ static int32_t agg_grow(tq_agg *a, uint64_t new_slots) {
   return TQ_OK;
 }
 
+static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int64_t n, bool merge);
+
+// Try the shared-memory pre-aggregation path for one raw batch; *done tells whether the batch was consumed.
+static int32_t agg_try_preagg(tq_agg *a, const DCol *cols, int64_t n, bool *done) {
+  *done = false;
+  static const bool disabled_by_env = [] { const char *e = getenv("TQ_AGG_NO_PREAGG"); return e && e[0] == '1'; }();
+  if (disabled_by_env || a->pre_disabled || a->n_group_by != 1 || n < (1 << 20) || n > 0xFFFFFFF0ll) return TQ_OK;
+  const int kc = a->key_col;
+  if (a->types[kc] == TQ_TYPE_FLOAT64 || cols[kc].bm != nullptr) return TQ_OK;  // integer key without NULLs
+  const int64_t g_est = a->known_groups > a->est_groups ? a->known_groups : a->est_groups;
+  if (g_est <= 0 || n / g_est < 4) return TQ_OK;  // unknown NDV, or too little reduction to pay for the extra pass
+  PreParams p{};
+  int col_of[AGG_MAXC];
+  for (int c = 0; c < AGG_MAXC; c++) col_of[c] = -1;
+  DCol used[4];
+  int n_used = 1, W = 0, n_out = 1;
+  used[0] = cols[kc];
+  col_of[kc] = 0;
+  for (int i = 0; i < a->n_funcs; i++) {
+    const int fn = a->funcs[i].func, ac = a->funcs[i].arg_col;
+    PreFunc &f = p.f[i];
+    f.col = 0;
+    f.w = W;
+    if (a->key_passthrough[i]) { f.kind = PRE_KEY; n_out += 1; continue; }
+    const bool arg_ok = ac >= 0 && a->types[ac] == TQ_TYPE_FLOAT64 && cols[ac].bm == nullptr;
+    if (fn == TQ_AGG_COUNT && (ac < 0 || cols[ac].bm == nullptr)) { f.kind = PRE_COUNT; W += 1; n_out += 1; continue; }
+    if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && arg_ok) {
+      if (col_of[ac] < 0) {
+        if (n_used == 4) return TQ_OK;
+        used[n_used] = cols[ac];
+        col_of[ac] = n_used++;
+      }
+      f.col = col_of[ac];
+      if (fn == TQ_AGG_SUM) { f.kind = PRE_SUM_F64; W += 1; n_out += 1; }
+      else { f.kind = PRE_AVG_F64; W += 2; n_out += 2; }
+      continue;
+    }
+    return TQ_OK;  // a function / argument type this path does not cover
+  }
+  if (W == 0 || W > 5) return TQ_OK;
+  int pbits = 0;
+  while (((int64_t)PRE_MAX_GROUPS_PER_PART << pbits) < g_est) pbits++;
+  if (pbits > 12) return TQ_OK;
+  // Measured (B200, 5e7 rows, SUM(f64)+COUNT): one table per CTA (<= 2400 groups) 0.69 ms vs 1.27 ms on the general path;
+  // with radix partitioning (3e4 / 1e6 groups) 1.65 / 1.69 ms vs 1.00 / 1.63 ms — the 64-bit shared-memory atomics cost
+  // more than the L2 atomics they replace, so the partitioned variant stays opt-in until that kernel is reworked.
+  if (pbits > 0 && !a->pre_partitioned) return TQ_OK;
+  Runtime &r = rt();
+  cudaStream_t s = r.compute;
+  const int P = 1 << pbits;
+  const int split = P >= 2 * r.sm_count ? 1 : (2 * r.sm_count + P - 1) / P;
+  const unsigned long long out_cap = (unsigned long long)P * split * PRE_SLOTS;
+  if (!a->ev_pa) { TQ_CUDA(cudaEventCreate(&a->ev_pa)); TQ_CUDA(cudaEventCreate(&a->ev_pb)); }
+  TQ_TRY(a->pre_meta.reserve(64));
+  TQ_CUDA(cudaMemsetAsync(a->pre_meta.p, 0, 64, s));
+  unsigned long long *d_out_n = a->pre_meta.as<unsigned long long>();      // [0] partial rows
+  unsigned long long *d_overflow = d_out_n + 1;                            // [1] scatter slab overflow
+  unsigned *d_fallback = reinterpret_cast<unsigned *>(d_out_n + 2);        // [2] pre-aggregation gave up
+  TQ_CUDA(cudaEventRecord(a->ev_pa, s));
+  if (pbits) {
+    TQ_TRY(scatter_rows_by_hash(used, n_used, 0, n, pbits, a->pre_slabs, a->pre_lo, a->pre_hi, a->pre_lim, d_overflow, s));
+    for (int c = 0; c < n_used; c++) p.col[c] = a->pre_slabs[c].as<uint64_t>();
+    p.lo = a->pre_lo.as<uint32_t>();
+    p.hi = a->pre_hi.as<uint32_t>();
+    p.lim = a->pre_lim.as<uint32_t>();
+  } else {
+    for (int c = 0; c < n_used; c++) p.col[c] = used[c].data;
+  }
+  p.n = n;
+  p.pbits = pbits;
+  p.split = split;
+  p.n_funcs = a->n_funcs;
+  p.W = W;
+  a->pre_out.resize(n_out);
+  for (int c = 0; c < n_out; c++) {
+    TQ_TRY(a->pre_out[c].reserve((size_t)out_cap * 8));
+    p.out[c] = a->pre_out[c].as<uint64_t>();
+  }
+  p.out_n = d_out_n;
+  p.out_cap = out_cap;
+  p.fallback = d_fallback;
+  const int smem = (int)(PRE_SLOTS * 8 * (1 + W));
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    TQ_CUDA(cudaFuncSetAttribute(k_agg_preagg, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  k_agg_preagg<<<P * split, PRE_THREADS, smem, s>>>(p);
+  count_launch();
+  a->launches++;
+  TQ_TRY(check_launch("k_agg_preagg"));
+  unsigned long long h_meta[3] = {0, 0, 0};
+  TQ_CUDA(cudaMemcpyAsync(h_meta, a->pre_meta.p, 24, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaStreamSynchronize(s));
+  if (h_meta[1] || (unsigned)h_meta[2]) {
+    // skewed keys / more groups per partition than estimated / the marker key: nothing was applied to the table yet —
+    // this batch and the following ones take the general path
+    a->pre_disabled = true;
+    return TQ_OK;
+  }
+  std::vector<DCol> view(n_out);
+  for (int c = 0; c < n_out; c++) { view[c].data = a->pre_out[c].as<uint64_t>(); view[c].bm = nullptr; }
+  TQ_TRY(agg_update_device(a, view.data(), n_out, (int64_t)h_meta[0], /*merge=*/true));
+  TQ_CUDA(cudaEventRecord(a->ev_pb, s));
+  TQ_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, a->ev_pa, a->ev_pb) == cudaSuccess) a->last_update_ns = (int64_t)(ms * 1e6);  // scatter + pre-aggregation + merge
+  *done = true;
+  return TQ_OK;
+}
+
 // Run the update kernel over device columns; handles deferred rows by growing the table.
 static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int64_t n, bool merge) {
   if (n == 0) return TQ_OK;
   Runtime &r = rt();
   cudaStream_t s = r.compute;
+  if (!merge) {
+    bool done = false;
+    TQ_TRY(agg_try_preagg(a, cols, n, &done));
+    if (done) return TQ_OK;
+  }
   if (a->n_slots == 0) {
     uint64_t want = 1 << 16;
     const uint64_t hint = a->est_groups > 0 ? (uint64_t)a->est_groups : 0;
@@ -596,7 +808,10 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
       float ms = 0;
       if (cudaEventElapsedTime(&ms, a->ev_a, a->ev_b) == cudaSuccess) a->last_update_ns = (int64_t)(ms * 1e6);
     }
-    if (n_def == 0) return TQ_OK;
+    if (n_def == 0) {
+      a->known_groups = (int64_t)*reinterpret_cast<unsigned long long *>(a->meta_host.as<uint8_t>() + 16);
+      return TQ_OK;
+    }
     // the table reached its load limit: grow 4x (at least enough for every deferred row) and redo only those rows
     const uint64_t used = *reinterpret_cast<unsigned long long *>(a->meta_host.as<uint8_t>() + 16);
     uint64_t want = a->n_slots * 4;
@@ -777,6 +992,7 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
   a->n_group_by = d->n_group_by;
   a->n_funcs = d->n_funcs;
   a->est_groups = d->est_groups;
+  { const char *e = getenv("TQ_AGG_PREAGG_PART"); a->pre_partitioned = e && e[0] == '1'; }
   for (int c = 0; c < a->n_cols; c++) { a->types[c] = d->input_types[c] & 0xFF; a->not_null[c] = (d->input_types[c] & TQ_TYPE_NOT_NULL) != 0; }
   for (int g = 0; g < a->n_group_by; g++) {
     a->gb_cols[g] = d->group_by_cols[g];

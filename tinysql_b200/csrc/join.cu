@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "dict.cuh"
 #include "varlen.cuh"
+#include "scatter.cuh"
 
 namespace tq {
 
@@ -872,6 +873,51 @@ static ScatterKernel scatter_fast_kernel(int np) {
     case 4: return k_probe_scatter_fast<4>;
   }
   return nullptr;
+}
+
+// scatter.cuh: the same scatter for other operators (HashAgg pre-aggregation)
+int32_t scatter_rows_by_hash(const DCol *cols, int n_cols, int key_col, int64_t n, int pbits, std::vector<DevBuf> &out, DevBuf &lo, DevBuf &hi, DevBuf &lim,
+                             unsigned long long *d_overflow, cudaStream_t s) {
+  ScatterKernel kern = scatter_fast_kernel(n_cols);
+  if (!kern || pbits < 1 || pbits > PART_MAX_BITS || n <= 0 || n > 0xFFFFFFF0ll) { set_error("internal: scatter_rows_by_hash arguments"); return TQ_ERR_INVALID_ARG; }
+  const int P = 1 << pbits, n_bins = P + 1;
+  const uint64_t slab = (uint64_t)n / P + (uint64_t)n / P / 4 + 4096;
+  if (slab * P > 0xFFFFFFF0ull) { set_error("batch too large for 32-bit partition offsets"); return TQ_ERR_INVALID_ARG; }
+  out.resize(n_cols);
+  ScatterParams sp{};
+  sp.n_cols = n_cols;
+  for (int c = 0; c < n_cols; c++) {
+    TQ_TRY(out[c].reserve((size_t)slab * P * 8));
+    sp.in[c] = cols[c];
+    sp.out[c].data = out[c].as<uint64_t>();
+    sp.out[c].bm = nullptr;
+  }
+  TQ_TRY(lo.reserve((size_t)(n_bins + 1) * 4));
+  TQ_TRY(hi.reserve((size_t)(n_bins + 1) * 4));
+  TQ_TRY(lim.reserve((size_t)(n_bins + 1) * 4));
+  k_init_slabs<<<(n_bins + 255) / 256, 256, 0, s>>>(lo.as<uint32_t>(), hi.as<uint32_t>(), lim.as<uint32_t>(), P, (uint32_t)slab, 0u);
+  count_launch();
+  sp.selected = nullptr;
+  sp.key_col = key_col;
+  sp.key_mode = KEYMODE_RAW;
+  sp.is_outer = 0;
+  sp.pbits = pbits;
+  sp.n = n;
+  sp.part_cnt = nullptr;
+  sp.part_cursor = hi.as<uint32_t>();
+  sp.part_lim = lim.as<uint32_t>();
+  sp.overflow = d_overflow;
+  const int smem_scat = SCAT_TILE * 8 + n_bins * 12 + SCAT_TILE * 2 + SCAT_TILE;
+  static bool attr_set[5] = {};
+  if (!attr_set[n_cols]) {
+    TQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 12)));
+    attr_set[n_cols] = true;
+  }
+  const int64_t tiles = (n + SCAT_TILE - 1) / SCAT_TILE;
+  const int64_t cap = (int64_t)rt().sm_count * (n_cols <= 2 ? 2 : 1);
+  kern<<<(int)(tiles < cap ? tiles : cap), SCATF_THREADS, smem_scat, s>>>(sp);
+  count_launch();
+  return check_launch("k_probe_scatter_fast");
 }
 
 // ---- partitioned probe: the partition's table image lives in shared memory ------------------------------
