@@ -2294,6 +2294,7 @@ int32_t tq_join_put_build(tq_join *j, const tq_column *cols, int32_t mem) {
       if (need > j->b_dcap) {
         const int64_t ncap = need > j->b_dcap * 2 ? need : j->b_dcap * 2;
         j->b_ddata.resize(j->nb_user);
+        TQ_CUDA(cudaStreamSynchronize(r.h2d));  // earlier chunks may still be uploading into the blocks that are about to move
         for (int c = 0; c < j->nb_user; c++) {
           DevBuf nb;
           TQ_TRY(nb.reserve((size_t)ncap * 8));
