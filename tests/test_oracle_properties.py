@@ -1,0 +1,84 @@
+"""CPU suite: property tests (hypothesis) of the oracle — the invariants the GPU suite relies on at sizes where no second
+implementation is run: build-side choice is result-neutral for inner joins, an outer join is the inner join plus exactly
+the unmatched outer rows, partial/final splitting is result-neutral, COUNT sums to the non-NULL rows."""
+import numpy as np
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+import oracle_py as O
+from tinysql_b200.chunk import FLOAT64, INT64, UINT64, Column
+
+INNER, LEFT, RIGHT = 0, 1, 2
+COUNT, SUM, AVG, MAX, MIN, FIRSTROW = range(6)
+
+cell = st.one_of(st.none(), st.integers(-3, 6))
+
+
+def table(rows, ncols):
+    return [Column(INT64, [0 if r[c] is None else r[c] for r in rows], [r[c] is not None for r in rows]) for c in range(ncols)]
+
+
+rows2 = st.lists(st.tuples(cell, cell), min_size=0, max_size=40)
+
+
+def key(r):
+    return tuple((0, 0) if v is None else (1, v) for v in r)
+
+
+@settings(max_examples=150, deadline=None)
+@given(rows2, rows2, st.integers(0, 1), st.integers(0, 1))
+def test_inner_join_is_build_side_neutral_and_outer_adds_exactly_the_misses(lhs, rhs, lk, rk):
+    l, r = table(lhs, 2), table(rhs, 2)
+    t2 = [INT64, INT64]
+    # build on the right child (probe = left) vs build on the left child (probe = right): same rows lhs ++ rhs
+    a = O.hash_join(INNER, False, t2, r, t2, l, [rk], [lk]).rows()
+    b = O.hash_join(INNER, True, t2, l, t2, r, [lk], [rk]).rows()
+    assert sorted(a, key=key) == sorted(b, key=key)
+    # reference definition: pairs with equal non-NULL keys
+    want = [x + y for x in map(tuple, lhs) for y in map(tuple, rhs) if x[lk] is not None and x[lk] == y[rk]]
+    assert sorted(a, key=key) == sorted(want, key=key)
+    # left outer = inner + (unmatched left rows ++ NULLs), each exactly once
+    lo = O.hash_join(LEFT, False, t2, r, t2, l, [rk], [lk]).rows()
+    rkeys = {y[rk] for y in rhs if y[rk] is not None}
+    misses = [tuple(x) + (None, None) for x in lhs if x[lk] is None or x[lk] not in rkeys]
+    assert sorted(lo, key=key) == sorted(want + misses, key=key)
+    # right outer (outer = right child, build = left child)
+    ro = O.hash_join(RIGHT, True, t2, l, t2, r, [lk], [rk]).rows()
+    lkeys = {x[lk] for x in lhs if x[lk] is not None}
+    rmiss = [(None, None) + tuple(y) for y in rhs if y[rk] is None or y[rk] not in lkeys]
+    assert sorted(ro, key=key) == sorted(want + rmiss, key=key)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.tuples(cell, cell, st.one_of(st.none(), st.integers(-50, 50))), min_size=0, max_size=60), st.integers(1, 5), st.booleans())
+def test_group_by_matches_a_dictionary_and_partial_split_is_neutral(rows, workers, two_keys):
+    cols = table(rows, 3)
+    gb = [0, 1] if two_keys else [0]
+    funcs = [(COUNT, -1), (COUNT, 2), (SUM, 2), (MAX, 2), (MIN, 2), (AVG, 2)] + [(FIRSTROW, g) for g in gb]
+    rc1, one = O.hash_agg([INT64] * 3, cols, gb, funcs, 1)
+    rc2, many = O.hash_agg([INT64] * 3, cols, gb, funcs, workers)
+    assert rc1 == rc2 == 0
+    assert sorted(one.rows(), key=key) == sorted(many.rows(), key=key)
+    groups = {}
+    for r in rows:
+        g = groups.setdefault(tuple(r[c] for c in gb), [0, []])
+        g[0] += 1
+        if r[2] is not None:
+            g[1].append(r[2])
+    want = []
+    for k, (n, vals) in groups.items():
+        s = sum(vals) if vals else None
+        avg = None if not vals else int(abs(s) // len(vals)) * (1 if s >= 0 else -1)  # Go truncating division (func_avg.go:53)
+        want.append((n, len(vals), s, max(vals) if vals else None, min(vals) if vals else None, avg) + k)
+    assert sorted(one.rows(), key=key) == sorted(want, key=key)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, (1 << 64) - 1), st.integers(-(1 << 63), (1 << 63) - 1)), min_size=1, max_size=30))
+def test_signed_unsigned_key_equality_is_numeric(pairs):
+    """util/codec/codec.go:219-231: an unsigned and a signed key are equal iff they denote the same number"""
+    u = Column(UINT64, np.array([p[0] for p in pairs], dtype=np.uint64))
+    i = Column(INT64, np.array([p[1] for p in pairs], dtype=np.int64))
+    got = O.hash_join(INNER, False, [UINT64], [u], [INT64], [i], [0], [0]).num_rows()
+    want = sum(1 for a in pairs for b in pairs if b[1] >= 0 and a[0] == b[1])
+    assert got == want
