@@ -1,6 +1,7 @@
 """GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
 Bit-exact for integer / key / COUNT work; SUM/AVG(float64) within 1e-9 relative (north_star)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -267,6 +268,18 @@ def test_join_partitioned_unique_pk_fk(lib, monkeypatch, no_fast):
     ids = np.sort(got.cols[3].values)
     assert np.array_equal(ids, np.arange(npr))
     assert np.array_equal(got.cols[2].values, pk[got.cols[3].values])
+
+
+@pytest.mark.skipif(os.environ.get("TQ_RUN_EXPERIMENTS") != "1", reason="round-2 experiment (per-warp output claims), not yet measured: TQ_RUN_EXPERIMENTS=1 runs it")
+def test_join_fast_kernel_warp_claim_experiment(lib, monkeypatch):
+    monkeypatch.setenv("TQ_JOIN_WARP_CLAIM", "1")
+    rng = np.random.default_rng(31)
+    nb, npr = 400000, 3000000
+    bk = rng.permutation(nb * 2)[:nb].astype(np.int64)
+    pk = rng.integers(0, nb * 2, npr).astype(np.int64)
+    got, want = _run_join([INT64, INT64], [Column(INT64, bk), Column(INT64, bk * 3 + 1)], [INT64, INT64], [Column(INT64, pk), Column(INT64, np.arange(npr))],
+                          INNER_JOIN, True, chunk=1 << 20)
+    assert_same_multiset(got, want)
 
 
 @pytest.mark.parametrize("nbc,npc", [(1, 1), (3, 2), (4, 4), (2, 3)])
