@@ -270,9 +270,10 @@ def test_join_partitioned_unique_pk_fk(lib, monkeypatch, no_fast):
     assert np.array_equal(got.cols[2].values, pk[got.cols[3].values])
 
 
-@pytest.mark.skipif(os.environ.get("TQ_RUN_EXPERIMENTS") != "1", reason="round-2 experiment (per-warp output claims), not yet measured: TQ_RUN_EXPERIMENTS=1 runs it")
-def test_join_fast_kernel_warp_claim_experiment(lib, monkeypatch):
-    monkeypatch.setenv("TQ_JOIN_WARP_CLAIM", "1")
+@pytest.mark.skipif(os.environ.get("TQ_RUN_EXPERIMENTS") != "1", reason="round-2 experiments (probe kernel variants), not yet measured: TQ_RUN_EXPERIMENTS=1 runs them")
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_join_fast_kernel_variant_experiments(lib, monkeypatch, variant):
+    monkeypatch.setenv("TQ_JOIN_PROBE_VARIANT", variant)
     rng = np.random.default_rng(31)
     nb, npr = 400000, 3000000
     bk = rng.permutation(nb * 2)[:nb].astype(np.int64)

@@ -38,7 +38,7 @@ static int64_t g_max_load_pct = 50;                      // TQ_JOIN_MAX_LOAD_PCT
 static bool g_exact_scatter = false;                     // TQ_JOIN_EXACT_SCATTER=1: always run the probe-side histogram pass
 static bool g_no_fast_kernel = false;                    // TQ_JOIN_NO_FAST=1: use the generic kernels (tests)
 static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
-static bool g_warp_claim = false;                        // TQ_JOIN_WARP_CLAIM=1: per-warp output claims in the PK-FK probe kernel (experiment)
+static int g_probe_variant = 0;                          // TQ_JOIN_PROBE_VARIANT=1|2: experiments in the PK-FK probe kernel (see k_probe_part_fast)
 
 // key_mode: how (flag, raw bytes) equality (util/codec/codec.go:212-240,363-382) maps onto raw 8-byte equality
 //   0: flags always agree (both signed, both unsigned, or both DOUBLE)  -> raw equality
@@ -1091,11 +1091,16 @@ __device__ __forceinline__ EntryPair ld_pair(const uint64_t *tbl, uint32_t loc_e
   return e;
 }
 
-// WARP_CLAIM (experiment, TQ_JOIN_WARP_CLAIM=1): every warp claims the output range of its 128 rows with its own global
-// atomic instead of one claim per 1024-row tile behind two CTA barriers — 8x the atomics on the cursor, but no warp ever
-// waits for another one.  Not the default until it has been measured.
-template <int NP, int NB, bool WARP_CLAIM = false>
-__global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const ProbeParams p, const JoinTable t) {
+// VAR selects an experiment (TQ_JOIN_PROBE_VARIANT=1|2), 0 = the measured default:
+//   1  WARP_CLAIM: every warp claims the output range of its 128 rows with its own global atomic instead of one claim
+//      per 1024-row tile behind two CTA barriers — 8x the atomics on the cursor, but no warp ever waits for another one;
+//   2  WARP_CLAIM + PREFETCH: the other probe columns are requested together with the table entries (not after the
+//      match is known), which takes one dependent DRAM round trip out of the tile's critical path at the price of
+//      registers (3 CTAs per SM instead of 4) and of wasted reads for rows that miss.
+// Not the default until measured.
+template <int NP, int NB, int VAR = 0>
+__global__ void __launch_bounds__(PROBE_THREADS, (VAR == 2 ? 3 : 4)) k_probe_part_fast(const ProbeParams p, const JoinTable t) {
+  constexpr bool WARP_CLAIM = VAR >= 1, PREFETCH = VAR == 2;
   extern __shared__ __align__(128) unsigned char s_dyn[];
   __shared__ __align__(8) uint64_t s_mbar;
   __shared__ unsigned s_total[2];
@@ -1143,6 +1148,18 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const Prob
     ulonglong2 ent[R];
     unsigned bal[R];
     unsigned wcnt = 0;
+    uint64_t pay[NP][R];
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        const bool in_range = (wbase + k * 32) < cx.p_hi;
+#pragma unroll
+        for (int c = 0; c < NP; c++) {
+          pay[c][k] = 0;
+          if (c != kc && in_range) pay[c][k] = tqd::ld_stream_u64(pin[c] + wbase + k * 32);
+        }
+      }
+    }
     if (shift == 1) {
       EntryPair pr[R];
 #pragma unroll
@@ -1217,14 +1234,15 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const Prob
     }
     // the other probe columns of the matched rows are requested NOW: their latency hides behind the two barriers and
     // the global atomic below (only word 1 of the matched entry stays live: word 0 is the key itself)
-    uint64_t pay[NP][R];
+    if constexpr (!PREFETCH) {
 #pragma unroll
-    for (int k = 0; k < R; k++) {
-      const bool hit = (bal[k] >> lane) & 1u;
+      for (int k = 0; k < R; k++) {
+        const bool hit = (bal[k] >> lane) & 1u;
 #pragma unroll
-      for (int c = 0; c < NP; c++) {
-        pay[c][k] = 0;
-        if (c != kc && hit) pay[c][k] = tqd::ld_stream_u64(pin[c] + wbase + k * 32);
+        for (int c = 0; c < NP; c++) {
+          pay[c][k] = 0;
+          if (c != kc && hit) pay[c][k] = tqd::ld_stream_u64(pin[c] + wbase + k * 32);
+        }
       }
     }
     unsigned long long q0;
@@ -1262,27 +1280,29 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const Prob
 }
 
 typedef void (*ProbeKernel)(const ProbeParams, const JoinTable);
-template <int NP, bool WC>
+template <int NP, int VAR>
 static ProbeKernel fast_kernel_nb(int nb) {
   switch (nb) {
-    case 1: return k_probe_part_fast<NP, 1, WC>;
-    case 2: return k_probe_part_fast<NP, 2, WC>;
-    case 3: return k_probe_part_fast<NP, 3, WC>;
-    case 4: return k_probe_part_fast<NP, 4, WC>;
+    case 1: return k_probe_part_fast<NP, 1, VAR>;
+    case 2: return k_probe_part_fast<NP, 2, VAR>;
+    case 3: return k_probe_part_fast<NP, 3, VAR>;
+    case 4: return k_probe_part_fast<NP, 4, VAR>;
   }
   return nullptr;
 }
-template <bool WC>
-static ProbeKernel fast_kernel_wc(int np, int nb) {
+template <int VAR>
+static ProbeKernel fast_kernel_var(int np, int nb) {
   switch (np) {
-    case 1: return fast_kernel_nb<1, WC>(nb);
-    case 2: return fast_kernel_nb<2, WC>(nb);
-    case 3: return fast_kernel_nb<3, WC>(nb);
-    case 4: return fast_kernel_nb<4, WC>(nb);
+    case 1: return fast_kernel_nb<1, VAR>(nb);
+    case 2: return fast_kernel_nb<2, VAR>(nb);
+    case 3: return fast_kernel_nb<3, VAR>(nb);
+    case 4: return fast_kernel_nb<4, VAR>(nb);
   }
   return nullptr;
 }
-static ProbeKernel fast_kernel(int np, int nb, bool warp_claim) { return warp_claim ? fast_kernel_wc<true>(np, nb) : fast_kernel_wc<false>(np, nb); }
+static ProbeKernel fast_kernel(int np, int nb, int variant) {
+  return variant == 2 ? fast_kernel_var<2>(np, nb) : variant == 1 ? fast_kernel_var<1>(np, nb) : fast_kernel_var<0>(np, nb);
+}
 
 // ---- partitioned probe, general (duplicate build keys): block scan + output-centric expansion ------------
 __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part(const ProbeParams p, const JoinTable t) {
@@ -1944,12 +1964,12 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     bool any_out_bm = false;
     for (int c = 0; c < j->n_probe_cols; c++) any_out_bm |= (p.out_probe[c].bm != nullptr);
     for (int c = 0; c < j->n_build_cols; c++) any_out_bm |= (p.out_build[c].bm != nullptr);
-    ProbeKernel fast = (j->row_mode && !p.is_outer && !any_out_bm && !g_no_fast_kernel) ? fast_kernel(j->n_probe_cols, j->n_build_cols, g_warp_claim) : nullptr;
+    ProbeKernel fast = (j->row_mode && !p.is_outer && !any_out_bm && !g_no_fast_kernel) ? fast_kernel(j->n_probe_cols, j->n_build_cols, g_probe_variant) : nullptr;
     if (fast) {
-      static bool fast_attr[2][5][5] = {};
-      if (!fast_attr[g_warp_claim ? 1 : 0][j->n_probe_cols][j->n_build_cols]) {
+      static bool fast_attr[3][5][5] = {};
+      if (!fast_attr[g_probe_variant][j->n_probe_cols][j->n_build_cols]) {
         TQ_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_MAX_SMEM_BYTES));
-        fast_attr[g_warp_claim ? 1 : 0][j->n_probe_cols][j->n_build_cols] = true;
+        fast_attr[g_probe_variant][j->n_probe_cols][j->n_build_cols] = true;
       }
       fast<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
     } else if (j->build_unique) k_probe_part_uniq<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
@@ -2198,7 +2218,7 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   if (d->join_type == TQ_JOIN_RIGHT_OUTER && !d->outer_is_right) { set_error("right outer join needs outer_is_right == 1"); return TQ_ERR_INVALID_ARG; }
   { const char *e = getenv("TQ_JOIN_FORCE_GLOBAL"); g_force_global_table = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_NO_FAST"); g_no_fast_kernel = e && e[0] == '1'; }
-  { const char *e = getenv("TQ_JOIN_WARP_CLAIM"); g_warp_claim = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_PROBE_VARIANT"); g_probe_variant = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
   { const char *e = getenv("TQ_JOIN_EXACT_SCATTER"); g_exact_scatter = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_MAX_LOAD_PCT"); if (e && atoll(e) >= 10 && atoll(e) <= 90) g_max_load_pct = atoll(e); }
   { const char *e = getenv("TQ_JOIN_TILES_PER_CTA"); if (e && atoll(e) > 0) g_tiles_per_cta = atoll(e); }
