@@ -41,7 +41,9 @@ def measured_traffic():
 def join_config(n_build, n_probe):
     return {"workload": f"C3: int64 equi-join, uniform keys, build={n_build} probe={n_probe}, 100% match, output (B.k,B.v,P.k,P.v) materialised",
             "build_rows": n_build, "probe_rows": n_probe, "l2": "inputs (1.76 GB) and output (3.2 GB) exceed the 126 MB L2; no flush needed",
-            "step": "tq_join create + build + probe + result, inputs resident in HBM"}
+            "step": "tq_join create + build + probe + result, inputs resident in HBM",
+            "e2e_step": "same through the C-ABI with HOST buffers: pinned inputs (tq_pinned_alloc, declared TQ_JOIN_STABLE_INPUT so uploads overlap "
+                        "result downloads), 8M-row probe pieces, every result column copied back to pinned host memory; all copies inside the timed region"}
 
 
 def measured_peak():
