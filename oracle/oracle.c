@@ -220,12 +220,67 @@ static void append_row(outbuf *obs, int base, int ncols, const orc_column *cols,
   for (int c = 0; c < ncols; c++) ob_push_cell(&obs[base + c], &cols[c], row); /* row < 0: defaultInner, all NULL (builder.go:463-465) */
 }
 
+static int cmp_int(int ua, int ub, int64_t x, int64_t y);
+static int cmp_f64(double x, double y);
+static int64_t cmp_result(int op, int c);
+
+/* One OtherCondition `out[lhs_col] op out[rhs_col]` (or `op constant`) on the joined row lhs ++ rhs.  baseJoiner.filter
+ * (joiner.go:155-167) keeps the joined rows for which every condition is TRUE — a NULL operand makes it not true
+ * (VectorizedFilter, chunk_executor.go:196-245). */
+typedef struct { int type; uint64_t bits; int is_null; } cond_operand;
+static cond_operand joined_cell(int o, int outer_is_right, int n_build_cols, const int *bt, const orc_column *bc, int64_t brow,
+                                int n_probe_cols, const int *pt, const orc_column *pc, int64_t prow) {
+  cond_operand r;
+  int first_is_build = outer_is_right;
+  int n_first = first_is_build ? n_build_cols : n_probe_cols;
+  int from_build = first_is_build ? (o < n_first) : (o >= n_first);
+  int c = o < n_first ? o : o - n_first;
+  const orc_column *col = from_build ? &bc[c] : &pc[c];
+  int64_t row = from_build ? brow : prow;
+  r.type = from_build ? bt[c] : pt[c];
+  r.is_null = col_is_null(col, row);
+  r.bits = r.is_null ? 0 : col_u64(col, row);
+  return r;
+}
+static int conds_true(int n_conds, const orc_join_cond *conds, int outer_is_right, int n_build_cols, const int *bt, const orc_column *bc, int64_t brow,
+                      int n_probe_cols, const int *pt, const orc_column *pc, int64_t prow) {
+  for (int k = 0; k < n_conds; k++) {
+    cond_operand a = joined_cell(conds[k].lhs_col, outer_is_right, n_build_cols, bt, bc, brow, n_probe_cols, pt, pc, prow), b;
+    if (conds[k].rhs_col >= 0) b = joined_cell(conds[k].rhs_col, outer_is_right, n_build_cols, bt, bc, brow, n_probe_cols, pt, pc, prow);
+    else { b.type = conds[k].const_type; b.bits = conds[k].const_bits; b.is_null = 0; }
+    if (a.is_null || b.is_null) return 0;
+    int c;
+    if (a.type == ORC_TYPE_FLOAT64) { double x, y; memcpy(&x, &a.bits, 8); memcpy(&y, &b.bits, 8); c = cmp_f64(x, y); }
+    else c = cmp_int(a.type == ORC_TYPE_UINT64, b.type == ORC_TYPE_UINT64, (int64_t)a.bits, (int64_t)b.bits);
+    if (!cmp_result(conds[k].op, c)) return 0;
+  }
+  return 1;
+}
+
 int orc_hash_join(int join_type, int outer_is_right,
                   int n_build_cols, const int *build_types, const orc_column *build_cols,
                   int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
                   int n_keys, const int *build_key_idx, const int *probe_key_idx,
                   const uint8_t *selected, orc_column *out_cols, int64_t *n_out) {
-  if (join_type < 0 || join_type > 2 || n_keys < 1) return ORC_ERR_INVALID;
+  return orc_hash_join_cond(join_type, outer_is_right, n_build_cols, build_types, build_cols, n_probe_cols, probe_types, probe_cols, n_keys, build_key_idx,
+                            probe_key_idx, selected, 0, NULL, out_cols, n_out);
+}
+
+int orc_hash_join_cond(int join_type, int outer_is_right,
+                       int n_build_cols, const int *build_types, const orc_column *build_cols,
+                       int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
+                       int n_keys, const int *build_key_idx, const int *probe_key_idx,
+                       const uint8_t *selected, int n_conds, const orc_join_cond *conds, orc_column *out_cols, int64_t *n_out) {
+  if (join_type < 0 || join_type > 2 || n_keys < 1 || n_conds < 0) return ORC_ERR_INVALID;
+  for (int k = 0; k < n_conds; k++) {  /* operands: the 8-byte types, integers with integers / doubles with doubles */
+    int nt = n_build_cols + n_probe_cols;
+    if (conds[k].op < 0 || conds[k].op > 5 || conds[k].lhs_col < 0 || conds[k].lhs_col >= nt || conds[k].rhs_col >= nt) return ORC_ERR_INVALID;
+    int o = conds[k].lhs_col, nf = outer_is_right ? n_build_cols : n_probe_cols;
+    int ta = (outer_is_right ? (o < nf) : (o >= nf)) ? build_types[o < nf ? o : o - nf] : probe_types[o < nf ? o : o - nf];
+    int tb = conds[k].const_type;
+    if (conds[k].rhs_col >= 0) { o = conds[k].rhs_col; tb = (outer_is_right ? (o < nf) : (o >= nf)) ? build_types[o < nf ? o : o - nf] : probe_types[o < nf ? o : o - nf]; }
+    if (ta < 1 || ta > 3 || tb < 1 || tb > 3 || ((ta == ORC_TYPE_FLOAT64) != (tb == ORC_TYPE_FLOAT64))) return ORC_ERR_UNSUPPORTED;
+  }
   for (int c = 0; c < n_build_cols; c++) if (build_types[c] < 1 || build_types[c] > 5) return ORC_ERR_UNSUPPORTED;
   for (int c = 0; c < n_probe_cols; c++) if (probe_types[c] < 1 || probe_types[c] > 5) return ORC_ERR_UNSUPPORTED;
   /* key columns: the 8-byte types only (FLOAT / var-len keys are not restated — "unsupport column type", codec.go:235) */
@@ -264,7 +319,9 @@ int orc_hash_join(int join_type, int outer_is_right,
       for (int64_t c = 0; c < cnt; c++) {
         int64_t brow = ((int64_t)pairs[2 * c] << 32) | pairs[2 * c + 1];
         if (!orc_equal_row(n_keys, build_types, build_cols, build_key_idx, brow, probe_types, probe_cols, probe_key_idx, i)) continue;
-        /* tryToMatchInners with no OtherConditions: makeJoinRowToChunk per inner (joiner.go:225-248,288-311,351-378) */
+        /* tryToMatchInners: makeJoinRowToChunk per inner, then baseJoiner.filter over the joined rows when there are
+         * OtherConditions (joiner.go:225-248,288-311,351-378,155-167); `matched` = some joined row survived */
+        if (n_conds && !conds_true(n_conds, conds, outer_is_right, n_build_cols, build_types, build_cols, brow, n_probe_cols, probe_types, probe_cols, i)) continue;
         append_row(obs, build_base, n_build_cols, build_cols, brow);
         append_row(obs, probe_base, n_probe_cols, probe_cols, i);
         n_matched++;

@@ -55,6 +55,14 @@ int orc_hash_join(int join_type, int outer_is_right,
                   int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
                   int n_keys, const int *build_key_idx, const int *probe_key_idx,
                   const uint8_t *selected, orc_column *out_cols, int64_t *n_out);
+/* The same with OtherConditions (HashJoinExec.joiners' filter, joiner.go:155-167): every condition compares output column
+ * lhs_col (index into lhs ++ rhs) with output column rhs_col, or with a constant when rhs_col < 0. */
+typedef struct orc_join_cond { int32_t op, lhs_col, rhs_col, const_type; uint64_t const_bits; } orc_join_cond;
+int orc_hash_join_cond(int join_type, int outer_is_right,
+                       int n_build_cols, const int *build_types, const orc_column *build_cols,
+                       int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
+                       int n_keys, const int *build_key_idx, const int *probe_key_idx,
+                       const uint8_t *selected, int n_conds, const orc_join_cond *conds, orc_column *out_cols, int64_t *n_out);
 void orc_free_columns(int n, orc_column *cols);
 
 /* HashAggExec — executor/aggregate.go:332-457,559-588; aggfuncs/ sources.  n_partial_workers

@@ -55,7 +55,23 @@ def _take(tq_cols, types, n):
     return cols
 
 
-def hash_join(join_type, outer_is_right, build_types, build_cols, probe_types, probe_cols, build_keys, probe_keys, selected=None):
+class OrcJoinCond(C.Structure):
+    _fields_ = [("op", C.c_int32), ("lhs_col", C.c_int32), ("rhs_col", C.c_int32), ("const_type", C.c_int32), ("const_bits", C.c_uint64)]
+
+
+def _conds(conds):
+    """conds: list of (op, lhs_col, rhs_col) or (op, lhs_col, None, const_type, const_value) over the output row lhs ++ rhs"""
+    arr = (OrcJoinCond * max(len(conds), 1))()
+    for i, c in enumerate(conds):
+        if c[2] is None:
+            bits = int(np.array([c[4]], dtype=_NP[c[3]]).view(np.uint64)[0])
+            arr[i] = OrcJoinCond(c[0], c[1], -1, c[3], bits)
+        else:
+            arr[i] = OrcJoinCond(c[0], c[1], c[2], 0, 0)
+    return arr
+
+
+def hash_join(join_type, outer_is_right, build_types, build_cols, probe_types, probe_cols, build_keys, probe_keys, selected=None, conds=()):
     lib = load()
     ncols = len(build_cols) + len(probe_cols)
     out = (TQColumn * ncols)()
@@ -63,9 +79,10 @@ def hash_join(join_type, outer_is_right, build_types, build_cols, probe_types, p
     sel = None
     if selected is not None:
         sel = np.ascontiguousarray(selected, dtype=np.uint8)
-    rc = lib.orc_hash_join(C.c_int(join_type), C.c_int(1 if outer_is_right else 0), C.c_int(len(build_cols)), _i32(build_types),
-                           tq_array(build_cols), C.c_int(len(probe_cols)), _i32(probe_types), tq_array(probe_cols), C.c_int(len(build_keys)),
-                           _i32(build_keys), _i32(probe_keys), C.c_void_p(sel.ctypes.data) if sel is not None else None, out, C.byref(n))
+    rc = lib.orc_hash_join_cond(C.c_int(join_type), C.c_int(1 if outer_is_right else 0), C.c_int(len(build_cols)), _i32(build_types),
+                                tq_array(build_cols), C.c_int(len(probe_cols)), _i32(probe_types), tq_array(probe_cols), C.c_int(len(build_keys)),
+                                _i32(build_keys), _i32(probe_keys), C.c_void_p(sel.ctypes.data) if sel is not None else None,
+                                C.c_int(len(conds)), _conds(conds), out, C.byref(n))
     if rc != 0:
         raise RuntimeError(f"oracle join failed: {rc}")
     types = (list(build_types) + list(probe_types)) if outer_is_right else (list(probe_types) + list(build_types))

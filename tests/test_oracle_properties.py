@@ -82,3 +82,51 @@ def test_signed_unsigned_key_equality_is_numeric(pairs):
     got = O.hash_join(INNER, False, [UINT64], [u], [INT64], [i], [0], [0]).num_rows()
     want = sum(1 for a in pairs for b in pairs if b[1] >= 0 and a[0] == b[1])
     assert got == want
+
+
+cond_st = st.tuples(st.integers(0, 5), st.integers(0, 3), st.one_of(st.integers(0, 3), st.none()), st.integers(-2, 5))
+
+
+@settings(max_examples=150, deadline=None)
+@given(rows2, rows2, st.lists(cond_st, min_size=1, max_size=2), st.integers(0, 2))
+def test_other_conditions_filter_matches_and_turn_all_failed_outer_rows_into_misses(lhs, rhs, conds, jt):
+    """joiner.go:155-167,225-248: OtherConditions filter the joined rows of one outer row; an outer row whose joined rows
+    all fail is emitted once with NULLs (outer joins) or not at all (inner join)"""
+    l, r = table(lhs, 2), table(rhs, 2)
+    t2 = [INT64, INT64]
+    oc = [(op, a, b) if b is not None else (op, a, None, INT64, k) for op, a, b, k in conds]
+    if jt == RIGHT:
+        got = O.hash_join(RIGHT, True, t2, l, t2, r, [0], [0], None, oc).rows()
+    else:
+        got = O.hash_join(jt, False, t2, r, t2, l, [0], [0], None, oc).rows()
+
+    def ok(row):
+        for op, a, b, k in conds:
+            x, y = row[a], (row[b] if b is not None else k)
+            if x is None or y is None:
+                return False
+            if not [x < y, x <= y, x > y, x >= y, x == y, x != y][op]:
+                return False
+        return True
+    want = []
+    outer, inner = (rhs, lhs) if jt == RIGHT else (lhs, rhs)
+    for o in map(tuple, outer):
+        rows = []
+        for i in map(tuple, inner):
+            if o[0] is not None and o[0] == i[0]:
+                joined = (i + o) if jt == RIGHT else (o + i)
+                if ok(joined):
+                    rows.append(joined)
+        if not rows and jt != INNER:
+            rows = [((None, None) + o) if jt == RIGHT else (o + (None, None))]
+        want += rows
+    assert sorted(got, key=key) == sorted(want, key=key)
+
+
+def test_other_condition_reference_golden():
+    # executor/join_test.go:137-139: t1 join t on t.a = t1.a and t.a < t1.b -> "1 2 1 1","1 3 1 1","1 4 1 1","3 4 3 3"
+    t1 = [(1, 2), (1, 3), (1, 4), (3, 4), (4, 5)]
+    t = [(1, 1), (2, 2), (3, 3)]
+    l, r = table(t1, 2), table(t, 2)
+    got = O.hash_join(INNER, False, [INT64, INT64], r, [INT64, INT64], l, [0], [0], None, [(0, 2, 1)]).rows()  # t.a (col 2) < t1.b (col 1)
+    assert sorted(got) == [(1, 2, 1, 1), (1, 3, 1, 1), (1, 4, 1, 1), (3, 4, 3, 3)]
