@@ -223,6 +223,19 @@ enum { TQ_JOIN_STABLE_INPUT = 1 };
 typedef struct tq_join tq_join;
 
 int32_t tq_join_create(const tq_join_desc *desc, tq_join **out);
+/* OtherConditions of the joiners (executor/joiner.go:155-167: baseJoiner.filter over the joined rows; an outer row whose
+ * joined rows all fail is emitted once with a NULL inner side).  Each condition compares output column lhs_col (index
+ * into lhs ++ rhs) with output column rhs_col, or with the constant when rhs_col < 0: BIGINT with BIGINT (any sign mix)
+ * or DOUBLE with DOUBLE; all conditions are ANDed.  Call once, right after tq_join_create.  EXPERIMENTAL in round 1
+ * (see DESIGN.md): general expressions stay with the shim, which filters the returned chunk with tq_vec_*. */
+typedef struct tq_join_cond {
+  int32_t op;         /* TQ_CMP_*                                   */
+  int32_t lhs_col;    /* output column                              */
+  int32_t rhs_col;    /* output column, or -1: the constant below   */
+  int32_t const_type; /* TQ_TYPE_* of the constant                  */
+  uint64_t const_bits;
+} tq_join_cond;
+int32_t tq_join_set_other_conditions(tq_join *j, int32_t n_conds, const tq_join_cond *conds);
 int32_t tq_join_put_build(tq_join *j, const tq_column *cols, int32_t mem);
 int32_t tq_join_finalize_build(tq_join *j);
 /* selected: outerSideFilter result (join.go:328), n bytes of 0/1 in HOST memory, or NULL = all selected. */

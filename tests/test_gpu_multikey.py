@@ -2,6 +2,7 @@
 the CPU oracle, which hashes and compares the full key tuple the way the reference does
 (executor/hash_table.go:110-141, util/codec/codec.go:363-382, executor/aggregate.go:359-394)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -214,4 +215,28 @@ def test_group_by_two_columns_partial_then_final(lib):
     got = Chunk([Column(t, np.concatenate(a), np.concatenate(b)) for t, a, b in zip(out_types, vals, nns)])
     rc, want = O.hash_agg(types, [k1, k2, x, v], [0, 1], funcs, 2)
     assert rc == 0
+    assert_same_multiset(got, want)
+
+
+# ------------------------------------------------------------------ OtherConditions on the device (experimental)
+@pytest.mark.skipif(os.environ.get("TQ_RUN_EXPERIMENTS") != "1", reason="OtherConditions device path was written after the round-1 GPU budget was spent; TQ_RUN_EXPERIMENTS=1 runs it")
+@pytest.mark.parametrize("jt,oir", [(INNER_JOIN, False), (INNER_JOIN, True), (LEFT_OUTER_JOIN, False), (RIGHT_OUTER_JOIN, True)])
+@pytest.mark.parametrize("nb,npr", [(0, 50), (300, 2000), (5000, 100000), (300000, 900000)])
+def test_join_other_conditions_experiment(lib, nb, npr, jt, oir):
+    rng = np.random.default_rng(nb + npr + jt)
+    ndv = max(nb // 3, 2)
+    bcols = [gen_col(rng, INT64, nb, 0.05, 0, ndv), gen_col(rng, INT64, nb, 0.1, -50, 50), gen_col(rng, FLOAT64, nb, 0.1)]
+    pcols = [gen_col(rng, FLOAT64, npr, 0.1), gen_col(rng, INT64, npr, 0.05, 0, ndv + 2), gen_col(rng, INT64, npr, 0.1, -50, 50)]
+    bt, pt = [INT64, INT64, FLOAT64], [FLOAT64, INT64, INT64]
+    # output row = lhs ++ rhs; compare the two integer payloads, one double pair, and a constant
+    if oir:   # build side is the left child: out = b0 b1 b2 p0 p1 p2
+        conds = [(0, 1, 5), (3, 2, 3), (5, 5, None, INT64, 7)]    # b1 < p2 and b2 >= p0 and p2 != 7
+    else:     # out = p0 p1 p2 b0 b1 b2
+        conds = [(0, 4, 2), (3, 5, 0), (5, 2, None, INT64, 7)]
+    inner, outer = MockDataSource(bt, bcols, 1 << 16), MockDataSource(pt, pcols, 1 << 16)
+    e = HashJoinExec(outer, inner, [1], [0], jt, oir, None, 1 << 18, other_conditions=conds)
+    e.Open()
+    got = e.drain()
+    e.Close()
+    want = O.hash_join(jt, oir, bt, bcols, pt, pcols, [0], [1], None, conds)
     assert_same_multiset(got, want)

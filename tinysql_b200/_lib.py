@@ -22,6 +22,10 @@ class TQJoinDesc(C.Structure):
                 ("probe_batch_rows", C.c_int64), ("flags", C.c_int32)]
 
 
+class TQJoinCond(C.Structure):
+    _fields_ = [("op", C.c_int32), ("lhs_col", C.c_int32), ("rhs_col", C.c_int32), ("const_type", C.c_int32), ("const_bits", C.c_uint64)]
+
+
 class TQAggFunc(C.Structure):
     _fields_ = [("func", C.c_int32), ("arg_col", C.c_int32)]
 
@@ -60,6 +64,7 @@ SYMBOLS = {
     "tq_vec_lt_plus_int": (_I32, [_I64, _COL, _COL, _COL, _COL, _I32]),
     "tq_vec_filter_int": (_I32, [_I64, _COL, _P, _I32]),
     "tq_join_create": (_I32, [C.POINTER(TQJoinDesc), C.POINTER(_P)]),
+    "tq_join_set_other_conditions": (_I32, [_P, _I32, C.POINTER(TQJoinCond)]),
     "tq_join_put_build": (_I32, [_P, _COL, _I32]), "tq_join_finalize_build": (_I32, [_P]),
     "tq_join_put_probe": (_I32, [_P, _COL, _P, _I32]), "tq_join_probe_eof": (_I32, [_P]),
     "tq_join_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),

@@ -22,6 +22,7 @@
 #include "dict.cuh"
 #include "varlen.cuh"
 #include "scatter.cuh"
+#include "othercond.cuh"
 
 namespace tq {
 
@@ -1544,6 +1545,7 @@ struct ResultBatch {
   // host copies (host-consumer path)
   std::vector<PinBuf> h_data, h_bm;
   std::vector<VarOut> var;   // gathered FLOAT / var-len output columns (indexed like cols)
+  std::vector<DevColBuf> alt;  // OtherConditions: the filtered copy of cols (swapped in)
   bool on_host = false;
   cudaEvent_t ev_ready = nullptr;
   ~ResultBatch() { if (ev_ready) cudaEventDestroy(ev_ready); }
@@ -1597,6 +1599,11 @@ struct tq_join {
   int out_side[2 * MAXC] = {};            // per result-batch column: 0 = plain, 1 = build-side store, 2 = probe-side store
   int out_col[2 * MAXC] = {};
   DevBuf lens_scratch, scan_scratch3;
+  // OtherConditions (experimental, othercond.cuh): applied to every finished result batch
+  bool has_oc = false;
+  OcPlan oc;
+  int p_hidden_rowid = -1;                // outer joins: hidden probe column carrying the row id within the batch
+  DevBuf oc_rowid[2], oc_scratch, oc_scan;
   int64_t batch_rows = 1 << 22;
 
   enum State { BUILDING, PROBING, CLOSED } state = BUILDING;
@@ -2117,6 +2124,28 @@ static int32_t enqueue_d2h(tq_join *j, ResultBatch *rb) {
   return TQ_OK;
 }
 
+// OtherConditions: filter the finished result batch in place (joiner.go:155-167; all-failed outer rows become miss rows).
+static int32_t apply_other_conditions(tq_join *j, ResultBatch *rb, int64_t n_probe_rows) {
+  const int ncols = j->n_build_cols + j->n_probe_cols;
+  if (rb->n == 0) return TQ_OK;
+  rb->alt.resize(ncols);
+  OcCols oc_cols;
+  oc_cols.n = ncols;
+  for (int c = 0; c < ncols; c++) {
+    TQ_TRY(rb->alt[c].data.reserve((size_t)rb->n * 8));
+    TQ_TRY(rb->alt[c].bm.reserve(bitmap_alloc_bytes(rb->n)));
+    oc_cols.data[c] = rb->cols[c].data.as<uint64_t>();
+    oc_cols.bm[c] = rb->cols[c].bm.as<uint32_t>();
+    oc_cols.out_data[c] = rb->alt[c].data.as<uint64_t>();
+    oc_cols.out_bm[c] = rb->alt[c].bm.as<uint32_t>();
+  }
+  int64_t kept = 0;
+  TQ_TRY(oc_filter(j->oc, oc_cols, rb->n, n_probe_rows, j->oc_scratch, j->oc_scan, &kept, rt().compute));
+  std::swap(rb->cols, rb->alt);
+  rb->n = kept;
+  return TQ_OK;
+}
+
 // Wait for the pending batch, re-run it if the output did not fit, queue its result.
 static int32_t finalize_pending(tq_join *j) {
   PendingBatch &pb = j->pending;
@@ -2144,7 +2173,8 @@ static int32_t finalize_pending(tq_join *j) {
     if (cudaEventElapsedTime(&ms, j->ev_a[pb.cursor_slot], j->ev_b[pb.cursor_slot]) == cudaSuccess) j->last_probe_ns = (int64_t)(ms * 1e6);
   }
   pb.rb->n = (int64_t)produced;
-  j->joined_rows_total += (int64_t)produced;
+  if (j->has_oc) TQ_TRY(apply_other_conditions(j, pb.rb.get(), pb.n));
+  j->joined_rows_total += pb.rb->n;
   if (j->any_ind) TQ_TRY(materialize_indirect(j, pb.rb.get(), pb.cursor_slot));  // synchronises the compute stream
   if (pb.want_host) {
     TQ_CUDA(cudaStreamWaitEvent(r.d2h, pb.ev_k, 0));
@@ -2175,6 +2205,14 @@ static int32_t start_batch(tq_join *j, const std::vector<DCol> &probe, const uin
     encoded[j->np_user].data = j->mk_probe_key[slot].as<uint64_t>();
     encoded[j->np_user].bm = j->mk_probe_bm[slot].as<uint32_t>();
     pin = &encoded;
+  }
+  if (j->p_hidden_rowid >= 0) {
+    // OtherConditions on an outer join: every joined row has to know which probe row it came from
+    if (pin == &probe) { encoded = probe; pin = &encoded; }
+    TQ_TRY(j->oc_rowid[slot].reserve((size_t)n * 8));
+    TQ_TRY(iota_u64(j->oc_rowid[slot].as<uint64_t>(), n, r.compute));
+    encoded[j->p_hidden_rowid].data = j->oc_rowid[slot].as<uint64_t>();
+    encoded[j->p_hidden_rowid].bm = nullptr;
   }
   // a join on unique build keys produces at most one row per probe row; with duplicate keys the
   // first launch doubles as the count pass (finalize_pending re-runs with the exact size)
@@ -2400,6 +2438,70 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   if (st == TQ_OK) st = j->cursors_host.reserve(64);
   if (st != TQ_OK) { delete j; return st; }
   *out = j;
+  return TQ_OK;
+}
+
+int32_t tq_join_set_other_conditions(tq_join *j, int32_t n_conds, const tq_join_cond *conds) {
+  if (!j || n_conds < 0 || n_conds > OC_MAX_CONDS || (n_conds && !conds)) { set_error("OtherConditions: 0..%d conditions", OC_MAX_CONDS); return TQ_ERR_INVALID_ARG; }
+  if (j->state != tq_join::BUILDING || j->n_build != 0 || j->has_oc) { set_error("OtherConditions must be set once, right after tq_join_create"); return TQ_ERR_STATE; }
+  if (n_conds == 0) return TQ_OK;
+  const bool outer = j->join_type != TQ_JOIN_INNER;
+  if (outer && j->n_probe_cols + 1 > MAXC) { set_error("OtherConditions on an outer join need one spare probe column"); return TQ_ERR_INVALID_ARG; }
+  const int n_user = j->nb_user + j->np_user;
+  // user output column (lhs ++ rhs) -> (side, column, type)
+  auto side_of = [&](int u, bool *is_build, int *col) {
+    const int first_user = j->outer_is_right ? j->nb_user : j->np_user;
+    const bool first = u < first_user;
+    *is_build = j->outer_is_right ? first : !first;
+    *col = first ? u : u - first_user;
+  };
+  int types[OC_MAX_CONDS][2], sides[OC_MAX_CONDS][2], ccols[OC_MAX_CONDS][2];
+  for (int k = 0; k < n_conds; k++) {
+    const tq_join_cond &q = conds[k];
+    if (q.op < TQ_CMP_LT || q.op > TQ_CMP_NE || q.lhs_col < 0 || q.lhs_col >= n_user || q.rhs_col >= n_user) { set_error("OtherConditions: bad condition %d", k); return TQ_ERR_INVALID_ARG; }
+    for (int o = 0; o < 2; o++) {
+      const int u = o == 0 ? q.lhs_col : q.rhs_col;
+      if (u < 0) { types[k][o] = q.const_type; sides[k][o] = -1; ccols[k][o] = -1; continue; }
+      bool is_build; int col;
+      side_of(u, &is_build, &col);
+      types[k][o] = is_build ? j->build_types[col] : j->probe_types[col];
+      sides[k][o] = is_build ? 1 : 0;
+      ccols[k][o] = col;
+    }
+    const bool fa = types[k][0] == TQ_TYPE_FLOAT64, fb = types[k][1] == TQ_TYPE_FLOAT64;
+    if (!type_ok(types[k][0]) || !type_ok(types[k][1]) || fa != fb) { set_error("OtherConditions compare BIGINT with BIGINT or DOUBLE with DOUBLE columns"); return TQ_ERR_UNSUPPORTED_TYPE; }
+  }
+  if (outer) {  // hidden probe row-id column, last on the probe side
+    j->p_hidden_rowid = j->n_probe_cols;
+    j->probe_types[j->n_probe_cols] = TQ_TYPE_INT64;
+    j->n_probe_cols++;
+    // the result-batch layout moved: recompute the caller -> batch column map and the indirect-column table
+    const int bbase = j->outer_is_right ? 0 : j->n_probe_cols, pbase = j->outer_is_right ? j->n_build_cols : 0;
+    for (int c = 0; c < 2 * MAXC; c++) { j->out_side[c] = 0; j->out_col[c] = 0; }
+    for (int c = 0; c < j->nb_user; c++) if (j->b_ind[c]) { j->out_side[bbase + c] = 1; j->out_col[bbase + c] = c; }
+    for (int c = 0; c < j->np_user; c++) if (j->p_ind[c]) { j->out_side[pbase + c] = 2; j->out_col[pbase + c] = c; }
+    const int first_user = j->outer_is_right ? j->nb_user : j->np_user, first_int = j->outer_is_right ? j->n_build_cols : j->n_probe_cols;
+    j->out_map.clear();
+    for (int u = 0; u < n_user; u++) j->out_map.push_back(u < first_user ? u : u - first_user + first_int);
+  }
+  const int bbase = j->outer_is_right ? 0 : j->n_probe_cols, pbase = j->outer_is_right ? j->n_build_cols : 0;
+  j->oc = OcPlan();
+  j->oc.n_conds = n_conds;
+  j->oc.outer = outer ? 1 : 0;
+  j->oc.build_key_col = bbase + j->build_key;
+  j->oc.rowid_col = outer ? pbase + j->p_hidden_rowid : -1;
+  j->oc.build_lo = bbase;
+  j->oc.build_hi = bbase + j->n_build_cols;
+  for (int k = 0; k < n_conds; k++) {
+    OcCond &d = j->oc.c[k];
+    d.op = conds[k].op;
+    d.lhs = (sides[k][0] ? bbase : pbase) + ccols[k][0];
+    d.rhs = sides[k][1] < 0 ? -1 : (sides[k][1] ? bbase : pbase) + ccols[k][1];
+    d.lhs_type = types[k][0];
+    d.rhs_type = types[k][1];
+    d.cbits = conds[k].const_bits;
+  }
+  j->has_oc = true;
   return TQ_OK;
 }
 

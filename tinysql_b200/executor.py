@@ -46,13 +46,16 @@ class HashJoinExec:
     """executor/join.go:31-146.  inner = build side, outer = probe side; output = left ++ right."""
 
     def __init__(self, outer_exec, inner_exec, outer_keys, inner_keys, join_type=INNER_JOIN, outer_is_right=False,
-                 outer_filter=None, probe_batch_rows=0, max_chunk_size=MAX_CHUNK_SIZE, stable_input=False):
+                 outer_filter=None, probe_batch_rows=0, max_chunk_size=MAX_CHUNK_SIZE, stable_input=False, other_conditions=()):
         self.outer, self.inner = outer_exec, inner_exec
         self.outer_keys, self.inner_keys = list(outer_keys), list(inner_keys)
         self.join_type, self.outer_is_right = join_type, outer_is_right
         self.outer_filter = outer_filter  # callable(chunk) -> selected bytes (expression.VectorizedFilter result)
         self.probe_batch_rows = probe_batch_rows
         self.stable_input = stable_input  # TQ_JOIN_STABLE_INPUT: the children keep every chunk alive and unmodified until Close
+        # OtherConditions (joiner.go:155-167) as (op, lhs_col, rhs_col) or (op, lhs_col, None, const_type, const_value) over
+        # the output row lhs ++ rhs — EXPERIMENTAL device path (tq_join_set_other_conditions)
+        self.other_conditions = list(other_conditions)
         self.max_chunk_size = max_chunk_size
         self.handle = None
         self.prepared = False
@@ -71,6 +74,15 @@ class HashJoinExec:
         h = C.c_void_p()
         L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
         self.handle = h
+        if self.other_conditions:
+            arr = (L.TQJoinCond * len(self.other_conditions))()
+            for i, c in enumerate(self.other_conditions):
+                if c[2] is None:
+                    np_t = {INT64: np.int64, UINT64: np.uint64, FLOAT64: np.float64}[c[3]]
+                    arr[i] = L.TQJoinCond(c[0], c[1], -1, c[3], int(np.array([c[4]], dtype=np_t).view(np.uint64)[0]))
+                else:
+                    arr[i] = L.TQJoinCond(c[0], c[1], c[2], 0, 0)
+            L.check(lib.tq_join_set_other_conditions(h, len(self.other_conditions), arr))
         self.prepared = False
         self.outer_done = False
 
