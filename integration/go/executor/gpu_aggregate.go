@@ -19,6 +19,7 @@ import (
 	"github.com/pingcap/tidb/expression/aggregation"
 	"github.com/pingcap/tidb/parser/ast"
 	"github.com/pingcap/tidb/parser/mysql"
+	"github.com/pingcap/tidb/types"
 	"github.com/pingcap/tidb/util/chunk"
 )
 
@@ -131,6 +132,14 @@ func (e *GPUHashAggExec) Next(ctx context.Context, req *chunk.Chunk) error {
 	}
 	req.SetNumVirtualRows(int(n))
 	return nil
+}
+
+// statusToAggError: SUM / AVG over BIGINT report types.ErrOverflow like types.AddInt64 does (func_sum.go:133-136).
+func statusToAggError(st C.int32_t) error {
+	if st == C.TQ_ERR_OVERFLOW_BIGINT {
+		return types.ErrOverflow.GenWithStackByArgs("BIGINT", "sum")
+	}
+	return chunk.StatusError(int32(st))
 }
 
 // Close implements Executor; Close may run after Open without Next (aggregate.go:187-197).
