@@ -259,6 +259,14 @@ int32_t tq_join_next_device(tq_join *j, tq_column *out_cols, int64_t *n_rows, in
  * [6] last build time in ns, [7] probe kernel launches.  */
 int32_t tq_join_stats(tq_join *j, int64_t *stats8);
 
+/* ------------------------------------------------------------------ chunk wire codec (host only)
+ * chunk.Codec.Encode / DecodeToChunk (util/chunk/codec.go:42-143) — the bytes child readers hand up.  Decoding fills
+ * tq_column VIEWS into the buffer (zero copy; null_bitmap == NULL for a column without NULLs), ready for
+ * tq_join_put_* / tq_agg_put.  No device is needed for these three calls. */
+int32_t tq_chunk_encoded_size(int32_t n_cols, const int32_t *types, const tq_column *cols, int64_t *bytes);
+int32_t tq_chunk_encode(int32_t n_cols, const int32_t *types, const tq_column *cols, uint8_t *buffer, int64_t capacity, int64_t *written);
+int32_t tq_chunk_decode(const uint8_t *buffer, int64_t len, int32_t n_cols, const int32_t *types, tq_column *out, int64_t *consumed);
+
 /* ------------------------------------------------------------------ hash agg
  * Replaces HashAggExec + workers (executor/aggregate.go) and the aggfuncs it drives
  * (executor/aggfuncs/ sources).  GROUP BY items and aggregate arguments are column

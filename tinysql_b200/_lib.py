@@ -63,6 +63,9 @@ SYMBOLS = {
     "tq_vec_in_int": (_I32, [_I64, _COL, _I32, _I32, _COL, C.POINTER(_I32), _COL, _I32]),
     "tq_vec_lt_plus_int": (_I32, [_I64, _COL, _COL, _COL, _COL, _I32]),
     "tq_vec_filter_int": (_I32, [_I64, _COL, _P, _I32]),
+    "tq_chunk_encoded_size": (_I32, [_I32, C.POINTER(_I32), _COL, C.POINTER(_I64)]),
+    "tq_chunk_encode": (_I32, [_I32, C.POINTER(_I32), _COL, _P, _I64, C.POINTER(_I64)]),
+    "tq_chunk_decode": (_I32, [_P, _I64, _I32, C.POINTER(_I32), _COL, C.POINTER(_I64)]),
     "tq_join_create": (_I32, [C.POINTER(TQJoinDesc), C.POINTER(_P)]),
     "tq_join_set_other_conditions": (_I32, [_P, _I32, C.POINTER(TQJoinCond)]),
     "tq_join_put_build": (_I32, [_P, _COL, _I32]), "tq_join_finalize_build": (_I32, [_P]),

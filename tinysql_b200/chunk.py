@@ -233,3 +233,47 @@ def device_to_host(tp, data_ptr, bm_ptr, n):
         else:
             out.bitmap = None
     return out
+
+
+# ---------------------------------------------------------------------------------------------- chunk wire codec
+def encode_chunk(types, cols):
+    """chunk.Codec.Encode (util/chunk/codec.go:42-79) through the C-ABI: the wire bytes of the chunk."""
+    lib = L.load()
+    t = (C.c_int32 * max(len(types), 1))(*types)
+    arr = tq_array(cols)
+    need = C.c_int64(0)
+    L.check(lib.tq_chunk_encoded_size(len(cols), t, arr, C.byref(need)))
+    buf = np.zeros(max(need.value, 1), dtype=np.uint8)
+    written = C.c_int64(0)
+    L.check(lib.tq_chunk_encode(len(cols), t, arr, buf.ctypes.data, need.value, C.byref(written)))
+    return buf[: written.value].tobytes()
+
+
+def decode_chunk(buf, types):
+    """chunk.Codec.DecodeToChunk (codec.go:92-143) through the C-ABI.  Returns (Chunk, bytes consumed); the columns are
+    copied out of the views here (the views themselves are what a Go caller passes on to tq_join_put_probe)."""
+    lib = L.load()
+    raw = np.frombuffer(buf, dtype=np.uint8)
+    t = (C.c_int32 * max(len(types), 1))(*types)
+    out = (L.TQColumn * max(len(types), 1))()
+    used = C.c_int64(0)
+    L.check(lib.tq_chunk_decode(raw.ctypes.data if raw.size else None, raw.size, len(types), t, out, C.byref(used)))
+    base = raw.ctypes.data
+    cols = []
+    for tp, v in zip(types, out):
+        n = v.length
+        nn = None
+        if v.null_bitmap:
+            o = v.null_bitmap - base
+            nn = unpack_not_null(raw[o: o + bitmap_bytes(n)], n)
+        if tp == BYTES:
+            oo = v.offsets - base
+            offs = raw[oo: oo + (n + 1) * 8].view(np.int64)
+            d0 = (v.data - base) if v.data else 0
+            cells = [raw[d0 + offs[i]: d0 + offs[i + 1]].tobytes() for i in range(n)]
+            cols.append(VarColumn(BYTES, [c if (nn is None or nn[i]) else None for i, c in enumerate(cells)], nn))
+        else:
+            w = 4 if tp == FLOAT32 else 8
+            d0 = (v.data - base) if v.data else 0
+            cols.append(Column(tp, raw[d0: d0 + n * w].view(_NP[tp]).copy(), nn))
+    return Chunk(cols), used.value
