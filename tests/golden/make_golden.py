@@ -46,6 +46,17 @@ JOIN = [
          where="r[2] < r[1]", expect=[[1, 2, 1, 1], [1, 3, 1, 1], [1, 4, 1, 1], [3, 4, 3, 3]]),
     dict(name="right_outer_unmatched_row", cite="executor/join_test.go:144-146", lhs=ta, rhs=tb, lkey=[0], rkey=[0], type="right",
          expect=[[1, 1, 1, 2], [1, 1, 1, 3], [1, 1, 1, 4], [3, 3, 3, 4], [N, N, 4, 5]]),
+    dict(name="issue5255_varchar_and_float_payload", cite="executor/join_test.go:337-346 (t1(a int, b varchar(64), c float) join t2(a))",
+         lhs=[[1, "2017-11-29", 2.2]], rhs=[[1]], ltypes=[I, B, "float32"], rtypes=[I], lkey=[0], rkey=[0], type="inner",
+         expect=[[1, "2017-11-29", 2.2, 1]]),
+    dict(name="two_column_key_self_join", cite="executor/join_test.go:381-388 (t t1 join t t2 on t1.b = t2.b and t1.a = t2.a)",
+         lhs=[[1, 1], [1, 2], [2, 1], [2, 2]], rhs=[[1, 1], [1, 2], [2, 1], [2, 2]], lkey=[1, 0], rkey=[1, 0], type="inner",
+         expect=[[1, 1, 1, 1], [1, 2, 1, 2], [2, 1, 2, 1], [2, 2, 2, 2]]),
+    dict(name="left_outer_no_key_match_with_outer_condition", cite="executor/join_test.go:372-379 (t1 left outer join t2 on t1.a=t2.a and t1.a!=3)",
+         lhs=[[i, 100] for i in range(1, 6)], rhs=[[i * 100, 10000] for i in range(1, 6)], lkey=[0], rkey=[0], type="left",
+         outer_selected=[1, 1, 0, 1, 1], expect=[[i, 100, N, N] for i in range(1, 6)]),
+    dict(name="issue5278_second_left_join", cite="executor/join_test.go:348-356 ((t left join tt) left join t ttt on t.a=ttt.a; tt is empty)",
+         lhs=[[1, 1, N, N]], rhs=[[1, 1]], lkey=[0], rkey=[0], type="left", expect=[[1, 1, N, N, 1, 1]]),
     dict(name="inner_100x100_limit_1_then_close", cite="executor/join_test.go:175-182", lhs=[[1]] * 100, rhs=[[1]] * 100, lkey=[0], rkey=[0],
          type="inner", limit=1, expect=[[1, 1]], total_rows=10000),
 ]
