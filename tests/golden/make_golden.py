@@ -140,6 +140,16 @@ EXPR += [
     dict(op="lt", cite="expression/builtin_compare_test.go:35", args=[[B, "123"], [B, "123"]], expect=[I, 0]),
 ]
 
+# ---- expression/evaluator_test.go TestUnaryOp (:117-139), expression/builtin_test.go TestIsNullFunc (:54-68)
+EXPR += [
+    dict(op="neg", cite="expression/evaluator_test.go:124", args=[[F, N]], expect=[F, N]),
+    dict(op="neg", cite="expression/evaluator_test.go:125", args=[[F, 1.0]], expect=[F, -1.0]),
+    dict(op="neg", cite="expression/evaluator_test.go:126", args=[[I, 1]], expect=[I, -1]),
+    dict(op="neg", cite="expression/evaluator_test.go:128", args=[[U, 1]], expect=[I, -1]),
+    dict(op="isnull", cite="expression/builtin_test.go:56-60", args=[[I, 1]], expect=[I, 0]),
+    dict(op="isnull", cite="expression/builtin_test.go:62-66", args=[[I, N]], expect=[I, 1]),
+]
+
 # ---- util/codec/codec_test.go TestHashChunkRow (:735-769) as join-key equalities
 KEYEQ = [
     dict(cite="util/codec/codec_test.go:741-747", a=[U, 1], b=[I, 1], equal=True),

@@ -63,6 +63,11 @@ class OracleEngine:
         assert rc == 0
         return out
 
+    def unary(self, op, a):
+        rc, out = O.vec_unary(op, a)
+        assert rc == 0
+        return out
+
     def in_int(self, a, lst):
         rc, out = O.vec_in_int(a, lst)
         assert rc == 0
@@ -106,6 +111,10 @@ class GpuEngine:
     def length(self, a):
         from tinysql_b200 import expression as E
         return E.vec_string_unary(E.STR_LENGTH, a)
+
+    def unary(self, op, a):
+        from tinysql_b200 import expression as E
+        return E.vec_unary(op, a)
 
     def in_int(self, a, lst):
         from tinysql_b200 import expression as E
@@ -202,6 +211,10 @@ def test_reference_builtin_goldens(engine, case):
         out = engine.compare(CMP[case["op"]], args[0], args[1])
     elif case["op"] == "length":
         out = engine.length(args[0])
+    elif case["op"] == "neg":
+        out = engine.unary(E.MINUS_REAL if args[0].tp == FLOAT64 else E.MINUS_INT, args[0])
+    elif case["op"] == "isnull":
+        out = engine.unary(E.ISNULL, args[0])
     else:
         out = engine.in_int(args[0], args[1:])
     tp, want = TP[case["expect"][0]], case["expect"][1]
