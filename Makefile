@@ -8,7 +8,8 @@ LIB = tinysql_b200/lib/libtinysql_b200.so
 
 all: $(LIB) oracle
 
-build/%.o: tinysql_b200/csrc/%.cu tinysql_b200/csrc/common.cuh tinysql_b200/csrc/dict.cuh tinysql_b200/csrc/varlen.cuh tinysql_b200/csrc/scatter.cuh include/tinysql_b200.h
+HDR = $(wildcard tinysql_b200/csrc/*.cuh) include/tinysql_b200.h
+build/%.o: tinysql_b200/csrc/%.cu $(HDR)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

@@ -45,9 +45,11 @@ enum {
   TQ_TYPE_INT64 = 1,   /* TINY..LONGLONG, YEAR (signed)            */
   TQ_TYPE_UINT64 = 2,  /* same, with mysql.UnsignedFlag            */
   TQ_TYPE_FLOAT64 = 3, /* DOUBLE                                   */
-  TQ_TYPE_FLOAT32 = 4, /* FLOAT (4-byte slots)     — HashJoin payload (non-key) columns, host memory      */
-  TQ_TYPE_BYTES = 5,   /* var-len (offsets + data) — HashJoin payload (non-key) columns, host memory:
-                        *   offsets = length+1 int64 (Go's Column.offsets), data = the cells' bytes            */
+  TQ_TYPE_FLOAT32 = 4, /* FLOAT (4-byte slots).  HashJoin key or payload column, HashAgg GROUP BY item or argument; as a key /
+                        *   group item / argument it counts as float64(f) (util/codec/codec.go:226-229).  Host memory only. */
+  TQ_TYPE_BYTES = 5,   /* var-len (VARCHAR, BLOB, ...): offsets = length+1 int64 (Go's Column.offsets), data = the cells' bytes.
+                        *   HashJoin key or payload, HashAgg GROUP BY item or COUNT / MAX / MIN / FIRSTROW argument; compared
+                        *   byte-wise (compactBytesFlag, codec.go:230-233).  Host memory only.                              */
   /* OR-ed into a tq_agg_desc.input_types entry: the column's FieldType carries mysql.NotNullFlag.  Lets HashAgg
    * drop the per-group "saw a non-NULL input" word of SUM / MAX / MIN (16-byte instead of 32-byte group records
    * for SUM + COUNT); any null bitmap passed for such a column is ignored. */
@@ -206,7 +208,7 @@ typedef struct tq_join_desc {
   const int32_t *build_types; /* TQ_TYPE_* per inner column                                   */
   int32_t n_probe_cols;       /* outer-side schema                                            */
   const int32_t *probe_types;
-  int32_t n_keys;             /* len(innerKeys) == len(outerKeys), 1..8; key columns are 8-byte types */
+  int32_t n_keys;             /* len(innerKeys) == len(outerKeys), 1..8; any supported column type (codec.go:216-236) */
   const int32_t *build_key_idx; /* innerKeys[i].Index                                         */
   const int32_t *probe_key_idx; /* outerKeys[i].Index                                         */
   int64_t probe_batch_rows;   /* device batch size the ≤1024-row chunks are accumulated into; 0 = default */
@@ -304,6 +306,9 @@ int32_t tq_agg_output_type(tq_agg *a, int32_t func_idx, int32_t *type_out);
 int32_t tq_agg_put(tq_agg *a, const tq_column *cols, int32_t mem);
 int32_t tq_agg_eof(tq_agg *a);
 int32_t tq_agg_next(tq_agg *a, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+/* Data bytes each output column of the NEXT tq_agg_next(a, max_rows, ...) call will carry (8 * rows; 4 * rows for a FLOAT
+ * result; the cells' total length for a var-len result), so the caller can size out_cols[c].data. */
+int32_t tq_agg_next_bytes(tq_agg *a, int64_t max_rows, int64_t *bytes_per_col);
 int32_t tq_agg_next_device(tq_agg *a, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
 int32_t tq_agg_destroy(tq_agg *a);
 /* [0] input rows, [1] groups, [2] last update-kernel time ns, [3] kernel launches */

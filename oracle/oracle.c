@@ -41,17 +41,24 @@ static void merge_nulls(orc_column *o, const orc_column *a, int64_t n) {
 }
 
 /* ------------------------------------------------------------------ key encoding + FNV-1 */
-enum { NIL_FLAG = 0, FLOAT_FLAG = 5, VARINT_FLAG = 8, UVARINT_FLAG = 9 }; /* util/codec/codec.go:34-43 */
+enum { NIL_FLAG = 0, COMPACT_BYTES_FLAG = 2, FLOAT_FLAG = 5, VARINT_FLAG = 8, UVARINT_FLAG = 9 }; /* util/codec/codec.go:32-45 */
 
-/* encodeHashChunkRowIdx (util/codec/codec.go:212-240): (flag, raw 8 bytes) */
-static int encode_key(int type, const orc_column *c, int64_t row, uint8_t *flag, uint64_t *raw) {
-  if (col_is_null(c, row)) { *flag = NIL_FLAG; *raw = 0; return 1; }
-  *raw = col_u64(c, row);
+/* encodeHashChunkRowIdx (util/codec/codec.go:212-240): (flag, raw bytes).  *raw holds the 8 raw bytes of the fixed-width
+ * types; for the var-len types (*bytes, *blen) is the cell (row.GetBytes). */
+static int encode_key(int type, const orc_column *c, int64_t row, uint8_t *flag, uint64_t *raw, const uint8_t **bytes, int64_t *blen) {
+  *bytes = NULL; *blen = 8;
+  if (col_is_null(c, row)) { *flag = NIL_FLAG; *raw = 0; *blen = 0; return 1; }
   switch (type) {
-    case ORC_TYPE_INT64: *flag = VARINT_FLAG; break;
-    case ORC_TYPE_UINT64: *flag = (col_i64(c, row) < 0) ? UVARINT_FLAG : VARINT_FLAG; break; /* :220-224 */
-    case ORC_TYPE_FLOAT64: *flag = FLOAT_FLAG; break;
-    default: *flag = 0xFF; break;
+    case ORC_TYPE_INT64: *raw = col_u64(c, row); *flag = VARINT_FLAG; break;
+    case ORC_TYPE_UINT64: *raw = col_u64(c, row); *flag = (col_i64(c, row) < 0) ? UVARINT_FLAG : VARINT_FLAG; break; /* :220-224 */
+    case ORC_TYPE_FLOAT64: *raw = col_u64(c, row); *flag = FLOAT_FLAG; break;
+    case ORC_TYPE_FLOAT32: { /* :226-229: f := float64(row.GetFloat32(idx)) */
+      float f; memcpy(&f, c->data + 4 * row, 4);
+      double d = (double)f; memcpy(raw, &d, 8); *flag = FLOAT_FLAG; break;
+    }
+    case ORC_TYPE_BYTES: /* :230-233 compactBytesFlag + row.GetBytes(idx) */
+      *flag = COMPACT_BYTES_FLAG; *raw = 0; *bytes = c->data + c->offsets[row]; *blen = c->offsets[row + 1] - c->offsets[row]; break;
+    default: *flag = 0xFF; *raw = 0; break;
   }
   return 0;
 }
@@ -65,11 +72,12 @@ uint64_t orc_hash_row(int n_keys, const int *types, const orc_column *cols, cons
   int hn = 0;
   for (int k = 0; k < n_keys; k++) {
     int ci = key_idx[k];
-    uint8_t flag; uint64_t raw;
-    int isnull = encode_key(types[ci], &cols[ci], row, &flag, &raw);
+    uint8_t flag; uint64_t raw; const uint8_t *bytes; int64_t blen;
+    int isnull = encode_key(types[ci], &cols[ci], row, &flag, &raw, &bytes, &blen);
     h = fnv1_byte(h, flag);                     /* h[i].Write(buf)  codec.go:273 */
     if (isnull) { hn = 1; continue; }           /* b = nil; isNull[i] = true  codec.go:263-264 */
-    for (int b = 0; b < 8; b++) h = fnv1_byte(h, (uint8_t)(raw >> (8 * b))); /* h[i].Write(b) little-endian raw */
+    if (flag == COMPACT_BYTES_FLAG) { for (int64_t b = 0; b < blen; b++) h = fnv1_byte(h, bytes[b]); }  /* h[i].Write(column.GetBytes(i)) codec.go:330-331 */
+    else for (int b = 0; b < 8; b++) h = fnv1_byte(h, (uint8_t)(raw >> (8 * b))); /* h[i].Write(b) little-endian raw */
   }
   if (has_null) *has_null = hn;
   return h;
@@ -77,13 +85,16 @@ uint64_t orc_hash_row(int n_keys, const int *types, const orc_column *cols, cons
 
 int orc_equal_row(int n_keys, const int *types1, const orc_column *cols1, const int *idx1, int64_t row1,
                   const int *types2, const orc_column *cols2, const int *idx2, int64_t row2) {
-  for (int k = 0; k < n_keys; k++) { /* util/codec/codec.go:367-380 */
-    uint8_t f1, f2; uint64_t r1, r2;
-    int n1 = encode_key(types1[idx1[k]], &cols1[idx1[k]], row1, &f1, &r1);
-    int n2 = encode_key(types2[idx2[k]], &cols2[idx2[k]], row2, &f2, &r2);
+  for (int k = 0; k < n_keys; k++) { /* util/codec/codec.go:367-380: flag1 == flag2 && bytes.Equal(b1, b2) */
+    uint8_t f1, f2; uint64_t r1, r2; const uint8_t *b1, *b2; int64_t l1, l2;
+    int n1 = encode_key(types1[idx1[k]], &cols1[idx1[k]], row1, &f1, &r1, &b1, &l1);
+    int n2 = encode_key(types2[idx2[k]], &cols2[idx2[k]], row2, &f2, &r2, &b2, &l2);
     if (f1 != f2) return 0;
     if (n1 != n2) return 0;
-    if (!n1 && r1 != r2) return 0;
+    if (n1) continue;
+    if (l1 != l2) return 0;
+    if (f1 == COMPACT_BYTES_FLAG) { if (l1 && memcmp(b1, b2, (size_t)l1)) return 0; }
+    else if (r1 != r2) return 0;
   }
   return 1;
 }
@@ -283,8 +294,7 @@ int orc_hash_join_cond(int join_type, int outer_is_right,
   }
   for (int c = 0; c < n_build_cols; c++) if (build_types[c] < 1 || build_types[c] > 5) return ORC_ERR_UNSUPPORTED;
   for (int c = 0; c < n_probe_cols; c++) if (probe_types[c] < 1 || probe_types[c] > 5) return ORC_ERR_UNSUPPORTED;
-  /* key columns: the 8-byte types only (FLOAT / var-len keys are not restated — "unsupport column type", codec.go:235) */
-  for (int k = 0; k < n_keys; k++) if (build_types[build_key_idx[k]] > 3 || probe_types[probe_key_idx[k]] > 3) return ORC_ERR_UNSUPPORTED;
+  /* key columns: every supported chunk type (codec.go:216-236: integers, FLOAT as float64(f), DOUBLE, var-len bytes) */
   int64_t nb = n_build_cols ? build_cols[0].length : 0, np = n_probe_cols ? probe_cols[0].length : 0;
 
   /* fetchAndBuildHashTable [stub join.go:148] + hashRowContainer.PutChunk (hash_table.go:146-169) */
@@ -363,9 +373,60 @@ static int add_int64(int64_t a, int64_t b, int64_t *r) {
   *r = a + b; return ORC_OK;
 }
 
+/* Byte strings inside the oracle's aggregation: every distinct cell is interned once (deep copy, like stringutil.Copy in
+ * func_max_min.go:352 / func_first_row.go:216) and states / group keys hold the intern id.  Interning is by byte equality. */
+typedef struct { uint8_t **str; int64_t *len; int64_t n, cap; int64_t *slots; int64_t n_slots; } str_pool;
+static str_pool g_pool;
+static void pool_reset(void) {
+  for (int64_t i = 0; i < g_pool.n; i++) free(g_pool.str[i]);
+  free(g_pool.str); free(g_pool.len); free(g_pool.slots); memset(&g_pool, 0, sizeof(g_pool));
+}
+static uint64_t pool_hash(const uint8_t *b, int64_t n) { uint64_t h = 14695981039346656037ULL; for (int64_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ULL; return h; }
+static int64_t pool_intern(const uint8_t *b, int64_t n) {
+  str_pool *m = &g_pool;
+  if ((m->n + 1) * 2 > m->n_slots) {
+    m->n_slots = m->n_slots ? m->n_slots * 2 : 1024;
+    m->slots = (int64_t *)realloc(m->slots, 8 * (size_t)m->n_slots);
+    for (int64_t i = 0; i < m->n_slots; i++) m->slots[i] = -1;
+    for (int64_t g = 0; g < m->n; g++) { int64_t s = (int64_t)(pool_hash(m->str[g], m->len[g]) & (uint64_t)(m->n_slots - 1)); while (m->slots[s] >= 0) s = (s + 1) & (m->n_slots - 1); m->slots[s] = g; }
+  }
+  int64_t s = (int64_t)(pool_hash(b, n) & (uint64_t)(m->n_slots - 1));
+  while (m->slots[s] >= 0) { int64_t g = m->slots[s]; if (m->len[g] == n && (n == 0 || !memcmp(m->str[g], b, (size_t)n))) return g; s = (s + 1) & (m->n_slots - 1); }
+  if (m->n == m->cap) { m->cap = m->cap ? m->cap * 2 : 1024; m->str = (uint8_t **)realloc(m->str, sizeof(uint8_t *) * (size_t)m->cap); m->len = (int64_t *)realloc(m->len, 8 * (size_t)m->cap); }
+  m->str[m->n] = (uint8_t *)malloc((size_t)(n ? n : 1)); if (n) memcpy(m->str[m->n], b, (size_t)n); m->len[m->n] = n;
+  m->slots[s] = m->n;
+  return m->n++;
+}
+static int compare_string(const uint8_t *x, int64_t lx, const uint8_t *y, int64_t ly);
+/* the value of cell `row` as the 8-byte word the states work on: FLOAT -> float64(f) bits (Column.VecEvalReal widens,
+ * expression/column.go:95-110), var-len -> intern id, everything else the raw slot */
+static uint64_t cell_word(int type, const orc_column *c, int64_t row) {
+  if (type == ORC_TYPE_FLOAT32) { float f; memcpy(&f, c->data + 4 * row, 4); double d = (double)f; uint64_t w; memcpy(&w, &d, 8); return w; }
+  if (type == ORC_TYPE_BYTES) return (uint64_t)pool_intern(c->data + c->offsets[row], c->offsets[row + 1] - c->offsets[row]);
+  return col_u64(c, row);
+}
+
 /* UpdatePartialResult for one input row */
 static int state_update(int func, int type, const orc_column *arg, int64_t row, agg_state *s) {
   int isnull = arg ? col_is_null(arg, row) : 0;    /* arg == NULL: constant 1 (COUNT(*) == count(1), parser.y:3258-3262) */
+  orc_column wcol; uint64_t wv;
+  if (arg && (type == ORC_TYPE_FLOAT32 || type == ORC_TYPE_BYTES)) {
+    /* FLOAT arguments are evaluated as float64 (EvalReal), strings by value: re-express the cell as one 8-byte word */
+    wv = isnull ? 0 : cell_word(type, arg, row);
+    wcol.length = 1; wcol.null_bitmap = NULL; wcol.offsets = NULL; wcol.data = (uint8_t *)&wv;
+    uint8_t nb = (uint8_t)(isnull ? 0 : 1); wcol.null_bitmap = &nb;
+    if (type == ORC_TYPE_FLOAT32) return state_update(func, ORC_TYPE_FLOAT64, &wcol, 0, s);
+    if (func == AGG_COUNT) { if (!isnull) s->i++; return ORC_OK; }                   /* countOriginal4String func_count.go */
+    if (func == AGG_FIRSTROW) { if (s->got_first) return ORC_OK; s->got_first = 1; s->is_null = (uint8_t)isnull; s->si = (int64_t)wv; return ORC_OK; }  /* func_first_row.go:206-220 */
+    if (func == AGG_MAX || func == AGG_MIN) {                                         /* maxMin4String func_max_min.go:337-361 */
+      if (isnull) return ORC_OK;
+      if (s->is_null) { s->si = (int64_t)wv; s->is_null = 0; return ORC_OK; }
+      int cmp = compare_string(g_pool.str[wv], g_pool.len[wv], g_pool.str[s->si], g_pool.len[s->si]);
+      if ((func == AGG_MAX && cmp == 1) || (func == AGG_MIN && cmp == -1)) s->si = (int64_t)wv;
+      return ORC_OK;
+    }
+    return ORC_ERR_UNSUPPORTED;                                                       /* SUM / AVG over strings arrive behind a cast */
+  }
   switch (func) {
     case AGG_COUNT: if (!isnull) s->i++; return ORC_OK;                    /* func_count.go:33-49 */
     case AGG_SUM:
@@ -412,6 +473,7 @@ static int state_update(int func, int type, const orc_column *arg, int64_t row, 
 
 /* MergePartialResult(src, dst) */
 static int state_merge(int func, int type, const agg_state *src, agg_state *dst) {
+  if (type == ORC_TYPE_FLOAT32) type = ORC_TYPE_FLOAT64;   /* states of FLOAT arguments hold float64(f) */
   switch (func) {
     case AGG_COUNT: dst->i += src->i; return ORC_OK;                       /* func_count.go:115-119 */
     case AGG_SUM:
@@ -426,6 +488,11 @@ static int state_merge(int func, int type, const agg_state *src, agg_state *dst)
       if (src->is_null) return ORC_OK;                                      /* func_max_min.go:105-118 */
       if (dst->is_null) { *dst = *src; return ORC_OK; }
       int is_max = (func == AGG_MAX);
+      if (type == ORC_TYPE_BYTES) {                                         /* func_max_min.go:363-376 */
+        int cmp = compare_string(g_pool.str[src->si], g_pool.len[src->si], g_pool.str[dst->si], g_pool.len[dst->si]);
+        if ((is_max && cmp == 1) || (!is_max && cmp == -1)) dst->si = src->si;
+        return ORC_OK;
+      }
       if (type == ORC_TYPE_FLOAT64) { if ((is_max && src->sf > dst->sf) || (!is_max && src->sf < dst->sf)) dst->sf = src->sf; }
       else if (type == ORC_TYPE_UINT64) { uint64_t a = (uint64_t)src->si, b = (uint64_t)dst->si; if ((is_max && a > b) || (!is_max && a < b)) dst->si = src->si; }
       else { if ((is_max && src->si > dst->si) || (!is_max && src->si < dst->si)) dst->si = src->si; }
@@ -437,8 +504,28 @@ static int state_merge(int func, int type, const agg_state *src, agg_state *dst)
 }
 
 /* AppendFinalResult2Chunk */
+static void ob_push_str(outbuf *b, int64_t id) { /* AppendString / AppendNull (id < 0) of a var-len result column */
+  orc_column c; int64_t off[2] = {0, 0}; uint8_t nb = 1;
+  c.length = 1; c.null_bitmap = &nb; c.offsets = off; c.data = NULL;
+  if (id >= 0) { off[1] = g_pool.len[id]; c.data = g_pool.str[id]; ob_push_cell(b, &c, 0); } else ob_push_cell(b, &c, -1);
+}
 static void state_final(int func, int type, const agg_state *s, outbuf *ob) {
   uint64_t bits;
+  if (type == ORC_TYPE_BYTES && func != AGG_COUNT) {   /* maxMin4String / firstRow4String AppendFinalResult2Chunk */
+    int isnull = (func == AGG_FIRSTROW) ? (s->is_null || !s->got_first) : s->is_null;
+    ob_push_str(ob, isnull ? -1 : s->si);
+    return;
+  }
+  if (type == ORC_TYPE_FLOAT32 && (func == AGG_MAX || func == AGG_MIN || func == AGG_FIRSTROW)) {
+    /* maxMin4Float32 / firstRow4Float32 keep a float32 and AppendFloat32 it (func_max_min.go:214-271, func_first_row.go:101-146);
+     * the state above holds float64(f), which narrows back exactly */
+    int isnull = (func == AGG_FIRSTROW) ? (s->is_null || !s->got_first) : s->is_null;
+    double d; if (func == AGG_FIRSTROW) memcpy(&d, &s->si, 8); else d = s->sf;
+    float f = (float)d; uint32_t w; memcpy(&w, &f, 4);
+    ob_push(ob, isnull ? 0 : w, !isnull);
+    return;
+  }
+  if (type == ORC_TYPE_FLOAT32) type = ORC_TYPE_FLOAT64;
   switch (func) {
     case AGG_COUNT: ob_push(ob, (uint64_t)s->i, 1); return;                /* func_count.go:23-27 */
     case AGG_SUM: case AGG_MAX: case AGG_MIN:
@@ -487,7 +574,10 @@ int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int
                  int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_func *funcs,
                  int n_partial_workers, orc_column *out_cols, int64_t *n_out) {
   if (n_partial_workers < 1) n_partial_workers = 1;
-  for (int c = 0; c < n_input_cols; c++) if (types[c] < 1 || types[c] > 3) return ORC_ERR_UNSUPPORTED;
+  for (int c = 0; c < n_input_cols; c++) if (types[c] < 1 || types[c] > 5) return ORC_ERR_UNSUPPORTED;
+  for (int f = 0; f < n_funcs; f++)
+    if (funcs[f].arg_col >= 0 && types[funcs[f].arg_col] == ORC_TYPE_BYTES && (funcs[f].func == AGG_SUM || funcs[f].func == AGG_AVG)) return ORC_ERR_UNSUPPORTED;
+  pool_reset();
   int *fn = (int *)malloc(sizeof(int) * (size_t)(n_funcs ? n_funcs : 1));
   int *ft = (int *)malloc(sizeof(int) * (size_t)(n_funcs ? n_funcs : 1));
   for (int f = 0; f < n_funcs; f++) { fn[f] = funcs[f].func; ft[f] = funcs[f].arg_col >= 0 ? types[funcs[f].arg_col] : ORC_TYPE_INT64; }
@@ -501,7 +591,8 @@ int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int
     for (int g = 0; g < n_group_by; g++) {
       const orc_column *c = &cols[group_by_cols[g]];
       int isnull = col_is_null(c, i);
-      key[2 * g] = (uint64_t)isnull; key[2 * g + 1] = isnull ? 0 : col_u64(c, i);   /* NilFlag: NULL is its own group */
+      /* NilFlag: NULL is its own group; FLOAT items are evaluated as float64 (getGroupKey -> VecEvalReal), strings by their bytes */
+      key[2 * g] = (uint64_t)isnull; key[2 * g + 1] = isnull ? 0 : cell_word(types[group_by_cols[g]], c, i);
     }
     int64_t gi = amap_get(&partial[w], key, fn);
     for (int f = 0; f < n_funcs && rc == ORC_OK; f++)
@@ -517,13 +608,16 @@ int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int
         rc = state_merge(fn[f], ft[f], &partial[w].states[g * n_funcs + f], &fin.states[gi * n_funcs + f]);
     }
   outbuf *obs = (outbuf *)calloc((size_t)(n_funcs ? n_funcs : 1), sizeof(outbuf));
-  for (int f = 0; f < n_funcs; f++) obs[f].elem = 8;
+  for (int f = 0; f < n_funcs; f++) {
+    int sel = (fn[f] == AGG_MAX || fn[f] == AGG_MIN || fn[f] == AGG_FIRSTROW);
+    obs[f].elem = (sel && ft[f] == ORC_TYPE_BYTES) ? 0 : ((sel && ft[f] == ORC_TYPE_FLOAT32) ? 4 : 8);
+  }
   if (rc == ORC_OK) {
     if (fin.n == 0 && n_group_by == 0) {
       /* empty input, no GROUP BY: defaultVal row (aggregate.go:572-574, builder.go:517-540):
        * COUNT -> 0, everything else NULL.  (all-FIRSTROW aggregates produce no row.) */
       int all_first = 1; for (int f = 0; f < n_funcs; f++) if (fn[f] != AGG_FIRSTROW) all_first = 0;
-      if (!all_first) for (int f = 0; f < n_funcs; f++) { if (fn[f] == AGG_COUNT) ob_push(&obs[f], 0, 1); else ob_push(&obs[f], 0, 0); }
+      if (!all_first) for (int f = 0; f < n_funcs; f++) { if (fn[f] == AGG_COUNT) ob_push(&obs[f], 0, 1); else if (obs[f].elem == 0) ob_push_str(&obs[f], -1); else ob_push(&obs[f], 0, 0); }
     } else {
       for (int64_t g = 0; g < fin.n; g++)              /* getFinalResult aggregate.go:429-457 */
         for (int f = 0; f < n_funcs; f++) state_final(fn[f], ft[f], &fin.states[g * n_funcs + f], &obs[f]);
@@ -534,6 +628,7 @@ int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int
   free(obs);
   for (int w = 0; w < n_partial_workers; w++) amap_free(&partial[w]);
   amap_free(&fin); free(partial); free(fn); free(ft);
+  pool_reset();
   return rc;
 }
 

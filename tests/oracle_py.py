@@ -96,6 +96,8 @@ def agg_out_type(func, arg_tp):
         return 1
     if func in (1, 2) and arg_tp == 2:
         return 1
+    if func in (1, 2) and arg_tp == 4:  # SUM / AVG of a FLOAT column: EvalReal -> DOUBLE
+        return 3
     return arg_tp
 
 

@@ -218,11 +218,10 @@ def test_group_by_two_columns_partial_then_final(lib):
     assert_same_multiset(got, want)
 
 
-# ------------------------------------------------------------------ OtherConditions on the device (experimental)
-@pytest.mark.skipif(os.environ.get("TQ_RUN_EXPERIMENTS") != "1", reason="OtherConditions device path was written after the round-1 GPU budget was spent; TQ_RUN_EXPERIMENTS=1 runs it")
+# ------------------------------------------------------------------ OtherConditions on the device
 @pytest.mark.parametrize("jt,oir", [(INNER_JOIN, False), (INNER_JOIN, True), (LEFT_OUTER_JOIN, False), (RIGHT_OUTER_JOIN, True)])
 @pytest.mark.parametrize("nb,npr", [(0, 50), (300, 2000), (5000, 100000), (300000, 900000)])
-def test_join_other_conditions_experiment(lib, nb, npr, jt, oir):
+def test_join_other_conditions(lib, nb, npr, jt, oir):
     rng = np.random.default_rng(nb + npr + jt)
     ndv = max(nb // 3, 2)
     bcols = [gen_col(rng, INT64, nb, 0.05, 0, ndv), gen_col(rng, INT64, nb, 0.1, -50, 50), gen_col(rng, FLOAT64, nb, 0.1)]

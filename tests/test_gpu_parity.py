@@ -270,19 +270,6 @@ def test_join_partitioned_unique_pk_fk(lib, monkeypatch, no_fast):
     assert np.array_equal(got.cols[2].values, pk[got.cols[3].values])
 
 
-@pytest.mark.skipif(os.environ.get("TQ_RUN_EXPERIMENTS") != "1", reason="round-2 experiments (probe kernel variants), not yet measured: TQ_RUN_EXPERIMENTS=1 runs them")
-@pytest.mark.parametrize("variant", ["1", "2"])
-def test_join_fast_kernel_variant_experiments(lib, monkeypatch, variant):
-    monkeypatch.setenv("TQ_JOIN_PROBE_VARIANT", variant)
-    rng = np.random.default_rng(31)
-    nb, npr = 400000, 3000000
-    bk = rng.permutation(nb * 2)[:nb].astype(np.int64)
-    pk = rng.integers(0, nb * 2, npr).astype(np.int64)
-    got, want = _run_join([INT64, INT64], [Column(INT64, bk), Column(INT64, bk * 3 + 1)], [INT64, INT64], [Column(INT64, pk), Column(INT64, np.arange(npr))],
-                          INNER_JOIN, True, chunk=1 << 20)
-    assert_same_multiset(got, want)
-
-
 @pytest.mark.parametrize("nbc,npc", [(1, 1), (3, 2), (4, 4), (2, 3)])
 def test_join_fast_kernel_shapes(lib, nbc, npc):
     """row-table fast path across column counts (16- and 32-byte entries), incl. misses and the empty-marker key"""
@@ -553,7 +540,6 @@ def test_agg_table_growth(lib):
 
 
 # ------------------------------------------------------------------ multi-GPU shard boundary, exercised on ONE GPU
-@pytest.mark.skipif(os.environ.get("TQ_RUN_EXPERIMENTS") != "1", reason="round-2 experiment (TMA bulk-store push kernel), not yet run on a GPU")
 def test_partition_push_bulk_store_experiment(lib, monkeypatch):
     monkeypatch.setenv("TQ_PUSH_BULK", "1")
     test_partition_count_and_push_local(lib)

@@ -106,11 +106,3 @@ def test_varlen_partitioned_build(lib):
         assert strs[i] == want
     lens = np.diff(got.cols[3].offsets)
     assert np.array_equal(lens, np.where(hit, 8 + keys % 5, 0))
-
-
-def test_varlen_key_columns_are_rejected(lib):
-    src = MockDataSource([BYTES], [Column(BYTES, [b"a"])])
-    e = HashJoinExec(src, src, [0], [0])
-    with pytest.raises(L.TQError) as ei:
-        e.Open()
-    assert ei.value.status == L.TQ_ERR_UNSUPPORTED_TYPE

@@ -79,6 +79,7 @@ SYMBOLS = {
     "tq_agg_put": (_I32, [_P, _COL, _I32]), "tq_agg_eof": (_I32, [_P]),
     "tq_agg_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
     "tq_agg_next_device": (_I32, [_P, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
+    "tq_agg_next_bytes": (_I32, [_P, _I64, C.POINTER(_I64)]),
     "tq_agg_destroy": (_I32, [_P]), "tq_agg_stats": (_I32, [_P, C.POINTER(_I64)]),
     "tq_agg_partial_width": (_I32, [_P, C.POINTER(_I32)]),
     "tq_agg_export_partial": (_I32, [_P, _COL, C.POINTER(_I64)]),

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "dict.cuh"
 #include "scatter.cuh"
+#include "strdict.cuh"
+#include "varlen.cuh"
 
 namespace tq {
 
@@ -41,6 +43,9 @@ struct AggFuncDev {
   int w0, w1, w2;       // word offsets of the state inside the slot
   int use_flag;         // SUM/MAX/MIN: maintain the "seen a non-NULL input" flag in w1
   int arg_not_null;     // the argument column is declared NOT NULL (mysql.NotNullFlag): no flag word, bitmaps ignored
+  // string arguments (arg_type == TQ_TYPE_BYTES): the column holds dictionary ids; MAX / MIN compare the arena strings
+  const int64_t *str_off;
+  const uint8_t *str_bytes;
 };
 
 struct AggParams {
@@ -163,6 +168,25 @@ __device__ __forceinline__ void agg_apply(const AggParams &p, uint32_t slot, int
       }
       case TQ_AGG_MAX:
       case TQ_AGG_MIN: {  // func_max_min.go:83-118 (+ Uint / Float64 twins); merge is the same comparison
+        if (f.arg_type == TQ_TYPE_BYTES) {
+          // maxMin4String (func_max_min.go:337-361): the state word holds id + 1 of the best string so far (0 = none);
+          // a candidate replaces it when types.CompareString says so — CAS loop, the compare reads the dictionary arena
+          if (live && nn) {
+            unsigned long long *w = reinterpret_cast<unsigned long long *>(sl + f.w0);
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(w);
+            for (;;) {
+              if (cur != 0ull) {
+                if (cur == v + 1) break;
+                const int c = sd_compare_ids(f.str_off, f.str_bytes, (uint32_t)v, (uint32_t)(cur - 1));
+                if (!((f.func == TQ_AGG_MAX && c > 0) || (f.func == TQ_AGG_MIN && c < 0))) break;
+              }
+              const unsigned long long prev = atomicCAS(w, cur, (unsigned long long)v + 1);
+              if (prev == cur) break;
+              cur = prev;
+            }
+          }
+          break;
+        }
         if (live && nn) {
           uint64_t m = order_map(v, f.arg_type);
           if (f.func == TQ_AGG_MIN) m = ~m;
@@ -312,6 +336,7 @@ __global__ void __launch_bounds__(256) k_agg_collect(const CollectParams p) {
           }
           case TQ_AGG_MAX:
           case TQ_AGG_MIN: {
+            if (f.arg_type == TQ_TYPE_BYTES) { put_out(p.out_state[w++], pos, sl[f.w0] ? sl[f.w0] - 1 : 0, sl[f.w0] != 0); break; }
             const uint64_t cnt = seen_of(f, sl);
             uint64_t m = sl[f.w0];
             if (f.func == TQ_AGG_MIN) m = ~m;
@@ -358,6 +383,7 @@ __global__ void __launch_bounds__(256) k_agg_collect(const CollectParams p) {
         }
         case TQ_AGG_MAX:
         case TQ_AGG_MIN: {                                                          // func_max_min.go:73-81
+          if (f.arg_type == TQ_TYPE_BYTES) { put_out(p.out[fi], pos, sl[f.w0] ? sl[f.w0] - 1 : 0, sl[f.w0] != 0); break; }   // :327-335
           const uint64_t cnt = seen_of(f, sl);
           uint64_t m = sl[f.w0];
           if (f.func == TQ_AGG_MIN) m = ~m;
@@ -504,6 +530,7 @@ using namespace tq;
 struct AggResult {
   std::vector<DevBuf> data, bm;
   std::vector<PinBuf> h_data, h_bm;
+  std::vector<VarOut> var;   // FLOAT (4-byte slots) and var-len result columns, converted / gathered from `data` (indexed like data)
   int64_t n = 0;
   bool on_host = false;
 };
@@ -511,7 +538,13 @@ struct AggResult {
 struct tq_agg {
   int n_cols = 0, n_group_by = 0, n_funcs = 0;
   int n_funcs_all = 0;      // n_funcs + one hidden FIRSTROW per GROUP BY column when there are several (their values leave with export_partial)
-  int types[AGG_MAXC];
+  int types[AGG_MAXC];      // the 8-byte type the kernels see: FLOAT columns are widened to FLOAT64, var-len columns become dictionary ids (TQ_TYPE_BYTES)
+  int in_kind[AGG_MAXC] = {};  // 0 = 8-byte slots as declared, 1 = FLOAT (4-byte slots, widened on the device), 2 = var-len (dictionary-encoded on the device)
+  bool any_kind = false;
+  StringDict sd[AGG_MAXC];  // one dictionary per var-len input column: GROUP BY items and string arguments work on ids (strdict.cuh)
+  int out_kind[AGG_MAXF] = {};  // result column i: 0 = 8-byte, 1 = FLOAT (narrowed back), 2 = var-len (gathered from sd[out_src[i]])
+  int out_src[AGG_MAXF] = {};
+  DevBuf lens_scratch, scan_scratch;
   int key_col = -1;         // the key column of the update kernel: the GROUP BY column, or the hidden encoded column (index n_cols)
   int gb_cols[MK_MAX_KEYS];
   MultiKeyEncoder mk;       // several GROUP BY columns: exact fold of the key tuple into one 64-bit word (dict.cuh)
@@ -540,7 +573,12 @@ struct tq_agg {
   DevBuf deferred;
   PinBuf meta_host;
   // host staging (double-buffered)
-  struct Stage { std::vector<PinBuf> data, bm; std::vector<bool> has_bm; int64_t n = 0; std::vector<DevBuf> d_data, d_bm; cudaEvent_t ev_done = nullptr; bool in_flight = false; } stage[2];
+  struct Stage {
+    std::vector<PinBuf> data, bm; std::vector<bool> has_bm; int64_t n = 0; std::vector<DevBuf> d_data, d_bm; cudaEvent_t ev_done = nullptr; bool in_flight = false;
+    std::vector<HostVarAccum> var;     // cells of the var-len columns of this stage
+    std::vector<SideStore> store;      // ... and their device copy
+    std::vector<DevBuf> d_raw;         // FLOAT columns: the 4-byte slots before widening
+  } stage[2];
   int cur_stage = 0;
   int64_t rows_total = 0, launches = 0, last_update_ns = 0;
   bool eof = false, finalized = false, closed = false;
@@ -595,6 +633,13 @@ static void fill_funcs(tq_agg *a, AggFuncDev *f, bool merge) {
     d.w1 = a->w1[i];
     d.w2 = a->w2[i];
     d.use_flag = (a->flag_on[i] && a->w1[i] >= 0) ? 1 : 0;
+    d.str_off = nullptr;
+    d.str_bytes = nullptr;
+    if (a->arg_type[i] == TQ_TYPE_BYTES && a->funcs[i].arg_col >= 0) {
+      const StringDict &sd = a->sd[a->funcs[i].arg_col];
+      d.str_off = sd.arena.offsets.as<int64_t>();
+      d.str_bytes = sd.arena.bytes.as<uint8_t>();
+    }
     d.arg_not_null = (!merge && a->funcs[i].arg_col >= 0 && a->not_null[a->funcs[i].arg_col]) ? 1 : 0;
   }
 }
@@ -618,7 +663,7 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
 static int32_t agg_try_preagg(tq_agg *a, const DCol *cols, int64_t n, bool *done) {
   *done = false;
   static const bool disabled_by_env = [] { const char *e = getenv("TQ_AGG_NO_PREAGG"); return e && e[0] == '1'; }();
-  if (disabled_by_env || a->pre_disabled || a->n_group_by != 1 || n < (1 << 20) || n > 0xFFFFFFF0ll) return TQ_OK;
+  if (disabled_by_env || a->pre_disabled || a->any_kind || a->n_group_by != 1 || n < (1 << 20) || n > 0xFFFFFFF0ll) return TQ_OK;
   const int kc = a->key_col;
   if (a->types[kc] == TQ_TYPE_FLOAT64 || cols[kc].bm != nullptr) return TQ_OK;  // integer key without NULLs
   const int64_t g_est = a->known_groups > a->est_groups ? a->known_groups : a->est_groups;
@@ -833,15 +878,30 @@ static int32_t agg_flush_stage(tq_agg *a, bool merge, int n_in_cols) {
   st.d_data.resize(n_in_cols);
   st.d_bm.resize(n_in_cols);
   std::vector<DCol> view(n_in_cols);
+  if (a->any_kind && !merge) { st.store.resize(n_in_cols); st.d_raw.resize(n_in_cols); }
   for (int c = 0; c < n_in_cols; c++) {
+    const int kind = merge ? 0 : a->in_kind[c];
     TQ_TRY(st.d_data[c].reserve((size_t)st.n * 8));
-    TQ_CUDA(cudaMemcpyAsync(st.d_data[c].p, st.data[c].p, (size_t)st.n * 8, cudaMemcpyHostToDevice, r.compute));
     view[c].data = st.d_data[c].as<uint64_t>();
     view[c].bm = nullptr;
     if (st.has_bm[c]) {
       TQ_TRY(st.d_bm[c].reserve(bitmap_alloc_bytes(st.n)));
       TQ_CUDA(cudaMemcpyAsync(st.d_bm[c].p, st.bm[c].p, bitmap_bytes(st.n), cudaMemcpyHostToDevice, r.compute));
       view[c].bm = st.d_bm[c].as<uint32_t>();
+    }
+    if (kind == 0) {
+      TQ_CUDA(cudaMemcpyAsync(st.d_data[c].p, st.data[c].p, (size_t)st.n * 8, cudaMemcpyHostToDevice, r.compute));
+    } else if (kind == 1) {
+      // FLOAT: the 4-byte slots were staged packed; EvalReal / getGroupKey see float64(f) (expression/column.go:95-110)
+      TQ_TRY(st.d_raw[c].reserve((size_t)st.n * 4));
+      TQ_CUDA(cudaMemcpyAsync(st.d_raw[c].p, st.data[c].p, (size_t)st.n * 4, cudaMemcpyHostToDevice, r.compute));
+      TQ_TRY(widen_f32(st.d_raw[c].as<uint32_t>(), st.n, st.d_data[c].as<uint64_t>(), r.compute));
+    } else {
+      // var-len: cells -> device store -> dictionary ids (the string itself lives once in the dictionary's arena)
+      // (insert mode: an id is valid iff the cell is NOT NULL, so the column's own bitmap stays the ids' bitmap)
+      TQ_TRY(upload_store(st.var[c], st.store[c], r.compute));
+      TQ_TRY(a->sd[c].encode(view_of(st.store[c]), view[c].bm, st.n, st.store[c].nbytes, /*insert=*/true, st.d_data[c].as<uint64_t>(), nullptr, r.compute));
+      st.var[c].reset();
     }
   }
   const int64_t n = st.n;
@@ -861,8 +921,11 @@ static int32_t agg_put_common(tq_agg *a, const tq_column *cols, int32_t mem, boo
   if (rows < 0) return TQ_ERR_INVALID_ARG;
   for (int c = 0; c < n_in_cols; c++) {
     if (cols[c].length != rows) { set_error("ragged aggregate input chunk"); return TQ_ERR_INVALID_ARG; }
-    if (cols[c].offsets) { set_error("unsupport column type for encode (var-len column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
-    if (rows && !cols[c].data) return TQ_ERR_INVALID_ARG;
+    const int kind = merge ? 0 : a->in_kind[c];
+    if (kind != 2 && cols[c].offsets) { set_error("unsupport column type for encode (var-len data in fixed-width column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
+    if (kind == 2 && !cols[c].offsets) { set_error("var-len column %d needs offsets", c); return TQ_ERR_INVALID_ARG; }
+    if (rows && !cols[c].data && !(kind == 2 && cols[c].offsets[rows] == cols[c].offsets[0])) return TQ_ERR_INVALID_ARG;
+    if (kind != 0 && mem != TQ_MEM_HOST) { set_error("FLOAT / var-len columns are accepted from host memory only"); return TQ_ERR_UNSUPPORTED_TYPE; }
   }
   if (rows == 0) return TQ_OK;
   Runtime &r = rt();
@@ -878,7 +941,7 @@ static int32_t agg_put_common(tq_agg *a, const tq_column *cols, int32_t mem, boo
   int64_t done = 0;
   while (done < rows) {
     tq_agg::Stage &st = a->stage[a->cur_stage];
-    if ((int)st.data.size() != n_in_cols) { st.data.resize(n_in_cols); st.bm.resize(n_in_cols); st.has_bm.assign(n_in_cols, false); }
+    if ((int)st.data.size() != n_in_cols) { st.data.resize(n_in_cols); st.bm.resize(n_in_cols); st.has_bm.assign(n_in_cols, false); st.var.resize(n_in_cols); }
     int64_t room = a->batch_rows - st.n;
     if (room <= 0) { TQ_TRY(agg_flush_stage(a, merge, n_in_cols)); continue; }
     int64_t take = rows - done < room ? rows - done : room;
@@ -887,7 +950,14 @@ static int32_t agg_put_common(tq_agg *a, const tq_column *cols, int32_t mem, boo
     for (int c = 0; c < n_in_cols; c++) {
       if (st.data[c].cap < (size_t)a->batch_rows * 8) TQ_TRY(st.data[c].reserve((size_t)a->batch_rows * 8));
       if (st.bm[c].cap < bitmap_alloc_bytes(a->batch_rows)) { TQ_TRY(st.bm[c].reserve(bitmap_alloc_bytes(a->batch_rows))); }
-      memcpy(st.data[c].as<uint8_t>() + st.n * 8, cols[c].data + done * 8, (size_t)take * 8);
+      const int kind = merge ? 0 : a->in_kind[c];
+      if (kind == 0) memcpy(st.data[c].as<uint8_t>() + st.n * 8, cols[c].data + done * 8, (size_t)take * 8);
+      else if (kind == 1) memcpy(st.data[c].as<uint8_t>() + st.n * 4, cols[c].data + done * 4, (size_t)take * 4);  // packed 4-byte slots
+      else {
+        tq_column piece = cols[c];
+        piece.offsets = cols[c].offsets + done;   // HostVarAccum rebases on offsets[0]
+        st.var[c].append(piece, take);
+      }
       if (cols[c].null_bitmap && !st.has_bm[c]) { host_bitmap_append(st.bm[c].as<uint8_t>(), 0, nullptr, st.n); st.has_bm[c] = true; }
       if (st.has_bm[c]) {
         if (cols[c].null_bitmap) {
@@ -984,7 +1054,15 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
   }
   for (int c = 0; c < d->n_input_cols; c++) {
     const int t = d->input_types[c] & 0xFF;
-    if (t != TQ_TYPE_INT64 && t != TQ_TYPE_UINT64 && t != TQ_TYPE_FLOAT64) { set_error("unsupport column type for encode %d", t); return TQ_ERR_UNSUPPORTED_TYPE; }
+    if (t < TQ_TYPE_INT64 || t > TQ_TYPE_BYTES) { set_error("unsupport column type for encode %d", t); return TQ_ERR_UNSUPPORTED_TYPE; }
+  }
+  for (int i = 0; i < d->n_funcs; i++) {
+    const int fn = d->funcs[i].func, ac = d->funcs[i].arg_col;
+    if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && ac >= 0 && ac < d->n_input_cols && (d->input_types[ac] & 0xFF) == TQ_TYPE_BYTES) {
+      // the planner wraps a string argument of SUM / AVG in a cast to DOUBLE; HashAgg never sees the raw string
+      set_error("SUM / AVG over a var-len column: project cast(col as double) first");
+      return TQ_ERR_UNSUPPORTED_TYPE;
+    }
   }
   tq_agg *a = new (std::nothrow) tq_agg();
   if (!a) return TQ_ERR_OOM;
@@ -993,7 +1071,13 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
   a->n_funcs = d->n_funcs;
   a->est_groups = d->est_groups;
   { const char *e = getenv("TQ_AGG_PREAGG_PART"); a->pre_partitioned = e && e[0] == '1'; }
-  for (int c = 0; c < a->n_cols; c++) { a->types[c] = d->input_types[c] & 0xFF; a->not_null[c] = (d->input_types[c] & TQ_TYPE_NOT_NULL) != 0; }
+  for (int c = 0; c < a->n_cols; c++) {
+    const int t = d->input_types[c] & 0xFF;
+    a->in_kind[c] = t == TQ_TYPE_FLOAT32 ? 1 : (t == TQ_TYPE_BYTES ? 2 : 0);
+    a->any_kind |= a->in_kind[c] != 0;
+    a->types[c] = t == TQ_TYPE_FLOAT32 ? TQ_TYPE_FLOAT64 : t;   // FLOAT is evaluated as float64(f): EvalReal / VecEvalReal (expression/column.go:95-110)
+    a->not_null[c] = (d->input_types[c] & TQ_TYPE_NOT_NULL) != 0;
+  }
   for (int g = 0; g < a->n_group_by; g++) {
     a->gb_cols[g] = d->group_by_cols[g];
     if (a->gb_cols[g] < 0 || a->gb_cols[g] >= a->n_cols) { delete a; return TQ_ERR_INVALID_ARG; }
@@ -1015,6 +1099,11 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
     if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->arg_type[i] == TQ_TYPE_UINT64) a->arg_type[i] = TQ_TYPE_INT64;  // sum4Int64 reads EvalInt (func_sum.go:118)
     a->out_type[i] = fn == TQ_AGG_COUNT ? TQ_TYPE_INT64 : (ac >= 0 ? a->types[ac] : TQ_TYPE_INT64);
     if ((fn == TQ_AGG_SUM || fn == TQ_AGG_AVG) && a->out_type[i] == TQ_TYPE_UINT64) a->out_type[i] = TQ_TYPE_INT64;
+    // MAX / MIN / FIRSTROW keep the argument's own column type: maxMin4Float32 / firstRow4Float32 append a FLOAT,
+    // maxMin4String / firstRow4String a string (aggfuncs/builder.go:119-172)
+    const bool sel = fn == TQ_AGG_MAX || fn == TQ_AGG_MIN || fn == TQ_AGG_FIRSTROW;
+    if (sel && ac >= 0 && a->in_kind[ac] == 1) { a->out_type[i] = TQ_TYPE_FLOAT32; a->out_kind[i] = 1; }
+    if (sel && ac >= 0 && a->in_kind[ac] == 2) { a->out_kind[i] = 2; a->out_src[i] = ac; }
     a->key_passthrough[i] = (fn == TQ_AGG_FIRSTROW && a->n_group_by == 1 && ac == a->key_col) ? 1 : 0;
     a->w0[i] = a->w1[i] = a->w2[i] = 0;
     if (!a->key_passthrough[i]) {
@@ -1023,7 +1112,8 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
       const bool flag_only = (fn == TQ_AGG_SUM || fn == TQ_AGG_MAX || fn == TQ_AGG_MIN);
       a->w0[i] = words++;
       a->w1[i] = -1;
-      if (fn != TQ_AGG_COUNT && !(flag_only && arg_nn)) a->w1[i] = words++;
+      const bool str_maxmin = (fn == TQ_AGG_MAX || fn == TQ_AGG_MIN) && a->arg_type[i] == TQ_TYPE_BYTES;  // state = id + 1, 0 = no value yet
+      if (fn != TQ_AGG_COUNT && !(flag_only && arg_nn) && !str_maxmin) a->w1[i] = words++;
       if (int_sum) a->w2[i] = words++;
     }
   }
@@ -1050,8 +1140,15 @@ int32_t tq_agg_put(tq_agg *a, const tq_column *cols, int32_t mem) {
   return agg_put_common(a, cols, mem, false, a->n_cols);
 }
 
+static bool agg_has_varlen(const tq_agg *a) {
+  for (int c = 0; c < a->n_cols; c++) if (a->in_kind[c] == 2) return true;
+  return false;
+}
+
 int32_t tq_agg_merge_partial(tq_agg *a, const tq_column *cols, int32_t mem) {
   if (!a) return TQ_ERR_INVALID_ARG;
+  // partial rows of a var-len column would carry ids of the exporting handle's dictionary
+  if (agg_has_varlen(a)) { set_error("partial export / merge with var-len columns is not supported"); return TQ_ERR_UNSUPPORTED_TYPE; }
   return agg_put_common(a, cols, mem, true, partial_width(a));
 }
 
@@ -1077,8 +1174,87 @@ static int32_t agg_ensure_final(tq_agg *a) {
   if (a->finalized) return TQ_OK;
   if (!a->eof) { set_error("next before eof: HashAgg is a pipeline breaker"); return TQ_ERR_STATE; }
   TQ_TRY(agg_finalize(a, false, a->result, a->n_funcs));
+  AggResult &res = a->result;
+  res.var.clear();
+  if (a->any_kind && res.n > 0) {
+    // FLOAT results are narrowed back to 4-byte slots (AppendFloat32), string results gathered from the dictionary arena
+    // into offsets + bytes (AppendString): chunk.Column layout of the result type (util/chunk/column.go:28-34)
+    cudaStream_t s = rt().compute;
+    res.var.resize(a->n_funcs);
+    for (int i = 0; i < a->n_funcs; i++) {
+      VarOut &v = res.var[i];
+      if (a->out_kind[i] == 2) {
+        TQ_TRY(gather_cells(a->sd[a->out_src[i]].arena, res.data[i].as<uint64_t>(), res.bm[i].as<uint32_t>(), res.n, v, a->lens_scratch, a->scan_scratch, s));
+      } else if (a->out_kind[i] == 1) {
+        TQ_TRY(v.bytes.reserve((size_t)res.n * 4));
+        TQ_TRY(narrow_f64(res.data[i].as<uint64_t>(), res.n, v.bytes.as<uint32_t>(), s));
+        v.elem = 4;
+        v.total = res.n * 4;
+        v.used = true;
+        v.on_host = false;
+      }
+    }
+    TQ_CUDA(cudaStreamSynchronize(s));
+  }
   a->finalized = true;
   a->result_pos = 0;
+  return TQ_OK;
+}
+
+static bool agg_out_indirect(const tq_agg *a, int i) { return a->out_kind[i] != 0 && i < (int)a->result.var.size() && a->result.var[i].used; }
+
+// copy the whole result to pinned host memory once (data, bitmaps, FLOAT / var-len forms)
+static int32_t agg_result_to_host(tq_agg *a) {
+  AggResult &res = a->result;
+  if (res.on_host) return TQ_OK;
+  Runtime &r = rt();
+  res.h_data.resize(a->n_funcs);
+  res.h_bm.resize(a->n_funcs);
+  for (int c = 0; c < a->n_funcs; c++) {
+    TQ_TRY(res.h_bm[c].reserve(bitmap_alloc_bytes(res.n)));
+    TQ_CUDA(cudaMemcpyAsync(res.h_bm[c].p, res.bm[c].p, bitmap_bytes(res.n), cudaMemcpyDeviceToHost, r.compute));
+    if (agg_out_indirect(a, c)) {
+      VarOut &v = res.var[c];
+      TQ_TRY(v.h_bytes.reserve((size_t)v.total + 16));
+      if (v.total) TQ_CUDA(cudaMemcpyAsync(v.h_bytes.p, v.bytes.p, (size_t)v.total, cudaMemcpyDeviceToHost, r.compute));
+      if (v.elem == 0) {
+        TQ_TRY(v.h_off.reserve((size_t)(res.n + 1) * 8));
+        TQ_CUDA(cudaMemcpyAsync(v.h_off.p, v.off.p, (size_t)(res.n + 1) * 8, cudaMemcpyDeviceToHost, r.compute));
+      }
+      v.on_host = true;
+    } else {
+      TQ_TRY(res.h_data[c].reserve((size_t)res.n * 8));
+      TQ_CUDA(cudaMemcpyAsync(res.h_data[c].p, res.data[c].p, (size_t)res.n * 8, cudaMemcpyDeviceToHost, r.compute));
+    }
+  }
+  TQ_CUDA(cudaStreamSynchronize(r.compute));
+  res.on_host = true;
+  return TQ_OK;
+}
+
+int32_t tq_agg_next_bytes(tq_agg *a, int64_t max_rows, int64_t *bytes_per_col) {
+  if (!a || !bytes_per_col || max_rows <= 0) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(ensure_init());
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  TQ_TRY(agg_ensure_final(a));
+  AggResult &res = a->result;
+  for (int c = 0; c < a->n_funcs; c++) bytes_per_col[c] = 0;
+  if (a->rows_total == 0 && a->n_group_by == 0 && a->result_pos == 0) {   // the default row: 8-byte / 4-byte slot, empty string
+    for (int c = 0; c < a->n_funcs; c++) bytes_per_col[c] = a->out_kind[c] == 2 ? 0 : (a->out_kind[c] == 1 ? 4 : 8);
+    return TQ_OK;
+  }
+  if (a->rows_total == 0 || a->result_pos >= res.n) return TQ_OK;
+  TQ_TRY(agg_result_to_host(a));
+  const int64_t take = res.n - a->result_pos < max_rows ? res.n - a->result_pos : max_rows;
+  for (int c = 0; c < a->n_funcs; c++) {
+    if (!agg_out_indirect(a, c)) bytes_per_col[c] = take * 8;
+    else if (res.var[c].elem == 4) bytes_per_col[c] = take * 4;
+    else {
+      const int64_t *off = res.var[c].h_off.as<int64_t>() + a->result_pos;
+      bytes_per_col[c] = off[take] - off[0];
+    }
+  }
   return TQ_OK;
 }
 
@@ -1099,8 +1275,9 @@ int32_t tq_agg_next(tq_agg *a, int64_t max_rows, tq_column *out_cols, int64_t *n
     a->result_pos = 1;
     if (!all_first && a->n_funcs) {
       for (int i = 0; i < a->n_funcs; i++) {
-        if (!out_cols[i].data || !out_cols[i].null_bitmap) return TQ_ERR_INVALID_ARG;
-        memset(out_cols[i].data, 0, 8);
+        if (!out_cols[i].null_bitmap || (a->out_kind[i] != 2 && !out_cols[i].data) || (a->out_kind[i] == 2 && !out_cols[i].offsets)) return TQ_ERR_INVALID_ARG;
+        if (a->out_kind[i] == 2) { out_cols[i].offsets[0] = 0; out_cols[i].offsets[1] = 0; }
+        else memset(out_cols[i].data, 0, a->out_kind[i] == 1 ? 4 : 8);
         out_cols[i].null_bitmap[0] = (a->funcs[i].func == TQ_AGG_COUNT) ? 1 : 0;
         out_cols[i].length = 1;
       }
@@ -1109,22 +1286,24 @@ int32_t tq_agg_next(tq_agg *a, int64_t max_rows, tq_column *out_cols, int64_t *n
     }
   }
   if (a->rows_total == 0 || a->result_pos >= res.n) { *eof = 1; for (int i = 0; i < a->n_funcs; i++) out_cols[i].length = 0; return TQ_OK; }
-  if (!res.on_host) {
-    res.h_data.resize(a->n_funcs);
-    res.h_bm.resize(a->n_funcs);
-    for (int c = 0; c < a->n_funcs; c++) {
-      TQ_TRY(res.h_data[c].reserve((size_t)res.n * 8));
-      TQ_TRY(res.h_bm[c].reserve(bitmap_alloc_bytes(res.n)));
-      TQ_CUDA(cudaMemcpyAsync(res.h_data[c].p, res.data[c].p, (size_t)res.n * 8, cudaMemcpyDeviceToHost, r.compute));
-      TQ_CUDA(cudaMemcpyAsync(res.h_bm[c].p, res.bm[c].p, bitmap_bytes(res.n), cudaMemcpyDeviceToHost, r.compute));
-    }
-    TQ_CUDA(cudaStreamSynchronize(r.compute));
-    res.on_host = true;
-  }
+  TQ_TRY(agg_result_to_host(a));
   const int64_t take = res.n - a->result_pos < max_rows ? res.n - a->result_pos : max_rows;
   for (int c = 0; c < a->n_funcs; c++) {
-    if (!out_cols[c].data || !out_cols[c].null_bitmap) { set_error("output column %d needs data and null_bitmap buffers", c); return TQ_ERR_INVALID_ARG; }
-    memcpy(out_cols[c].data, res.h_data[c].as<uint8_t>() + a->result_pos * 8, (size_t)take * 8);
+    const bool ind = agg_out_indirect(a, c), var = ind && res.var[c].elem == 0;
+    if (!out_cols[c].null_bitmap || (!out_cols[c].data && !var) || (var && !out_cols[c].offsets)) {
+      set_error("output column %d needs data and null_bitmap buffers (and offsets for a var-len column)", c);
+      return TQ_ERR_INVALID_ARG;
+    }
+    if (var) {   // offsets rebased to 0 + the cells' bytes (chunk.Column layout)
+      const int64_t *off = res.var[c].h_off.as<int64_t>() + a->result_pos;
+      const int64_t b0 = off[0];
+      for (int64_t i = 0; i <= take; i++) out_cols[c].offsets[i] = off[i] - b0;
+      if (off[take] > b0) {
+        if (!out_cols[c].data) { set_error("output column %d needs a data buffer (tq_agg_next_bytes tells its size)", c); return TQ_ERR_INVALID_ARG; }
+        memcpy(out_cols[c].data, res.var[c].h_bytes.as<uint8_t>() + b0, (size_t)(off[take] - b0));
+      }
+    } else if (ind) memcpy(out_cols[c].data, res.var[c].h_bytes.as<uint8_t>() + a->result_pos * 4, (size_t)take * 4);
+    else memcpy(out_cols[c].data, res.h_data[c].as<uint8_t>() + a->result_pos * 8, (size_t)take * 8);
     host_bitmap_extract(out_cols[c].null_bitmap, res.h_bm[c].as<uint8_t>(), a->result_pos, take);
     out_cols[c].length = take;
   }
@@ -1147,6 +1326,10 @@ int32_t tq_agg_next_device(tq_agg *a, tq_column *out_cols, int64_t *n_rows, int3
     out_cols[c].data = a->result.data[c].as<uint8_t>();
     out_cols[c].null_bitmap = a->result.bm[c].as<uint8_t>();
     out_cols[c].offsets = nullptr;
+    if (agg_out_indirect(a, c)) {   // FLOAT slots / gathered strings, device resident
+      out_cols[c].data = a->result.var[c].bytes.as<uint8_t>();
+      if (a->result.var[c].elem == 0) out_cols[c].offsets = a->result.var[c].off.as<int64_t>();
+    }
   }
   *n_rows = a->result.n;
   a->result_pos = a->result.n;
@@ -1158,6 +1341,7 @@ int32_t tq_agg_export_partial(tq_agg *a, tq_column *out_cols, int64_t *n_rows) {
   TQ_TRY(ensure_init());
   Runtime &r = rt();
   std::lock_guard<std::recursive_mutex> lk(r.mu);
+  if (agg_has_varlen(a)) { set_error("partial export / merge with var-len columns is not supported"); return TQ_ERR_UNSUPPORTED_TYPE; }
   if (!a->eof) TQ_TRY(tq_agg_eof(a));
   const int w = partial_width(a);
   TQ_TRY(agg_finalize(a, true, a->result, w));

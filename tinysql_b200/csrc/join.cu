@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "dict.cuh"
 #include "varlen.cuh"
+#include "strdict.cuh"
 #include "scatter.cuh"
 #include "othercond.cuh"
 
@@ -39,7 +40,6 @@ static int64_t g_max_load_pct = 50;                      // TQ_JOIN_MAX_LOAD_PCT
 static bool g_exact_scatter = false;                     // TQ_JOIN_EXACT_SCATTER=1: always run the probe-side histogram pass
 static bool g_no_fast_kernel = false;                    // TQ_JOIN_NO_FAST=1: use the generic kernels (tests)
 static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
-static int g_probe_variant = 0;                          // TQ_JOIN_PROBE_VARIANT=1|2: experiments in the PK-FK probe kernel (see k_probe_part_fast)
 
 // key_mode: how (flag, raw bytes) equality (util/codec/codec.go:212-240,363-382) maps onto raw 8-byte equality
 //   0: flags always agree (both signed, both unsigned, or both DOUBLE)  -> raw equality
@@ -1196,16 +1196,8 @@ __device__ __forceinline__ EntryPair ld_pair(const uint64_t *tbl, uint32_t loc_e
   return e;
 }
 
-// VAR selects an experiment (TQ_JOIN_PROBE_VARIANT=1|2), 0 = the measured default:
-//   1  WARP_CLAIM: every warp claims the output range of its 128 rows with its own global atomic instead of one claim
-//      per 1024-row tile behind two CTA barriers — 8x the atomics on the cursor, but no warp ever waits for another one;
-//   2  WARP_CLAIM + PREFETCH: the other probe columns are requested together with the table entries (not after the
-//      match is known), which takes one dependent DRAM round trip out of the tile's critical path at the price of
-//      registers (3 CTAs per SM instead of 4) and of wasted reads for rows that miss.
-// Not the default until measured.
-template <int NP, int NB, int VAR = 0>
-__global__ void __launch_bounds__(PROBE_THREADS, (VAR == 2 ? 3 : 4)) k_probe_part_fast(const ProbeParams p, const JoinTable t) {
-  constexpr bool WARP_CLAIM = VAR >= 1, PREFETCH = VAR == 2;
+template <int NP, int NB>
+__global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const ProbeParams p, const JoinTable t) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
   __shared__ __align__(8) uint64_t s_mbar;
   __shared__ unsigned s_total[2];
@@ -1254,17 +1246,6 @@ __global__ void __launch_bounds__(PROBE_THREADS, (VAR == 2 ? 3 : 4)) k_probe_par
     unsigned bal[R];
     unsigned wcnt = 0;
     uint64_t pay[NP][R];
-    if constexpr (PREFETCH) {
-#pragma unroll
-      for (int k = 0; k < R; k++) {
-        const bool in_range = (wbase + k * 32) < cx.p_hi;
-#pragma unroll
-        for (int c = 0; c < NP; c++) {
-          pay[c][k] = 0;
-          if (c != kc && in_range) pay[c][k] = tqd::ld_stream_u64(pin[c] + wbase + k * 32);
-        }
-      }
-    }
     if (shift == 1) {
       EntryPair pr[R];
 #pragma unroll
@@ -1331,38 +1312,29 @@ __global__ void __launch_bounds__(PROBE_THREADS, (VAR == 2 ? 3 : 4)) k_probe_par
       }
     }
     unsigned woff = 0;
-    unsigned long long wclaim = 0;
     if (lane == 0) {
       matched_acc += wcnt;
-      if constexpr (WARP_CLAIM) { if (wcnt) wclaim = atomicAdd(p.cursor, (unsigned long long)wcnt); }
-      else if (wcnt) woff = atomicAdd(&s_total[par], wcnt);
+      if (wcnt) woff = atomicAdd(&s_total[par], wcnt);
     }
     // the other probe columns of the matched rows are requested NOW: their latency hides behind the two barriers and
     // the global atomic below (only word 1 of the matched entry stays live: word 0 is the key itself)
-    if constexpr (!PREFETCH) {
 #pragma unroll
-      for (int k = 0; k < R; k++) {
-        const bool hit = (bal[k] >> lane) & 1u;
+    for (int k = 0; k < R; k++) {
+      const bool hit = (bal[k] >> lane) & 1u;
 #pragma unroll
-        for (int c = 0; c < NP; c++) {
-          pay[c][k] = 0;
-          if (c != kc && hit) pay[c][k] = tqd::ld_stream_u64(pin[c] + wbase + k * 32);
-        }
+      for (int c = 0; c < NP; c++) {
+        pay[c][k] = 0;
+        if (c != kc && hit) pay[c][k] = tqd::ld_stream_u64(pin[c] + wbase + k * 32);
       }
     }
-    unsigned long long q0;
-    if constexpr (WARP_CLAIM) {
-      q0 = __shfl_sync(0xffffffffu, wclaim, 0);
-    } else {
-      __syncthreads();
-      if (tid == 0) {
-        const unsigned tot = s_total[par];
-        s_base[par] = tot ? atomicAdd(p.cursor, (unsigned long long)tot) : 0ull;
-        s_total[par] = 0;
-      }
-      __syncthreads();
-      q0 = s_base[par] + __shfl_sync(0xffffffffu, woff, 0);
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned tot = s_total[par];
+      s_base[par] = tot ? atomicAdd(p.cursor, (unsigned long long)tot) : 0ull;
+      s_total[par] = 0;
     }
+    __syncthreads();
+    unsigned long long q0 = s_base[par] + __shfl_sync(0xffffffffu, woff, 0);
 #pragma unroll
     for (int k = 0; k < R; k++) {
       const unsigned long long q = q0 + __popc(bal[k] & lt_mask);
@@ -1385,28 +1357,24 @@ __global__ void __launch_bounds__(PROBE_THREADS, (VAR == 2 ? 3 : 4)) k_probe_par
 }
 
 typedef void (*ProbeKernel)(const ProbeParams, const JoinTable);
-template <int NP, int VAR>
+template <int NP>
 static ProbeKernel fast_kernel_nb(int nb) {
   switch (nb) {
-    case 1: return k_probe_part_fast<NP, 1, VAR>;
-    case 2: return k_probe_part_fast<NP, 2, VAR>;
-    case 3: return k_probe_part_fast<NP, 3, VAR>;
-    case 4: return k_probe_part_fast<NP, 4, VAR>;
+    case 1: return k_probe_part_fast<NP, 1>;
+    case 2: return k_probe_part_fast<NP, 2>;
+    case 3: return k_probe_part_fast<NP, 3>;
+    case 4: return k_probe_part_fast<NP, 4>;
   }
   return nullptr;
 }
-template <int VAR>
-static ProbeKernel fast_kernel_var(int np, int nb) {
+static ProbeKernel fast_kernel(int np, int nb) {
   switch (np) {
-    case 1: return fast_kernel_nb<1, VAR>(nb);
-    case 2: return fast_kernel_nb<2, VAR>(nb);
-    case 3: return fast_kernel_nb<3, VAR>(nb);
-    case 4: return fast_kernel_nb<4, VAR>(nb);
+    case 1: return fast_kernel_nb<1>(nb);
+    case 2: return fast_kernel_nb<2>(nb);
+    case 3: return fast_kernel_nb<3>(nb);
+    case 4: return fast_kernel_nb<4>(nb);
   }
   return nullptr;
-}
-static ProbeKernel fast_kernel(int np, int nb, int variant) {
-  return variant == 2 ? fast_kernel_var<2>(np, nb) : variant == 1 ? fast_kernel_var<1>(np, nb) : fast_kernel_var<0>(np, nb);
 }
 
 // ---- partitioned probe, general (duplicate build keys): block scan + output-centric expansion ------------
@@ -1516,24 +1484,6 @@ struct HostAccum {
   void reset() { n = 0; has_bm = false; }
 };
 
-// host staging of the cells of one FLOAT (elem 4) or var-len (elem 0) column
-struct HostVarAccum {
-  std::vector<int64_t> off{0};
-  std::vector<uint8_t> bytes;
-  int elem = 0;
-  int64_t n = 0;
-  void append(const tq_column &c, int64_t rows) {
-    if (elem == 4) bytes.insert(bytes.end(), c.data, c.data + rows * 4);
-    else {
-      const int64_t base = c.offsets[0];
-      for (int64_t i = 0; i < rows; i++) off.push_back(off.back() + (c.offsets[i + 1] - c.offsets[i]));
-      bytes.insert(bytes.end(), c.data + base, c.data + c.offsets[rows]);
-    }
-    n += rows;
-  }
-  void reset() { off.assign(1, 0); bytes.clear(); n = 0; }
-};
-
 struct DevColBuf {
   DevBuf data, bm;
 };
@@ -1590,6 +1540,13 @@ struct tq_join {
   bool mk_no_signbit[MK_MAX_KEYS] = {};
   MultiKeyEncoder mk;
   DevBuf mk_build_key, mk_build_bm, mk_probe_key[2], mk_probe_bm[2];
+  // FLOAT / var-len KEY columns (codec.go:226-233,276-333): a FLOAT key is compared as float64(f) — widened into an 8-byte
+  // column; a var-len key is compared byte for byte — replaced by its id in a string dictionary built from the build side
+  // (strdict.cuh).  Either makes the key "hidden" (an extra 8-byte column per side), like a multi-column key.
+  bool key_hidden = false;
+  int bkey_kind[MK_MAX_KEYS] = {}, pkey_kind[MK_MAX_KEYS] = {};   // 0 = 8-byte column as is, 1 = FLOAT widened, 2 = var-len via dictionary
+  StringDict sdict[MK_MAX_KEYS];
+  DevBuf kx_b_data[MK_MAX_KEYS], kx_b_bm[MK_MAX_KEYS], kx_p_data[2][MK_MAX_KEYS], kx_p_bm[2][MK_MAX_KEYS];
   std::vector<int> out_map;               // caller's output column -> column of the result batch
   // FLOAT / var-len payload columns travel through the kernels as row ids into a side store (varlen.cuh)
   bool b_ind[MAXC] = {}, p_ind[MAXC] = {}, any_ind = false;
@@ -1685,21 +1642,6 @@ static int stream_grid(int64_t n) {
 static bool type_ok(int t) { return t == TQ_TYPE_INT64 || t == TQ_TYPE_UINT64 || t == TQ_TYPE_FLOAT64; }
 static bool type_indirect(int t) { return t == TQ_TYPE_FLOAT32 || t == TQ_TYPE_BYTES; }
 
-// Upload the staged cells of an indirect column into its device store.
-static int32_t upload_store(const HostVarAccum &h, SideStore &st, cudaStream_t s) {
-  st.elem = h.elem;
-  st.n = h.n;
-  st.base = 0;
-  TQ_TRY(st.bytes.reserve(h.bytes.size() + 16));
-  if (!h.bytes.empty()) TQ_CUDA(cudaMemcpyAsync(st.bytes.p, h.bytes.data(), h.bytes.size(), cudaMemcpyHostToDevice, s));
-  if (h.elem == 0) {
-    TQ_TRY(st.offsets.reserve(h.off.size() * 8));
-    TQ_CUDA(cudaMemcpyAsync(st.offsets.p, h.off.data(), h.off.size() * 8, cudaMemcpyHostToDevice, s));
-  }
-  TQ_CUDA(cudaStreamSynchronize(s));  // pageable source
-  return TQ_OK;
-}
-
 // Result row ids -> cells, for every indirect column of a finished result batch.
 static int32_t materialize_indirect(tq_join *j, ResultBatch *rb, int slot) {
   const int ncols = j->n_build_cols + j->n_probe_cols;
@@ -1721,6 +1663,28 @@ static int32_t upload_col(const HostAccum &h, DevColBuf &d, cudaStream_t s) {
     if (h.data.p) TQ_CUDA(cudaMemcpyAsync(d.data.p, h.data.p, (size_t)h.n * 8, cudaMemcpyHostToDevice, s));
     TQ_CUDA(cudaMemcpyAsync(d.bm.p, h.bm.p, bitmap_bytes(h.n), cudaMemcpyHostToDevice, s));
   }
+  return TQ_OK;
+}
+
+// The 8-byte form of key column i of one side: the column itself, a FLOAT column widened to float64 bits, or the
+// dictionary ids of a var-len column (the build side inserts, the probe side only looks up: a string the build side
+// never had gets a 0 validity bit = "cannot match", exactly like a NULL key).
+static int32_t key_source(tq_join *j, bool build, int i, const std::vector<DCol> &view, const SideStore *store, int64_t n, DevBuf &xd, DevBuf &xb, DCol *out,
+                          cudaStream_t s) {
+  const int col = build ? j->bkeys[i] : j->pkeys[i];
+  const int kind = build ? j->bkey_kind[i] : j->pkey_kind[i];
+  if (kind == 0) { *out = view[col]; return TQ_OK; }
+  if (!store) { set_error("internal: FLOAT / var-len key column without a side store"); return TQ_ERR_STATE; }
+  TQ_TRY(xd.reserve((size_t)(n ? n : 1) * 8));
+  out->data = xd.as<uint64_t>();
+  if (kind == 1) {
+    TQ_TRY(widen_f32(store[col].bytes.as<uint32_t>(), n, xd.as<uint64_t>(), s));
+    out->bm = view[col].bm;
+    return TQ_OK;
+  }
+  TQ_TRY(xb.reserve(bitmap_alloc_bytes(n)));
+  TQ_TRY(j->sdict[i].encode(view_of(store[col]), view[col].bm, n, store[col].nbytes, /*insert=*/build, xd.as<uint64_t>(), xb.as<uint32_t>(), s));
+  out->bm = xb.as<uint32_t>();
   return TQ_OK;
 }
 
@@ -2075,12 +2039,12 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     bool any_out_bm = false;
     for (int c = 0; c < j->n_probe_cols; c++) any_out_bm |= (p.out_probe[c].bm != nullptr);
     for (int c = 0; c < j->n_build_cols; c++) any_out_bm |= (p.out_build[c].bm != nullptr);
-    ProbeKernel fast = (j->row_mode && !p.is_outer && !any_out_bm && !g_no_fast_kernel) ? fast_kernel(j->n_probe_cols, j->n_build_cols, g_probe_variant) : nullptr;
+    ProbeKernel fast = (j->row_mode && !p.is_outer && !any_out_bm && !g_no_fast_kernel) ? fast_kernel(j->n_probe_cols, j->n_build_cols) : nullptr;
     if (fast) {
-      static bool fast_attr[3][5][5] = {};
-      if (!fast_attr[g_probe_variant][j->n_probe_cols][j->n_build_cols]) {
+      static bool fast_attr[5][5] = {};
+      if (!fast_attr[j->n_probe_cols][j->n_build_cols]) {
         TQ_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_MAX_SMEM_BYTES));
-        fast_attr[g_probe_variant][j->n_probe_cols][j->n_build_cols] = true;
+        fast_attr[j->n_probe_cols][j->n_build_cols] = true;
       }
       fast<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
     } else if (j->build_unique) k_probe_part_uniq<<<work_parts * split, PROBE_THREADS, table_bytes, s>>>(p, j->table);
@@ -2193,10 +2157,19 @@ static int32_t start_batch(tq_join *j, const std::vector<DCol> &probe, const uin
   if (j->pending.active && j->pending.cursor_slot == slot) TQ_TRY(finalize_pending(j));
   std::vector<DCol> encoded;
   const std::vector<DCol> *pin = &probe;
-  if (j->n_keys > 1) {
+  if (j->key_hidden && j->n_keys == 1) {
+    DCol kc;
+    const std::vector<SideStore> &st = j->in_set[slot].store;
+    TQ_TRY(key_source(j, false, 0, probe, st.empty() ? nullptr : st.data(), n, j->kx_p_data[slot][0], j->kx_p_bm[slot][0], &kc, r.compute));
+    encoded = probe;
+    encoded[j->np_user] = kc;
+    pin = &encoded;
+  } else if (j->key_hidden) {
     // probe-side key tuples -> the hidden key column (lookup only: a value the build side never had is a miss)
     DCol kc[MK_MAX_KEYS];
-    for (int i = 0; i < j->n_keys; i++) kc[i] = probe[j->pkeys[i]];
+    const std::vector<SideStore> &st = j->in_set[slot].store;
+    for (int i = 0; i < j->n_keys; i++)
+      TQ_TRY(key_source(j, false, i, probe, st.empty() ? nullptr : st.data(), n, j->kx_p_data[slot][i], j->kx_p_bm[slot][i], &kc[i], r.compute));
     TQ_TRY(j->mk_probe_key[slot].reserve((size_t)n * 8));
     TQ_TRY(j->mk_probe_bm[slot].reserve(bitmap_alloc_bytes(n)));
     TQ_TRY(j->mk.encode(kc, j->mk_no_signbit, n, /*insert=*/false, /*null_is_value=*/false, j->mk_probe_key[slot].as<uint64_t>(),
@@ -2264,6 +2237,7 @@ static int32_t process_host_piece(tq_join *j, const tq_column *cols, int64_t row
       } else {
         const int64_t b0 = cols[c].offsets[row0], b1 = cols[c].offsets[row0 + rows];
         st.base = b0;
+        st.nbytes = b1 - b0;
         TQ_TRY(st.offsets.reserve((size_t)(rows + 1) * 8));
         TQ_TRY(st.bytes.reserve((size_t)(b1 - b0) + 16));
         TQ_CUDA(cudaMemcpyAsync(st.offsets.p, cols[c].offsets + row0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, r.h2d));
@@ -2340,27 +2314,22 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
     return TQ_ERR_INVALID_ARG;
   }
   if (d->n_keys < 1 || d->n_keys > MK_MAX_KEYS) { set_error("hash join on %d key columns: 1..%d are supported", d->n_keys, MK_MAX_KEYS); return TQ_ERR_INVALID_ARG; }
-  const int hidden = d->n_keys > 1 ? 1 : 0;
-  if (d->n_build_cols + hidden > MAXC || d->n_probe_cols + hidden > MAXC) { set_error("multi-column join keys need one spare column per side"); return TQ_ERR_INVALID_ARG; }
+  for (int i = 0; i < d->n_keys; i++)
+    if (d->build_key_idx[i] < 0 || d->build_key_idx[i] >= d->n_build_cols || d->probe_key_idx[i] < 0 || d->probe_key_idx[i] >= d->n_probe_cols) return TQ_ERR_INVALID_ARG;
+  // a hidden key column per side: several key columns, or a FLOAT / var-len key (compared as float64 / byte string)
+  int hidden = d->n_keys > 1 ? 1 : 0;
+  for (int i = 0; i < d->n_keys; i++)
+    if (type_indirect(d->build_types[d->build_key_idx[i]]) || type_indirect(d->probe_types[d->probe_key_idx[i]])) hidden = 1;
+  if (d->n_build_cols + hidden > MAXC || d->n_probe_cols + hidden > MAXC) { set_error("multi-column / FLOAT / var-len join keys need one spare column per side"); return TQ_ERR_INVALID_ARG; }
   for (int c = 0; c < d->n_build_cols; c++)
     if (!type_ok(d->build_types[c]) && !type_indirect(d->build_types[c])) { set_error("unsupport column type for encode %d", d->build_types[c]); return TQ_ERR_UNSUPPORTED_TYPE; }
   for (int c = 0; c < d->n_probe_cols; c++)
     if (!type_ok(d->probe_types[c]) && !type_indirect(d->probe_types[c])) { set_error("unsupport column type for encode %d", d->probe_types[c]); return TQ_ERR_UNSUPPORTED_TYPE; }
-  for (int i = 0; i < d->n_keys; i++) {
-    if (d->build_key_idx[i] < 0 || d->build_key_idx[i] >= d->n_build_cols || d->probe_key_idx[i] < 0 || d->probe_key_idx[i] >= d->n_probe_cols)
-      return TQ_ERR_INVALID_ARG;
-    // join keys: the 8-byte types (FLOAT / var-len keys hit the reference's "unsupport column type" too, codec.go:235)
-    if (!type_ok(d->build_types[d->build_key_idx[i]]) || !type_ok(d->probe_types[d->probe_key_idx[i]])) {
-      set_error("unsupport column type for encode (join key column of type %d / %d)", d->build_types[d->build_key_idx[i]], d->probe_types[d->probe_key_idx[i]]);
-      return TQ_ERR_UNSUPPORTED_TYPE;
-    }
-  }
   // LeftOuter keeps the left child as the outer side, RightOuter the right child (builder.go:451-477)
   if (d->join_type == TQ_JOIN_LEFT_OUTER && d->outer_is_right) { set_error("left outer join needs outer_is_right == 0"); return TQ_ERR_INVALID_ARG; }
   if (d->join_type == TQ_JOIN_RIGHT_OUTER && !d->outer_is_right) { set_error("right outer join needs outer_is_right == 1"); return TQ_ERR_INVALID_ARG; }
   { const char *e = getenv("TQ_JOIN_FORCE_GLOBAL"); g_force_global_table = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_NO_FAST"); g_no_fast_kernel = e && e[0] == '1'; }
-  { const char *e = getenv("TQ_JOIN_PROBE_VARIANT"); g_probe_variant = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
   { const char *e = getenv("TQ_JOIN_EXACT_SCATTER"); g_exact_scatter = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_MAX_LOAD_PCT"); if (e && atoll(e) >= 10 && atoll(e) <= 90) g_max_load_pct = atoll(e); }
   { const char *e = getenv("TQ_JOIN_TILES_PER_CTA"); if (e && atoll(e) > 0) g_tiles_per_cta = atoll(e); }
@@ -2379,12 +2348,16 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   for (int c = 0; c < d->n_probe_cols; c++) j->probe_types[c] = d->probe_types[c];
   // key comparison across types (codec.go:219-231,363-382): a DOUBLE never equals an integer key; signed vs unsigned
   // integers are equal only when both are below 2^63
-  auto mode_of = [](int bt, int pt) {
-    const bool bf = bt == TQ_TYPE_FLOAT64, pf = pt == TQ_TYPE_FLOAT64;
-    if (bf != pf) return (int)KEYMODE_NEVER;
-    if (!bf && bt != pt) return (int)KEYMODE_NO_SIGNBIT;
+  // flags: varintFlag / uvarintFlag for the integer types, floatFlag for FLOAT and DOUBLE (a FLOAT is hashed and compared as
+  // float64(f): float32(1) == float64(1), codec_test.go:735-769), compactBytesFlag for the var-len types
+  auto class_of = [](int t) { return (t == TQ_TYPE_FLOAT64 || t == TQ_TYPE_FLOAT32) ? 1 : (t == TQ_TYPE_BYTES ? 2 : 0); };
+  auto mode_of = [&](int bt, int pt) {
+    if (class_of(bt) != class_of(pt)) return (int)KEYMODE_NEVER;
+    if (class_of(bt) == 0 && bt != pt) return (int)KEYMODE_NO_SIGNBIT;
     return (int)KEYMODE_RAW;
   };
+  auto kind_of = [](int t) { return t == TQ_TYPE_FLOAT32 ? 1 : (t == TQ_TYPE_BYTES ? 2 : 0); };
+  j->key_hidden = hidden != 0;
   if (!hidden) {
     j->build_key = d->build_key_idx[0];
     j->probe_key = d->probe_key_idx[0];
@@ -2399,10 +2372,14 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
     for (int i = 0; i < d->n_keys; i++) {
       j->bkeys[i] = d->build_key_idx[i];
       j->pkeys[i] = d->probe_key_idx[i];
+      j->bkey_kind[i] = kind_of(j->build_types[j->bkeys[i]]);
+      j->pkey_kind[i] = kind_of(j->probe_types[j->pkeys[i]]);
       const int m = mode_of(j->build_types[j->bkeys[i]], j->probe_types[j->pkeys[i]]);
       if (m == KEYMODE_NEVER) j->key_mode = KEYMODE_NEVER;
       j->mk_no_signbit[i] = (m == KEYMODE_NO_SIGNBIT);
     }
+    // one key column: the hidden column IS that column's 8-byte form, so the signed/unsigned rule stays with the kernels
+    if (d->n_keys == 1 && j->key_mode != KEYMODE_NEVER && j->mk_no_signbit[0]) j->key_mode = KEYMODE_NO_SIGNBIT;
   }
   {
     const int bbase = j->outer_is_right ? 0 : j->n_probe_cols, pbase = j->outer_is_right ? j->n_build_cols : 0;
@@ -2618,11 +2595,18 @@ int32_t tq_join_finalize_build(tq_join *j) {
       j->b_view[c].bm = j->b_host[c].has_bm ? j->b_cols[c].bm.as<uint32_t>() : nullptr;
     }
   }
-  if (j->n_keys > 1) {
+  if (j->key_hidden && j->n_keys == 1) {
+    DCol kc;
+    TQ_TRY(key_source(j, true, 0, j->b_view, j->b_store, j->n_build, j->kx_b_data[0], j->kx_b_bm[0], &kc, r.compute));
+    j->b_view[j->nb_user] = kc;
+  } else if (j->key_hidden) {
     // build-side key tuples -> the hidden key column; a NULL in any key column leaves the row out of the table (hash_table.go:161-163)
     DCol kc[MK_MAX_KEYS];
     bool any_bm = false;
-    for (int i = 0; i < j->n_keys; i++) { kc[i] = j->b_view[j->bkeys[i]]; any_bm |= (kc[i].bm != nullptr); }
+    for (int i = 0; i < j->n_keys; i++) {
+      TQ_TRY(key_source(j, true, i, j->b_view, j->b_store, j->n_build, j->kx_b_data[i], j->kx_b_bm[i], &kc[i], r.compute));
+      any_bm |= (kc[i].bm != nullptr);
+    }
     TQ_TRY(j->mk_build_key.reserve((size_t)(j->n_build ? j->n_build : 1) * 8));
     if (any_bm) TQ_TRY(j->mk_build_bm.reserve(bitmap_alloc_bytes(j->n_build)));
     TQ_TRY(j->mk.encode(kc, nullptr, j->n_build, /*insert=*/true, /*null_is_value=*/false, j->mk_build_key.as<uint64_t>(),
@@ -2633,6 +2617,7 @@ int32_t tq_join_finalize_build(tq_join *j) {
   TQ_TRY(join_build(j));
   j->mk_build_key.release();
   j->mk_build_bm.release();
+  for (int i = 0; i < j->n_keys; i++) { j->kx_b_data[i].release(); j->kx_b_bm[i].release(); }
   for (auto &h : j->b_host) { h.data.release(); h.bm.release(); }
   j->b_dev_chunks.clear();
   j->state = tq_join::PROBING;

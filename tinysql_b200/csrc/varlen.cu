@@ -62,6 +62,46 @@ __global__ void __launch_bounds__(256) k_var_copy(const int64_t *off, int64_t ba
   }
 }
 
+__global__ void k_widen_f32(const uint32_t *src, int64_t n, uint64_t *dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = (uint64_t)__double_as_longlong((double)__uint_as_float(src[i]));
+}
+__global__ void k_narrow_f64(const uint64_t *src, int64_t n, uint32_t *dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float_as_uint((float)__longlong_as_double((long long)src[i]));
+}
+
+int32_t widen_f32(const uint32_t *src, int64_t n, uint64_t *dst, cudaStream_t s) {
+  if (n <= 0) return TQ_OK;
+  k_widen_f32<<<vl_grid(n), 256, 0, s>>>(src, n, dst);
+  count_launch();
+  return check_launch("k_widen_f32");
+}
+int32_t narrow_f64(const uint64_t *src, int64_t n, uint32_t *dst, cudaStream_t s) {
+  if (n <= 0) return TQ_OK;
+  k_narrow_f64<<<vl_grid(n), 256, 0, s>>>(src, n, dst);
+  count_launch();
+  return check_launch("k_narrow_f64");
+}
+
+// Upload the staged cells of an indirect column into its device store.
+int32_t upload_store(const HostVarAccum &h, SideStore &st, cudaStream_t s) {
+  st.elem = h.elem;
+  st.n = h.n;
+  st.base = 0;
+  st.nbytes = (int64_t)h.bytes.size();
+  TQ_TRY(st.bytes.reserve(h.bytes.size() + 16));
+  if (!h.bytes.empty()) TQ_CUDA(cudaMemcpyAsync(st.bytes.p, h.bytes.data(), h.bytes.size(), cudaMemcpyHostToDevice, s));
+  if (h.elem == 0) {
+    TQ_TRY(st.offsets.reserve(h.off.size() * 8));
+    TQ_CUDA(cudaMemcpyAsync(st.offsets.p, h.off.data(), h.off.size() * 8, cudaMemcpyHostToDevice, s));
+  }
+  TQ_CUDA(cudaStreamSynchronize(s));  // pageable source
+  return TQ_OK;
+}
+
 int32_t iota_u64(uint64_t *dst, int64_t n, cudaStream_t s) {
   if (n <= 0) return TQ_OK;
   k_iota_u64<<<vl_grid(n), 256, 0, s>>>(dst, n);

@@ -187,12 +187,19 @@ class HashAggExec:
                 L.check(lib.tq_agg_put(self.handle, tq_array(chk.cols), L.TQ_MEM_HOST))
             L.check(lib.tq_agg_eof(self.handle))
             self.prepared = True
-        out = [Column.empty(t, req) for t in self.types]
+        out = [VarColumn.empty(BYTES, req) if t == BYTES else Column.empty(t, req) for t in self.types]
+        if BYTES in self.types:
+            # size the var-len result buffers for this call (the *_next_size query of the ownership contract)
+            need = (C.c_int64 * len(self.types))()
+            L.check(lib.tq_agg_next_bytes(self.handle, req, need))
+            for i, t in enumerate(self.types):
+                if t == BYTES:
+                    out[i] = VarColumn.empty(BYTES, req, int(need[i]))
         arr = tq_array(out, req)
         n, eof = C.c_int64(0), C.c_int32(0)
         L.check(lib.tq_agg_next(self.handle, req, arr, C.byref(n), C.byref(eof)))
         k = n.value
-        return Chunk([Column(t, c.values[:k], c.not_null()[:k]) for t, c in zip(self.types, out)])
+        return Chunk([c.head(k) if t == BYTES else Column(t, c.values[:k], c.not_null()[:k]) for t, c in zip(self.types, out)])
 
     def Close(self):
         if self.handle is not None:
