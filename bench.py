@@ -29,15 +29,6 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
-def measured_traffic():
-    """dram__bytes_read + dram__bytes_write of the probe-pipeline kernels, from the committed ncu --set full capture"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_join_probe_traffic.json")) as f:
-            return float(json.load(f)["probe_pipeline_total"])
-    except Exception:
-        return None
-
-
 def join_config(n_build, n_probe):
     return {"workload": f"C3: int64 equi-join, uniform keys, build={n_build} probe={n_probe}, 100% match, output (B.k,B.v,P.k,P.v) materialised",
             "build_rows": n_build, "probe_rows": n_probe, "l2": "inputs (1.76 GB) and output (3.2 GB) exceed the 126 MB L2; no flush needed",
@@ -136,6 +127,22 @@ def cpu_join_sample(n_build, n_probe_full, sample_probe, workers, seed_rank=0):
             "build_s": bs.value, "probe_s": ps.value}
 
 
+def verify_join_result(rows, cols, pk, n_probe_expected, id_base=0):
+    """Size-independent properties of the C3 join, checked on EVERY row: B.v = 7*B.k + 1, B.k = P.k, P.k is the key the
+    probe row P.v really carried, and every probe row id appears exactly once (100 % match, unique build keys)."""
+    bk, bv, pkk, pv = cols
+    checks = {"row_count": rows == n_probe_expected,
+              "B.v == 7*B.k + 1": bool(np.array_equal(bv, bk * 7 + 1)),
+              "B.k == P.k": bool(np.array_equal(bk, pkk))}
+    ids = pv - id_base
+    in_range = bool(((ids >= 0) & (ids < len(pk))).all()) if rows else True
+    checks["P.v in range"] = in_range
+    if in_range and rows:
+        checks["P.k == probe_keys[P.v]"] = bool(np.array_equal(pkk, pk[ids]))
+        checks["every probe row exactly once"] = bool((np.bincount(ids, minlength=len(pk)) == 1).all()) if rows == len(pk) else False
+    return {"ok": all(checks.values()), "rows": int(rows), "checks": checks}
+
+
 # ------------------------------------------------------------------ GPU arm
 class JoinBench:
     def __init__(self, lib, L, n_build, n_probe, rank=0, world=1):
@@ -154,8 +161,9 @@ class JoinBench:
         self._keep = (t, k)
         return L.TQJoinDesc(0, 1, 2, t, 2, t, 1, k, k, batch, flags)
 
-    def step_device(self):
-        """build + probe with inputs resident in HBM; returns (joined rows, probe kernel ns, build ns)."""
+    def step_device(self, keep=False):
+        """build + probe with inputs resident in HBM; returns (joined rows, probe kernel ns, build ns).  keep=True copies the
+        four result columns to the host (verification leg, outside every timed region)."""
         L, lib = self.L, self.lib
         h = C.c_void_p()
         d = self.desc()
@@ -177,8 +185,22 @@ class JoinBench:
         lib.tq_join_stats(h, st)
         rows = n.value
         self.last_out = None
+        if keep:
+            self.last_out = []
+            for c in range(4):
+                a = np.empty(rows, dtype=np.int64)
+                L.check(lib.tq_memcpy_d2h(a.ctypes.data, out[c].data, rows * 8))
+                self.last_out.append(a)
         L.check(lib.tq_join_destroy(h))
         return rows, st[5], st[6]
+
+    def verify(self):
+        """Full-size value check of the device-resident join (outside the timed region): output = (B.k, B.v, P.k, P.v)."""
+        return verify_join_result(*self.step_and_keep(), self.pk, self.n_probe)
+
+    def step_and_keep(self):
+        rows, _, _ = self.step_device(keep=True)
+        return rows, self.last_out
 
     def setup_e2e(self):
         """pinned host inputs / outputs for the C-ABI host path"""
@@ -232,6 +254,7 @@ class JoinBench:
                 if n.value == 0:
                     return bool(eof.value)
                 total += n.value
+                self.last_e2e_rows = n.value
                 checksum += int(self.h_out[1][1][0])  # touch the result on the host
         for lo in range(0, self.n_probe, piece):
             rows = min(piece, self.n_probe - lo)
@@ -247,6 +270,74 @@ class JoinBench:
         return total
 
 
+    def free(self):
+        """give the join tables back before the secondary workloads allocate theirs"""
+        for c in self.d_b + self.d_p:
+            c.free()
+        for bufs in (getattr(self, "h_b", []), getattr(self, "h_p", []), getattr(self, "h_out", [])):
+            for p, _ in bufs:
+                self.lib.tq_pinned_free(p)
+        self.h_b = self.h_p = self.h_out = []
+
+    def verify_e2e_tail(self):
+        """the host buffers still hold the LAST result piece of the last e2e step: its rows must satisfy the row-wise properties"""
+        n = self.last_e2e_rows
+        bk, bv, pkk, pv = (self.h_out[c][1][:n] for c in range(4))
+        ok = bool(n > 0 and np.array_equal(bv, bk * 7 + 1) and np.array_equal(bk, pkk) and np.array_equal(pkk, self.pk[pv]))
+        return {"rows": int(n), "ok": ok}
+
+    def step_e2e_chunked(self):
+        """The reference's own calling pattern (executor/join.go:194-221, the shim in INTEGRATION.md): ONE <=1024-row chunk per
+        tq_join_put_build / tq_join_put_probe call from ordinary (pageable) host memory, no TQ_JOIN_STABLE_INPUT, results drained
+        through tq_join_next with 1024-row chunks.  ~2e5 C-ABI calls per step; the caller here is a Python loop, so the
+        figure includes ~1 us of ctypes overhead per call (a cgo call costs about the same)."""
+        L, lib = self.L, self.lib
+        h = C.c_void_p()
+        d = self.desc()
+        L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
+        CH = 1024
+        t0 = time.perf_counter()
+        a = (L.TQColumn * 2)()
+        for lo in range(0, self.n_build, CH):
+            rows = min(CH, self.n_build - lo)
+            for i, src in enumerate((self.bk, self.bv)):
+                a[i].length, a[i].data, a[i].null_bitmap, a[i].offsets = rows, src.ctypes.data + lo * 8, None, None
+            L.check(lib.tq_join_put_build(h, a, L.TQ_MEM_HOST))
+        L.check(lib.tq_join_finalize_build(h))
+        outs = [np.empty(CH, dtype=np.int64) for _ in range(4)]
+        bms = [np.zeros(CH // 8 + 8, dtype=np.uint8) for _ in range(4)]
+        out = (L.TQColumn * 4)()
+        for i in range(4):
+            out[i].data, out[i].null_bitmap = outs[i].ctypes.data, bms[i].ctypes.data
+        n, eof = C.c_int64(0), C.c_int32(0)
+        total, ok = 0, True
+
+        def drain():
+            nonlocal total, ok
+            while True:
+                L.check(lib.tq_join_next(h, CH, out, C.byref(n), C.byref(eof)))
+                if n.value == 0:
+                    return bool(eof.value)
+                total += n.value
+                ok = ok and int(outs[1][0]) == int(outs[0][0]) * 7 + 1   # touch the chunk on the host
+        for lo in range(0, self.n_probe, CH):
+            rows = min(CH, self.n_probe - lo)
+            for i, src in enumerate((self.pk, self.pv)):
+                a[i].length, a[i].data, a[i].null_bitmap, a[i].offsets = rows, src.ctypes.data + lo * 8, None, None
+            L.check(lib.tq_join_put_probe(h, a, None, L.TQ_MEM_HOST))
+            drain()
+        L.check(lib.tq_join_probe_eof(h))
+        while not drain():
+            pass
+        dt = time.perf_counter() - t0
+        L.check(lib.tq_join_destroy(h))
+        calls = 2 * ((self.n_probe + CH - 1) // CH) + (self.n_build + CH - 1) // CH
+        return {"value": total / dt, "unit": "joined rows/s", "ms_per_step": dt * 1e3, "rows": int(total), "ok": bool(ok and total == self.n_probe),
+                "chunk_rows": CH, "c_abi_calls_per_step": int(calls), "h2d_bytes_per_step": 16 * (self.n_build + self.n_probe),
+                "d2h_bytes_per_step": 32 * self.n_probe,
+                "note": "one <=1024-row chunk per call from pageable host memory (no STABLE_INPUT), 1 step, driven from Python"}
+
+
 def run_join_bench(args, rank, world, local_rank, dist):
     from tinysql_b200 import _lib as L
     lib = L.load()
@@ -257,7 +348,6 @@ def run_join_bench(args, rank, world, local_rank, dist):
         from tinysql_b200 import dist as D
         return D.bench_distributed_join(args, rank, world, local_rank, dist, peak, peak_src)
     jb = JoinBench(lib, L, n_build, n_probe, rank, world)
-    launches0 = lib.tq_kernel_launch_count()
     for _ in range(args.warmup):
         rows, _, _ = jb.step_device()
         assert rows == n_probe, rows
@@ -278,12 +368,17 @@ def run_join_bench(args, rank, world, local_rank, dist):
     launches2 = lib.tq_kernel_launch_count()
     ms_per_step = ms.value / args.steps
     value = n_probe / (ms_per_step * 1e-3)
-    # roofline of the dominant kernel (k_probe): 64 algorithmic bytes per probe row (SURVEY §8d / DESIGN.md)
+    # roofline of the dominant kernels (the probe pipeline): 64 algorithmic bytes per probe row (SURVEY §8d / DESIGN.md)
     probe_s = statistics.mean(probe_ns) * 1e-9
     achieved = 64.0 * n_probe / probe_s / 1e9
     if args.kernel_only:
-        return {"value": value, "ms_per_step": ms_per_step, "kernel_ms": probe_s * 1e3, "build_ms": statistics.mean(build_ns) * 1e-6,
-                "frac": achieved / peak, "gpu_launches": int(launches2 - launches1)}
+        out = {"value": value, "ms_per_step": ms_per_step, "kernel_ms": probe_s * 1e3, "build_ms": statistics.mean(build_ns) * 1e-6,
+               "frac": achieved / peak, "gpu_launches": int(launches2 - launches1)}
+        if args.verify:
+            out["verified"] = jb.verify()
+        return out
+    # every value of the full-size result is checked once, outside the timed region
+    verified = jb.verify()
     # end to end through the C-ABI with pinned host buffers
     jb.setup_e2e()
     e2e_steps = max(1, min(args.steps, 3))
@@ -294,6 +389,8 @@ def run_join_bench(args, rank, world, local_rank, dist):
         assert total == n_probe
     lib.tq_device_synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    verified["e2e_last_piece"] = jb.verify_e2e_tail()
+    chunked = jb.step_e2e_chunked() if not args.no_chunked_e2e else None
     workers = os.cpu_count() or 1
     cpu = cpu_join_sample(n_build, n_probe, min(n_probe, args.cpu_sample_rows), workers)
     out = {
@@ -301,35 +398,63 @@ def run_join_bench(args, rank, world, local_rank, dist):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
         "config": join_config(n_build, n_probe),
-        "roofline": {"bound": "hbm", "kernel": "probe pipeline = k_probe_scatter_fast<2> + k_probe_part_fast<2,2> (timed together with CUDA events on the library stream)",
+        "roofline": {"bound": "hbm", "kernel": "probe pipeline = k_scatter_aos<2> (TMA-fed radix scatter) + k_probe_pos<2,2> (TMA-fed positional probe) + hole filling, "
+                                                "timed together with CUDA events on the library stream",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic() if (n_build, n_probe) == (10_000_000, 100_000_000) else None,
+                     "traffic": None, "traffic_note": "not measured in this run (ncu --set full captures: profiles/)",
                      "peak_source": peak_src, "algorithmic_bytes_per_row": 64, "algorithmic_bytes": 64 * n_probe, "kernel_ms": probe_s * 1e3,
                      "build_ms": statistics.mean(build_ns) * 1e-6},
         "e2e": {"value": n_probe / e2e_s, "unit": "joined rows/s", "h2d_bytes_per_step": 16 * (n_build + n_probe), "d2h_bytes_per_step": 32 * n_probe,
                 "ms_per_step": e2e_s * 1e3},
+        "e2e_chunked": chunked,
+        "verified": verified,
         "gpu_launches": int(launches2 - launches1), "clocks": clocks, "cpu_baseline": cpu,
     }
+    jb.free()
+    if not args.no_secondary:
+        out["secondary"] = run_secondary(args, lib, peak, peak_src)
     return out
 
 
+def run_secondary(args, lib, peak, peak_src):
+    """BASELINE configs C2 (vectorized LT + Plus over 1e8 rows) and C4 (1e8-row GROUP BY, 1e6 groups) in the same driver-run
+    record: value, roofline, cpu_baseline, e2e and a full-size value check each; timed after the headline."""
+    import bench_extra
+    sec = {}
+    sub = argparse.Namespace(**vars(args))
+    sub.steps, sub.warmup = max(3, min(args.steps, 10)), max(3, min(args.warmup, 5))
+    for name, fn in (("C2", bench_extra.run_expr), ("C4", bench_extra.run_agg)):
+        try:
+            r = fn(sub, lib, peak, peak_src, ClockSampler)
+            sec[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config", "roofline", "e2e", "cpu_baseline", "verified", "gpu_launches", "clocks")
+                         if k in r}
+        except Exception as e:  # the headline line must survive a secondary failure; the failure itself is reported
+            sec[name] = {"error": f"{type(e).__name__}: {e}"}
+    return sec
+
+
 def run_reference(args, rank):
-    """--impl reference: the CPU restatement of the reference's goroutine design on the host cores."""
+    """--impl reference: the CPU restatement of the reference's goroutine design on the host cores (all host threads).
+    Every step builds the full hash table and probes a bounded sample of the probe side: the WHOLE probe side when the
+    run is short enough, else 40 % of it (stated in `sample`); the reported value is the median step."""
     if rank != 0:
         return None
     n_build, n_probe = args.build_rows, args.probe_rows
     workers = os.cpu_count() or 1
-    sample = min(n_probe, args.cpu_sample_rows)
+    n_steps = args.warmup + args.steps
+    sample = n_probe if n_steps <= 8 else min(n_probe, max(args.cpu_sample_rows, int(n_probe * 0.4)))
     res = None
     times = []
-    for i in range(args.warmup + args.steps):
+    for i in range(n_steps):
         r = cpu_join_sample(n_build, n_probe, sample, workers)
         if i >= args.warmup:
             times.append(r)
         res = r
-    v = statistics.mean([r["value"] for r in times]) if times else res["value"]
+    vals = sorted(r["value"] for r in times) if times else [res["value"]]
+    v = statistics.median(vals)
     res = dict(res)
     res["value"] = v
+    res["step_values_min_median_max"] = [vals[0], v, vals[-1]]
     return {"impl": "reference", "metric": "joined rows/sec on 1e8-row int64 equi-join", "value": v, "unit": "joined rows/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_probe / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
@@ -348,6 +473,9 @@ def main():
     ap.add_argument("--probe-rows", type=int, default=100_000_000)
     ap.add_argument("--cpu-sample-rows", type=int, default=20_000_000)
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and CPU legs (profiling runs)")
+    ap.add_argument("--verify", action="store_true", help="with --kernel-only: still run the full-size value check")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C4 secondary block")
+    ap.add_argument("--no-chunked-e2e", action="store_true", help="skip the <=1024-row chunk protocol e2e figure")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

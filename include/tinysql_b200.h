@@ -175,6 +175,15 @@ int32_t tq_vec_in_int(int64_t n, const tq_column *a, int32_t a_unsigned, int32_t
                       const tq_column *list, const int32_t *list_unsigned, tq_column *out,
                       int32_t mem);
 
+/* builtinInRealSig — expression/builtin_other_vec_generated.go:151-204 (DOUBLE operands, types.CompareFloat64 == 0). */
+int32_t tq_vec_in_real(int64_t n, const tq_column *a, int32_t n_list, const tq_column *list, tq_column *out, int32_t mem);
+/* builtinInStringSig — builtin_other_vec_generated.go:97-149 (var-len operands, byte-wise equality); n_list <= 8 per call. */
+int32_t tq_vec_in_string(int64_t n, const tq_column *a, int32_t n_list, const tq_column *list, tq_column *out, int32_t mem);
+/* builtinIfStringSig / builtinIfNullStringSig.vecEvalString — builtin_control_vec_generated.go:209-262, 81-112.  a / b / out are
+ * var-len columns; out needs offsets for n + 1 entries, a null_bitmap, and a data buffer of at least bytes(a) + bytes(b). */
+int32_t tq_vec_if_string(int64_t n, const tq_column *cond, const tq_column *a, const tq_column *b, tq_column *out, int32_t mem);
+int32_t tq_vec_ifnull_string(int64_t n, const tq_column *a, const tq_column *b, tq_column *out, int32_t mem);
+
 /* The BASELINE config-2 pair in one pass: lt_out = (a < b), plus_out = a + b, both
  * signed BIGINT — one read of a and b instead of two (32 B/row instead of 48). */
 int32_t tq_vec_lt_plus_int(int64_t n, const tq_column *a, const tq_column *b,
@@ -184,6 +193,8 @@ int32_t tq_vec_lt_plus_int(int64_t n, const tq_column *a, const tq_column *b,
  * (expression/chunk_executor.go:196-245, toBool expression.go:281-326): selected[i] =
  * (not NULL && value != 0).  selected is n bytes (Go []bool). */
 int32_t tq_vec_filter_int(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem);
+/* the same for an ETReal expression: toBool's zero test is types.RoundFloat(f) == 0, i.e. |f| < 0.5 (expression.go:296-307). */
+int32_t tq_vec_filter_real(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem);
 
 /* ------------------------------------------------------------------ hash join
  * Replaces HashJoinExec (executor/join.go:31-146), hashRowContainer / rowHashMap
@@ -213,6 +224,12 @@ typedef struct tq_join_desc {
   const int32_t *probe_key_idx; /* outerKeys[i].Index                                         */
   int64_t probe_batch_rows;   /* device batch size the ≤1024-row chunks are accumulated into; 0 = default */
   int32_t flags;              /* TQ_JOIN_STABLE_INPUT or 0                                    */
+  /* defaultInner of an outer join — PhysicalHashJoin.DefaultValues (executor/joiner.go:139-143, builder.go:449-465; set by
+   * the aggregation push-down, planner/core/rule_aggregation_push_down.go:211-214, e.g. COUNT -> 0): the inner side of a miss
+   * row.  default_inner_not_null[c] != 0 gives inner column c the value default_inner_bits[c] (8-byte column types);
+   * both NULL = the usual all-NULL inner side. */
+  const uint64_t *default_inner_bits;
+  const uint8_t *default_inner_not_null;
 } tq_join_desc;
 
 /* tq_join_desc.flags.  STABLE_INPUT: every host buffer passed to tq_join_put_build / tq_join_put_probe stays valid and

@@ -282,6 +282,18 @@ int orc_hash_join_cond(int join_type, int outer_is_right,
                        int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
                        int n_keys, const int *build_key_idx, const int *probe_key_idx,
                        const uint8_t *selected, int n_conds, const orc_join_cond *conds, orc_column *out_cols, int64_t *n_out) {
+  return orc_hash_join_full(join_type, outer_is_right, n_build_cols, build_types, build_cols, n_probe_cols, probe_types, probe_cols, n_keys, build_key_idx,
+                            probe_key_idx, selected, n_conds, conds, NULL, NULL, out_cols, n_out);
+}
+
+/* default_bits / default_nn: defaultInner (joiner.go:139-143 initDefaultInner from PhysicalHashJoin.DefaultValues): the inner side of
+ * a miss row of an outer join; NULL = all NULL (builder.go:463-465) */
+int orc_hash_join_full(int join_type, int outer_is_right,
+                       int n_build_cols, const int *build_types, const orc_column *build_cols,
+                       int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
+                       int n_keys, const int *build_key_idx, const int *probe_key_idx,
+                       const uint8_t *selected, int n_conds, const orc_join_cond *conds,
+                       const uint64_t *default_bits, const uint8_t *default_nn, orc_column *out_cols, int64_t *n_out) {
   if (join_type < 0 || join_type > 2 || n_keys < 1 || n_conds < 0) return ORC_ERR_INVALID;
   for (int k = 0; k < n_conds; k++) {  /* operands: the 8-byte types, integers with integers / doubles with doubles */
     int nt = n_build_cols + n_probe_cols;
@@ -338,7 +350,10 @@ int orc_hash_join_cond(int join_type, int outer_is_right,
       }
     }
     if (n_matched == 0 && is_outer) {                           /* onMissMatch joiner.go:274-277,337-340; inner: :405 */
-      append_row(obs, build_base, n_build_cols, build_cols, -1);
+      for (int c = 0; c < n_build_cols; c++) {                  /* outer ++ defaultInner */
+        if (default_nn && default_nn[c] && elem_of_type(build_types[c]) == 8) ob_push(&obs[build_base + c], default_bits[c], 1);
+        else ob_push_cell(&obs[build_base + c], &build_cols[c], -1);
+      }
       append_row(obs, probe_base, n_probe_cols, probe_cols, i);
     }
   }
@@ -876,3 +891,62 @@ int orc_vec_string_unary(int op, int64_t n, const orc_column *a, orc_column *out
   }
   return ORC_OK;
 }
+
+/* builtinInRealSig.vecEvalInt (expression/builtin_other_vec_generated.go:151-204): like IN over ints with types.CompareFloat64 */
+int orc_vec_in_real(int64_t n, const orc_column *a, int n_list, const orc_column *list, orc_column *out) {
+  out_init(out, n);
+  int64_t *r = (int64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) {
+    int has_null = 0, found = 0;
+    for (int j = 0; j < n_list; j++) {
+      if (col_is_null(a, i) || col_is_null(&list[j], i)) { has_null = 1; continue; }   /* buf1.MergeNulls(buf0) :185 */
+      double x = col_f64(a, i), y = col_f64(&list[j], i);
+      if (cmp_f64(x, y) == 0) found = 1;                                             /* :193-197 */
+    }
+    r[i] = found;
+    col_set_null(out, i, !found && has_null);                                        /* :199-203 */
+  }
+  return ORC_OK;
+}
+
+/* builtinInStringSig.vecEvalInt (builtin_other_vec_generated.go:97-149) */
+int orc_vec_in_string(int64_t n, const orc_column *a, int n_list, const orc_column *list, orc_column *out) {
+  out_init(out, n);
+  int64_t *r = (int64_t *)out->data;
+  for (int64_t i = 0; i < n; i++) {
+    int has_null = 0, found = 0;
+    for (int j = 0; j < n_list; j++) {
+      if (col_is_null(a, i) || col_is_null(&list[j], i)) { has_null = 1; continue; }
+      const orc_column *b = &list[j];
+      if (compare_string(a->data + a->offsets[i], a->offsets[i + 1] - a->offsets[i], b->data + b->offsets[i], b->offsets[i + 1] - b->offsets[i]) == 0) found = 1;
+    }
+    r[i] = found;
+    col_set_null(out, i, !found && has_null);
+  }
+  return ORC_OK;
+}
+
+/* builtinIfStringSig (builtin_control_vec_generated.go:209-262, mode 0) / builtinIfNullStringSig (:81-112, mode 1): the result
+ * column is malloc'ed here (free with orc_free_columns) */
+int orc_vec_pick_string(int mode, int64_t n, const orc_column *cond, const orc_column *a, const orc_column *b, orc_column *out) {
+  outbuf ob; memset(&ob, 0, sizeof(ob)); ob.elem = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const orc_column *src;
+    if (mode == 0) src = (col_is_null(cond, i) || col_i64(cond, i) == 0) ? b : a;
+    else src = !col_is_null(a, i) ? a : b;
+    ob_push_cell(&ob, src, col_is_null(src, i) ? -1 : i);
+  }
+  ob_finish(&ob, out);
+  return ORC_OK;
+}
+
+/* toBool for ETReal (expression/expression.go:296-307): zero iff types.RoundFloat(f) == 0 (types/helper.go:28-34) */
+int orc_vec_filter_real(int64_t n, const orc_column *a, uint8_t *selected) {
+  for (int64_t i = 0; i < n; i++) {
+    double f = col_f64(a, i), rf;
+    if (fabs(f) < 0.5) rf = 0; else rf = trunc(f + copysign(0.5, f));
+    selected[i] = (uint8_t)(!col_is_null(a, i) && !(rf == 0));
+  }
+  return ORC_OK;
+}
+

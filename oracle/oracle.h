@@ -109,6 +109,17 @@ int64_t orc_mt_lt_plus_bench(int64_t n, const int64_t *a, const int64_t *b, int6
 int orc_vec_compare_string(int op, int64_t n, const orc_column *a, const orc_column *b, orc_column *out);
 int orc_vec_string_unary(int op, int64_t n, const orc_column *a, orc_column *out);
 
+int orc_hash_join_full(int join_type, int outer_is_right,
+                       int n_build_cols, const int *build_types, const orc_column *build_cols,
+                       int n_probe_cols, const int *probe_types, const orc_column *probe_cols,
+                       int n_keys, const int *build_key_idx, const int *probe_key_idx,
+                       const uint8_t *selected, int n_conds, const orc_join_cond *conds,
+                       const uint64_t *default_bits, const uint8_t *default_nn, orc_column *out_cols, int64_t *n_out);
+/* the rest of the vectorized signatures (builtin_other_vec_generated.go:97-204, builtin_control_vec_generated.go:81-112,209-262) */
+int orc_vec_in_real(int64_t n, const orc_column *a, int n_list, const orc_column *list, orc_column *out);
+int orc_vec_in_string(int64_t n, const orc_column *a, int n_list, const orc_column *list, orc_column *out);
+int orc_vec_pick_string(int mode, int64_t n, const orc_column *cond, const orc_column *a, const orc_column *b, orc_column *out);
+int orc_vec_filter_real(int64_t n, const orc_column *a, uint8_t *selected);
 #ifdef __cplusplus
 }
 #endif

@@ -71,7 +71,8 @@ def _conds(conds):
     return arr
 
 
-def hash_join(join_type, outer_is_right, build_types, build_cols, probe_types, probe_cols, build_keys, probe_keys, selected=None, conds=()):
+def hash_join(join_type, outer_is_right, build_types, build_cols, probe_types, probe_cols, build_keys, probe_keys, selected=None, conds=(), default_inner=None):
+    """default_inner: list of per-inner-column values (None = NULL) — PhysicalHashJoin.DefaultValues"""
     lib = load()
     ncols = len(build_cols) + len(probe_cols)
     out = (TQColumn * ncols)()
@@ -79,10 +80,14 @@ def hash_join(join_type, outer_is_right, build_types, build_cols, probe_types, p
     sel = None
     if selected is not None:
         sel = np.ascontiguousarray(selected, dtype=np.uint8)
-    rc = lib.orc_hash_join_cond(C.c_int(join_type), C.c_int(1 if outer_is_right else 0), C.c_int(len(build_cols)), _i32(build_types),
+    dbits = dnn = None
+    if default_inner is not None:
+        dbits = (C.c_uint64 * len(build_cols))(*[0 if v is None else int(np.array([v], dtype=_NP[t]).view(np.uint64)[0]) for v, t in zip(default_inner, build_types)])
+        dnn = (C.c_uint8 * len(build_cols))(*[0 if v is None else 1 for v in default_inner])
+    rc = lib.orc_hash_join_full(C.c_int(join_type), C.c_int(1 if outer_is_right else 0), C.c_int(len(build_cols)), _i32(build_types),
                                 tq_array(build_cols), C.c_int(len(probe_cols)), _i32(probe_types), tq_array(probe_cols), C.c_int(len(build_keys)),
                                 _i32(build_keys), _i32(probe_keys), C.c_void_p(sel.ctypes.data) if sel is not None else None,
-                                C.c_int(len(conds)), _conds(conds), out, C.byref(n))
+                                C.c_int(len(conds)), _conds(conds), dbits, dnn, out, C.byref(n))
     if rc != 0:
         raise RuntimeError(f"oracle join failed: {rc}")
     types = (list(build_types) + list(probe_types)) if outer_is_right else (list(probe_types) + list(build_types))
@@ -189,4 +194,32 @@ def vec_filter_int(a):
     ta = a.tq()
     sel = np.zeros(max(a.length, 1), dtype=np.uint8)
     load().orc_vec_filter_int(C.c_int64(a.length), C.byref(ta), C.c_void_p(sel.ctypes.data))
+    return sel[: a.length]
+
+
+def vec_in_real(a, lst):
+    ta = a.tq()
+    return _vec(load().orc_vec_in_real, 1, a.length, C.c_int64(a.length), C.byref(ta), C.c_int(len(lst)), tq_array(lst))
+
+
+def vec_in_string(a, lst):
+    ta = a.tq()
+    return _vec(load().orc_vec_in_string, 1, a.length, C.c_int64(a.length), C.byref(ta), C.c_int(len(lst)), tq_array(lst))
+
+
+def vec_pick_string(mode, cond, a, b):
+    """mode 0: IF(cond, a, b); mode 1: IFNULL(a, b) over var-len columns"""
+    out = (TQColumn * 1)()
+    tc = cond.tq() if cond is not None else TQColumn()
+    ta, tb = a.tq(), b.tq()
+    rc = load().orc_vec_pick_string(C.c_int(mode), C.c_int64(a.length), C.byref(tc), C.byref(ta), C.byref(tb), out)
+    res = _take(out, [5], a.length)[0]
+    load().orc_free_columns(C.c_int(1), out)
+    return rc, res
+
+
+def vec_filter_real(a):
+    ta = a.tq()
+    sel = np.zeros(max(a.length, 1), dtype=np.uint8)
+    load().orc_vec_filter_real(C.c_int64(a.length), C.byref(ta), C.c_void_p(sel.ctypes.data))
     return sel[: a.length]

@@ -38,7 +38,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(L.TQColumn) == 32  # int64 + 3 pointers
     assert L.TQColumn.length.offset == 0 and L.TQColumn.null_bitmap.offset == 8 and L.TQColumn.offsets.offset == 16 and L.TQColumn.data.offset == 24
     assert C.sizeof(L.TQAggFunc) == 8
-    assert C.sizeof(L.TQJoinDesc) == 80 and L.TQJoinDesc.flags.offset == 72  # ... int64 probe_batch_rows, int32 flags (+ pad)
+    # ... int64 probe_batch_rows, int32 flags (+ pad), then the two defaultInner pointers
+    assert C.sizeof(L.TQJoinDesc) == 96 and L.TQJoinDesc.flags.offset == 72 and L.TQJoinDesc.default_inner_bits.offset == 80 and L.TQJoinDesc.default_inner_not_null.offset == 88
     assert C.sizeof(L.TQAggDesc) == 56
 
 

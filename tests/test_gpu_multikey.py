@@ -239,3 +239,23 @@ def test_join_other_conditions(lib, nb, npr, jt, oir):
     e.Close()
     want = O.hash_join(jt, oir, bt, bcols, pt, pcols, [0], [1], None, conds)
     assert_same_multiset(got, want)
+
+
+@pytest.mark.parametrize("jt,oir", [(LEFT_OUTER_JOIN, False), (RIGHT_OUTER_JOIN, True)])
+@pytest.mark.parametrize("nb,npr", [(300, 2000), (300000, 900000)])
+def test_join_default_inner_row(lib, nb, npr, jt, oir):
+    """defaultInner (joiner.go:139-143): miss rows of an outer join carry PhysicalHashJoin.DefaultValues on the inner side — e.g.
+    COUNT -> 0 after the aggregation push-down (rule_aggregation_push_down.go:211-214) — with and without OtherConditions"""
+    rng = np.random.default_rng(nb + jt)
+    bcols = [gen_col(rng, INT64, nb, 0.05, 0, nb // 2 + 2), gen_col(rng, INT64, nb, 0.1, -50, 50), gen_col(rng, FLOAT64, nb, 0.1)]
+    pcols = [gen_col(rng, INT64, npr, 0.05, 0, nb), gen_col(rng, INT64, npr, 0.1, -50, 50)]
+    bt, pt = [INT64, INT64, FLOAT64], [INT64, INT64]
+    defaults = [None, 0, 2.5]
+    for conds in ((), ([(0, 1, 3)] if oir else [(0, 3, 1)])):   # b1 < p1
+        inner, outer = MockDataSource(bt, bcols, 1 << 16), MockDataSource(pt, pcols, 1 << 16)
+        e = HashJoinExec(outer, inner, [0], [0], jt, oir, None, 1 << 18, other_conditions=conds, default_inner=defaults)
+        e.Open()
+        got = e.drain()
+        e.Close()
+        want = O.hash_join(jt, oir, bt, bcols, pt, pcols, [0], [0], None, conds, default_inner=defaults)
+        assert_same_multiset(got, want)

@@ -51,3 +51,38 @@ def test_string_compare_long_cells_and_high_bytes(lib):
         assert_col_equal(E.vec_compare_string(op, a, b), want, check_null_slots=True)
     assert E.vec_compare_string(E.STRCMP, a, b).tolist() == [0, 1, 1, -1, 1, -1, 1, 0]
     assert E.vec_string_unary(E.STR_LENGTH, a).tolist() == [5120, 5120, 5121, 5120, 1, 1, 6, 0]
+
+
+@pytest.mark.parametrize("n", [0, 1, 33, 1000, 20011])
+def test_string_if_ifnull_in(lib, n):
+    """builtinIfStringSig / builtinIfNullStringSig / builtinInStringSig (builtin_control_vec_generated.go:81-112,209-262,
+    builtin_other_vec_generated.go:97-149) against the oracle"""
+    from tinysql_b200.chunk import INT64
+    rng = np.random.default_rng(n + 9)
+    a, b = Column(BYTES, rand_strings(rng, n, 40, 0.2, alphabet=2)), Column(BYTES, rand_strings(rng, n, 40, 0.2, alphabet=2))
+    cond = Column(INT64, rng.integers(-1, 2, n), rng.random(n) > 0.2)
+    rc, want = O.vec_pick_string(0, cond, a, b)
+    assert rc == 0 and E.vec_if_string(cond, a, b).tolist() == want.tolist()
+    rc, want = O.vec_pick_string(1, None, a, b)
+    assert rc == 0 and E.vec_ifnull_string(a, b).tolist() == want.tolist()
+    short = [Column(BYTES, rand_strings(rng, n, 3, 0.15, alphabet=2)) for _ in range(4)]
+    x = Column(BYTES, rand_strings(rng, n, 3, 0.15, alphabet=2))
+    for k in (1, 4):
+        rc, want = O.vec_in_string(x, short[:k])
+        assert rc == 0
+        assert_col_equal(E.vec_in_string(x, short[:k]), want, check_null_slots=True)
+
+
+@pytest.mark.parametrize("n", [0, 5, 64, 10007])
+def test_in_real_and_real_to_bool(lib, n):
+    """builtinInRealSig (builtin_other_vec_generated.go:151-204); toBool for ETReal (expression.go:296-307, RoundFloat)"""
+    from tinysql_b200.chunk import FLOAT64
+    rng = np.random.default_rng(n)
+    vals = np.array([0.0, -0.0, 0.25, 0.5, -0.5, 0.49999999999999994, 1.5, np.nan, np.inf, -3.0])
+    a = Column(FLOAT64, rng.choice(vals, n), rng.random(n) > 0.15)
+    lst = [Column(FLOAT64, rng.choice(vals, n), rng.random(n) > 0.15) for _ in range(3)]
+    for k in (1, 3):
+        rc, want = O.vec_in_real(a, lst[:k])
+        assert rc == 0
+        assert_col_equal(E.vec_in_real(a, lst[:k]), want, check_null_slots=True)
+    assert np.array_equal(E.vectorized_filter_real(a), O.vec_filter_real(a))

@@ -19,7 +19,8 @@ class TQJoinDesc(C.Structure):
     _fields_ = [("join_type", C.c_int32), ("outer_is_right", C.c_int32), ("n_build_cols", C.c_int32),
                 ("build_types", C.POINTER(C.c_int32)), ("n_probe_cols", C.c_int32), ("probe_types", C.POINTER(C.c_int32)),
                 ("n_keys", C.c_int32), ("build_key_idx", C.POINTER(C.c_int32)), ("probe_key_idx", C.POINTER(C.c_int32)),
-                ("probe_batch_rows", C.c_int64), ("flags", C.c_int32)]
+                ("probe_batch_rows", C.c_int64), ("flags", C.c_int32),
+                ("default_inner_bits", C.POINTER(C.c_uint64)), ("default_inner_not_null", C.POINTER(C.c_uint8))]
 
 
 class TQJoinCond(C.Structure):
@@ -63,6 +64,11 @@ SYMBOLS = {
     "tq_vec_in_int": (_I32, [_I64, _COL, _I32, _I32, _COL, C.POINTER(_I32), _COL, _I32]),
     "tq_vec_lt_plus_int": (_I32, [_I64, _COL, _COL, _COL, _COL, _I32]),
     "tq_vec_filter_int": (_I32, [_I64, _COL, _P, _I32]),
+    "tq_vec_filter_real": (_I32, [_I64, _COL, _P, _I32]),
+    "tq_vec_in_real": (_I32, [_I64, _COL, _I32, _COL, _COL, _I32]),
+    "tq_vec_in_string": (_I32, [_I64, _COL, _I32, _COL, _COL, _I32]),
+    "tq_vec_if_string": (_I32, [_I64, _COL, _COL, _COL, _COL, _I32]),
+    "tq_vec_ifnull_string": (_I32, [_I64, _COL, _COL, _COL, _I32]),
     "tq_chunk_encoded_size": (_I32, [_I32, C.POINTER(_I32), _COL, C.POINTER(_I64)]),
     "tq_chunk_encode": (_I32, [_I32, C.POINTER(_I32), _COL, _P, _I64, C.POINTER(_I64)]),
     "tq_chunk_decode": (_I32, [_P, _I64, _I32, C.POINTER(_I32), _COL, C.POINTER(_I64)]),

@@ -293,6 +293,7 @@ struct FLtPlus {  // config C2: (a < b, a + b) in one pass over a and b
 struct InList {
   int n;
   bool ua;
+  bool real;   // builtinInRealSig: operands are DOUBLE, equality is types.CompareFloat64 == 0 (builtin_other_vec_generated.go:151-204)
   const uint64_t *d[MAX_IN_LIST];
   const uint32_t *bm[MAX_IN_LIST];
   bool u[MAX_IN_LIST];
@@ -317,7 +318,8 @@ __global__ void __launch_bounds__(MAP_THREADS) k_in_int(const uint64_t *a, const
         if (!ann || !tqd::bm_not_null(L.bm[j], r)) { has_null = true; continue; }
         const int64_t y = (int64_t)L.d[j][r];
         bool eq;
-        if (L.ua == L.u[j]) eq = (x == y);
+        if (L.real) eq = __longlong_as_double(x) == __longlong_as_double(y);
+        else if (L.ua == L.u[j]) eq = (x == y);
         else if (!L.ua) eq = (x >= 0 && y == x);
         else eq = (y >= 0 && y == x);
         found |= eq;
@@ -334,11 +336,17 @@ __global__ void __launch_bounds__(MAP_THREADS) k_in_int(const uint64_t *a, const
   }
 }
 
-__global__ void k_filter_int(const uint64_t *a, const uint32_t *abm, uint8_t *sel, int64_t n) {
-  // VecEvalBool + toBool (expression/expression.go:205-326): selected = !isNull && value != 0
+__global__ void k_filter_int(const uint64_t *a, const uint32_t *abm, uint8_t *sel, int64_t n, int real) {
+  // VecEvalBool + toBool (expression/expression.go:205-326): selected = !isNull && value != 0;
+  // ETReal: "zero" is types.RoundFloat(f) == 0 (types/helper.go:28-34), i.e. |f| < 0.5 — NaN rounds to NaN, which is not zero
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) sel[i] = (uint8_t)(tqd::bm_not_null(abm, i) && a[i] != 0);
+  for (; i < n; i += stride) {
+    bool nz;
+    if (real) nz = !(fabs(__longlong_as_double((long long)a[i])) < 0.5);
+    else nz = a[i] != 0;
+    sel[i] = (uint8_t)(tqd::bm_not_null(abm, i) && nz);
+  }
 }
 
 // ------------------------------------------------------------------ host driver
@@ -560,10 +568,10 @@ int32_t tq_vec_lt_plus_int(int64_t n, const tq_column *a, const tq_column *b, tq
   return err_to_status(eo.err, "(a + b)");
 }
 
-int32_t tq_vec_in_int(int64_t n, const tq_column *a, int32_t a_unsigned, int32_t n_list, const tq_column *list, const int32_t *list_unsigned,
-                      tq_column *out, int32_t mem) {
+static int32_t vec_in(int64_t n, const tq_column *a, int32_t a_unsigned, int32_t n_list, const tq_column *list, const int32_t *list_unsigned, tq_column *out,
+                      int32_t mem, bool real) {
   if (n_list < 0 || n_list > MAX_IN_LIST) { set_error("IN list of %d columns (max %d per call)", n_list, MAX_IN_LIST); return TQ_ERR_INVALID_ARG; }
-  if (n_list > 0 && (!list || !list_unsigned)) return TQ_ERR_INVALID_ARG;
+  if (n_list > 0 && (!list || (!real && !list_unsigned))) return TQ_ERR_INVALID_ARG;
   const tq_column *ins[1 + MAX_IN_LIST];
   ins[0] = a;
   for (int j = 0; j < n_list; j++) ins[1 + j] = &list[j];
@@ -571,8 +579,8 @@ int32_t tq_vec_in_int(int64_t n, const tq_column *a, int32_t a_unsigned, int32_t
   ErrOut eo;
   auto launch = [&](const uint64_t **id, const uint32_t **ib, uint64_t **od, uint32_t **ob, int64_t rows, unsigned *, unsigned long long *) {
     InList L;
-    L.n = n_list; L.ua = a_unsigned != 0;
-    for (int j = 0; j < n_list; j++) { L.d[j] = id[1 + j]; L.bm[j] = ib[1 + j]; L.u[j] = list_unsigned[j] != 0; }
+    L.n = n_list; L.ua = a_unsigned != 0; L.real = real;
+    for (int j = 0; j < n_list; j++) { L.d[j] = id[1 + j]; L.bm[j] = ib[1 + j]; L.u[j] = !real && list_unsigned[j] != 0; }
     const int64_t groups = (rows + 63) >> 6;
     int64_t blocks = (groups * 32 + MAP_THREADS - 1) / MAP_THREADS;
     const int64_t cap = (int64_t)rt().sm_count * 8;
@@ -583,7 +591,20 @@ int32_t tq_vec_in_int(int64_t n, const tq_column *a, int32_t a_unsigned, int32_t
   return run_map(n, mem, 1 + n_list, ins, 1, outs, launch, &eo);
 }
 
-int32_t tq_vec_filter_int(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem) {
+int32_t tq_vec_in_int(int64_t n, const tq_column *a, int32_t a_unsigned, int32_t n_list, const tq_column *list, const int32_t *list_unsigned,
+                      tq_column *out, int32_t mem) {
+  return vec_in(n, a, a_unsigned, n_list, list, list_unsigned, out, mem, false);
+}
+
+int32_t tq_vec_in_real(int64_t n, const tq_column *a, int32_t n_list, const tq_column *list, tq_column *out, int32_t mem) {
+  return vec_in(n, a, 0, n_list, list, nullptr, out, mem, true);
+}
+
+static int32_t vec_filter(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem, int real);
+int32_t tq_vec_filter_int(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem) { return vec_filter(n, a, selected, mem, 0); }
+int32_t tq_vec_filter_real(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem) { return vec_filter(n, a, selected, mem, 1); }
+
+static int32_t vec_filter(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem, int real) {
   TQ_TRY(ensure_init());
   if (n < 0 || !a || (n > 0 && (!a->data || !selected))) return TQ_ERR_INVALID_ARG;
   if (n == 0) return TQ_OK;
@@ -591,7 +612,7 @@ int32_t tq_vec_filter_int(int64_t n, const tq_column *a, uint8_t *selected, int3
   std::lock_guard<std::recursive_mutex> lk(r.mu);
   const int grid = (int)((n + 255) / 256 < (int64_t)r.sm_count * 8 ? (n + 255) / 256 : (int64_t)r.sm_count * 8);
   if (mem == TQ_MEM_DEVICE) {
-    k_filter_int<<<grid, 256, 0, r.compute>>>((const uint64_t *)a->data, (const uint32_t *)a->null_bitmap, selected, n);
+    k_filter_int<<<grid, 256, 0, r.compute>>>((const uint64_t *)a->data, (const uint32_t *)a->null_bitmap, selected, n, real);
     count_launch();
     TQ_TRY(check_launch("k_filter_int"));
     TQ_CUDA(cudaStreamSynchronize(r.compute));
@@ -607,7 +628,7 @@ int32_t tq_vec_filter_int(int64_t n, const tq_column *a, uint8_t *selected, int3
     TQ_CUDA(cudaMemcpyAsync(bm.p, a->null_bitmap, bitmap_bytes(n), cudaMemcpyHostToDevice, r.compute));
     dbm = bm.as<uint32_t>();
   }
-  k_filter_int<<<grid, 256, 0, r.compute>>>(d.as<uint64_t>(), dbm, sel.as<uint8_t>(), n);
+  k_filter_int<<<grid, 256, 0, r.compute>>>(d.as<uint64_t>(), dbm, sel.as<uint8_t>(), n, real);
   count_launch();
   TQ_TRY(check_launch("k_filter_int"));
   TQ_CUDA(cudaMemcpyAsync(selected, sel.p, (size_t)n, cudaMemcpyDeviceToHost, r.compute));

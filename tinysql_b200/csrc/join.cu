@@ -40,6 +40,9 @@ static int64_t g_max_load_pct = 50;                      // TQ_JOIN_MAX_LOAD_PCT
 static bool g_exact_scatter = false;                     // TQ_JOIN_EXACT_SCATTER=1: always run the probe-side histogram pass
 static bool g_no_fast_kernel = false;                    // TQ_JOIN_NO_FAST=1: use the generic kernels (tests)
 static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
+static bool g_old_fast = false;                          // TQ_JOIN_OLD_FAST=1: the round-1 PK-FK kernels instead of the streaming pipeline (A/B)
+static bool g_no_tma = false;                            // TQ_JOIN_NO_TMA=1: plain loads instead of TMA bulk copies in the AoS scatter (diagnostics)
+static int g_scatter_tile = 4096;                        // TQ_JOIN_SCATTER_TILE=2048|4096: rows per tile of the AoS scatter
 
 // key_mode: how (flag, raw bytes) equality (util/codec/codec.go:212-240,363-382) maps onto raw 8-byte equality
 //   0: flags always agree (both signed, both unsigned, or both DOUBLE)  -> raw equality
@@ -302,7 +305,9 @@ struct ProbeParams {
   const uint8_t *selected;    // outerSideFilter result or nullptr (one-table path only; the scatter applies it on the partitioned path)
   int key_col;
   int key_mode;
-  int is_outer;               // LeftOuter / RightOuter: misses emit probe row ++ NULLs (joiner.go:274-277,337-340)
+  int is_outer;               // LeftOuter / RightOuter: misses emit probe row ++ defaultInner (joiner.go:274-277,337-340)
+  uint64_t def_val[MAXC];     // defaultInner (PhysicalHashJoin.DefaultValues, joiner.go:139-143): value of build column c in a miss row
+  uint32_t def_mask;          // ... and its NOT-NULL bits (0 = the usual all-NULL inner side)
   int64_t n;
   uint64_t capacity;          // rows the output columns can hold
   unsigned long long *cursor; // [0] rows produced (may exceed capacity: then the batch is re-run), [1] matched probe rows
@@ -337,7 +342,7 @@ struct BuildRow {
 __device__ __forceinline__ BuildRow build_row_of(const ProbeParams &p, bool want, uint32_t off, bool have01 = false, uint64_t w0 = 0, uint64_t w1 = 0) {
   BuildRow b;
   b.row = nullptr;
-  b.mask = 0;
+  b.mask = p.def_mask;   // a miss row carries defaultInner
   b.have01 = have01;
   b.w0 = w0;
   b.w1 = w1;
@@ -454,7 +459,7 @@ __device__ __forceinline__ void tile_expand(const ProbeParams &p, const TileSmem
     }
     const BuildRow b = build_row_of(p, active, off == OFF_MISS ? OFF_MISS : (uint32_t)(off + j));
     for (int c = 0; c < p.n_build_cols; c++) {
-      if (active) tqd::st_stream_u64(p.out_build[c].data + q, b.row ? b.word(p.build_word[c]) : 0ull);  // miss: defaultInner = NULL (builder.go:463-465)
+      if (active) tqd::st_stream_u64(p.out_build[c].data + q, b.row ? b.word(p.build_word[c]) : p.def_val[c]);  // miss: defaultInner (builder.go:463-465)
       if (p.out_build[c].bm) {
         const unsigned word = __ballot_sync(0xffffffffu, (b.mask >> c) & 1u);
         if (lane == 0 && word) {
@@ -498,7 +503,7 @@ __device__ __forceinline__ void emit_row(const ProbeParams &p, bool emit, int64_
   }
   const BuildRow b = build_row_of(p, emit, off, have01, w0, w1);
   for (int c = 0; c < p.n_build_cols; c++) {
-    if (emit) tqd::st_stream_u64(p.out_build[c].data + q, b.row ? b.word(p.build_word[c]) : 0ull);
+    if (emit) tqd::st_stream_u64(p.out_build[c].data + q, b.row ? b.word(p.build_word[c]) : p.def_val[c]);
     if (p.out_build[c].bm) warp_set_bits(p.out_build[c].bm, emit, q, (b.mask >> c) & 1u);
   }
 }
@@ -632,7 +637,7 @@ struct ScatterParams {
   int n_parts_mod;
   uint64_t *out_bin[8][4];
 };
-__device__ __forceinline__ int scatter_bins(const ScatterParams &p) { return (p.n_parts_mod ? p.n_parts_mod : (1 << p.pbits)) + 1; }
+__host__ __device__ __forceinline__ int scatter_bins(const ScatterParams &p) { return (p.n_parts_mod ? p.n_parts_mod : (1 << p.pbits)) + 1; }
 __device__ __forceinline__ uint32_t scatter_pid(const ScatterParams &p, uint64_t key) {
   const uint64_t h = tqd::mix64(key);
   return p.n_parts_mod ? (uint32_t)((h >> 40) % (uint64_t)p.n_parts_mod) : (uint32_t)part_of_hash(h, p.pbits);
@@ -1434,6 +1439,10 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part(const ProbeParams 
   if ((tid & 31) == 0 && matched_acc) atomicAdd(p.cursor + 1, (unsigned long long)matched_acc);
 }
 
+}  // namespace tq
+#include "join_stream.cuh"
+namespace tq {
+
 // ------------------------------------------------------------------ host side
 // Pinned accumulation of ≤1024-row host chunks into one column.
 struct HostAccum {
@@ -1543,6 +1552,8 @@ struct tq_join {
   // FLOAT / var-len KEY columns (codec.go:226-233,276-333): a FLOAT key is compared as float64(f) — widened into an 8-byte
   // column; a var-len key is compared byte for byte — replaced by its id in a string dictionary built from the build side
   // (strdict.cuh).  Either makes the key "hidden" (an extra 8-byte column per side), like a multi-column key.
+  uint64_t def_val[MAXC] = {};            // defaultInner per build column (+ NOT-NULL bits); all NULL unless the descriptor says otherwise
+  uint32_t def_mask = 0;
   bool key_hidden = false;
   int bkey_kind[MK_MAX_KEYS] = {}, pkey_kind[MK_MAX_KEYS] = {};   // 0 = 8-byte column as is, 1 = FLOAT widened, 2 = var-len via dictionary
   StringDict sdict[MK_MAX_KEYS];
@@ -1605,6 +1616,9 @@ struct tq_join {
   std::vector<DevColBuf> part_cols[2];    // per cursor slot: probe columns in partition order
   DevBuf part_cnt[2], part_off[2], part_cursor[2], part_lim[2];
   bool optimistic_scatter = true;         // skip the probe-side histogram pass: fixed slabs with 25% slack (falls back on overflow)
+  // streaming PK-FK pipeline (join_stream.cuh): AoS slabs, positional output, hole filling
+  DevBuf part_aos[2], pos_base[2], pos_valid[2], hole_cnt[2], hole_pre[2], hole_pos[2], hole_src[2], hole_scan;
+  DevBuf b_aos;                           // build-side AoS slabs (released after the build)
   DevBuf scan_scratch2;
   PinBuf cursors_host;
   PendingBatch pending;
@@ -1688,6 +1702,110 @@ static int32_t key_source(tq_join *j, bool build, int i, const std::vector<DCol>
   return TQ_OK;
 }
 
+// Partition-local build (join_stream.cuh): scatter the build rows into AoS partition slabs, then one CTA per partition
+// initialises that partition's table and inserts its rows while the table sits in L2.  Covers the PK-FK shape — NOT NULL
+// build columns that fit a table entry, unique keys; anything else (*done == false) takes the general build below.
+static int32_t try_stream_build(tq_join *j, bool *done) {
+  *done = false;
+  Runtime &r = rt();
+  cudaStream_t s = r.compute;
+  const int64_t n = j->n_build;
+  const int NB = j->n_build_cols;
+  int pbits = 0;
+  while (((uint64_t)g_part_target_rows << pbits) < (uint64_t)n) pbits++;
+  if (pbits > SA_MAX_PBITS) pbits = SA_MAX_PBITS;
+  if (pbits < 1) return TQ_OK;
+  const int P = 1 << pbits;
+  const uint64_t slab = ((uint64_t)n / P + (uint64_t)n / P / 4 + 4096 + 31) & ~31ull;
+  if (slab * P > 0xFFFFFFF0ull) return TQ_OK;
+  DevBuf &off = j->part_off[0], &hi = j->part_cursor[0], &lim = j->part_lim[0];
+  TQ_TRY(off.reserve((size_t)(P + 3) * 4));
+  TQ_TRY(hi.reserve((size_t)(P + 3) * 4));
+  TQ_TRY(lim.reserve((size_t)(P + 3) * 4));
+  TQ_TRY(j->b_aos.reserve((size_t)slab * P * NB * 8 + 256));
+  unsigned long long *cur = j->cursors.as<unsigned long long>();
+  TQ_CUDA(cudaMemsetAsync(cur, 0, 64, s));
+  k_init_slabs<<<(P + 1 + 255) / 256, 256, 0, s>>>(off.as<uint32_t>(), hi.as<uint32_t>(), lim.as<uint32_t>(), P, (uint32_t)slab, 0u);
+  count_launch();
+  ScatterAosParams q{};
+  q.sp.n_cols = NB;
+  q.use_tma = g_no_tma ? 0 : 1;
+  for (int c = 0; c < NB; c++) {
+    q.sp.in[c] = j->b_view[c];
+    if ((reinterpret_cast<uintptr_t>(j->b_view[c].data) & 15) != 0) q.use_tma = 0;
+  }
+  q.sp.key_col = j->build_key;
+  q.sp.key_mode = j->key_mode;   // rows whose key can never match are dropped here (hash_table.go:161-163 skips NULL keys; none here)
+  q.sp.pbits = pbits;
+  q.sp.n = n;
+  q.sp.part_cursor = hi.as<uint32_t>();
+  q.sp.part_lim = lim.as<uint32_t>();
+  q.sp.overflow = cur + 2;
+  q.out = j->b_aos.as<uint64_t>();
+  TQ_TRY(launch_scatter_aos(q, NB, s));
+  std::vector<uint32_t> h_hi((size_t)P);
+  unsigned long long h_cur[4] = {0, 0, 0, 0};
+  TQ_CUDA(cudaMemcpyAsync(h_hi.data(), hi.p, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaMemcpyAsync(h_cur, cur, 32, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaStreamSynchronize(s));
+  if (h_cur[2]) return TQ_OK;  // a slab overflowed: skewed hash partitions
+  uint64_t max_cnt = 0, n_valid = 0;
+  for (int q2 = 0; q2 < P; q2++) {
+    const uint64_t c = h_hi[q2] - (uint64_t)q2 * slab;
+    n_valid += c;
+    if (c > max_cnt) max_cnt = c;
+  }
+  uint64_t cap = 64;
+  while (cap * (uint64_t)g_max_load_pct < max_cnt * 100) cap <<= 1;
+  if (cap * P > (uint64_t)n * 12 + 4096) return TQ_OK;
+  const uint64_t n_slots = (uint64_t)P * cap;
+  if (n_slots > 0xFFFFFFF0ull) return TQ_OK;
+  const int shift = NB > 2 ? 2 : 1;
+  TQ_TRY(j->slots.reserve(((n_slots + 1) << shift) * 8));
+  uint64_t *words = j->slots.as<uint64_t>();
+  k_init_table<<<1, 32, 0, s>>>(words + (n_slots << shift), 1, shift);  // the side entry of the empty-marker key (unused on this path)
+  BuildPartParams bp{};
+  bp.slab = j->b_aos.as<uint64_t>();
+  bp.lo = off.as<uint32_t>();
+  bp.hi = hi.as<uint32_t>();
+  bp.words = words;
+  bp.cap = cap;
+  bp.shift = shift;
+  bp.n_parts = P;
+  bp.key_col = j->build_key;
+  {
+    int w = 1;
+    for (int c = 0; c < NB; c++) {
+      j->row_word[c] = (c == j->build_key) ? 0 : w++;
+      bp.word_of_col[c] = j->row_word[c];
+    }
+    j->row_mask_word = -1;
+  }
+  bp.flags = reinterpret_cast<unsigned *>(cur + 3);
+  build_part_kernel(NB)<<<P < r.sm_count ? P : r.sm_count, BP_THREADS, 0, s>>>(bp);
+  count_launch(2);
+  TQ_TRY(check_launch("k_build_part"));
+  TQ_CUDA(cudaMemcpyAsync(h_cur, cur, 32, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaStreamSynchronize(s));
+  if (h_cur[3]) return TQ_OK;  // duplicate keys or the empty-marker key: the general build handles them
+  j->shift = shift;
+  j->pbits = pbits;
+  j->n_slots = n_slots;
+  j->n_valid = (int64_t)n_valid;
+  j->n_distinct = (int64_t)n_valid;
+  j->build_unique = true;
+  j->row_mode = true;
+  j->table.words = words;
+  j->table.mask = cap - 1;
+  j->table.pbits = pbits;
+  j->table.shift = shift;
+  j->table.row_mode = 1;
+  j->table.sent_off = (uint32_t)n_slots;
+  j->table.sent_cnt = 0;
+  *done = true;
+  return TQ_OK;
+}
+
 static int32_t join_build(tq_join *j) {
   Runtime &r = rt();
   cudaStream_t s = r.compute;
@@ -1699,6 +1817,22 @@ static int32_t join_build(tq_join *j) {
   TQ_CUDA(cudaMemsetAsync(counters, 0, 64, s));
   j->build_has_nulls = false;
   for (int c = 0; c < j->n_build_cols; c++) j->build_has_nulls |= (j->b_view[c].bm != nullptr);
+  if (n >= PART_MIN_BUILD_ROWS && !g_force_global_table && !g_no_fast_kernel && !g_old_fast && !j->build_has_nulls && j->n_build_cols <= 4 &&
+      j->key_mode != KEYMODE_NEVER) {
+    bool done = false;
+    TQ_TRY(try_stream_build(j, &done));
+    j->b_aos.release();
+    if (done) {
+      TQ_CUDA(cudaEventRecord(j->ev_b[0], s));
+      TQ_CUDA(cudaStreamSynchronize(s));
+      float ms = 0;
+      TQ_CUDA(cudaEventElapsedTime(&ms, j->ev_a[0], j->ev_b[0]));
+      j->build_ns = (int64_t)(ms * 1e6);
+      j->b_cols.clear();
+      j->b_view.clear();
+      return TQ_OK;
+    }
+  }
   // entry layout: ROW mode needs key + other columns (+ mask word) to fit 2 or 4 words
   const int row_words = j->n_build_cols + (j->build_has_nulls ? 1 : 0);
   const bool row_candidate = row_words <= 4;
@@ -1861,6 +1995,166 @@ static std::unique_ptr<ResultBatch> get_result_batch(tq_join *j) {
   return rb;
 }
 
+// Device-driven hole filling for up to HOLE_FAST_CAP holes (the foreign-key case: only the padding); more holes are left to
+// the host, which knows the exact number after the batch's row count has been read back (finalize_pending).
+static constexpr uint64_t HOLE_FAST_CAP = 1ull << 20;
+__global__ void __launch_bounds__(256) k_hole_popc_dev(const uint32_t *valid, const unsigned long long *cur, int64_t n_words_max, uint32_t *cnt) {
+  const int64_t n_words = (int64_t)(cur[3] >> 5);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w <= n_words_max; w += stride) cnt[w] = w < n_words ? __popc(valid[w]) : 0u;
+}
+__global__ void __launch_bounds__(256) k_hole_lists_dev(const uint32_t *valid, const uint32_t *vpre, unsigned long long *cur, uint32_t *hole_pos, uint32_t *tail_src) {
+  const uint64_t M = cur[0], S = cur[3];
+  if (S - M > HOLE_FAST_CAP) { if (blockIdx.x == 0 && threadIdx.x == 0) cur[4] = 1; return; }
+  const int64_t n_words = (int64_t)(S >> 5);
+  const uint32_t below = valid_rank(valid, vpre, M, n_words);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    const uint32_t bits = valid[w];
+    const uint64_t p0 = (uint64_t)w << 5;
+    if (p0 + 32 <= M && bits == 0xFFFFFFFFu) continue;
+    if (p0 >= M && bits == 0) continue;
+    const uint32_t pre = vpre[w];
+    for (int b = 0; b < 32; b++) {
+      const uint64_t pos = p0 + b;
+      const bool v = (bits >> b) & 1u;
+      const uint32_t vr = pre + __popc(bits & ((1u << b) - 1u));
+      if (pos < M && !v) hole_pos[pos - vr] = (uint32_t)pos;
+      else if (pos >= M && v) tail_src[vr - below] = (uint32_t)pos;
+    }
+  }
+}
+struct HoleMoveDevParams {
+  int n_cols;
+  uint64_t *col[8];
+  const uint32_t *hole_pos, *tail_src, *valid, *vpre;
+  const unsigned long long *cur;
+};
+__global__ void __launch_bounds__(256) k_hole_move_dev(const HoleMoveDevParams h) {
+  const uint64_t M = h.cur[0], S = h.cur[3];
+  if (S - M > HOLE_FAST_CAP) return;
+  const uint64_t H = M - valid_rank(h.valid, h.vpre, M, (int64_t)(S >> 5));
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < H; k += stride) {
+    const uint32_t d = h.hole_pos[k], sidx = h.tail_src[k];
+    for (int c = 0; c < h.n_cols; c++) h.col[c][d] = h.col[c][sidx];
+  }
+}
+
+// scatter (AoS, TMA-fed) -> partition bases -> positional probe -> device-driven hole filling
+static int32_t launch_probe_stream(tq_join *j, const ProbeParams &p, const std::vector<DCol> &probe, const uint8_t *d_selected, int64_t n,
+                                   unsigned long long *cur, int slot, uint64_t alloc_rows) {
+  cudaStream_t s = rt().compute;
+  const int P = 1 << j->pbits, NP = j->n_probe_cols, NB = j->n_build_cols;
+  const uint64_t slab = ((uint64_t)n / P + (uint64_t)n / P / 4 + 4096 + 31) & ~31ull;
+  if (slab * P > 0xFFFFFFF0ull) { set_error("probe batch too large for 32-bit partition offsets"); return TQ_ERR_INVALID_ARG; }
+  DevBuf &off = j->part_off[slot], &cur_b = j->part_cursor[slot], &lim = j->part_lim[slot];
+  TQ_TRY(off.reserve((size_t)(P + 3) * 4));
+  TQ_TRY(cur_b.reserve((size_t)(P + 3) * 4));
+  TQ_TRY(lim.reserve((size_t)(P + 3) * 4));
+  TQ_TRY(j->pos_base[slot].reserve((size_t)(P + 2) * 4));
+  TQ_TRY(j->part_aos[slot].reserve((size_t)slab * P * NP * 8 + 256));
+  const int64_t n_words_max = (int64_t)(alloc_rows >> 5) + 1;
+  TQ_TRY(j->pos_valid[slot].reserve((size_t)(n_words_max + 2) * 4));
+  TQ_TRY(j->hole_cnt[slot].reserve((size_t)(n_words_max + 2) * 4));
+  TQ_TRY(j->hole_pre[slot].reserve((size_t)(n_words_max + 2) * 4));
+  TQ_TRY(j->hole_pos[slot].reserve((size_t)(HOLE_FAST_CAP + 64) * 4));
+  TQ_TRY(j->hole_src[slot].reserve((size_t)(HOLE_FAST_CAP + 64) * 4));
+  k_init_slabs<<<(P + 1 + 255) / 256, 256, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), P, (uint32_t)slab, 0u);
+  count_launch();
+  ScatterAosParams q{};
+  q.sp.n_cols = NP;
+  q.use_tma = g_no_tma ? 0 : 1;
+  for (int c = 0; c < NP; c++) {
+    q.sp.in[c] = probe[c];
+    if ((reinterpret_cast<uintptr_t>(probe[c].data) & 15) != 0) q.use_tma = 0;
+  }
+  q.sp.selected = d_selected;
+  q.sp.key_col = j->probe_key;
+  q.sp.key_mode = j->key_mode;
+  q.sp.is_outer = 0;
+  q.sp.pbits = j->pbits;
+  q.sp.n = n;
+  q.sp.part_cursor = cur_b.as<uint32_t>();
+  q.sp.part_lim = lim.as<uint32_t>();
+  q.sp.overflow = cur + 2;
+  q.out = j->part_aos[slot].as<uint64_t>();
+  TQ_TRY(launch_scatter_aos(q, NP, s));
+  k_part_bases<<<1, 32, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), P, j->pos_base[slot].as<uint32_t>(), cur + 3);
+  count_launch();
+  ProbePosParams pp{};
+  pp.slab = j->part_aos[slot].as<uint64_t>();
+  pp.lo = off.as<uint32_t>();
+  pp.hi = cur_b.as<uint32_t>();
+  pp.lim = lim.as<uint32_t>();
+  pp.out_base = j->pos_base[slot].as<uint32_t>();
+  for (int c = 0; c < NP; c++) pp.out_probe[c] = p.out_probe[c].data;
+  for (int c = 0; c < NB; c++) { pp.out_build[c] = p.out_build[c].data; pp.build_word[c] = p.build_word[c]; }
+  pp.valid = j->pos_valid[slot].as<uint32_t>();
+  pp.cursor = cur;
+  pp.key_col = j->probe_key;
+  const int64_t tiles_per_part = (n / P + PP_TILE - 1) / PP_TILE;
+  int64_t split = tiles_per_part / g_tiles_per_cta;
+  if (split < 1) split = 1;
+  pp.split = (int)split;
+  ProbePosKernel k = probe_pos_kernel(NP, NB);
+  const int smem = PP_STAGES * PP_TILE * NP * 8;
+  static bool attr[5][5] = {};
+  if (!attr[NP][NB]) {
+    TQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr[NP][NB] = true;
+  }
+  k<<<(unsigned)(P * split), PP_THREADS, smem, s>>>(pp, j->table);
+  count_launch();
+  TQ_TRY(check_launch("k_probe_pos"));
+  // holes: padding of every partition to 32 rows + probe rows without a match
+  uint32_t *cnt = j->hole_cnt[slot].as<uint32_t>(), *pre = j->hole_pre[slot].as<uint32_t>();
+  k_hole_popc_dev<<<stream_grid(n_words_max + 1), 256, 0, s>>>(pp.valid, cur, n_words_max, cnt);
+  count_launch();
+  TQ_TRY(exclusive_scan_u32(cnt, 1, pre, 1, n_words_max + 1, nullptr, j->hole_scan, s));
+  k_hole_lists_dev<<<stream_grid(n_words_max), 256, 0, s>>>(pp.valid, pre, cur, j->hole_pos[slot].as<uint32_t>(), j->hole_src[slot].as<uint32_t>());
+  HoleMoveDevParams hm{};
+  hm.n_cols = NP + NB;
+  for (int c = 0; c < NP; c++) hm.col[c] = p.out_probe[c].data;
+  for (int c = 0; c < NB; c++) hm.col[NP + c] = p.out_build[c].data;
+  hm.hole_pos = j->hole_pos[slot].as<uint32_t>();
+  hm.tail_src = j->hole_src[slot].as<uint32_t>();
+  hm.valid = pp.valid;
+  hm.vpre = pre;
+  hm.cur = cur;
+  k_hole_move_dev<<<stream_grid((int64_t)HOLE_FAST_CAP / 4), 256, 0, s>>>(hm);
+  count_launch(2);
+  j->probe_launches += 3;
+  return check_launch("k_hole_move");
+}
+
+// more holes than the device-driven pass covers (a join with many misses): exact-size lists, after the counts are on the host
+static int32_t fill_holes_host(tq_join *j, ResultBatch *rb, int slot, uint64_t M, uint64_t S) {
+  cudaStream_t s = rt().compute;
+  const int64_t n_words = (int64_t)(S >> 5);
+  const uint64_t max_holes = S - M;
+  DevBuf hp, hs;
+  TQ_TRY(hp.reserve((size_t)(max_holes + 64) * 4));
+  TQ_TRY(hs.reserve((size_t)(max_holes + 64) * 4));
+  const uint32_t *valid = j->pos_valid[slot].as<uint32_t>(), *pre = j->hole_pre[slot].as<uint32_t>();  // the prefix counts are already there
+  k_hole_lists<<<stream_grid(n_words), 256, 0, s>>>(valid, pre, n_words, M, hp.as<uint32_t>(), hs.as<uint32_t>());
+  HoleMoveParams hm{};
+  hm.n_cols = (int)rb->cols.size();
+  if (hm.n_cols > 8) { set_error("internal: positional result with %d columns", hm.n_cols); return TQ_ERR_STATE; }
+  for (int c = 0; c < hm.n_cols; c++) hm.col[c] = rb->cols[c].data.as<uint64_t>();
+  hm.hole_pos = hp.as<uint32_t>();
+  hm.tail_src = hs.as<uint32_t>();
+  hm.valid = valid;
+  hm.vpre = pre;
+  hm.n_words = n_words;
+  hm.M = M;
+  k_hole_move<<<stream_grid((int64_t)max_holes), 256, 0, s>>>(hm);
+  count_launch(2);
+  TQ_TRY(check_launch("k_hole_move"));
+  TQ_CUDA(cudaStreamSynchronize(s));  // hp / hs go back to the allocator
+  return TQ_OK;
+}
+
 // Enqueue one probe launch for `n` rows of device columns `probe` into rb (capacity rows).
 static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const uint8_t *d_selected, int64_t n, ResultBatch *rb, uint64_t capacity,
                             int cursor_slot) {
@@ -1879,11 +2173,13 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
   p.key_col = j->probe_key;
   p.key_mode = j->key_mode;
   p.is_outer = (j->join_type != TQ_JOIN_INNER);
+  for (int c = 0; c < MAXC; c++) p.def_val[c] = j->def_val[c];
+  p.def_mask = j->def_mask;
   p.n = n;
   p.capacity = capacity;
-  unsigned long long *cur = j->cursors.as<unsigned long long>() + 4 * cursor_slot;  // [0] rows, [1] matched probe rows, [2] slab overflow
+  unsigned long long *cur = j->cursors.as<unsigned long long>() + 8 * cursor_slot;  // [0] rows, [1] matched probe rows, [2] slab overflow, [3] span of the positional result, [4] holes left to the host
   p.cursor = cur;
-  TQ_CUDA(cudaMemsetAsync(cur, 0, 32, s));
+  TQ_CUDA(cudaMemsetAsync(cur, 0, 64, s));
   {
     const int64_t n_tiles = (n + PROBE_TILE - 1) / PROBE_TILE;
     DevBuf &ts = j->tile_state[cursor_slot];
@@ -1892,9 +2188,16 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     p.tile_state = ts.as<unsigned long long>();
     p.ticket = reinterpret_cast<unsigned *>(ts.as<unsigned long long>() + n_tiles);
   }
+  // The streaming PK-FK pipeline (join_stream.cuh): unique build keys held in the table entries, inner join, no NULL bitmap
+  // on either side, optimistic slabs.  Its result is positional: room for the padding of every partition to 32 rows.
+  bool any_in_bm = false;
+  for (int c = 0; c < j->n_probe_cols; c++) any_in_bm |= (probe[c].bm != nullptr);
+  const bool pos_path = j->pbits > 0 && j->pbits <= SA_MAX_PBITS && j->row_mode && !p.is_outer && !any_in_bm && !j->build_has_nulls && !g_no_fast_kernel &&
+                        !g_old_fast && j->optimistic_scatter && !g_exact_scatter && j->n_probe_cols <= 4 && j->n_build_cols <= 4 && !j->has_oc;
+  const uint64_t alloc_rows = capacity + (pos_path ? 32ull * ((1ull << j->pbits) + 2) : 0);
   for (int c = 0; c < ncols; c++) {
-    TQ_TRY(rb->cols[c].data.reserve((size_t)(capacity ? capacity : 1) * 8));
-    TQ_TRY(rb->cols[c].bm.reserve(bitmap_alloc_bytes((int64_t)capacity)));
+    TQ_TRY(rb->cols[c].data.reserve((size_t)(alloc_rows ? alloc_rows : 1) * 8));
+    TQ_TRY(rb->cols[c].bm.reserve(bitmap_alloc_bytes((int64_t)alloc_rows)));
   }
   for (int c = 0; c < j->n_probe_cols; c++) {
     p.probe[c] = probe[c];
@@ -1925,7 +2228,9 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     p.out_build[c].bm = may_null ? o.bm.as<uint32_t>() : nullptr;
   }
   TQ_CUDA(cudaEventRecord(j->ev_a[cursor_slot], s));
-  if (j->pbits == 0) {
+  if (pos_path) {
+    TQ_TRY(launch_probe_stream(j, p, probe, d_selected, n, cur, cursor_slot, alloc_rows));
+  } else if (j->pbits == 0) {
     k_probe<<<probe_grid(n), PROBE_THREADS, 0, s>>>(p, j->table);
     count_launch();
     j->probe_launches++;
@@ -2054,7 +2359,7 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
     TQ_TRY(check_launch("k_probe_part"));
   }
   TQ_CUDA(cudaEventRecord(j->ev_b[cursor_slot], s));
-  TQ_CUDA(cudaMemcpyAsync(j->cursors_host.as<unsigned long long>() + 4 * cursor_slot, cur, 32, cudaMemcpyDeviceToHost, s));
+  TQ_CUDA(cudaMemcpyAsync(j->cursors_host.as<unsigned long long>() + 8 * cursor_slot, cur, 64, cudaMemcpyDeviceToHost, s));
   return TQ_OK;
 }
 
@@ -2116,7 +2421,7 @@ static int32_t finalize_pending(tq_join *j) {
   if (!pb.active) return TQ_OK;
   Runtime &r = rt();
   TQ_CUDA(cudaEventSynchronize(pb.ev_k));
-  unsigned long long *hc = j->cursors_host.as<unsigned long long>() + 4 * pb.cursor_slot;
+  unsigned long long *hc = j->cursors_host.as<unsigned long long>() + 8 * pb.cursor_slot;
   uint64_t produced = hc[0];
   float ms = 0;
   if (cudaEventElapsedTime(&ms, j->ev_a[pb.cursor_slot], j->ev_b[pb.cursor_slot]) == cudaSuccess) j->last_probe_ns = (int64_t)(ms * 1e6);
@@ -2128,6 +2433,7 @@ static int32_t finalize_pending(tq_join *j) {
     TQ_CUDA(cudaStreamSynchronize(r.compute));
     produced = hc[0];
   }
+  if (hc[4]) TQ_TRY(fill_holes_host(j, pb.rb.get(), pb.cursor_slot, hc[0], hc[3]));  // positional result with many misses
   if (produced > pb.rb->capacity) {
     // duplicate build keys: the first launch served as the count pass; run again with the exact size
     TQ_TRY(launch_probe(j, pb.probe, pb.d_selected, pb.n, pb.rb.get(), produced, pb.cursor_slot));
@@ -2330,6 +2636,9 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   if (d->join_type == TQ_JOIN_RIGHT_OUTER && !d->outer_is_right) { set_error("right outer join needs outer_is_right == 1"); return TQ_ERR_INVALID_ARG; }
   { const char *e = getenv("TQ_JOIN_FORCE_GLOBAL"); g_force_global_table = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_NO_FAST"); g_no_fast_kernel = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_OLD_FAST"); g_old_fast = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_NO_TMA"); g_no_tma = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_SCATTER_TILE"); g_scatter_tile = (e && atoi(e) == 2048) ? 2048 : 4096; }
   { const char *e = getenv("TQ_JOIN_EXACT_SCATTER"); g_exact_scatter = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_MAX_LOAD_PCT"); if (e && atoll(e) >= 10 && atoll(e) <= 90) g_max_load_pct = atoll(e); }
   { const char *e = getenv("TQ_JOIN_TILES_PER_CTA"); if (e && atoll(e) > 0) g_tiles_per_cta = atoll(e); }
@@ -2402,6 +2711,16 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
     const int first_user = j->outer_is_right ? j->nb_user : j->np_user, first_int = j->outer_is_right ? j->n_build_cols : j->n_probe_cols;
     for (int u = 0; u < j->nb_user + j->np_user; u++) j->out_map.push_back(u < first_user ? u : u - first_user + first_int);
   }
+  if (d->default_inner_not_null) {
+    // defaultInner of an outer join (joiner.go:139-143; set by the aggregation push-down, rule_aggregation_push_down.go:211-214)
+    if (d->join_type == TQ_JOIN_INNER) { set_error("default_inner is only meaningful for outer joins"); delete j; return TQ_ERR_INVALID_ARG; }
+    for (int c = 0; c < j->nb_user; c++) {
+      if (!d->default_inner_not_null[c]) continue;
+      if (!type_ok(j->build_types[c]) || !d->default_inner_bits) { set_error("default_inner: non-NULL defaults are supported for the 8-byte column types"); delete j; return TQ_ERR_UNSUPPORTED_TYPE; }
+      j->def_val[c] = d->default_inner_bits[c];
+      j->def_mask |= 1u << c;
+    }
+  }
   if (d->probe_batch_rows > 0) j->batch_rows = (d->probe_batch_rows + 63) & ~63ll;
   j->b_host.resize(j->nb_user);
   j->p_host.resize(j->np_user);
@@ -2411,8 +2730,8 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
     if (e == cudaSuccess) e = cudaEventCreate(&j->ev_b[i]);
   }
   if (e != cudaSuccess) { delete j; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
-  int32_t st = j->cursors.reserve(64);
-  if (st == TQ_OK) st = j->cursors_host.reserve(64);
+  int32_t st = j->cursors.reserve(128);
+  if (st == TQ_OK) st = j->cursors_host.reserve(128);
   if (st != TQ_OK) { delete j; return st; }
   *out = j;
   return TQ_OK;
@@ -2469,6 +2788,8 @@ int32_t tq_join_set_other_conditions(tq_join *j, int32_t n_conds, const tq_join_
   j->oc.rowid_col = outer ? pbase + j->p_hidden_rowid : -1;
   j->oc.build_lo = bbase;
   j->oc.build_hi = bbase + j->n_build_cols;
+  for (int c = 0; c < j->n_build_cols; c++) j->oc.def_val[c] = j->def_val[c];
+  j->oc.def_mask = j->def_mask;
   for (int k = 0; k < n_conds; k++) {
     OcCond &d = j->oc.c[k];
     d.op = conds[k].op;

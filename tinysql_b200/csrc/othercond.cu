@@ -91,7 +91,14 @@ __global__ void __launch_bounds__(256) k_oc_compact(const OcPlan pl, const OcCol
     const bool to_miss = flag[i] == 3;
     for (int col = 0; col < c.n; col++) {
       const bool build_side = col >= pl.build_lo && col < pl.build_hi;
-      const bool nn = (to_miss && build_side) ? false : tqd::bm_not_null(c.bm[col], i);
+      if (to_miss && build_side) {   // onMissMatch: the inner side becomes defaultInner
+        const int bc = col - pl.build_lo;
+        const bool dn = (pl.def_mask >> bc) & 1u;
+        c.out_data[col][d] = dn ? pl.def_val[bc] : 0ull;
+        if (dn) atomicOr(&c.out_bm[col][d >> 5], 1u << (d & 31));
+        continue;
+      }
+      const bool nn = tqd::bm_not_null(c.bm[col], i);
       c.out_data[col][d] = nn ? c.data[col][i] : 0ull;
       if (nn) atomicOr(&c.out_bm[col][d >> 5], 1u << (d & 31));
     }

@@ -28,6 +28,8 @@ struct OcPlan {
   int build_key_col = -1;  // result column of the build-side key: NOT NULL <=> the row is a key match
   int rowid_col = -1;      // outer joins: result column holding the probe row id within the batch
   int build_lo = 0, build_hi = 0;  // result columns [build_lo, build_hi) belong to the build (inner) side
+  uint64_t def_val[16] = {};       // defaultInner: what the inner side of a miss row holds (joiner.go:139-143)
+  uint32_t def_mask = 0;
 };
 
 struct OcCols {

@@ -46,7 +46,7 @@ class HashJoinExec:
     """executor/join.go:31-146.  inner = build side, outer = probe side; output = left ++ right."""
 
     def __init__(self, outer_exec, inner_exec, outer_keys, inner_keys, join_type=INNER_JOIN, outer_is_right=False,
-                 outer_filter=None, probe_batch_rows=0, max_chunk_size=MAX_CHUNK_SIZE, stable_input=False, other_conditions=()):
+                 outer_filter=None, probe_batch_rows=0, max_chunk_size=MAX_CHUNK_SIZE, stable_input=False, other_conditions=(), default_inner=None):
         self.outer, self.inner = outer_exec, inner_exec
         self.outer_keys, self.inner_keys = list(outer_keys), list(inner_keys)
         self.join_type, self.outer_is_right = join_type, outer_is_right
@@ -56,6 +56,8 @@ class HashJoinExec:
         # OtherConditions (joiner.go:155-167) as (op, lhs_col, rhs_col) or (op, lhs_col, None, const_type, const_value) over
         # the output row lhs ++ rhs — EXPERIMENTAL device path (tq_join_set_other_conditions)
         self.other_conditions = list(other_conditions)
+        # PhysicalHashJoin.DefaultValues (builder.go:449-465): per inner column the value a miss row of an outer join carries (None = NULL)
+        self.default_inner = default_inner
         self.max_chunk_size = max_chunk_size
         self.handle = None
         self.prepared = False
@@ -71,6 +73,12 @@ class HashJoinExec:
         bk, pk = _i32arr(self.inner_keys), _i32arr(self.outer_keys)
         d = L.TQJoinDesc(self.join_type, 1 if self.outer_is_right else 0, len(self.inner.types), bt, len(self.outer.types), pt,
                          len(self.inner_keys), bk, pk, self.probe_batch_rows, L.TQ_JOIN_STABLE_INPUT if self.stable_input else 0)
+        if self.default_inner is not None:
+            np_t = {INT64: np.int64, UINT64: np.uint64, FLOAT64: np.float64}
+            bits = [0 if v is None else int(np.array([v], dtype=np_t[t]).view(np.uint64)[0]) for v, t in zip(self.default_inner, self.inner.types)]
+            self._dbits = (C.c_uint64 * len(bits))(*bits)
+            self._dnn = (C.c_uint8 * len(bits))(*[0 if v is None else 1 for v in self.default_inner])
+            d.default_inner_bits, d.default_inner_not_null = self._dbits, self._dnn
         h = C.c_void_p()
         L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
         self.handle = h

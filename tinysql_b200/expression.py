@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .chunk import Column, FLOAT64, INT64, UINT64, tq_array
+from .chunk import BYTES, Column, FLOAT64, INT64, UINT64, VarColumn, tq_array
 
 LT, LE, GT, GE, EQ, NE = range(6)
 PLUS, MINUS, MUL, DIV = range(4)
@@ -129,3 +129,46 @@ def vectorized_filter(a):
     ta = a.tq()
     L.check(L.load().tq_vec_filter_int(a.length, C.byref(ta), sel.ctypes.data, L.TQ_MEM_HOST))
     return sel[: a.length]
+
+
+def vectorized_filter_real(a):
+    """VecEvalBool / toBool for an ETReal expression (expression/expression.go:296-307): zero iff RoundFloat(f) == 0."""
+    sel = np.zeros(max(a.length, 1), dtype=np.uint8)
+    ta = a.tq()
+    L.check(L.load().tq_vec_filter_real(a.length, C.byref(ta), sel.ctypes.data, L.TQ_MEM_HOST))
+    return sel[: a.length]
+
+
+def vec_in_real(a, lst):
+    """builtinInRealSig — expression/builtin_other_vec_generated.go:151-204"""
+    out = Column.empty(INT64, a.length)
+    ta, to = a.tq(), out.tq()
+    L.check(L.load().tq_vec_in_real(a.length, C.byref(ta), len(lst), tq_array(lst), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def vec_in_string(a, lst):
+    """builtinInStringSig — expression/builtin_other_vec_generated.go:97-149"""
+    out = Column.empty(INT64, a.length)
+    ta, to = a.tq(), out.tq()
+    L.check(L.load().tq_vec_in_string(a.length, C.byref(ta), len(lst), tq_array(lst), C.byref(to), L.TQ_MEM_HOST))
+    return out
+
+
+def _pick_string(fn, n, cap, *args):
+    out = VarColumn.empty(BYTES, n, cap)
+    to = out.tq()
+    L.check(fn(n, *args, C.byref(to), L.TQ_MEM_HOST))
+    return out.head(n)
+
+
+def vec_if_string(cond, a, b):
+    """builtinIfStringSig.vecEvalString — expression/builtin_control_vec_generated.go:209-262"""
+    tc, ta, tb = cond.tq(), a.tq(), b.tq()
+    return _pick_string(L.load().tq_vec_if_string, a.length, int(a.data.size + b.data.size), C.byref(tc), C.byref(ta), C.byref(tb))
+
+
+def vec_ifnull_string(a, b):
+    """builtinIfNullStringSig.vecEvalString — expression/builtin_control_vec_generated.go:81-112"""
+    ta, tb = a.tq(), b.tq()
+    return _pick_string(L.load().tq_vec_ifnull_string, a.length, int(a.data.size + b.data.size), C.byref(ta), C.byref(tb))
