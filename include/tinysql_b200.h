@@ -260,6 +260,12 @@ int32_t tq_join_finalize_build(tq_join *j);
 /* selected: outerSideFilter result (join.go:328), n bytes of 0/1 in HOST memory, or NULL = all selected. */
 int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *selected, int32_t mem);
 int32_t tq_join_probe_eof(tq_join *j);
+/* Multi-GPU variant of put_probe: the batch is the concatenation of n_segs DEVICE regions (one per source rank, filled by the
+ * peers' tq_partition_push_regions kernels).  cols[g * n_probe_cols + c] = column c of region g (NOT NULL 8-byte columns,
+ * `length` ignored); *seg_counts[g] = the rows region g holds — a DEVICE value, read by the kernels, never by the host, so no
+ * host synchronisation sits between the exchange and the join; seg_cap = rows a region can hold.  Inner PK-FK joins on the
+ * streaming path only (TQ_ERR_UNSUPPORTED_TYPE otherwise: read the counts and use tq_join_put_probe per region). */
+int32_t tq_join_put_probe_segments(tq_join *j, int32_t n_segs, const tq_column *cols, const uint64_t *const *seg_counts, int64_t seg_cap);
 /* Fills at most max_rows joined rows into out_cols (n_build_cols + n_probe_cols caller-
  * allocated columns, host memory).  *n_rows == 0 with *eof == 0 means "feed more probe
  * chunks"; *n_rows == 0 with *eof != 0 is the reference's end of stream. */
@@ -374,6 +380,19 @@ int32_t tq_partition_push_device(int32_t n_cols, const tq_column *cols, int32_t 
 int32_t tq_partition_push_device_async(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts,
                                        void *const *dest_data, const int64_t *dest_row_offsets);
 int32_t tq_partition_push_wait(void);
+/* Push into per-source REGIONS (no count exchange before the push): destination q reserves `region_cap` rows per source rank and
+ * column; dest_data[q * n_cols + c] = the start of THIS rank's region for column c on rank q (local or PEER pointer),
+ * dest_counts[q] = where to publish (as one u64, ~0 = region overflow) how many rows this rank wrote there.  Enqueued on the
+ * library's push stream; tq_partition_push_sync(slot) waits for that push (slots 0..15 may be in flight together).  The
+ * receiver joins its regions with tq_join_put_probe_segments after a cross-rank barrier. */
+int32_t tq_partition_push_regions(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts, void *const *dest_data,
+                                  void *const *dest_counts, int64_t region_cap, int32_t slot, uint64_t epoch);
+int32_t tq_partition_push_sync(int32_t slot);
+/* dest_counts[q] points at a 16-byte slot {u64 rows, u64 epoch}: the count is published first, the epoch after a system-scope
+ * fence.  tq_region_wait enqueues, on the compute stream, a kernel that waits (bounded) until the n_sources consecutive slots at
+ * `slots` (this rank's own table) carry `epoch` — the device-side barrier between the peers' pushes and the kernels that read
+ * the regions; no host synchronisation, no NCCL call on the data path. */
+int32_t tq_region_wait(const void *slots, int32_t n_sources, uint64_t epoch);
 
 #ifdef __cplusplus
 }

@@ -33,17 +33,15 @@ def main():
     def local_join(b, p):
         return D.gpu_local_join(lib, L, b, p, keep_result=True)
     rows, st, res = D.distributed_join([t(bk), t(bv)], [t(pk), t(pv)], world, rank, part, local_join)
-    # the fused push path (scatter straight into the peers' receive buffers) must give the same rows
-    px = D.PushExchange(lib, L, world, rank, dev, [2, 2], [int(nb * 1.5) + 65536, int(npr * 1.5) + 65536])
-    tb, tp = [t(bk), t(bv)], [t(pk), t(pv)]
-    offs, arriving = px.plan(px.counts([tb[0], tp[0]]))
-    px.push(0, tb, offs[0])
-    px.push(1, tp, offs[1])
-    dist.barrier()
-    rows2, _, res2 = D.gpu_local_join(lib, L, [x[: arriving[0]] for x in px.recv[0]], [x[: arriving[1]] for x in px.recv[1]], keep_result=True)
-    out2 = np.stack([c.values for c in res2], axis=1) if rows2 else np.zeros((0, 4), np.int64)
-    srt = lambda m: m[np.lexsort(m.T[::-1])]
-    assert rows2 == rows and np.array_equal(srt(out2), srt(np.stack([c.values for c in res], axis=1))), "push exchange differs from NCCL exchange"
+    # the region exchange (fused scatter + NVLink push, device-side flags, segmented local join) must give the same rows;
+    # two steps: the second reuses the regions under a new epoch
+    rj = D.RegionJoin(lib, L, world, rank, 400000 + 1000 * (world - 1), 1500000 + 777 * (world - 1), n_chunks=3)
+    for _ in range(2):
+        rows2, _, res2 = rj.step(t(bk), t(bv), t(pk), t(pv), keep_result=True)
+        out2 = np.stack(res2, axis=1) if rows2 else np.zeros((0, 4), np.int64)
+        srt = lambda m: m[np.lexsort(m.T[::-1])]
+        assert rows2 == rows and np.array_equal(srt(out2), srt(np.stack([c.values for c in res], axis=1))), "region exchange differs from the NCCL exchange"
+    rj.close()
     out = np.stack([c.values for c in res], axis=1) if rows else np.zeros((0, 4), np.int64)
     if rows:
         assert np.all(D.dest_rank_np(out[:, 0], world) == rank), "a key landed on the wrong rank"

@@ -736,3 +736,27 @@ def test_join_stream_pipeline_device_columns_unaligned(lib):
         assert np.array_equal(np.sort(cols[3]), np.arange(npr)) and np.array_equal(cols[2], pk[cols[3]])
         for c in d_b + d_p:
             c.free()
+
+
+@pytest.mark.parametrize("n,ndv,est", [(3, 2, 0), (200000, 50000, 60000), (700000, 300000, 1)])
+def test_agg_fast_update_path(lib, n, ndv, est):
+    """k_agg_update_fast: NOT NULL integer GROUP BY column, COUNT(*) + COUNT(col) + SUM(double NOT NULL) x 2 + FIRSTROW(key); with table
+    growth (est far too small: deferred rows are replayed by the generic kernel into the same table) and the empty-marker key"""
+    rng = np.random.default_rng(n)
+    kv = rng.integers(-ndv // 2, ndv // 2 + 1, n)
+    kv[0] = np.int64(np.uint64(0xA5C3F00DDEADBEEF).astype(np.int64))
+    k = Column(UINT64 if n == 3 else INT64, kv)
+    x = Column(FLOAT64, np.floor(rng.random(n) * 4096) / 16)   # dyadic values: float sums exact in any order
+    y = Column(FLOAT64, np.floor(rng.random(n) * 1024) / 4)
+    tp = [k.tp, FLOAT64, FLOAT64]
+    funcs = [(AGG_SUM, 1), (AGG_COUNT, -1), (AGG_FIRSTROW, 0), (AGG_SUM, 2), (AGG_COUNT, 2)]
+    src = MockDataSource(tp, [k, x, y], 1 << 16)
+    e = HashAggExec(src, [0], funcs, est, not_null_cols=(0, 1, 2))
+    e.Open()
+    got = e.drain()
+    e.Close()
+    rc, want = O.hash_agg(tp, [k, x, y], [0], funcs, 2)
+    assert rc == 0
+    g, w = _sorted_by_key(got, 2), _sorted_by_key(want, 2)
+    for a, b in zip(g, w):
+        assert_col_equal(a, b)

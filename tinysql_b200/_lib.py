@@ -76,6 +76,7 @@ SYMBOLS = {
     "tq_join_set_other_conditions": (_I32, [_P, _I32, C.POINTER(TQJoinCond)]),
     "tq_join_put_build": (_I32, [_P, _COL, _I32]), "tq_join_finalize_build": (_I32, [_P]),
     "tq_join_put_probe": (_I32, [_P, _COL, _P, _I32]), "tq_join_probe_eof": (_I32, [_P]),
+    "tq_join_put_probe_segments": (_I32, [_P, _I32, _COL, C.POINTER(_P), _I64]),
     "tq_join_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
     "tq_join_next_device": (_I32, [_P, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
     "tq_join_next_bytes": (_I32, [_P, _I64, C.POINTER(_I64)]),
@@ -97,6 +98,9 @@ SYMBOLS = {
     "tq_partition_push_device": (_I32, [_I32, _COL, _I32, _I64, _I32, C.POINTER(_P), C.POINTER(_I64)]),
     "tq_partition_push_device_async": (_I32, [_I32, _COL, _I32, _I64, _I32, C.POINTER(_P), C.POINTER(_I64)]),
     "tq_partition_push_wait": (_I32, []),
+    "tq_partition_push_regions": (_I32, [_I32, _COL, _I32, _I64, _I32, C.POINTER(_P), C.POINTER(_P), _I64, _I32, C.c_uint64]),
+    "tq_region_wait": (_I32, [_P, _I32, C.c_uint64]),
+    "tq_partition_push_sync": (_I32, [_I32]),
 }
 
 # status codes (include/tinysql_b200.h)

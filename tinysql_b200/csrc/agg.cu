@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) k_agg_update(const AggParams p) {
           if (p.side_used[1] == 0) p.side_used[1] = 1;
         } else {
           // ---- getPartialResult (aggregate.go:396-410): find or claim the group's slot, bucket by bucket
-          uint64_t b = (tqd::mix64(key) & p.mask) & ~3ull;
+          uint64_t b = (tqd::hash_key(key) & p.mask) & ~3ull;
           bool defer = false, found = false;
           for (uint64_t buckets = 0; !found && !defer; buckets++) {
             if (buckets * 4 > p.mask) { defer = true; break; }  // table full (cannot happen below `limit`)
@@ -259,6 +259,87 @@ __global__ void __launch_bounds__(256) k_agg_update(const AggParams p) {
       }
     }
     agg_apply(p, slot, r);
+  }
+}
+
+// ---- fast path of the common analytic shape: ONE integer GROUP BY column without NULLs, aggregates drawn from
+// COUNT(*) / COUNT(not-null col) / SUM(double NOT NULL col) / FIRSTROW(key).  Same table, same state layout as k_agg_update (the
+// collect / merge / rehash kernels do not care which kernel filled it), but: four rows per thread with their key and bucket
+// loads issued back to back (the generic kernel handled one row per thread per iteration — a dependent DRAM + L2 round
+// trip each), the one-multiply table hash, no per-row walk over a function descriptor table, no NULL bookkeeping.
+static constexpr int AF_ROWS = 4;
+struct AggFastParams {
+  const uint64_t *key;
+  int n_sum, n_cnt;
+  const uint64_t *sum_arg[4];
+  int sum_w[4], cnt_w[4];
+  uint64_t *keys, *tbl;
+  int stride;
+  uint64_t mask, n_slots;
+  uint32_t *side_used;
+  unsigned long long *n_used;
+  uint64_t limit;
+  uint32_t *deferred;
+  unsigned *n_deferred;
+  int64_t n;
+};
+__global__ void __launch_bounds__(256) k_agg_update_fast(const AggFastParams p) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < p.n; base += stride * AF_ROWS) {
+    uint64_t key[AF_ROWS];
+    uint64_t b[AF_ROWS];
+    bool live[AF_ROWS];
+#pragma unroll
+    for (int k = 0; k < AF_ROWS; k++) {  // rows base, base + stride, ...: every load of the warp is coalesced
+      const int64_t r = base + k * stride;
+      live[k] = r < p.n;
+      key[k] = live[k] ? tqd::ld_stream_u64(p.key + r) : 0;
+      b[k] = (tqd::hash_key(key[k]) & p.mask) & ~3ull;
+    }
+    unsigned long long kk[AF_ROWS][4];
+#pragma unroll
+    for (int k = 0; k < AF_ROWS; k++)
+      if (live[k] && key[k] != AGG_EMPTY) {  // one sector = four candidate slots; keys never change once written, so a cached copy is safe
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(p.keys + b[k]);
+        const ulonglong2 y = *reinterpret_cast<const ulonglong2 *>(p.keys + b[k] + 2);
+        kk[k][0] = x.x; kk[k][1] = x.y; kk[k][2] = y.x; kk[k][3] = y.y;
+      }
+#pragma unroll
+    for (int k = 0; k < AF_ROWS; k++) {
+      if (!live[k]) continue;
+      const int64_t r = base + k * stride;
+      uint64_t slot = ~0ull;
+      if (key[k] == AGG_EMPTY) {
+        slot = p.n_slots + 1;
+        if (p.side_used[1] == 0) p.side_used[1] = 1;
+      } else {
+        uint64_t bb = b[k];
+        bool defer = false;
+        for (uint64_t buckets = 0; slot == ~0ull && !defer; buckets++) {
+          if (buckets * 4 > p.mask) { defer = true; break; }
+          if (buckets) {  // rare: the home bucket was full of other keys
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(kk[k][0]), "=l"(kk[k][1]) : "l"(p.keys + bb));
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(kk[k][2]), "=l"(kk[k][3]) : "l"(p.keys + bb + 2));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (slot != ~0ull || defer) break;
+            if (kk[k][j] == key[k]) { slot = bb + j; break; }
+            if (kk[k][j] == AGG_EMPTY) {
+              if (*reinterpret_cast<volatile unsigned long long *>(p.n_used) >= p.limit) { defer = true; break; }
+              const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&p.keys[bb + j]), (unsigned long long)AGG_EMPTY, (unsigned long long)key[k]);
+              if (prev == AGG_EMPTY) { atomicAdd(p.n_used, 1ull); slot = bb + j; break; }
+              if (prev == key[k]) { slot = bb + j; break; }
+            }
+          }
+          bb = (bb + 4) & p.mask;
+        }
+        if (defer) { p.deferred[atomicAdd(p.n_deferred, 1u)] = (uint32_t)r; continue; }
+      }
+      uint64_t *sl = p.tbl + slot * p.stride;
+      for (int f = 0; f < p.n_sum; f++) atomicAdd(reinterpret_cast<double *>(sl + p.sum_w[f]), __longlong_as_double((long long)tqd::ld_stream_u64(p.sum_arg[f] + r)));
+      for (int f = 0; f < p.n_cnt; f++) atomicAdd(reinterpret_cast<unsigned long long *>(sl + p.cnt_w[f]), 1ull);
+    }
   }
 }
 
@@ -418,7 +499,7 @@ __global__ void __launch_bounds__(256) k_agg_rehash(const uint64_t *old_keys, co
     else {
       const uint64_t key = old_keys[i];
       if (key == AGG_EMPTY) continue;
-      uint64_t idx = (tqd::mix64(key) & new_mask) & ~3ull;  // same bucket-aligned probe order as the update kernel
+      uint64_t idx = (tqd::hash_key(key) & new_mask) & ~3ull;  // same bucket-aligned probe order as the update kernels
       for (;;) {
         const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&new_keys[idx]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
         if (prev == AGG_EMPTY) break;
@@ -841,7 +922,31 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
     p.row_list = row_list;
     p.n = todo;
     TQ_CUDA(cudaMemsetAsync(meta32 + 2, 0, 4, s));
-    k_agg_update<<<agg_grid(todo), 256, 0, s>>>(p);
+    // ---- fast path (first pass over a raw batch): one NOT NULL integer GROUP BY column; COUNT / SUM(double, declared NOT NULL) /
+    // FIRSTROW(key) only
+    bool fast = !merge && !row_list && a->n_group_by == 1 && p.key_col >= 0 && cols[p.key_col].bm == nullptr && a->types[a->key_col] != TQ_TYPE_FLOAT64 &&
+                a->in_kind[a->key_col] == 0;
+    AggFastParams fp{};
+    for (int i = 0; fast && i < a->n_funcs_all; i++) {
+      const AggFuncDev &f = p.f[i];
+      if (f.key_passthrough) continue;
+      const bool arg_plain = f.arg_col < 0 || cols[f.arg_col].bm == nullptr;
+      if (f.func == TQ_AGG_COUNT && arg_plain && fp.n_cnt < 4) fp.cnt_w[fp.n_cnt++] = f.w0;
+      else if (f.func == TQ_AGG_SUM && f.arg_col >= 0 && f.arg_type == TQ_TYPE_FLOAT64 && f.w1 < 0 && arg_plain && fp.n_sum < 4) {
+        fp.sum_arg[fp.n_sum] = cols[f.arg_col].data;
+        fp.sum_w[fp.n_sum++] = f.w0;
+      } else fast = false;
+    }
+    if (fast) {
+      fp.key = cols[p.key_col].data;
+      fp.keys = p.keys; fp.tbl = p.tbl; fp.stride = p.stride; fp.mask = p.mask; fp.n_slots = p.n_slots; fp.side_used = p.side_used;
+      fp.n_used = p.n_used; fp.limit = p.limit; fp.deferred = p.deferred; fp.n_deferred = p.n_deferred; fp.n = todo;
+      const int64_t blocks = (todo + 256 * AF_ROWS - 1) / (256 * AF_ROWS);
+      const int64_t cap = (int64_t)r.sm_count * 8;
+      k_agg_update_fast<<<(int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap), 256, 0, s>>>(fp);
+    } else {
+      k_agg_update<<<agg_grid(todo), 256, 0, s>>>(p);
+    }
     count_launch();
     a->launches++;
     TQ_TRY(check_launch("k_agg_update"));

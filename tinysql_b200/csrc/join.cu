@@ -41,8 +41,10 @@ static bool g_exact_scatter = false;                     // TQ_JOIN_EXACT_SCATTE
 static bool g_no_fast_kernel = false;                    // TQ_JOIN_NO_FAST=1: use the generic kernels (tests)
 static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
 static bool g_old_fast = false;                          // TQ_JOIN_OLD_FAST=1: the round-1 PK-FK kernels instead of the streaming pipeline (A/B)
+static bool g_debug_sums = false;                        // TQ_JOIN_DEBUG_SUMS=1: print per-stage row counts / column checksums of the streaming pipeline (diagnostics)
+static int g_pp_variant = 0;                             // TQ_JOIN_PP_VARIANT=0..5: probe kernel shape (rows per lane / warps / CTAs per SM), A/B measurements
 static bool g_no_tma = false;                            // TQ_JOIN_NO_TMA=1: plain loads instead of TMA bulk copies in the AoS scatter (diagnostics)
-static int g_scatter_tile = 4096;                        // TQ_JOIN_SCATTER_TILE=2048|4096: rows per tile of the AoS scatter
+static int g_scatter_tile = 2048;                        // TQ_JOIN_SCATTER_TILE=1024|2048|4096: rows per tile of the AoS scatter
 
 // key_mode: how (flag, raw bytes) equality (util/codec/codec.go:212-240,363-382) maps onto raw 8-byte equality
 //   0: flags always agree (both signed, both unsigned, or both DOUBLE)  -> raw equality
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256) k_build_insert(const InsertParams b) {
       if (b.write_rows && prior == 0) write_row_words(b, b.words + ((uint64_t)b.sent_entry << b.shift), i, true);
       continue;
     }
-    const uint64_t h = tqd::mix64(key);
+    const uint64_t h = tqd::hash_key(key);
     const uint64_t base = part_of_hash(h, b.pbits) * (b.mask + 1);
     uint64_t loc = (b.shift == 1) ? ((h & b.mask) & ~1ull) : (h & b.mask);  // 16-byte entries: start on a 32-byte sector boundary (probes read entry PAIRS)
     my_valid++;
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(256) k_build_part_hist(const uint64_t *keys, c
   for (; i < n; i += stride) {
     const uint64_t key = keys[i];
     if (!key_valid(key, tqd::bm_not_null(bm, i), key_mode) || key == EMPTY_KEY) continue;
-    atomicAdd(&s_hist[part_of_hash(tqd::mix64(key), pbits)], 1u);
+    atomicAdd(&s_hist[part_of_hash(tqd::hash_key(key), pbits)], 1u);
   }
   __syncthreads();
   for (int b = threadIdx.x; b < n_bins; b += blockDim.x)
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeParams p, co
         const bool sel = p.selected ? (p.selected[r] != 0) : true;          // join.go:344 `!selected[i] || hasNull[i]` -> miss
         valid[k] = sel && key_valid(key[k], tqd::bm_not_null(kbm, r), p.key_mode);
       }
-      const uint64_t h = tqd::mix64(key[k]);
+      const uint64_t h = tqd::hash_key(key[k]);
       ebase[k] = part_of_hash(h, t.pbits) * (t.mask + 1);
       loc[k] = home_loc(h, t.mask, t.shift);
     }
@@ -639,8 +641,8 @@ struct ScatterParams {
 };
 __host__ __device__ __forceinline__ int scatter_bins(const ScatterParams &p) { return (p.n_parts_mod ? p.n_parts_mod : (1 << p.pbits)) + 1; }
 __device__ __forceinline__ uint32_t scatter_pid(const ScatterParams &p, uint64_t key) {
-  const uint64_t h = tqd::mix64(key);
-  return p.n_parts_mod ? (uint32_t)((h >> 40) % (uint64_t)p.n_parts_mod) : (uint32_t)part_of_hash(h, p.pbits);
+  // multi-GPU destination rank: (mix64 >> 40) % world (dist.py mirrors it in numpy); table partition: top bits of the table hash
+  return p.n_parts_mod ? (uint32_t)((tqd::mix64(key) >> 40) % (uint64_t)p.n_parts_mod) : (uint32_t)part_of_hash(tqd::hash_key(key), p.pbits);
 }
 
 __device__ __forceinline__ uint32_t probe_pid(const ScatterParams &p, int64_t r, uint64_t key) {
@@ -1139,7 +1141,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part_uniq(const ProbePa
     ulonglong2 first[R];
 #pragma unroll
     for (int k = 0; k < R; k++) {  // independent entry loads issued back to back
-      loc[k] = home_loc(tqd::mix64(key[k]), t.mask, t.shift);
+      loc[k] = home_loc(tqd::hash_key(key[k]), t.mask, t.shift);
       first[k] = make_ulonglong2(EMPTY_KEY, 0);
       if (inb[k] && cx.has_table && key[k] != EMPTY_KEY) first[k] = ld_entry(cx.tbl, loc[k], t.shift);
     }
@@ -1255,7 +1257,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const Prob
       EntryPair pr[R];
 #pragma unroll
       for (int k = 0; k < R; k++) {  // R independent sector loads in flight
-        loc[k] = home_loc(tqd::mix64(key[k]), mask, 1);
+        loc[k] = home_loc(tqd::hash_key(key[k]), mask, 1);
         pr[k].a = make_ulonglong2(EMPTY_KEY, 0);
         pr[k].b = pr[k].a;
         if (key[k] != EMPTY_KEY) pr[k] = ld_pair(cx.tbl, loc[k], smem);
@@ -1289,7 +1291,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 4) k_probe_part_fast(const Prob
     } else {
 #pragma unroll
       for (int k = 0; k < R; k++) {
-        loc[k] = home_loc(tqd::mix64(key[k]), mask, shift);
+        loc[k] = home_loc(tqd::hash_key(key[k]), mask, shift);
         ent[k] = make_ulonglong2(EMPTY_KEY, 0);
         if (key[k] != EMPTY_KEY) ent[k] = ld_entry(cx.tbl, loc[k], shift);
       }
@@ -1408,7 +1410,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part(const ProbeParams 
 #pragma unroll
     for (int k = 0; k < PROBE_ROWS_PER_THREAD; k++) {
       const int64_t r = tile_base + k * PROBE_THREADS + tid;
-      loc[k] = home_loc(tqd::mix64(key[k]), t.mask, t.shift);
+      loc[k] = home_loc(tqd::hash_key(key[k]), t.mask, t.shift);
       first[k] = make_ulonglong2(EMPTY_KEY, 0);
       if (r < cx.p_hi && cx.has_table && key[k] != EMPTY_KEY) first[k] = ld_entry(cx.tbl, loc[k], t.shift);
     }
@@ -1526,6 +1528,7 @@ struct PendingBatch {  // a launched probe batch whose row count has not been re
   const uint8_t *d_selected = nullptr;
   int64_t n = 0;
   bool want_host = false;
+  bool segmented = false;
   int cursor_slot = 0;
   cudaEvent_t ev_k = nullptr;
 };
@@ -1617,8 +1620,10 @@ struct tq_join {
   DevBuf part_cnt[2], part_off[2], part_cursor[2], part_lim[2];
   bool optimistic_scatter = true;         // skip the probe-side histogram pass: fixed slabs with 25% slack (falls back on overflow)
   // streaming PK-FK pipeline (join_stream.cuh): AoS slabs, positional output, hole filling
-  DevBuf part_aos[2], pos_base[2], pos_valid[2], hole_cnt[2], hole_pre[2], hole_pos[2], hole_src[2], hole_scan;
+  DevBuf part_aos[2], pos_base[2], pos_valid[2], hole_pos[2], hole_src[2], hole_scan;
   DevBuf b_aos;                           // build-side AoS slabs (released after the build)
+  // segmented probe batch (tq_join_put_probe_segments): consumed by the next launch_probe_stream
+  struct SegSpec { int n = 0; int64_t cap = 0; const uint64_t *col[SA_MAX_SEGS][4]; const unsigned long long *cnt[SA_MAX_SEGS]; } seg;
   DevBuf scan_scratch2;
   PinBuf cursors_host;
   PendingBatch pending;
@@ -1995,50 +2000,91 @@ static std::unique_ptr<ResultBatch> get_result_batch(tq_join *j) {
   return rb;
 }
 
-// Device-driven hole filling for up to HOLE_FAST_CAP holes (the foreign-key case: only the padding); more holes are left to
-// the host, which knows the exact number after the batch's row count has been read back (finalize_pending).
-static constexpr uint64_t HOLE_FAST_CAP = 1ull << 20;
-__global__ void __launch_bounds__(256) k_hole_popc_dev(const uint32_t *valid, const unsigned long long *cur, int64_t n_words_max, uint32_t *cnt) {
-  const int64_t n_words = (int64_t)(cur[3] >> 5);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w <= n_words_max; w += stride) cnt[w] = w < n_words ? __popc(valid[w]) : 0u;
-}
-__global__ void __launch_bounds__(256) k_hole_lists_dev(const uint32_t *valid, const uint32_t *vpre, unsigned long long *cur, uint32_t *hole_pos, uint32_t *tail_src) {
-  const uint64_t M = cur[0], S = cur[3];
-  if (S - M > HOLE_FAST_CAP) { if (blockIdx.x == 0 && threadIdx.x == 0) cur[4] = 1; return; }
-  const int64_t n_words = (int64_t)(S >> 5);
-  const uint32_t below = valid_rank(valid, vpre, M, n_words);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
-    const uint32_t bits = valid[w];
-    const uint64_t p0 = (uint64_t)w << 5;
-    if (p0 + 32 <= M && bits == 0xFFFFFFFFu) continue;
-    if (p0 >= M && bits == 0) continue;
-    const uint32_t pre = vpre[w];
-    for (int b = 0; b < 32; b++) {
-      const uint64_t pos = p0 + b;
-      const bool v = (bits >> b) & 1u;
-      const uint32_t vr = pre + __popc(bits & ((1u << b) - 1u));
-      if (pos < M && !v) hole_pos[pos - vr] = (uint32_t)pos;
-      else if (pos >= M && v) tail_src[vr - below] = (uint32_t)pos;
-    }
+// Hole filling, fast path: when every probe row of the batch found its match (the foreign-key join) the only holes of the
+// positional result are the pads that round each partition up to 32 slots, and both lists — the pad slots below M and the real
+// rows at or above M — follow from the partition bases alone: one small kernel instead of passes over the validity bitmap.
+// A batch with misses (M != rows in the slabs) is completed by fill_holes_host once the counts are on the host.
+static constexpr int HOLE_PAD_THREADS = 512;   // >= partitions of the streaming path (SA_MAX_PBITS)
+__global__ void __launch_bounds__(HOLE_PAD_THREADS) k_hole_pads(const uint32_t *lo, const uint32_t *hi, const uint32_t *lim, const uint32_t *out_base, int n_parts,
+                                                                 unsigned long long *cur, uint32_t *hole_pos, uint32_t *tail_src) {
+  __shared__ uint32_t s_h[HOLE_PAD_THREADS], s_t[HOLE_PAD_THREADS];
+  __shared__ unsigned long long s_rows;
+  const int q = threadIdx.x;
+  if (q == 0) s_rows = 0;
+  __syncthreads();
+  const uint64_t M = cur[0];
+  uint32_t cnt = 0, base = 0, h = 0, t = 0;
+  if (q < n_parts) {
+    uint32_t e = hi[q];
+    if (lim && e > lim[q]) e = lim[q];
+    cnt = e - lo[q];
+    base = out_base[q];
+    atomicAdd(&s_rows, (unsigned long long)cnt);
+    const uint64_t pad_lo = (uint64_t)base + cnt, pad_hi = out_base[q + 1];        // pad slots of this partition
+    const uint64_t hole_hi = pad_hi < M ? pad_hi : M;
+    h = hole_hi > pad_lo ? (uint32_t)(hole_hi - pad_lo) : 0u;                      // ... that lie below M
+    const uint64_t real_lo = (uint64_t)base > M ? (uint64_t)base : M;
+    t = pad_lo > real_lo ? (uint32_t)(pad_lo - real_lo) : 0u;                      // real rows of this partition at or above M
+  }
+  s_h[q] = h;
+  s_t[q] = t;
+  __syncthreads();
+  if (q == 0) {
+    cur[6] = s_rows;                  // rows the scatter placed: == M iff no probe row missed
+    uint32_t rh = 0, rt = 0;
+    for (int i = 0; i < n_parts; i++) { const uint32_t a = s_h[i], b = s_t[i]; s_h[i] = rh; s_t[i] = rt; rh += a; rt += b; }
+    cur[5] = rh;                      // holes to fill (== rt when nothing missed)
+  }
+  __syncthreads();
+  if (q < n_parts && cur[6] == M) {
+    const uint64_t pad_lo = (uint64_t)base + cnt;
+    for (uint32_t i = 0; i < h; i++) hole_pos[s_h[q] + i] = (uint32_t)(pad_lo + i);
+    const uint64_t real_lo = (uint64_t)base > M ? (uint64_t)base : M;
+    for (uint32_t i = 0; i < t; i++) tail_src[s_t[q] + i] = (uint32_t)(real_lo + i);
   }
 }
 struct HoleMoveDevParams {
   int n_cols;
   uint64_t *col[8];
-  const uint32_t *hole_pos, *tail_src, *valid, *vpre;
+  const uint32_t *hole_pos, *tail_src;
   const unsigned long long *cur;
 };
-__global__ void __launch_bounds__(256) k_hole_move_dev(const HoleMoveDevParams h) {
-  const uint64_t M = h.cur[0], S = h.cur[3];
-  if (S - M > HOLE_FAST_CAP) return;
-  const uint64_t H = M - valid_rank(h.valid, h.vpre, M, (int64_t)(S >> 5));
+__global__ void __launch_bounds__(256) k_hole_move_pads(const HoleMoveDevParams h) {
+  if (h.cur[6] != h.cur[0]) return;  // misses: the host-sized pass does the whole job
+  const uint64_t H = h.cur[5];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < H; k += stride) {
     const uint32_t d = h.hole_pos[k], sidx = h.tail_src[k];
     for (int c = 0; c < h.n_cols; c++) h.col[c][d] = h.col[c][sidx];
   }
+}
+
+// ---- diagnostics (TQ_JOIN_DEBUG_SUMS=1): wrapping sums of 8-byte words over strided ranges
+__global__ void k_dbg_sum(const uint64_t *base, int64_t n, int stride, unsigned long long *out) {
+  unsigned long long acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += base[i * stride];
+  atomicAdd(out, acc);
+}
+__global__ void k_dbg_sum_slab(const uint64_t *slab, const uint32_t *lo, const uint32_t *hi, int n_parts, int nc, int c, unsigned long long *out) {
+  unsigned long long acc = 0, cnt = 0;
+  for (int q = blockIdx.x; q < n_parts; q += gridDim.x)
+    for (int64_t r = lo[q] + threadIdx.x; r < (int64_t)hi[q]; r += blockDim.x) { acc += slab[r * nc + c]; cnt++; }
+  atomicAdd(out, acc);
+  atomicAdd(out + 1, cnt);
+}
+__global__ void k_dbg_sum_valid(const uint64_t *col, const uint32_t *valid, const unsigned long long *cur, unsigned long long *out) {
+  const int64_t S = (int64_t)cur[3];
+  unsigned long long acc = 0, cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x)
+    if ((valid[i >> 5] >> (i & 31)) & 1u) { acc += col[i]; cnt++; }
+  atomicAdd(out, acc);
+  atomicAdd(out + 1, cnt);
+}
+static void dbg_report(const char *what, int c, const unsigned long long *d_out, cudaStream_t s) {
+  unsigned long long h[2] = {0, 0};
+  cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  fprintf(stderr, "[tq debug] %-28s col %d  sum=%016llx  rows=%llu\n", what, c, h[0], h[1]);
 }
 
 // scatter (AoS, TMA-fed) -> partition bases -> positional probe -> device-driven hole filling
@@ -2056,10 +2102,8 @@ static int32_t launch_probe_stream(tq_join *j, const ProbeParams &p, const std::
   TQ_TRY(j->part_aos[slot].reserve((size_t)slab * P * NP * 8 + 256));
   const int64_t n_words_max = (int64_t)(alloc_rows >> 5) + 1;
   TQ_TRY(j->pos_valid[slot].reserve((size_t)(n_words_max + 2) * 4));
-  TQ_TRY(j->hole_cnt[slot].reserve((size_t)(n_words_max + 2) * 4));
-  TQ_TRY(j->hole_pre[slot].reserve((size_t)(n_words_max + 2) * 4));
-  TQ_TRY(j->hole_pos[slot].reserve((size_t)(HOLE_FAST_CAP + 64) * 4));
-  TQ_TRY(j->hole_src[slot].reserve((size_t)(HOLE_FAST_CAP + 64) * 4));
+  TQ_TRY(j->hole_pos[slot].reserve((size_t)(32 * (P + 2)) * 4));   // at most 31 pad slots per partition
+  TQ_TRY(j->hole_src[slot].reserve((size_t)(32 * (P + 2)) * 4));
   k_init_slabs<<<(P + 1 + 255) / 256, 256, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), P, (uint32_t)slab, 0u);
   count_launch();
   ScatterAosParams q{};
@@ -2068,6 +2112,18 @@ static int32_t launch_probe_stream(tq_join *j, const ProbeParams &p, const std::
   for (int c = 0; c < NP; c++) {
     q.sp.in[c] = probe[c];
     if ((reinterpret_cast<uintptr_t>(probe[c].data) & 15) != 0) q.use_tma = 0;
+  }
+  if (j->seg.n) {  // regions filled by the peers' push kernels; row counts live on the device
+    const int T = scatter_aos_tile(NP, P + 2);
+    q.n_segs = j->seg.n;
+    q.seg_tiles = (int)((j->seg.cap + T - 1) / T);
+    for (int g = 0; g < j->seg.n; g++) {
+      q.seg_cnt[g] = j->seg.cnt[g];
+      for (int c = 0; c < NP; c++) {
+        q.seg_in[g][c] = j->seg.col[g][c];
+        if ((reinterpret_cast<uintptr_t>(j->seg.col[g][c]) & 15) != 0) q.use_tma = 0;
+      }
+    }
   }
   q.sp.selected = d_selected;
   q.sp.key_col = j->probe_key;
@@ -2080,6 +2136,18 @@ static int32_t launch_probe_stream(tq_join *j, const ProbeParams &p, const std::
   q.sp.overflow = cur + 2;
   q.out = j->part_aos[slot].as<uint64_t>();
   TQ_TRY(launch_scatter_aos(q, NP, s));
+  DevBuf dbg;
+  if (g_debug_sums && !j->seg.n) {
+    TQ_TRY(dbg.reserve(64));
+    for (int c = 0; c < NP; c++) {
+      cudaMemsetAsync(dbg.p, 0, 16, s);
+      k_dbg_sum<<<296, 256, 0, s>>>(probe[c].data, n, 1, dbg.as<unsigned long long>());
+      dbg_report("probe input", c, dbg.as<unsigned long long>(), s);
+      cudaMemsetAsync(dbg.p, 0, 16, s);
+      k_dbg_sum_slab<<<P, 256, 0, s>>>(j->part_aos[slot].as<uint64_t>(), off.as<uint32_t>(), cur_b.as<uint32_t>(), P, NP, c, dbg.as<unsigned long long>());
+      dbg_report("slabs after scatter", c, dbg.as<unsigned long long>(), s);
+    }
+  }
   k_part_bases<<<1, 32, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), P, j->pos_base[slot].as<uint32_t>(), cur + 3);
   count_launch();
   ProbePosParams pp{};
@@ -2093,51 +2161,71 @@ static int32_t launch_probe_stream(tq_join *j, const ProbeParams &p, const std::
   pp.valid = j->pos_valid[slot].as<uint32_t>();
   pp.cursor = cur;
   pp.key_col = j->probe_key;
-  const int64_t tiles_per_part = (n / P + PP_TILE - 1) / PP_TILE;
-  int64_t split = tiles_per_part / g_tiles_per_cta;
+  { const char *e = getenv("TQ_JOIN_PP_DEBUG"); const int f = e ? atoi(e) : 0; pp.dbg_no_tma = f & 1; pp.dbg_late_release = (f >> 1) & 1; }
+  const ProbePosVariant pv = probe_pos_kernel(NP, NB, g_pp_variant);
+  const int64_t rows_per_cta = g_tiles_per_cta * 1024;   // ~8K rows per CTA: enough CTAs per partition that only a handful of partitions are live at once
+  int64_t split = (n / P) / rows_per_cta;
   if (split < 1) split = 1;
   pp.split = (int)split;
-  ProbePosKernel k = probe_pos_kernel(NP, NB);
-  const int smem = PP_STAGES * PP_TILE * NP * 8;
-  static bool attr[5][5] = {};
-  if (!attr[NP][NB]) {
-    TQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr[NP][NB] = true;
-  }
-  k<<<(unsigned)(P * split), PP_THREADS, smem, s>>>(pp, j->table);
+  const int smem = PP_STAGES * pv.tile * NP * 8;
+  TQ_CUDA(cudaFuncSetAttribute(pv.k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  pv.k<<<(unsigned)(P * split), pv.threads, smem, s>>>(pp, j->table);
   count_launch();
   TQ_TRY(check_launch("k_probe_pos"));
-  // holes: padding of every partition to 32 rows + probe rows without a match
-  uint32_t *cnt = j->hole_cnt[slot].as<uint32_t>(), *pre = j->hole_pre[slot].as<uint32_t>();
-  k_hole_popc_dev<<<stream_grid(n_words_max + 1), 256, 0, s>>>(pp.valid, cur, n_words_max, cnt);
-  count_launch();
-  TQ_TRY(exclusive_scan_u32(cnt, 1, pre, 1, n_words_max + 1, nullptr, j->hole_scan, s));
-  k_hole_lists_dev<<<stream_grid(n_words_max), 256, 0, s>>>(pp.valid, pre, cur, j->hole_pos[slot].as<uint32_t>(), j->hole_src[slot].as<uint32_t>());
+  if (g_debug_sums) {
+    for (int c = 0; c < NP; c++) {
+      cudaMemsetAsync(dbg.p, 0, 16, s);
+      k_dbg_sum_valid<<<296, 256, 0, s>>>(p.out_probe[c].data, pp.valid, cur, dbg.as<unsigned long long>());
+      dbg_report("probe output (valid slots)", c, dbg.as<unsigned long long>(), s);
+    }
+  }
+  // holes: the padding of every partition to 32 slots (filled here) + probe rows without a match (finalize_pending)
+  k_hole_pads<<<1, HOLE_PAD_THREADS, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), j->pos_base[slot].as<uint32_t>(), P, cur,
+                                            j->hole_pos[slot].as<uint32_t>(), j->hole_src[slot].as<uint32_t>());
   HoleMoveDevParams hm{};
   hm.n_cols = NP + NB;
   for (int c = 0; c < NP; c++) hm.col[c] = p.out_probe[c].data;
   for (int c = 0; c < NB; c++) hm.col[NP + c] = p.out_build[c].data;
   hm.hole_pos = j->hole_pos[slot].as<uint32_t>();
   hm.tail_src = j->hole_src[slot].as<uint32_t>();
-  hm.valid = pp.valid;
-  hm.vpre = pre;
   hm.cur = cur;
-  k_hole_move_dev<<<stream_grid((int64_t)HOLE_FAST_CAP / 4), 256, 0, s>>>(hm);
+  k_hole_move_pads<<<32, 256, 0, s>>>(hm);
   count_launch(2);
   j->probe_launches += 3;
-  return check_launch("k_hole_move");
+  TQ_TRY(check_launch("k_hole_move_pads"));
+  if (g_debug_sums) {
+    unsigned long long h_cur[8];
+    cudaMemcpyAsync(h_cur, cur, 64, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "[tq debug] probe: M=%llu span=%llu pad_holes=%llu rows_in_slabs=%llu\n", h_cur[0], h_cur[3], h_cur[5], h_cur[6]);
+    for (int c = 0; c < NP; c++) {
+      cudaMemsetAsync(dbg.p, 0, 16, s);
+      k_dbg_sum<<<296, 256, 0, s>>>(p.out_probe[c].data, (int64_t)h_cur[0], 1, dbg.as<unsigned long long>());
+      dbg_report("result probe column [0,M)", c, dbg.as<unsigned long long>(), s);
+    }
+  }
+  j->probe_launches += 3;
+  return TQ_OK;
 }
 
-// more holes than the device-driven pass covers (a join with many misses): exact-size lists, after the counts are on the host
+// misses among the probe rows (a join with many misses): exact-size lists, after the counts are on the host
 static int32_t fill_holes_host(tq_join *j, ResultBatch *rb, int slot, uint64_t M, uint64_t S) {
   cudaStream_t s = rt().compute;
   const int64_t n_words = (int64_t)(S >> 5);
+  if (n_words == 0 || S == M) return TQ_OK;
   const uint64_t max_holes = S - M;
-  DevBuf hp, hs;
+  // prefix popcounts of the validity bitmap (n_words + 1 entries: the last one is the total), then the two lists, then the moves
+  DevBuf cnt, pre, hp, hs;
+  TQ_TRY(cnt.reserve((size_t)(n_words + 2) * 4));
+  TQ_TRY(pre.reserve((size_t)(n_words + 2) * 4));
   TQ_TRY(hp.reserve((size_t)(max_holes + 64) * 4));
   TQ_TRY(hs.reserve((size_t)(max_holes + 64) * 4));
-  const uint32_t *valid = j->pos_valid[slot].as<uint32_t>(), *pre = j->hole_pre[slot].as<uint32_t>();  // the prefix counts are already there
-  k_hole_lists<<<stream_grid(n_words), 256, 0, s>>>(valid, pre, n_words, M, hp.as<uint32_t>(), hs.as<uint32_t>());
+  const uint32_t *valid = j->pos_valid[slot].as<uint32_t>();
+  TQ_CUDA(cudaMemsetAsync(cnt.as<uint32_t>() + n_words, 0, 4, s));
+  k_hole_popc<<<stream_grid(n_words), 256, 0, s>>>(valid, n_words, cnt.as<uint32_t>());
+  count_launch();
+  TQ_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), 1, pre.as<uint32_t>(), 1, n_words + 1, nullptr, j->hole_scan, s));
+  k_hole_lists<<<stream_grid(n_words), 256, 0, s>>>(valid, pre.as<uint32_t>(), n_words, M, hp.as<uint32_t>(), hs.as<uint32_t>());
   HoleMoveParams hm{};
   hm.n_cols = (int)rb->cols.size();
   if (hm.n_cols > 8) { set_error("internal: positional result with %d columns", hm.n_cols); return TQ_ERR_STATE; }
@@ -2145,13 +2233,13 @@ static int32_t fill_holes_host(tq_join *j, ResultBatch *rb, int slot, uint64_t M
   hm.hole_pos = hp.as<uint32_t>();
   hm.tail_src = hs.as<uint32_t>();
   hm.valid = valid;
-  hm.vpre = pre;
+  hm.vpre = pre.as<uint32_t>();
   hm.n_words = n_words;
   hm.M = M;
   k_hole_move<<<stream_grid((int64_t)max_holes), 256, 0, s>>>(hm);
   count_launch(2);
   TQ_TRY(check_launch("k_hole_move"));
-  TQ_CUDA(cudaStreamSynchronize(s));  // hp / hs go back to the allocator
+  TQ_CUDA(cudaStreamSynchronize(s));  // the scratch arrays go back to the allocator
   return TQ_OK;
 }
 
@@ -2177,7 +2265,7 @@ static int32_t launch_probe(tq_join *j, const std::vector<DCol> &probe, const ui
   p.def_mask = j->def_mask;
   p.n = n;
   p.capacity = capacity;
-  unsigned long long *cur = j->cursors.as<unsigned long long>() + 8 * cursor_slot;  // [0] rows, [1] matched probe rows, [2] slab overflow, [3] span of the positional result, [4] holes left to the host
+  unsigned long long *cur = j->cursors.as<unsigned long long>() + 8 * cursor_slot;  // [0] rows, [1] matched probe rows, [2] slab overflow, [3] span of the positional result, [5] pad holes, [6] rows the scatter placed
   p.cursor = cur;
   TQ_CUDA(cudaMemsetAsync(cur, 0, 64, s));
   {
@@ -2426,6 +2514,7 @@ static int32_t finalize_pending(tq_join *j) {
   float ms = 0;
   if (cudaEventElapsedTime(&ms, j->ev_a[pb.cursor_slot], j->ev_b[pb.cursor_slot]) == cudaSuccess) j->last_probe_ns = (int64_t)(ms * 1e6);
   else cudaGetLastError();
+  if (hc[2] && pb.segmented) { set_error("segmented probe batch: a partition slab overflowed (heavily skewed keys)"); return TQ_ERR_INVALID_ARG; }
   if (hc[2]) {
     // a partition slab of the optimistic (histogram-free) scatter was too small — skewed keys: exact offsets from now on
     j->optimistic_scatter = false;
@@ -2433,7 +2522,7 @@ static int32_t finalize_pending(tq_join *j) {
     TQ_CUDA(cudaStreamSynchronize(r.compute));
     produced = hc[0];
   }
-  if (hc[4]) TQ_TRY(fill_holes_host(j, pb.rb.get(), pb.cursor_slot, hc[0], hc[3]));  // positional result with many misses
+  if (hc[3] && hc[6] != hc[0]) TQ_TRY(fill_holes_host(j, pb.rb.get(), pb.cursor_slot, hc[0], hc[3]));  // positional result with misses among the probe rows
   if (produced > pb.rb->capacity) {
     // duplicate build keys: the first launch served as the count pass; run again with the exact size
     TQ_TRY(launch_probe(j, pb.probe, pb.d_selected, pb.n, pb.rb.get(), produced, pb.cursor_slot));
@@ -2511,6 +2600,8 @@ static int32_t start_batch(tq_join *j, const std::vector<DCol> &probe, const uin
   pb.d_selected = d_selected;
   pb.n = n;
   pb.want_host = want_host;
+  pb.segmented = j->seg.n != 0;
+  j->seg.n = 0;
   pb.cursor_slot = slot;
   j->probe_rows_total += n;
   return TQ_OK;
@@ -2638,7 +2729,9 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   { const char *e = getenv("TQ_JOIN_NO_FAST"); g_no_fast_kernel = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_OLD_FAST"); g_old_fast = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_NO_TMA"); g_no_tma = e && e[0] == '1'; }
-  { const char *e = getenv("TQ_JOIN_SCATTER_TILE"); g_scatter_tile = (e && atoi(e) == 2048) ? 2048 : 4096; }
+  { const char *e = getenv("TQ_JOIN_PP_VARIANT"); g_pp_variant = e ? atoi(e) : 0; }
+  { const char *e = getenv("TQ_JOIN_DEBUG_SUMS"); g_debug_sums = e && e[0] == '1'; }
+  { const char *e = getenv("TQ_JOIN_SCATTER_TILE"); g_scatter_tile = (e && (atoi(e) == 4096 || atoi(e) == 1024)) ? atoi(e) : 2048; }
   { const char *e = getenv("TQ_JOIN_EXACT_SCATTER"); g_exact_scatter = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_MAX_LOAD_PCT"); if (e && atoll(e) >= 10 && atoll(e) <= 90) g_max_load_pct = atoll(e); }
   { const char *e = getenv("TQ_JOIN_TILES_PER_CTA"); if (e && atoll(e) > 0) g_tiles_per_cta = atoll(e); }
@@ -3007,6 +3100,40 @@ int32_t tq_join_put_probe(tq_join *j, const tq_column *cols, const uint8_t *sele
   return TQ_OK;
 }
 
+int32_t tq_join_put_probe_segments(tq_join *j, int32_t n_segs, const tq_column *cols, const uint64_t *const *seg_counts, int64_t seg_cap) {
+  if (!j || !cols || !seg_counts || n_segs < 1 || n_segs > SA_MAX_SEGS || seg_cap < 1) return TQ_ERR_INVALID_ARG;
+  TQ_TRY(ensure_init());
+  if (j->state != tq_join::PROBING) { set_error("put_probe before finalize_build"); return TQ_ERR_STATE; }
+  if (j->probe_eof) { set_error("put_probe after probe_eof"); return TQ_ERR_STATE; }
+  const bool eligible = j->pbits > 0 && j->pbits <= SA_MAX_PBITS && j->row_mode && j->join_type == TQ_JOIN_INNER && !j->build_has_nulls && !j->key_hidden &&
+                        !j->any_ind && !j->has_oc && j->n_probe_cols <= 4 && j->n_build_cols <= 4 && j->optimistic_scatter && !g_no_fast_kernel && !g_old_fast;
+  if (!eligible) {
+    set_error("segmented probe batches need the streaming PK-FK path (inner join, unique NOT NULL build side >= 2^18 rows, <= 4 columns per side)");
+    return TQ_ERR_UNSUPPORTED_TYPE;
+  }
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  TQ_TRY(flush_probe_staging(j));
+  const int T = scatter_aos_tile(j->n_probe_cols, (1 << j->pbits) + 2);
+  const int64_t seg_rows = (seg_cap + T - 1) / T * T;
+  std::vector<DCol> view(j->n_probe_cols);
+  j->seg.n = n_segs;
+  j->seg.cap = seg_cap;
+  for (int g = 0; g < n_segs; g++) {
+    j->seg.cnt[g] = reinterpret_cast<const unsigned long long *>(seg_counts[g]);
+    for (int c = 0; c < j->n_probe_cols; c++) {
+      const tq_column &col = cols[g * j->n_probe_cols + c];
+      if (!col.data || col.null_bitmap || col.offsets) { j->seg.n = 0; set_error("segment columns: NOT NULL 8-byte device columns"); return TQ_ERR_INVALID_ARG; }
+      j->seg.col[g][c] = reinterpret_cast<const uint64_t *>(col.data);
+    }
+  }
+  for (int c = 0; c < j->n_probe_cols; c++) { view[c].data = j->seg.col[0][c]; view[c].bm = nullptr; }
+  const int slot = j->pending.active ? 1 - j->pending.cursor_slot : 0;
+  const int32_t st = start_batch(j, view, nullptr, (int64_t)n_segs * seg_rows, /*want_host=*/false, slot);
+  j->seg.n = 0;
+  return st;
+}
+
 int32_t tq_join_probe_eof(tq_join *j) {
   if (!j) return TQ_ERR_INVALID_ARG;
   TQ_TRY(ensure_init());
@@ -3301,6 +3428,133 @@ int32_t tq_partition_push_device_async(int32_t n_cols, const tq_column *cols, in
 int32_t tq_partition_push_wait(void) {
   TQ_TRY(ensure_init());
   TQ_CUDA(cudaStreamSynchronize(rt().h2d));
+  return TQ_OK;
+}
+
+// ---- push into per-source REGIONS of the peers' receive buffers: no count exchange before the push -----------------------
+// Every destination rank reserves one region of `region_cap` rows per source rank and per column; this rank scatters its rows
+// straight into "its" region on every peer (stores over NVLink) and then publishes how many rows it wrote to each peer in
+// that peer's count table (one 8-byte peer store per destination).  The receiver joins the regions as ONE segmented batch
+// (tq_join_put_probe_segments) whose kernels read the counts from device memory — between the exchange and the join there
+// is no host round trip, only the cross-rank barrier that says "all pushes of this chunk have landed".
+static constexpr int PUSH_SLOTS = 16;
+// One 16-byte slot per (destination, table, source): {rows written, epoch}.  The count is stored first, the epoch flag after a
+// system-scope fence: a receiver that sees the flag sees the count, and — the push kernel having completed before this
+// kernel started — the rows.
+__global__ void k_publish_counts(const uint32_t *cursor, const unsigned long long *overflow, int n_parts, unsigned long long *const *dest_slots,
+                                 unsigned long long epoch) {
+  const int q = threadIdx.x;
+  if (q < n_parts) {
+    volatile unsigned long long *slot = dest_slots[q];
+    slot[0] = *overflow ? ~0ull : (unsigned long long)cursor[q];
+    __threadfence_system();
+    slot[1] = epoch;
+  }
+}
+// Device-side wait for the peers: spins (bounded: ~4 s) until the n slots of this rank's table carry `epoch`.  Enqueued on the
+// compute stream in front of the kernels that read the regions, so the exchange needs no host barrier.
+__global__ void k_region_wait(const unsigned long long *slots, int n, unsigned long long epoch, unsigned *timed_out) {
+  const int g = threadIdx.x;
+  if (g >= n) return;
+  const volatile unsigned long long *flag = slots + 2 * g + 1;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*flag < epoch) {
+    __nanosleep(500);
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) { atomicOr(timed_out, 1u << g); return; }
+  }
+}
+struct PushSlot {
+  DevBuf cursor, lim, ovf, counts_ptrs;
+  PinBuf h_lim, h_ptrs;
+  cudaEvent_t ev = nullptr;
+};
+static PushSlot g_push_slot[PUSH_SLOTS];
+
+int32_t tq_partition_push_regions(int32_t n_cols, const tq_column *cols, int32_t key_col, int64_t n, int32_t n_parts, void *const *dest_data,
+                                  void *const *dest_counts, int64_t region_cap, int32_t slot, uint64_t epoch) {
+  TQ_TRY(ensure_init());
+  if (!cols || !dest_data || !dest_counts || n_cols < 1 || n_cols > 4 || key_col < 0 || key_col >= n_cols || slot < 0 || slot >= PUSH_SLOTS || region_cap < 1 ||
+      region_cap > 0xFFFFFFF0ll) {
+    set_error("tq_partition_push_regions: 1..4 columns, slot 0..%d", PUSH_SLOTS - 1);
+    return TQ_ERR_INVALID_ARG;
+  }
+  TQ_TRY(part_common_check(n_parts, n));
+  for (int c = 0; c < n_cols; c++)
+    if (cols[c].null_bitmap) { set_error("tq_partition_push_regions: columns with NULL bitmaps are not supported"); return TQ_ERR_UNSUPPORTED_TYPE; }
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  cudaStream_t s = r.h2d;  // the push stream: rows cross NVLink while the compute stream joins what has already arrived
+  PushSlot &ps = g_push_slot[slot];
+  if (!ps.ev) TQ_CUDA(cudaEventCreateWithFlags(&ps.ev, cudaEventDisableTiming));
+  TQ_TRY(ps.cursor.reserve(64));
+  TQ_TRY(ps.lim.reserve(64));
+  TQ_TRY(ps.ovf.reserve(8));
+  TQ_TRY(ps.counts_ptrs.reserve(64));
+  TQ_TRY(ps.h_lim.reserve(64));
+  TQ_TRY(ps.h_ptrs.reserve(64));
+  TQ_CUDA(cudaEventSynchronize(ps.ev));  // the previous push of this slot no longer reads the pinned tables below
+  for (int q = 0; q < 16; q++) ps.h_lim.as<uint32_t>()[q] = (uint32_t)region_cap;
+  for (int q = 0; q < n_parts; q++) ps.h_ptrs.as<void *>()[q] = dest_counts[q];
+  TQ_CUDA(cudaMemsetAsync(ps.cursor.p, 0, 64, s));
+  TQ_CUDA(cudaMemsetAsync(ps.ovf.p, 0, 8, s));
+  TQ_CUDA(cudaMemcpyAsync(ps.lim.p, ps.h_lim.p, 64, cudaMemcpyHostToDevice, s));
+  TQ_CUDA(cudaMemcpyAsync(ps.counts_ptrs.p, ps.h_ptrs.p, 64, cudaMemcpyHostToDevice, s));
+  if (n > 0) {
+    ScatterParams sp{};
+    sp.n_cols = n_cols;
+    sp.key_col = key_col;
+    sp.key_mode = KEYMODE_RAW;
+    sp.n = n;
+    sp.n_parts_mod = n_parts;
+    for (int c = 0; c < n_cols; c++) { sp.in[c].data = (const uint64_t *)cols[c].data; sp.in[c].bm = nullptr; }
+    for (int q = 0; q < n_parts; q++)
+      for (int c = 0; c < n_cols; c++) sp.out_bin[q][c] = (uint64_t *)dest_data[q * n_cols + c];
+    sp.part_cursor = ps.cursor.as<uint32_t>();
+    sp.part_lim = ps.lim.as<uint32_t>();
+    sp.overflow = ps.ovf.as<unsigned long long>();
+    ScatterKernel k = scatter_fast_kernel(n_cols);
+    static bool attr[5] = {};
+    if (!attr[n_cols]) {
+      TQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 12)));
+      attr[n_cols] = true;
+    }
+    const int n_bins = n_parts + 1;
+    const int smem = SCAT_TILE * 8 + n_bins * 12 + SCAT_TILE * 2 + SCAT_TILE;
+    const int64_t tiles = (n + SCAT_TILE - 1) / SCAT_TILE;
+    static int64_t push_ctas = -1;
+    if (push_ctas < 0) { const char *e = getenv("TQ_PUSH_CTAS"); push_ctas = (e && atoll(e) > 0) ? atoll(e) : 0; }
+    int64_t cap = (int64_t)r.sm_count * (n_cols <= 2 ? 2 : 1);
+    if (push_ctas > 0 && push_ctas < cap) cap = push_ctas;
+    k<<<(int)(tiles < cap ? tiles : cap), SCATF_THREADS, smem, s>>>(sp);
+    count_launch();
+    TQ_TRY(check_launch("k_probe_scatter_fast(push regions)"));
+  }
+  k_publish_counts<<<1, 32, 0, s>>>(ps.cursor.as<uint32_t>(), ps.ovf.as<unsigned long long>(), n_parts, ps.counts_ptrs.as<unsigned long long *>(), epoch);
+  count_launch();
+  TQ_TRY(check_launch("k_publish_counts"));
+  TQ_CUDA(cudaEventRecord(ps.ev, s));
+  return TQ_OK;
+}
+
+int32_t tq_region_wait(const void *slots, int32_t n_sources, uint64_t epoch) {
+  TQ_TRY(ensure_init());
+  if (!slots || n_sources < 1 || n_sources > 32) return TQ_ERR_INVALID_ARG;
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  static DevBuf timed_out;
+  if (!timed_out.p) { TQ_TRY(timed_out.reserve(8)); TQ_CUDA(cudaMemsetAsync(timed_out.p, 0, 8, r.compute)); }
+  k_region_wait<<<1, 32, 0, r.compute>>>(reinterpret_cast<const unsigned long long *>(slots), n_sources, epoch, timed_out.as<unsigned>());
+  count_launch();
+  return check_launch("k_region_wait");
+}
+
+int32_t tq_partition_push_sync(int32_t slot) {
+  TQ_TRY(ensure_init());
+  if (slot < 0 || slot >= PUSH_SLOTS || !g_push_slot[slot].ev) return TQ_ERR_INVALID_ARG;
+  TQ_CUDA(cudaEventSynchronize(g_push_slot[slot].ev));
   return TQ_OK;
 }
 

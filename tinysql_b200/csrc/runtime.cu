@@ -275,17 +275,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_block_sums(const uint32_t
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-__global__ void k_scan_sums_serial(uint64_t *block_sums, int64_t n_blocks, uint64_t *total_out) {
-  // one thread: n_blocks is at most a few tens of thousands
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    uint64_t run = 0;
-    for (int64_t i = 0; i < n_blocks; i++) {
-      uint64_t v = block_sums[i];
-      block_sums[i] = run;
-      run += v;
-    }
-    if (total_out) *total_out = run;
+// exclusive scan of the per-block sums by ONE CTA: thread t owns a contiguous run of ceil(n / 1024) sums
+__global__ void __launch_bounds__(1024) k_scan_sums_serial(uint64_t *block_sums, int64_t n_blocks, uint64_t *total_out) {
+  __shared__ uint64_t s_part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (n_blocks + 1023) / 1024;
+  const int64_t lo = t * per, hi = (lo + per) < n_blocks ? (lo + per) : n_blocks;
+  uint64_t sum = 0;
+  for (int64_t i = lo; i < hi; i++) sum += block_sums[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele over 1024 partials
+    const uint64_t v = t >= d ? s_part[t - d] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
   }
+  uint64_t run = s_part[t] - sum;  // exclusive prefix of this thread's run
+  for (int64_t i = lo; i < hi; i++) {
+    const uint64_t v = block_sums[i];
+    block_sums[i] = run;
+    run += v;
+  }
+  if (t == 1023 && total_out) *total_out = s_part[1023];
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const uint32_t *in, int in_stride, uint32_t *out, int out_stride, int64_t n,
@@ -321,7 +333,7 @@ int32_t exclusive_scan_u32(const uint32_t *d_in, int in_stride_words, uint32_t *
   TQ_TRY(scratch.reserve((size_t)n_blocks * 8));
   uint64_t *sums = scratch.as<uint64_t>();
   k_scan_block_sums<<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(d_in, in_stride_words, n, sums);
-  k_scan_sums_serial<<<1, 32, 0, s>>>(sums, n_blocks, d_total);
+  k_scan_sums_serial<<<1, 1024, 0, s>>>(sums, n_blocks, d_total);
   k_scan_final<<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(d_in, in_stride_words, d_out, out_stride_words, n, sums);
   count_launch(3);
   return check_launch("exclusive_scan_u32");

@@ -1,7 +1,13 @@
-"""Multi-GPU hash join: radix-partition both sides on the join key across the ranks, exchange the partitions with ONE
-grouped NCCL send/recv (the all-to-all at the shard boundary — NCCL 2.27/2.28 has no ncclAllToAllv), then run the
-single-GPU join on what arrived.  One process per GPU; torch.distributed is plumbing only (device buffers + the
-collective); partitioning and joining are the CUDA kernels of libtinysql_b200.so.
+"""Multi-GPU hash join: radix-partition both sides on the join key across the ranks, exchange the partitions, run the
+single-GPU join on what arrived.  One process per GPU; torch.distributed is plumbing only (process group, barriers, the NCCL
+variant); partitioning, exchange and join are the CUDA kernels of libtinysql_b200.so.
+
+Two exchanges:
+  * RegionExchange / RegionJoin (the default of bench.py --gpus N): the scatter kernel stores every row straight into the
+    destination rank's receive region over NVLink peer memory (CUDA IPC), chunk by chunk, overlapped with the local join of
+    the chunks that have already arrived; device-side epoch flags replace host barriers.
+  * exchange() (distributed_join / distributed_agg): partition locally, then ONE grouped NCCL send/recv — the all-to-all at the
+    shard boundary (NCCL 2.27/2.28 has no ncclAllToAllv); also what the gloo CPU tests drive.
 
 The moral equivalent of the reference's partial->final hash shuffle (executor/aggregate.go:96-133,352-356): a row goes to
 rank  (mix64(key) >> 40) % world  — a pure function of its key, so equal keys meet on one rank and nothing else moves.
@@ -80,60 +86,6 @@ def exchange(cols, send_offsets, world, rank, group=None, recv_counts=None, asyn
     return out, recv_counts
 
 
-class PeerExchange:
-    """All-to-all over NVSwitch PEER MEMORY instead of NCCL send/recv: every rank keeps its partitioned columns in
-    persistent "send" buffers whose CUDA IPC handles are shared once; an exchange is then one tiny offsets all-gather
-    plus, per source rank, a peer-to-peer copy (copy engines over NVLink) that PULLS the slice addressed to this rank.
-    Two barriers per exchange order the producers' scatter kernels against the consumers' pulls."""
-
-    def __init__(self, world, rank, device, n_tables_cols, capacity_rows, dtype=torch.int64):
-        from torch.multiprocessing.reductions import reduce_tensor
-        self.world, self.rank, self.dev = world, rank, device
-        # send[t][c]: partition output of table t, column c (written by tq_partition_device)
-        self.send = [[torch.empty(cap, dtype=dtype, device=device) for _ in range(nc)] for nc, cap in zip(n_tables_cols, capacity_rows)]
-        handles = [[reduce_tensor(x) for x in cols] for cols in self.send]
-        gathered = [None] * world
-        dist.all_gather_object(gathered, handles)
-        self.peer = []
-        for src in range(world):
-            if src == rank:
-                self.peer.append(self.send)
-            else:
-                self.peer.append([[fn(*args) for fn, args in cols] for cols in gathered[src]])
-        self.streams = [torch.cuda.Stream(device=device) for _ in range(max(1, min(world - 1, 4)))]
-
-    def offsets_matrix(self, offsets_list):
-        """all ranks' partition offsets for every table: [src][table][world+1] (one all-gather, one D2H sync)"""
-        mine = torch.tensor(offsets_list, dtype=torch.int64, device=self.dev)
-        allo = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(allo, mine)
-        return torch.stack(allo).cpu().numpy()
-
-    def pull(self, table, offs, out=None):
-        """copy, from every source rank, the rows it partitioned for THIS rank.  offs = offsets_matrix(...)[:, table, :]"""
-        world, rank = self.world, self.rank
-        counts = [int(offs[src, rank + 1] - offs[src, rank]) for src in range(world)]
-        total = sum(counts)
-        ncols = len(self.send[table])
-        if out is None:
-            out = [torch.empty(total, dtype=self.send[table][c].dtype, device=self.dev) for c in range(ncols)]
-        cur = torch.cuda.current_stream()
-        pos = 0
-        events = []
-        for i, src in enumerate([(rank + d) % world for d in range(world)]):  # start with the local slice, then ring order
-            lo, hi = int(offs[src, rank]), int(offs[src, rank + 1])
-            dst_lo = sum(counts[:src])
-            st = self.streams[i % len(self.streams)]
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                for c in range(ncols):
-                    out[c][dst_lo:dst_lo + (hi - lo)].copy_(self.peer[src][table][c][lo:hi], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(st)
-            events.append(ev)
-        return out, counts, events
-
-
 class RawCol:
     """a device column that is just (pointer, rows): quacks like the torch tensors the helpers below take"""
 
@@ -151,96 +103,103 @@ class RawCol:
         return RawCol(self.ptr, min(self.n, sl.stop))
 
 
-class PushExchange:
-    """The fused scatter + exchange: every rank owns persistent RECEIVE buffers (tq_device_alloc) exported once as CUDA IPC
-    handles; every peer opens them under its own device (lazy peer access, like NCCL's P2P transport).  Per step each
-    rank counts its rows per destination (tq_partition_count_device), one tiny all-gather turns the counts into write
-    offsets, and tq_partition_push_device scatters every row straight into the destination rank's receive buffer —
-    stores over NVLink peer memory, no separate exchange pass.  Barriers order pushes against consumers."""
+class RegionExchange:
+    """The exchange the multi-GPU join runs on: every rank owns ONE device allocation (tq_device_alloc, exported once through
+    CUDA IPC and opened by every peer under its own device) that holds, per table t (0 = build side, 1.. = probe chunks):
+        slots[t][src] = {u64 rows, u64 epoch}                  16-byte slot per source rank
+        region[t][src][col] = cap_t rows x 8 bytes             where source `src` scatters its rows for THIS rank
+    A rank pushes table t with tq_partition_push_regions: its scatter kernel stores rows straight into "its" region on every
+    peer (NVLink peer stores, no staging, no count exchange first) and then publishes count + epoch in the peer's slot.  The
+    receiver enqueues tq_region_wait(slots[t], world, epoch) — a device-side wait — in front of the kernels that read the
+    regions and joins them as one segmented batch (tq_join_put_probe_segments): no host round trip and no NCCL call sits
+    between the exchange and the join."""
 
-    def __init__(self, lib, L, world, rank, device, n_tables_cols, capacity_rows):
-        self.lib, self.L, self.world, self.rank, self.dev = lib, L, world, rank, device
-        self.cap = list(capacity_rows)
-        self.own, handles = [], []
-        for nc, cap in zip(n_tables_cols, capacity_rows):
-            ptrs, hs = [], []
-            for _ in range(nc):
-                p = C.c_void_p()
-                L.check(lib.tq_device_alloc(cap * 8, C.byref(p)))
-                h = (C.c_ubyte * 64)()
-                L.check(lib.tq_ipc_get_handle(p, h))
-                ptrs.append(p.value)
-                hs.append(bytes(h))
-            self.own.append(ptrs)
-            handles.append(hs)
+    def __init__(self, lib, L, world, rank, tables, align_rows=4096):
+        self.lib, self.L, self.world, self.rank = lib, L, world, rank
+        self.ncols = [nc for nc, _ in tables]
+        self.cap = [((cap + align_rows - 1) // align_rows) * align_rows for _, cap in tables]
+        self.slot_off = [t * world * 16 for t in range(len(tables))]
+        off = ((len(tables) * world * 16 + 4095) // 4096) * 4096
+        self.reg_off = []
+        for nc, cap in zip(self.ncols, self.cap):
+            self.reg_off.append(off)
+            off += world * nc * cap * 8
+        self.total = off
+        p = C.c_void_p()
+        L.check(lib.tq_device_alloc(self.total, C.byref(p)))
+        L.check(lib.tq_memset_device(p, 0, self.total))
+        L.check(lib.tq_device_synchronize())
+        self.own = p.value
+        h = (C.c_ubyte * 64)()
+        L.check(lib.tq_ipc_get_handle(p, h))
         gathered = [None] * world
-        dist.all_gather_object(gathered, handles)
-        self.peer_ptr = []   # [dst][table][col] -> address valid in THIS process
-        self._opened = []
-        for dst in range(world):
-            if dst == rank:
-                self.peer_ptr.append(self.own)
+        dist.all_gather_object(gathered, bytes(h))
+        self.base, self._opened = [], []
+        for d in range(world):
+            if d == rank:
+                self.base.append(self.own)
                 continue
-            tabs = []
-            for hs in gathered[dst]:
-                cols = []
-                for hb in hs:
-                    p = C.c_void_p()
-                    buf = (C.c_ubyte * 64).from_buffer_copy(hb)
-                    L.check(lib.tq_ipc_open_handle(buf, C.byref(p)))
-                    cols.append(p.value)
-                    self._opened.append(p.value)
-                tabs.append(cols)
-            self.peer_ptr.append(tabs)
-        self.recv = [[RawCol(p, cap) for p in ptrs] for ptrs, cap in zip(self.own, self.cap)]
+            q = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(gathered[d])
+            L.check(lib.tq_ipc_open_handle(buf, C.byref(q)))
+            self.base.append(q.value)
+            self._opened.append(q.value)
+        self.epoch = 0
 
     def close(self):
         for p in self._opened:
             self.lib.tq_ipc_close_handle(C.c_void_p(p))
         self._opened = []
         dist.barrier()  # nobody frees a buffer a peer still has mapped
-        for ptrs in self.own:
-            for p in ptrs:
-                self.lib.tq_device_free(C.c_void_p(p))
-        self.own = []
+        self.lib.tq_device_free(C.c_void_p(self.own))
 
-    def counts(self, key_cols):
-        """local rows per destination for each table: tq_partition_count_device"""
-        out = []
-        for k in key_cols:
-            n = int(k.numel())
-            c = (C.c_int64 * self.world)()
-            col = _tq_cols(self.L, [k], n)
-            self.L.check(self.lib.tq_partition_count_device(col, n, self.world, c))
-            out.append(list(c))
-        return out
+    def region_ptr(self, dst, t, src, c):
+        return self.base[dst] + self.reg_off[t] + ((src * self.ncols[t] + c) * self.cap[t]) * 8
 
-    def plan(self, local_counts):
-        """all-gather the count matrices; returns (write offsets [table][dst], rows arriving here [table])"""
-        mine = torch.tensor(local_counts, dtype=torch.int64, device=self.dev)      # [tables][world]
-        allc = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(allc, mine)
-        m = torch.stack(allc).cpu().numpy()                                      # [src][table][dst]
-        offs = [[int(m[: self.rank, t, d].sum()) for d in range(self.world)] for t in range(m.shape[1])]
-        arriving = [int(m[:, t, self.rank].sum()) for t in range(m.shape[1])]
-        for t, a in enumerate(arriving):
-            if a > self.cap[t]:
-                raise RuntimeError(f"receive buffer of table {t} too small: {a} rows arriving, capacity {self.cap[t]} (skewed keys)")
-        return offs, arriving
+    def slot_ptr(self, dst, t, src):
+        return self.base[dst] + self.slot_off[t] + src * 16
 
-    def push(self, table, cols, offs, async_op=False):
-        n = int(cols[0].numel())
-        ncols = len(cols)
-        dest = (C.c_void_p * (self.world * ncols))()
-        for d in range(self.world):
-            for c in range(ncols):
-                dest[d * ncols + c] = self.peer_ptr[d][table][c]
-        o = (C.c_int64 * self.world)(*offs)
-        fn = self.lib.tq_partition_push_device_async if async_op else self.lib.tq_partition_push_device
-        self.L.check(fn(ncols, _tq_cols(self.L, cols, n), 0, n, self.world, dest, o))
+    def next_epoch(self):
+        self.epoch += 1
+        return self.epoch
 
-    def wait(self):
-        self.L.check(self.lib.tq_partition_push_wait())
+    def push(self, t, cols, n, slot):
+        """scatter this rank's rows of table t into its region on every rank; asynchronous (push stream)"""
+        nc, w = self.ncols[t], self.world
+        dest = (C.c_void_p * (w * nc))()
+        cnts = (C.c_void_p * w)()
+        for d in range(w):
+            for c in range(nc):
+                dest[d * nc + c] = self.region_ptr(d, t, self.rank, c)
+            cnts[d] = self.slot_ptr(d, t, self.rank)
+        self.L.check(self.lib.tq_partition_push_regions(nc, _tq_cols(self.L, cols, n), 0, n, w, dest, cnts, self.cap[t], slot, self.epoch))
+
+    def wait(self, t):
+        """device-side: the compute stream waits until every source has published table t for this epoch"""
+        self.L.check(self.lib.tq_region_wait(C.c_void_p(self.slot_ptr(self.rank, t, 0)), self.world, self.epoch))
+
+    def counts(self, t):
+        """rows each source wrote into this rank's regions of table t (host read: synchronises the compute stream)"""
+        self.wait(t)
+        self.L.check(self.lib.tq_device_synchronize())
+        raw = np.zeros(2 * self.world, dtype=np.uint64)
+        self.L.check(self.lib.tq_memcpy_d2h(raw.ctypes.data, C.c_void_p(self.slot_ptr(self.rank, t, 0)), 16 * self.world))
+        cnt = [int(raw[2 * g]) for g in range(self.world)]
+        if any(c > self.cap[t] for c in cnt):
+            raise RuntimeError(f"region overflow in table {t}: {cnt} rows, capacity {self.cap[t]} (skewed keys)")
+        return cnt
+
+    def segment_args(self, t):
+        """(tq_column array [src][col], count pointer array) of this rank's regions of table t"""
+        nc, w = self.ncols[t], self.world
+        cols = (self.L.TQColumn * (w * nc))()
+        cnts = (C.c_void_p * w)()
+        for g in range(w):
+            for c in range(nc):
+                k = g * nc + c
+                cols[k].length, cols[k].data, cols[k].null_bitmap, cols[k].offsets = self.cap[t], self.region_ptr(self.rank, t, g, c), None, None
+            cnts[g] = self.slot_ptr(self.rank, t, g)
+        return cols, cnts
 
 
 def distributed_join(build_cols, probe_cols, world, rank, partition_fn, local_join_fn, group=None):
@@ -395,186 +354,150 @@ def gpu_local_join(lib, L, build, probe, keep_result=False):
     return join_finish(lib, L, join_begin(lib, L, build, len(probe)), probe, keep_result)
 
 
+class RegionJoin:
+    """The multi-GPU join over a RegionExchange.  Tables: 0 = build side, 1 + c = probe chunk c.  One step:
+
+        push stream    push(build) | push(chunk 0) | push(chunk 1) | ...        (all enqueued up front; NVLink stays busy)
+        compute stream wait(build) -> local build | wait(chunk 0) -> join | wait(chunk 1) -> join | ...
+
+    wait(t) is the device-side tq_region_wait; the chunk-c join overlaps the chunk-(c+1) push.  Host synchronisation: one count
+    read for the build side (tq_join_put_build takes host lengths), the result drain, and ONE barrier at the end of the step
+    (nobody may overwrite a region a peer is still joining)."""
+
+    def __init__(self, lib, L, world, rank, n_build_max, n_probe_max, n_chunks, slack=1.25):
+        """n_build_max / n_probe_max: the largest per-rank shard (every rank must pass the same numbers: the layout is shared)"""
+        self.lib, self.L, self.world, self.rank, self.n_chunks = lib, L, world, rank, n_chunks
+        cap = lambda n: int(n / world * slack) + (1 << 14)   # keys are hash-spread: +25 % covers the imbalance between (source, destination) pairs
+        chunk_max = (n_probe_max + n_chunks - 1) // n_chunks
+        tables = [(2, cap(n_build_max))] + [(2, cap(chunk_max)) for c in range(n_chunks)]
+        self.rx = RegionExchange(lib, L, world, rank, tables)
+
+    def close(self):
+        self.rx.close()
+
+    def step(self, bk, bv, pk, pv, keep_result=False):
+        """bk / bv / pk / pv: this rank's row shards as (device pointer, rows)-like objects.  Returns (rows, stats, result)."""
+        lib, L, rx, w = self.lib, self.L, self.rx, self.world
+        n_probe = int(pk.numel())
+        bounds = [n_probe * i // self.n_chunks for i in range(self.n_chunks + 1)]
+        rx.next_epoch()
+        rx.push(0, [bk, bv], int(bk.numel()), 0)
+        for c in range(self.n_chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            rx.push(1 + c, [RawCol(pk.data_ptr() + lo * 8, hi - lo), RawCol(pv.data_ptr() + lo * 8, hi - lo)], hi - lo, 1 + c)
+        # ---- build side: the only place the host needs row counts
+        cnt_b = rx.counts(0)
+        t = (C.c_int32 * 2)(1, 1)
+        k = (C.c_int32 * 1)(0)
+        d = L.TQJoinDesc(0, 1, 2, t, 2, t, 1, k, k, 0, 0)
+        h = C.c_void_p()
+        L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
+        total, result, st = 0, None, (C.c_int64 * 8)()
+        try:
+            for g in range(w):
+                if cnt_b[g]:
+                    cols = [RawCol(rx.region_ptr(self.rank, 0, g, c), cnt_b[g]) for c in range(2)]
+                    L.check(lib.tq_join_put_build(h, _tq_cols(L, cols, cnt_b[g]), L.TQ_MEM_DEVICE))
+            L.check(lib.tq_join_finalize_build(h))
+            out = (L.TQColumn * 4)()
+            n, eof = C.c_int64(0), C.c_int32(0)
+            chunks = []
+
+            def drain(final):
+                nonlocal total
+                while True:
+                    L.check(lib.tq_join_next_device(h, out, C.byref(n), C.byref(eof)))
+                    if n.value == 0:
+                        return
+                    total += n.value
+                    if keep_result:
+                        from .chunk import device_to_host
+                        chunks.append([device_to_host(1, out[c].data, None, n.value).values for c in range(4)])
+                    if not final:
+                        return
+            for c in range(self.n_chunks):
+                rx.wait(1 + c)                                   # device-side: chunk c has landed from every source
+                cols, cnts = rx.segment_args(1 + c)
+                st_ = lib.tq_join_put_probe_segments(h, w, cols, cnts, rx.cap[1 + c])
+                L.check(st_)
+                if c >= 1:
+                    drain(False)                                 # hand back the batch before last (keeps two result sets alive, not n_chunks)
+            L.check(lib.tq_join_probe_eof(h))
+            drain(True)
+            lib.tq_join_stats(h, st)
+            if keep_result:
+                result = [np.concatenate([ch[c] for ch in chunks]) if chunks else np.zeros(0, np.int64) for c in range(4)]
+        finally:
+            lib.tq_join_destroy(h)
+        for c in range(self.n_chunks):                           # a region overflow would have dropped rows: fail loudly
+            rx.counts(1 + c)
+        dist.barrier()
+        return total, list(st), result
+
+
+def gen_dist_tables(rank, world, n_b, n_p):
+    """this rank's shard of the C5 tables: B.k = the keys k with k % world == rank (shuffled), B.v = 7k + 1; probe row i of
+    rank r has the global id g = r * n_p + i, P.v = g and P.k = mix64(g) % (n_b * world) — uniform keys, every probe row
+    matches exactly once, and any rank can check any row it receives from its values alone."""
+    rng = np.random.default_rng(1000 + rank)
+    bk = rng.permutation(n_b).astype(np.int64) * world + rank
+    gid = np.arange(n_p, dtype=np.int64) + rank * n_p
+    pk = (mix64_np(gid) % np.uint64(n_b * world)).astype(np.int64)
+    return bk, bk * 7 + 1, pk, gid
+
+
+def verify_dist_result(cols, rank, world, n_b, n_p):
+    """every row this rank produced: B.v = 7 B.k + 1, B.k = P.k, P.k = mix64(P.v) % N_b (the key that probe row really carried),
+    the key belongs to this rank's hash partition, no probe row twice.  Returns (ok, rows, wrapping sum of P.v)."""
+    bk, bv, pkk, pv = cols
+    ok = bool(np.array_equal(bv, bk * 7 + 1) and np.array_equal(bk, pkk))
+    ok = ok and bool(np.array_equal(pkk, (mix64_np(pv) % np.uint64(n_b * world)).astype(np.int64)))
+    ok = ok and bool((dest_rank_np(pkk, world) == rank).all())
+    ok = ok and bool(np.unique(pv).size == pv.size)
+    return ok, int(pv.size), int(pv.astype(np.uint64).sum(dtype=np.uint64))
+
+
 def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_src):
-    """bench.py N>1: weak scaling — every rank holds build_rows x probe_rows of a world-times larger join."""
+    """bench.py N>1.  Default tables: C5 — build 1e8 / probe 1e9 at 8 GPUs, i.e. 1.25e7 / 1.25e8 rows PER GPU at every N
+    (weak scaling: per-GPU work is fixed); --build-rows / --probe-rows override the per-GPU sizes."""
     import statistics
 
     from . import _lib as L
     lib = L.load()
     dev = torch.device("cuda", local_rank)
-    n_b, n_p = args.build_rows, args.probe_rows
-    N_b = n_b * world
-    rng = np.random.default_rng(1000 + rank)
-    # this rank's build shard: the keys k with k % world == rank, shuffled (a disjoint cover of [0, N_b)); B.v = 7k+1
-    bk_h = rng.permutation(n_b).astype(np.int64) * world + rank
-    pk_h = rng.integers(0, N_b, n_p, dtype=np.int64)
-    bk = torch.from_numpy(bk_h).to(dev)
-    bv = bk * 7 + 1
-    pk = torch.from_numpy(pk_h).to(dev)
-    pv = torch.arange(n_p, dtype=torch.int64, device=dev) + rank * n_p
-    part = gpu_partition_fn(lib, L)
-    mode = os.environ.get("TQ_DIST_EXCHANGE", "push")
-    use_peer = mode == "peer"
-    px = None
-    pushx = None
-    if mode == "push":
-        try:
-            slack = lambda n: int(n * 1.25) + (1 << 16)   # keys are hash-spread: +25 % covers the imbalance
-            pushx = PushExchange(lib, L, world, rank, dev, [2, 2], [slack(n_b), slack(n_p)])
-        except Exception as e:
-            if rank == 0:
-                print(f"[dist] push exchange unavailable ({e}); falling back", flush=True)
-            pushx = None
-        okp = torch.tensor([1 if pushx is not None else 0], device=dev)
-        dist_mod.all_reduce(okp, op=dist_mod.ReduceOp.MIN)
-        if int(okp) == 0:
-            pushx, use_peer = None, True
-    if use_peer:
-        try:
-            px = PeerExchange(world, rank, dev, [2, 2], [n_b, n_p])
-        except Exception as e:  # no CUDA IPC in this container: NCCL all_to_all instead
-            if rank == 0:
-                print(f"[dist] peer-memory exchange unavailable ({e}); using NCCL all_to_all", flush=True)
-            px = None
-    ok = torch.tensor([1 if px is not None else 0], device=dev)
-    dist_mod.all_reduce(ok, op=dist_mod.ReduceOp.MIN)
-    if int(ok) == 0:
-        px = None
+    default_sizes = (args.build_rows, args.probe_rows) == (10_000_000, 100_000_000)
+    n_b, n_p = (12_500_000, 125_000_000) if default_sizes else (args.build_rows, args.probe_rows)
+    N_b, N_p = n_b * world, n_p * world
+    bk_h, bv_h, pk_h, pv_h = gen_dist_tables(rank, world, n_b, n_p)
+    bk, bv, pk, pv = (torch.from_numpy(x).to(dev) for x in (bk_h, bv_h, pk_h, pv_h))
+    del bk_h, bv_h, pv_h
+    torch.cuda.synchronize()
+    n_chunks = max(1, int(os.environ.get("TQ_DIST_CHUNKS", "4")))
+    rj = RegionJoin(lib, L, world, rank, n_b, n_p, n_chunks)
 
-    phase_ms = {}
-
-    def tick(name, t0):
-        torch.cuda.synchronize()
-        lib.tq_device_synchronize()
-        phase_ms[name] = phase_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
-        return time.perf_counter()
-
-    profile_phases = os.environ.get("TQ_DIST_PHASES") == "1"  # extra syncs per phase (diagnostics only; slows the step)
-
-    def part_into(cols, outs):
-        n = int(cols[0].numel())
-        offs = (C.c_int64 * (world + 1))()
-        types = (C.c_int32 * len(cols))(*([1] * len(cols)))
-        L.check(lib.tq_partition_device(len(cols), _tq_cols(L, cols, n), types, 0, n, world, _tq_cols(L, outs, n), offs))
-        return list(offs)
-
-    def step_peer():
-        t = time.perf_counter()
-        b_off = part_into([bk, bv], px.send[0])   # tq_partition_device synchronises its stream before returning
-        p_off = part_into([pk, pv], px.send[1])
-        if profile_phases:
-            t = tick("partition", t)
-        offs = px.offsets_matrix([b_off, p_off])  # also orders every rank's scatter before anyone pulls
-        b_recv, _, ev_b = px.pull(0, offs[:, 0, :])
-        p_recv, _, ev_p = px.pull(1, offs[:, 1, :])
-        for ev in ev_b:
-            ev.synchronize()
-        if profile_phases:
-            t = tick("pull_build(+probe in flight)", t)
-        h = join_begin(lib, L, b_recv)            # the probe rows are still arriving while the table is built
-        for ev in ev_p:
-            ev.synchronize()
-        if profile_phases:
-            t = tick("build+pull_probe", t)
-        rows, st = join_finish(lib, L, h, p_recv)
-        if profile_phases:
-            t = tick("local_probe", t)
-        dist_mod.barrier()                        # nobody overwrites its send buffers until every peer has pulled
-        return rows, st, int(p_recv[0].numel())
-
-    def step_nccl():
-        t = time.perf_counter()
-        b_part, b_off = part([bk, bv], world)
-        p_part, p_off = part([pk, pv], world)
-        if profile_phases:
-            t = tick("partition", t)
-        torch.cuda.synchronize()
-        b_cnt, p_cnt = exchange_counts([b_off, p_off], world, rank, dev)
-        b_recv, _ = exchange(b_part, b_off, world, rank, recv_counts=b_cnt)
-        # the probe rows travel while the hash table is built from the build rows that already arrived
-        p_recv, _, works = exchange(p_part, p_off, world, rank, recv_counts=p_cnt, async_op=True)
-        torch.cuda.current_stream().synchronize()
-        if profile_phases:
-            t = tick("exchange_build", t)
-        h = join_begin(lib, L, b_recv)
-        for w in works:
-            w.wait()
-        torch.cuda.synchronize()
-        if profile_phases:
-            t = tick("build+exchange_probe", t)
-        rows, st = join_finish(lib, L, h, p_recv)
-        if profile_phases:
-            t = tick("local_probe", t)
-        return rows, st, int(p_recv[0].numel())
-
-    n_chunks = max(1, int(os.environ.get("TQ_DIST_CHUNKS", "1")))
-    bounds = [n_p * i // n_chunks for i in range(n_chunks + 1)]
-    pk_c = [pk[bounds[i]:bounds[i + 1]] for i in range(n_chunks)]
-    pv_c = [pv[bounds[i]:bounds[i + 1]] for i in range(n_chunks)]
-
-    def step_push():
-        """count -> one all-gather -> push build -> [push probe chunk i+1 over NVLink || probe chunk i locally]"""
-        t = time.perf_counter()
-        cnt = pushx.counts([bk] + pk_c)                      # rows per destination: build, then every probe chunk
-        mine = torch.tensor(cnt, dtype=torch.int64, device=dev)
-        allc = [torch.empty_like(mine) for _ in range(world)]
-        dist_mod.all_gather(allc, mine)                      # also: every rank has finished consuming the previous step
-        m = torch.stack(allc).cpu().numpy()                  # [src][table][dst]; table 0 = build, 1.. = probe chunks
-        arr_b = int(m[:, 0, rank].sum())
-        arr_c = [int(m[:, 1 + i, rank].sum()) for i in range(n_chunks)]
-        if arr_b > pushx.cap[0] or sum(arr_c) > pushx.cap[1]:
-            raise RuntimeError("receive buffer too small (skewed keys)")
-        # write offsets: chunk i of the probe side lands behind chunks < i in the destination's receive buffer
-        off_b = [int(m[:rank, 0, d].sum()) for d in range(world)]
-        base = [[int(m[:, 1:1 + i, d].sum()) for d in range(world)] for i in range(n_chunks)]
-        off_c = [[base[i][d] + int(m[:rank, 1 + i, d].sum()) for d in range(world)] for i in range(n_chunks)]
-        if profile_phases:
-            t = tick("count+plan", t)
-        pushx.push(0, [bk, bv], off_b)                       # rows cross NVLink as the scatter kernel stores them
-        dist_mod.barrier()                                   # every rank's build rows have landed
-        pushx.push(1, [pk_c[0], pv_c[0]], off_c[0], async_op=True)   # first probe chunk travels while the table is built
-        h = join_begin(lib, L, [x[:arr_b] for x in pushx.recv[0]])
-        if profile_phases:
-            t = tick("push_build+build", t)
-        hh, nbc = h
-        my_base = 0
-        for i in range(n_chunks):
-            pushx.wait()
-            dist_mod.barrier()                               # chunk i has landed everywhere
-            if i + 1 < n_chunks:
-                pushx.push(1, [pk_c[i + 1], pv_c[i + 1]], off_c[i + 1], async_op=True)
-            if arr_c[i]:
-                cols = [RawCol(x.ptr + my_base * 8, arr_c[i]) for x in pushx.recv[1]]
-                L.check(lib.tq_join_put_probe(hh, _tq_cols(L, cols, arr_c[i]), None, L.TQ_MEM_DEVICE))   # asynchronous: kernels queued
-            my_base += arr_c[i]
-        if profile_phases:
-            t = tick("push_probe||local_probe", t)
-        rows, st = join_finish(lib, L, h, [RawCol(0, 0), RawCol(0, 0)])
-        if profile_phases:
-            t = tick("drain", t)
-        return rows, st, sum(arr_c)
-
-    step = step_push if pushx is not None else (step_peer if px is not None else step_nccl)
+    def step(keep=False):
+        return rj.step(bk, bv, pk, pv, keep_result=keep)
 
     for _ in range(args.warmup):
         step()
-    phase_ms.clear()
     from bench import ClockSampler
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize()
+    lib.tq_device_synchronize()
     dist_mod.barrier()
     launches1 = lib.tq_kernel_launch_count()
     L.check(lib.tq_timer_start())
     t0 = time.perf_counter()
-    rows_total, probe_ns = 0, []
+    rows_total, probe_ns, build_ns = 0, [], []
     for _ in range(args.steps):
         rows, st, _ = step()
         rows_total += rows
         probe_ns.append(st[5])
+        build_ns.append(st[6])
     ms = C.c_float(0)
     L.check(lib.tq_timer_stop(C.byref(ms)))
-    torch.cuda.synchronize()
+    lib.tq_device_synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     dist_mod.barrier()
     clocks = sampler.stop()
@@ -587,23 +510,152 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
     ms_per_step = float(tmax[0]) / args.steps
     joined_per_step = float(tsum[1]) / args.steps
     value = joined_per_step / (ms_per_step * 1e-3)
+    # ---- full-size value check at this N (outside the timed region): every rank verifies every row it produced
+    rows_v, _, res = step(keep=True)
+    ok, n_rows, pv_sum = verify_dist_result(res, rank, world, n_b, n_p)
+    del res
+    v = torch.tensor([1 if ok else 0, n_rows, pv_sum % (1 << 62), pv_sum >> 62], dtype=torch.int64, device=dev)
+    vmin = v.clone()
+    dist_mod.all_reduce(vmin, op=dist_mod.ReduceOp.MIN)
+    vsum = v.clone()
+    dist_mod.all_reduce(vsum, op=dist_mod.ReduceOp.SUM)
+    want_sum = (N_p * (N_p - 1) // 2) % (1 << 64)
+    got_sum = ((int(vsum[3]) << 62) + int(vsum[2])) % (1 << 64)
+    verified = {"ok": bool(int(vmin[0]) == 1 and int(vsum[1]) == N_p and got_sum == want_sum), "rows": int(vsum[1]), "expected_rows": N_p,
+                "checks": ["per rank, every row: B.v == 7*B.k + 1, B.k == P.k, P.k == mix64(P.v) % N_build, dest_rank(P.k) == rank, P.v distinct",
+                           "all ranks: row count == probe rows, sum(P.v) == N(N-1)/2 (every probe row exactly once)"]}
+    # ---- the exchange north_star names, measured once for the record: partition + ONE grouped NCCL send/recv (all-to-all)
+    nccl_ms = None
+    try:
+        part = gpu_partition_fn(lib, L)
+        torch.cuda.synchronize()
+        dist_mod.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p_part, p_off = part([pk, pv], world)
+        torch.cuda.synchronize()
+        cnt = exchange_counts([p_off], world, rank, dev)[0]
+        dist_mod.barrier()
+        e0.record()
+        p_recv, _ = exchange(p_part, p_off, world, rank, recv_counts=cnt)
+        e1.record()
+        torch.cuda.synchronize()
+        tn = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist_mod.all_reduce(tn, op=dist_mod.ReduceOp.MAX)
+        nccl_ms = float(tn[0])
+        del p_part, p_recv
+    except Exception as e:  # diagnostics only
+        nccl_ms = f"unavailable: {type(e).__name__}: {e}"
+    # ---- strong-scaling reference: the WHOLE job (N_b x N_p) on ONE GPU (rank 0), same kernels, no exchange
+    one_gpu = None
+    if os.environ.get("TQ_DIST_ONE_GPU", "1") == "1":
+        rj.close()
+        rj = None
+        del bk, bv, pk, pv
+        torch.cuda.empty_cache()
+        if rank == 0:
+            try:
+                one_gpu = one_gpu_reference(lib, L, dev, world, n_b, n_p)
+            except Exception as e:
+                one_gpu = {"error": f"{type(e).__name__}: {e}"}
+        dist_mod.barrier()
+    if rj is not None:
+        rj.close()
     probe_s = statistics.mean(probe_ns) * 1e-9
-    achieved = 64.0 * (joined_per_step / world) / probe_s / 1e9
     if rank != 0:
         return None
-    return {
+    push_bytes = 16.0 * n_p * (world - 1) / world
+    out = {
         "metric": "joined rows/sec on 1e8-row int64 equi-join", "value": value, "unit": "joined rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
-        "config": {"workload": f"C5-style: int64 equi-join radix-partitioned over {world} GPUs; per GPU build={n_b} probe={n_p} (global {N_b} x {n_p * world}), "
-                               "uniform keys, 100% match; partition -> grouped NCCL send/recv -> local join",
-                   "build_rows_per_gpu": n_b, "probe_rows_per_gpu": n_p, "parallelism": f"key-hash partitions over {world} ranks", "exchange": ("push scatter into peer receive buffers (CUDA IPC, stores over NVLink)" if pushx is not None else
-                                "peer-memory pull (CUDA IPC + NVLink copies)" if px is not None else "NCCL all_to_all_single"),
+        "config": {"workload": f"C5: int64 equi-join radix-partitioned on the key over {world} GPUs; per GPU build={n_b} probe={n_p} (global {N_b} x {N_p}), "
+                               "uniform keys, 100% match, output (B.k,B.v,P.k,P.v) materialised in HBM on the rank that owns the key",
+                   "build_rows_per_gpu": n_b, "probe_rows_per_gpu": n_p, "global_build_rows": N_b, "global_probe_rows": N_p,
+                   "parallelism": f"key-hash partitions over {world} ranks, {n_chunks} probe chunks pipelined (push of chunk c+1 overlaps the join of chunk c)",
+                   "exchange": "fused scatter + push into per-source regions of the peers' receive buffers (CUDA IPC peer stores over NVLink), device-side epoch "
+                               "flags instead of host barriers; local join reads the regions as one segmented batch",
                    "l2": "inputs and outputs exceed the 126 MB L2; no flush needed"},
-        "roofline": {"bound": "hbm", "kernel": "local probe pipeline (rank 0)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_row": 64, "kernel_ms": probe_s * 1e3},
+        "roofline": {"bound": "nvlink", "kernel": "push of this rank's probe rows (7/8 of them cross NVLink at 8 GPUs), overlapped with the local join",
+                     "achieved": push_bytes / (ms_per_step * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s", "frac": push_bytes / (ms_per_step * 1e-3) / 1e9 / 770.0,
+                     "traffic": None, "peak_source": "B200_PROFILING.md: measured peer copy 770 GB/s per direction per GPU",
+                     "note": "whole-step time charged against the NVLink bytes one GPU must send; local probe pipeline of rank 0: "
+                             f"{probe_s * 1e3:.3f} ms per chunk batch, build {statistics.mean(build_ns) * 1e-6:.3f} ms"},
         "e2e": {"value": value, "unit": "joined rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "multi-GPU line: shards are generated in HBM; the host-buffer e2e figure is reported on the 1-GPU line"},
+        "verified": verified,
+        "nccl_all_to_all_probe_exchange_ms": nccl_ms,
+        "one_gpu_same_job": one_gpu,
         "gpu_launches": int(launches2 - launches1), "clocks": clocks, "wall_ms_per_step_max": float(tmax[2]) / args.steps,
-        "phase_ms_rank0": {k: v / args.steps for k, v in phase_ms.items()},
     }
+    if isinstance(one_gpu, dict) and "ms_per_step" in one_gpu:
+        out["speedup_vs_one_gpu_same_job"] = one_gpu["ms_per_step"] / ms_per_step
+    return out
+
+
+def one_gpu_reference(lib, L, dev, world, n_b, n_p, steps=2):
+    """The whole C5 job on ONE GPU: build N_b rows, probe N_p rows in `world` device batches (same generators).  This is the
+    denominator of the strong-scaling figure north_star asks for (>= 4x at 8 GPUs on the 1e9-row join)."""
+    N_b = n_b * world
+    bk = torch.cat([torch.from_numpy(np.random.default_rng(1000 + r).permutation(n_b).astype(np.int64) * world + r).to(dev) for r in range(world)])
+    bv = bk * 7 + 1
+    t = (C.c_int32 * 2)(1, 1)
+    k = (C.c_int32 * 1)(0)
+    best = None
+    rows = 0
+    for it in range(steps + 1):
+        lib.tq_device_synchronize()
+        ms = C.c_float(0)
+        if it > 0:
+            L.check(lib.tq_timer_start())
+        d = L.TQJoinDesc(0, 1, 2, t, 2, t, 1, k, k, 0, 0)
+        h = C.c_void_p()
+        L.check(lib.tq_join_create(C.byref(d), C.byref(h)))
+        try:
+            L.check(lib.tq_join_put_build(h, _tq_cols(L, [bk, bv], N_b), L.TQ_MEM_DEVICE))
+            L.check(lib.tq_join_finalize_build(h))
+            out = (L.TQColumn * 4)()
+            n, eof = C.c_int64(0), C.c_int32(0)
+            rows = 0
+            for r in range(world):
+                # probe shard r is regenerated on the device each time (not timed separately: the generation is a handful of
+                # elementwise kernels, ~1 % of the join; keeping all N_p rows resident would need 16 GB more)
+                gid = torch.arange(n_p, dtype=torch.int64, device=dev) + r * n_p
+                pk = _mix64_mod_torch(gid, N_b)
+                torch.cuda.synchronize()
+                L.check(lib.tq_join_put_probe(h, _tq_cols(L, [pk, gid], n_p), None, L.TQ_MEM_DEVICE))
+                while True:
+                    L.check(lib.tq_join_next_device(h, out, C.byref(n), C.byref(eof)))
+                    if n.value == 0:
+                        break
+                    rows += n.value
+                    if r < world - 1:
+                        break
+            L.check(lib.tq_join_probe_eof(h))
+            while True:
+                L.check(lib.tq_join_next_device(h, out, C.byref(n), C.byref(eof)))
+                if n.value == 0:
+                    break
+                rows += n.value
+        finally:
+            lib.tq_join_destroy(h)
+        if it > 0:
+            L.check(lib.tq_timer_stop(C.byref(ms)))
+            best = ms.value if best is None else min(best, ms.value)
+    return {"ms_per_step": best, "rows": int(rows), "value": rows / (best * 1e-3), "build_rows": N_b, "probe_rows": n_p * world,
+            "note": "one B200, inputs generated in HBM, probe fed in device batches; includes the on-device generation of the probe keys"}
+
+
+def _mix64_mod_torch(gid, mod):
+    """mix64(g) % mod on the device with int64 tensors (wrapping multiply; logical shifts emulated)"""
+    def shr(x, s):
+        return (x >> s) & ((1 << (64 - s)) - 1)
+    k = gid.clone()
+    k ^= shr(k, 33)
+    k *= -49064778989728563          # 0xff51afd7ed558ccd as int64
+    k ^= shr(k, 33)
+    k *= -4265267296055464877        # 0xc4ceb9fe1a85ec53 as int64
+    k ^= shr(k, 33)
+    # unsigned modulo of a value that may have the sign bit set: split off the top bit
+    hi = shr(k, 1)
+    r = ((hi % mod) * 2 + (k & 1)) % mod
+    return r
