@@ -66,7 +66,10 @@ enum {
  *   data        = length * 8 bytes, little-endian values (NULL slots are don't-care)
  *   null_bitmap = ceil(length/8) bytes; bit (i&7) of byte (i>>3); 1 = NOT NULL.
  *                 May be NULL meaning "no NULLs". High bits of the last byte are ignored.
- * For outputs the caller provides both buffers (capacity >= the rows it asks for). */
+ * For outputs the caller provides both buffers (capacity >= the rows it asks for).
+ * TQ_MEM_DEVICE columns (not Go memory) have stricter rules, checked by the vectorized-builtin calls: data
+ * 16-byte aligned; null_bitmap 8-byte aligned and allocated as ((length + 63) / 64) * 8 bytes — the kernels move
+ * whole 64-row bitmap groups. */
 typedef struct tq_column {
   int64_t length;
   uint8_t *null_bitmap;
@@ -195,6 +198,42 @@ int32_t tq_vec_lt_plus_int(int64_t n, const tq_column *a, const tq_column *b,
 int32_t tq_vec_filter_int(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem);
 /* the same for an ETReal expression: toBool's zero test is types.RoundFloat(f) == 0, i.e. |f| < 0.5 (expression.go:296-307). */
 int32_t tq_vec_filter_real(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem);
+
+/* ---- fused Selection + Projection -------------------------------------
+ * One pass over a chunk for a whole list of filters and projection expressions: replaces
+ * SelectionExec.Next → expression.VectorizedFilter (executor/executor.go:463-499,
+ * expression/chunk_executor.go:196-245, VecEvalBool expression/expression.go:205-279) followed by
+ * ProjectionExec's per-expression VecEval (expression/chunk_executor.go evalOneVec).  The planner-side
+ * shim lowers the expression trees of fixed-width (ETInt / ETReal) builtins to a straight-line program:
+ * register k < n_inputs is input column k, register n_inputs + i is the result of ops[i]; an op may read
+ * only inputs and earlier results.  IN (a, l0, l1 …) lowers to a chain of EQ + LOGIC_OR, which has the
+ * same three-valued result as builtinInIntSig / builtinInRealSig.
+ *   TQ_X_FILTER a      : one CNF item of the filter list; op = 0 for an ETInt item, 1 for ETReal (toBool,
+ *                        expression.go:281-326).  A row whose item is zero (or, ETReal, NULL) leaves the
+ *                        evaluation set exactly as VecEvalBool narrows input.Sel(): overflow errors and
+ *                        division-by-zero warnings of LATER ops do not count for it.  An ETInt NULL keeps the
+ *                        row in the set (nulls[] quirk, expression.go:249-259) but it is not selected.
+ *   TQ_X_COMPACT       : the Selection → Projection boundary: only selected rows remain in the set.
+ * Outputs are dense (all n rows; values of unselected rows are unspecified); selected (n bytes, may be
+ * NULL when no FILTER op is present) is Go's []bool.  Errors are the first of the reference's overflow
+ * errors any in-set row raises (same codes as tq_vec_arith_*). */
+enum { TQ_X_CONST = 0, TQ_X_CMP_INT, TQ_X_CMP_REAL, TQ_X_ARITH_INT, TQ_X_ARITH_REAL, TQ_X_LOGIC, TQ_X_UNARY,
+       TQ_X_IF, TQ_X_IFNULL, TQ_X_FILTER, TQ_X_COMPACT };
+#define TQ_EXPR_MAX_INPUTS 8
+#define TQ_EXPR_MAX_OPS 32
+#define TQ_EXPR_MAX_OUTPUTS 4
+typedef struct tq_expr_op {
+  int32_t kind;        /* TQ_X_* */
+  int32_t op;          /* TQ_CMP_* / TQ_ARITH_* / TQ_LOGIC_* / TQ_UNARY_* for the kind; FILTER: 0 int, 1 real */
+  int32_t a, b, c;     /* operand registers (IF: a = condition, b = then, c = else) */
+  int32_t a_unsigned;  /* mysql.UnsignedFlag of operand a / b (CMP_INT, ARITH_INT, UNARY minus) */
+  int32_t b_unsigned;
+  int32_t is_null;     /* CONST: the constant is NULL */
+  uint64_t imm;        /* CONST: the 8 value bytes (int64 / uint64 / float64 bits) */
+} tq_expr_op;
+int32_t tq_expr_eval(int64_t n, int32_t n_inputs, const tq_column *inputs, int32_t n_ops,
+                     const tq_expr_op *ops, int32_t n_outputs, const int32_t *out_regs, tq_column *outs,
+                     uint8_t *selected, int64_t *div_by_zero_warnings, int32_t mem);
 
 /* ------------------------------------------------------------------ hash join
  * Replaces HashJoinExec (executor/join.go:31-146), hashRowContainer / rowHashMap

@@ -27,6 +27,11 @@ class TQJoinCond(C.Structure):
     _fields_ = [("op", C.c_int32), ("lhs_col", C.c_int32), ("rhs_col", C.c_int32), ("const_type", C.c_int32), ("const_bits", C.c_uint64)]
 
 
+class TQExprOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("c", C.c_int32),
+                ("a_unsigned", C.c_int32), ("b_unsigned", C.c_int32), ("is_null", C.c_int32), ("imm", C.c_uint64)]
+
+
 class TQAggFunc(C.Structure):
     _fields_ = [("func", C.c_int32), ("arg_col", C.c_int32)]
 
@@ -65,6 +70,7 @@ SYMBOLS = {
     "tq_vec_lt_plus_int": (_I32, [_I64, _COL, _COL, _COL, _COL, _I32]),
     "tq_vec_filter_int": (_I32, [_I64, _COL, _P, _I32]),
     "tq_vec_filter_real": (_I32, [_I64, _COL, _P, _I32]),
+    "tq_expr_eval": (_I32, [_I64, _I32, _COL, _I32, C.POINTER(TQExprOp), _I32, C.POINTER(_I32), _COL, _P, C.POINTER(_I64), _I32]),
     "tq_vec_in_real": (_I32, [_I64, _COL, _I32, _COL, _COL, _I32]),
     "tq_vec_in_string": (_I32, [_I64, _COL, _I32, _COL, _COL, _I32]),
     "tq_vec_if_string": (_I32, [_I64, _COL, _COL, _COL, _COL, _I32]),

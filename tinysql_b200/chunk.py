@@ -182,6 +182,8 @@ class DeviceColumn:
 
     def __init__(self, tp, n, with_bitmap=True):
         lib = L.load()
+        if tp in (FLOAT32, BYTES):
+            raise ValueError("DeviceColumn holds 8-byte slots (INT64 / UINT64 / FLOAT64); FLOAT32 and var-len columns enter through host chunks")
         self.tp, self.length = tp, int(n)
         self._data = C.c_void_p()
         L.check(lib.tq_device_alloc(max(self.length, 1) * 8, C.byref(self._data)))
@@ -196,7 +198,7 @@ class DeviceColumn:
         d = cls(col.tp, col.length, with_bitmap=col.bitmap is not None)
         lib = L.load()
         if col.length:
-            L.check(lib.tq_memcpy_h2d(d._data, col.values.ctypes.data, col.length * 8))
+            L.check(lib.tq_memcpy_h2d(d._data, col.values.ctypes.data, col.values.nbytes))
             if col.bitmap is not None:
                 L.check(lib.tq_memcpy_h2d(d._bm, col.bitmap.ctypes.data, bitmap_bytes(col.length)))
         return d
@@ -227,7 +229,7 @@ def device_to_host(tp, data_ptr, bm_ptr, n):
     lib = L.load()
     out = Column.empty(tp, n)
     if n:
-        L.check(lib.tq_memcpy_d2h(out.values.ctypes.data, data_ptr, n * 8))
+        L.check(lib.tq_memcpy_d2h(out.values.ctypes.data, data_ptr, out.values.nbytes))
         if bm_ptr:
             L.check(lib.tq_memcpy_d2h(out.bitmap.ctypes.data, bm_ptr, bitmap_bytes(n)))
         else:

@@ -4,6 +4,8 @@
 // No tensor cores: nothing here is a contraction.
 #include <cfloat>
 #include <cmath>
+#include <cstring>
+#include <cstdint>
 
 #include "common.cuh"
 
@@ -349,11 +351,149 @@ __global__ void k_filter_int(const uint64_t *a, const uint32_t *abm, uint8_t *se
   }
 }
 
+// ------------------------------------------------------------------ fused expression program
+// Selection + Projection in one pass over the chunk (executor/executor.go SelectionExec.Next :463-499 →
+// expression.VectorizedFilter chunk_executor.go:196-245, VecEvalBool expression.go:205-279; ProjectionExec →
+// evalOneVec chunk_executor.go).  The host lowers the expression trees to a straight-line register program over
+// the builtin functors above; every intermediate column the reference materialises (one chunk.Column per builtin,
+// globalColumnAllocator) stays in a per-row register file here, so the HBM traffic is the input columns once and
+// the output columns once.  Register k < n_in is input column k; register n_in + i is the result of op i.
+static constexpr int XP_MAX_IN = TQ_EXPR_MAX_INPUTS;
+static constexpr int XP_MAX_OPS = TQ_EXPR_MAX_OPS;
+static constexpr int XP_MAX_OUT = TQ_EXPR_MAX_OUTPUTS;
+static constexpr int XP_REGS = XP_MAX_IN + XP_MAX_OPS;
+
+struct XOp {
+  int8_t kind, op, a, b, c, flags;   // flags: 1 a_unsigned, 2 b_unsigned, 4 constant is NULL
+  uint64_t imm;
+};
+struct ExprProg {
+  int n_in, n_ops, n_out;
+  const uint64_t *in_d[XP_MAX_IN];
+  const uint32_t *in_bm[XP_MAX_IN];
+  uint64_t *out_d[XP_MAX_OUT];
+  uint32_t *out_bm[XP_MAX_OUT];
+  int out_reg[XP_MAX_OUT];
+  uint8_t *selected;
+  XOp ops[XP_MAX_OPS];
+};
+
+__global__ void __launch_bounds__(MAP_THREADS) k_expr_prog(const __grid_constant__ ExprProg P, int64_t n, unsigned *err,
+                                                            unsigned long long *counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_groups = (n + 63) >> 6;
+  unsigned my_err = 0, my_cnt = 0;
+  for (int64_t g = warp_global; g < n_groups; g += n_warps) {
+    const int64_t r0 = g * 64 + 2 * lane;
+    ulonglong2 iv[XP_MAX_IN];
+    uint32_t iw[XP_MAX_IN];
+#pragma unroll
+    for (int k = 0; k < XP_MAX_IN; k++) {
+      iv[k] = make_ulonglong2(0, 0);
+      iw[k] = 0xffffffffu;
+      if (k < P.n_in) {
+        if (r0 + 1 < n) iv[k] = tqd::ld_stream_u64x2(P.in_d[k] + r0);
+        else if (r0 < n) iv[k].x = P.in_d[k][r0];
+        if (P.in_bm[k]) iw[k] = P.in_bm[k][g * 2 + (lane >> 4)];
+      }
+    }
+    uint64_t o[2][XP_MAX_OUT];
+    unsigned bits[XP_MAX_OUT];
+    unsigned selbits = 0;
+#pragma unroll
+    for (int q = 0; q < XP_MAX_OUT; q++) bits[q] = 0;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const bool active = (r0 + e) < n;
+      uint64_t rv[XP_REGS];
+      uint64_t nn = 0;               // bit r: register r is not NULL
+#pragma unroll
+      for (int k = 0; k < XP_MAX_IN; k++) {
+        rv[k] = e ? iv[k].y : iv[k].x;
+        if (active && ((iw[k] >> ((2 * lane + e) & 31)) & 1u)) nn |= 1ull << k;
+      }
+      // alive: the row is still in VecEvalBool's sel slice (errors and warnings of later builtins count for it);
+      // sel: the row passes every filter seen so far.
+      bool alive = active, sel = active;
+      for (int i = 0; i < P.n_ops; i++) {
+        const XOp x = P.ops[i];
+        const uint64_t v2[2] = {rv[x.a], rv[x.b]};
+        const bool n2[2] = {(bool)((nn >> x.a) & 1), (bool)((nn >> x.b) & 1)};
+        uint64_t o1[1] = {0};
+        bool on[1] = {true};
+        unsigned e_ = 0, c_ = 0;
+        switch (x.kind) {
+          case TQ_X_CONST: o1[0] = x.imm; on[0] = !(x.flags & 4); break;
+          case TQ_X_CMP_INT: FCompareInt{x.op, (bool)(x.flags & 1), (bool)(x.flags & 2)}(v2, n2, o1, on, e_, c_, active); break;
+          case TQ_X_CMP_REAL: FCompareReal{x.op}(v2, n2, o1, on, e_, c_, active); break;
+          case TQ_X_ARITH_INT: FArithInt{x.op, (bool)(x.flags & 1), (bool)(x.flags & 2)}(v2, n2, o1, on, e_, c_, active); break;
+          case TQ_X_ARITH_REAL: FArithReal{x.op}(v2, n2, o1, on, e_, c_, active); break;
+          case TQ_X_LOGIC: FLogic{x.op}(v2, n2, o1, on, e_, c_, active); break;
+          case TQ_X_UNARY: {
+            const uint64_t v1[1] = {v2[0]};
+            const bool n1[1] = {n2[0]};
+            FUnary{x.op, (bool)(x.flags & 1)}(v1, n1, o1, on, e_, c_, active);
+            break;
+          }
+          case TQ_X_IF: {
+            const uint64_t v3[3] = {v2[0], v2[1], rv[x.c]};
+            const bool n3[3] = {n2[0], n2[1], (bool)((nn >> x.c) & 1)};
+            FIf{}(v3, n3, o1, on, e_, c_, active);
+            break;
+          }
+          case TQ_X_IFNULL: FIfNull{}(v2, n2, o1, on, e_, c_, active); break;
+          case TQ_X_FILTER: {                                          // VecEvalBool expression.go:231-268
+            const bool isnull = !n2[0];
+            const bool zero = x.op ? (fabs(__longlong_as_double((long long)v2[0])) < 0.5) : (v2[0] == 0);
+            if (isnull) { sel = false; if (x.op) alive = false; }       // ETInt NULL stays in sel, flagged in nulls[]
+            else if (zero) { sel = false; alive = false; }
+            break;
+          }
+          default: alive = sel; break;                                 // TQ_X_COMPACT: Selection hands only selected rows on
+        }
+        if (alive) { my_err |= e_; my_cnt += c_; }
+        rv[P.n_in + i] = o1[0];
+        nn = (nn & ~(1ull << (P.n_in + i))) | ((uint64_t)on[0] << (P.n_in + i));
+      }
+#pragma unroll
+      for (int q = 0; q < XP_MAX_OUT; q++) {
+        if (q < P.n_out) {
+          o[e][q] = rv[P.out_reg[q]];
+          bits[q] |= (active && ((nn >> P.out_reg[q]) & 1)) ? (1u << e) : 0u;
+        }
+      }
+      selbits |= sel ? (1u << e) : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < XP_MAX_OUT; q++) {
+      if (q < P.n_out) {
+        if (r0 + 1 < n) tqd::st_stream_u64x2(P.out_d[q] + r0, make_ulonglong2(o[0][q], o[1][q]));
+        else if (r0 < n) P.out_d[q][r0] = o[0][q];
+        const unsigned sh = bits[q] << ((2 * lane) & 31);
+        const unsigned lo = __reduce_or_sync(0xffffffffu, lane < 16 ? sh : 0u);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, lane >= 16 ? sh : 0u);
+        if (lane == 0) *reinterpret_cast<uint2 *>(P.out_bm[q] + g * 2) = make_uint2(lo, hi);
+      }
+    }
+    if (P.selected) {
+      if (r0 < n) P.selected[r0] = (uint8_t)(selbits & 1u);
+      if (r0 + 1 < n) P.selected[r0 + 1] = (uint8_t)(selbits >> 1);
+    }
+  }
+  if (my_err) atomicOr(err, my_err);
+  if (counter) {
+    unsigned c = __reduce_add_sync(0xffffffffu, my_cnt);
+    if (lane == 0 && c) atomicAdd(counter, (unsigned long long)c);
+  }
+}
+
 // ------------------------------------------------------------------ host driver
 // Device scratch for the host (cgo) path: a ring of two slab sets so the H2D copy of slab i+1, the
 // kernel of slab i and the D2H copy of slab i-1 overlap.
 struct SlabSet {
-  DevBuf in_d[3 + MAX_IN_LIST], in_bm[3 + MAX_IN_LIST], out_d[2], out_bm[2];
+  DevBuf in_d[3 + MAX_IN_LIST], in_bm[3 + MAX_IN_LIST], out_d[4], out_bm[4], sel_d;
   cudaEvent_t ev_h2d = nullptr, ev_k = nullptr, ev_d2h = nullptr;
   bool used = false;
 };
@@ -397,9 +537,15 @@ struct ErrOut {
 };
 
 // launch(ins, in_bms, outs, out_bms, rows, err*, counter*) enqueues the kernel on rt().compute.
+// RunSel: an optional n-byte selection vector next to the output columns; run_map points .dev at the device bytes
+// the current launch must write (the caller's own buffer in device mode, a per-slab buffer in host mode).
+struct RunSel {
+  uint8_t *user = nullptr;
+  uint8_t *dev = nullptr;
+};
 template <typename Launch>
 static int32_t run_map(int64_t n, int32_t mem, int nin, const tq_column *const *ins, int nout, tq_column *const *outs, Launch launch,
-                       ErrOut *eo) {
+                       ErrOut *eo, RunSel *rs = nullptr) {
   TQ_TRY(ensure_init());
   if (n < 0) { set_error("negative row count"); return TQ_ERR_INVALID_ARG; }
   for (int k = 0; k < nin; k++)
@@ -417,7 +563,20 @@ static int32_t run_map(int64_t n, int32_t mem, int nin, const tq_column *const *
   TQ_CUDA(cudaMemsetAsync(d_err, 0, 16, r.compute));
 
   if (mem == TQ_MEM_DEVICE) {
-    const uint64_t *id[3 + MAX_IN_LIST]; const uint32_t *ib[3 + MAX_IN_LIST]; uint64_t *od[2]; uint32_t *ob[2];
+    // device callers hand over raw HBM pointers: the kernels move two rows per lane (16-byte accesses) and whole 64-row
+    // bitmap groups (one 8-byte store / 4-byte loads), so the buffers must be aligned and the bitmaps padded as the header says
+    for (int k = 0; k < nin; k++)
+      if (((uintptr_t)ins[k]->data & 15) || ((uintptr_t)ins[k]->null_bitmap & 3)) {
+        set_error("device input column %d: data must be 16-byte aligned, null_bitmap 4-byte aligned and padded to ((n + 63) / 64) * 8 bytes", k);
+        return TQ_ERR_INVALID_ARG;
+      }
+    for (int q = 0; q < nout; q++)
+      if (((uintptr_t)outs[q]->data & 15) || ((uintptr_t)outs[q]->null_bitmap & 7)) {
+        set_error("device output column %d: data must be 16-byte aligned, null_bitmap 8-byte aligned and padded to ((n + 63) / 64) * 8 bytes", q);
+        return TQ_ERR_INVALID_ARG;
+      }
+    const uint64_t *id[3 + MAX_IN_LIST]; const uint32_t *ib[3 + MAX_IN_LIST]; uint64_t *od[4]; uint32_t *ob[4];
+    if (rs) rs->dev = rs->user;
     for (int k = 0; k < nin; k++) { id[k] = (const uint64_t *)ins[k]->data; ib[k] = (const uint32_t *)ins[k]->null_bitmap; }
     for (int q = 0; q < nout; q++) { od[q] = (uint64_t *)outs[q]->data; ob[q] = (uint32_t *)outs[q]->null_bitmap; }
     launch(id, ib, od, ob, n, d_err, d_cnt);
@@ -430,7 +589,7 @@ static int32_t run_map(int64_t n, int32_t mem, int nin, const tq_column *const *
     for (int64_t row0 = 0; row0 < n; row0 += SLAB_ROWS, slab++) {
       const int64_t rows = (n - row0 < SLAB_ROWS) ? (n - row0) : SLAB_ROWS;
       SlabSet &ss = sc.set[slab & 1];
-      const uint64_t *id[3 + MAX_IN_LIST]; const uint32_t *ib[3 + MAX_IN_LIST]; uint64_t *od[2]; uint32_t *ob[2];
+      const uint64_t *id[3 + MAX_IN_LIST]; const uint32_t *ib[3 + MAX_IN_LIST]; uint64_t *od[4]; uint32_t *ob[4];
       if (ss.used) TQ_CUDA(cudaStreamWaitEvent(r.h2d, ss.ev_d2h, 0));  // previous results of this set have left
       for (int k = 0; k < nin; k++) {
         TQ_TRY(ss.in_d[k].reserve((size_t)rows * 8));
@@ -449,6 +608,10 @@ static int32_t run_map(int64_t n, int32_t mem, int nin, const tq_column *const *
         od[q] = ss.out_d[q].as<uint64_t>();
         ob[q] = ss.out_bm[q].as<uint32_t>();
       }
+      if (rs && rs->user) {
+        TQ_TRY(ss.sel_d.reserve((size_t)rows));
+        rs->dev = ss.sel_d.as<uint8_t>();
+      }
       TQ_CUDA(cudaEventRecord(ss.ev_h2d, r.h2d));
       TQ_CUDA(cudaStreamWaitEvent(r.compute, ss.ev_h2d, 0));
       launch(id, ib, od, ob, rows, d_err, d_cnt);
@@ -460,6 +623,7 @@ static int32_t run_map(int64_t n, int32_t mem, int nin, const tq_column *const *
         TQ_CUDA(cudaMemcpyAsync(outs[q]->data + row0 * 8, od[q], (size_t)rows * 8, cudaMemcpyDeviceToHost, r.d2h));
         TQ_CUDA(cudaMemcpyAsync(outs[q]->null_bitmap + (row0 >> 3), ob[q], bitmap_bytes(rows), cudaMemcpyDeviceToHost, r.d2h));
       }
+      if (rs && rs->user) TQ_CUDA(cudaMemcpyAsync(rs->user + row0, rs->dev, (size_t)rows, cudaMemcpyDeviceToHost, r.d2h));
       TQ_CUDA(cudaEventRecord(ss.ev_d2h, r.d2h));
       ss.used = true;
     }
@@ -634,6 +798,69 @@ static int32_t vec_filter(int64_t n, const tq_column *a, uint8_t *selected, int3
   TQ_CUDA(cudaMemcpyAsync(selected, sel.p, (size_t)n, cudaMemcpyDeviceToHost, r.compute));
   TQ_CUDA(cudaStreamSynchronize(r.compute));
   return TQ_OK;
+}
+
+int32_t tq_expr_eval(int64_t n, int32_t n_inputs, const tq_column *inputs, int32_t n_ops, const tq_expr_op *ops, int32_t n_outputs,
+                     const int32_t *out_regs, tq_column *outs, uint8_t *selected, int64_t *div_by_zero_warnings, int32_t mem) {
+  if (n_inputs < 0 || n_inputs > XP_MAX_IN || n_ops < 0 || n_ops > XP_MAX_OPS || n_outputs < 0 || n_outputs > XP_MAX_OUT) {
+    set_error("expression program: at most %d inputs, %d ops, %d outputs", XP_MAX_IN, XP_MAX_OPS, XP_MAX_OUT);
+    return TQ_ERR_INVALID_ARG;
+  }
+  if ((n_inputs && !inputs) || (n_ops && !ops) || (n_outputs && (!out_regs || !outs)) || (!n_outputs && !selected)) {
+    set_error("expression program: missing argument");
+    return TQ_ERR_INVALID_ARG;
+  }
+  ExprProg P;
+  memset(&P, 0, sizeof(P));
+  P.n_in = n_inputs; P.n_ops = n_ops; P.n_out = n_outputs;
+  bool want_counter = false;
+  for (int i = 0; i < n_ops; i++) {
+    const tq_expr_op &s = ops[i];
+    const int avail = n_inputs + i;   // an op reads inputs and earlier results only
+    int arity = 2, lo = 0, hi = 0;
+    switch (s.kind) {
+      case TQ_X_CONST: arity = 0; break;
+      case TQ_X_CMP_INT: case TQ_X_CMP_REAL: lo = TQ_CMP_LT; hi = TQ_CMP_NE; break;
+      case TQ_X_ARITH_INT: lo = TQ_ARITH_PLUS; hi = TQ_ARITH_MUL; break;
+      case TQ_X_ARITH_REAL: lo = TQ_ARITH_PLUS; hi = TQ_ARITH_DIV; want_counter = true; break;
+      case TQ_X_LOGIC: lo = TQ_LOGIC_AND; hi = TQ_LOGIC_OR; break;
+      case TQ_X_UNARY: arity = 1; lo = TQ_UNARY_NOT_INT; hi = TQ_UNARY_ISNULL; break;
+      case TQ_X_IF: arity = 3; break;
+      case TQ_X_IFNULL: break;
+      case TQ_X_FILTER: arity = 1; lo = 0; hi = 1; break;
+      case TQ_X_COMPACT: arity = 0; break;
+      default: set_error("expression program: op %d has unknown kind %d", i, s.kind); return TQ_ERR_INVALID_ARG;
+    }
+    if (s.op < lo || s.op > hi) { set_error("expression program: op %d (kind %d) has bad operator %d", i, s.kind, s.op); return TQ_ERR_INVALID_ARG; }
+    const int regs[3] = {s.a, s.b, s.c};
+    for (int k = 0; k < arity; k++)
+      if (regs[k] < 0 || regs[k] >= avail) { set_error("expression program: op %d reads register %d before it is written", i, regs[k]); return TQ_ERR_INVALID_ARG; }
+    XOp &x = P.ops[i];
+    x.kind = (int8_t)s.kind; x.op = (int8_t)s.op;
+    x.a = (int8_t)(arity > 0 ? s.a : 0); x.b = (int8_t)(arity > 1 ? s.b : 0); x.c = (int8_t)(arity > 2 ? s.c : 0);
+    x.flags = (int8_t)((s.a_unsigned ? 1 : 0) | (s.b_unsigned ? 2 : 0) | (s.is_null ? 4 : 0));
+    x.imm = s.imm;
+  }
+  const tq_column *ins[XP_MAX_IN]; tq_column *op[XP_MAX_OUT];
+  for (int k = 0; k < n_inputs; k++) ins[k] = &inputs[k];
+  for (int q = 0; q < n_outputs; q++) {
+    if (out_regs[q] < 0 || out_regs[q] >= n_inputs + n_ops) { set_error("expression program: output %d names register %d", q, out_regs[q]); return TQ_ERR_INVALID_ARG; }
+    P.out_reg[q] = out_regs[q];
+    op[q] = &outs[q];
+  }
+  RunSel rs;
+  rs.user = selected;
+  auto launch = [&](const uint64_t **id, const uint32_t **ib, uint64_t **od, uint32_t **ob, int64_t rows, unsigned *d_err,
+                    unsigned long long *d_cnt) {
+    for (int k = 0; k < n_inputs; k++) { P.in_d[k] = id[k]; P.in_bm[k] = ib[k]; }
+    for (int q = 0; q < n_outputs; q++) { P.out_d[q] = od[q]; P.out_bm[q] = ob[q]; }
+    P.selected = rs.dev;
+    k_expr_prog<<<map_grid(rows), MAP_THREADS, 0, rt().compute>>>(P, rows, d_err, want_counter ? d_cnt : nullptr);
+  };
+  ErrOut eo;
+  TQ_TRY(run_map(n, mem, n_inputs, ins, n_outputs, op, launch, &eo, &rs));
+  if (div_by_zero_warnings) *div_by_zero_warnings = (int64_t)eo.counter;
+  return err_to_status(eo.err, "expression program");
 }
 
 }  // extern "C"

@@ -344,7 +344,7 @@ struct BuildRow {
 __device__ __forceinline__ BuildRow build_row_of(const ProbeParams &p, bool want, uint32_t off, bool have01 = false, uint64_t w0 = 0, uint64_t w1 = 0) {
   BuildRow b;
   b.row = nullptr;
-  b.mask = p.def_mask;   // a miss row carries defaultInner
+  b.mask = want ? p.def_mask : 0u;   // a miss row carries defaultInner; lanes past the tile's rows contribute no bits
   b.have01 = have01;
   b.w0 = w0;
   b.w1 = w1;
@@ -2104,6 +2104,12 @@ static int32_t launch_probe_stream(tq_join *j, const ProbeParams &p, const std::
   TQ_TRY(j->pos_valid[slot].reserve((size_t)(n_words_max + 2) * 4));
   TQ_TRY(j->hole_pos[slot].reserve((size_t)(32 * (P + 2)) * 4));   // at most 31 pad slots per partition
   TQ_TRY(j->hole_src[slot].reserve((size_t)(32 * (P + 2)) * 4));
+  static const bool poison = [] { const char *e = getenv("TQ_JOIN_DEBUG_POISON"); return e && e[0] == '1'; }();
+  if (poison) {  // diagnostics: stale bytes become recognisable (0xEE.. = slab never written, 0xDD.. = result slot never written)
+    TQ_CUDA(cudaMemsetAsync(j->part_aos[slot].p, 0xEE, (size_t)slab * P * NP * 8, s));
+    for (int c = 0; c < NP; c++) TQ_CUDA(cudaMemsetAsync(p.out_probe[c].data, 0xDD, (size_t)alloc_rows * 8, s));
+    for (int c = 0; c < NB; c++) TQ_CUDA(cudaMemsetAsync(p.out_build[c].data, 0xDD, (size_t)alloc_rows * 8, s));
+  }
   k_init_slabs<<<(P + 1 + 255) / 256, 256, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), P, (uint32_t)slab, 0u);
   count_launch();
   ScatterAosParams q{};

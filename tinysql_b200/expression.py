@@ -172,3 +172,152 @@ def vec_ifnull_string(a, b):
     """builtinIfNullStringSig.vecEvalString — expression/builtin_control_vec_generated.go:81-112"""
     ta, tb = a.tq(), b.tq()
     return _pick_string(L.load().tq_vec_ifnull_string, a.length, int(a.data.size + b.data.size), C.byref(ta), C.byref(tb))
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused Selection + Projection: expression trees lowered to one tq_expr_eval program
+# ---------------------------------------------------------------------------------------------
+X_CONST, X_CMP_INT, X_CMP_REAL, X_ARITH_INT, X_ARITH_REAL, X_LOGIC, X_UNARY, X_IF, X_IFNULL, X_FILTER, X_COMPACT = range(11)
+MAX_PROGRAM_INPUTS, MAX_PROGRAM_OPS, MAX_PROGRAM_OUTPUTS = 8, 32, 4
+
+
+class Expr:
+    """expression.Expression (expression/expression.go:47-113) for the fixed-width builtins: a tree of Col / Const / Func
+    nodes whose eval type is 'int', 'uint' (ETInt with mysql.UnsignedFlag) or 'real' (ETReal)."""
+    tp = "int"
+
+
+class Col(Expr):
+    """expression.Column (expression/column.go): the idx-th column of the input chunk."""
+
+    def __init__(self, idx, tp="int"):
+        self.idx, self.tp = idx, tp
+
+
+class Const(Expr):
+    """expression.Constant (expression/constant.go); value None is NULL."""
+
+    def __init__(self, value, tp="int"):
+        self.value, self.tp = value, tp
+
+
+_CMP = {"lt": LT, "le": LE, "gt": GT, "ge": GE, "eq": EQ, "ne": NE}
+_ARITH = {"plus": PLUS, "minus": MINUS, "mul": MUL, "div": DIV}
+
+
+class Func(Expr):
+    """expression.ScalarFunction (expression/scalar_function.go) over the builtins this library implements:
+    lt le gt ge eq ne | plus minus mul div | and or | not neg isnull | if ifnull | in."""
+
+    def __init__(self, name, *args):
+        self.name, self.args = name, list(args)
+        real = any(a.tp == "real" for a in args)
+        if name in _CMP or name in ("and", "or", "not", "isnull", "in"):
+            self.tp = "int"
+        elif name in _ARITH:
+            self.tp = "real" if real else ("uint" if any(a.tp == "uint" for a in args) else "int")
+            if name == "div" and not real:
+                raise ValueError("integer division (DIV / decimal '/') is outside the vectorized builtins of the hot path")
+        elif name == "neg":
+            self.tp = "real" if real else "int"
+        elif name == "if":
+            self.tp = args[1].tp
+        elif name == "ifnull":
+            self.tp = args[0].tp
+        else:
+            raise ValueError(f"unknown builtin {name}")
+
+
+class ExprProgram:
+    """Lowers filters (a CNF list, expression.CNFExprs) and projection expressions to the register program of
+    tq_expr_eval.  Common sub-trees are evaluated once (the reference re-evaluates them per expression)."""
+
+    def __init__(self, n_inputs, filters=(), projections=()):
+        if n_inputs > MAX_PROGRAM_INPUTS:
+            raise ValueError("too many input columns for one program")
+        self.n_inputs = n_inputs
+        self.ops = []
+        self.out_regs = []
+        self.out_types = []
+        self._memo = {}
+        self.has_filter = bool(filters)
+        for f in filters:
+            r = self._lower(f)
+            self._emit(X_FILTER, 1 if f.tp == "real" else 0, r)
+            self._memo.clear()   # later items are evaluated on the narrowed row set; do not reuse earlier (wider) error scopes
+        if filters and projections:
+            self._emit(X_COMPACT, 0)
+        for e in projections:
+            self.out_regs.append(self._lower(e))
+            self.out_types.append({"int": INT64, "uint": UINT64, "real": FLOAT64}[e.tp])
+        if len(self.ops) > MAX_PROGRAM_OPS or len(self.out_regs) > MAX_PROGRAM_OUTPUTS:
+            raise ValueError("expression program too long")
+
+    def _emit(self, kind, op, a=0, b=0, c=0, ua=0, ub=0, is_null=0, imm=0):
+        self.ops.append(L.TQExprOp(kind, op, a, b, c, ua, ub, is_null, imm))
+        return self.n_inputs + len(self.ops) - 1
+
+    def _key(self, e):
+        if isinstance(e, Col):
+            return ("c", e.idx)
+        if isinstance(e, Const):
+            return ("k", e.tp, e.value)
+        return ("f", e.name) + tuple(self._key(a) for a in e.args)
+
+    def _lower(self, e):
+        if isinstance(e, Col):
+            return e.idx
+        k = self._key(e)
+        if k in self._memo:
+            return self._memo[k]
+        if isinstance(e, Const):
+            if e.value is None:
+                r = self._emit(X_CONST, 0, is_null=1)
+            elif e.tp == "real":
+                r = self._emit(X_CONST, 0, imm=int(np.float64(e.value).view(np.uint64)))
+            else:
+                r = self._emit(X_CONST, 0, imm=int(e.value) & 0xFFFFFFFFFFFFFFFF)
+        elif e.name == "in":
+            # a IN (l0, l1, …) == (a = l0) OR (a = l1) OR …  — the same three-valued result as builtinIn{Int,Real}Sig
+            acc = None
+            for item in e.args[1:]:
+                eq = self._lower(Func("eq", e.args[0], item))
+                acc = eq if acc is None else self._emit(X_LOGIC, OR, acc, eq)
+            r = acc
+        else:
+            regs = [self._lower(a) for a in e.args]
+            tps = [a.tp for a in e.args]
+            real = "real" in tps
+            ua = 1 if tps[0] == "uint" else 0
+            ub = 1 if len(tps) > 1 and tps[1] == "uint" else 0
+            n = e.name
+            if n in _CMP:
+                r = self._emit(X_CMP_REAL if real else X_CMP_INT, _CMP[n], regs[0], regs[1], ua=ua, ub=ub)
+            elif n in _ARITH:
+                r = self._emit(X_ARITH_REAL if real else X_ARITH_INT, _ARITH[n], regs[0], regs[1], ua=ua, ub=ub)
+            elif n in ("and", "or"):
+                r = self._emit(X_LOGIC, AND if n == "and" else OR, regs[0], regs[1])
+            elif n == "not":
+                r = self._emit(X_UNARY, NOT_REAL if real else NOT_INT, regs[0])
+            elif n == "neg":
+                r = self._emit(X_UNARY, MINUS_REAL if real else MINUS_INT, regs[0], ua=ua)
+            elif n == "isnull":
+                r = self._emit(X_UNARY, ISNULL, regs[0])
+            elif n == "if":
+                r = self._emit(X_IF, 0, regs[0], regs[1], regs[2])
+            else:
+                r = self._emit(X_IFNULL, 0, regs[0], regs[1])
+        self._memo[k] = r
+        return r
+
+    def run(self, cols):
+        """-> (projection columns, selected uint8[n] or None, division-by-zero warnings)"""
+        n = cols[0].length if cols else 0
+        outs = [Column.empty(tp, n) for tp in self.out_types]
+        sel = np.zeros(max(n, 1), dtype=np.uint8) if (self.has_filter or not outs) else None
+        ops = (L.TQExprOp * max(len(self.ops), 1))(*self.ops)
+        regs = (C.c_int32 * max(len(outs), 1))(*self.out_regs)
+        dz = C.c_int64(0)
+        L.check(L.load().tq_expr_eval(n, len(cols), tq_array(cols), len(self.ops), ops, len(outs), regs, tq_array(outs),
+                                      sel.ctypes.data if sel is not None else None, C.byref(dz), L.TQ_MEM_HOST))
+        return outs, (sel[:n] if sel is not None else None), dz.value
