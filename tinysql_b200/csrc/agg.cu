@@ -282,6 +282,7 @@ struct AggFastParams {
   uint32_t *deferred;
   unsigned *n_deferred;
   int64_t n;
+  int l2_hint;
 };
 // slow path of the fast kernel, one lane at a time (rare once the groups exist): walk the buckets with volatile loads, claim an
 // empty slot with a CAS.  Returns the slot, or ~0 when the row was deferred (table at its load limit: the host grows it).
@@ -317,6 +318,7 @@ defer:
 template <int NS>
 __global__ void __launch_bounds__(256) k_agg_update_fast(const AggFastParams p) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint64_t pol = tqd::l2_policy_evict_last();  // the table outlives the input in L2
   for (int64_t blk = (int64_t)blockIdx.x * blockDim.x; blk < p.n; blk += stride * AF_ROWS) {
     __syncwarp();
     const int64_t base = blk + threadIdx.x;
@@ -338,8 +340,13 @@ __global__ void __launch_bounds__(256) k_agg_update_fast(const AggFastParams p) 
       x[k] = make_ulonglong2(AGG_EMPTY, AGG_EMPTY);
       y[k] = x[k];
       if (live[k]) {
-        x[k] = *reinterpret_cast<const ulonglong2 *>(p.keys + b[k]);
-        y[k] = *reinterpret_cast<const ulonglong2 *>(p.keys + b[k] + 2);
+        if (p.l2_hint) {
+          x[k] = tqd::ld_hint_u64x2(p.keys + b[k], pol);
+          y[k] = tqd::ld_hint_u64x2(p.keys + b[k] + 2, pol);
+        } else {
+          x[k] = *reinterpret_cast<const ulonglong2 *>(p.keys + b[k]);
+          y[k] = *reinterpret_cast<const ulonglong2 *>(p.keys + b[k] + 2);
+        }
       }
     }
     bool any_slow = false;
@@ -361,9 +368,15 @@ __global__ void __launch_bounds__(256) k_agg_update_fast(const AggFastParams p) 
     for (int k = 0; k < AF_ROWS; k++) {
       if (slot[k] == ~0ull) continue;   // past the end, or deferred
       uint64_t *sl = p.tbl + slot[k] * p.stride;
+      if (p.l2_hint) {
 #pragma unroll
-      for (int f = 0; f < NS; f++) atomicAdd(reinterpret_cast<double *>(sl + p.sum_w[f]), __longlong_as_double((long long)arg[k][f]));
-      for (int f = 0; f < p.n_cnt; f++) atomicAdd(reinterpret_cast<unsigned long long *>(sl + p.cnt_w[f]), 1ull);
+        for (int f = 0; f < NS; f++) tqd::red_add_f64_hint(reinterpret_cast<double *>(sl + p.sum_w[f]), __longlong_as_double((long long)arg[k][f]), pol);
+        for (int f = 0; f < p.n_cnt; f++) tqd::red_add_u64_hint(reinterpret_cast<unsigned long long *>(sl + p.cnt_w[f]), 1ull, pol);
+      } else {
+#pragma unroll
+        for (int f = 0; f < NS; f++) atomicAdd(reinterpret_cast<double *>(sl + p.sum_w[f]), __longlong_as_double((long long)arg[k][f]));
+        for (int f = 0; f < p.n_cnt; f++) atomicAdd(reinterpret_cast<unsigned long long *>(sl + p.cnt_w[f]), 1ull);
+      }
     }
   }
 }
@@ -965,6 +978,7 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
       fp.key = cols[p.key_col].data;
       fp.keys = p.keys; fp.tbl = p.tbl; fp.stride = p.stride; fp.mask = p.mask; fp.n_slots = p.n_slots; fp.side_used = p.side_used;
       fp.n_used = p.n_used; fp.limit = p.limit; fp.deferred = p.deferred; fp.n_deferred = p.n_deferred; fp.n = todo;
+      { static const bool no_hint = [] { const char *e = getenv("TQ_AGG_NO_L2_HINT"); return e && e[0] == '1'; }(); fp.l2_hint = no_hint ? 0 : 1; }
       const int64_t blocks = (todo + 256 * AF_ROWS - 1) / (256 * AF_ROWS);
       const int64_t cap = (int64_t)r.sm_count * 8;
       const int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);

@@ -362,6 +362,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, OCC) k_probe_pos(const ProbePos
   extern __shared__ __align__(128) unsigned char s_raw[];
   uint64_t *s_tile = reinterpret_cast<uint64_t *>(s_raw);  // [PP_STAGES][PP_TILE][NP]
   __shared__ __align__(8) uint64_t s_full[PP_STAGES], s_empty[PP_STAGES];
+  __shared__ uint64_t s_sink[CW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t part = blockIdx.x / p.split, sub = blockIdx.x % p.split;
   const int64_t p_lo = p.lo[part];
@@ -441,15 +442,21 @@ __global__ void __launch_bounds__((CW + 1) * 32, OCC) k_probe_pos(const ProbePos
       }
     }
     // The stage may be refilled (a TMA write) as soon as every warp has released it, so the values must have LEFT shared
-    // memory first: an issued LDS is not a completed one (the barrier arrive runs in the SYNCS unit and can overtake loads
-    // still queued in the LSU) — the empty asm makes every loaded word a register operand, i.e. waits for the loads.
+    // memory first.  An issued LDS is not a completed one: SASS showed LDS.128 x4, WARPSYNC, SYNCS.ARRIVE with no scoreboard
+    // wait in between, and on a B200 the refill then tore rows (first 16 bytes of one tile, last 16 of another, ~50 rows in
+    // half the runs of a 1.5M-row probe).  The register scoreboard is per warp, so ONE instruction that reads every loaded
+    // register waits for the whole warp's loads: lane 0 stores their XOR to a sink word before it arrives on the barrier.
+    uint64_t dep = 0;
 #pragma unroll
     for (int k = 0; k < R; k++) {
 #pragma unroll
-      for (int c = 0; c < NP; c++) asm volatile("" ::"l"(v[k][c]) : "memory");
+      for (int c = 0; c < NP; c++) dep ^= v[k][c];
     }
     __syncwarp();
-    if (lane == 0 && !p.dbg_late_release) mbar_arrive(&s_empty[s]);  // the stage can be refilled while this warp probes
+    if (lane == 0) {
+      *reinterpret_cast<volatile uint64_t *>(&s_sink[warp]) = dep;
+      if (!p.dbg_late_release) mbar_arrive(&s_empty[s]);  // the stage can be refilled while this warp probes
+    }
     uint64_t key[R];
     uint32_t loc[R];
     bool inb[R];
