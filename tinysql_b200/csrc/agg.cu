@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) k_agg_update(const AggParams p) {
           if (p.side_used[1] == 0) p.side_used[1] = 1;
         } else {
           // ---- getPartialResult (aggregate.go:396-410): find or claim the group's slot, bucket by bucket
-          uint64_t b = (tqd::hash_key(key) & p.mask) & ~3ull;
+          uint64_t b = (tqd::mix64(key) & p.mask) & ~3ull;
           bool defer = false, found = false;
           for (uint64_t buckets = 0; !found && !defer; buckets++) {
             if (buckets * 4 > p.mask) { defer = true; break; }  // table full (cannot happen below `limit`)
@@ -259,125 +259,6 @@ __global__ void __launch_bounds__(256) k_agg_update(const AggParams p) {
       }
     }
     agg_apply(p, slot, r);
-  }
-}
-
-// ---- fast path of the common analytic shape: ONE integer GROUP BY column without NULLs, aggregates drawn from
-// COUNT(*) / COUNT(not-null col) / SUM(double NOT NULL col) / FIRSTROW(key).  Same table, same state layout as k_agg_update (the
-// collect / merge / rehash kernels do not care which kernel filled it), but: four rows per thread with their key and bucket
-// loads issued back to back (the generic kernel handled one row per thread per iteration — a dependent DRAM + L2 round
-// trip each), the one-multiply table hash, no per-row walk over a function descriptor table, no NULL bookkeeping.
-static constexpr int AF_ROWS = 4;
-struct AggFastParams {
-  const uint64_t *key;
-  int n_sum, n_cnt;
-  const uint64_t *sum_arg[4];
-  int sum_w[4], cnt_w[4];
-  uint64_t *keys, *tbl;
-  int stride;
-  uint64_t mask, n_slots;
-  uint32_t *side_used;
-  unsigned long long *n_used;
-  uint64_t limit;
-  uint32_t *deferred;
-  unsigned *n_deferred;
-  int64_t n;
-  int l2_hint;
-};
-// slow path of the fast kernel, one lane at a time (rare once the groups exist): walk the buckets with volatile loads, claim an
-// empty slot with a CAS.  Returns the slot, or ~0 when the row was deferred (table at its load limit: the host grows it).
-__device__ __noinline__ uint64_t agg_fast_find_or_insert(const AggFastParams &p, uint64_t key, int64_t r) {
-  if (key == AGG_EMPTY) {
-    if (p.side_used[1] == 0) p.side_used[1] = 1;
-    return p.n_slots + 1;
-  }
-  uint64_t bb = (tqd::hash_key(key) & p.mask) & ~3ull;
-  for (uint64_t buckets = 0; buckets * 4 <= p.mask; buckets++) {
-    unsigned long long kk[4];
-    ld_bucket(p.keys, bb, kk);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (kk[j] == key) return bb + j;
-      if (kk[j] == AGG_EMPTY) {
-        if (*reinterpret_cast<volatile unsigned long long *>(p.n_used) >= p.limit) goto defer;
-        const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&p.keys[bb + j]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
-        if (prev == AGG_EMPTY) { atomicAdd(p.n_used, 1ull); return bb + j; }
-        if (prev == key) return bb + j;
-      }
-    }
-    bb = (bb + 4) & p.mask;
-  }
-defer:
-  p.deferred[atomicAdd(p.n_deferred, 1u)] = (uint32_t)r;
-  return ~0ull;
-}
-
-// NS = number of SUM(double) aggregates (0..2): their arguments are loaded with the keys, before anything diverges.
-// The loop bound is CTA-uniform and every iteration starts with the warp converged: a first version that let lanes `continue`
-// individually ran the whole loop with ~10 of 32 lanes active (ncu: 3x the instructions, every load split into partial requests).
-template <int NS>
-__global__ void __launch_bounds__(256) k_agg_update_fast(const AggFastParams p) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const uint64_t pol = tqd::l2_policy_evict_last();  // the table outlives the input in L2
-  for (int64_t blk = (int64_t)blockIdx.x * blockDim.x; blk < p.n; blk += stride * AF_ROWS) {
-    __syncwarp();
-    const int64_t base = blk + threadIdx.x;
-    uint64_t key[AF_ROWS], b[AF_ROWS], slot[AF_ROWS];
-    uint64_t arg[AF_ROWS][NS > 0 ? NS : 1];
-    bool live[AF_ROWS];
-#pragma unroll
-    for (int k = 0; k < AF_ROWS; k++) {  // rows base, base + stride, ...: every load of the warp is one contiguous 256-byte run
-      const int64_t r = base + k * stride;
-      live[k] = r < p.n;
-      key[k] = live[k] ? tqd::ld_stream_u64(p.key + r) : AGG_EMPTY;
-#pragma unroll
-      for (int f = 0; f < NS; f++) arg[k][f] = live[k] ? tqd::ld_stream_u64(p.sum_arg[f] + r) : 0;
-      b[k] = (tqd::hash_key(key[k]) & p.mask) & ~3ull;
-    }
-    ulonglong2 x[AF_ROWS], y[AF_ROWS];
-#pragma unroll
-    for (int k = 0; k < AF_ROWS; k++) {  // one sector = four candidate slots; keys never change once written, so a cached copy is safe
-      x[k] = make_ulonglong2(AGG_EMPTY, AGG_EMPTY);
-      y[k] = x[k];
-      if (live[k]) {
-        if (p.l2_hint) {
-          x[k] = tqd::ld_hint_u64x2(p.keys + b[k], pol);
-          y[k] = tqd::ld_hint_u64x2(p.keys + b[k] + 2, pol);
-        } else {
-          x[k] = *reinterpret_cast<const ulonglong2 *>(p.keys + b[k]);
-          y[k] = *reinterpret_cast<const ulonglong2 *>(p.keys + b[k] + 2);
-        }
-      }
-    }
-    bool any_slow = false;
-#pragma unroll
-    for (int k = 0; k < AF_ROWS; k++) {  // branch-free resolve of the common case: the group exists in its home bucket
-      const uint64_t kk = key[k];
-      const bool ok = live[k] && kk != AGG_EMPTY;
-      const int j = (x[k].x == kk) ? 0 : (x[k].y == kk) ? 1 : (y[k].x == kk) ? 2 : (y[k].y == kk) ? 3 : -1;
-      slot[k] = (ok && j >= 0) ? b[k] + (uint64_t)j : ~0ull;
-      any_slow |= live[k] && slot[k] == ~0ull;
-    }
-    if (any_slow) {
-#pragma unroll
-      for (int k = 0; k < AF_ROWS; k++)
-        if (live[k] && slot[k] == ~0ull) slot[k] = agg_fast_find_or_insert(p, key[k], base + k * stride);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < AF_ROWS; k++) {
-      if (slot[k] == ~0ull) continue;   // past the end, or deferred
-      uint64_t *sl = p.tbl + slot[k] * p.stride;
-      if (p.l2_hint) {
-#pragma unroll
-        for (int f = 0; f < NS; f++) tqd::red_add_f64_hint(reinterpret_cast<double *>(sl + p.sum_w[f]), __longlong_as_double((long long)arg[k][f]), pol);
-        for (int f = 0; f < p.n_cnt; f++) tqd::red_add_u64_hint(reinterpret_cast<unsigned long long *>(sl + p.cnt_w[f]), 1ull, pol);
-      } else {
-#pragma unroll
-        for (int f = 0; f < NS; f++) atomicAdd(reinterpret_cast<double *>(sl + p.sum_w[f]), __longlong_as_double((long long)arg[k][f]));
-        for (int f = 0; f < p.n_cnt; f++) atomicAdd(reinterpret_cast<unsigned long long *>(sl + p.cnt_w[f]), 1ull);
-      }
-    }
   }
 }
 
@@ -535,7 +416,7 @@ __global__ void __launch_bounds__(256) k_agg_rehash(const uint64_t *old_keys, co
     else {
       const uint64_t key = old_keys[i];
       if (key == AGG_EMPTY) continue;
-      uint64_t idx = (tqd::hash_key(key) & new_mask) & ~3ull;  // same bucket-aligned probe order as the update kernels
+      uint64_t idx = (tqd::mix64(key) & new_mask) & ~3ull;  // same bucket-aligned probe order as the update kernels
       for (;;) {
         const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&new_keys[idx]), (unsigned long long)AGG_EMPTY, (unsigned long long)key);
         if (prev == AGG_EMPTY) break;
@@ -958,36 +839,7 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
     p.row_list = row_list;
     p.n = todo;
     TQ_CUDA(cudaMemsetAsync(meta32 + 2, 0, 4, s));
-    // ---- fast path (first pass over a raw batch): one NOT NULL integer GROUP BY column; COUNT / SUM(double, declared NOT NULL) /
-    // FIRSTROW(key) only
-    static const bool no_fast = [] { const char *e = getenv("TQ_AGG_NO_FAST"); return e && e[0] == '1'; }();
-    bool fast = !no_fast && !merge && !row_list && a->n_group_by == 1 && p.key_col >= 0 && cols[p.key_col].bm == nullptr && a->types[a->key_col] != TQ_TYPE_FLOAT64 &&
-                a->in_kind[a->key_col] == 0;
-    AggFastParams fp{};
-    for (int i = 0; fast && i < a->n_funcs_all; i++) {
-      const AggFuncDev &f = p.f[i];
-      if (f.key_passthrough) continue;
-      const bool arg_plain = f.arg_col < 0 || cols[f.arg_col].bm == nullptr;
-      if (f.func == TQ_AGG_COUNT && arg_plain && fp.n_cnt < 4) fp.cnt_w[fp.n_cnt++] = f.w0;
-      else if (f.func == TQ_AGG_SUM && f.arg_col >= 0 && f.arg_type == TQ_TYPE_FLOAT64 && f.w1 < 0 && arg_plain && fp.n_sum < 2) {
-        fp.sum_arg[fp.n_sum] = cols[f.arg_col].data;
-        fp.sum_w[fp.n_sum++] = f.w0;
-      } else fast = false;
-    }
-    if (fast) {
-      fp.key = cols[p.key_col].data;
-      fp.keys = p.keys; fp.tbl = p.tbl; fp.stride = p.stride; fp.mask = p.mask; fp.n_slots = p.n_slots; fp.side_used = p.side_used;
-      fp.n_used = p.n_used; fp.limit = p.limit; fp.deferred = p.deferred; fp.n_deferred = p.n_deferred; fp.n = todo;
-      { static const bool no_hint = [] { const char *e = getenv("TQ_AGG_NO_L2_HINT"); return e && e[0] == '1'; }(); fp.l2_hint = no_hint ? 0 : 1; }
-      const int64_t blocks = (todo + 256 * AF_ROWS - 1) / (256 * AF_ROWS);
-      const int64_t cap = (int64_t)r.sm_count * 8;
-      const int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
-      if (fp.n_sum == 0) k_agg_update_fast<0><<<grid, 256, 0, s>>>(fp);
-      else if (fp.n_sum == 1) k_agg_update_fast<1><<<grid, 256, 0, s>>>(fp);
-      else k_agg_update_fast<2><<<grid, 256, 0, s>>>(fp);
-    } else {
-      k_agg_update<<<agg_grid(todo), 256, 0, s>>>(p);
-    }
+    k_agg_update<<<agg_grid(todo), 256, 0, s>>>(p);
     count_launch();
     a->launches++;
     TQ_TRY(check_launch("k_agg_update"));

@@ -151,24 +151,5 @@ __device__ __forceinline__ void st_stream_u64(void *p, uint64_t v) {
   asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// L2 eviction-priority hints (createpolicy + .L2::cache_hint): a hash table that must stay L2-resident while gigabytes of
-// single-use input stream past it is accessed with evict_last.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ ulonglong2 ld_hint_u64x2(const void *a, uint64_t pol) {
-  ulonglong2 r;
-  asm volatile("ld.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(a), "l"(pol));
-  return r;
-}
-__device__ __forceinline__ void red_add_f64_hint(double *a, double v, uint64_t pol) {
-  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void red_add_u64_hint(unsigned long long *a, unsigned long long v, uint64_t pol) {
-  asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(a), "l"(v), "l"(pol) : "memory");
-}
-
 }  // namespace tqd
 #endif
