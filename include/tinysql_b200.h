@@ -99,6 +99,8 @@ int32_t tq_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 int32_t tq_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes); /* e.g. keep rows lent by *_next_device / export_partial */
 int32_t tq_memset_device(void *dst_dev, int32_t byte_value, size_t bytes);
 int32_t tq_device_synchronize(void);
+/* waits for the library's compute stream only (kernels of the operators): copies and peer pushes on the other streams go on */
+int32_t tq_compute_synchronize(void);
 
 /* Device-side timing on the library's compute stream (the stream every kernel of
  * this library is launched on).  tq_timer_stop returns elapsed milliseconds. */

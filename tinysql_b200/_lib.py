@@ -53,7 +53,7 @@ SYMBOLS = {
     "tq_device_alloc": (_I32, [C.c_size_t, C.POINTER(_P)]), "tq_device_free": (_I32, [_P]),
     "tq_memcpy_h2d": (_I32, [_P, _P, C.c_size_t]), "tq_memcpy_d2h": (_I32, [_P, _P, C.c_size_t]),
     "tq_memcpy_d2d": (_I32, [_P, _P, C.c_size_t]),
-    "tq_memset_device": (_I32, [_P, _I32, C.c_size_t]), "tq_device_synchronize": (_I32, []),
+    "tq_memset_device": (_I32, [_P, _I32, C.c_size_t]), "tq_device_synchronize": (_I32, []), "tq_compute_synchronize": (_I32, []),
     "tq_timer_start": (_I32, []), "tq_timer_stop": (_I32, [C.POINTER(C.c_float)]),
     "tq_kernel_launch_count": (_I64, []), "tq_flush_l2": (_I32, []),
     "tq_vec_compare_int": (_I32, [_I32, _I64, _COL, _I32, _COL, _I32, _COL, _I32]),

@@ -442,7 +442,9 @@ static constexpr int PRE_THREADS = 512;
 static constexpr int PRE_MAX_GROUPS_PER_PART = 2400;
 static constexpr int PRE_MAX_OUT_COLS = 1 + 2 * AGG_MAXF;
 struct PreParams {
-  const uint64_t *col[4];        // col[0] = key, then the distinct argument columns (slabs, or the batch itself when pbits == 0)
+  const uint64_t *col[4];        // col[0] = key, then the distinct argument columns (the batch itself when pbits == 0, column slabs on the old scatter)
+  const uint64_t *aos;           // non-null: array-of-structs slabs of aos_nc words per row (word 0 = key, word c = argument column c)
+  int aos_nc;
   const uint32_t *lo, *hi, *lim; // partition bounds inside the slabs (pbits > 0)
   int64_t n;
   int pbits, split;
@@ -471,7 +473,11 @@ __global__ void __launch_bounds__(PRE_THREADS) k_agg_preagg(const PreParams p) {
   const int64_t len = hi - lo;
   const int64_t r_lo = lo + len * sub / p.split, r_hi = lo + len * (sub + 1) / p.split;
   for (int64_t r = r_lo + threadIdx.x; r < r_hi; r += PRE_THREADS) {
-    const uint64_t key = tqd::ld_stream_u64(p.col[0] + r);
+    uint64_t key, w1 = 0;
+    if (p.aos) {
+      if (p.aos_nc == 2) { const ulonglong2 x = tqd::ld_stream_u64x2(p.aos + r * 2); key = x.x; w1 = x.y; }
+      else key = tqd::ld_stream_u64(p.aos + r * p.aos_nc);
+    } else key = tqd::ld_stream_u64(p.col[0] + r);
     if (key == AGG_EMPTY) { atomicOr(p.fallback, 1u); continue; }
     uint32_t idx = (uint32_t)(tqd::mix64(key) >> 20) & (PRE_SLOTS - 1);  // bits disjoint from the partition bits and the global table's
     bool ok = false;
@@ -488,11 +494,14 @@ __global__ void __launch_bounds__(PRE_THREADS) k_agg_preagg(const PreParams p) {
     uint64_t *st = s_st + (size_t)idx * p.W;
     for (int fi = 0; fi < p.n_funcs; fi++) {
       const PreFunc &f = p.f[fi];
-      if (f.kind == PRE_COUNT) atomicAdd(reinterpret_cast<unsigned long long *>(st + f.w), 1ull);
-      else if (f.kind == PRE_SUM_F64) atomicAdd(reinterpret_cast<double *>(st + f.w), __longlong_as_double((long long)tqd::ld_stream_u64(p.col[f.col] + r)));
-      else if (f.kind == PRE_AVG_F64) {
-        atomicAdd(reinterpret_cast<unsigned long long *>(st + f.w), 1ull);
-        atomicAdd(reinterpret_cast<double *>(st + f.w + 1), __longlong_as_double((long long)tqd::ld_stream_u64(p.col[f.col] + r)));
+      if (f.kind == PRE_COUNT) atomicAdd(reinterpret_cast<unsigned *>(st + f.w), 1u);   // low half of the word: a CTA sees < 2^32 rows, and 32-bit shared atomics are native (64-bit ones are CAS loops)
+      else {
+        const uint64_t bits = !p.aos ? tqd::ld_stream_u64(p.col[f.col] + r) : (p.aos_nc == 2 ? w1 : tqd::ld_stream_u64(p.aos + r * p.aos_nc + f.col));
+        if (f.kind == PRE_SUM_F64) atomicAdd(reinterpret_cast<double *>(st + f.w), __longlong_as_double((long long)bits));
+        else if (f.kind == PRE_AVG_F64) {
+          atomicAdd(reinterpret_cast<unsigned *>(st + f.w), 1u);
+          atomicAdd(reinterpret_cast<double *>(st + f.w + 1), __longlong_as_double((long long)bits));
+        }
       }
     }
   }
@@ -552,6 +561,7 @@ struct tq_agg {
   bool pre_partitioned = false;  // TQ_AGG_PREAGG_PART=1: also pre-aggregate when the groups need radix partitioning (measured slower)
   int64_t known_groups = 0;  // groups in the table after the last batch
   std::vector<DevBuf> pre_slabs, pre_out;
+  DevBuf pre_aos;
   DevBuf pre_lo, pre_hi, pre_lim, pre_meta;
   cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;
   tq_agg_func funcs[AGG_MAXF];
@@ -714,7 +724,15 @@ static int32_t agg_try_preagg(tq_agg *a, const DCol *cols, int64_t n, bool *done
   unsigned long long *d_overflow = d_out_n + 1;                            // [1] scatter slab overflow
   unsigned *d_fallback = reinterpret_cast<unsigned *>(d_out_n + 2);        // [2] pre-aggregation gave up
   TQ_CUDA(cudaEventRecord(a->ev_pa, s));
-  if (pbits) {
+  static const bool old_scatter = [] { const char *e = getenv("TQ_AGG_PREAGG_OLD_SCATTER"); return e && e[0] == '1'; }();
+  if (pbits && pbits <= SCATTER_AOS_MAX_PBITS && !old_scatter) {
+    TQ_TRY(scatter_rows_by_hash_aos(used, n_used, 0, n, pbits, a->pre_aos, a->pre_lo, a->pre_hi, a->pre_lim, d_overflow, s));
+    p.aos = a->pre_aos.as<uint64_t>();
+    p.aos_nc = n_used;
+    p.lo = a->pre_lo.as<uint32_t>();
+    p.hi = a->pre_hi.as<uint32_t>();
+    p.lim = a->pre_lim.as<uint32_t>();
+  } else if (pbits) {
     TQ_TRY(scatter_rows_by_hash(used, n_used, 0, n, pbits, a->pre_slabs, a->pre_lo, a->pre_hi, a->pre_lim, d_overflow, s));
     for (int c = 0; c < n_used; c++) p.col[c] = a->pre_slabs[c].as<uint64_t>();
     p.lo = a->pre_lo.as<uint32_t>();

@@ -1445,6 +1445,39 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_part(const ProbeParams 
 #include "join_stream.cuh"
 namespace tq {
 
+// scatter.cuh: the streaming AoS scatter for other operators (HashAgg pre-aggregation)
+int32_t scatter_rows_by_hash_aos(const DCol *cols, int n_cols, int key_col, int64_t n, int pbits, DevBuf &aos, DevBuf &lo, DevBuf &hi, DevBuf &lim,
+                                 unsigned long long *d_overflow, cudaStream_t s) {
+  if (n_cols < 1 || n_cols > 4 || pbits < 1 || pbits > SA_MAX_PBITS || n <= 0 || n > 0xFFFFFFF0ll) { set_error("internal: scatter_rows_by_hash_aos arguments"); return TQ_ERR_INVALID_ARG; }
+  const int P = 1 << pbits;
+  const uint64_t slab = ((uint64_t)n / P + (uint64_t)n / P / 4 + 4096 + 31) & ~31ull;
+  if (slab * P > 0xFFFFFFF0ull) { set_error("batch too large for 32-bit partition offsets"); return TQ_ERR_INVALID_ARG; }
+  TQ_TRY(aos.reserve((size_t)slab * P * n_cols * 8 + 256));
+  TQ_TRY(lo.reserve((size_t)(P + 3) * 4));
+  TQ_TRY(hi.reserve((size_t)(P + 3) * 4));
+  TQ_TRY(lim.reserve((size_t)(P + 3) * 4));
+  k_init_slabs<<<(P + 1 + 255) / 256, 256, 0, s>>>(lo.as<uint32_t>(), hi.as<uint32_t>(), lim.as<uint32_t>(), P, (uint32_t)slab, 0u);
+  count_launch();
+  ScatterAosParams q{};
+  q.sp.n_cols = n_cols;
+  q.use_tma = g_no_tma ? 0 : 1;
+  for (int c = 0; c < n_cols; c++) {
+    q.sp.in[c] = cols[c];
+    if ((reinterpret_cast<uintptr_t>(cols[c].data) & 15) != 0) q.use_tma = 0;
+  }
+  q.sp.selected = nullptr;
+  q.sp.key_col = key_col;
+  q.sp.key_mode = KEYMODE_RAW;
+  q.sp.is_outer = 0;
+  q.sp.pbits = pbits;
+  q.sp.n = n;
+  q.sp.part_cursor = hi.as<uint32_t>();
+  q.sp.part_lim = lim.as<uint32_t>();
+  q.sp.overflow = d_overflow;
+  q.out = aos.as<uint64_t>();
+  return launch_scatter_aos(q, n_cols, s);
+}
+
 // ------------------------------------------------------------------ host side
 // Pinned accumulation of ≤1024-row host chunks into one column.
 struct HostAccum {
@@ -1748,36 +1781,35 @@ static int32_t try_stream_build(tq_join *j, bool *done) {
   q.sp.overflow = cur + 2;
   q.out = j->b_aos.as<uint64_t>();
   TQ_TRY(launch_scatter_aos(q, NB, s));
-  std::vector<uint32_t> h_hi((size_t)P);
-  unsigned long long h_cur[4] = {0, 0, 0, 0};
-  TQ_CUDA(cudaMemcpyAsync(h_hi.data(), hi.p, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
-  TQ_CUDA(cudaMemcpyAsync(h_cur, cur, 32, cudaMemcpyDeviceToHost, s));
-  TQ_CUDA(cudaStreamSynchronize(s));
-  if (h_cur[2]) return TQ_OK;  // a slab overflowed: skewed hash partitions
-  uint64_t max_cnt = 0, n_valid = 0;
-  for (int q2 = 0; q2 < P; q2++) {
-    const uint64_t c = h_hi[q2] - (uint64_t)q2 * slab;
-    n_valid += c;
-    if (c > max_cnt) max_cnt = c;
-  }
+  // Table capacity from the row count alone (no host round trip for the partition histogram): hash partitions of n rows hold
+  // n / P +- a few sqrt(n / P); a partition that turns out fuller than the load limit allows is flagged by the build kernel
+  // and the general path takes over.
+  const double mean = (double)n / P;
+  const uint64_t est_max = (uint64_t)(mean + 8.0 * sqrt(mean) + 64.0);
   uint64_t cap = 64;
-  while (cap * (uint64_t)g_max_load_pct < max_cnt * 100) cap <<= 1;
+  while (cap * (uint64_t)g_max_load_pct < est_max * 100) cap <<= 1;
   if (cap * P > (uint64_t)n * 12 + 4096) return TQ_OK;
   const uint64_t n_slots = (uint64_t)P * cap;
   if (n_slots > 0xFFFFFFF0ull) return TQ_OK;
   const int shift = NB > 2 ? 2 : 1;
   TQ_TRY(j->slots.reserve(((n_slots + 1) << shift) * 8));
   uint64_t *words = j->slots.as<uint64_t>();
-  k_init_table<<<1, 32, 0, s>>>(words + (n_slots << shift), 1, shift);  // the side entry of the empty-marker key (unused on this path)
+  k_init_table<<<r.sm_count * 8, 256, 0, s>>>(words, n_slots + 1, shift);  // (+ the side entry of the empty-marker key, unused on this path)
   BuildPartParams bp{};
   bp.slab = j->b_aos.as<uint64_t>();
   bp.lo = off.as<uint32_t>();
   bp.hi = hi.as<uint32_t>();
+  bp.lim = lim.as<uint32_t>();
   bp.words = words;
   bp.cap = cap;
+  bp.max_rows = cap * (uint64_t)g_max_load_pct / 100;
   bp.shift = shift;
   bp.n_parts = P;
   bp.key_col = j->build_key;
+  {
+    int64_t split = (int64_t)(mean / 4096.0);   // ~4K rows per CTA: a dozen partitions are live across the 148 SMs
+    bp.split = (int)(split < 1 ? 1 : (split > 256 ? 256 : split));
+  }
   {
     int w = 1;
     for (int c = 0; c < NB; c++) {
@@ -1787,12 +1819,18 @@ static int32_t try_stream_build(tq_join *j, bool *done) {
     j->row_mask_word = -1;
   }
   bp.flags = reinterpret_cast<unsigned *>(cur + 3);
-  build_part_kernel(NB)<<<P < r.sm_count ? P : r.sm_count, BP_THREADS, 0, s>>>(bp);
+  build_part_kernel(NB)<<<(unsigned)(P * bp.split), BP_THREADS, 0, s>>>(bp);
   count_launch(2);
   TQ_TRY(check_launch("k_build_part"));
+  std::vector<uint32_t> h_hi((size_t)P);
+  unsigned long long h_cur[4] = {0, 0, 0, 0};
+  TQ_CUDA(cudaMemcpyAsync(h_hi.data(), hi.p, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
   TQ_CUDA(cudaMemcpyAsync(h_cur, cur, 32, cudaMemcpyDeviceToHost, s));
   TQ_CUDA(cudaStreamSynchronize(s));
-  if (h_cur[3]) return TQ_OK;  // duplicate keys or the empty-marker key: the general build handles them
+  if (h_cur[2]) return TQ_OK;  // a slab overflowed: skewed hash partitions
+  if (h_cur[3]) return TQ_OK;  // duplicate keys, the empty-marker key, or a partition over the load limit: the general build handles them
+  uint64_t n_valid = 0;
+  for (int q2 = 0; q2 < P; q2++) n_valid += h_hi[q2] - (uint64_t)q2 * slab;
   j->shift = shift;
   j->pbits = pbits;
   j->n_slots = n_slots;
@@ -2007,11 +2045,8 @@ static std::unique_ptr<ResultBatch> get_result_batch(tq_join *j) {
 static constexpr int HOLE_PAD_THREADS = 512;   // >= partitions of the streaming path (SA_MAX_PBITS)
 __global__ void __launch_bounds__(HOLE_PAD_THREADS) k_hole_pads(const uint32_t *lo, const uint32_t *hi, const uint32_t *lim, const uint32_t *out_base, int n_parts,
                                                                  unsigned long long *cur, uint32_t *hole_pos, uint32_t *tail_src) {
-  __shared__ uint32_t s_h[HOLE_PAD_THREADS], s_t[HOLE_PAD_THREADS];
-  __shared__ unsigned long long s_rows;
+  __shared__ uint32_t s_warp[33];
   const int q = threadIdx.x;
-  if (q == 0) s_rows = 0;
-  __syncthreads();
   const uint64_t M = cur[0];
   uint32_t cnt = 0, base = 0, h = 0, t = 0;
   if (q < n_parts) {
@@ -2019,28 +2054,34 @@ __global__ void __launch_bounds__(HOLE_PAD_THREADS) k_hole_pads(const uint32_t *
     if (lim && e > lim[q]) e = lim[q];
     cnt = e - lo[q];
     base = out_base[q];
-    atomicAdd(&s_rows, (unsigned long long)cnt);
     const uint64_t pad_lo = (uint64_t)base + cnt, pad_hi = out_base[q + 1];        // pad slots of this partition
     const uint64_t hole_hi = pad_hi < M ? pad_hi : M;
     h = hole_hi > pad_lo ? (uint32_t)(hole_hi - pad_lo) : 0u;                      // ... that lie below M
     const uint64_t real_lo = (uint64_t)base > M ? (uint64_t)base : M;
     t = pad_lo > real_lo ? (uint32_t)(pad_lo - real_lo) : 0u;                      // real rows of this partition at or above M
   }
-  s_h[q] = h;
-  s_t[q] = t;
-  __syncthreads();
+  uint32_t rows, n_holes, n_tail;
+  block_excl_scan(cnt, s_warp, &rows);
+  const uint32_t h_off = block_excl_scan(h, s_warp, &n_holes);
+  const uint32_t t_off = block_excl_scan(t, s_warp, &n_tail);
   if (q == 0) {
-    cur[6] = s_rows;                  // rows the scatter placed: == M iff no probe row missed
-    uint32_t rh = 0, rt = 0;
-    for (int i = 0; i < n_parts; i++) { const uint32_t a = s_h[i], b = s_t[i]; s_h[i] = rh; s_t[i] = rt; rh += a; rt += b; }
-    cur[5] = rh;                      // holes to fill (== rt when nothing missed)
+    cur[6] = rows;                    // rows the scatter placed: == M iff no probe row missed
+    cur[5] = n_holes;                 // holes to fill (== n_tail when nothing missed)
   }
-  __syncthreads();
-  if (q < n_parts && cur[6] == M) {
+  if ((uint64_t)rows != M) return;    // misses among the probe rows: fill_holes_host builds exact lists (CTA-uniform exit)
+  if (q < n_parts) {
     const uint64_t pad_lo = (uint64_t)base + cnt;
-    for (uint32_t i = 0; i < h; i++) hole_pos[s_h[q] + i] = (uint32_t)(pad_lo + i);
-    const uint64_t real_lo = (uint64_t)base > M ? (uint64_t)base : M;
-    for (uint32_t i = 0; i < t; i++) tail_src[s_t[q] + i] = (uint32_t)(real_lo + i);
+    for (uint32_t i = 0; i < h; i++) hole_pos[h_off + i] = (uint32_t)(pad_lo + i);   // at most 31 per partition
+  }
+  // the real rows at or above M sit in the last partition(s), up to 31 * P of them in one partition: written by the whole CTA
+  __shared__ uint32_t s_t[HOLE_PAD_THREADS], s_toff[HOLE_PAD_THREADS], s_lo[HOLE_PAD_THREADS];
+  s_t[q] = t;
+  s_toff[q] = t_off;
+  s_lo[q] = (uint32_t)((uint64_t)base > M ? (uint64_t)base : M);
+  __syncthreads();
+  for (int pq = 0; pq < n_parts; pq++) {
+    const uint32_t tq = s_t[pq];
+    for (uint32_t i = q; i < tq; i += HOLE_PAD_THREADS) tail_src[s_toff[pq] + i] = s_lo[pq] + i;
   }
 }
 struct HoleMoveDevParams {
@@ -2154,7 +2195,7 @@ static int32_t launch_probe_stream(tq_join *j, const ProbeParams &p, const std::
       dbg_report("slabs after scatter", c, dbg.as<unsigned long long>(), s);
     }
   }
-  k_part_bases<<<1, 32, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), P, j->pos_base[slot].as<uint32_t>(), cur + 3);
+  k_part_bases<<<1, PART_BASES_THREADS, 0, s>>>(off.as<uint32_t>(), cur_b.as<uint32_t>(), lim.as<uint32_t>(), P, j->pos_base[slot].as<uint32_t>(), cur + 3);
   count_launch();
   ProbePosParams pp{};
   pp.slab = j->part_aos[slot].as<uint64_t>();

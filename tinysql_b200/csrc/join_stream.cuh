@@ -300,17 +300,45 @@ static int32_t launch_scatter_aos(const ScatterAosParams &q, int nc, cudaStream_
 
 // ------------------------------------------------------------------------------------------------ positional probe
 // out_base[q] = first output slot of partition q (a multiple of 32), out_base[n_parts] = the span S of the result.
-__global__ void k_part_bases(const uint32_t *lo, const uint32_t *hi, const uint32_t *lim, int n_parts, uint32_t *out_base, unsigned long long *span) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint32_t run = 0;
-  for (int q = 0; q < n_parts; q++) {
+// exclusive scan of one value per thread over a CTA of up to 1024 threads (s_warp: 33 words); returns the prefix, *total = the sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp, uint32_t *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < n_warps ? s_warp[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += x; }
+    if (lane < n_warps) s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  const uint32_t res = inc - v + s_warp[warp];
+  *total = s_warp[32];
+  __syncthreads();
+  return res;
+}
+
+// output base of every partition: its rows rounded up to 32 slots, so a warp's 32 rows never straddle two partitions
+static constexpr int PART_BASES_THREADS = 512;   // >= partitions of the streaming path (SA_MAX_PBITS)
+__global__ void __launch_bounds__(PART_BASES_THREADS) k_part_bases(const uint32_t *lo, const uint32_t *hi, const uint32_t *lim, int n_parts, uint32_t *out_base,
+                                                                    unsigned long long *span) {
+  __shared__ uint32_t s_warp[33];
+  const int q = threadIdx.x;
+  uint32_t padded = 0;
+  if (q < n_parts) {
     uint32_t h = hi[q];
     if (lim && h > lim[q]) h = lim[q];
-    out_base[q] = run;
-    run += ((h - lo[q]) + 31u) & ~31u;
+    padded = ((h - lo[q]) + 31u) & ~31u;
   }
-  out_base[n_parts] = run;
-  *span = run;
+  uint32_t total;
+  const uint32_t base = block_excl_scan(padded, s_warp, &total);
+  if (q < n_parts) out_base[q] = base;
+  if (q == 0) { out_base[n_parts] = total; *span = total; }
 }
 
 static constexpr int PP_STAGES = 4;
@@ -601,60 +629,66 @@ __global__ void __launch_bounds__(256) k_hole_move(const HoleMoveParams h) {
 }
 
 // ------------------------------------------------------------------------------------------------ partition-local build
-static constexpr int BP_THREADS = 1024;
+// The table is initialised by one grid-wide streaming pass (k_init_table); the inserts then run partition by partition:
+// CTA b works on partition b / split, so the CTAs resident at any moment touch a dozen partition tables (a few MB each) and
+// the CAS of an insert finds its line in L2 after the first touch.  (A first version gave each partition to ONE 1024-thread
+// CTA, init included: 128 CTAs of dependent CAS chains, 0.80 ms for 1e7 rows — slower than the global insert it replaced.)
+static constexpr int BP_THREADS = 512;
 struct BuildPartParams {
   const uint64_t *slab;              // AoS build rows (NB words each)
-  const uint32_t *lo, *hi;
+  const uint32_t *lo, *hi, *lim;     // a slab that overflowed (hi > lim) holds lim - lo rows; the caller discards the build anyway
   uint64_t *words;                   // the table
   uint64_t cap;                      // entries per partition table (power of two)
-  int shift, n_parts, key_col;
+  uint64_t max_rows;                 // rows a partition may hold at the configured load factor
+  int shift, n_parts, key_col, split;
   int word_of_col[4];
-  unsigned *flags;                   // |= 1: duplicate key, |= 2: the empty-marker key appeared  -> the caller rebuilds on the general path
+  unsigned *flags;                   // |= 1: duplicate key, |= 2: the empty-marker key appeared, |= 4: a partition is over the load limit  -> the caller rebuilds on the general path
 };
 template <int NB>
-__global__ void __launch_bounds__(BP_THREADS, 1) k_build_part(const BuildPartParams b) {
+__global__ void __launch_bounds__(BP_THREADS, 2) k_build_part(const BuildPartParams b) {
   const int tid = threadIdx.x;
   const uint64_t mask = b.cap - 1;
-  for (int part = blockIdx.x; part < b.n_parts; part += gridDim.x) {
-    uint64_t *tbl = b.words + (((uint64_t)part * b.cap) << b.shift);
-    // ---- init: (EMPTY_KEY, 0[, 0, 0]) entries, 16-byte stores; the table partition stays in L2 for the inserts below
-    const uint64_t n_vec = (b.cap << b.shift) >> 1;
-    const int per_entry = 1 << (b.shift - 1);  // 16-byte pieces per entry
-    for (uint64_t i = tid; i < n_vec; i += BP_THREADS) {
-      const bool first = (i & (uint64_t)(per_entry - 1)) == 0;
-      *reinterpret_cast<ulonglong2 *>(tbl + i * 2) = make_ulonglong2(first ? EMPTY_KEY : 0ull, 0ull);
+  const int part = blockIdx.x / b.split, sub = blockIdx.x % b.split;
+  const int64_t p_lo = b.lo[part];
+  int64_t p_hi = b.hi[part];
+  if (p_hi > (int64_t)b.lim[part]) p_hi = b.lim[part];
+  if ((uint64_t)(p_hi - p_lo) > b.max_rows) {  // (the optimistic capacity was too small for this partition)
+    if (tid == 0 && sub == 0) atomicOr(b.flags, 4u);
+    return;
+  }
+  const int64_t rows = p_hi - p_lo;
+  const int64_t lo = p_lo + rows * sub / b.split, hi = p_lo + rows * (sub + 1) / b.split;
+  uint64_t *tbl = b.words + (((uint64_t)part * b.cap) << b.shift);
+  for (int64_t r = lo + tid; r < hi; r += BP_THREADS) {
+    uint64_t w[NB];
+    if constexpr (NB == 2) {
+      const ulonglong2 x = tqd::ld_stream_u64x2(b.slab + r * 2);
+      w[0] = x.x;
+      w[1] = x.y;
+    } else if constexpr (NB == 4) {
+      const ulonglong2 x = tqd::ld_stream_u64x2(b.slab + r * 4), y = tqd::ld_stream_u64x2(b.slab + r * 4 + 2);
+      w[0] = x.x; w[1] = x.y; w[2] = y.x; w[3] = y.y;
+    } else {
+#pragma unroll
+      for (int c = 0; c < NB; c++) w[c] = tqd::ld_stream_u64(b.slab + r * NB + c);
     }
-    __syncthreads();
-    const int64_t lo = b.lo[part], hi = b.hi[part];
-    for (int64_t r = lo + tid; r < hi; r += BP_THREADS) {
-      uint64_t w[NB];
-      if constexpr (NB == 2) {
-        const ulonglong2 x = tqd::ld_stream_u64x2(b.slab + r * 2);
-        w[0] = x.x;
-        w[1] = x.y;
-      } else {
+    uint64_t key = w[0];
 #pragma unroll
-        for (int c = 0; c < NB; c++) w[c] = tqd::ld_stream_u64(b.slab + r * NB + c);
+    for (int c = 1; c < NB; c++) if (c == b.key_col) key = w[c];
+    if (key == EMPTY_KEY) { atomicOr(b.flags, 2u); continue; }
+    const uint64_t h = tqd::hash_key(key);
+    uint64_t loc = (b.shift == 1) ? ((h & mask) & ~1ull) : (h & mask);
+    for (;;) {
+      uint64_t *ent = tbl + (loc << b.shift);
+      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(ent), (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+      if (prev == EMPTY_KEY) {
+#pragma unroll
+        for (int c = 0; c < NB; c++) if (c != b.key_col) ent[b.word_of_col[c]] = w[c];
+        break;
       }
-      uint64_t key = w[0];
-#pragma unroll
-      for (int c = 1; c < NB; c++) if (c == b.key_col) key = w[c];
-      if (key == EMPTY_KEY) { atomicOr(b.flags, 2u); continue; }
-      const uint64_t h = tqd::hash_key(key);
-      uint64_t loc = (b.shift == 1) ? ((h & mask) & ~1ull) : (h & mask);
-      for (;;) {
-        uint64_t *ent = tbl + (loc << b.shift);
-        const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(ent), (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-        if (prev == EMPTY_KEY) {
-#pragma unroll
-          for (int c = 0; c < NB; c++) if (c != b.key_col) ent[b.word_of_col[c]] = w[c];
-          break;
-        }
-        if (prev == key) { atomicOr(b.flags, 1u); break; }
-        loc = (loc + 1) & mask;
-      }
+      if (prev == key) { atomicOr(b.flags, 1u); break; }
+      loc = (loc + 1) & mask;
     }
-    // (no barrier needed before the next partition: it lives elsewhere)
   }
 }
 typedef void (*BuildPartKernel)(const BuildPartParams);

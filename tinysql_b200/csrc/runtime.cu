@@ -436,6 +436,11 @@ int32_t tq_device_synchronize(void) {
   TQ_CUDA(cudaDeviceSynchronize());
   return TQ_OK;
 }
+int32_t tq_compute_synchronize(void) {
+  TQ_TRY(ensure_init());
+  TQ_CUDA(cudaStreamSynchronize(rt().compute));
+  return TQ_OK;
+}
 int32_t tq_timer_start(void) {
   TQ_TRY(ensure_init());
   TQ_CUDA(cudaEventRecord(rt().t0, rt().compute));

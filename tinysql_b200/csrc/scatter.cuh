@@ -14,4 +14,10 @@ namespace tq {
 int32_t scatter_rows_by_hash(const DCol *cols, int n_cols, int key_col, int64_t n, int pbits, std::vector<DevBuf> &out, DevBuf &lo, DevBuf &hi, DevBuf &lim,
                              unsigned long long *d_overflow, cudaStream_t s);
 
+// The streaming variant (join_stream.cuh: TMA-fed tiles, shared-atomic ranking): rows land as array-of-structs records of n_cols
+// words in ONE slab buffer (`aos`), partition = top pbits (<= 9) bits of tqd::hash_key(key).  Same lo / hi / lim / overflow contract.
+int32_t scatter_rows_by_hash_aos(const DCol *cols, int n_cols, int key_col, int64_t n, int pbits, DevBuf &aos, DevBuf &lo, DevBuf &hi, DevBuf &lim,
+                                 unsigned long long *d_overflow, cudaStream_t s);
+static constexpr int SCATTER_AOS_MAX_PBITS = 9;
+
 }  // namespace tq

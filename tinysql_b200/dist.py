@@ -181,13 +181,23 @@ class RegionExchange:
     def counts(self, t):
         """rows each source wrote into this rank's regions of table t (host read: synchronises the compute stream)"""
         self.wait(t)
-        self.L.check(self.lib.tq_device_synchronize())
+        self.L.check(self.lib.tq_compute_synchronize())   # the compute stream only: the pushes of later tables keep running
         raw = np.zeros(2 * self.world, dtype=np.uint64)
         self.L.check(self.lib.tq_memcpy_d2h(raw.ctypes.data, C.c_void_p(self.slot_ptr(self.rank, t, 0)), 16 * self.world))
         cnt = [int(raw[2 * g]) for g in range(self.world)]
         if any(c > self.cap[t] for c in cnt):
             raise RuntimeError(f"region overflow in table {t}: {cnt} rows, capacity {self.cap[t]} (skewed keys)")
         return cnt
+
+    def check_all_counts(self):
+        """one host read of every slot of this rank (after the step's joins have consumed the regions): overflow check"""
+        nt = len(self.ncols)
+        raw = np.zeros(2 * self.world * nt, dtype=np.uint64)
+        self.L.check(self.lib.tq_memcpy_d2h(raw.ctypes.data, C.c_void_p(self.slot_ptr(self.rank, 0, 0)), 16 * self.world * nt))
+        for t in range(nt):
+            cnt = [int(raw[2 * (t * self.world + g)]) for g in range(self.world)]
+            if any(c > self.cap[t] for c in cnt):
+                raise RuntimeError(f"region overflow in table {t}: {cnt} rows, capacity {self.cap[t]} (skewed keys)")
 
     def segment_args(self, t):
         """(tq_column array [src][col], count pointer array) of this rank's regions of table t"""
@@ -378,6 +388,9 @@ class RegionJoin:
     def step(self, bk, bv, pk, pv, keep_result=False):
         """bk / bv / pk / pv: this rank's row shards as (device pointer, rows)-like objects.  Returns (rows, stats, result)."""
         lib, L, rx, w = self.lib, self.L, self.rx, self.world
+        t_start = time.perf_counter()
+        trace = []
+        mark = lambda name: trace.append((name, (time.perf_counter() - t_start) * 1e3))   # host-side timeline: where the host blocks
         n_probe = int(pk.numel())
         bounds = [n_probe * i // self.n_chunks for i in range(self.n_chunks + 1)]
         rx.next_epoch()
@@ -385,8 +398,10 @@ class RegionJoin:
         for c in range(self.n_chunks):
             lo, hi = bounds[c], bounds[c + 1]
             rx.push(1 + c, [RawCol(pk.data_ptr() + lo * 8, hi - lo), RawCol(pv.data_ptr() + lo * 8, hi - lo)], hi - lo, 1 + c)
+        mark("pushes enqueued")
         # ---- build side: the only place the host needs row counts
         cnt_b = rx.counts(0)
+        mark("build rows arrived (host read)")
         t = (C.c_int32 * 2)(1, 1)
         k = (C.c_int32 * 1)(0)
         d = L.TQJoinDesc(0, 1, 2, t, 2, t, 1, k, k, 0, 0)
@@ -399,6 +414,7 @@ class RegionJoin:
                     cols = [RawCol(rx.region_ptr(self.rank, 0, g, c), cnt_b[g]) for c in range(2)]
                     L.check(lib.tq_join_put_build(h, _tq_cols(L, cols, cnt_b[g]), L.TQ_MEM_DEVICE))
             L.check(lib.tq_join_finalize_build(h))
+            mark("build done")
             out = (L.TQColumn * 4)()
             n, eof = C.c_int64(0), C.c_int32(0)
             chunks = []
@@ -420,18 +436,23 @@ class RegionJoin:
                 cols, cnts = rx.segment_args(1 + c)
                 st_ = lib.tq_join_put_probe_segments(h, w, cols, cnts, rx.cap[1 + c])
                 L.check(st_)
+                mark(f"chunk {c} enqueued")
                 if c >= 1:
                     drain(False)                                 # hand back the batch before last (keeps two result sets alive, not n_chunks)
+                    mark(f"chunk {c - 1} drained")
             L.check(lib.tq_join_probe_eof(h))
             drain(True)
+            mark("all drained")
             lib.tq_join_stats(h, st)
             if keep_result:
                 result = [np.concatenate([ch[c] for ch in chunks]) if chunks else np.zeros(0, np.int64) for c in range(4)]
         finally:
             lib.tq_join_destroy(h)
-        for c in range(self.n_chunks):                           # a region overflow would have dropped rows: fail loudly
-            rx.counts(1 + c)
+        rx.check_all_counts()                                    # a region overflow would have dropped rows: fail loudly
+        mark("overflow checks")
         dist.barrier()
+        mark("barrier")
+        self.last_trace = trace
         return total, list(st), result
 
 
@@ -489,9 +510,10 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
     launches1 = lib.tq_kernel_launch_count()
     L.check(lib.tq_timer_start())
     t0 = time.perf_counter()
-    rows_total, probe_ns, build_ns = 0, [], []
+    rows_total, probe_ns, build_ns, traces = 0, [], [], []
     for _ in range(args.steps):
         rows, st, _ = step()
+        traces.append(rj.last_trace)
         rows_total += rows
         probe_ns.append(st[5])
         build_ns.append(st[6])
@@ -534,6 +556,9 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
         p_part, p_off = part([pk, pv], world)
         torch.cuda.synchronize()
         cnt = exchange_counts([p_off], world, rank, dev)[0]
+        p_recv, _ = exchange(p_part, p_off, world, rank, recv_counts=cnt)   # warm-up: connection setup and buffer registration
+        del p_recv
+        torch.cuda.synchronize()
         dist_mod.barrier()
         e0.record()
         p_recv, _ = exchange(p_part, p_off, world, rank, recv_counts=cnt)
@@ -583,6 +608,8 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
         "e2e": {"value": value, "unit": "joined rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "multi-GPU line: shards are generated in HBM; the host-buffer e2e figure is reported on the 1-GPU line"},
         "verified": verified,
+        "phase_ms_rank0": {name: round(statistics.mean(tr[i][1] for tr in traces), 3) for i, (name, _) in enumerate(traces[0])},
+        "phase_note": "host-side timeline of one step on rank 0 (ms since the step began, mean over the timed steps): the points where the host thread resumes",
         "nccl_all_to_all_probe_exchange_ms": nccl_ms,
         "one_gpu_same_job": one_gpu,
         "gpu_launches": int(launches2 - launches1), "clocks": clocks, "wall_ms_per_step_max": float(tmax[2]) / args.steps,
@@ -598,6 +625,11 @@ def one_gpu_reference(lib, L, dev, world, n_b, n_p, steps=2):
     N_b = n_b * world
     bk = torch.cat([torch.from_numpy(np.random.default_rng(1000 + r).permutation(n_b).astype(np.int64) * world + r).to(dev) for r in range(world)])
     bv = bk * 7 + 1
+    shards = []
+    for r in range(world):   # all N_p probe rows resident (16 bytes each): generated once, outside the timed region
+        gid = torch.arange(n_p, dtype=torch.int64, device=dev) + r * n_p
+        shards.append((_mix64_mod_torch(gid, N_b), gid))
+    torch.cuda.synchronize()
     t = (C.c_int32 * 2)(1, 1)
     k = (C.c_int32 * 1)(0)
     best = None
@@ -617,11 +649,7 @@ def one_gpu_reference(lib, L, dev, world, n_b, n_p, steps=2):
             n, eof = C.c_int64(0), C.c_int32(0)
             rows = 0
             for r in range(world):
-                # probe shard r is regenerated on the device each time (not timed separately: the generation is a handful of
-                # elementwise kernels, ~1 % of the join; keeping all N_p rows resident would need 16 GB more)
-                gid = torch.arange(n_p, dtype=torch.int64, device=dev) + r * n_p
-                pk = _mix64_mod_torch(gid, N_b)
-                torch.cuda.synchronize()
+                pk, gid = shards[r]
                 L.check(lib.tq_join_put_probe(h, _tq_cols(L, [pk, gid], n_p), None, L.TQ_MEM_DEVICE))
                 while True:
                     L.check(lib.tq_join_next_device(h, out, C.byref(n), C.byref(eof)))
@@ -642,7 +670,7 @@ def one_gpu_reference(lib, L, dev, world, n_b, n_p, steps=2):
             L.check(lib.tq_timer_stop(C.byref(ms)))
             best = ms.value if best is None else min(best, ms.value)
     return {"ms_per_step": best, "rows": int(rows), "value": rows / (best * 1e-3), "build_rows": N_b, "probe_rows": n_p * world,
-            "note": "one B200, inputs generated in HBM, probe fed in device batches; includes the on-device generation of the probe keys"}
+            "note": "one B200, all inputs resident in HBM before the timed region, probe fed in device batches of one shard each; best of the timed repetitions"}
 
 
 def _mix64_mod_torch(gid, mod):
