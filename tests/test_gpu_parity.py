@@ -540,11 +540,6 @@ def test_agg_table_growth(lib):
 
 
 # ------------------------------------------------------------------ multi-GPU shard boundary, exercised on ONE GPU
-def test_partition_push_bulk_store_experiment(lib, monkeypatch):
-    monkeypatch.setenv("TQ_PUSH_BULK", "1")
-    test_partition_count_and_push_local(lib)
-
-
 def test_partition_count_and_push_local(lib):
     """tq_partition_count_device + tq_partition_push_device with all destination buffers on this GPU: every row lands in
     the partition (mix64(key) >> 40) % n_parts, at the offsets the count pass implies, nothing lost or duplicated"""

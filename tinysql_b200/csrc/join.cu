@@ -42,7 +42,6 @@ static bool g_no_fast_kernel = false;                    // TQ_JOIN_NO_FAST=1: u
 static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
 static bool g_old_fast = false;                          // TQ_JOIN_OLD_FAST=1: the round-1 PK-FK kernels instead of the streaming pipeline (A/B)
 static bool g_debug_sums = false;                        // TQ_JOIN_DEBUG_SUMS=1: print per-stage row counts / column checksums of the streaming pipeline (diagnostics)
-static int g_pp_variant = 0;                             // TQ_JOIN_PP_VARIANT=0..5: probe kernel shape (rows per lane / warps / CTAs per SM), A/B measurements
 static bool g_no_tma = false;                            // TQ_JOIN_NO_TMA=1: plain loads instead of TMA bulk copies in the AoS scatter (diagnostics)
 static int g_scatter_tile = 2048;                        // TQ_JOIN_SCATTER_TILE=1024|2048|4096: rows per tile of the AoS scatter
 
@@ -956,110 +955,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(mbar)),
       "r"(parity)
       : "memory");
-}
-
-// ---- push scatter with TMA bulk stores (experiment, TQ_PUSH_BULK=1) --------------------------------------------------
-// Same job as k_probe_scatter_fast in push mode (n_parts_mod ranks, every row has a destination), but the sorted tile
-// leaves shared memory as a few LARGE asynchronous bulk copies — one per (destination rank, column), ~4 KB each —
-// issued by one thread per rank (cp.async.bulk.global.shared::cta, SASS UBLKCP) instead of 8-byte stores from every
-// thread: the copy engine streams them over NVLink while the CTA already sorts its next tile.  Bulk copies need
-// 16-byte aligned source, destination and size; rows are 8 bytes, so each run is placed in shared memory with the
-// parity of its destination row and an odd first / last row goes out as a plain store.
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-static constexpr int PUSHB_STAGE = SCAT_TILE + 16;  // rows per column stage: the tile + one padding slot per run
-template <int NP>
-__global__ void __launch_bounds__(SCATF_THREADS, (NP <= 2 ? 2 : 1)) k_push_bulk(const ScatterParams p) {
-  extern __shared__ __align__(128) unsigned char s_pb[];
-  uint64_t *s_stage = reinterpret_cast<uint64_t *>(s_pb);              // [NP][PUSHB_STAGE]
-  __shared__ uint32_t s_cnt[8], s_start[8], s_g[8];
-  const int tid = threadIdx.x;
-  const int n_parts = p.n_parts_mod;
-  const uint64_t *in[NP];
-#pragma unroll
-  for (int c = 0; c < NP; c++) in[c] = p.in[c].data;
-  const int kc = p.key_col;
-  const int64_t n_tiles = (p.n + SCAT_TILE - 1) / SCAT_TILE;
-  const bool issuer = (tid & 31) == 0 && (tid >> 5) < n_parts;       // lane 0 of warp b issues the copies of rank b
-  const int my_bin = tid >> 5;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t tile_base = tile * SCAT_TILE;
-    uint64_t v[NP][SCATF_ROWS];
-#pragma unroll
-    for (int k = 0; k < SCATF_ROWS; k++) {
-      const int64_t r = tile_base + k * SCATF_THREADS + tid;
-#pragma unroll
-      for (int c = 0; c < NP; c++) v[c][k] = (r < p.n) ? tqd::ld_stream_u64(in[c] + r) : 0;
-    }
-    if (issuer) bulk_wait_read_all();   // the previous tile's copies have left shared memory
-    __syncthreads();                    // ... and every issuer is done with the previous tile's run table
-    if (tid < 8) s_cnt[tid] = 0;
-    __syncthreads();
-    uint32_t pid[SCATF_ROWS], spos[SCATF_ROWS];
-#pragma unroll
-    for (int k = 0; k < SCATF_ROWS; k++) {
-      const int64_t r = tile_base + k * SCATF_THREADS + tid;
-      uint64_t key = v[0][k];
-#pragma unroll
-      for (int c = 1; c < NP; c++) if (c == kc) key = v[c][k];
-      pid[k] = PID_DROP;
-      spos[k] = 0;
-      if (r < p.n) { pid[k] = scatter_pid(p, key); spos[k] = atomicAdd(&s_cnt[pid[k]], 1u); }
-    }
-    __syncthreads();
-    if (tid < n_parts) s_g[tid] = s_cnt[tid] ? atomicAdd(&p.part_cursor[tid], s_cnt[tid]) : 0u;  // claim the run in rank tid's receive buffer
-    __syncthreads();
-    if (tid == 0) {  // run starts inside the stage, each with the parity of its destination row
-      uint32_t cur = 0;
-      for (int b = 0; b < n_parts; b++) {
-        uint32_t st = cur;
-        if ((st ^ s_g[b]) & 1u) st++;
-        s_start[b] = st;
-        cur = st + s_cnt[b];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < NP; c++) {
-#pragma unroll
-      for (int k = 0; k < SCATF_ROWS; k++)
-        if (pid[k] != PID_DROP) s_stage[c * PUSHB_STAGE + s_start[pid[k]] + spos[k]] = v[c][k];
-    }
-    fence_async_smem();   // generic-proxy writes above -> visible to the async proxy (the bulk copies below)
-    __syncthreads();
-    if (issuer) {
-      const uint32_t st = s_start[my_bin], cnt = s_cnt[my_bin], g = s_g[my_bin];
-      const uint32_t head = (cnt && (st & 1u)) ? 1u : 0u;
-      const uint32_t mid = (cnt - head) & ~1u;
-      const uint32_t tail = cnt - head - mid;
-#pragma unroll
-      for (int c = 0; c < NP; c++) {
-        uint64_t *dst = p.out_bin[my_bin][c];
-        const uint64_t *src = s_stage + c * PUSHB_STAGE;
-        if (head) dst[g] = src[st];
-        if (mid) bulk_store(dst + g + head, src + st + head, mid * 8u);
-        if (tail) dst[g + cnt - 1] = src[st + cnt - 1];
-      }
-      bulk_commit();
-    }
-  }
-  if (issuer) bulk_wait_all();
-}
-typedef void (*PushBulkKernel)(const ScatterParams);
-static PushBulkKernel push_bulk_kernel(int np) {
-  switch (np) {
-    case 1: return k_push_bulk<1>;
-    case 2: return k_push_bulk<2>;
-    case 3: return k_push_bulk<3>;
-    case 4: return k_push_bulk<4>;
-  }
-  return nullptr;
 }
 
 // Common prologue of the partitioned probe kernels: which rows does this CTA own, where is its table.
@@ -2209,7 +2104,7 @@ static int32_t launch_probe_stream(tq_join *j, const ProbeParams &p, const std::
   pp.cursor = cur;
   pp.key_col = j->probe_key;
   { const char *e = getenv("TQ_JOIN_PP_DEBUG"); const int f = e ? atoi(e) : 0; pp.dbg_no_tma = f & 1; pp.dbg_late_release = (f >> 1) & 1; }
-  const ProbePosVariant pv = probe_pos_kernel(NP, NB, g_pp_variant);
+  const ProbePosVariant pv = probe_pos_kernel(NP, NB);
   const int64_t rows_per_cta = g_tiles_per_cta * 1024;   // ~8K rows per CTA: enough CTAs per partition that only a handful of partitions are live at once
   int64_t split = (n / P) / rows_per_cta;
   if (split < 1) split = 1;
@@ -2776,7 +2671,6 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   { const char *e = getenv("TQ_JOIN_NO_FAST"); g_no_fast_kernel = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_OLD_FAST"); g_old_fast = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_NO_TMA"); g_no_tma = e && e[0] == '1'; }
-  { const char *e = getenv("TQ_JOIN_PP_VARIANT"); g_pp_variant = e ? atoi(e) : 0; }
   { const char *e = getenv("TQ_JOIN_DEBUG_SUMS"); g_debug_sums = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_SCATTER_TILE"); g_scatter_tile = (e && (atoi(e) == 4096 || atoi(e) == 1024)) ? atoi(e) : 2048; }
   { const char *e = getenv("TQ_JOIN_EXACT_SCATTER"); g_exact_scatter = e && e[0] == '1'; }
@@ -3439,24 +3333,16 @@ static int32_t partition_push(int32_t n_cols, const tq_column *cols, int32_t key
   static DevBuf ovf;
   TQ_TRY(ovf.reserve(8));
   sp.overflow = ovf.as<unsigned long long>();
-  const char *bulk_env = getenv("TQ_PUSH_BULK");  // experiment: TMA bulk stores (k_push_bulk)
-  const bool use_bulk = bulk_env && bulk_env[0] == '1';
-  ScatterKernel k = use_bulk ? push_bulk_kernel(n_cols) : scatter_fast_kernel(n_cols);
-  static bool attr[2][5] = {};
-  if (!attr[use_bulk ? 1 : 0][n_cols]) {
-    const int max_smem = use_bulk ? n_cols * PUSHB_STAGE * 8 : (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 12);
-    TQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr[use_bulk ? 1 : 0][n_cols] = true;
+  ScatterKernel k = scatter_fast_kernel(n_cols);
+  static bool attr[5] = {};
+  if (!attr[n_cols]) {
+    TQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAT_TILE * 11 + ((1 << PART_MAX_BITS) + 1) * 12)));
+    attr[n_cols] = true;
   }
   const int n_bins = n_parts + 1;
-  const int smem = use_bulk ? n_cols * PUSHB_STAGE * 8 : SCAT_TILE * 8 + n_bins * 12 + SCAT_TILE * 2 + SCAT_TILE;
+  const int smem = SCAT_TILE * 8 + n_bins * 12 + SCAT_TILE * 2 + SCAT_TILE;
   const int64_t tiles = (n + SCAT_TILE - 1) / SCAT_TILE;
-  int64_t cap = (int64_t)r.sm_count * (n_cols <= 2 ? 2 : 1);
-  if (async) {  // an overlapped push is NVLink-bound: a few dozen CTAs saturate the links and leave the SMs to the local probe
-    static int64_t push_ctas = -1;
-    if (push_ctas < 0) { const char *e = getenv("TQ_PUSH_CTAS"); push_ctas = (e && atoll(e) > 0) ? atoll(e) : 0; }
-    if (push_ctas > 0 && push_ctas < cap) cap = push_ctas;
-  }
+  const int64_t cap = (int64_t)r.sm_count * (n_cols <= 2 ? 2 : 1);
   k<<<(int)(tiles < cap ? tiles : cap), SCATF_THREADS, smem, s>>>(sp);
   count_launch();
   TQ_TRY(check_launch("k_probe_scatter_fast(push)"));
@@ -3571,10 +3457,7 @@ int32_t tq_partition_push_regions(int32_t n_cols, const tq_column *cols, int32_t
     const int n_bins = n_parts + 1;
     const int smem = SCAT_TILE * 8 + n_bins * 12 + SCAT_TILE * 2 + SCAT_TILE;
     const int64_t tiles = (n + SCAT_TILE - 1) / SCAT_TILE;
-    static int64_t push_ctas = -1;
-    if (push_ctas < 0) { const char *e = getenv("TQ_PUSH_CTAS"); push_ctas = (e && atoll(e) > 0) ? atoll(e) : 0; }
-    int64_t cap = (int64_t)r.sm_count * (n_cols <= 2 ? 2 : 1);
-    if (push_ctas > 0 && push_ctas < cap) cap = push_ctas;
+    const int64_t cap = (int64_t)r.sm_count * (n_cols <= 2 ? 2 : 1);
     k<<<(int)(tiles < cap ? tiles : cap), SCATF_THREADS, smem, s>>>(sp);
     count_launch();
     TQ_TRY(check_launch("k_probe_scatter_fast(push regions)"));

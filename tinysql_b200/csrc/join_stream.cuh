@@ -549,36 +549,28 @@ struct ProbePosVariant {
   int tile, threads;
 };
 template <int NP, int NB>
-static ProbePosVariant probe_pos_variant(int variant) {
-  // Measured on the C3 shape (B200, profiles/r2_probe_variants.txt): 2 rows per lane x 12 consumer warps x 3 CTAs per SM beats
-  // 4 rows x 8 warps (more warps in flight hide the L2 latency of the table gathers better than more loads per warp, and the
-  // kernel stops spilling).  Other shapes of the benchmark columns are compiled for A/B runs (TQ_JOIN_PP_VARIANT).
-  if constexpr (NP == 2 && NB == 2) {
-    switch (variant) {
-      case 1: return {k_probe_pos<NP, NB, 2, 16, 2>, 16 * 32 * 2, 17 * 32};
-      case 2: return {k_probe_pos<NP, NB, 4, 8, 3>, 8 * 32 * 4, 9 * 32};
-      case 3: return {k_probe_pos<NP, NB, 2, 8, 4>, 8 * 32 * 2, 9 * 32};
-      case 4: return {k_probe_pos<NP, NB, 4, 8, 2>, 8 * 32 * 4, 9 * 32};
-    }
-  }
+static ProbePosVariant probe_pos_variant() {
+  // Measured on the C3 shape (B200): 2 rows per lane x 12 consumer warps x 3 CTAs per SM (1.85 ms probe pipeline) beats 4 rows x 8
+  // warps x 3 (1.94, spills), 2 x 16 x 2 and 2 x 8 x 4: more warps in flight hide the L2 latency of the table gathers better than
+  // more loads per warp.  The losing shapes were deleted.
   return {k_probe_pos<NP, NB, 2, 12, 3>, 12 * 32 * 2, 13 * 32};
 }
 template <int NP>
-static ProbePosVariant probe_pos_nb(int nb, int variant) {
+static ProbePosVariant probe_pos_nb(int nb) {
   switch (nb) {
-    case 1: return probe_pos_variant<NP, 1>(variant);
-    case 2: return probe_pos_variant<NP, 2>(variant);
-    case 3: return probe_pos_variant<NP, 3>(variant);
-    case 4: return probe_pos_variant<NP, 4>(variant);
+    case 1: return probe_pos_variant<NP, 1>();
+    case 2: return probe_pos_variant<NP, 2>();
+    case 3: return probe_pos_variant<NP, 3>();
+    case 4: return probe_pos_variant<NP, 4>();
   }
   return {nullptr, 0, 0};
 }
-static ProbePosVariant probe_pos_kernel(int np, int nb, int variant) {
+static ProbePosVariant probe_pos_kernel(int np, int nb) {
   switch (np) {
-    case 1: return probe_pos_nb<1>(nb, variant);
-    case 2: return probe_pos_nb<2>(nb, variant);
-    case 3: return probe_pos_nb<3>(nb, variant);
-    case 4: return probe_pos_nb<4>(nb, variant);
+    case 1: return probe_pos_nb<1>(nb);
+    case 2: return probe_pos_nb<2>(nb);
+    case 3: return probe_pos_nb<3>(nb);
+    case 4: return probe_pos_nb<4>(nb);
   }
   return {nullptr, 0, 0};
 }

@@ -493,7 +493,7 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
     bk, bv, pk, pv = (torch.from_numpy(x).to(dev) for x in (bk_h, bv_h, pk_h, pv_h))
     del bk_h, bv_h, pv_h
     torch.cuda.synchronize()
-    n_chunks = max(1, int(os.environ.get("TQ_DIST_CHUNKS", "4")))
+    n_chunks = max(1, int(os.environ.get("TQ_DIST_CHUNKS", "2")))   # measured at N=2: 2 chunks 5.87 ms, 3: 6.12, 4: 6.28, 8: 10.0 per step
     rj = RegionJoin(lib, L, world, rank, n_b, n_p, n_chunks)
 
     def step(keep=False):
