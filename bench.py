@@ -110,10 +110,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm (oracle/cpu_ref.c)
-def cpu_join_sample(n_build, n_probe_full, sample_probe, workers, seed_rank=0):
+def cpu_join_sample(n_build, n_probe_full, sample_probe, workers, seed_rank=0, tables=None):
     import oracle_py as O
     lib = O.load()
-    bk, bv, pk, pv = gen_join_tables(n_build, sample_probe, n_build, rank=seed_rank)
+    bk, bv, pk, pv = tables if tables is not None else gen_join_tables(n_build, sample_probe, n_build, rank=seed_rank)
     bs, ps, ck = C.c_double(0), C.c_double(0), C.c_uint64(0)
     rows = lib.orc_mt_join_bench(C.c_int64(n_build), C.c_void_p(bk.ctypes.data), C.c_void_p(bv.ctypes.data), C.c_int64(sample_probe),
                                  C.c_void_p(pk.ctypes.data), C.c_void_p(pv.ctypes.data), C.c_int(workers), C.byref(bs), C.byref(ps), C.byref(ck))
@@ -440,13 +440,25 @@ def run_reference(args, rank):
     if rank != 0:
         return None
     n_build, n_probe = args.build_rows, args.probe_rows
+    config = join_config(n_build, n_probe)
+    if args.gpus > 1:   # the same GLOBAL job our arm runs at this N (dist.py: C5 sizes per GPU x N), on the host cores
+        from tinysql_b200.dist import dist_sizes, dist_workload_config
+        n_b, n_p = dist_sizes(args)
+        n_build, n_probe = n_b * args.gpus, n_p * args.gpus
+        config = dist_workload_config(args.gpus, n_b, n_p, max(1, int(os.environ.get("TQ_DIST_CHUNKS", "2"))))
     workers = os.cpu_count() or 1
     n_steps = args.warmup + args.steps
-    sample = n_probe if n_steps <= 8 else min(n_probe, max(args.cpu_sample_rows, int(n_probe * 0.4)))
+    # bounded sample: the whole run (W + K steps, each = full serial build + probe of `sample` rows) should end within ~3 minutes
+    # on the box's host cores (measured: build 62 ns/row on one core, probe 22 ns/row over 128 threads); the whole probe side
+    # whenever that fits — then nothing is extrapolated
+    budget_s = 170.0 / max(n_steps, 1)
+    sample = int(max(args.cpu_sample_rows, min(n_probe, (budget_s - 6.2e-8 * n_build) / 2.2e-8)))
+    sample = min(sample, n_probe)
     res = None
     times = []
+    tables = gen_join_tables(n_build, sample, n_build)   # generated once: the steps time the join, not numpy
     for i in range(n_steps):
-        r = cpu_join_sample(n_build, n_probe, sample, workers)
+        r = cpu_join_sample(n_build, n_probe, sample, workers, tables=tables)
         if i >= args.warmup:
             times.append(r)
         res = r
@@ -458,7 +470,7 @@ def run_reference(args, rank):
     return {"impl": "reference", "metric": "joined rows/sec on 1e8-row int64 equi-join", "value": v, "unit": "joined rows/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_probe / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": join_config(n_build, n_probe),
+            "config": config,
             "cpu_baseline": res, "e2e": {"value": v, "unit": "joined rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 

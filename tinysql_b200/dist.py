@@ -478,6 +478,27 @@ def verify_dist_result(cols, rank, world, n_b, n_p):
     return ok, int(pv.size), int(pv.astype(np.uint64).sum(dtype=np.uint64))
 
 
+def dist_sizes(args):
+    """per-GPU (build, probe) rows of the N > 1 line: C5's 1e8 x 1e9 at 8 GPUs = 1.25e7 / 1.25e8 per GPU at every N, unless
+    --build-rows / --probe-rows override the per-GPU sizes"""
+    default_sizes = (args.build_rows, args.probe_rows) == (10_000_000, 100_000_000)
+    return (12_500_000, 125_000_000) if default_sizes else (args.build_rows, args.probe_rows)
+
+
+def dist_workload_config(world, n_b, n_p, n_chunks=None):
+    """the `config` of the N > 1 bench line; the reference arm (--impl reference --gpus N) reports the same workload"""
+    N_b, N_p = n_b * world, n_p * world
+    cfg = {"workload": f"C5: int64 equi-join radix-partitioned on the key over {world} GPUs; per GPU build={n_b} probe={n_p} (global {N_b} x {N_p}), "
+                       "uniform keys, 100% match, output (B.k,B.v,P.k,P.v) materialised in HBM on the rank that owns the key",
+           "build_rows_per_gpu": n_b, "probe_rows_per_gpu": n_p, "global_build_rows": N_b, "global_probe_rows": N_p,
+           "exchange": "fused scatter + push into per-source regions of the peers' receive buffers (CUDA IPC peer stores over NVLink), device-side epoch "
+                       "flags instead of host barriers; local join reads the regions as one segmented batch",
+           "l2": "inputs and outputs exceed the 126 MB L2; no flush needed"}
+    if n_chunks is not None:
+        cfg["parallelism"] = f"key-hash partitions over {world} ranks, {n_chunks} probe chunks pipelined (push of chunk c+1 overlaps the join of chunk c)"
+    return cfg
+
+
 def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_src):
     """bench.py N>1.  Default tables: C5 — build 1e8 / probe 1e9 at 8 GPUs, i.e. 1.25e7 / 1.25e8 rows PER GPU at every N
     (weak scaling: per-GPU work is fixed); --build-rows / --probe-rows override the per-GPU sizes."""
@@ -486,8 +507,7 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
     from . import _lib as L
     lib = L.load()
     dev = torch.device("cuda", local_rank)
-    default_sizes = (args.build_rows, args.probe_rows) == (10_000_000, 100_000_000)
-    n_b, n_p = (12_500_000, 125_000_000) if default_sizes else (args.build_rows, args.probe_rows)
+    n_b, n_p = dist_sizes(args)
     N_b, N_p = n_b * world, n_p * world
     bk_h, bv_h, pk_h, pv_h = gen_dist_tables(rank, world, n_b, n_p)
     bk, bv, pk, pv = (torch.from_numpy(x).to(dev) for x in (bk_h, bv_h, pk_h, pv_h))
@@ -548,7 +568,10 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
                            "all ranks: row count == probe rows, sum(P.v) == N(N-1)/2 (every probe row exactly once)"]}
     # ---- the exchange north_star names, measured once for the record: partition + ONE grouped NCCL send/recv (all-to-all)
     nccl_ms = None
+    lean = os.environ.get("TQ_DIST_LEAN", "0") == "1"   # quick validation runs: skip the NCCL comparison and the one-GPU baseline
     try:
+        if lean:
+            raise RuntimeError("skipped (TQ_DIST_LEAN=1)")
         part = gpu_partition_fn(lib, L)
         torch.cuda.synchronize()
         dist_mod.barrier()
@@ -572,7 +595,7 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
         nccl_ms = f"unavailable: {type(e).__name__}: {e}"
     # ---- strong-scaling reference: the WHOLE job (N_b x N_p) on ONE GPU (rank 0), same kernels, no exchange
     one_gpu = None
-    if os.environ.get("TQ_DIST_ONE_GPU", "1") == "1":
+    if os.environ.get("TQ_DIST_ONE_GPU", "1") == "1" and not lean:
         rj.close()
         rj = None
         del bk, bv, pk, pv
@@ -593,13 +616,7 @@ def bench_distributed_join(args, rank, world, local_rank, dist_mod, peak, peak_s
         "metric": "joined rows/sec on 1e8-row int64 equi-join", "value": value, "unit": "joined rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
-        "config": {"workload": f"C5: int64 equi-join radix-partitioned on the key over {world} GPUs; per GPU build={n_b} probe={n_p} (global {N_b} x {N_p}), "
-                               "uniform keys, 100% match, output (B.k,B.v,P.k,P.v) materialised in HBM on the rank that owns the key",
-                   "build_rows_per_gpu": n_b, "probe_rows_per_gpu": n_p, "global_build_rows": N_b, "global_probe_rows": N_p,
-                   "parallelism": f"key-hash partitions over {world} ranks, {n_chunks} probe chunks pipelined (push of chunk c+1 overlaps the join of chunk c)",
-                   "exchange": "fused scatter + push into per-source regions of the peers' receive buffers (CUDA IPC peer stores over NVLink), device-side epoch "
-                               "flags instead of host barriers; local join reads the regions as one segmented batch",
-                   "l2": "inputs and outputs exceed the 126 MB L2; no flush needed"},
+        "config": dist_workload_config(world, n_b, n_p, n_chunks),
         "roofline": {"bound": "nvlink", "kernel": "push of this rank's probe rows (7/8 of them cross NVLink at 8 GPUs), overlapped with the local join",
                      "achieved": push_bytes / (ms_per_step * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s", "frac": push_bytes / (ms_per_step * 1e-3) / 1e9 / 770.0,
                      "traffic": None, "peak_source": "B200_PROFILING.md: measured peer copy 770 GB/s per direction per GPU",
