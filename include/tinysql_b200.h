@@ -387,6 +387,34 @@ int32_t tq_agg_partial_width(tq_agg *a, int32_t *n_cols);
 int32_t tq_agg_export_partial(tq_agg *a, tq_column *out_cols, int64_t *n_rows);
 int32_t tq_agg_merge_partial(tq_agg *a, const tq_column *cols, int32_t mem);
 
+/* FinalMode HashAgg over pushed-down partial results.  The planner splits an aggregation into a Partial1
+ * half that runs inside the coprocessor (planner/core/task.go:564-625, store/mockstore/mocktikv/aggregate.go:81-124: each row
+ * it returns = the GetPartialResult columns of every function — COUNT: count; SUM / MAX / MIN / FIRSTROW: value; AVG: count
+ * then sum — followed by the GROUP BY columns) and a FinalMode HashAggExec whose AggFuncDesc.Args are column references into
+ * that partial schema (expression/aggregation/descriptor.go:52-75, aggfuncs/builder.go:50-62,86-109: countPartial,
+ * avgPartial4Int64 / avgPartial4Float64; SUM / MAX / MIN / FIRSTROW merge with their ordinary functions).
+ * tq_agg_create_final builds that executor: tq_agg_put then takes the child's chunks of PARTIAL rows (any column order; all
+ * three chunk layouts), and eof / next / next_bytes / destroy behave as for tq_agg_create.  arg_col = the partial column the
+ * function reads (for AVG: the partial COUNT), arg_col2 = AVG's partial SUM column (ignored otherwise).  A partial row whose
+ * COUNT or SUM is NULL is skipped by AVG (func_avg.go:93-103), NULL partial values are skipped by SUM / MAX / MIN / COUNT. */
+typedef struct tq_agg_final_func {
+  int32_t func;     /* TQ_AGG_* */
+  int32_t arg_col;
+  int32_t arg_col2;
+} tq_agg_final_func;
+
+typedef struct tq_agg_final_desc {
+  int32_t n_input_cols;
+  const int32_t *input_types;   /* TQ_TYPE_* per column of the partial schema */
+  int32_t n_group_by;
+  const int32_t *group_by_cols;
+  int32_t n_funcs;
+  const tq_agg_final_func *funcs;
+  int64_t est_groups;
+} tq_agg_final_desc;
+
+int32_t tq_agg_create_final(const tq_agg_final_desc *desc, tq_agg **out);
+
 /* ------------------------------------------------------------- radix exchange
  * The shard boundary of the multi-GPU path: splits rows into n_parts partitions by
  * the key's hash (the moral equivalent of shuffleIntermData, aggregate.go:352-356).

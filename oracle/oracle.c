@@ -647,6 +647,144 @@ int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int
   return rc;
 }
 
+/* ------------------------------------------------------------------ pushed-down partial aggregation + FinalMode HashAgg
+ * orc_cop_partial_agg restates the coprocessor's hashAggExec (store/mockstore/mocktikv/aggregate.go:66-182): ONE map, groups
+ * in first-seen order (:159-163), Update per row (:166-172), and per group one output row = the GetPartialResult datums of
+ * every function (:98-107; expression/aggregation/{count,sum,avg,max_min,first_row}.go GetPartialResult — COUNT: count;
+ * SUM: value or NULL; AVG: count, value; MAX / MIN / FIRSTROW: the datum in the argument's own type) followed by the GROUP BY
+ * values of the group's first row (:108, :118-147).  calculateSum (aggregation/util.go:57-91) adds BIGINT arguments as int64
+ * (ComputePlus: overflow error) and everything else as float64 — exactly what state_update's SUM / AVG cases do. */
+static void state_partial_out(int func, int type, const agg_state *s, outbuf *obs, int *oc) {
+  uint64_t bits;
+  int ft = type == ORC_TYPE_FLOAT32 ? ORC_TYPE_FLOAT64 : type;
+  switch (func) {
+    case AGG_COUNT: ob_push(&obs[(*oc)++], (uint64_t)s->i, 1); return;
+    case AGG_AVG:
+      ob_push(&obs[(*oc)++], (uint64_t)s->i, 1);          /* types.NewIntDatum(evalCtx.Count), avg.go:79-81 */
+      if (s->i == 0) { ob_push(&obs[(*oc)++], 0, 0); return; }   /* evalCtx.Value is still the NULL datum */
+      if (ft == ORC_TYPE_FLOAT64) { memcpy(&bits, &s->sf, 8); ob_push(&obs[(*oc)++], bits, 1); } else ob_push(&obs[(*oc)++], (uint64_t)s->si, 1);
+      return;
+    default:
+      state_final(func, type, s, &obs[(*oc)++]);           /* SUM / MAX / MIN / FIRSTROW: GetResult == the final value */
+      return;
+  }
+}
+static int partial_out_type(int func, int type) {   /* column type of a partial VALUE column */
+  if (func == AGG_COUNT) return ORC_TYPE_INT64;
+  if (func == AGG_SUM || func == AGG_AVG) return (type == ORC_TYPE_FLOAT64 || type == ORC_TYPE_FLOAT32) ? ORC_TYPE_FLOAT64 : ORC_TYPE_INT64;
+  return type;
+}
+int orc_cop_partial_agg(int n_input_cols, const int *types, const orc_column *cols, int64_t n_rows,
+                        int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_func *funcs,
+                        orc_column *out_cols, int *out_types, int64_t *n_out) {
+  for (int c = 0; c < n_input_cols; c++) if (types[c] < 1 || types[c] > 5) return ORC_ERR_UNSUPPORTED;
+  for (int f = 0; f < n_funcs; f++)
+    if (funcs[f].arg_col >= 0 && types[funcs[f].arg_col] == ORC_TYPE_BYTES && (funcs[f].func == AGG_SUM || funcs[f].func == AGG_AVG)) return ORC_ERR_UNSUPPORTED;
+  pool_reset();
+  int *fn = (int *)malloc(sizeof(int) * (size_t)(n_funcs ? n_funcs : 1));
+  int *ft = (int *)malloc(sizeof(int) * (size_t)(n_funcs ? n_funcs : 1));
+  int n_outc = n_group_by;
+  for (int f = 0; f < n_funcs; f++) { fn[f] = funcs[f].func; ft[f] = funcs[f].arg_col >= 0 ? types[funcs[f].arg_col] : ORC_TYPE_INT64; n_outc += fn[f] == AGG_AVG ? 2 : 1; }
+  agg_map m; amap_init(&m, n_group_by, n_funcs);
+  int64_t *first_row = NULL; int64_t fr_cap = 0;
+  uint64_t key[64];
+  int rc = ORC_OK;
+  for (int64_t i = 0; i < n_rows && rc == ORC_OK; i++) {
+    for (int g = 0; g < n_group_by; g++) {
+      const orc_column *c = &cols[group_by_cols[g]];
+      int isnull = col_is_null(c, i);
+      key[2 * g] = (uint64_t)isnull; key[2 * g + 1] = isnull ? 0 : cell_word(types[group_by_cols[g]], c, i);
+    }
+    int64_t before = m.n;
+    int64_t gi = amap_get(&m, key, fn);
+    if (m.n != before) {   /* a new group: remember the row its GROUP BY values are taken from (groupKeyRows, :159-163) */
+      if (m.n > fr_cap) { fr_cap = fr_cap ? fr_cap * 2 : 1024; while (fr_cap < m.n) fr_cap *= 2; first_row = (int64_t *)realloc(first_row, 8 * (size_t)fr_cap); }
+      first_row[gi] = i;
+    }
+    for (int f = 0; f < n_funcs && rc == ORC_OK; f++)
+      rc = state_update(fn[f], ft[f], funcs[f].arg_col >= 0 ? &cols[funcs[f].arg_col] : NULL, i, &m.states[gi * n_funcs + f]);
+  }
+  outbuf *obs = (outbuf *)calloc((size_t)(n_outc ? n_outc : 1), sizeof(outbuf));
+  int oc = 0;
+  for (int f = 0; f < n_funcs; f++) {
+    if (fn[f] == AGG_AVG) { out_types[oc] = ORC_TYPE_INT64; obs[oc++].elem = 8; }
+    out_types[oc] = partial_out_type(fn[f], ft[f]); obs[oc].elem = elem_of_type(out_types[oc]); oc++;
+  }
+  for (int g = 0; g < n_group_by; g++) { out_types[oc] = types[group_by_cols[g]]; obs[oc].elem = elem_of_type(out_types[oc]); oc++; }
+  if (rc == ORC_OK)
+    for (int64_t g = 0; g < m.n; g++) {
+      oc = 0;
+      for (int f = 0; f < n_funcs; f++) state_partial_out(fn[f], ft[f], &m.states[g * n_funcs + f], obs, &oc);
+      for (int k = 0; k < n_group_by; k++) ob_push_cell(&obs[oc++], &cols[group_by_cols[k]], first_row[g]);
+    }
+  *n_out = n_outc ? obs[0].n : 0;
+  for (int c = 0; c < n_outc; c++) ob_finish(&obs[c], &out_cols[c]);
+  free(obs); free(first_row); amap_free(&m); free(fn); free(ft);
+  pool_reset();
+  return rc;
+}
+
+/* HashAggExec in FinalMode over partial rows (executor/aggregate.go with AggFuncDesc.Mode == FinalMode; the functions
+ * aggfuncs/builder.go builds for Partial2Mode / FinalMode):
+ *   COUNT  -> countPartial.UpdatePartialResult   func_count.go:99-113   (adds the partial counts, NULL skipped)
+ *   AVG    -> avgPartial4Int64 / avgPartial4Float64   func_avg.go:86-113, 200-227   (args[0] = count, args[1] = sum; a row whose
+ *             sum or count is NULL is skipped)
+ *   SUM / MAX / MIN / FIRSTROW -> the ordinary functions over the partial value column (builder.go:66-80,112-175)
+ * One partial worker / one final worker is result-equivalent (see orc_hash_agg). */
+int orc_hash_agg_final(int n_input_cols, const int *types, const orc_column *cols, int64_t n_rows,
+                       int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_final_func *funcs,
+                       orc_column *out_cols, int64_t *n_out) {
+  for (int c = 0; c < n_input_cols; c++) if (types[c] < 1 || types[c] > 5) return ORC_ERR_UNSUPPORTED;
+  pool_reset();
+  int *fn = (int *)malloc(sizeof(int) * (size_t)(n_funcs ? n_funcs : 1));
+  int *ft = (int *)malloc(sizeof(int) * (size_t)(n_funcs ? n_funcs : 1));
+  for (int f = 0; f < n_funcs; f++) {
+    fn[f] = funcs[f].func;
+    ft[f] = fn[f] == AGG_AVG ? types[funcs[f].arg_col2] : (fn[f] == AGG_COUNT ? ORC_TYPE_INT64 : types[funcs[f].arg_col]);
+  }
+  agg_map m; amap_init(&m, n_group_by, n_funcs);
+  uint64_t key[64];
+  int rc = ORC_OK;
+  for (int64_t i = 0; i < n_rows && rc == ORC_OK; i++) {
+    for (int g = 0; g < n_group_by; g++) {
+      const orc_column *c = &cols[group_by_cols[g]];
+      int isnull = col_is_null(c, i);
+      key[2 * g] = (uint64_t)isnull; key[2 * g + 1] = isnull ? 0 : cell_word(types[group_by_cols[g]], c, i);
+    }
+    int64_t gi = amap_get(&m, key, fn);
+    for (int f = 0; f < n_funcs && rc == ORC_OK; f++) {
+      agg_state *st = &m.states[gi * n_funcs + f];
+      const orc_column *a = &cols[funcs[f].arg_col];
+      if (fn[f] == AGG_COUNT) { if (!col_is_null(a, i)) st->i += col_i64(a, i); }
+      else if (fn[f] == AGG_AVG) {
+        const orc_column *sc = &cols[funcs[f].arg_col2];
+        if (col_is_null(sc, i) || col_is_null(a, i)) continue;
+        if (ft[f] == ORC_TYPE_FLOAT64) { st->sf += col_f64(sc, i); st->i += col_i64(a, i); }
+        else { rc = add_int64(st->si, col_i64(sc, i), &st->si); if (rc == ORC_OK) st->i += col_i64(a, i); }
+      } else rc = state_update(fn[f], ft[f], a, i, st);
+    }
+  }
+  outbuf *obs = (outbuf *)calloc((size_t)(n_funcs ? n_funcs : 1), sizeof(outbuf));
+  for (int f = 0; f < n_funcs; f++) {
+    int sel = (fn[f] == AGG_MAX || fn[f] == AGG_MIN || fn[f] == AGG_FIRSTROW);
+    obs[f].elem = (sel && ft[f] == ORC_TYPE_BYTES) ? 0 : ((sel && ft[f] == ORC_TYPE_FLOAT32) ? 4 : 8);
+  }
+  if (rc == ORC_OK) {
+    if (m.n == 0 && n_group_by == 0) {   /* the default row of a scalar aggregate over empty input, as in orc_hash_agg */
+      int all_first = 1; for (int f = 0; f < n_funcs; f++) if (fn[f] != AGG_FIRSTROW) all_first = 0;
+      if (!all_first) for (int f = 0; f < n_funcs; f++) { if (fn[f] == AGG_COUNT) ob_push(&obs[f], 0, 1); else if (obs[f].elem == 0) ob_push_str(&obs[f], -1); else ob_push(&obs[f], 0, 0); }
+    } else {
+      for (int64_t g = 0; g < m.n; g++)
+        for (int f = 0; f < n_funcs; f++) state_final(fn[f], ft[f], &m.states[g * n_funcs + f], &obs[f]);
+    }
+  }
+  *n_out = n_funcs ? obs[0].n : 0;
+  for (int f = 0; f < n_funcs; f++) ob_finish(&obs[f], &out_cols[f]);
+  free(obs); amap_free(&m); free(fn); free(ft);
+  pool_reset();
+  return rc;
+}
+
 /* ------------------------------------------------------------------ vectorized builtins */
 /* types/compare.go:44-100 VecCompare{UU,II,UI,IU} -> -1/0/1 */
 static int cmp_int(int ua, int ub, int64_t x, int64_t y) {

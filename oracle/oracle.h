@@ -74,6 +74,18 @@ int orc_hash_agg(int n_input_cols, const int *types, const orc_column *cols, int
                  int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_func *funcs,
                  int n_partial_workers, orc_column *out_cols, int64_t *n_out);
 
+/* The coprocessor's partial aggregation (store/mockstore/mocktikv/aggregate.go) and the FinalMode HashAggExec that consumes
+ * its rows (aggfuncs/builder.go Partial2Mode / FinalMode).  orc_cop_partial_agg writes, per group in first-seen order, the
+ * GetPartialResult columns of every function (AVG: count then sum) followed by the GROUP BY columns; out_types receives the
+ * column types (n_group_by + n_funcs + number of AVGs entries). */
+typedef struct orc_agg_final_func { int32_t func; int32_t arg_col; int32_t arg_col2; } orc_agg_final_func;
+int orc_cop_partial_agg(int n_input_cols, const int *types, const orc_column *cols, int64_t n_rows,
+                        int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_func *funcs,
+                        orc_column *out_cols, int *out_types, int64_t *n_out);
+int orc_hash_agg_final(int n_input_cols, const int *types, const orc_column *cols, int64_t n_rows,
+                       int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_final_func *funcs,
+                       orc_column *out_cols, int64_t *n_out);
+
 /* vectorized builtins — restated statement by statement from expression/builtin_*_vec*.go */
 int orc_vec_compare_int(int op, int64_t n, const orc_column *a, int a_unsigned, const orc_column *b,
                         int b_unsigned, orc_column *out);

@@ -121,6 +121,42 @@ def hash_agg(types, cols, group_by, funcs, n_partial_workers=1):
     return rc, res
 
 
+class OrcAggFinalFunc(C.Structure):
+    _fields_ = [("func", C.c_int32), ("arg_col", C.c_int32), ("arg_col2", C.c_int32)]
+
+
+def cop_partial_agg(types, cols, group_by, funcs):
+    """the coprocessor's partial aggregation (mocktikv/aggregate.go): returns (status, out_types, Chunk of partial rows)"""
+    lib = load()
+    n_rows = cols[0].length if cols else 0
+    n_outc = len(group_by) + len(funcs) + sum(1 for f, _ in funcs if f == 2)
+    fa = (TQAggFunc * max(len(funcs), 1))(*[TQAggFunc(f, a) for f, a in funcs])
+    out = (TQColumn * max(n_outc, 1))()
+    ot = (C.c_int * max(n_outc, 1))()
+    n = C.c_int64(0)
+    rc = lib.orc_cop_partial_agg(C.c_int(len(cols)), _i32(types), tq_array(cols), C.c_int64(n_rows), C.c_int(len(group_by)), _i32(group_by),
+                                 C.c_int(len(funcs)), fa, out, ot, C.byref(n))
+    out_types = [int(ot[i]) for i in range(n_outc)]
+    res = Chunk(_take(out, out_types, n.value if rc == 0 else 0))
+    lib.orc_free_columns(C.c_int(n_outc), out)
+    return rc, out_types, res
+
+
+def hash_agg_final(types, cols, group_by, funcs):
+    """FinalMode HashAggExec over partial rows; funcs = [(func, arg_col, arg_col2)].  returns (status, Chunk)"""
+    lib = load()
+    n_rows = cols[0].length if cols else 0
+    fa = (OrcAggFinalFunc * max(len(funcs), 1))(*[OrcAggFinalFunc(f, a, b) for f, a, b in funcs])
+    out = (TQColumn * max(len(funcs), 1))()
+    n = C.c_int64(0)
+    rc = lib.orc_hash_agg_final(C.c_int(len(cols)), _i32(types), tq_array(cols), C.c_int64(n_rows), C.c_int(len(group_by)), _i32(group_by),
+                                C.c_int(len(funcs)), fa, out, C.byref(n))
+    out_types = [1 if f == 0 else types[b if f == 2 else a] for f, a, b in funcs]
+    res = Chunk(_take(out, out_types, n.value if rc == 0 else 0))
+    lib.orc_free_columns(C.c_int(len(funcs)), out)
+    return rc, res
+
+
 def _vec(fn, out_tp, n, *args):
     out = Column.empty(out_tp, n)
     to = out.tq()

@@ -42,6 +42,16 @@ class TQAggDesc(C.Structure):
                 ("est_groups", C.c_int64)]
 
 
+class TQAggFinalFunc(C.Structure):
+    _fields_ = [("func", C.c_int32), ("arg_col", C.c_int32), ("arg_col2", C.c_int32)]
+
+
+class TQAggFinalDesc(C.Structure):
+    _fields_ = [("n_input_cols", C.c_int32), ("input_types", C.POINTER(C.c_int32)), ("n_group_by", C.c_int32),
+                ("group_by_cols", C.POINTER(C.c_int32)), ("n_funcs", C.c_int32), ("funcs", C.POINTER(TQAggFinalFunc)),
+                ("est_groups", C.c_int64)]
+
+
 # every symbol include/tinysql_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _COL = C.POINTER(TQColumn)
@@ -88,6 +98,7 @@ SYMBOLS = {
     "tq_join_next_bytes": (_I32, [_P, _I64, C.POINTER(_I64)]),
     "tq_join_stats": (_I32, [_P, C.POINTER(_I64)]), "tq_join_destroy": (_I32, [_P]),
     "tq_agg_create": (_I32, [C.POINTER(TQAggDesc), C.POINTER(_P)]),
+    "tq_agg_create_final": (_I32, [C.POINTER(TQAggFinalDesc), C.POINTER(_P)]),
     "tq_agg_output_type": (_I32, [_P, _I32, C.POINTER(_I32)]),
     "tq_agg_put": (_I32, [_P, _COL, _I32]), "tq_agg_eof": (_I32, [_P]),
     "tq_agg_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),

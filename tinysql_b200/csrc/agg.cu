@@ -580,6 +580,11 @@ struct tq_agg {
   bool flag_on[AGG_MAXF] = {};  // SUM/MAX/MIN: a batch with a NULL bitmap (or partial rows) has been seen for this argument
   int64_t est_groups = 0;
   int64_t batch_rows = 1 << 22;
+  // FinalMode handle (tq_agg_create_final): the child's chunks are PARTIAL rows; internal column j (keys first, then one
+  // state column per function, two for AVG) is the caller's input column final_src[j]
+  bool final_mode = false;
+  int final_src[AGG_MAXC] = {};
+  int final_n_in = 0;
 
   // table
   DevBuf keys, table, meta;   // meta: [0..1] side_used u32, [2] n_deferred u32, [3] err u32, u64@16 n_used, u64@24 out_n
@@ -898,6 +903,10 @@ static int32_t agg_update_device(tq_agg *a, const DCol *cols, int n_in_cols, int
   return TQ_ERR_CUDA;
 }
 
+// layout of input column c: partial rows lent by another handle (tq_agg_merge_partial) are 8-byte words throughout; the partial
+// rows of a FinalMode handle come from a child executor and carry their real chunk layout (FLOAT slots, var-len cells)
+static inline int col_kind(const tq_agg *a, bool merge, int c) { return (merge && !a->final_mode) ? 0 : a->in_kind[c]; }
+
 static int32_t agg_flush_stage(tq_agg *a, bool merge, int n_in_cols) {
   tq_agg::Stage &st = a->stage[a->cur_stage];
   if (st.n == 0) return TQ_OK;
@@ -905,9 +914,9 @@ static int32_t agg_flush_stage(tq_agg *a, bool merge, int n_in_cols) {
   st.d_data.resize(n_in_cols);
   st.d_bm.resize(n_in_cols);
   std::vector<DCol> view(n_in_cols);
-  if (a->any_kind && !merge) { st.store.resize(n_in_cols); st.d_raw.resize(n_in_cols); }
+  if (a->any_kind && (!merge || a->final_mode)) { st.store.resize(n_in_cols); st.d_raw.resize(n_in_cols); }
   for (int c = 0; c < n_in_cols; c++) {
-    const int kind = merge ? 0 : a->in_kind[c];
+    const int kind = col_kind(a, merge, c);
     TQ_TRY(st.d_data[c].reserve((size_t)st.n * 8));
     view[c].data = st.d_data[c].as<uint64_t>();
     view[c].bm = nullptr;
@@ -948,7 +957,7 @@ static int32_t agg_put_common(tq_agg *a, const tq_column *cols, int32_t mem, boo
   if (rows < 0) return TQ_ERR_INVALID_ARG;
   for (int c = 0; c < n_in_cols; c++) {
     if (cols[c].length != rows) { set_error("ragged aggregate input chunk"); return TQ_ERR_INVALID_ARG; }
-    const int kind = merge ? 0 : a->in_kind[c];
+    const int kind = col_kind(a, merge, c);
     if (kind != 2 && cols[c].offsets) { set_error("unsupport column type for encode (var-len data in fixed-width column %d)", c); return TQ_ERR_UNSUPPORTED_TYPE; }
     if (kind == 2 && !cols[c].offsets) { set_error("var-len column %d needs offsets", c); return TQ_ERR_INVALID_ARG; }
     if (rows && !cols[c].data && !(kind == 2 && cols[c].offsets[rows] == cols[c].offsets[0])) return TQ_ERR_INVALID_ARG;
@@ -977,7 +986,7 @@ static int32_t agg_put_common(tq_agg *a, const tq_column *cols, int32_t mem, boo
     for (int c = 0; c < n_in_cols; c++) {
       if (st.data[c].cap < (size_t)a->batch_rows * 8) TQ_TRY(st.data[c].reserve((size_t)a->batch_rows * 8));
       if (st.bm[c].cap < bitmap_alloc_bytes(a->batch_rows)) { TQ_TRY(st.bm[c].reserve(bitmap_alloc_bytes(a->batch_rows))); }
-      const int kind = merge ? 0 : a->in_kind[c];
+      const int kind = col_kind(a, merge, c);
       if (kind == 0) memcpy(st.data[c].as<uint8_t>() + st.n * 8, cols[c].data + done * 8, (size_t)take * 8);
       else if (kind == 1) memcpy(st.data[c].as<uint8_t>() + st.n * 4, cols[c].data + done * 4, (size_t)take * 4);  // packed 4-byte slots
       else {
@@ -1156,6 +1165,66 @@ int32_t tq_agg_create(const tq_agg_desc *d, tq_agg **out) {
   return TQ_OK;
 }
 
+int32_t tq_agg_create_final(const tq_agg_final_desc *d, tq_agg **out) {
+  if (!d || !out) return TQ_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (d->n_input_cols < 0 || d->n_group_by < 0 || d->n_group_by > MK_MAX_KEYS || d->n_funcs < 0 || d->n_funcs > AGG_MAXF) {
+    set_error("too many columns / functions");
+    return TQ_ERR_INVALID_ARG;
+  }
+  // internal layout = the one tq_agg_merge_partial reads: GROUP BY columns, then the state columns in function order
+  int32_t types[AGG_MAXC], gb[MK_MAX_KEYS], src[AGG_MAXC];
+  tq_agg_func fn[AGG_MAXF];
+  int n = 0;
+  auto in_type = [&](int c) { return d->input_types[c] & 0xFF; };   // TQ_TYPE_NOT_NULL is dropped: a partial SUM / MAX / MIN may be NULL
+  auto bad_col = [&](int c) { return c < 0 || c >= d->n_input_cols; };
+  for (int g = 0; g < d->n_group_by; g++) {
+    if (bad_col(d->group_by_cols[g])) { set_error("GROUP BY item %d is not an input column", g); return TQ_ERR_INVALID_ARG; }
+    gb[g] = n; src[n] = d->group_by_cols[g]; types[n] = in_type(src[n]); n++;
+  }
+  for (int i = 0; i < d->n_funcs; i++) {
+    const tq_agg_final_func &f = d->funcs[i];
+    const bool avg = f.func == TQ_AGG_AVG;
+    if (f.func < TQ_AGG_COUNT || f.func > TQ_AGG_FIRSTROW || bad_col(f.arg_col) || (avg && bad_col(f.arg_col2)) || n + (avg ? 2 : 1) > AGG_MAXC) {
+      set_error("bad FinalMode aggregate descriptor %d", i);
+      return TQ_ERR_INVALID_ARG;
+    }
+    // countPartial / avgPartial4* read the partial COUNT with EvalInt (func_count.go:99-113, func_avg.go:86-113,200-227)
+    if ((f.func == TQ_AGG_COUNT || avg) && in_type(f.arg_col) != TQ_TYPE_INT64 && in_type(f.arg_col) != TQ_TYPE_UINT64) {
+      set_error("partial COUNT column of function %d must be BIGINT", i);
+      return TQ_ERR_UNSUPPORTED_TYPE;
+    }
+    src[n] = f.arg_col; types[n] = in_type(f.arg_col); n++;
+    fn[i].func = f.func;
+    fn[i].arg_col = n - 1;
+    if (avg) {
+      const int t2 = in_type(f.arg_col2);
+      if (t2 != TQ_TYPE_INT64 && t2 != TQ_TYPE_UINT64 && t2 != TQ_TYPE_FLOAT64) { set_error("partial SUM column of AVG %d must be BIGINT or DOUBLE", i); return TQ_ERR_UNSUPPORTED_TYPE; }
+      src[n] = f.arg_col2; types[n] = t2; n++;
+      fn[i].arg_col = n - 1;   // the value type of AVG is the type of its partial sum (aggfuncs/builder.go:103-109)
+    }
+    if (f.func == TQ_AGG_SUM && types[fn[i].arg_col] != TQ_TYPE_INT64 && types[fn[i].arg_col] != TQ_TYPE_UINT64 && types[fn[i].arg_col] != TQ_TYPE_FLOAT64) {
+      set_error("partial SUM column of function %d must be BIGINT or DOUBLE", i);
+      return TQ_ERR_UNSUPPORTED_TYPE;
+    }
+  }
+  tq_agg_desc syn{};
+  syn.n_input_cols = n;
+  syn.input_types = types;
+  syn.n_group_by = d->n_group_by;
+  syn.group_by_cols = gb;
+  syn.n_funcs = d->n_funcs;
+  syn.funcs = fn;
+  syn.est_groups = d->est_groups;
+  tq_agg *a = nullptr;
+  TQ_TRY(tq_agg_create(&syn, &a));
+  a->final_mode = true;
+  a->final_n_in = d->n_input_cols;
+  for (int j = 0; j < n; j++) a->final_src[j] = src[j];
+  *out = a;
+  return TQ_OK;
+}
+
 int32_t tq_agg_output_type(tq_agg *a, int32_t i, int32_t *t) {
   if (!a || !t || i < 0 || i >= a->n_funcs) return TQ_ERR_INVALID_ARG;
   *t = a->out_type[i];
@@ -1164,6 +1233,17 @@ int32_t tq_agg_output_type(tq_agg *a, int32_t i, int32_t *t) {
 
 int32_t tq_agg_put(tq_agg *a, const tq_column *cols, int32_t mem) {
   if (!a) return TQ_ERR_INVALID_ARG;
+  if (a->final_mode) {
+    // FinalMode: the chunk holds partial rows in the child's column order; hand them to the merge path in its own order
+    if (!cols) return TQ_ERR_INVALID_ARG;
+    tq_column view[AGG_MAXC];
+    for (int j = 0; j < a->n_cols; j++) view[j] = cols[a->final_src[j]];
+    if (a->n_cols == 0) {  // no GROUP BY and no functions: nothing to aggregate, but the row count must still be seen
+      if (a->final_n_in == 0) return TQ_ERR_INVALID_ARG;
+      return TQ_OK;
+    }
+    return agg_put_common(a, view, mem, true, a->n_cols);
+  }
   return agg_put_common(a, cols, mem, false, a->n_cols);
 }
 
@@ -1174,6 +1254,7 @@ static bool agg_has_varlen(const tq_agg *a) {
 
 int32_t tq_agg_merge_partial(tq_agg *a, const tq_column *cols, int32_t mem) {
   if (!a) return TQ_ERR_INVALID_ARG;
+  if (a->final_mode) { set_error("a FinalMode handle takes its partial rows through tq_agg_put"); return TQ_ERR_STATE; }
   // partial rows of a var-len column would carry ids of the exporting handle's dictionary
   if (agg_has_varlen(a)) { set_error("partial export / merge with var-len columns is not supported"); return TQ_ERR_UNSUPPORTED_TYPE; }
   return agg_put_common(a, cols, mem, true, partial_width(a));

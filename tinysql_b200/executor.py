@@ -223,3 +223,27 @@ class HashAggExec:
                 break
             chunks.append(c)
         return Chunk.concat(chunks, self.types)
+
+
+class HashAggFinalExec(HashAggExec):
+    """FinalMode HashAggExec over pushed-down partial results (aggfuncs/builder.go:50-62,86-109; planner/core/task.go:564-625):
+    the child returns PARTIAL rows — the layout store/mockstore/mocktikv/aggregate.go:81-124 produces (per function its
+    GetPartialResult columns, then the GROUP BY columns).  funcs: list of (AGG_*, arg_col, arg_col2); arg_col2 is AVG's
+    partial-sum column (arg_col its partial count), -1 otherwise."""
+
+    def Open(self):
+        self.child.Open()
+        lib = L.load()
+        it = _i32arr(list(self.child.types))
+        gb = _i32arr(self.group_by)
+        fa = (L.TQAggFinalFunc * max(len(self.funcs), 1))(*[L.TQAggFinalFunc(f, a, b) for f, a, b in self.funcs])
+        d = L.TQAggFinalDesc(len(self.child.types), it, len(self.group_by), gb, len(self.funcs), fa, self.est_groups)
+        h = C.c_void_p()
+        L.check(lib.tq_agg_create_final(C.byref(d), C.byref(h)))
+        self.handle = h
+        self.types = []
+        for i in range(len(self.funcs)):
+            t = C.c_int32(0)
+            L.check(lib.tq_agg_output_type(h, i, C.byref(t)))
+            self.types.append(t.value)
+        self.prepared = False
