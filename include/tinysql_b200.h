@@ -325,13 +325,25 @@ int32_t tq_join_next_device(tq_join *j, tq_column *out_cols, int64_t *n_rows, in
  * [6] last build time in ns, [7] probe kernel launches.  */
 int32_t tq_join_stats(tq_join *j, int64_t *stats8);
 
-/* ------------------------------------------------------------------ chunk wire codec (host only)
+/* ------------------------------------------------------------------ chunk wire codec
  * chunk.Codec.Encode / DecodeToChunk (util/chunk/codec.go:42-143) — the bytes child readers hand up.  Decoding fills
  * tq_column VIEWS into the buffer (zero copy; null_bitmap == NULL for a column without NULLs), ready for
  * tq_join_put_* / tq_agg_put.  No device is needed for these three calls. */
 int32_t tq_chunk_encoded_size(int32_t n_cols, const int32_t *types, const tq_column *cols, int64_t *bytes);
 int32_t tq_chunk_encode(int32_t n_cols, const int32_t *types, const tq_column *cols, uint8_t *buffer, int64_t capacity, int64_t *written);
 int32_t tq_chunk_decode(const uint8_t *buffer, int64_t len, int32_t n_cols, const int32_t *types, tq_column *out, int64_t *consumed);
+
+/* Decoder for the device: the wire bytes cross PCIe once, as they are, and ONE kernel launch lays every column out in HBM
+ * (util/chunk/codec.go:92-143,246-353; distsql/select_result.go:102-141 is where the reference decodes on the CPU).
+ * out[c] receives DEVICE pointers — data (8-byte slots; 4-byte slots for FLOAT; the cells' bytes for var-len columns),
+ * offsets (var-len only) and null_bitmap (NULL when the column has no NULLs; otherwise 8-byte aligned words, tail bits 0) —
+ * which the TQ_MEM_DEVICE entry points accept as they are (tq_join_put_build / put_probe, tq_agg_put, tq_vec_*, tq_expr_eval:
+ * 8-byte column types).  *chunk == NULL creates a handle; passing the same handle again reuses its device memory (the
+ * previous columns become invalid).  The call returns after the bytes have left `buffer` and the columns are complete. */
+typedef struct tq_chunk_device tq_chunk_device;
+int32_t tq_chunk_decode_device(const uint8_t *buffer, int64_t len, int32_t n_cols, const int32_t *types, tq_chunk_device **chunk,
+                               tq_column *out, int64_t *consumed);
+int32_t tq_chunk_device_free(tq_chunk_device *chunk);
 
 /* ------------------------------------------------------------------ hash agg
  * Replaces HashAggExec + workers (executor/aggregate.go) and the aggfuncs it drives

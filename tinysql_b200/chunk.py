@@ -279,3 +279,54 @@ def decode_chunk(buf, types):
             d0 = (v.data - base) if v.data else 0
             cols.append(Column(tp, raw[d0: d0 + n * w].view(_NP[tp]).copy(), nn))
     return Chunk(cols), used.value
+
+
+class DeviceChunk:
+    """A chunk decoded straight into HBM (tq_chunk_decode_device): the wire bytes cross PCIe once and one kernel lays the
+    columns out.  `tq_cols` are device tq_column views for the TQ_MEM_DEVICE entry points; reuse one DeviceChunk for a stream
+    of wire chunks to decode without allocating."""
+
+    def __init__(self):
+        self.handle = C.c_void_p()
+        self.types, self.tq_cols, self.consumed = [], None, 0
+
+    def decode(self, buf, types):
+        lib = L.load()
+        raw = np.frombuffer(buf, dtype=np.uint8)
+        t = (C.c_int32 * max(len(types), 1))(*types)
+        out = (L.TQColumn * max(len(types), 1))()
+        used = C.c_int64(0)
+        L.check(lib.tq_chunk_decode_device(raw.ctypes.data if raw.size else None, raw.size, len(types), t, C.byref(self.handle), out, C.byref(used)))
+        self.types, self.tq_cols, self.consumed = list(types), out, used.value
+        return self
+
+    def to_host(self):
+        """copy the device columns back (tests / debugging)"""
+        lib = L.load()
+        cols = []
+        for tp, v in zip(self.types, self.tq_cols):
+            n = v.length
+            nn = None
+            if v.null_bitmap and n:
+                bm = np.zeros(bitmap_bytes(n), dtype=np.uint8)
+                L.check(lib.tq_memcpy_d2h(bm.ctypes.data, v.null_bitmap, bm.nbytes))
+                nn = unpack_not_null(bm, n)
+            if tp == BYTES:
+                offs = np.zeros(n + 1, dtype=np.int64)
+                L.check(lib.tq_memcpy_d2h(offs.ctypes.data, v.offsets, offs.nbytes))
+                data = np.zeros(max(int(offs[n]), 1), dtype=np.uint8)
+                if offs[n]:
+                    L.check(lib.tq_memcpy_d2h(data.ctypes.data, v.data, int(offs[n])))
+                cells = [data[offs[i]: offs[i + 1]].tobytes() for i in range(n)]
+                cols.append(VarColumn(BYTES, [c if (nn is None or nn[i]) else None for i, c in enumerate(cells)], nn))
+            else:
+                vals = np.zeros(n, dtype=_NP[tp])
+                if n:
+                    L.check(lib.tq_memcpy_d2h(vals.ctypes.data, v.data, vals.nbytes))
+                cols.append(Column(tp, vals, nn))
+        return Chunk(cols)
+
+    def free(self):
+        if self.handle:
+            L.load().tq_chunk_device_free(self.handle)
+            self.handle = C.c_void_p()

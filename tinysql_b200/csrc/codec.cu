@@ -2,10 +2,14 @@
 // (util/chunk/codec.go:42-143), the bytes child readers hand up (distsql/select_result.go:102-141).  Per column:
 //     u32 length | u32 nullCount | nullBitmap[(length+7)/8] (only if nullCount > 0)
 //     | int64 offsets[length+1] (var-len columns only) | data (length * fixedLen bytes, or offsets[length] bytes)
-// Host-only code (no kernel, no device needed): decoding yields tq_column VIEWS into the buffer — zero copy — which can be
+// Host side (no kernel, no device needed): decoding yields tq_column VIEWS into the buffer — zero copy — which can be
 // passed straight to tq_join_put_probe / tq_agg_put; when the buffer lives in pinned memory (tq_pinned_alloc) the
 // scan -> join path needs no host-side copy at all.
+// Device side (tq_chunk_decode_device): the wire bytes cross PCIe ONCE, as they are, and k_chunk_unpack lays the columns
+// out in HBM (8-byte aligned data / offsets / bitmap words, tail bits zeroed) ready for the TQ_MEM_DEVICE entry points —
+// the host never touches the payload.
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -29,7 +33,46 @@ int64_t null_count(const tq_column &c) {  // Column.nullCount, column.go:94-104:
   return c.length - ones;
 }
 
+// One contiguous piece of a wire-format column (bitmap, offsets or data) on its way to an aligned device array.
+struct UnpackSeg {
+  uint64_t src_off;     // byte offset inside the blob — ANY alignment (the wire format packs columns back to back)
+  uint64_t *dst;        // 8-byte aligned destination
+  uint64_t n_words;     // 8-byte words to write (the destination is padded to whole words)
+  uint64_t valid_bits;  // bits of the piece that carry data; everything above is written as 0
+};
+static constexpr int UNPACK_MAX_SEGS = 48;
+struct UnpackParams {
+  const uint8_t *blob;
+  int n_segs;
+  UnpackSeg seg[UNPACK_MAX_SEGS];
+};
+
+// blockIdx.y = piece; grid-stride over its destination words.  A destination word is assembled from the two aligned
+// source words it straddles (funnel shift by the piece's misalignment); loads stay inside [blob, blob + len + 16).
+__global__ void __launch_bounds__(256) k_chunk_unpack(const UnpackParams p) {
+  const UnpackSeg s = p.seg[blockIdx.y];
+  const uint64_t *a = reinterpret_cast<const uint64_t *>(p.blob + (s.src_off & ~7ull));
+  const unsigned sh = (unsigned)(s.src_off & 7ull) * 8u;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n_words; i += stride) {
+    uint64_t v = 0;
+    const uint64_t first_bit = i * 64;
+    if (first_bit < s.valid_bits) {
+      const uint64_t lo = a[i];
+      v = lo;
+      if (sh) v = (lo >> sh) | (a[i + 1] << (64u - sh));
+      const uint64_t keep = s.valid_bits - first_bit;
+      if (keep < 64) v &= (1ull << keep) - 1ull;
+    }
+    s.dst[i] = v;
+  }
+}
+
 }  // namespace
+
+struct tq_chunk_device {
+  tq::DevBuf blob, arena;   // grow-only: a handle that is reused decodes without allocating
+};
 
 extern "C" {
 
@@ -125,6 +168,101 @@ int32_t tq_chunk_decode(const uint8_t *buffer, int64_t len, int32_t n_cols, cons
     p += data_bytes;
   }
   *consumed = p - buffer;
+  return TQ_OK;
+}
+
+// Decoder for the device (util/chunk/codec.go:92-143, 246-353; the consumer side of distsql/select_result.go:102-141).
+// Parses the headers on the host (a few bytes per column), ships buffer[0, consumed) to HBM in one copy and unpacks every
+// column with ONE kernel launch.  out[c] receives DEVICE pointers (null_bitmap == NULL: no NULLs; var-len columns:
+// offsets + data; FLOAT: 4-byte slots), valid until the handle is decoded into again or freed.
+int32_t tq_chunk_decode_device(const uint8_t *buffer, int64_t len, int32_t n_cols, const int32_t *types, tq_chunk_device **chunk,
+                               tq_column *out, int64_t *consumed) {
+  if (!chunk || (n_cols > 0 && !out) || n_cols > UNPACK_MAX_SEGS / 3) { if (chunk) tq::set_error("chunk codec: more than %d columns", UNPACK_MAX_SEGS / 3); return TQ_ERR_INVALID_ARG; }
+  std::vector<tq_column> view((size_t)(n_cols > 0 ? n_cols : 1));
+  TQ_TRY(tq_chunk_decode(buffer, len, n_cols, types, view.data(), consumed));   // validates sizes; views are host pointers
+  TQ_TRY(tq::ensure_init());
+  tq::Runtime &r = tq::rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  tq_chunk_device *h = *chunk ? *chunk : new tq_chunk_device();
+  auto fail = [&](int32_t st) { if (!*chunk) delete h; return st; };
+  // arena layout: per column bitmap words (+1 pad word: kernels read bitmaps as 32-bit words), offsets, data
+  UnpackParams p{};
+  uint64_t arena_words = 0;
+  std::vector<uint64_t> dst_word((size_t)n_cols * 3 + 1, 0);
+  for (int c = 0; c < n_cols; c++) {
+    const tq_column &v = view[c];
+    const int64_t n = v.length;
+    const int fl = fixed_len(types[c]);
+    if (v.null_bitmap) {
+      UnpackSeg &sg = p.seg[p.n_segs];
+      sg.src_off = (uint64_t)(v.null_bitmap - buffer);
+      sg.valid_bits = (uint64_t)n;
+      sg.n_words = (uint64_t)((n + 63) >> 6) + 1;
+      dst_word[p.n_segs++] = arena_words;
+      arena_words += sg.n_words;
+    }
+    if (fl < 0) {
+      UnpackSeg &sg = p.seg[p.n_segs];
+      sg.src_off = (uint64_t)(reinterpret_cast<const uint8_t *>(v.offsets) - buffer);
+      sg.valid_bits = (uint64_t)(n + 1) * 64;
+      sg.n_words = (uint64_t)(n + 1);
+      dst_word[p.n_segs++] = arena_words;
+      arena_words += sg.n_words;
+    }
+    int64_t data_bytes = n * fl;
+    if (fl < 0) memcpy(&data_bytes, reinterpret_cast<const uint8_t *>(v.offsets) + n * 8, 8);
+    {
+      UnpackSeg &sg = p.seg[p.n_segs];
+      sg.src_off = (uint64_t)(v.data - buffer);
+      sg.valid_bits = (uint64_t)data_bytes * 8;
+      sg.n_words = (uint64_t)((data_bytes + 7) >> 3) + 1;   // at least one word: data is never a NULL pointer
+      dst_word[p.n_segs++] = arena_words;
+      arena_words += sg.n_words;
+    }
+  }
+  int32_t st = h->blob.reserve((size_t)*consumed + 32);
+  if (st == TQ_OK) st = h->arena.reserve((size_t)(arena_words ? arena_words : 1) * 8);
+  if (st != TQ_OK) return fail(st);
+  uint64_t max_words = 0;
+  for (int i = 0; i < p.n_segs; i++) { p.seg[i].dst = h->arena.as<uint64_t>() + dst_word[i]; if (p.seg[i].n_words > max_words) max_words = p.seg[i].n_words; }
+  p.blob = h->blob.as<uint8_t>();
+  cudaStream_t s = r.compute;
+  if (*consumed > 0) {
+    cudaError_t e = cudaMemcpyAsync(h->blob.p, buffer, (size_t)*consumed, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return fail(tq::cuda_fail(e, "cudaMemcpyAsync(chunk blob)", __FILE__, __LINE__));
+  }
+  if (p.n_segs > 0) {
+    uint64_t bx = (max_words + 255) / 256;
+    const uint64_t cap = (uint64_t)r.sm_count * 8;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    k_chunk_unpack<<<dim3((unsigned)bx, (unsigned)p.n_segs), 256, 0, s>>>(p);
+    tq::count_launch();
+    st = tq::check_launch("k_chunk_unpack");
+    if (st != TQ_OK) return fail(st);
+  }
+  // the caller may reuse `buffer` and hand the columns to any entry point as soon as this returns
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail(tq::cuda_fail(e, "cudaStreamSynchronize(chunk decode)", __FILE__, __LINE__));
+  int sg = 0;
+  for (int c = 0; c < n_cols; c++) {
+    const tq_column &v = view[c];
+    out[c].length = v.length;
+    out[c].null_bitmap = nullptr;
+    out[c].offsets = nullptr;
+    if (v.null_bitmap) out[c].null_bitmap = reinterpret_cast<uint8_t *>(p.seg[sg++].dst);
+    if (fixed_len(types[c]) < 0) out[c].offsets = reinterpret_cast<int64_t *>(p.seg[sg++].dst);
+    out[c].data = reinterpret_cast<uint8_t *>(p.seg[sg++].dst);
+  }
+  *chunk = h;
+  return TQ_OK;
+}
+
+int32_t tq_chunk_device_free(tq_chunk_device *chunk) {
+  if (!chunk) return TQ_OK;
+  tq::Runtime &r = tq::rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  delete chunk;
   return TQ_OK;
 }
 
