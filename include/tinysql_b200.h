@@ -427,6 +427,59 @@ typedef struct tq_agg_final_desc {
 
 int32_t tq_agg_create_final(const tq_agg_final_desc *desc, tq_agg **out);
 
+/* ------------------------------------------------------------------ sort / top-n / merge join
+ * SortExec and TopNExec (executor/sort.go:28-157, 159-318): put every child chunk, eof, then next until eof.
+ * ByItems are column references (the shim pre-projects expressions) with a Desc flag; the comparator is
+ * chunk.GetCompareFunc (util/chunk/compare.go:27-110): NULL first, then signed / unsigned / float / byte-string order; Desc
+ * reverses the whole comparison (NULLs last).  Rows that compare equal keep child order (sort.Slice promises no order for
+ * them).  limit_count >= 0 makes it a TopNExec returning rows [limit_offset, limit_offset + limit_count) of the order
+ * (sort.go:210-214); limit_count < 0 is a SortExec.  All three chunk layouts, as keys and as payload. */
+typedef struct tq_sort_desc {
+  int32_t n_cols;
+  const int32_t *types;     /* TQ_TYPE_* per child column */
+  int32_t n_by;             /* 0..8 ByItems */
+  const int32_t *by_cols;   /* column index of ByItems[i].Expr */
+  const int32_t *by_desc;   /* ByItems[i].Desc */
+  int64_t limit_offset;
+  int64_t limit_count;
+} tq_sort_desc;
+typedef struct tq_sort tq_sort;
+int32_t tq_sort_create(const tq_sort_desc *desc, tq_sort **out);
+int32_t tq_sort_put(tq_sort *s, const tq_column *cols, int32_t mem);   /* host chunks */
+int32_t tq_sort_eof(tq_sort *s);
+int32_t tq_sort_next_bytes(tq_sort *s, int64_t max_rows, int64_t *bytes_per_col);
+int32_t tq_sort_next(tq_sort *s, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+int32_t tq_sort_destroy(tq_sort *s);
+
+/* MergeJoinExec (executor/merge_join.go:31-373).  Both children deliver rows sorted ascending by their join keys (the planner
+ * guarantees it, exhaust_physical_plans.go:281-295; an unsorted inner child is reported as TQ_ERR_STATE).  Inner rows with a
+ * NULL key are skipped (merge_join.go:154-162); an outer row that fails the outer filter (`selected`), has a NULL key or finds
+ * no inner row with an equal key takes the joiner's miss path: outer joins emit it padded with NULLs / defaultInner
+ * (joiner.go:139-143), inner joins drop it.  Output order = outer child order, inner child order inside a key group —
+ * the order joinToChunk produces (merge_join.go:246-321).  Output schema = left child columns ++ right child columns.
+ * Key pairs must share an evaluation type (int incl. signed/unsigned mixes, real incl. FLOAT, string). */
+typedef struct tq_mjoin_desc {
+  int32_t join_type;        /* TQ_JOIN_* */
+  int32_t outer_is_right;   /* 1: the inner child is the left child */
+  int32_t n_inner_cols;
+  const int32_t *inner_types;
+  int32_t n_outer_cols;
+  const int32_t *outer_types;
+  int32_t n_keys;
+  const int32_t *inner_keys;
+  const int32_t *outer_keys;
+  const uint64_t *default_inner_bits;       /* per inner column, may be NULL: the 8 value bytes of its default */
+  const uint8_t *default_inner_not_null;    /* per inner column, may be NULL (= all NULL): 1 = the default is a value */
+} tq_mjoin_desc;
+typedef struct tq_mjoin tq_mjoin;
+int32_t tq_mjoin_create(const tq_mjoin_desc *desc, tq_mjoin **out);
+int32_t tq_mjoin_put_inner(tq_mjoin *j, const tq_column *cols, int32_t mem);                          /* host chunks */
+int32_t tq_mjoin_put_outer(tq_mjoin *j, const tq_column *cols, const uint8_t *selected, int32_t mem); /* selected: Go []bool or NULL */
+int32_t tq_mjoin_finish(tq_mjoin *j);   /* both children exhausted */
+int32_t tq_mjoin_next_bytes(tq_mjoin *j, int64_t max_rows, int64_t *bytes_per_col);
+int32_t tq_mjoin_next(tq_mjoin *j, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+int32_t tq_mjoin_destroy(tq_mjoin *j);
+
 /* ------------------------------------------------------------- radix exchange
  * The shard boundary of the multi-GPU path: splits rows into n_parts partitions by
  * the key's hash (the moral equivalent of shuffleIntermData, aggregate.go:352-356).

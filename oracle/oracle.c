@@ -1088,3 +1088,144 @@ int orc_vec_filter_real(int64_t n, const orc_column *a, uint8_t *selected) {
   return ORC_OK;
 }
 
+/* ------------------------------------------------------------------ SortExec / TopNExec / MergeJoinExec
+ * chunk.GetCompareFunc (util/chunk/compare.go:27-110): cmpNull first, then the type's comparison.  kind: the column type. */
+static int cmp_cell(int type, const orc_column *a, int64_t ra, const orc_column *b, int64_t rb) {
+  int an = col_is_null(a, ra), bn = col_is_null(b, rb);
+  if (an || bn) return (an && bn) ? 0 : (an ? -1 : 1);                       /* cmpNull :45-53 */
+  switch (type) {
+    case ORC_TYPE_INT64: { int64_t x = col_i64(a, ra), y = col_i64(b, rb); return x < y ? -1 : (x == y ? 0 : 1); }      /* cmpInt64 :55-61 */
+    case ORC_TYPE_UINT64: { uint64_t x = col_u64(a, ra), y = col_u64(b, rb); return x < y ? -1 : (x == y ? 0 : 1); }    /* cmpUint64 :63-69 */
+    case ORC_TYPE_FLOAT64: return cmp_f64(col_f64(a, ra), col_f64(b, rb));                                                /* cmpFloat64 :87-93 */
+    case ORC_TYPE_FLOAT32: { float x, y; memcpy(&x, a->data + 4 * ra, 4); memcpy(&y, b->data + 4 * rb, 4); return cmp_f64((double)x, (double)y); } /* cmpFloat32 :79-85 */
+    default: return compare_string(a->data + a->offsets[ra], a->offsets[ra + 1] - a->offsets[ra],
+                                   b->data + b->offsets[rb], b->offsets[rb + 1] - b->offsets[rb]);                       /* cmpString :71-77 */
+  }
+}
+
+/* SortExec.Next / keyColumnsLess / lessRow (executor/sort.go:58-129) and TopNExec (:159-318).  The reference sorts row
+ * pointers with sort.Slice, which leaves rows that compare equal in an unspecified order; the oracle fixes ONE of the
+ * allowed outcomes — ties stay in child order (a bottom-up merge sort) — and the tests state that contract.  TopNExec keeps
+ * the totalLimit = Offset + Count smallest rows in a heap and emits them from Offset on (:210-214, :262-279): the rows
+ * [Offset, Offset + Count) of the full order.  limit_count < 0: SortExec. */
+typedef struct { int n_by; const int *by_cols, *by_desc, *types; const orc_column *cols; } sort_ctx;
+static int sort_less_eq(const sort_ctx *c, int64_t i, int64_t j) {   /* !lessRow(j, i) */
+  for (int k = 0; k < c->n_by; k++) {
+    int col = c->by_cols[k];
+    int cmp = cmp_cell(c->types[col], &c->cols[col], j, &c->cols[col], i);
+    if (c->by_desc[k]) cmp = -cmp;                                            /* sort.go:120-122 */
+    if (cmp < 0) return 0;                                                    /* row j sorts before row i */
+    if (cmp > 0) return 1;
+  }
+  return 1;
+}
+int orc_sort(int n_cols, const int *types, const orc_column *cols, int64_t n_rows, int n_by, const int *by_cols, const int *by_desc,
+             int64_t limit_offset, int64_t limit_count, orc_column *out_cols, int64_t *n_out) {
+  for (int c = 0; c < n_cols; c++) if (types[c] < 1 || types[c] > 5) return ORC_ERR_UNSUPPORTED;
+  for (int k = 0; k < n_by; k++) if (by_cols[k] < 0 || by_cols[k] >= n_cols) return ORC_ERR_INVALID;
+  sort_ctx ctx = {n_by, by_cols, by_desc, types, cols};
+  int64_t *ptr = (int64_t *)malloc(8 * (size_t)(n_rows ? n_rows : 1)), *tmp = (int64_t *)malloc(8 * (size_t)(n_rows ? n_rows : 1));
+  for (int64_t i = 0; i < n_rows; i++) ptr[i] = i;                            /* initPointers :88-97 */
+  for (int64_t w = 1; w < n_rows; w *= 2) {
+    for (int64_t lo = 0; lo < n_rows; lo += 2 * w) {
+      int64_t mid = lo + w < n_rows ? lo + w : n_rows, hi = lo + 2 * w < n_rows ? lo + 2 * w : n_rows;
+      int64_t a = lo, b = mid, o = lo;
+      while (a < mid && b < hi) tmp[o++] = sort_less_eq(&ctx, ptr[a], ptr[b]) ? ptr[a++] : ptr[b++];
+      while (a < mid) tmp[o++] = ptr[a++];
+      while (b < hi) tmp[o++] = ptr[b++];
+    }
+    int64_t *t = ptr; ptr = tmp; tmp = t;
+  }
+  int64_t lo = limit_offset < n_rows ? limit_offset : n_rows, hi = n_rows;
+  if (limit_count >= 0) hi = (limit_count < n_rows - lo) ? lo + limit_count : n_rows;
+  outbuf *obs = (outbuf *)calloc((size_t)(n_cols ? n_cols : 1), sizeof(outbuf));
+  for (int c = 0; c < n_cols; c++) obs[c].elem = elem_of_type(types[c]);
+  for (int64_t i = lo; i < hi; i++) append_row(obs, 0, n_cols, cols, ptr[i]);   /* req.AppendRow(e.rowChunks.GetRow(rowPtr)) :71-75 */
+  *n_out = hi - lo;
+  for (int c = 0; c < n_cols; c++) ob_finish(&obs[c], &out_cols[c]);
+  free(obs); free(ptr); free(tmp);
+  return ORC_OK;
+}
+
+/* MergeJoinExec (executor/merge_join.go).  Children sorted ascending by their keys.  compare() (:323-337) uses the
+ * expression CompareFuncs: NULL outer key -> compareNull = -1 (a miss); integers by CompareInt incl. mixed unsigned flags
+ * (builtin_compare.go:525-560), reals by CompareFloat64 (FLOAT columns evaluate as float64), strings by CompareString. */
+static int mj_cmp_key(int to, const orc_column *o, int64_t ro, int ti, const orc_column *i, int64_t ri) {
+  if (col_is_null(o, ro)) return -1;                                          /* the inner row never has a NULL key (:154-162) */
+  if (to == ORC_TYPE_BYTES) return compare_string(o->data + o->offsets[ro], o->offsets[ro + 1] - o->offsets[ro], i->data + i->offsets[ri], i->offsets[ri + 1] - i->offsets[ri]);
+  if (to == ORC_TYPE_FLOAT64 || to == ORC_TYPE_FLOAT32) {
+    uint64_t a = cell_word(to, o, ro), b = cell_word(ti, i, ri); double x, y; memcpy(&x, &a, 8); memcpy(&y, &b, 8);
+    return cmp_f64(x, y);
+  }
+  return cmp_int(to == ORC_TYPE_UINT64, ti == ORC_TYPE_UINT64, col_i64(o, ro), col_i64(i, ri));
+}
+/* mergeJoinInnerTable: nextRow (:127-152) skips rows with a NULL join key; rowsWithSameKey (:96-125) returns the next run of
+ * rows whose keys compare equal to the run's first row */
+typedef struct { int n_keys; const int *keys, *types; const orc_column *cols; int64_t n, ip; int64_t *grp; int64_t g_n; } mj_inner;
+static int mj_inner_null_key(const mj_inner *t, int64_t r) {
+  for (int k = 0; k < t->n_keys; k++) if (col_is_null(&t->cols[t->keys[k]], r)) return 1;
+  return 0;
+}
+static void mj_fetch_group(mj_inner *t) {
+  t->g_n = 0;
+  while (t->ip < t->n && mj_inner_null_key(t, t->ip)) t->ip++;
+  if (t->ip >= t->n) return;
+  int64_t first = t->ip;
+  t->grp[t->g_n++] = t->ip++;
+  for (;;) {
+    while (t->ip < t->n && mj_inner_null_key(t, t->ip)) t->ip++;
+    if (t->ip >= t->n) return;
+    for (int k = 0; k < t->n_keys; k++)
+      if (cmp_cell(t->types[t->keys[k]], &t->cols[t->keys[k]], t->ip, &t->cols[t->keys[k]], first) != 0) return;   /* compareChunkRow != 0 */
+    t->grp[t->g_n++] = t->ip++;
+  }
+}
+int orc_merge_join(int join_type, int outer_is_right,
+                   int n_inner_cols, const int *inner_types, const orc_column *inner_cols,
+                   int n_outer_cols, const int *outer_types, const orc_column *outer_cols,
+                   int n_keys, const int *inner_keys, const int *outer_keys, const uint8_t *selected,
+                   const uint64_t *default_bits, const uint8_t *default_nn, orc_column *out_cols, int64_t *n_out) {
+  if (join_type < 0 || join_type > 2 || n_keys < 0) return ORC_ERR_INVALID;
+  for (int c = 0; c < n_inner_cols; c++) if (inner_types[c] < 1 || inner_types[c] > 5) return ORC_ERR_UNSUPPORTED;
+  for (int c = 0; c < n_outer_cols; c++) if (outer_types[c] < 1 || outer_types[c] > 5) return ORC_ERR_UNSUPPORTED;
+  int64_t ni = n_inner_cols ? inner_cols[0].length : 0, no = n_outer_cols ? outer_cols[0].length : 0;
+  int ncols = n_inner_cols + n_outer_cols;
+  outbuf *obs = (outbuf *)calloc((size_t)ncols, sizeof(outbuf));
+  int inner_base = outer_is_right ? 0 : n_outer_cols, outer_base = outer_is_right ? n_inner_cols : 0;
+  for (int c = 0; c < n_inner_cols; c++) obs[inner_base + c].elem = elem_of_type(inner_types[c]);
+  for (int c = 0; c < n_outer_cols; c++) obs[outer_base + c].elem = elem_of_type(outer_types[c]);
+  int is_outer = join_type != 0;
+  mj_inner in = {n_keys, inner_keys, inner_types, inner_cols, ni, 0, (int64_t *)malloc(8 * (size_t)(ni ? ni : 1)), 0};
+  mj_fetch_group(&in);                           /* prepare -> fetchNextInnerRows (:217-223) */
+  int64_t o = 0;
+  while (o < no) {                               /* joinToChunk (:246-321) */
+    int cmp = -1;
+    if ((selected ? selected[o] != 0 : 1) && in.g_n > 0) {
+      cmp = 0;
+      for (int k = 0; k < n_keys && cmp == 0; k++)
+        cmp = mj_cmp_key(outer_types[outer_keys[k]], &outer_cols[outer_keys[k]], o, inner_types[inner_keys[k]], &inner_cols[inner_keys[k]], in.grp[0]);
+    }
+    if (cmp > 0) { mj_fetch_group(&in); continue; }    /* :267-272 */
+    if (cmp < 0) {                               /* onMissMatch (:274-288) */
+      if (is_outer) {
+        for (int c = 0; c < n_inner_cols; c++) {
+          if (default_nn && default_nn[c] && elem_of_type(inner_types[c]) == 8) ob_push(&obs[inner_base + c], default_bits[c], 1);
+          else ob_push_cell(&obs[inner_base + c], &inner_cols[c], -1);
+        }
+        append_row(obs, outer_base, n_outer_cols, outer_cols, o);
+      }
+      o++;
+      continue;
+    }
+    for (int64_t g = 0; g < in.g_n; g++) {      /* tryToMatchInners over the whole group (:290-305); no OtherConditions */
+      append_row(obs, inner_base, n_inner_cols, inner_cols, in.grp[g]);
+      append_row(obs, outer_base, n_outer_cols, outer_cols, o);
+    }
+    o++;
+  }
+  free(in.grp);
+  *n_out = ncols ? obs[0].n : 0;
+  for (int c = 0; c < ncols; c++) ob_finish(&obs[c], &out_cols[c]);
+  free(obs);
+  return ORC_OK;
+}

@@ -86,6 +86,17 @@ int orc_hash_agg_final(int n_input_cols, const int *types, const orc_column *col
                        int n_group_by, const int *group_by_cols, int n_funcs, const orc_agg_final_func *funcs,
                        orc_column *out_cols, int64_t *n_out);
 
+/* SortExec / TopNExec (executor/sort.go) and MergeJoinExec (executor/merge_join.go).  orc_sort keeps rows that compare equal
+ * in child order (one of the outcomes sort.Slice may produce); limit_count < 0 = SortExec, else the rows
+ * [limit_offset, limit_offset + limit_count) of the order.  orc_merge_join expects both inputs sorted ascending by their keys. */
+int orc_sort(int n_cols, const int *types, const orc_column *cols, int64_t n_rows, int n_by, const int *by_cols, const int *by_desc,
+             int64_t limit_offset, int64_t limit_count, orc_column *out_cols, int64_t *n_out);
+int orc_merge_join(int join_type, int outer_is_right,
+                   int n_inner_cols, const int *inner_types, const orc_column *inner_cols,
+                   int n_outer_cols, const int *outer_types, const orc_column *outer_cols,
+                   int n_keys, const int *inner_keys, const int *outer_keys, const uint8_t *selected,
+                   const uint64_t *default_bits, const uint8_t *default_nn, orc_column *out_cols, int64_t *n_out);
+
 /* vectorized builtins — restated statement by statement from expression/builtin_*_vec*.go */
 int orc_vec_compare_int(int op, int64_t n, const orc_column *a, int a_unsigned, const orc_column *b,
                         int b_unsigned, orc_column *out);

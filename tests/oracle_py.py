@@ -157,6 +157,43 @@ def hash_agg_final(types, cols, group_by, funcs):
     return rc, res
 
 
+def sort(types, cols, by, limit_offset=0, limit_count=-1):
+    """SortExec / TopNExec; by = [(col, desc)].  Ties keep child order."""
+    lib = load()
+    n_rows = cols[0].length if cols else 0
+    out = (TQColumn * max(len(cols), 1))()
+    n = C.c_int64(0)
+    rc = lib.orc_sort(C.c_int(len(cols)), _i32(types), tq_array(cols), C.c_int64(n_rows), C.c_int(len(by)), _i32([c for c, _ in by]),
+                      _i32([1 if d else 0 for _, d in by]), C.c_int64(limit_offset), C.c_int64(limit_count), out, C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"oracle sort failed: {rc}")
+    res = Chunk(_take(out, types, n.value))
+    lib.orc_free_columns(C.c_int(len(cols)), out)
+    return res
+
+
+def merge_join(join_type, outer_is_right, inner_types, inner_cols, outer_types, outer_cols, inner_keys, outer_keys, selected=None, default_inner=None):
+    """MergeJoinExec over inputs sorted ascending by their keys; output = left ++ right, outer order x inner order"""
+    lib = load()
+    ncols = len(inner_cols) + len(outer_cols)
+    out = (TQColumn * ncols)()
+    n = C.c_int64(0)
+    sel = np.ascontiguousarray(selected, dtype=np.uint8) if selected is not None else None
+    dbits = dnn = None
+    if default_inner is not None:
+        dbits = (C.c_uint64 * len(inner_cols))(*[0 if v is None else int(np.array([v], dtype=_NP[t]).view(np.uint64)[0]) for v, t in zip(default_inner, inner_types)])
+        dnn = (C.c_uint8 * len(inner_cols))(*[0 if v is None else 1 for v in default_inner])
+    rc = lib.orc_merge_join(C.c_int(join_type), C.c_int(1 if outer_is_right else 0), C.c_int(len(inner_cols)), _i32(inner_types), tq_array(inner_cols),
+                            C.c_int(len(outer_cols)), _i32(outer_types), tq_array(outer_cols), C.c_int(len(inner_keys)), _i32(inner_keys), _i32(outer_keys),
+                            C.c_void_p(sel.ctypes.data) if sel is not None else None, dbits, dnn, out, C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"oracle merge join failed: {rc}")
+    types = (list(inner_types) + list(outer_types)) if outer_is_right else (list(outer_types) + list(inner_types))
+    res = Chunk(_take(out, types, n.value))
+    lib.orc_free_columns(C.c_int(ncols), out)
+    return res
+
+
 def _vec(fn, out_tp, n, *args):
     out = Column.empty(out_tp, n)
     to = out.tq()

@@ -52,6 +52,17 @@ class TQAggFinalDesc(C.Structure):
                 ("est_groups", C.c_int64)]
 
 
+class TQSortDesc(C.Structure):
+    _fields_ = [("n_cols", C.c_int32), ("types", C.POINTER(C.c_int32)), ("n_by", C.c_int32), ("by_cols", C.POINTER(C.c_int32)),
+                ("by_desc", C.POINTER(C.c_int32)), ("limit_offset", C.c_int64), ("limit_count", C.c_int64)]
+
+
+class TQMJoinDesc(C.Structure):
+    _fields_ = [("join_type", C.c_int32), ("outer_is_right", C.c_int32), ("n_inner_cols", C.c_int32), ("inner_types", C.POINTER(C.c_int32)),
+                ("n_outer_cols", C.c_int32), ("outer_types", C.POINTER(C.c_int32)), ("n_keys", C.c_int32), ("inner_keys", C.POINTER(C.c_int32)),
+                ("outer_keys", C.POINTER(C.c_int32)), ("default_inner_bits", C.POINTER(C.c_uint64)), ("default_inner_not_null", C.POINTER(C.c_uint8))]
+
+
 # every symbol include/tinysql_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _COL = C.POINTER(TQColumn)
@@ -110,6 +121,18 @@ SYMBOLS = {
     "tq_agg_partial_width": (_I32, [_P, C.POINTER(_I32)]),
     "tq_agg_export_partial": (_I32, [_P, _COL, C.POINTER(_I64)]),
     "tq_agg_merge_partial": (_I32, [_P, _COL, _I32]),
+    "tq_sort_create": (_I32, [C.POINTER(TQSortDesc), C.POINTER(_P)]),
+    "tq_sort_put": (_I32, [_P, _COL, _I32]), "tq_sort_eof": (_I32, [_P]),
+    "tq_sort_next_bytes": (_I32, [_P, _I64, C.POINTER(_I64)]),
+    "tq_sort_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
+    "tq_sort_destroy": (_I32, [_P]),
+    "tq_mjoin_create": (_I32, [C.POINTER(TQMJoinDesc), C.POINTER(_P)]),
+    "tq_mjoin_put_inner": (_I32, [_P, _COL, _I32]),
+    "tq_mjoin_put_outer": (_I32, [_P, _COL, _P, _I32]),
+    "tq_mjoin_finish": (_I32, [_P]),
+    "tq_mjoin_next_bytes": (_I32, [_P, _I64, C.POINTER(_I64)]),
+    "tq_mjoin_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
+    "tq_mjoin_destroy": (_I32, [_P]),
     "tq_partition_device": (_I32, [_I32, _COL, C.POINTER(_I32), _I32, _I64, _I32, _COL, C.POINTER(_I64)]),
     "tq_enable_peer_access": (_I32, [_I32]),
     "tq_ipc_get_handle": (_I32, [_P, _P]), "tq_ipc_open_handle": (_I32, [_P, C.POINTER(_P)]), "tq_ipc_close_handle": (_I32, [_P]),

@@ -247,3 +247,138 @@ class HashAggFinalExec(HashAggExec):
             L.check(lib.tq_agg_output_type(h, i, C.byref(t)))
             self.types.append(t.value)
         self.prepared = False
+
+
+def _drain_result(lib, types, req, next_bytes, nxt, handle):
+    """one Next() of an operator that hands out a materialised result in <= req-row chunks"""
+    out = [VarColumn.empty(BYTES, req) if t == BYTES else Column.empty(t, req) for t in types]
+    if BYTES in types:
+        need = (C.c_int64 * len(types))()
+        L.check(next_bytes(handle, req, need))
+        for i, t in enumerate(types):
+            if t == BYTES:
+                out[i] = VarColumn.empty(BYTES, req, int(need[i]))
+    n, eof = C.c_int64(0), C.c_int32(0)
+    L.check(nxt(handle, req, tq_array(out, req), C.byref(n), C.byref(eof)))
+    k = n.value
+    return Chunk([c.head(k) if t == BYTES else Column(t, c.values[:k], c.not_null()[:k]) for t, c in zip(types, out)])
+
+
+class SortExec:
+    """executor/sort.go:28-157.  by_items: list of (column index, desc).  Ties keep child order (sort.Slice promises none)."""
+
+    def __init__(self, child, by_items, max_chunk_size=MAX_CHUNK_SIZE):
+        self.child, self.by_items, self.max_chunk_size = child, list(by_items), max_chunk_size
+        self.limit_offset, self.limit_count = 0, -1
+        self.handle, self.fetched = None, False
+        self.types = list(child.types)
+
+    def Open(self):
+        self.child.Open()
+        lib = L.load()
+        d = L.TQSortDesc(len(self.types), _i32arr(self.types), len(self.by_items), _i32arr([c for c, _ in self.by_items]),
+                         _i32arr([1 if x else 0 for _, x in self.by_items]), self.limit_offset, self.limit_count)
+        h = C.c_void_p()
+        L.check(lib.tq_sort_create(C.byref(d), C.byref(h)))
+        self.handle, self.fetched = h, False
+
+    def Next(self, required_rows=None):
+        lib = L.load()
+        if not self.fetched:  # fetchRowChunks (sort.go:77-86)
+            while True:
+                chk = self.child.Next()
+                if chk.num_rows() == 0:
+                    break
+                L.check(lib.tq_sort_put(self.handle, tq_array(chk.cols), L.TQ_MEM_HOST))
+            L.check(lib.tq_sort_eof(self.handle))
+            self.fetched = True
+        return _drain_result(lib, self.types, required_rows or self.max_chunk_size, lib.tq_sort_next_bytes, lib.tq_sort_next, self.handle)
+
+    def Close(self):
+        if self.handle is not None:
+            L.load().tq_sort_destroy(self.handle)
+            self.handle = None
+        self.child.Close()
+
+    def drain(self):
+        chunks = []
+        while True:
+            c = self.Next()
+            if c.num_rows() == 0:
+                break
+            chunks.append(c)
+        return Chunk.concat(chunks, self.types)
+
+
+class TopNExec(SortExec):
+    """executor/sort.go:159-318: the rows [offset, offset + count) of the order (plannercore.PhysicalLimit)."""
+
+    def __init__(self, child, by_items, offset, count, max_chunk_size=MAX_CHUNK_SIZE):
+        super().__init__(child, by_items, max_chunk_size)
+        self.limit_offset, self.limit_count = int(offset), int(count)
+
+
+class MergeJoinExec:
+    """executor/merge_join.go:31-373.  Both children sorted ascending by their keys; output = left ++ right in outer order."""
+
+    def __init__(self, outer_exec, inner_exec, outer_keys, inner_keys, join_type=INNER_JOIN, outer_is_right=False, outer_filter=None,
+                 max_chunk_size=MAX_CHUNK_SIZE, default_inner=None):
+        self.outer, self.inner = outer_exec, inner_exec
+        self.outer_keys, self.inner_keys = list(outer_keys), list(inner_keys)
+        self.join_type, self.outer_is_right, self.outer_filter = join_type, outer_is_right, outer_filter
+        self.max_chunk_size, self.default_inner = max_chunk_size, default_inner
+        self.handle, self.prepared = None, False
+        self.types = (list(inner_exec.types) + list(outer_exec.types)) if outer_is_right else (list(outer_exec.types) + list(inner_exec.types))
+
+    def Open(self):
+        self.outer.Open()
+        self.inner.Open()
+        lib = L.load()
+        dbits = dnn = None
+        if self.default_inner is not None:
+            from .chunk import _NP
+            nb = len(self.inner.types)
+            dbits = (C.c_uint64 * nb)(*[0 if v is None else int(np.array([v], dtype=_NP[t]).view(np.uint64)[0]) for v, t in zip(self.default_inner, self.inner.types)])
+            dnn = (C.c_uint8 * nb)(*[0 if v is None else 1 for v in self.default_inner])
+        self._keep = (dbits, dnn)
+        d = L.TQMJoinDesc(self.join_type, 1 if self.outer_is_right else 0, len(self.inner.types), _i32arr(self.inner.types), len(self.outer.types),
+                          _i32arr(self.outer.types), len(self.inner_keys), _i32arr(self.inner_keys), _i32arr(self.outer_keys), dbits, dnn)
+        h = C.c_void_p()
+        L.check(lib.tq_mjoin_create(C.byref(d), C.byref(h)))
+        self.handle, self.prepared = h, False
+
+    def Next(self, required_rows=None):
+        lib = L.load()
+        if not self.prepared:
+            while True:  # mergeJoinInnerTable.nextRow's reader loop (merge_join.go:127-152)
+                chk = self.inner.Next()
+                if chk.num_rows() == 0:
+                    break
+                L.check(lib.tq_mjoin_put_inner(self.handle, tq_array(chk.cols), L.TQ_MEM_HOST))
+            while True:  # fetchNextOuterRows (merge_join.go:350-372): one outer chunk + VectorizedFilter -> selected
+                chk = self.outer.Next()
+                if chk.num_rows() == 0:
+                    break
+                sel = None
+                if self.outer_filter is not None:
+                    sel = np.ascontiguousarray(self.outer_filter(chk), dtype=np.uint8)
+                L.check(lib.tq_mjoin_put_outer(self.handle, tq_array(chk.cols), sel.ctypes.data if sel is not None else None, L.TQ_MEM_HOST))
+            L.check(lib.tq_mjoin_finish(self.handle))
+            self.prepared = True
+        return _drain_result(lib, self.types, required_rows or self.max_chunk_size, lib.tq_mjoin_next_bytes, lib.tq_mjoin_next, self.handle)
+
+    def Close(self):
+        if self.handle is not None:
+            L.load().tq_mjoin_destroy(self.handle)
+            self.handle = None
+        self.outer.Close()
+        self.inner.Close()
+
+    def drain(self):
+        chunks = []
+        while True:
+            c = self.Next()
+            if c.num_rows() == 0:
+                break
+            chunks.append(c)
+        return Chunk.concat(chunks, self.types)
