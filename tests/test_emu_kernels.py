@@ -1,0 +1,80 @@
+"""CPU suite: the kernels of csrc/sort.cu (radix sort, gathers, merge-join search / expand) and csrc/codec.cu (k_chunk_unpack)
+executed WITHOUT a GPU.  tests/emu compiles those product sources unchanged with g++ against an emulation of the CUDA primitives
+they use (one OS thread per CUDA thread, pthread barriers for __syncthreads and the warp collectives — tests/emu/include/
+cuda_runtime.h) into libtq_emu.so, which exports the same C-ABI entry points.  The host-side mirror (tinysql_b200/executor.py,
+chunk.py) is pointed at that library and the bodies of the GPU parity tests run against the oracle.  This checks the code's
+LOGIC (indexing, ranking, masks, searches, the host orchestration); timing, memory-model and launch behaviour are what the
+`-m gpu` tests of the same names check on the B200."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import test_gpu_chunk_codec as TC
+import test_gpu_sort_merge as TS
+from sort_cases import MERGE_CASES, SORT_CASES
+from tinysql_b200 import _lib as L
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+EMU_SO = os.path.join(EMU_DIR, "libtq_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    subprocess.check_call(["make", "-C", EMU_DIR, "-s"])
+    lib = C.CDLL(EMU_SO)
+    for name, (res, args) in L.SYMBOLS.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype, fn.argtypes = res, args
+    return lib
+
+
+@pytest.fixture()
+def emu(emu_lib, monkeypatch):
+    monkeypatch.setattr(L, "_lib", emu_lib)   # executor.py / chunk.py call L.load()
+    return emu_lib
+
+
+@pytest.mark.parametrize("case", SORT_CASES, ids=[c[0] for c in SORT_CASES])
+def test_emu_sort_reference_goldens(emu, case):
+    TS.test_sort_reference_goldens(emu, case)
+
+
+@pytest.mark.parametrize("case", MERGE_CASES, ids=[c[0] for c in MERGE_CASES])
+def test_emu_merge_join_reference_goldens(emu, case):
+    TS.test_merge_join_reference_goldens(emu, case)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 255, 256, 257, 4095, 4096, 4097, 9001])
+def test_emu_sort_every_layout_vs_oracle(emu, n):
+    TS.test_sort_every_layout_vs_oracle(emu, n)
+
+
+def test_emu_sort_wide_keys_and_long_strings(emu, monkeypatch):
+    TS.test_sort_wide_keys_and_long_strings(emu, n=3000)
+
+
+@pytest.mark.parametrize("jt,oir", [(0, False), (1, False), (2, True)])
+def test_emu_merge_join_vs_oracle(emu, jt, oir):
+    TS.test_merge_join_vs_oracle(emu, jt, oir, ni=3000, no=5000)
+
+
+def test_emu_merge_join_typed_keys_default_inner_and_unsorted_input(emu):
+    TS.test_merge_join_typed_keys_default_inner_and_unsorted_input(emu)
+
+
+def test_emu_chunk_decode_golden(emu):
+    TC.test_reference_test_codec_golden_on_device(emu)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 63, 64, 65, 1000, 10003])
+@pytest.mark.parametrize("null_frac", [0.0, 0.3])
+def test_emu_chunk_decode_equals_host_decode(emu, n, null_frac):
+    TC.test_device_decode_equals_host_decode(emu, n, null_frac)
+
+
+def test_emu_chunk_decode_rejects_truncated_buffers(emu):
+    TC.test_device_decode_rejects_truncated_buffers(emu)

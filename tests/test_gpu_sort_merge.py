@@ -62,9 +62,8 @@ def test_sort_every_layout_vs_oracle(lib, n):
     assert_same_ordered(run_sort(types, cols, [(4, False), (0, True)], 3, 1000), O.sort(types, cols, [(4, False), (0, True)], 3, 1000))
 
 
-def test_sort_wide_keys_and_long_strings(lib):
+def test_sort_wide_keys_and_long_strings(lib, n=30000):
     rng = np.random.default_rng(3)
-    n = 30000
     big = Column(INT64, rng.integers(-(1 << 63), (1 << 63) - 1, n, dtype=np.int64), rng.random(n) > 0.05)
     ubig = Column(UINT64, rng.integers(0, (1 << 64) - 1, n, dtype=np.uint64))
     dbl = Column(FLOAT64, np.concatenate([rng.standard_normal(n - 6) * 1e300, [0.0, -0.0, np.inf, -np.inf, 1e-310, -1e-310]]))
@@ -95,11 +94,10 @@ def test_sort_large_properties(lib):
 
 
 @pytest.mark.parametrize("jt,oir", [(INNER_JOIN, False), (INNER_JOIN, True), (LEFT_OUTER_JOIN, False), (RIGHT_OUTER_JOIN, True)])
-def test_merge_join_vs_oracle(lib, jt, oir):
+def test_merge_join_vs_oracle(lib, jt, oir, ni=30000, no=50000):
     rng = np.random.default_rng(60 + jt * 2 + int(oir))
-    ni, no = 30000, 50000
     it, ot = [INT64, BYTES, INT64, FLOAT32], [BYTES, INT64, FLOAT64]
-    words = [b"", b"a", b"ab", b"b", b"ba", b"c" * 9, b"c" * 17]
+    words = [b"", b"a", b"ab", b"b", b"ba", b"c" * 9, b"c" * 17] + [b"w%04d" % i + b"x" * (i % 23) for i in range(max(ni // 20, 8))]
 
     def keys(n):
         ki = gen_col(rng, INT64, n, 0.05, 0, 4000)

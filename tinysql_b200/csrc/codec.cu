@@ -236,7 +236,7 @@ int32_t tq_chunk_decode_device(const uint8_t *buffer, int64_t len, int32_t n_col
     const uint64_t cap = (uint64_t)r.sm_count * 8;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    k_chunk_unpack<<<dim3((unsigned)bx, (unsigned)p.n_segs), 256, 0, s>>>(p);
+    TQ_LAUNCH(k_chunk_unpack, dim3((unsigned)bx, (unsigned)p.n_segs), 256, 0, s, p);
     tq::count_launch();
     st = tq::check_launch("k_chunk_unpack");
     if (st != TQ_OK) return fail(st);

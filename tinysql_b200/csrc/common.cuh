@@ -12,6 +12,13 @@
 
 #include "../../include/tinysql_b200.h"
 
+// Kernel launch.  sort.cu and codec.cu launch through this macro so that tests/emu can compile the SAME sources with g++
+// against a thread-per-CUDA-thread emulation of the few primitives they use and check them against the oracle without a GPU
+// (the emulation's cuda_runtime.h defines TQ_LAUNCH first).
+#ifndef TQ_LAUNCH
+#define TQ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace tq {
 
 // ---------------------------------------------------------------- errors (thread-local text)

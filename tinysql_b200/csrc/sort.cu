@@ -92,7 +92,7 @@ __device__ __forceinline__ uint64_t key_word(const KeySrc &k, uint32_t r) {
     case KS_MIX_CLASS:
       if (nn) { const uint64_t v = k.d8[r]; w = (k.type == TQ_TYPE_INT64) ? ((v >> 63) ? 0 : 1) : ((v >> 63) ? 2 : 1); }
       break;
-    default: if (nn) w = (k.type == TQ_TYPE_INT64) ? (k.d8[r] ^ 0x8000000000000000ull) : k.d8[r]; break;   // KS_MIX_VALUE, inside a class
+    default: if (nn) w = k.d8[r]; break;   // KS_MIX_VALUE: inside a class the raw two's-complement word orders both domains
   }
   return k.desc ? ~w : w;
 }
@@ -414,27 +414,27 @@ int32_t gather_columns(const RowStore &st, const uint32_t *d_rows, int64_t m, co
     if (m == 0) continue;
     const int nn_dflt = (sc.kind == 0 && dflt_nn) ? dflt_nn[c] : 0;
     TQ_TRY(g.obm.reserve(bitmap_alloc_bytes(m)));
-    k_gather_bm<<<grid_for(words * 32), 256, 0, s>>>(sc.bm(), d_rows, m, nn_dflt, g.obm.as<uint32_t>(), words);
+    TQ_LAUNCH(k_gather_bm, grid_for(words * 32), 256, 0, s, sc.bm(), d_rows, m, nn_dflt, g.obm.as<uint32_t>(), words);
     count_launch();
     TQ_TRY(check_launch("k_gather_bm"));
     TQ_CUDA(cudaMemcpyAsync(rc.bm.data(), g.obm.p, (size_t)words * 4, cudaMemcpyDeviceToHost, s));
     if (sc.kind == 0) {
       TQ_TRY(g.out.reserve((size_t)m * 8));
-      k_gather_u64<<<grid_for(m), 256, 0, s>>>(sc.d_data.as<uint64_t>(), d_rows, m, (dflt_bits && nn_dflt) ? dflt_bits[c] : 0ull, g.out.as<uint64_t>());
+      TQ_LAUNCH(k_gather_u64, grid_for(m), 256, 0, s, sc.d_data.as<uint64_t>(), d_rows, m, (dflt_bits && nn_dflt) ? dflt_bits[c] : 0ull, g.out.as<uint64_t>());
       count_launch();
       TQ_TRY(check_launch("k_gather_u64"));
       rc.data.resize((size_t)m * 8);
       TQ_CUDA(cudaMemcpyAsync(rc.data.data(), g.out.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
     } else if (sc.kind == 1) {
       TQ_TRY(g.out.reserve((size_t)m * 4));
-      k_gather_u32<<<grid_for(m), 256, 0, s>>>(sc.d_data.as<uint32_t>(), d_rows, m, g.out.as<uint32_t>());
+      TQ_LAUNCH(k_gather_u32, grid_for(m), 256, 0, s, sc.d_data.as<uint32_t>(), d_rows, m, g.out.as<uint32_t>());
       count_launch();
       TQ_TRY(check_launch("k_gather_u32"));
       rc.data.resize((size_t)m * 4);
       TQ_CUDA(cudaMemcpyAsync(rc.data.data(), g.out.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
     } else {
       TQ_TRY(g.rowid64.reserve((size_t)m * 8));
-      k_rows_to_u64<<<grid_for(m), 256, 0, s>>>(d_rows, m, g.rowid64.as<uint64_t>());
+      TQ_LAUNCH(k_rows_to_u64, grid_for(m), 256, 0, s, d_rows, m, g.rowid64.as<uint64_t>());
       count_launch();
       TQ_TRY(check_launch("k_rows_to_u64"));
       TQ_TRY(gather_cells(sc.store, g.rowid64.as<uint64_t>(), g.obm.as<uint32_t>(), m, g.var, g.lens, g.scan, s));
@@ -509,7 +509,7 @@ int32_t radix_sort_word(SortBufs &b, int64_t n, cudaStream_t s) {
   TQ_TRY(b.meta.reserve(64));
   const unsigned long long init[2] = {0ull, ~0ull};
   TQ_CUDA(cudaMemcpyAsync(b.meta.p, init, 16, cudaMemcpyHostToDevice, s));
-  k_or_and<<<grid_for(n), 256, 0, s>>>(b.keys[b.cur].as<uint64_t>(), n, b.meta.as<unsigned long long>());
+  TQ_LAUNCH(k_or_and, grid_for(n), 256, 0, s, b.keys[b.cur].as<uint64_t>(), n, b.meta.as<unsigned long long>());
   count_launch();
   TQ_TRY(check_launch("k_or_and"));
   unsigned long long oa[2] = {0, 0};
@@ -521,11 +521,11 @@ int32_t radix_sort_word(SortBufs &b, int64_t n, cudaStream_t s) {
     if (((diff >> (8 * d)) & 0xFFull) == 0) continue;
     const int nxt = b.cur ^ 1;
     TQ_TRY(b.counts.reserve((size_t)n_blocks * 256 * 4));
-    k_radix_count<<<(unsigned)n_blocks, RADIX_THREADS, 0, s>>>(b.keys[b.cur].as<uint64_t>(), n, 8 * d, b.counts.as<uint32_t>(), (int)n_blocks);
+    TQ_LAUNCH(k_radix_count, (unsigned)n_blocks, RADIX_THREADS, 0, s, b.keys[b.cur].as<uint64_t>(), n, 8 * d, b.counts.as<uint32_t>(), (int)n_blocks);
     count_launch();
     TQ_TRY(check_launch("k_radix_count"));
     TQ_TRY(exclusive_scan_u32(b.counts.as<uint32_t>(), 1, b.counts.as<uint32_t>(), 1, n_blocks * 256, nullptr, b.scan, s));
-    k_radix_scatter<<<(unsigned)n_blocks, RADIX_THREADS, 0, s>>>(b.keys[b.cur].as<uint64_t>(), b.perm[b.cur].as<uint32_t>(), n, 8 * d, b.counts.as<uint32_t>(),
+    TQ_LAUNCH(k_radix_scatter, (unsigned)n_blocks, RADIX_THREADS, 0, s, b.keys[b.cur].as<uint64_t>(), b.perm[b.cur].as<uint32_t>(), n, 8 * d, b.counts.as<uint32_t>(),
                                                                  (int)n_blocks, b.keys[nxt].as<uint64_t>(), b.perm[nxt].as<uint32_t>());
     count_launch();
     TQ_TRY(check_launch("k_radix_scatter"));
@@ -548,7 +548,7 @@ int32_t sort_by_column(const StoreCol &sc, int desc, SortBufs &b, int64_t n, cud
   }
   if (sc.has_bm) words.push_back(key_src(sc, KS_NULL_FLAG, 0, desc));   // cmpNull: NULL before everything (after, when Desc)
   for (const KeySrc &k : words) {
-    k_sort_keys<<<grid_for(n), 256, 0, s>>>(k, b.perm[b.cur].as<uint32_t>(), n, b.keys[b.cur].as<uint64_t>());
+    TQ_LAUNCH(k_sort_keys, grid_for(n), 256, 0, s, k, b.perm[b.cur].as<uint32_t>(), n, b.keys[b.cur].as<uint64_t>());
     count_launch();
     TQ_TRY(check_launch("k_sort_keys"));
     TQ_TRY(radix_sort_word(b, n, s));
@@ -634,7 +634,7 @@ int32_t tq_sort_eof(tq_sort *h) {
   TQ_TRY(h->rows.upload(s));
   SortBufs b;
   for (int i = 0; i < 2; i++) { TQ_TRY(b.keys[i].reserve((size_t)n * 8)); TQ_TRY(b.perm[i].reserve((size_t)n * 4 + 16)); }
-  k_iota_u32<<<grid_for(n), 256, 0, s>>>(b.perm[0].as<uint32_t>(), n);
+  TQ_LAUNCH(k_iota_u32, grid_for(n), 256, 0, s, b.perm[0].as<uint32_t>(), n);
   count_launch();
   TQ_TRY(check_launch("k_iota_u32"));
   if (n > 1)
@@ -776,7 +776,7 @@ int32_t tq_mjoin_finish(tq_mjoin *h) {
         if (n > 0) {
           KeySrc ks = key_src(sc, mixed ? modes[part] : (sc.kind == 1 ? KS_F32 : KS_COL8), 0, 0);
           ks.bm = nullptr;   // NULL keys never reach a comparison (k_mj_valid)
-          k_sort_keys<<<grid_for(n), 256, 0, s>>>(ks, nullptr, n, eb.as<uint64_t>());
+          TQ_LAUNCH(k_sort_keys, grid_for(n), 256, 0, s, ks, nullptr, n, eb.as<uint64_t>());
           count_launch();
           TQ_TRY(check_launch("k_sort_keys"));
         }
@@ -793,11 +793,11 @@ int32_t tq_mjoin_finish(tq_mjoin *h) {
   if (ni > 0) {
     TQ_TRY(iflags.reserve((size_t)ni * 4));
     TQ_TRY(ioffs.reserve((size_t)ni * 4));
-    k_mj_valid<<<grid_for(ni), 256, 0, s>>>(ibm, nullptr, ni, iflags.as<uint32_t>());
+    TQ_LAUNCH(k_mj_valid, grid_for(ni), 256, 0, s, ibm, nullptr, ni, iflags.as<uint32_t>());
     count_launch();
     TQ_TRY(check_launch("k_mj_valid"));
     TQ_TRY(exclusive_scan_u32(iflags.as<uint32_t>(), 1, ioffs.as<uint32_t>(), 1, ni, meta.as<uint64_t>(), scan, s));
-    k_compact<<<grid_for(ni), 256, 0, s>>>(iflags.as<uint32_t>(), ioffs.as<uint32_t>(), ni, ivalid.as<uint32_t>());
+    TQ_LAUNCH(k_compact, grid_for(ni), 256, 0, s, iflags.as<uint32_t>(), ioffs.as<uint32_t>(), ni, ivalid.as<uint32_t>());
     count_launch();
     TQ_TRY(check_launch("k_compact"));
     uint64_t total = 0;
@@ -805,7 +805,7 @@ int32_t tq_mjoin_finish(tq_mjoin *h) {
     TQ_CUDA(cudaStreamSynchronize(s));
     iv = (int64_t)total;
     if (iv > 1) {
-      k_mj_check_sorted<<<grid_for(iv), 256, 0, s>>>(K, ivalid.as<uint32_t>(), iv, meta.as<unsigned>() + 4);
+      TQ_LAUNCH(k_mj_check_sorted, grid_for(iv), 256, 0, s, K, ivalid.as<uint32_t>(), iv, meta.as<unsigned>() + 4);
       count_launch();
       TQ_TRY(check_launch("k_mj_check_sorted"));
       unsigned bad = 0;
@@ -822,13 +822,13 @@ int32_t tq_mjoin_finish(tq_mjoin *h) {
     TQ_CUDA(cudaMemcpyAsync(d_sel.p, h->selected.data(), (size_t)no, cudaMemcpyHostToDevice, s));
     dsel = d_sel.as<uint8_t>();
   }
-  k_mj_valid<<<grid_for(no), 256, 0, s>>>(obm, dsel, no, oflags.as<uint32_t>());
+  TQ_LAUNCH(k_mj_valid, grid_for(no), 256, 0, s, obm, dsel, no, oflags.as<uint32_t>());
   count_launch();
   TQ_TRY(check_launch("k_mj_valid"));
   TQ_TRY(lo.reserve((size_t)no * 4));
   TQ_TRY(cnt.reserve((size_t)no * 4));
   TQ_TRY(emit.reserve((size_t)no * 4));
-  k_mj_bounds<<<grid_for(no), 256, 0, s>>>(K, ivalid.as<uint32_t>(), iv, oflags.as<uint32_t>(), no, outer_join ? 1 : 0, lo.as<uint32_t>(), cnt.as<uint32_t>(),
+  TQ_LAUNCH(k_mj_bounds, grid_for(no), 256, 0, s, K, ivalid.as<uint32_t>(), iv, oflags.as<uint32_t>(), no, outer_join ? 1 : 0, lo.as<uint32_t>(), cnt.as<uint32_t>(),
                                            emit.as<uint32_t>());
   count_launch();
   TQ_TRY(check_launch("k_mj_bounds"));
@@ -842,7 +842,7 @@ int32_t tq_mjoin_finish(tq_mjoin *h) {
   TQ_TRY(out_o.reserve((size_t)(m ? m : 1) * 4));
   TQ_TRY(out_i.reserve((size_t)(m ? m : 1) * 4));
   if (m > 0) {
-    k_mj_expand<<<grid_for(m), 256, 0, s>>>(emit.as<uint32_t>(), lo.as<uint32_t>(), cnt.as<uint32_t>(), ivalid.as<uint32_t>(), no, m, out_o.as<uint32_t>(),
+    TQ_LAUNCH(k_mj_expand, grid_for(m), 256, 0, s, emit.as<uint32_t>(), lo.as<uint32_t>(), cnt.as<uint32_t>(), ivalid.as<uint32_t>(), no, m, out_o.as<uint32_t>(),
                                             out_i.as<uint32_t>());
     count_launch();
     TQ_TRY(check_launch("k_mj_expand"));
