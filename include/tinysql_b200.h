@@ -201,6 +201,12 @@ int32_t tq_vec_filter_int(int64_t n, const tq_column *a, uint8_t *selected, int3
 /* the same for an ETReal expression: toBool's zero test is types.RoundFloat(f) == 0, i.e. |f| < 0.5 (expression.go:296-307). */
 int32_t tq_vec_filter_real(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem);
 
+/* the same for an ETString expression: toBool's zero test is types.StrToInt(cell) == 0 in the statement context of a SELECT
+ * (expression.go:308-322; types/convert.go:224-232: white space trimmed, longest valid numeric prefix, rounded to an integer —
+ * "0.5" is 1, "abc" is 0).  Returns TQ_ERR_OVERFLOW_BIGINT when the LAST non-NULL row's integer does not fit BIGINT — the
+ * error VecEvalBool keeps (`err = err1` per row).  `a` is a var-len column (offsets + data). */
+int32_t tq_vec_filter_string(int64_t n, const tq_column *a, uint8_t *selected, int32_t mem);
+
 /* ---- fused Selection + Projection -------------------------------------
  * One pass over a chunk for a whole list of filters and projection expressions: replaces
  * SelectionExec.Next → expression.VectorizedFilter (executor/executor.go:463-499,

@@ -1229,3 +1229,132 @@ int orc_merge_join(int join_type, int outer_is_right,
   free(obs);
   return ORC_OK;
 }
+
+/* ------------------------------------------------------------------ toBool for ETString (expression/expression.go:308-322)
+ * isZero = (types.StrToInt(sc, s) == 0), and the error VecEvalBool sees is the err of the LAST non-NULL row (`err = err1`
+ * inside the loop).  StrToInt (types/convert.go:224-232) in a SELECT statement (InSelectStmt, truncation is a warning,
+ * CastStrToIntStrict == false): TrimSpace -> getValidFloatPrefix (:430-475) -> floatStrToIntStr (:318-405) -> strconv.ParseInt;
+ * a ParseInt failure (syntax or range) is reported as ErrOverflow("BIGINT").  Restated LITERALLY — the intermediate strings are
+ * built exactly as the Go code builds them — so that it is independent of the streaming form the device kernel uses.
+ * strings.TrimSpace: the ASCII white space characters (the Unicode ones, U+0085 / U+00A0 / U+2000..., are not trimmed here
+ * or on the device: documented deviation). */
+typedef struct { char *p; int64_t n; } gostr;
+static gostr gs_make(const char *p, int64_t n) { gostr s; s.p = (char *)malloc((size_t)(n + 1)); if (n) memcpy(s.p, p, (size_t)n); s.p[n] = 0; s.n = n; return s; }
+static int is_digit_b(char c) { return c >= '0' && c <= '9'; }
+/* strconv.ParseInt(s, 10, 64): returns 0 ok, 1 syntax error (value 0), 2 range error (value = max / min) */
+static int go_parse_int(const char *s, int64_t n, int64_t *out) {
+  *out = 0;
+  if (n == 0) return 1;
+  int neg = 0; int64_t i = 0;
+  if (s[0] == '+') i = 1; else if (s[0] == '-') { neg = 1; i = 1; }
+  if (i == n) return 1;
+  uint64_t un = 0; int range = 0;
+  for (; i < n; i++) {
+    if (!is_digit_b(s[i])) return 1;
+    uint64_t d = (uint64_t)(s[i] - '0');
+    if (un > (UINT64_MAX - d) / 10) { range = 1; un = UINT64_MAX; } else if (!range) un = un * 10 + d;
+  }
+  if (!neg && (range || un > (uint64_t)INT64_MAX)) { *out = INT64_MAX; return 2; }
+  if (neg && (range || un > (uint64_t)INT64_MAX + 1)) { *out = INT64_MIN; return 2; }
+  *out = neg ? (int64_t)(0 - un) : (int64_t)un;
+  return 0;
+}
+/* strconv.Atoi for the exponent: 0 ok, 1 error */
+static int go_atoi(const char *s, int64_t n, int64_t *out) { int rc = go_parse_int(s, n, out); return rc != 0; }
+/* roundIntStr (types/convert.go:283-311) */
+static gostr round_int_str(char next, gostr in) {
+  if (next < '5') return in;
+  gostr r = gs_make(in.p, in.n + 1); r.n = in.n;   /* room for one appended '0' */
+  int64_t idx = in.n - 1;
+  for (; idx >= 1; idx--) { if (r.p[idx] != '9') { r.p[idx]++; break; } r.p[idx] = '0'; }
+  if (idx == 0) {
+    if (in.p[0] == '9') { r.p[0] = '1'; r.p[r.n++] = '0'; }
+    else if (is_digit_b(in.p[0])) r.p[0]++;
+    else { r.p[1] = '1'; r.p[r.n++] = '0'; }
+  }
+  r.p[r.n] = 0;
+  free(in.p);
+  return r;
+}
+int orc_str_to_int(const uint8_t *bytes, int64_t len, int64_t *ival, int *overflow_err) {
+  const char *s = (const char *)bytes;
+  int64_t n = len;
+  while (n > 0 && (s[0] == ' ' || (s[0] >= '\t' && s[0] <= '\r'))) { s++; n--; }            /* strings.TrimSpace */
+  while (n > 0 && (s[n - 1] == ' ' || (s[n - 1] >= '\t' && s[n - 1] <= '\r'))) n--;
+  /* getValidFloatPrefix */
+  gostr valid;
+  if (n == 0) valid = gs_make("0", 1);                                                        /* InSelectStmt && s == "" */
+  else {
+    int saw_dot = 0, saw_digit = 0; int64_t valid_len = 0, e_idx = 0;
+    for (int64_t i = 0; i < n; i++) {
+      char c = s[i];
+      if (c == '+' || c == '-') { if (i != 0 && i != e_idx + 1) break; }
+      else if (c == '.') { if (saw_dot || e_idx > 0) break; saw_dot = 1; if (saw_digit) valid_len = i + 1; }
+      else if (c == 'e' || c == 'E') { if (!saw_digit) break; if (e_idx != 0) break; e_idx = i; }
+      else if (c < '0' || c > '9') break;
+      else { saw_digit = 1; valid_len = i + 1; }
+    }
+    valid = valid_len ? gs_make(s, valid_len) : gs_make("0", 1);
+  }
+  /* floatStrToIntStr(validFloat) */
+  gostr vf = valid, int_str;
+  int64_t dot = -1, eidx = -1;
+  for (int64_t i = 0; i < vf.n; i++) { if (vf.p[i] == '.') dot = i; else if (vf.p[i] == 'e' || vf.p[i] == 'E') eidx = i; }
+  if (eidx == -1) {
+    if (dot == -1) int_str = gs_make(vf.p, vf.n);
+    else {
+      const char *digits = vf.p; int64_t dl = vf.n;
+      if (vf.p[0] == '-' || vf.p[0] == '+') { dot--; digits = vf.p + 1; dl = vf.n - 1; }
+      int_str = dot == 0 ? gs_make("0", 1) : gs_make(digits, dot);
+      if (dl > dot + 1) int_str = round_int_str(digits[dot + 1], int_str);
+      if ((int_str.n > 1 || int_str.p[0] != '0') && vf.p[0] == '-') {
+        gostr t = gs_make("-", 1); t.p = (char *)realloc(t.p, (size_t)(int_str.n + 2)); memcpy(t.p + 1, int_str.p, (size_t)int_str.n + 1); t.n = int_str.n + 1;
+        free(int_str.p); int_str = t;
+      }
+    }
+  } else {
+    gostr digits = gs_make("", 0); digits.p = (char *)realloc(digits.p, (size_t)(vf.n + 1));
+    int64_t int_cnt;
+    if (dot == -1) { memcpy(digits.p, vf.p, (size_t)eidx); digits.n = eidx; int_cnt = eidx; }
+    else { memcpy(digits.p, vf.p, (size_t)dot); int_cnt = dot; memcpy(digits.p + dot, vf.p + dot + 1, (size_t)(eidx - dot - 1)); digits.n = dot + (eidx - dot - 1); }
+    digits.p[digits.n] = 0;
+    int64_t exp = 0;
+    if (go_atoi(vf.p + eidx + 1, vf.n - eidx - 1, &exp)) int_str = gs_make(vf.p, vf.n);     /* return validFloat, err */
+    else {
+      int_cnt = (int64_t)((uint64_t)int_cnt + (uint64_t)exp);                                 /* Go int addition wraps */
+      if (exp >= 0 && (int_cnt > 21 || int_cnt < 0)) int_str = gs_make(vf.p, eidx);            /* + an overflow WARNING */
+      else if (int_cnt <= 0) {
+        int_str = gs_make("0", 1);
+        if (int_cnt == 0 && digits.n > 0 && is_digit_b(digits.p[0])) int_str = round_int_str(digits.p[0], int_str);
+      } else if (int_cnt == 1 && (digits.p[0] == '-' || digits.p[0] == '+')) {
+        int_str = gs_make("0", 1);
+        if (digits.n > 1) int_str = round_int_str(digits.p[1], int_str);
+        if (int_str.p[0] == '1') { gostr t = gs_make(digits.p, 1); t.p = (char *)realloc(t.p, (size_t)(int_str.n + 2)); memcpy(t.p + 1, int_str.p, (size_t)int_str.n + 1); t.n = int_str.n + 1; free(int_str.p); int_str = t; }
+      } else if (int_cnt <= digits.n) {
+        int_str = gs_make(digits.p, int_cnt);
+        if (int_cnt < digits.n) int_str = round_int_str(digits.p[int_cnt], int_str);
+      } else {
+        int64_t extra = int_cnt - digits.n;
+        int_str = gs_make(digits.p, digits.n); int_str.p = (char *)realloc(int_str.p, (size_t)(digits.n + extra + 1));
+        memset(int_str.p + digits.n, '0', (size_t)extra); int_str.n = digits.n + extra; int_str.p[int_str.n] = 0;
+      }
+    }
+    free(digits.p);
+  }
+  int rc = go_parse_int(int_str.p, int_str.n, ival);                                          /* StrToInt :227-231 */
+  *overflow_err = rc != 0;
+  free(int_str.p); free(vf.p);
+  return ORC_OK;
+}
+/* the valid int string itself, for the reference's floatStrToIntStr / getValidIntPrefix vectors (tests only) */
+int orc_vec_filter_string(int64_t n, const orc_column *a, uint8_t *selected, int *err_overflow) {
+  *err_overflow = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (col_is_null(a, i)) { selected[i] = 0; continue; }                                     /* isZero = -1 */
+    int64_t v; int e;
+    orc_str_to_int(a->data + a->offsets[i], a->offsets[i + 1] - a->offsets[i], &v, &e);
+    *err_overflow = e;                                                                         /* err = err1: the last row wins */
+    selected[i] = (uint8_t)(v != 0);
+  }
+  return ORC_OK;
+}

@@ -97,6 +97,11 @@ int orc_merge_join(int join_type, int outer_is_right,
                    int n_keys, const int *inner_keys, const int *outer_keys, const uint8_t *selected,
                    const uint64_t *default_bits, const uint8_t *default_nn, orc_column *out_cols, int64_t *n_out);
 
+/* types.StrToInt in a SELECT statement (types/convert.go:224-232) and toBool for ETString (expression/expression.go:308-322):
+ * *overflow_err = ParseInt failed (ErrOverflow "BIGINT"); orc_vec_filter_string reports the error of the LAST non-NULL row. */
+int orc_str_to_int(const uint8_t *bytes, int64_t len, int64_t *ival, int *overflow_err);
+int orc_vec_filter_string(int64_t n, const orc_column *a, uint8_t *selected, int *err_overflow);
+
 /* vectorized builtins — restated statement by statement from expression/builtin_*_vec*.go */
 int orc_vec_compare_int(int op, int64_t n, const orc_column *a, int a_unsigned, const orc_column *b,
                         int b_unsigned, orc_column *out);

@@ -194,6 +194,22 @@ def merge_join(join_type, outer_is_right, inner_types, inner_cols, outer_types, 
     return res
 
 
+def str_to_int(b):
+    """types.StrToInt in a SELECT statement: (value, ParseInt failed -> ErrOverflow)"""
+    v, e = C.c_int64(0), C.c_int(0)
+    load().orc_str_to_int(b, C.c_int64(len(b)), C.byref(v), C.byref(e))
+    return v.value, bool(e.value)
+
+
+def vec_filter_string(a):
+    """toBool for ETString: (selected bytes, the error of the last non-NULL row)"""
+    sel = np.zeros(max(a.length, 1), dtype=np.uint8)
+    ta = a.tq()
+    e = C.c_int(0)
+    load().orc_vec_filter_string(C.c_int64(a.length), C.byref(ta), C.c_void_p(sel.ctypes.data), C.byref(e))
+    return sel[: a.length], bool(e.value)
+
+
 def _vec(fn, out_tp, n, *args):
     out = Column.empty(out_tp, n)
     to = out.tq()

@@ -14,6 +14,7 @@ import pytest
 
 import test_gpu_chunk_codec as TC
 import test_gpu_sort_merge as TS
+import test_gpu_string_filter as TF
 from sort_cases import MERGE_CASES, SORT_CASES
 from tinysql_b200 import _lib as L
 
@@ -78,3 +79,13 @@ def test_emu_chunk_decode_equals_host_decode(emu, n, null_frac):
 
 def test_emu_chunk_decode_rejects_truncated_buffers(emu):
     TC.test_device_decode_rejects_truncated_buffers(emu)
+
+
+def test_emu_string_filter_reference_vectors(emu):
+    TF.test_reference_vectors(emu)
+    TF.test_error_of_the_last_non_null_row(emu)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_emu_string_filter_differential_fuzz(emu, seed):
+    TF.test_differential_fuzz(emu, seed, n=6000)

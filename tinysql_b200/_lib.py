@@ -110,6 +110,7 @@ SYMBOLS = {
     "tq_join_stats": (_I32, [_P, C.POINTER(_I64)]), "tq_join_destroy": (_I32, [_P]),
     "tq_chunk_decode_device": (_I32, [_P, _I64, _I32, C.POINTER(_I32), C.POINTER(_P), _COL, C.POINTER(_I64)]),
     "tq_chunk_device_free": (_I32, [_P]),
+    "tq_vec_filter_string": (_I32, [_I64, _COL, _P, _I32]),
     "tq_agg_create": (_I32, [C.POINTER(TQAggDesc), C.POINTER(_P)]),
     "tq_agg_create_final": (_I32, [C.POINTER(TQAggFinalDesc), C.POINTER(_P)]),
     "tq_agg_output_type": (_I32, [_P, _I32, C.POINTER(_I32)]),

@@ -139,6 +139,14 @@ def vectorized_filter_real(a):
     return sel[: a.length]
 
 
+def vectorized_filter_string(a):
+    """VectorizedFilter over an ETString expression result: toBool = types.StrToInt(cell) != 0 (expression.go:308-322)"""
+    sel = np.zeros(max(a.length, 1), dtype=np.uint8)
+    ta = a.tq()
+    L.check(L.load().tq_vec_filter_string(a.length, C.byref(ta), sel.ctypes.data, L.TQ_MEM_HOST))
+    return sel[: a.length]
+
+
 def vec_in_real(a, lst):
     """builtinInRealSig — expression/builtin_other_vec_generated.go:151-204"""
     out = Column.empty(INT64, a.length)
