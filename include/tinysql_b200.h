@@ -455,6 +455,9 @@ int32_t tq_sort_put(tq_sort *s, const tq_column *cols, int32_t mem);   /* host c
 int32_t tq_sort_eof(tq_sort *s);
 int32_t tq_sort_next_bytes(tq_sort *s, int64_t max_rows, int64_t *bytes_per_col);
 int32_t tq_sort_next(tq_sort *s, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+/* [0] rows sorted, [1] device time of the sort phase in ns (CUDA events; upload and result gather excluded),
+ * [2] kernel launches of tq_sort_eof, [3] radix digit passes that ran (constant digits are skipped) */
+int32_t tq_sort_stats(tq_sort *s, int64_t *stats4);
 int32_t tq_sort_destroy(tq_sort *s);
 
 /* MergeJoinExec (executor/merge_join.go:31-373).  Both children deliver rows sorted ascending by their join keys (the planner

@@ -502,6 +502,7 @@ int32_t result_next(ResultHost &res, int64_t max_rows, tq_column *out, int64_t *
 struct SortBufs {
   DevBuf keys[2], perm[2], counts, scan, meta;
   int cur = 0;
+  int64_t passes = 0;   // radix digit passes that ran
 };
 
 // stable sort of (keys[cur], perm[cur]) by the 64-bit keys: LSD over the digits that are not constant
@@ -530,6 +531,7 @@ int32_t radix_sort_word(SortBufs &b, int64_t n, cudaStream_t s) {
     count_launch();
     TQ_TRY(check_launch("k_radix_scatter"));
     b.cur = nxt;
+    b.passes++;
   }
   return TQ_OK;
 }
@@ -566,7 +568,7 @@ struct tq_sort {
   int64_t limit_offset = 0, limit_count = -1;
   bool eof = false;
   ResultHost res;
-  int64_t launches = 0;
+  int64_t launches = 0, passes = 0, sort_ns = 0;   // tq_sort_stats
 };
 
 struct tq_mjoin {
@@ -634,11 +636,23 @@ int32_t tq_sort_eof(tq_sort *h) {
   TQ_TRY(h->rows.upload(s));
   SortBufs b;
   for (int i = 0; i < 2; i++) { TQ_TRY(b.keys[i].reserve((size_t)n * 8)); TQ_TRY(b.perm[i].reserve((size_t)n * 4 + 16)); }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the sort phase (upload and result gather excluded)
+  TQ_CUDA(cudaEventCreate(&ev0));
+  TQ_CUDA(cudaEventCreate(&ev1));
+  TQ_CUDA(cudaEventRecord(ev0, s));
   TQ_LAUNCH(k_iota_u32, grid_for(n), 256, 0, s, b.perm[0].as<uint32_t>(), n);
   count_launch();
-  TQ_TRY(check_launch("k_iota_u32"));
-  if (n > 1)
-    for (int i = h->n_by - 1; i >= 0; i--) TQ_TRY(sort_by_column(h->rows.cols[(size_t)h->by_col[i]], h->by_desc[i], b, n, s));
+  int32_t st = check_launch("k_iota_u32");
+  if (st == TQ_OK && n > 1)
+    for (int i = h->n_by - 1; i >= 0 && st == TQ_OK; i--) st = sort_by_column(h->rows.cols[(size_t)h->by_col[i]], h->by_desc[i], b, n, s);
+  if (st == TQ_OK && cudaEventRecord(ev1, s) == cudaSuccess && cudaEventSynchronize(ev1) == cudaSuccess) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) h->sort_ns = (int64_t)(ms * 1e6);
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  TQ_TRY(st);
+  h->passes = b.passes;
   GatherScratch g;
   TQ_TRY(gather_columns(h->rows, b.perm[b.cur].as<uint32_t>() + lo, m, nullptr, nullptr, h->res, g, s));
   h->launches = r.launches.load() - launches0;
@@ -655,6 +669,15 @@ int32_t tq_sort_next(tq_sort *h, int64_t max_rows, tq_column *out_cols, int64_t 
   if (!h || !out_cols || !n_rows || !eof || max_rows <= 0) return TQ_ERR_INVALID_ARG;
   if (!h->eof) { set_error("next before eof"); return TQ_ERR_STATE; }
   return result_next(h->res, max_rows, out_cols, n_rows, eof);
+}
+
+int32_t tq_sort_stats(tq_sort *h, int64_t *stats4) {
+  if (!h || !stats4) return TQ_ERR_INVALID_ARG;
+  stats4[0] = h->rows.n;
+  stats4[1] = h->sort_ns;
+  stats4[2] = h->launches;
+  stats4[3] = h->passes;
+  return TQ_OK;
 }
 
 int32_t tq_sort_destroy(tq_sort *h) {
