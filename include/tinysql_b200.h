@@ -482,6 +482,10 @@ typedef struct tq_mjoin_desc {
 } tq_mjoin_desc;
 typedef struct tq_mjoin tq_mjoin;
 int32_t tq_mjoin_create(const tq_mjoin_desc *desc, tq_mjoin **out);
+/* OtherConditions of the joiner (baseJoiner.filter, joiner.go:155-167; tryToMatchInners in merge_join.go:290-305): the same
+ * tq_join_cond comparisons tq_join_set_other_conditions takes, over the joined row left ++ right; an outer row whose joined rows
+ * all fail takes the miss path.  Call once, right after tq_mjoin_create. */
+int32_t tq_mjoin_set_other_conditions(tq_mjoin *j, int32_t n_conds, const tq_join_cond *conds);
 int32_t tq_mjoin_put_inner(tq_mjoin *j, const tq_column *cols, int32_t mem);                          /* host chunks */
 int32_t tq_mjoin_put_outer(tq_mjoin *j, const tq_column *cols, const uint8_t *selected, int32_t mem); /* selected: Go []bool or NULL */
 int32_t tq_mjoin_finish(tq_mjoin *j);   /* both children exhausted */

@@ -164,6 +164,7 @@ type GPUMergeJoinExec struct {
 	outerKeys     []*expression.Column
 	innerKeys     []*expression.Column
 	outerFilter   expression.CNFExprs
+	otherConditions expression.CNFExprs
 	defaultValues []types.Datum // PhysicalMergeJoin.DefaultValues -> defaultInner (joiner.go:139-143)
 
 	h        *C.tq_mjoin
@@ -175,8 +176,9 @@ type GPUMergeJoinExec struct {
 	pump     resultPump
 }
 
-// Open implements Executor (merge_join.go:185-198).  OtherConditions are not offloaded: buildMergeJoin keeps them in a
-// SelectionExec above an inner join and plans outer joins that carry them as GPUHashJoinExec (whose joiners filter on the device).
+// Open implements Executor (merge_join.go:185-198).  OtherConditions that asJoinConds (gpu_join.go) can lower — comparisons of
+// fixed-width columns / constants — are handed to tq_mjoin_set_other_conditions; buildMergeJoin keeps the rest in a SelectionExec
+// above an inner join.
 func (e *GPUMergeJoinExec) Open(ctx context.Context) error {
 	if err := e.baseExecutor.Open(ctx); err != nil {
 		return err
@@ -213,6 +215,14 @@ func (e *GPUMergeJoinExec) Open(ctx context.Context) error {
 	}
 	if st := C.tq_mjoin_create(d, &e.h); st != C.TQ_OK {
 		return chunk.StatusError(int32(st))
+	}
+	if conds, _, ok := asJoinConds(e.otherConditions, e.outerIdx == 1, len(oft), len(ift)); ok && len(conds) > 0 {
+		cc := (*[1 << 6]C.tq_join_cond)(C.calloc(C.size_t(len(conds)), C.sizeof_tq_join_cond))
+		defer C.free(unsafe.Pointer(cc))
+		copy(cc[:len(conds)], conds)
+		if st := C.tq_mjoin_set_other_conditions(e.h, C.int32_t(len(conds)), &cc[0]); st != C.TQ_OK {
+			return chunk.StatusError(int32(st))
+		}
 	}
 	e.prepared = false
 	e.chk = [2]*chunk.Chunk{newFirstChunk(inner), newFirstChunk(outer)}

@@ -1184,8 +1184,9 @@ int orc_merge_join(int join_type, int outer_is_right,
                    int n_inner_cols, const int *inner_types, const orc_column *inner_cols,
                    int n_outer_cols, const int *outer_types, const orc_column *outer_cols,
                    int n_keys, const int *inner_keys, const int *outer_keys, const uint8_t *selected,
+                   int n_conds, const orc_join_cond *conds,
                    const uint64_t *default_bits, const uint8_t *default_nn, orc_column *out_cols, int64_t *n_out) {
-  if (join_type < 0 || join_type > 2 || n_keys < 0) return ORC_ERR_INVALID;
+  if (join_type < 0 || join_type > 2 || n_keys < 0 || n_conds < 0) return ORC_ERR_INVALID;
   for (int c = 0; c < n_inner_cols; c++) if (inner_types[c] < 1 || inner_types[c] > 5) return ORC_ERR_UNSUPPORTED;
   for (int c = 0; c < n_outer_cols; c++) if (outer_types[c] < 1 || outer_types[c] > 5) return ORC_ERR_UNSUPPORTED;
   int64_t ni = n_inner_cols ? inner_cols[0].length : 0, no = n_outer_cols ? outer_cols[0].length : 0;
@@ -1217,8 +1218,18 @@ int orc_merge_join(int join_type, int outer_is_right,
       o++;
       continue;
     }
-    for (int64_t g = 0; g < in.g_n; g++) {      /* tryToMatchInners over the whole group (:290-305); no OtherConditions */
+    int has_match = 0;
+    for (int64_t g = 0; g < in.g_n; g++) {      /* tryToMatchInners over the whole group (:290-305): makeJoinRowToChunk + baseJoiner.filter */
+      if (n_conds && !conds_true(n_conds, conds, outer_is_right, n_inner_cols, inner_types, inner_cols, in.grp[g], n_outer_cols, outer_types, outer_cols, o)) continue;
       append_row(obs, inner_base, n_inner_cols, inner_cols, in.grp[g]);
+      append_row(obs, outer_base, n_outer_cols, outer_cols, o);
+      has_match = 1;
+    }
+    if (!has_match && is_outer) {                /* :300-304 every joined row was filtered: onMissMatch */
+      for (int c = 0; c < n_inner_cols; c++) {
+        if (default_nn && default_nn[c] && elem_of_type(inner_types[c]) == 8) ob_push(&obs[inner_base + c], default_bits[c], 1);
+        else ob_push_cell(&obs[inner_base + c], &inner_cols[c], -1);
+      }
       append_row(obs, outer_base, n_outer_cols, outer_cols, o);
     }
     o++;

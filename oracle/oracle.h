@@ -95,6 +95,7 @@ int orc_merge_join(int join_type, int outer_is_right,
                    int n_inner_cols, const int *inner_types, const orc_column *inner_cols,
                    int n_outer_cols, const int *outer_types, const orc_column *outer_cols,
                    int n_keys, const int *inner_keys, const int *outer_keys, const uint8_t *selected,
+                   int n_conds, const orc_join_cond *conds,
                    const uint64_t *default_bits, const uint8_t *default_nn, orc_column *out_cols, int64_t *n_out);
 
 /* types.StrToInt in a SELECT statement (types/convert.go:224-232) and toBool for ETString (expression/expression.go:308-322):

@@ -172,7 +172,7 @@ def sort(types, cols, by, limit_offset=0, limit_count=-1):
     return res
 
 
-def merge_join(join_type, outer_is_right, inner_types, inner_cols, outer_types, outer_cols, inner_keys, outer_keys, selected=None, default_inner=None):
+def merge_join(join_type, outer_is_right, inner_types, inner_cols, outer_types, outer_cols, inner_keys, outer_keys, selected=None, default_inner=None, conds=()):
     """MergeJoinExec over inputs sorted ascending by their keys; output = left ++ right, outer order x inner order"""
     lib = load()
     ncols = len(inner_cols) + len(outer_cols)
@@ -185,7 +185,7 @@ def merge_join(join_type, outer_is_right, inner_types, inner_cols, outer_types, 
         dnn = (C.c_uint8 * len(inner_cols))(*[0 if v is None else 1 for v in default_inner])
     rc = lib.orc_merge_join(C.c_int(join_type), C.c_int(1 if outer_is_right else 0), C.c_int(len(inner_cols)), _i32(inner_types), tq_array(inner_cols),
                             C.c_int(len(outer_cols)), _i32(outer_types), tq_array(outer_cols), C.c_int(len(inner_keys)), _i32(inner_keys), _i32(outer_keys),
-                            C.c_void_p(sel.ctypes.data) if sel is not None else None, dbits, dnn, out, C.byref(n))
+                            C.c_void_p(sel.ctypes.data) if sel is not None else None, C.c_int(len(conds)), _conds(conds), dbits, dnn, out, C.byref(n))
     if rc != 0:
         raise RuntimeError(f"oracle merge join failed: {rc}")
     types = (list(inner_types) + list(outer_types)) if outer_is_right else (list(outer_types) + list(inner_types))

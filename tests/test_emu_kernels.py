@@ -89,3 +89,8 @@ def test_emu_string_filter_reference_vectors(emu):
 @pytest.mark.parametrize("seed", range(4))
 def test_emu_string_filter_differential_fuzz(emu, seed):
     TF.test_differential_fuzz(emu, seed, n=6000)
+
+
+@pytest.mark.parametrize("jt,oir", [(0, False), (1, False), (2, True), (0, True)])
+def test_emu_merge_join_other_conditions(emu, jt, oir):
+    TS.test_merge_join_other_conditions(emu, jt, oir, ni=2000, no=3000)

@@ -24,7 +24,7 @@ def run_sort(types, cols, by, off=0, cnt=-1, chunk=1024):
     return got
 
 
-def run_mj(jt, oir, it, ic, ot, oc, ik, ok, sel=None, chunk=1024, default_inner=None):
+def run_mj(jt, oir, it, ic, ot, oc, ik, ok, sel=None, chunk=1024, default_inner=None, conds=()):
     flt = None
     if sel is not None:
         sel = np.asarray(sel, dtype=np.uint8)
@@ -34,7 +34,7 @@ def run_mj(jt, oir, it, ic, ot, oc, ik, ok, sel=None, chunk=1024, default_inner=
             lo = pos[0]
             pos[0] += chk.num_rows()
             return sel[lo: pos[0]]
-    e = MergeJoinExec(MockDataSource(ot, oc, chunk), MockDataSource(it, ic, chunk), ok, ik, jt, oir, flt, default_inner=default_inner)
+    e = MergeJoinExec(MockDataSource(ot, oc, chunk), MockDataSource(it, ic, chunk), ok, ik, jt, oir, flt, default_inner=default_inner, other_conditions=conds)
     e.Open()
     got = e.drain()
     e.Close()
@@ -139,6 +139,28 @@ def test_merge_join_typed_keys_default_inner_and_unsorted_input(lib):
     with pytest.raises(L.TQError) as ei:
         run_mj(INNER_JOIN, False, [INT64], [Column(INT64, [3, 1, 2])], [INT64], [Column(INT64, [1, 2, 3])], [0], [0])
     assert ei.value.status == L.TQ_ERR_STATE
+
+
+@pytest.mark.parametrize("jt,oir", [(INNER_JOIN, False), (LEFT_OUTER_JOIN, False), (RIGHT_OUTER_JOIN, True), (INNER_JOIN, True)])
+def test_merge_join_other_conditions(lib, jt, oir, ni=20000, no=30000):
+    """OtherConditions inside the joiner (baseJoiner.filter): joined rows that fail are dropped, an outer row whose joined rows all
+    fail becomes a miss row (merge_join.go:290-305); compared in order with the oracle and, as a multiset, with the hash join"""
+    rng = np.random.default_rng(90 + jt + 3 * int(oir))
+    it, ot = [INT64, INT64, FLOAT64], [INT64, UINT64, FLOAT64, INT64]
+    ic = [Column(INT64, np.sort(rng.integers(0, ni // 4, ni))), gen_col(rng, INT64, ni, 0.1, -50, 50), Column(FLOAT64, rng.integers(0, 100, ni) * 0.5, rng.random(ni) > 0.1)]
+    oc = [Column(INT64, np.sort(rng.integers(0, ni // 3, no))), gen_col(rng, UINT64, no, 0.1, 0, 50), Column(FLOAT64, rng.integers(0, 100, no) * 0.5), Column(INT64, np.arange(no))]
+    sel = (rng.random(no) > 0.1).astype(np.uint8)
+    n_left = len(it) if oir else len(ot)
+    icol = lambda c: c if oir else n_left + c            # output column of inner column c
+    ocol = lambda c: n_left + c if oir else c            # ... of outer column c
+    for conds in ([(0, icol(1), ocol(1))],                                    # inner.b < outer.u  (BIGINT vs BIGINT UNSIGNED)
+                  [(3, icol(2), ocol(2)), (5, icol(1), None, INT64, 7)],      # inner.f >= outer.f and inner.b != 7
+                  [(4, ocol(2), None, FLOAT64, 12.5)],                        # a condition on the outer side only
+                  [(2, icol(1), None, INT64, 1000)]):                         # never true: every match becomes a miss
+        got = run_mj(jt, oir, it, ic, ot, oc, [0], [0], sel, chunk=1000, conds=conds)
+        want = O.merge_join(jt, oir, it, ic, ot, oc, [0], [0], sel, conds=conds)
+        assert_same_ordered(got, want)
+        assert_same_multiset(want, O.hash_join(jt, oir, it, ic, ot, oc, [0], [0], sel, conds=conds))
 
 
 def test_merge_join_equals_hash_join_at_scale(lib):

@@ -129,6 +129,7 @@ SYMBOLS = {
     "tq_sort_stats": (_I32, [_P, C.POINTER(_I64)]),
     "tq_sort_destroy": (_I32, [_P]),
     "tq_mjoin_create": (_I32, [C.POINTER(TQMJoinDesc), C.POINTER(_P)]),
+    "tq_mjoin_set_other_conditions": (_I32, [_P, _I32, C.POINTER(TQJoinCond)]),
     "tq_mjoin_put_inner": (_I32, [_P, _COL, _I32]),
     "tq_mjoin_put_outer": (_I32, [_P, _COL, _P, _I32]),
     "tq_mjoin_finish": (_I32, [_P]),

@@ -283,6 +283,90 @@ __global__ void __launch_bounds__(256) k_mj_expand(const uint32_t *__restrict__ 
   }
 }
 
+// OtherConditions of the joiner (baseJoiner.filter, executor/joiner.go:155-167) over the joined pairs: comparisons of two 8-byte
+// columns of the joined row, or of a column with a constant; a NULL operand fails the condition (VectorizedFilter drops it)
+constexpr int MJ_MAX_CONDS = 8;
+struct MJOperand {
+  int side;               // 0 inner row, 1 outer row, 2 constant
+  int type;               // TQ_TYPE_INT64 / UINT64 / FLOAT64
+  const uint64_t *data;
+  const uint32_t *bm;
+  uint64_t cbits;
+};
+struct MJCond { int op; MJOperand a, b; };
+struct MJConds { int n; MJCond c[MJ_MAX_CONDS]; };
+
+__device__ __forceinline__ bool mj_operand(const MJOperand &x, uint32_t inner_row, uint32_t outer_row, uint64_t *v) {
+  if (x.side == 2) { *v = x.cbits; return true; }
+  const uint32_t r = x.side == 0 ? inner_row : outer_row;
+  if (!tqd::bm_not_null(x.bm, r)) return false;
+  *v = x.data[r];
+  return true;
+}
+// types.CompareInt with the operands' unsigned flags (expression/builtin_compare.go:541-560), CompareFloat64
+__device__ __forceinline__ int mj_cmp_values(int ta, uint64_t a, int tb, uint64_t b) {
+  if (ta == TQ_TYPE_FLOAT64) { const double x = __longlong_as_double((long long)a), y = __longlong_as_double((long long)b); return x < y ? -1 : (x == y ? 0 : 1); }
+  const bool ua = ta == TQ_TYPE_UINT64, ub = tb == TQ_TYPE_UINT64;
+  if (ua && ub) return a < b ? -1 : (a == b ? 0 : 1);
+  const int64_t x = (int64_t)a, y = (int64_t)b;
+  if (!ua && !ub) return x < y ? -1 : (x == y ? 0 : 1);
+  if (ua && !ub) { if (y < 0 || a > 0x7FFFFFFFFFFFFFFFull) return 1; return x < y ? -1 : (x == y ? 0 : 1); }
+  if (x < 0 || b > 0x7FFFFFFFFFFFFFFFull) return -1;
+  return x < y ? -1 : (x == y ? 0 : 1);
+}
+// flags[t] = 1 iff pair t joins an inner row and passes every condition
+__global__ void __launch_bounds__(256) k_mj_cond(const MJConds C, const uint32_t *__restrict__ out_outer, const uint32_t *__restrict__ out_inner, int64_t m,
+                                                 uint32_t *__restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += stride) {
+    const uint32_t ir = out_inner[t], orow = out_outer[t];
+    bool ok = ir != ROW_MISS;
+    for (int k = 0; ok && k < C.n; k++) {
+      uint64_t a, b;
+      if (!mj_operand(C.c[k].a, ir, orow, &a) || !mj_operand(C.c[k].b, ir, orow, &b)) { ok = false; break; }
+      const int c = mj_cmp_values(C.c[k].a.type, a, C.c[k].b.type, b);
+      const int op = C.c[k].op;
+      ok = op == TQ_CMP_LT ? c < 0 : op == TQ_CMP_LE ? c <= 0 : op == TQ_CMP_GT ? c > 0 : op == TQ_CMP_GE ? c >= 0 : op == TQ_CMP_EQ ? c == 0 : c != 0;
+    }
+    flags[t] = ok ? 1u : 0u;
+  }
+}
+// rows each outer row emits once its pairs are filtered: the survivors, or the miss row of an outer join when none survived
+__global__ void __launch_bounds__(256) k_mj_survivors(const uint32_t *__restrict__ emit_off, const uint32_t *__restrict__ fscan, int64_t n_outer, int64_t m, uint32_t n_pass,
+                                                      int outer_join, uint32_t *__restrict__ emit2) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_outer; o += stride) {
+    const int64_t lo = emit_off[o], hi = o + 1 < n_outer ? (int64_t)emit_off[o + 1] : m;
+    const uint32_t s0 = lo < m ? fscan[lo] : n_pass, s1 = hi < m ? fscan[hi] : n_pass;
+    const uint32_t surv = s1 - s0;
+    emit2[o] = surv ? surv : (outer_join ? 1u : 0u);
+  }
+}
+// surviving pairs keep their order inside the outer row's new range; an outer row without survivors writes its miss row
+__global__ void __launch_bounds__(256) k_mj_refill_pairs(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ fscan, const uint32_t *__restrict__ emit_off,
+                                                         const uint32_t *__restrict__ emit2_off, const uint32_t *__restrict__ out_outer, const uint32_t *__restrict__ out_inner,
+                                                         int64_t m, uint32_t *__restrict__ new_outer, uint32_t *__restrict__ new_inner) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += stride) {
+    if (!flags[t]) continue;
+    const uint32_t o = out_outer[t];
+    const uint32_t pos = emit2_off[o] + (fscan[t] - fscan[emit_off[o]]);
+    new_outer[pos] = o;
+    new_inner[pos] = out_inner[t];
+  }
+}
+__global__ void __launch_bounds__(256) k_mj_refill_misses(const uint32_t *__restrict__ emit_off, const uint32_t *__restrict__ fscan, const uint32_t *__restrict__ emit2_off,
+                                                          int64_t n_outer, int64_t m, uint32_t n_pass, int64_t m2, uint32_t *__restrict__ new_outer,
+                                                          uint32_t *__restrict__ new_inner) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_outer; o += stride) {
+    const int64_t lo = emit_off[o], hi = o + 1 < n_outer ? (int64_t)emit_off[o + 1] : m;
+    const uint32_t s0 = lo < m ? fscan[lo] : n_pass, s1 = hi < m ? fscan[hi] : n_pass;
+    const int64_t p0 = emit2_off[o], p1 = o + 1 < n_outer ? (int64_t)emit2_off[o + 1] : m2;
+    if (s1 == s0 && p1 > p0) { new_outer[p0] = (uint32_t)o; new_inner[p0] = ROW_MISS; }   // only outer joins have p1 > p0 here
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side: row store
 struct StoreCol {
   int type = 0;
@@ -579,6 +663,7 @@ struct tq_mjoin {
   bool has_selected = false;
   std::vector<uint64_t> dflt_bits;
   std::vector<uint8_t> dflt_nn;
+  std::vector<tq_join_cond> conds;   // OtherConditions (tq_mjoin_set_other_conditions)
   bool finished = false;
   ResultHost res;
 };
@@ -722,6 +807,32 @@ int32_t tq_mjoin_create(const tq_mjoin_desc *d, tq_mjoin **out) {
       if (h->dflt_nn[(size_t)c] && h->inner.cols[(size_t)c].kind != 0) { set_error("defaultInner values are supported for 8-byte columns"); return TQ_ERR_UNSUPPORTED_TYPE; }
   }
   *out = h.release();
+  return TQ_OK;
+}
+
+// OtherConditions: comparisons over the joined row (left ++ right), as tq_join_set_other_conditions takes them
+int32_t tq_mjoin_set_other_conditions(tq_mjoin *h, int32_t n_conds, const tq_join_cond *conds) {
+  if (!h || n_conds < 0 || n_conds > MJ_MAX_CONDS || (n_conds && !conds)) { set_error("at most %d other conditions", MJ_MAX_CONDS); return TQ_ERR_INVALID_ARG; }
+  if (h->finished || h->inner.n || h->outer.n) { set_error("other conditions must be set right after tq_mjoin_create"); return TQ_ERR_STATE; }
+  const int n_first = (int)(h->outer_is_right ? h->inner.cols.size() : h->outer.cols.size());
+  const int n_all = (int)(h->inner.cols.size() + h->outer.cols.size());
+  auto col_of = [&](int c) -> const StoreCol & {   // output column c of left ++ right
+    const bool in_first = c < n_first;
+    const RowStore &st = (in_first == (h->outer_is_right != 0)) ? h->inner : h->outer;
+    return st.cols[(size_t)(in_first ? c : c - n_first)];
+  };
+  for (int k = 0; k < n_conds; k++) {
+    const tq_join_cond &c = conds[k];
+    if (c.op < TQ_CMP_LT || c.op > TQ_CMP_NE || c.lhs_col < 0 || c.lhs_col >= n_all || c.rhs_col >= n_all) { set_error("bad other condition %d", k); return TQ_ERR_INVALID_ARG; }
+    const StoreCol &a = col_of(c.lhs_col);
+    const int tb = c.rhs_col >= 0 ? col_of(c.rhs_col).type : (c.const_type & 0xFF);
+    const bool b_fixed8 = c.rhs_col >= 0 ? col_of(c.rhs_col).kind == 0 : (tb >= TQ_TYPE_INT64 && tb <= TQ_TYPE_FLOAT64);
+    if (a.kind != 0 || !b_fixed8 || ((a.type == TQ_TYPE_FLOAT64) != (tb == TQ_TYPE_FLOAT64))) {
+      set_error("other condition %d: BIGINT with BIGINT (any sign mix) or DOUBLE with DOUBLE", k);
+      return TQ_ERR_UNSUPPORTED_TYPE;
+    }
+  }
+  h->conds.assign(conds, conds + n_conds);
   return TQ_OK;
 }
 
@@ -870,9 +981,74 @@ int32_t tq_mjoin_finish(tq_mjoin *h) {
     count_launch();
     TQ_TRY(check_launch("k_mj_expand"));
   }
+  const uint32_t *rows_o = out_o.as<uint32_t>(), *rows_i = out_i.as<uint32_t>();
+  int64_t m_out = m;
+  DevBuf flags, fscan, emit2, new_o, new_i;
+  if (!h->conds.empty()) {
+    // tryToMatchInners filters the joined rows of an outer row with the OtherConditions; when none survives the outer row
+    // takes the miss path (merge_join.go:290-305, joiner.go:225-248,288-311,351-378)
+    MJConds C{};
+    C.n = (int)h->conds.size();
+    const int n_first = (int)first->cols.size();
+    auto operand = [&](int c, int const_type, uint64_t cbits) {
+      MJOperand x{};
+      if (c < 0) { x.side = 2; x.type = const_type & 0xFF; x.cbits = cbits; return x; }
+      const bool in_first = c < n_first;
+      const RowStore *st = in_first ? first : second;
+      const StoreCol &sc = st->cols[(size_t)(in_first ? c : c - n_first)];
+      x.side = st == &h->inner ? 0 : 1;
+      x.type = sc.type;
+      x.data = sc.d_data.as<uint64_t>();
+      x.bm = sc.bm();
+      return x;
+    };
+    for (int k = 0; k < C.n; k++) {
+      C.c[k].op = h->conds[(size_t)k].op;
+      C.c[k].a = operand(h->conds[(size_t)k].lhs_col, 0, 0);
+      C.c[k].b = operand(h->conds[(size_t)k].rhs_col, h->conds[(size_t)k].const_type, h->conds[(size_t)k].const_bits);
+    }
+    TQ_TRY(flags.reserve((size_t)(m ? m : 1) * 4));
+    TQ_TRY(fscan.reserve((size_t)(m ? m : 1) * 4));
+    TQ_TRY(emit2.reserve((size_t)no * 4));
+    uint64_t n_pass = 0;
+    if (m > 0) {
+      TQ_LAUNCH(k_mj_cond, grid_for(m), 256, 0, s, C, out_o.as<uint32_t>(), out_i.as<uint32_t>(), m, flags.as<uint32_t>());
+      count_launch();
+      TQ_TRY(check_launch("k_mj_cond"));
+      TQ_TRY(exclusive_scan_u32(flags.as<uint32_t>(), 1, fscan.as<uint32_t>(), 1, m, meta.as<uint64_t>() + 3, scan, s));
+      TQ_CUDA(cudaMemcpyAsync(&n_pass, meta.as<uint64_t>() + 3, 8, cudaMemcpyDeviceToHost, s));
+      TQ_CUDA(cudaStreamSynchronize(s));
+    }
+    TQ_LAUNCH(k_mj_survivors, grid_for(no), 256, 0, s, emit.as<uint32_t>(), fscan.as<uint32_t>(), no, m, (uint32_t)n_pass, outer_join ? 1 : 0, emit2.as<uint32_t>());
+    count_launch();
+    TQ_TRY(check_launch("k_mj_survivors"));
+    TQ_TRY(exclusive_scan_u32(emit2.as<uint32_t>(), 1, emit2.as<uint32_t>(), 1, no, meta.as<uint64_t>() + 4, scan, s));
+    uint64_t total2 = 0;
+    TQ_CUDA(cudaMemcpyAsync(&total2, meta.as<uint64_t>() + 4, 8, cudaMemcpyDeviceToHost, s));
+    TQ_CUDA(cudaStreamSynchronize(s));
+    const int64_t m2 = (int64_t)total2;
+    TQ_TRY(new_o.reserve((size_t)(m2 ? m2 : 1) * 4));
+    TQ_TRY(new_i.reserve((size_t)(m2 ? m2 : 1) * 4));
+    if (m > 0 && m2 > 0) {
+      TQ_LAUNCH(k_mj_refill_pairs, grid_for(m), 256, 0, s, flags.as<uint32_t>(), fscan.as<uint32_t>(), emit.as<uint32_t>(), emit2.as<uint32_t>(), out_o.as<uint32_t>(),
+                out_i.as<uint32_t>(), m, new_o.as<uint32_t>(), new_i.as<uint32_t>());
+      count_launch();
+      TQ_TRY(check_launch("k_mj_refill_pairs"));
+    }
+    if (m2 > 0 && outer_join) {
+      TQ_LAUNCH(k_mj_refill_misses, grid_for(no), 256, 0, s, emit.as<uint32_t>(), fscan.as<uint32_t>(), emit2.as<uint32_t>(), no, m, (uint32_t)n_pass, m2,
+                new_o.as<uint32_t>(), new_i.as<uint32_t>());
+      count_launch();
+      TQ_TRY(check_launch("k_mj_refill_misses"));
+    }
+    rows_o = new_o.as<uint32_t>();
+    rows_i = new_i.as<uint32_t>();
+    m_out = m2;
+    h->res.n = m2;
+  }
   // output schema = left child columns ++ right child columns (executor/builder.go: the joiner's makeJoinRowToChunk)
-  TQ_TRY(gather_columns(*first, first == &h->inner ? out_i.as<uint32_t>() : out_o.as<uint32_t>(), m, dflt_b(first), dflt_n(first), h->res, g, s));
-  TQ_TRY(gather_columns(*second, second == &h->inner ? out_i.as<uint32_t>() : out_o.as<uint32_t>(), m, dflt_b(second), dflt_n(second), h->res, g, s));
+  TQ_TRY(gather_columns(*first, first == &h->inner ? rows_i : rows_o, m_out, dflt_b(first), dflt_n(first), h->res, g, s));
+  TQ_TRY(gather_columns(*second, second == &h->inner ? rows_i : rows_o, m_out, dflt_b(second), dflt_n(second), h->res, g, s));
   return TQ_OK;
 }
 

@@ -322,7 +322,9 @@ class MergeJoinExec:
     """executor/merge_join.go:31-373.  Both children sorted ascending by their keys; output = left ++ right in outer order."""
 
     def __init__(self, outer_exec, inner_exec, outer_keys, inner_keys, join_type=INNER_JOIN, outer_is_right=False, outer_filter=None,
-                 max_chunk_size=MAX_CHUNK_SIZE, default_inner=None):
+                 max_chunk_size=MAX_CHUNK_SIZE, default_inner=None, other_conditions=()):
+        # other_conditions: (op, lhs_col, rhs_col) or (op, lhs_col, None, const_type, const_value) over the output row left ++ right
+        self.other_conditions = list(other_conditions)
         self.outer, self.inner = outer_exec, inner_exec
         self.outer_keys, self.inner_keys = list(outer_keys), list(inner_keys)
         self.join_type, self.outer_is_right, self.outer_filter = join_type, outer_is_right, outer_filter
@@ -346,6 +348,15 @@ class MergeJoinExec:
         h = C.c_void_p()
         L.check(lib.tq_mjoin_create(C.byref(d), C.byref(h)))
         self.handle, self.prepared = h, False
+        if self.other_conditions:
+            from .chunk import _NP
+            arr = (L.TQJoinCond * len(self.other_conditions))()
+            for i, c in enumerate(self.other_conditions):
+                if c[2] is None:
+                    arr[i] = L.TQJoinCond(c[0], c[1], -1, c[3], int(np.array([c[4]], dtype=_NP[c[3]]).view(np.uint64)[0]))
+                else:
+                    arr[i] = L.TQJoinCond(c[0], c[1], c[2], 0, 0)
+            L.check(lib.tq_mjoin_set_other_conditions(h, len(self.other_conditions), arr))
 
     def Next(self, required_rows=None):
         lib = L.load()
