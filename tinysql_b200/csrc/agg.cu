@@ -740,8 +740,7 @@ static int32_t agg_try_preagg(tq_agg *a, const DCol *cols, int64_t n, bool *done
   unsigned long long *d_overflow = d_out_n + 1;                            // [1] scatter slab overflow
   unsigned *d_fallback = reinterpret_cast<unsigned *>(d_out_n + 2);        // [2] pre-aggregation gave up
   TQ_CUDA(cudaEventRecord(a->ev_pa, s));
-  static const bool old_scatter = [] { const char *e = getenv("TQ_AGG_PREAGG_OLD_SCATTER"); return e && e[0] == '1'; }();
-  if (pbits && pbits <= SCATTER_AOS_MAX_PBITS && !old_scatter) {
+  if (pbits && pbits <= SCATTER_AOS_MAX_PBITS) {
     TQ_TRY(scatter_rows_by_hash_aos(used, n_used, 0, n, pbits, a->pre_aos, a->pre_lo, a->pre_hi, a->pre_lim, d_overflow, s));
     p.aos = a->pre_aos.as<uint64_t>();
     p.aos_nc = n_used;

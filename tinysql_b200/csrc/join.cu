@@ -34,16 +34,16 @@ static constexpr uint32_t OFF_MISS = 0xFFFFFFFFu;
 static constexpr int64_t PART_MIN_BUILD_ROWS = 1 << 18;  // below this the whole table (<= 8 MB) is L2-resident anyway
 static constexpr int PART_MAX_BITS = 12;
 static constexpr uint64_t PART_MAX_SMEM_BYTES = 128 << 10;  // a partition table image that still fits in shared memory
-static int64_t g_tiles_per_cta = 8;
+static const int64_t g_tiles_per_cta = 8;
 static int64_t g_part_target_rows = 150000;              // build rows per partition: a partition table ~ 4-8 MB, a few live ones fit in L2
-static int64_t g_max_load_pct = 50;                      // TQ_JOIN_MAX_LOAD_PCT: partition-table load-factor bound (pair probing keeps chains short)
+static const int64_t g_max_load_pct = 50;                // partition-table load-factor bound (pair probing keeps chains short)
 static bool g_exact_scatter = false;                     // TQ_JOIN_EXACT_SCATTER=1: always run the probe-side histogram pass
 static bool g_no_fast_kernel = false;                    // TQ_JOIN_NO_FAST=1: use the generic kernels (tests)
 static bool g_force_global_table = false;                // TQ_JOIN_FORCE_GLOBAL=1: A/B switch for profiling
-static bool g_old_fast = false;                          // TQ_JOIN_OLD_FAST=1: the round-1 PK-FK kernels instead of the streaming pipeline (A/B)
+static const bool g_old_fast = false;                    // the round-1 PK-FK kernels instead of the streaming pipeline: measured slower, kept only for the paths that still call them
 static bool g_debug_sums = false;                        // TQ_JOIN_DEBUG_SUMS=1: print per-stage row counts / column checksums of the streaming pipeline (diagnostics)
 static bool g_no_tma = false;                            // TQ_JOIN_NO_TMA=1: plain loads instead of TMA bulk copies in the AoS scatter (diagnostics)
-static int g_scatter_tile = 2048;                        // TQ_JOIN_SCATTER_TILE=1024|2048|4096: rows per tile of the AoS scatter
+static const int g_scatter_tile = 2048;                  // rows per tile of the AoS scatter (1024 / 4096 measured slower: DESIGN §5)
 
 // key_mode: how (flag, raw bytes) equality (util/codec/codec.go:212-240,363-382) maps onto raw 8-byte equality
 //   0: flags always agree (both signed, both unsigned, or both DOUBLE)  -> raw equality
@@ -2669,13 +2669,9 @@ int32_t tq_join_create(const tq_join_desc *d, tq_join **out) {
   if (d->join_type == TQ_JOIN_RIGHT_OUTER && !d->outer_is_right) { set_error("right outer join needs outer_is_right == 1"); return TQ_ERR_INVALID_ARG; }
   { const char *e = getenv("TQ_JOIN_FORCE_GLOBAL"); g_force_global_table = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_NO_FAST"); g_no_fast_kernel = e && e[0] == '1'; }
-  { const char *e = getenv("TQ_JOIN_OLD_FAST"); g_old_fast = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_NO_TMA"); g_no_tma = e && e[0] == '1'; }
   { const char *e = getenv("TQ_JOIN_DEBUG_SUMS"); g_debug_sums = e && e[0] == '1'; }
-  { const char *e = getenv("TQ_JOIN_SCATTER_TILE"); g_scatter_tile = (e && (atoi(e) == 4096 || atoi(e) == 1024)) ? atoi(e) : 2048; }
   { const char *e = getenv("TQ_JOIN_EXACT_SCATTER"); g_exact_scatter = e && e[0] == '1'; }
-  { const char *e = getenv("TQ_JOIN_MAX_LOAD_PCT"); if (e && atoll(e) >= 10 && atoll(e) <= 90) g_max_load_pct = atoll(e); }
-  { const char *e = getenv("TQ_JOIN_TILES_PER_CTA"); if (e && atoll(e) > 0) g_tiles_per_cta = atoll(e); }
   { const char *e = getenv("TQ_JOIN_PART_ROWS"); if (e && atoll(e) > 0) g_part_target_rows = atoll(e); }
   tq_join *j = new (std::nothrow) tq_join();
   if (!j) return TQ_ERR_OOM;
