@@ -105,8 +105,8 @@ int32_t check_launch(const char *) { return TQ_OK; }
 int32_t DevBuf::reserve(size_t bytes) {
   if (bytes <= cap && p) return TQ_OK;
   release();
-  p = malloc(bytes + 64);
-  memset(p, 0xA5, bytes + 64);   // device memory is not zeroed
+  p = malloc(bytes ? bytes : 1);   // exact size: an out-of-bounds access of a kernel is visible to AddressSanitizer / valgrind
+  if (p) memset(p, 0xA5, bytes);   // device memory is not zeroed
   cap = bytes;
   return p ? TQ_OK : TQ_ERR_OOM;
 }
@@ -114,7 +114,7 @@ void DevBuf::release() { free(p); p = nullptr; cap = 0; }
 int32_t PinBuf::reserve(size_t bytes) {
   if (bytes <= cap && p) return TQ_OK;
   release();
-  p = malloc(bytes + 64);
+  p = malloc(bytes ? bytes : 1);
   cap = bytes;
   return p ? TQ_OK : TQ_ERR_OOM;
 }
