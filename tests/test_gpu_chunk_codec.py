@@ -62,6 +62,8 @@ def test_device_decode_equals_host_decode(lib, n, null_frac):
         d.decode(buf + buf, types)    # two chunks back to back: `consumed` finds the boundary
         assert d.consumed == used == len(buf)
         assert_chunks_equal(d.to_host(), want)
+        for v in d.tq_cols:   # the alignment the TQ_MEM_DEVICE entry points ask for (include/tinysql_b200.h: tq_column)
+            assert v.data % 16 == 0 and (not v.null_bitmap or v.null_bitmap % 8 == 0) and (not v.offsets or v.offsets % 8 == 0)
     d.free()
 
 

@@ -185,7 +185,7 @@ int32_t tq_chunk_decode_device(const uint8_t *buffer, int64_t len, int32_t n_col
   std::lock_guard<std::recursive_mutex> lk(r.mu);
   tq_chunk_device *h = *chunk ? *chunk : new tq_chunk_device();
   auto fail = [&](int32_t st) { if (!*chunk) delete h; return st; };
-  // arena layout: per column bitmap words (+1 pad word: kernels read bitmaps as 32-bit words), offsets, data
+  // arena layout: per column bitmap words (+1 pad word: kernels read bitmaps as 32-bit words), offsets, data; each piece 16-byte aligned
   UnpackParams p{};
   uint64_t arena_words = 0;
   std::vector<uint64_t> dst_word((size_t)n_cols * 3 + 1, 0);
@@ -199,7 +199,7 @@ int32_t tq_chunk_decode_device(const uint8_t *buffer, int64_t len, int32_t n_col
       sg.valid_bits = (uint64_t)n;
       sg.n_words = (uint64_t)((n + 63) >> 6) + 1;
       dst_word[p.n_segs++] = arena_words;
-      arena_words += sg.n_words;
+      arena_words += (sg.n_words + 1) & ~1ull;   // every piece starts 16-byte aligned (the tq_vec_* / tq_expr_eval device rule)
     }
     if (fl < 0) {
       UnpackSeg &sg = p.seg[p.n_segs];
@@ -207,7 +207,7 @@ int32_t tq_chunk_decode_device(const uint8_t *buffer, int64_t len, int32_t n_col
       sg.valid_bits = (uint64_t)(n + 1) * 64;
       sg.n_words = (uint64_t)(n + 1);
       dst_word[p.n_segs++] = arena_words;
-      arena_words += sg.n_words;
+      arena_words += (sg.n_words + 1) & ~1ull;   // every piece starts 16-byte aligned (the tq_vec_* / tq_expr_eval device rule)
     }
     int64_t data_bytes = n * fl;
     if (fl < 0) memcpy(&data_bytes, reinterpret_cast<const uint8_t *>(v.offsets) + n * 8, 8);
@@ -217,7 +217,7 @@ int32_t tq_chunk_decode_device(const uint8_t *buffer, int64_t len, int32_t n_col
       sg.valid_bits = (uint64_t)data_bytes * 8;
       sg.n_words = (uint64_t)((data_bytes + 7) >> 3) + 1;   // at least one word: data is never a NULL pointer
       dst_word[p.n_segs++] = arena_words;
-      arena_words += sg.n_words;
+      arena_words += (sg.n_words + 1) & ~1ull;   // every piece starts 16-byte aligned (the tq_vec_* / tq_expr_eval device rule)
     }
   }
   int32_t st = h->blob.reserve((size_t)*consumed + 32);
