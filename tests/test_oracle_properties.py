@@ -130,3 +130,57 @@ def test_other_condition_reference_golden():
     l, r = table(t1, 2), table(t, 2)
     got = O.hash_join(INNER, False, [INT64, INT64], r, [INT64, INT64], l, [0], [0], None, [(0, 2, 1)]).rows()  # t.a (col 2) < t1.b (col 1)
     assert sorted(got) == [(1, 2, 1, 1), (1, 3, 1, 1), (1, 4, 1, 1), (3, 4, 3, 3)]
+
+
+# ---------------------------------------------------------------------------------------------- sort / top-n / merge join
+by_item = st.tuples(st.integers(0, 1), st.booleans())
+
+
+@settings(max_examples=150, deadline=None)
+@given(rows2, st.lists(by_item, min_size=0, max_size=3), st.integers(0, 6), st.integers(-1, 8))
+def test_sort_is_a_stable_permutation_ordered_by_the_by_items(rows, by, off, cnt):
+    t2 = [INT64, INT64]
+    cols = table(rows, 2) + [Column(INT64, np.arange(len(rows)))]            # row id: makes the permutation visible
+    got = O.sort(t2 + [INT64], cols, by).rows()
+    assert sorted(r[2] for r in got) == list(range(len(rows)))                # a permutation of the child rows
+    assert [r[:2] for r in got] == [tuple(rows[r[2]]) for r in got]           # rows travel whole
+
+    def cmp_key(r):   # cmpNull + the value, sign flipped for Desc (sort.go:115-129)
+        return tuple(((0, 0) if r[c] is None else (1, r[c])) for c, _ in by)
+    for a, b in zip(got, got[1:]):
+        for c, desc in by:
+            ka, kb = ((0, 0) if a[c] is None else (1, a[c])), ((0, 0) if b[c] is None else (1, b[c]))
+            if ka != kb:
+                assert (ka > kb) if desc else (ka < kb)
+                break
+        else:
+            assert a[2] < b[2]                                                 # equal keys keep child order
+    # sorting the sorted rows again changes nothing (idempotence), TopN is a window of the order
+    again = O.sort(t2 + [INT64], [Column(INT64, [0 if r[c] is None else r[c] for r in got], [r[c] is not None for r in got]) for c in range(2)] +
+                   [Column(INT64, [r[2] for r in got])], by).rows()
+    assert again == got
+    lo = min(off, len(got))
+    assert O.sort(t2 + [INT64], cols, by, off, cnt).rows() == (got[lo:] if cnt < 0 else got[lo: lo + cnt])
+
+
+@settings(max_examples=150, deadline=None)
+@given(rows2, rows2, st.sampled_from([(INNER, False), (INNER, True), (LEFT, False), (RIGHT, True)]), st.lists(st.booleans(), min_size=40, max_size=40))
+def test_merge_join_of_sorted_children_is_the_hash_join_in_outer_order(inner_rows, outer_rows, mode, sel_bits):
+    jt, oir = mode
+    t2 = [INT64, INT64]
+    inner = O.sort(t2, table(inner_rows, 2), [(0, False)])
+    outer = O.sort(t2, table(outer_rows, 2), [(0, False)])
+    sel = np.array(sel_bits[: len(outer_rows)], dtype=np.uint8)
+    mj = O.merge_join(jt, oir, t2, inner.cols, t2, outer.cols, [0], [0], sel).rows()
+    hj = O.hash_join(jt, oir, t2, inner.cols, t2, outer.cols, [0], [0], sel).rows()
+    assert sorted(mj, key=key) == sorted(hj, key=key)                         # the same rows as the hash join ...
+    o_cols = slice(2, 4) if oir else slice(0, 2)
+    orows = outer.rows()
+    pos, it = [], iter(range(len(orows)))
+    cur = next(it, None)
+    for r in mj:                                                               # ... in the order of the outer child
+        while cur is not None and tuple(orows[cur]) != r[o_cols]:
+            cur = next(it, None)
+        assert cur is not None, "an output row does not follow the outer child's order"
+        pos.append(cur)
+    assert pos == sorted(pos)
