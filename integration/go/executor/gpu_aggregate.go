@@ -8,12 +8,14 @@ package executor
 /*
 #cgo CFLAGS: -I${SRCDIR}/../../../include
 #cgo LDFLAGS: -ltinysql_b200
+#include <stdlib.h>
 #include "tinysql_b200.h"
 */
 import "C"
 
 import (
 	"context"
+	"unsafe"
 
 	"github.com/pingcap/tidb/expression"
 	"github.com/pingcap/tidb/expression/aggregation"
@@ -32,7 +34,8 @@ type GPUHashAggExec struct {
 
 	h           *C.tq_agg
 	childResult *chunk.Chunk
-	views       []chunk.CColumn
+	inViews     *chunk.CViewSet // argument block in C memory (cgo pointer rules, util/chunk/gpu_bridge.go)
+	pump        resultPump      // result chunks incl. FLOAT / var-len columns (gpu_sort_merge.go)
 	prepared    bool
 }
 
@@ -60,36 +63,57 @@ func (e *GPUHashAggExec) Open(ctx context.Context) error {
 		return err
 	}
 	childTypes := retTypes(e.children[0])
-	it := i32s(len(childTypes), func(i int) C.int32_t {
-		t := tqType(childTypes[i])
+	it := make([]C.int32_t, len(childTypes))
+	for i := range it {
+		it[i] = tqType(childTypes[i])
 		if mysql.HasNotNullFlag(childTypes[i].Flag) {
-			t |= C.TQ_TYPE_NOT_NULL // lets SUM / MAX / MIN drop their "saw a value" word
+			it[i] |= C.TQ_TYPE_NOT_NULL // lets SUM / MAX / MIN drop their "saw a value" word
 		}
-		return t
-	})
-	gb := i32s(len(e.groupByItems), func(i int) C.int32_t { return C.int32_t(e.groupByItems[i].(*expression.Column).Index) })
+	}
+	gb := make([]C.int32_t, len(e.groupByItems))
+	for i := range gb {
+		gb[i] = C.int32_t(e.groupByItems[i].(*expression.Column).Index)
+	}
 	funcs := make([]C.tq_agg_func, len(e.aggFuncs))
 	for i, f := range e.aggFuncs {
 		kind, _ := aggKind(f.Name)
-		funcs[i].func = kind
+		funcs[i]._func = kind // cgo renames the C field `func`
 		funcs[i].arg_col = -1 // a constant non-NULL argument: COUNT(*) == count(1) (parser.y:3258-3262)
 		if col, ok := f.Args[0].(*expression.Column); ok {
 			funcs[i].arg_col = C.int32_t(col.Index)
 		}
 	}
-	var d C.tq_agg_desc
-	d.n_input_cols, d.input_types = C.int32_t(len(it)), &it[0]
-	d.n_group_by = C.int32_t(len(gb))
-	if len(gb) > 0 {
-		d.group_by_cols = &gb[0]
-	}
-	d.n_funcs, d.funcs = C.int32_t(len(funcs)), &funcs[0]
-	d.est_groups = C.int64_t(e.estGroups) // the planner's NDV estimate sizes the table and enables pre-aggregation
-	if st := C.tq_agg_create(&d, &e.h); st != C.TQ_OK {
-		return chunk.StatusError(int32(st))
+	if isFinalMode(e.aggFuncs) { // pushed-down partial results: gpu_aggregate_final.go
+		if err := e.openFinal(ctx); err != nil {
+			return err
+		}
+	} else {
+		// the descriptor and its arrays live in C memory for the duration of the call
+		d := (*C.tq_agg_desc)(C.calloc(1, C.sizeof_tq_agg_desc))
+		cit := cInt32s(len(it), func(i int) C.int32_t { return it[i] })
+		cgb := cInt32s(len(gb), func(i int) C.int32_t { return gb[i] })
+		cf := (*[1 << 8]C.tq_agg_func)(C.calloc(C.size_t(len(funcs)), C.sizeof_tq_agg_func))
+		copy(cf[:len(funcs)], funcs)
+		d.n_input_cols, d.input_types = C.int32_t(len(it)), cit
+		d.n_group_by, d.group_by_cols = C.int32_t(len(gb)), cgb
+		d.n_funcs, d.funcs = C.int32_t(len(funcs)), &cf[0]
+		d.est_groups = C.int64_t(e.estGroups) // the planner's NDV estimate sizes the table and enables pre-aggregation
+		st := C.tq_agg_create(d, &e.h)
+		for _, p := range []unsafe.Pointer{unsafe.Pointer(d), unsafe.Pointer(cit), unsafe.Pointer(cgb), unsafe.Pointer(cf)} {
+			C.free(p)
+		}
+		if st != C.TQ_OK {
+			return chunk.StatusError(int32(st))
+		}
 	}
 	e.childResult = newFirstChunk(e.children[0])
-	e.views = make([]chunk.CColumn, len(funcs))
+	e.inViews = chunk.NewCViewSet(len(childTypes))
+	e.pump = resultPump{outViews: chunk.NewCViewSet(len(e.aggFuncs)), sizes: (*C.int64_t)(C.calloc(C.size_t(len(e.aggFuncs)), 8))}
+	for i := range e.aggFuncs {
+		var t C.int32_t
+		C.tq_agg_output_type(e.h, C.int32_t(i), &t) // COUNT -> BIGINT; MAX / MIN / FIRSTROW keep FLOAT / string columns
+		e.pump.outTypes = append(e.pump.outTypes, t)
+	}
 	e.prepared = false
 	return nil
 }
@@ -98,7 +122,6 @@ func (e *GPUHashAggExec) Open(ctx context.Context) error {
 func (e *GPUHashAggExec) Next(ctx context.Context, req *chunk.Chunk) error {
 	req.Reset()
 	if !e.prepared {
-		in := make([]chunk.CColumn, e.childResult.NumCols())
 		for { // fetchChildData (aggregate.go:487-522)
 			if err := Next(ctx, e.children[0], e.childResult); err != nil {
 				return err
@@ -106,8 +129,10 @@ func (e *GPUHashAggExec) Next(ctx context.Context, req *chunk.Chunk) error {
 			if e.childResult.NumRows() == 0 {
 				break
 			}
-			e.childResult.CViews(in)
-			if st := C.tq_agg_put(e.h, &in[0], C.TQ_MEM_HOST); st != C.TQ_OK {
+			e.inViews.FillChunk(e.childResult)
+			st := C.tq_agg_put(e.h, e.inViews.Ptr(), C.TQ_MEM_HOST)
+			e.inViews.Release()
+			if st != C.TQ_OK {
 				return chunk.StatusError(int32(st))
 			}
 		}
@@ -116,22 +141,15 @@ func (e *GPUHashAggExec) Next(ctx context.Context, req *chunk.Chunk) error {
 		}
 		e.prepared = true
 	}
-	want := req.RequiredRows()
-	for i := range e.views {
-		req.Column(i).PrepareFixedResult(want, 8, &e.views[i])
+	// the default row of an empty scalar aggregate (aggregate.go:572-574) is produced by the library;
+	// SUM(BIGINT) overflow surfaces here as types.ErrOverflow (func_sum.go:133-136)
+	err := e.pump.fill(req,
+		func(want C.int64_t, sizes *C.int64_t) C.int32_t { return C.tq_agg_next_bytes(e.h, want, sizes) },
+		func(want C.int64_t, out *C.tq_column, n *C.int64_t, eof *C.int32_t) C.int32_t { return C.tq_agg_next(e.h, want, out, n, eof) })
+	if se, ok := err.(chunk.StatusError); ok {
+		return statusToAggError(C.int32_t(se))
 	}
-	var n C.int64_t
-	var eof C.int32_t
-	// the default row of an empty scalar aggregate (aggregate.go:572-574) is produced by the library
-	st := C.tq_agg_next(e.h, C.int64_t(want), &e.views[0], &n, &eof)
-	if st != C.TQ_OK {
-		return statusToAggError(st) // SUM(BIGINT) overflow -> types.ErrOverflow (func_sum.go:133-136)
-	}
-	for i := range e.views {
-		req.Column(i).SetResultRows(int(n))
-	}
-	req.SetNumVirtualRows(int(n))
-	return nil
+	return err
 }
 
 // statusToAggError: SUM / AVG over BIGINT report types.ErrOverflow like types.AddInt64 does (func_sum.go:133-136).
@@ -147,6 +165,9 @@ func (e *GPUHashAggExec) Close() error {
 	if e.h != nil {
 		C.tq_agg_destroy(e.h)
 		e.h = nil
+		e.inViews.Free()
+		e.pump.outViews.Free()
+		C.free(unsafe.Pointer(e.pump.sizes))
 	}
 	return e.baseExecutor.Close()
 }
