@@ -14,6 +14,8 @@ package expression
 import "C"
 
 import (
+	"unsafe"
+
 	"github.com/pingcap/tidb/parser/mysql"
 	"github.com/pingcap/tidb/types"
 	"github.com/pingcap/tidb/util/chunk"
@@ -73,10 +75,36 @@ func evalTwoArgs(b *baseBuiltinFunc, input *chunk.Chunk, et types.EvalType) (buf
 	return
 }
 
+// twoArgCall is the per-signature argument block of a tq_vec_* call: three tq_column structs in C memory (cgo pointer rules:
+// a tq_column in Go memory would hold Go pointers — util/chunk/gpu_bridge.go) — entries 0 / 1 the operands, 2 the result.
+type twoArgCall struct{ v *chunk.CViewSet }
+
+func (c *twoArgCall) begin(buf0, buf1, result *chunk.Column, n, elemLen int) (a, b, out *C.tq_column) {
+	if c.v == nil {
+		c.v = chunk.NewCViewSet(3)
+	}
+	c.v.Fill(0, buf0)
+	c.v.Fill(1, buf1)
+	result.PrepareFixedResult(n, elemLen)
+	c.v.FillResult(2, result)
+	return (*C.tq_column)(unsafe.Pointer(c.v.At(0))), (*C.tq_column)(unsafe.Pointer(c.v.At(1))), (*C.tq_column)(unsafe.Pointer(c.v.At(2)))
+}
+
+// end unpins the operands and, on success, moves the produced rows into the result column (a no-op when the result buffer was
+// pinned or C-owned and written in place).
+func (c *twoArgCall) end(result *chunk.Column, n int, st C.int32_t) {
+	c.v.Release()
+	if st == C.TQ_OK {
+		c.v.CopyBack(2, result, n)
+		result.SetResultRows(n)
+	}
+}
+
 // gpuCompareIntSig: builtin{LT,LE,GT,GE,EQ,NE}IntSig.vecEvalInt (builtin_compare_vec.go:22-292)
 type gpuCompareIntSig struct {
 	baseBuiltinFunc
-	op C.int32_t
+	op   C.int32_t
+	call twoArgCall
 }
 
 func (b *gpuCompareIntSig) vectorized() bool { return true }
@@ -88,20 +116,19 @@ func (b *gpuCompareIntSig) vecEvalInt(input *chunk.Chunk, result *chunk.Column) 
 		return err
 	}
 	defer release()
-	var a, bb, out chunk.CColumn
-	buf0.CView(&a)
-	buf1.CView(&bb)
-	result.PrepareFixedResult(n, 8, &out)
+	a, bb, out := b.call.begin(buf0, buf1, result, n, 8)
 	st := C.tq_vec_compare_int(b.op, C.int64_t(n),
-		&a, cbool(mysql.HasUnsignedFlag(b.args[0].GetType().Flag)),
-		&bb, cbool(mysql.HasUnsignedFlag(b.args[1].GetType().Flag)), &out, C.TQ_MEM_HOST)
+		a, cbool(mysql.HasUnsignedFlag(b.args[0].GetType().Flag)),
+		bb, cbool(mysql.HasUnsignedFlag(b.args[1].GetType().Flag)), out, C.TQ_MEM_HOST)
+	b.call.end(result, n, st)
 	return statusToError(st, "")
 }
 
 // gpuCompareRealSig / gpuCompareStringSig: builtin{LT..NE}{Real,String}Sig (builtin_compare_vec_generated.go)
 type gpuCompareRealSig struct {
 	baseBuiltinFunc
-	op C.int32_t
+	op   C.int32_t
+	call twoArgCall
 }
 
 func (b *gpuCompareRealSig) vectorized() bool { return true }
@@ -113,16 +140,16 @@ func (b *gpuCompareRealSig) vecEvalInt(input *chunk.Chunk, result *chunk.Column)
 		return err
 	}
 	defer release()
-	var a, bb, out chunk.CColumn
-	buf0.CView(&a)
-	buf1.CView(&bb)
-	result.PrepareFixedResult(n, 8, &out)
-	return statusToError(C.tq_vec_compare_real(b.op, C.int64_t(n), &a, &bb, &out, C.TQ_MEM_HOST), "")
+	a, bb, out := b.call.begin(buf0, buf1, result, n, 8)
+	st := C.tq_vec_compare_real(b.op, C.int64_t(n), a, bb, out, C.TQ_MEM_HOST)
+	b.call.end(result, n, st)
+	return statusToError(st, "")
 }
 
 type gpuCompareStringSig struct {
 	baseBuiltinFunc
-	op C.int32_t // TQ_CMP_* or TQ_STR_STRCMP (builtinStrcmpSig, builtin_string_vec.go:52-83)
+	op   C.int32_t // TQ_CMP_* or TQ_STR_STRCMP (builtinStrcmpSig, builtin_string_vec.go:52-83)
+	call twoArgCall
 }
 
 func (b *gpuCompareStringSig) vectorized() bool { return true }
@@ -134,11 +161,10 @@ func (b *gpuCompareStringSig) vecEvalInt(input *chunk.Chunk, result *chunk.Colum
 		return err
 	}
 	defer release()
-	var a, bb, out chunk.CColumn
-	buf0.CView(&a)
-	buf1.CView(&bb)
-	result.PrepareFixedResult(n, 8, &out)
-	return statusToError(C.tq_vec_compare_string(b.op, C.int64_t(n), &a, &bb, &out, C.TQ_MEM_HOST), "")
+	a, bb, out := b.call.begin(buf0, buf1, result, n, 8)
+	st := C.tq_vec_compare_string(b.op, C.int64_t(n), a, bb, out, C.TQ_MEM_HOST)
+	b.call.end(result, n, st)
+	return statusToError(st, "")
 }
 
 // gpuArithIntSig: builtinArithmetic{Plus,Minus,Multiply}IntSig and MultiplyIntUnsignedSig
@@ -147,6 +173,7 @@ type gpuArithIntSig struct {
 	baseBuiltinFunc
 	op   C.int32_t
 	expr string // "(%s + %s)" text for the overflow error, as the Go loops build it
+	call twoArgCall
 }
 
 func (b *gpuArithIntSig) vectorized() bool { return true }
@@ -158,13 +185,11 @@ func (b *gpuArithIntSig) vecEvalInt(input *chunk.Chunk, result *chunk.Column) er
 		return err
 	}
 	defer release()
-	var a, bb, out chunk.CColumn
-	buf0.CView(&a)
-	buf1.CView(&bb)
-	result.PrepareFixedResult(n, 8, &out)
+	a, bb, out := b.call.begin(buf0, buf1, result, n, 8)
 	st := C.tq_vec_arith_int(b.op, C.int64_t(n),
-		&a, cbool(mysql.HasUnsignedFlag(b.args[0].GetType().Flag)),
-		&bb, cbool(mysql.HasUnsignedFlag(b.args[1].GetType().Flag)), &out, C.TQ_MEM_HOST)
+		a, cbool(mysql.HasUnsignedFlag(b.args[0].GetType().Flag)),
+		bb, cbool(mysql.HasUnsignedFlag(b.args[1].GetType().Flag)), out, C.TQ_MEM_HOST)
+	b.call.end(result, n, st)
 	return statusToError(st, b.expr)
 }
 
@@ -173,6 +198,7 @@ type gpuArithRealSig struct {
 	baseBuiltinFunc
 	op   C.int32_t
 	expr string
+	call twoArgCall
 }
 
 func (b *gpuArithRealSig) vectorized() bool { return true }
@@ -184,12 +210,10 @@ func (b *gpuArithRealSig) vecEvalReal(input *chunk.Chunk, result *chunk.Column) 
 		return err
 	}
 	defer release()
-	var a, bb, out chunk.CColumn
-	buf0.CView(&a)
-	buf1.CView(&bb)
-	result.PrepareFixedResult(n, 8, &out)
-	var divByZero C.int64_t
-	st := C.tq_vec_arith_real(b.op, C.int64_t(n), &a, &bb, &out, &divByZero, C.TQ_MEM_HOST)
+	a, bb, out := b.call.begin(buf0, buf1, result, n, 8)
+	var divByZero C.int64_t // a Go int64 holds no pointers: legal as a direct argument
+	st := C.tq_vec_arith_real(b.op, C.int64_t(n), a, bb, out, &divByZero, C.TQ_MEM_HOST)
+	b.call.end(result, n, st)
 	if err := statusToError(st, b.expr); err != nil {
 		return err
 	}

@@ -75,6 +75,9 @@ func (s *CViewSet) Free() {
 // Ptr is what a tq_* call takes.
 func (s *CViewSet) Ptr() *C.tq_column { return s.cols }
 
+// At returns entry i of the C array (for entry points that take single tq_column pointers, the tq_vec_* family).
+func (s *CViewSet) At(i int) *C.tq_column { return s.at(i) }
+
 func (s *CViewSet) at(i int) *C.tq_column {
 	return (*C.tq_column)(unsafe.Pointer(uintptr(unsafe.Pointer(s.cols)) + uintptr(i)*unsafe.Sizeof(C.tq_column{})))
 }
