@@ -451,10 +451,15 @@ typedef struct tq_sort_desc {
 } tq_sort_desc;
 typedef struct tq_sort tq_sort;
 int32_t tq_sort_create(const tq_sort_desc *desc, tq_sort **out);
-int32_t tq_sort_put(tq_sort *s, const tq_column *cols, int32_t mem);   /* host chunks */
+/* Chunks come from host memory (all chunk layouts) or, for 8-byte column types, from HBM (TQ_MEM_DEVICE: e.g. the rows
+ * tq_join_next_device lends) — one or the other per handle.  With device chunks the rows never leave the GPU: tq_sort_next_device
+ * lends the result (the TopN window) as device columns, and tq_sort_next copies it to the host only if it is called. */
+int32_t tq_sort_put(tq_sort *s, const tq_column *cols, int32_t mem);
 int32_t tq_sort_eof(tq_sort *s);
 int32_t tq_sort_next_bytes(tq_sort *s, int64_t max_rows, int64_t *bytes_per_col);
 int32_t tq_sort_next(tq_sort *s, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+/* device-chunk handles: the whole result at once as DEVICE columns, lent until tq_sort_destroy; then eof */
+int32_t tq_sort_next_device(tq_sort *s, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
 /* [0] rows sorted, [1] device time of the sort phase in ns (CUDA events; upload and result gather excluded),
  * [2] kernel launches of tq_sort_eof, [3] radix digit passes that ran (constant digits are skipped) */
 int32_t tq_sort_stats(tq_sort *s, int64_t *stats4);
@@ -486,11 +491,14 @@ int32_t tq_mjoin_create(const tq_mjoin_desc *desc, tq_mjoin **out);
  * tq_join_cond comparisons tq_join_set_other_conditions takes, over the joined row left ++ right; an outer row whose joined rows
  * all fail takes the miss path.  Call once, right after tq_mjoin_create. */
 int32_t tq_mjoin_set_other_conditions(tq_mjoin *j, int32_t n_conds, const tq_join_cond *conds);
-int32_t tq_mjoin_put_inner(tq_mjoin *j, const tq_column *cols, int32_t mem);                          /* host chunks */
-int32_t tq_mjoin_put_outer(tq_mjoin *j, const tq_column *cols, const uint8_t *selected, int32_t mem); /* selected: Go []bool or NULL */
+/* host chunks (all layouts) or, for 8-byte column types, device chunks (TQ_MEM_DEVICE) — per child one or the other */
+int32_t tq_mjoin_put_inner(tq_mjoin *j, const tq_column *cols, int32_t mem);
+int32_t tq_mjoin_put_outer(tq_mjoin *j, const tq_column *cols, const uint8_t *selected, int32_t mem); /* selected: HOST Go []bool or NULL */
 int32_t tq_mjoin_finish(tq_mjoin *j);   /* both children exhausted */
 int32_t tq_mjoin_next_bytes(tq_mjoin *j, int64_t max_rows, int64_t *bytes_per_col);
 int32_t tq_mjoin_next(tq_mjoin *j, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
+/* handles with a device-chunk child: the whole result at once as DEVICE columns, lent until tq_mjoin_destroy; then eof */
+int32_t tq_mjoin_next_device(tq_mjoin *j, tq_column *out_cols, int64_t *n_rows, int32_t *eof);
 int32_t tq_mjoin_destroy(tq_mjoin *j);
 
 /* ------------------------------------------------------------- radix exchange

@@ -209,3 +209,8 @@ extern "C" int32_t tq_last_error(char *buf, int32_t buf_len) {
 // "device" memory is host memory here
 extern "C" int32_t tq_init(int32_t) { return TQ_OK; }
 extern "C" int32_t tq_memcpy_d2h(void *dst, const void *src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); return TQ_OK; }
+extern "C" int32_t tq_memcpy_h2d(void *dst, const void *src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); return TQ_OK; }
+extern "C" int32_t tq_memcpy_d2d(void *dst, const void *src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); return TQ_OK; }
+extern "C" int32_t tq_memset_device(void *dst, int32_t v, size_t bytes) { if (bytes) memset(dst, v, bytes); return TQ_OK; }
+extern "C" int32_t tq_device_alloc(size_t bytes, void **out) { *out = malloc(bytes ? bytes : 1); return *out ? TQ_OK : TQ_ERR_OOM; }
+extern "C" int32_t tq_device_free(void *p) { free(p); return TQ_OK; }

@@ -15,6 +15,7 @@ import pytest
 import test_gpu_chunk_codec as TC
 import test_gpu_sort_merge as TS
 import test_gpu_string_filter as TF
+import test_gpu_zz_device_chain as TD
 from sort_cases import MERGE_CASES, SORT_CASES
 from tinysql_b200 import _lib as L
 
@@ -94,3 +95,23 @@ def test_emu_string_filter_differential_fuzz(emu, seed):
 @pytest.mark.parametrize("jt,oir", [(0, False), (1, False), (2, True), (0, True)])
 def test_emu_merge_join_other_conditions(emu, jt, oir):
     TS.test_merge_join_other_conditions(emu, jt, oir, ni=2000, no=3000)
+
+
+@pytest.mark.parametrize("n,piece", [(0, 1000), (1, 1000), (5001, 900), (5001, 100000)])
+def test_emu_sort_device_chunks(emu, n, piece):
+    TD.test_sort_device_chunks(emu, n, piece)
+
+
+def test_emu_device_chunk_rules(emu):
+    TD.test_device_chunk_rules(emu)
+
+
+def test_emu_sort_sort_merge_join_chain_on_the_device(emu):
+    """the chain of test_join_then_sort_then_merge_join_stay_on_the_device with the oracle standing in for the hash join
+    (join.cu is not part of the emulation build): its result is uploaded as the producer's device columns"""
+    import oracle_py as O
+    from tinysql_b200.chunk import DeviceColumn
+    types, b, p = TD.chain_tables(3000, 20000)
+    want_join = O.hash_join(0, True, types, b, types, p, [0], [0])
+    dj = [DeviceColumn.from_host(c) for c in want_join.cols]
+    TD.chain_after_join(emu, TD.arr_nn(dj), lambda: [d.free() for d in dj], want_join, types, b)

@@ -126,6 +126,7 @@ SYMBOLS = {
     "tq_sort_put": (_I32, [_P, _COL, _I32]), "tq_sort_eof": (_I32, [_P]),
     "tq_sort_next_bytes": (_I32, [_P, _I64, C.POINTER(_I64)]),
     "tq_sort_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
+    "tq_sort_next_device": (_I32, [_P, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
     "tq_sort_stats": (_I32, [_P, C.POINTER(_I64)]),
     "tq_sort_destroy": (_I32, [_P]),
     "tq_mjoin_create": (_I32, [C.POINTER(TQMJoinDesc), C.POINTER(_P)]),
@@ -135,6 +136,7 @@ SYMBOLS = {
     "tq_mjoin_finish": (_I32, [_P]),
     "tq_mjoin_next_bytes": (_I32, [_P, _I64, C.POINTER(_I64)]),
     "tq_mjoin_next": (_I32, [_P, _I64, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
+    "tq_mjoin_next_device": (_I32, [_P, _COL, C.POINTER(_I64), C.POINTER(_I32)]),
     "tq_mjoin_destroy": (_I32, [_P]),
     "tq_partition_device": (_I32, [_I32, _COL, C.POINTER(_I32), _I32, _I64, _I32, _COL, C.POINTER(_I64)]),
     "tq_enable_peer_access": (_I32, [_I32]),

@@ -385,6 +385,8 @@ struct RowStore {
   std::vector<StoreCol> cols;
   int64_t n = 0;
   bool uploaded = false;
+  bool host_mode = false, device_mode = false;   // a handle takes host chunks or device chunks, not both
+  int64_t dev_cap = 0;                           // device mode: rows the columns' device arrays can hold
 
   int32_t init(int n_cols, const int32_t *types) {
     cols.resize((size_t)n_cols);
@@ -409,6 +411,8 @@ struct RowStore {
       if (cols[c].kind != 2 && in[c].offsets) { set_error("unsupport column type for encode (var-len data in fixed-width column %d)", (int)c); return TQ_ERR_UNSUPPORTED_TYPE; }
       if (rows && !in[c].data && !(cols[c].kind == 2 && in[c].offsets[rows] == in[c].offsets[0])) return TQ_ERR_INVALID_ARG;
     }
+    if (device_mode) { set_error("one handle takes either host chunks or device chunks"); return TQ_ERR_STATE; }
+    host_mode = true;
     if (rows == 0) return TQ_OK;
     if (n + rows > 0xFFFFFFF0ll) { set_error("more than 2^32 rows in one sort / merge-join input"); return TQ_ERR_INVALID_ARG; }
     for (size_t c = 0; c < cols.size(); c++) {
@@ -420,16 +424,65 @@ struct RowStore {
         const size_t w = sc.kind == 1 ? 4 : 8;
         sc.h_data.insert(sc.h_data.end(), in[c].data, in[c].data + (size_t)rows * w);
       }
-      if (in[c].null_bitmap && !sc.has_bm) {   // first chunk with NULL information: everything before it was NOT NULL
-        sc.h_bm.assign(bitmap_alloc_bytes(n + rows), 0);
-        host_bitmap_append(sc.h_bm.data(), 0, nullptr, n);
-        sc.has_bm = true;
-      }
-      if (sc.has_bm) {
-        if (sc.h_bm.size() < bitmap_alloc_bytes(n + rows)) sc.h_bm.resize(std::max(bitmap_alloc_bytes(n + rows), sc.h_bm.size() * 2), 0);
-        host_bitmap_append(sc.h_bm.data(), n, in[c].null_bitmap, rows);
-      }
+      append_bitmap(sc, in[c].null_bitmap, rows);
     }
+    n += rows;
+    return TQ_OK;
+  }
+
+  // NOT-NULL bits of `rows` more rows of column sc (host bytes, bit 0 = first new row; nullptr = no NULLs)
+  void append_bitmap(StoreCol &sc, const uint8_t *bits, int64_t rows) {
+    if (bits && !sc.has_bm) {   // first chunk with NULL information: everything before it was NOT NULL
+      sc.h_bm.assign(bitmap_alloc_bytes(n + rows), 0);
+      host_bitmap_append(sc.h_bm.data(), 0, nullptr, n);
+      sc.has_bm = true;
+    }
+    if (sc.has_bm) {
+      if (sc.h_bm.size() < bitmap_alloc_bytes(n + rows)) sc.h_bm.resize(std::max(bitmap_alloc_bytes(n + rows), sc.h_bm.size() * 2), 0);
+      host_bitmap_append(sc.h_bm.data(), n, bits, rows);
+    }
+  }
+
+  // One chunk whose columns live in HBM (TQ_MEM_DEVICE: e.g. rows lent by tq_join_next_device).  8-byte columns only; the data
+  // never leaves the device: it is appended to the column's device array (grown by doubling), only the NOT-NULL bitmap — one
+  // bit per row — is read back so that chunks can be concatenated at any bit offset.  The call returns after the copies, so
+  // the caller may recycle its buffers.
+  int32_t append_device(const tq_column *in, cudaStream_t s) {
+    if (cols.empty()) return TQ_OK;
+    if (host_mode) { set_error("one handle takes either host chunks or device chunks"); return TQ_ERR_STATE; }
+    const int64_t rows = in[0].length;
+    if (rows < 0) return TQ_ERR_INVALID_ARG;
+    for (size_t c = 0; c < cols.size(); c++) {
+      if (cols[c].kind != 0 || in[c].offsets) { set_error("device chunks: 8-byte columns only (column %d)", (int)c); return TQ_ERR_UNSUPPORTED_TYPE; }
+      if (in[c].length != rows) { set_error("ragged input chunk"); return TQ_ERR_INVALID_ARG; }
+      if (rows && !in[c].data) return TQ_ERR_INVALID_ARG;
+    }
+    device_mode = true;
+    if (rows == 0) return TQ_OK;
+    if (n + rows > 0xFFFFFFF0ll) { set_error("more than 2^32 rows in one sort / merge-join input"); return TQ_ERR_INVALID_ARG; }
+    if (n + rows > dev_cap) {
+      const int64_t new_cap = std::max<int64_t>(std::max<int64_t>(n + rows, dev_cap * 2), 1 << 16);
+      for (StoreCol &sc : cols) {
+        DevBuf bigger;
+        TQ_TRY(bigger.reserve((size_t)new_cap * 8 + 16));
+        if (n) TQ_CUDA(cudaMemcpyAsync(bigger.p, sc.d_data.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        TQ_CUDA(cudaStreamSynchronize(s));   // the old array goes back to the allocator's cache: nothing may still read it
+        sc.d_data = std::move(bigger);
+      }
+      dev_cap = new_cap;
+    }
+    std::vector<uint8_t> bits;
+    for (size_t c = 0; c < cols.size(); c++) {
+      StoreCol &sc = cols[c];
+      TQ_CUDA(cudaMemcpyAsync(sc.d_data.as<uint8_t>() + (size_t)n * 8, in[c].data, (size_t)rows * 8, cudaMemcpyDeviceToDevice, s));
+      if (in[c].null_bitmap) {
+        bits.assign(bitmap_bytes(rows), 0);
+        TQ_CUDA(cudaMemcpyAsync(bits.data(), in[c].null_bitmap, bitmap_bytes(rows), cudaMemcpyDeviceToHost, s));
+        TQ_CUDA(cudaStreamSynchronize(s));
+        append_bitmap(sc, bits.data(), rows);
+      } else append_bitmap(sc, nullptr, rows);
+    }
+    TQ_CUDA(cudaStreamSynchronize(s));
     n += rows;
     return TQ_OK;
   }
@@ -438,7 +491,7 @@ struct RowStore {
     if (uploaded) return TQ_OK;
     for (StoreCol &sc : cols) {
       if (sc.kind == 2) TQ_TRY(upload_store(sc.h_var, sc.store, s));
-      else {
+      else if (!device_mode) {   // device mode: the data is in d_data already
         TQ_TRY(sc.d_data.reserve(sc.h_data.size() + 16));
         if (!sc.h_data.empty()) TQ_CUDA(cudaMemcpyAsync(sc.d_data.p, sc.h_data.data(), sc.h_data.size(), cudaMemcpyHostToDevice, s));
       }
@@ -529,6 +582,66 @@ int32_t gather_columns(const RowStore &st, const uint32_t *d_rows, int64_t m, co
     TQ_CUDA(cudaStreamSynchronize(s));   // the scratch buffers are reused by the next column
   }
   return TQ_OK;
+}
+
+// The same result kept in HBM (tq_sort_next_device / tq_mjoin_next_device): one device array per column, lent to the caller
+struct ResultDev {
+  std::vector<DevBuf> data, bm;
+  std::vector<VarOut> var;      // var-len columns: offsets + bytes (indexed like data)
+  std::vector<int> kind;
+  DevBuf rowid64, lens, scan;
+  bool ready = false, lent = false;
+};
+
+int32_t gather_columns_device(const RowStore &st, const uint32_t *d_rows, int64_t m, const uint64_t *dflt_bits, const uint8_t *dflt_nn, ResultDev &rd, cudaStream_t s) {
+  for (size_t c = 0; c < st.cols.size(); c++) {
+    const StoreCol &sc = st.cols[c];
+    rd.data.emplace_back();
+    rd.bm.emplace_back();
+    rd.var.emplace_back();
+    rd.kind.push_back(sc.kind);
+    DevBuf &od = rd.data.back(), &ob = rd.bm.back();
+    VarOut &ov = rd.var.back();
+    const int64_t words = (m + 31) >> 5;
+    const int nn_dflt = (sc.kind == 0 && dflt_nn) ? dflt_nn[c] : 0;
+    TQ_TRY(ob.reserve(bitmap_alloc_bytes(m)));
+    TQ_CUDA(cudaMemsetAsync(ob.p, 0, bitmap_alloc_bytes(m), s));   // the pad words consumers of 64-row groups may touch
+    TQ_TRY(od.reserve((size_t)(m ? m : 1) * 8 + 16));
+    if (m == 0) continue;
+    TQ_LAUNCH(k_gather_bm, grid_for(words * 32), 256, 0, s, sc.bm(), d_rows, m, nn_dflt, ob.as<uint32_t>(), words);
+    count_launch();
+    TQ_TRY(check_launch("k_gather_bm"));
+    if (sc.kind == 0) {
+      TQ_LAUNCH(k_gather_u64, grid_for(m), 256, 0, s, sc.d_data.as<uint64_t>(), d_rows, m, (dflt_bits && nn_dflt) ? dflt_bits[c] : 0ull, od.as<uint64_t>());
+      count_launch();
+      TQ_TRY(check_launch("k_gather_u64"));
+    } else if (sc.kind == 1) {
+      TQ_LAUNCH(k_gather_u32, grid_for(m), 256, 0, s, sc.d_data.as<uint32_t>(), d_rows, m, od.as<uint32_t>());
+      count_launch();
+      TQ_TRY(check_launch("k_gather_u32"));
+    } else {
+      TQ_TRY(rd.rowid64.reserve((size_t)m * 8));
+      TQ_LAUNCH(k_rows_to_u64, grid_for(m), 256, 0, s, d_rows, m, rd.rowid64.as<uint64_t>());
+      count_launch();
+      TQ_TRY(check_launch("k_rows_to_u64"));
+      TQ_TRY(gather_cells(sc.store, rd.rowid64.as<uint64_t>(), ob.as<uint32_t>(), m, ov, rd.lens, rd.scan, s));
+    }
+  }
+  TQ_CUDA(cudaStreamSynchronize(s));
+  rd.ready = true;
+  return TQ_OK;
+}
+
+// lend the device result: everything in one batch, then eof
+void result_lend(ResultDev &rd, int64_t m, int first_col, int n_cols, tq_column *out) {
+  for (int c = 0; c < n_cols; c++) {
+    const size_t i = (size_t)(first_col + c);
+    out[c].length = m;
+    out[c].null_bitmap = rd.bm[i].as<uint8_t>();
+    out[c].offsets = nullptr;
+    out[c].data = rd.data[i].as<uint8_t>();
+    if (rd.kind[i] == 2) { out[c].offsets = rd.var[i].off.as<int64_t>(); out[c].data = rd.var[i].bytes.as<uint8_t>(); }
+  }
 }
 
 int32_t result_next_bytes(const ResultHost &res, int64_t max_rows, int64_t *bytes_per_col) {
@@ -652,6 +765,9 @@ struct tq_sort {
   int64_t limit_offset = 0, limit_count = -1;
   bool eof = false;
   ResultHost res;
+  bool host_ready = false;     // res holds the rows (device-chunk handles materialise the host copy only if tq_sort_next asks)
+  DevBuf keep_rows;            // device-chunk handles: row ids of the result window, kept for the lazy gathers
+  ResultDev dev;
   int64_t launches = 0, passes = 0, sort_ns = 0;   // tq_sort_stats
 };
 
@@ -666,6 +782,9 @@ struct tq_mjoin {
   std::vector<tq_join_cond> conds;   // OtherConditions (tq_mjoin_set_other_conditions)
   bool finished = false;
   ResultHost res;
+  bool host_ready = false;
+  DevBuf keep_o, keep_i;             // device-chunk handles: (outer row, inner row) of every result row
+  ResultDev dev;
 };
 
 extern "C" {
@@ -694,8 +813,14 @@ int32_t tq_sort_create(const tq_sort_desc *d, tq_sort **out) {
 
 int32_t tq_sort_put(tq_sort *h, const tq_column *cols, int32_t mem) {
   if (!h || !cols) return TQ_ERR_INVALID_ARG;
-  if (mem != TQ_MEM_HOST) { set_error("tq_sort_put takes host chunks"); return TQ_ERR_INVALID_ARG; }
   if (h->eof) { set_error("put after eof"); return TQ_ERR_STATE; }
+  if (mem == TQ_MEM_DEVICE) {
+    TQ_TRY(ensure_init());
+    Runtime &r = rt();
+    std::lock_guard<std::recursive_mutex> lk(r.mu);
+    return h->rows.append_device(cols, r.compute);
+  }
+  if (mem != TQ_MEM_HOST) return TQ_ERR_INVALID_ARG;
   return h->rows.append(cols);
 }
 
@@ -716,6 +841,7 @@ int32_t tq_sort_eof(tq_sort *h) {
   h->res.n = m;
   if (n == 0 || m == 0) {
     GatherScratch g;
+    h->host_ready = true;
     return gather_columns(h->rows, nullptr, 0, nullptr, nullptr, h->res, g, s);
   }
   TQ_TRY(h->rows.upload(s));
@@ -738,22 +864,61 @@ int32_t tq_sort_eof(tq_sort *h) {
   cudaEventDestroy(ev1);
   TQ_TRY(st);
   h->passes = b.passes;
-  GatherScratch g;
-  TQ_TRY(gather_columns(h->rows, b.perm[b.cur].as<uint32_t>() + lo, m, nullptr, nullptr, h->res, g, s));
+  if (h->rows.device_mode) {
+    // device chunks in: the result stays in HBM until somebody asks for it (tq_sort_next_device lends it, tq_sort_next copies it)
+    TQ_TRY(h->keep_rows.reserve((size_t)m * 4 + 16));
+    TQ_CUDA(cudaMemcpyAsync(h->keep_rows.p, b.perm[b.cur].as<uint32_t>() + lo, (size_t)m * 4, cudaMemcpyDeviceToDevice, s));
+    TQ_CUDA(cudaStreamSynchronize(s));
+  } else {
+    GatherScratch g;
+    TQ_TRY(gather_columns(h->rows, b.perm[b.cur].as<uint32_t>() + lo, m, nullptr, nullptr, h->res, g, s));
+    h->host_ready = true;
+  }
   h->launches = r.launches.load() - launches0;
+  return TQ_OK;
+}
+
+// device-chunk handles: the host copy of the result is made on the first tq_sort_next / tq_sort_next_bytes
+static int32_t sort_host_result(tq_sort *h) {
+  if (h->host_ready) return TQ_OK;
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  GatherScratch g;
+  TQ_TRY(gather_columns(h->rows, h->keep_rows.as<uint32_t>(), h->res.n, nullptr, nullptr, h->res, g, r.compute));
+  h->host_ready = true;
   return TQ_OK;
 }
 
 int32_t tq_sort_next_bytes(tq_sort *h, int64_t max_rows, int64_t *bytes_per_col) {
   if (!h || !bytes_per_col || max_rows <= 0) return TQ_ERR_INVALID_ARG;
   if (!h->eof) { set_error("next before eof"); return TQ_ERR_STATE; }
+  TQ_TRY(sort_host_result(h));
   return result_next_bytes(h->res, max_rows, bytes_per_col);
 }
 
 int32_t tq_sort_next(tq_sort *h, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof) {
   if (!h || !out_cols || !n_rows || !eof || max_rows <= 0) return TQ_ERR_INVALID_ARG;
   if (!h->eof) { set_error("next before eof"); return TQ_ERR_STATE; }
+  TQ_TRY(sort_host_result(h));
   return result_next(h->res, max_rows, out_cols, n_rows, eof);
+}
+
+// The whole result (the TopN window) as DEVICE columns, lent until the handle is destroyed: first call = all rows, then eof.
+int32_t tq_sort_next_device(tq_sort *h, tq_column *out_cols, int64_t *n_rows, int32_t *eof) {
+  if (!h || !out_cols || !n_rows || !eof) return TQ_ERR_INVALID_ARG;
+  if (!h->eof) { set_error("next before eof"); return TQ_ERR_STATE; }
+  TQ_TRY(ensure_init());
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  *n_rows = 0;
+  *eof = 0;
+  if (h->dev.lent || h->res.n == 0) { *eof = 1; return TQ_OK; }
+  if (!h->rows.device_mode) { set_error("tq_sort_next_device needs a handle fed with device chunks"); return TQ_ERR_STATE; }
+  if (!h->dev.ready) TQ_TRY(gather_columns_device(h->rows, h->keep_rows.as<uint32_t>(), h->res.n, nullptr, nullptr, h->dev, r.compute));
+  result_lend(h->dev, h->res.n, 0, (int)h->rows.cols.size(), out_cols);
+  h->dev.lent = true;
+  *n_rows = h->res.n;
+  return TQ_OK;
 }
 
 int32_t tq_sort_stats(tq_sort *h, int64_t *stats4) {
@@ -838,17 +1003,28 @@ int32_t tq_mjoin_set_other_conditions(tq_mjoin *h, int32_t n_conds, const tq_joi
 
 int32_t tq_mjoin_put_inner(tq_mjoin *h, const tq_column *cols, int32_t mem) {
   if (!h || !cols) return TQ_ERR_INVALID_ARG;
-  if (mem != TQ_MEM_HOST) { set_error("tq_mjoin_put_inner takes host chunks"); return TQ_ERR_INVALID_ARG; }
   if (h->finished) { set_error("put after finish"); return TQ_ERR_STATE; }
+  if (mem == TQ_MEM_DEVICE) {
+    TQ_TRY(ensure_init());
+    Runtime &r = rt();
+    std::lock_guard<std::recursive_mutex> lk(r.mu);
+    return h->inner.append_device(cols, r.compute);
+  }
+  if (mem != TQ_MEM_HOST) return TQ_ERR_INVALID_ARG;
   return h->inner.append(cols);
 }
 
 int32_t tq_mjoin_put_outer(tq_mjoin *h, const tq_column *cols, const uint8_t *selected, int32_t mem) {
   if (!h || !cols) return TQ_ERR_INVALID_ARG;
-  if (mem != TQ_MEM_HOST) { set_error("tq_mjoin_put_outer takes host chunks"); return TQ_ERR_INVALID_ARG; }
   if (h->finished) { set_error("put after finish"); return TQ_ERR_STATE; }
+  if (mem != TQ_MEM_HOST && mem != TQ_MEM_DEVICE) return TQ_ERR_INVALID_ARG;
   const int64_t before = h->outer.n;
-  TQ_TRY(h->outer.append(cols));
+  if (mem == TQ_MEM_DEVICE) {   // `selected` stays a host []bool either way
+    TQ_TRY(ensure_init());
+    Runtime &r = rt();
+    std::lock_guard<std::recursive_mutex> lk(r.mu);
+    TQ_TRY(h->outer.append_device(cols, r.compute));
+  } else TQ_TRY(h->outer.append(cols));
   const int64_t rows = h->outer.n - before;
   if (selected && !h->has_selected) { h->selected.assign((size_t)before, 1); h->has_selected = true; }
   if (h->has_selected) {
@@ -875,6 +1051,7 @@ int32_t tq_mjoin_finish(tq_mjoin *h) {
   auto dflt_n = [&](RowStore *st) { return (st == &h->inner && !h->dflt_nn.empty()) ? h->dflt_nn.data() : nullptr; };
   if (no == 0) {
     h->res.n = 0;
+    h->host_ready = true;
     TQ_TRY(gather_columns(*first, nullptr, 0, nullptr, nullptr, h->res, g, s));
     return gather_columns(*second, nullptr, 0, nullptr, nullptr, h->res, g, s);
   }
@@ -1046,22 +1223,86 @@ int32_t tq_mjoin_finish(tq_mjoin *h) {
     m_out = m2;
     h->res.n = m2;
   }
+  if (h->inner.device_mode || h->outer.device_mode) {
+    // device chunks in: keep the (outer row, inner row) lists; the columns are gathered when a next call asks for them
+    TQ_TRY(h->keep_o.reserve((size_t)(m_out ? m_out : 1) * 4));
+    TQ_TRY(h->keep_i.reserve((size_t)(m_out ? m_out : 1) * 4));
+    if (m_out) {
+      TQ_CUDA(cudaMemcpyAsync(h->keep_o.p, rows_o, (size_t)m_out * 4, cudaMemcpyDeviceToDevice, s));
+      TQ_CUDA(cudaMemcpyAsync(h->keep_i.p, rows_i, (size_t)m_out * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    TQ_CUDA(cudaStreamSynchronize(s));
+    h->res.n = m_out;
+    return TQ_OK;
+  }
   // output schema = left child columns ++ right child columns (executor/builder.go: the joiner's makeJoinRowToChunk)
   TQ_TRY(gather_columns(*first, first == &h->inner ? rows_i : rows_o, m_out, dflt_b(first), dflt_n(first), h->res, g, s));
   TQ_TRY(gather_columns(*second, second == &h->inner ? rows_i : rows_o, m_out, dflt_b(second), dflt_n(second), h->res, g, s));
+  h->host_ready = true;
   return TQ_OK;
 }
+
+}  // extern "C"
+
+// gathers of a device-chunk merge join: left child columns ++ right child columns from the kept row lists
+template <typename Gather>
+static int32_t mjoin_gather(tq_mjoin *h, Gather &&gather) {
+  RowStore *first = h->outer_is_right ? &h->inner : &h->outer, *second = h->outer_is_right ? &h->outer : &h->inner;
+  for (RowStore *st : {first, second}) {
+    const bool is_inner = st == &h->inner;
+    const uint64_t *db = (is_inner && !h->dflt_nn.empty()) ? h->dflt_bits.data() : nullptr;
+    const uint8_t *dn = (is_inner && !h->dflt_nn.empty()) ? h->dflt_nn.data() : nullptr;
+    TQ_TRY(gather(*st, is_inner ? h->keep_i.as<uint32_t>() : h->keep_o.as<uint32_t>(), db, dn));
+  }
+  return TQ_OK;
+}
+static int32_t mjoin_host_result(tq_mjoin *h) {
+  if (h->host_ready) return TQ_OK;
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  GatherScratch g;
+  TQ_TRY(mjoin_gather(h, [&](const RowStore &st, const uint32_t *rows, const uint64_t *db, const uint8_t *dn) {
+    return gather_columns(st, rows, h->res.n, db, dn, h->res, g, r.compute);
+  }));
+  h->host_ready = true;
+  return TQ_OK;
+}
+
+extern "C" {
 
 int32_t tq_mjoin_next_bytes(tq_mjoin *h, int64_t max_rows, int64_t *bytes_per_col) {
   if (!h || !bytes_per_col || max_rows <= 0) return TQ_ERR_INVALID_ARG;
   if (!h->finished) { set_error("next before finish"); return TQ_ERR_STATE; }
+  TQ_TRY(mjoin_host_result(h));
   return result_next_bytes(h->res, max_rows, bytes_per_col);
 }
 
 int32_t tq_mjoin_next(tq_mjoin *h, int64_t max_rows, tq_column *out_cols, int64_t *n_rows, int32_t *eof) {
   if (!h || !out_cols || !n_rows || !eof || max_rows <= 0) return TQ_ERR_INVALID_ARG;
   if (!h->finished) { set_error("next before finish"); return TQ_ERR_STATE; }
+  TQ_TRY(mjoin_host_result(h));
   return result_next(h->res, max_rows, out_cols, n_rows, eof);
+}
+
+// The whole join result as DEVICE columns, lent until the handle is destroyed: first call = all rows, then eof.
+int32_t tq_mjoin_next_device(tq_mjoin *h, tq_column *out_cols, int64_t *n_rows, int32_t *eof) {
+  if (!h || !out_cols || !n_rows || !eof) return TQ_ERR_INVALID_ARG;
+  if (!h->finished) { set_error("next before finish"); return TQ_ERR_STATE; }
+  TQ_TRY(ensure_init());
+  Runtime &r = rt();
+  std::lock_guard<std::recursive_mutex> lk(r.mu);
+  *n_rows = 0;
+  *eof = 0;
+  if (h->dev.lent || h->res.n == 0) { *eof = 1; return TQ_OK; }
+  if (!h->inner.device_mode && !h->outer.device_mode) { set_error("tq_mjoin_next_device needs a handle fed with device chunks"); return TQ_ERR_STATE; }
+  if (!h->dev.ready)
+    TQ_TRY(mjoin_gather(h, [&](const RowStore &st, const uint32_t *rows, const uint64_t *db, const uint8_t *dn) {
+      return gather_columns_device(st, rows, h->res.n, db, dn, h->dev, r.compute);
+    }));
+  result_lend(h->dev, h->res.n, 0, (int)(h->inner.cols.size() + h->outer.cols.size()), out_cols);
+  h->dev.lent = true;
+  *n_rows = h->res.n;
+  return TQ_OK;
 }
 
 int32_t tq_mjoin_destroy(tq_mjoin *h) {
